@@ -1,0 +1,89 @@
+"""The oracle restatement vs the fixtures produced by the live reference
+(oracle/make_golden.py).  CPU only; no /root/reference needed."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_case, load_golden, relerr
+
+from oracle import oracle_net, oracle_ops
+
+TINY = ["tiny_simp", "tiny_full", "tiny_crf", "tiny_d", "tiny_pre", "tiny_win"]
+
+
+def _sub(t, *strides):
+    t = torch.as_tensor(t)
+    sl = [slice(None)] * (t.dim() - len(strides)) + [slice(None, None, s) for s in strides]
+    return t[tuple(sl)].numpy()
+
+
+def check_against_golden(o, fx, tol, big):
+    """Shared by the CPU oracle test and the GPU parity tests.  ``o`` holds NCHW tensors."""
+    assert tuple(o["image_batch"].shape) == tuple(fx["image_shape"])
+    s = (8, 8) if big else (2, 2)
+    errs = {}
+    errs["image"] = relerr(_sub(o["image_batch"], *s), fx["image_sub"])
+    assert np.array_equal(np.concatenate(o["coors_t"], 0), fx["coors_t"])            # bit-exact
+    assert np.array_equal(np.asarray(o["index_map"]), fx["index_map"])                # bit-exact
+    errs["seg_emb"] = relerr(np.concatenate([np.asarray(e) for e in o["seg_emb"]], 0)[:, ::(8 if big else 2)], fx["seg_emb"])
+    p = (4, 4) if big else (2, 2)
+    errs["p_fuse"] = relerr(_sub(o["p_fuse"], *p)[:, ::4], fx["p_fuse_sub"])
+    errs["roi"] = relerr(torch.as_tensor(o["roi"])[:, ::(8 if big else 4)].numpy(), fx["roi_sub"])
+    errs["late"] = relerr(torch.as_tensor(o["late"])[:, ::4].numpy(), fx["late_sub"])
+    if "logits" in fx:
+        errs["logits"] = relerr(o["logits"], fx["logits"])
+    if fx["meta"]["classifier_mode"] == "crf":
+        assert np.array_equal(np.asarray(o["pred_label"]), fx["pred_label"])
+    else:
+        errs["pred_label"] = relerr(o["pred_label"], fx["pred_label"])
+        if fx["meta"]["classifier_mode"] == "simp":
+            assert np.array_equal(np.asarray(o["pred_label"]).argmax(1), fx["pred_label"].argmax(1))
+    if "pred_mask" in o:
+        errs["pred_mask"] = relerr(_sub(o["pred_mask"], *s), fx["pred_mask_sub"])
+        errs["pred_ss"] = relerr(_sub(o["pred_ss"], *s), fx["pred_ss_sub"])
+        pn = np.asarray(o["pos_neg_labels"])
+        assert [int((pn == v).sum()) for v in (0, 1, 2)] == list(fx["pos_neg_sum"])
+        assert np.array_equal(pn[..., ::4, ::4].astype(np.int8), fx["pos_neg_sub"])
+        if "class_sub" in fx:
+            assert np.array_equal(np.asarray(o["class_labels"])[..., ::4, ::4].astype(np.int8), fx["class_sub"])
+    assert np.array_equal(np.asarray(o["gt_label"]), fx["gt_label"])
+    bad = {k: v for k, v in errs.items() if v > tol.get(k, tol["default"])}
+    assert not bad, f"deviates from the reference fixture: {bad} (all: {errs})"
+    return errs
+
+
+@pytest.mark.parametrize("name", TINY + ["cfg1"])
+def test_oracle_matches_reference_fixture(name, bert_dir, tmp_path, monkeypatch):
+    fx = load_golden(name)
+    monkeypatch.chdir(tmp_path)
+    cfg, kw, net, batch = build_case(fx["meta"])
+    ocfg = oracle_net.OracleConfig(backbone=cfg.backbone, classifier_mode=cfg.classifier_mode,
+                                   num_classes=cfg.num_classes, min_size=kw["test_image_min_size"],
+                                   max_size=kw["image_max_size"])
+    o = oracle_net.forward(net.state_dict(), ocfg, *batch)
+    check_against_golden(o, fx, {"default": 2e-5}, big=name.startswith("cfg"))
+
+
+def test_known_answers_from_survey():
+    """SURVEY.md Appendix A known-answer vectors (verified on the live reference)."""
+    # A.1 coord resize with the axis swap: 333x777 image, min 512 / max 800
+    sc = oracle_ops.resize_scale(333, 777, 512, 800)
+    nh, nw = oracle_ops.resized_shape(333, 777, sc)
+    got = oracle_ops.resize_coords(np.array([[100, 50, 300, 150]]), (333, 777), (nh, nw))
+    assert got.tolist() == [[102, 51, 308, 154]]
+    # A.4 window counts
+    for L, n in [(509, 1), (510, 2), (512, 2), (1020, 3), (1024, 3)]:
+        assert len(oracle_ops.bert_windows(np.ones((1, L), np.int64), np.ones((1, L), np.int64))) == n
+    # A.6 run-length mean
+    tok = np.array([[10.], [20.], [30.], [40.], [50.]], np.float32)
+    assert oracle_ops.segment_aggregate(tok, np.array([0, 0, 1, 2, 2])).ravel().tolist() == [15., 30., 45.]
+    assert oracle_ops.segment_aggregate(tok, np.array([0, 0, 1, 2, 2]), "first").ravel().tolist() == [10., 30., 40.]
+    # A.7 scatter KAT: stride 8, 32x48 image
+    boxes = [np.array([[0, 0, 24, 16], [16, 8, 40, 24], [7, 7, 9, 9]], np.int32)]
+    idx = oracle_ops.box_index_map(boxes, 32, 48, 8)
+    grid = oracle_ops.scatter_grid([np.array([[15.], [30.], [45.]], np.float32)], idx)[0, 0]
+    assert grid.tolist() == [[45, 15, 15, 0, 0, 0], [15, 15, 30, 30, 30, 0], [0, 0, 30, 30, 30, 0], [0] * 6]
+    # A.12 ROIAlign sampling grids
+    g = [oracle_ops.roi_geometry(np.array(b, np.float32), 0.25, 7)[4:] for b in
+         ([0, 0, 40, 40], [8, 8, 8, 8], [0, 0, 75, 110], [0, 0, 28, 56])]
+    assert g == [(2, 2), (1, 1), (3, 4), (1, 2)]
