@@ -1,0 +1,160 @@
+/*
+ * vbg.h -- C ABI of libvbg_sm100a.so: the ViBERTgrid joint-forward hot path as
+ * hand-written CUDA for NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  The reference is pure Python
+ * and reaches its arithmetic through torch / torchvision / transformers; each
+ * entry point below names the reference call site it replaces (paths relative
+ * to the reference repository root).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative VBG_E* code; it never
+ *     throws, exits or synchronises the device.  vbg_last_error() returns the
+ *     calling thread's last message.
+ *   - all pointers are DEVICE pointers unless the name starts with h_.
+ *     The caller owns every buffer (including workspaces); the library
+ *     allocates nothing persistent.
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); the legacy
+ *     default stream is never used implicitly.  Functions are re-entrant.
+ *   - activations are fp32, channels-last (NHWC); weights of convolutions are
+ *     [Cout, kh, kw, Cin] (see vbg_repack_oihw_to_ohwi); linear weights keep
+ *     PyTorch's [out, in] layout.
+ *   - "seg_off" is an int32 [B+1] exclusive prefix sum of segments per sample,
+ *     built by the host from tensor SHAPES (no device sync).
+ */
+#ifndef VBG_H_
+#define VBG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBG_VERSION 100 /* 0.1.0 */
+
+enum { VBG_OK = 0, VBG_EINVAL = -1, VBG_ECUDA = -2, VBG_EUNSUPPORTED = -3, VBG_EWORKSPACE = -4 };
+
+/* arithmetic path of the dense contractions */
+enum { VBG_PREC_FP32 = 0,  /* CUDA-core FFMA, fp32 operands and accumulate            */
+       VBG_PREC_TF32 = 1   /* tcgen05.mma kind::tf32, TMA-fed, TMEM fp32 accumulators  */ };
+
+enum { VBG_ACT_NONE = 0, VBG_ACT_RELU = 1, VBG_ACT_GELU = 2 /* erf form, as HF "gelu" */ };
+enum { VBG_RES_NONE = 0, VBG_RES_SAME = 1, /* residual[m*ldr + n]                                  */
+       VBG_RES_UP2 = 2   /* residual is NHWC [B, out_h/2, out_w/2, N]: nearest x2 upsample-add   */ };
+enum { VBG_AGG_MEAN = 0, VBG_AGG_FIRST = 1 };
+
+typedef void* vbg_stream_t;
+
+#if defined(__GNUC__)
+#define VBG_API __attribute__((visibility("default")))
+#else
+#define VBG_API
+#endif
+
+/* Fused epilogue of vbg_gemm / vbg_conv2d:  y = act( acc * scale[n] + shift[n] + residual ) */
+typedef struct vbg_epilogue {
+  const float* scale;    /* [N] or NULL (= 1)  -- folded BatchNorm gamma/sqrt(var+eps)          */
+  const float* shift;    /* [N] or NULL (= 0)  -- bias, or folded BatchNorm beta - mean*scale   */
+  const float* residual; /* or NULL */
+  int res_mode;          /* VBG_RES_* */
+  int ldr;               /* row stride of residual for VBG_RES_SAME */
+  int out_h, out_w;      /* output spatial dims, needed by VBG_RES_UP2 for vbg_gemm            */
+  int act;               /* VBG_ACT_* */
+} vbg_epilogue_t;
+
+VBG_API int vbg_version(void);
+/* copies the calling thread's last error text into buf (NUL terminated); returns its length */
+VBG_API int vbg_last_error(char* buf, size_t n);
+/* 1 if the tcgen05/TMA path can run on the current device + driver, else 0 */
+VBG_API int vbg_tc_available(void);
+
+/* ---- a1: GeneralizedViBERTgridTransform (pipeline/transform.py:104-171, 225-312) ---------- */
+/* One source image [3,h,w] (CHW, [0,1]) -> normalised, bilinearly resized to (oh,ow)
+ * (align_corners=False, scale = in/out as F.interpolate(recompute_scale_factor=True) uses),
+ * written into sample b of the zero-initialised NHWC batch [B,H,W,3].                          */
+VBG_API int vbg_normalize_resize_pad(const float* img_chw, int h, int w, float* batch_nhwc, int b, int H, int W,
+                             int oh, int ow, const float* h_mean3, const float* h_std3, vbg_stream_t stream);
+/* coords int64 [K,4] (l,t,r,b) -> int32 [K,4]: cols 0,2 *= ratio[b][0] (height ratio), cols 1,3 *= ratio[b][1]
+ * (width ratio) in fp32, then truncation (pipeline/transform.py:163-169, axis swap included).    */
+VBG_API int vbg_resize_coords(const int64_t* coors, const int32_t* seg_off, const float* ratios /*[B,2]*/, int B, int K,
+                      int32_t* out, vbg_stream_t stream);
+
+/* ---- a2: windowed BERT encoder (model/BERTgrid_generator.py:81-146 -> HF BertModel) -------- */
+/* Packs the real rows of every 510-token window: [CLS] tokens [SEP].  seq_tab int32 [nseq,4] =
+ * (sample, first corpus column, n real tokens, position id of [SEP]); cu int32 [nseq+1] row offsets. */
+VBG_API int vbg_bert_assemble(const int64_t* corpus, int L, const int32_t* seq_tab, const int32_t* cu, int nseq, int R,
+                      int32_t* ids, int32_t* pos, vbg_stream_t stream);
+/* x[r] = LayerNorm(word[ids[r]] + position[pos[r]] + token_type[0]) */
+VBG_API int vbg_embed_ln(const int32_t* ids, const int32_t* pos, const float* word, const float* position,
+                 const float* type0, const float* gamma, const float* beta, float eps, int R, int hidden,
+                 int vocab, int max_pos, float* out, vbg_stream_t stream);
+VBG_API int vbg_layernorm(const float* x, const float* gamma, const float* beta, float eps, int R, int hidden, float* out,
+                  vbg_stream_t stream);
+/* softmax(Q K^T / sqrt(d)) V per sequence and head over packed qkv [R, 3*heads*d] (q | k | v). */
+VBG_API int vbg_attention_fwd(const float* qkv, const int32_t* cu, int nseq, int max_len, int heads, int head_dim,
+                      float* out, int precision, vbg_stream_t stream);
+
+/* ---- a3: token -> segment aggregation (model/BERTgrid_generator.py:148-189) ----------------- */
+/* Run starts of consecutive-equal ids inside each sample.  status[0] |= 1 if #runs != K.        */
+VBG_API int vbg_segment_starts(const int32_t* seg_ids, const int32_t* tok_off, int B, int n_tok, int K,
+                       int32_t* seg_start /*[K+1]*/, int32_t* status, vbg_stream_t stream);
+/* out[k] = mean (sequential fp32 sum, one divide) or first of hidden[tok_row[t]], t in run k.   */
+VBG_API int vbg_segment_reduce(const float* hidden, const int32_t* tok_row, const int32_t* seg_start, int K, int C,
+                       int mode, float* out, vbg_stream_t stream);
+
+/* ---- a4 / a6: box -> index map, BERTgrid scatter, label painting ---------------------------- */
+/* idx[b,y,x] = max{ s : cell in [int(t/stride):int(b/stride)) x [int(l/stride):int(r/stride)) } or -1,
+ * Python slice semantics (model/BERTgrid_generator.py:230-243; "last writer wins").            */
+VBG_API int vbg_box_index_map(const int32_t* boxes, const int32_t* seg_off, int B, int stride, int Hg, int Wg,
+                      int32_t* idx, vbg_stream_t stream);
+/* grid[b,y,x,:] = idx<0 ? 0 : seg_emb[seg_off[b]+idx]   (NHWC BERTgrid, C % 4 == 0)             */
+VBG_API int vbg_grid_scatter(const float* seg_emb, const int32_t* idx, const int32_t* seg_off, int B, int cells, int C,
+                     float* grid, vbg_stream_t stream);
+/* full-resolution labels (model/semantic_segmentation_head.py:199-214): pos_neg = 1 if cls>0 else 2. */
+VBG_API int vbg_label_paint(const int32_t* boxes, const int32_t* seg_off, const int32_t* seg_cls, int B, int H, int W,
+                    int64_t* pos_neg, int64_t* cls, vbg_stream_t stream);
+
+/* ---- a5 / a6 / a8 / a9: dense contractions ------------------------------------------------- */
+/* C[M,N] = epilogue( [A | A2][M,K] * W[N,K]^T ).  A supplies columns [0,K1), A2 (may be NULL when
+ * K1 == K) columns [K1,K): the torch.cat-free form of ResNetFPN_ViBERTgrid.py:317-318 and
+ * field_type_classification_head.py:185-188.                                                     */
+VBG_API int vbg_gemm(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int ldw, float* C, int ldc,
+             int M, int N, int K, const vbg_epilogue_t* ep, int precision, vbg_stream_t stream);
+/* NHWC convolution as implicit GEMM: y[B,Ho,Wo,Cout] = epilogue(conv(x[B,H,W,Cin], w[Cout,kh,kw,Cin])) */
+VBG_API int vbg_conv2d(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int kh, int kw, int stride,
+               int pad, float* y, const vbg_epilogue_t* ep, int precision, vbg_stream_t stream);
+VBG_API int vbg_maxpool3x3s2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream);
+VBG_API int vbg_avgpool2x2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream);
+/* eval-mode BatchNorm folded to y = x*scale + shift */
+VBG_API int vbg_bn_fold(const float* weight, const float* bias, const float* mean, const float* var, float eps, int C,
+                float* scale, float* shift, vbg_stream_t stream);
+/* PyTorch conv weight [O,I,H,W] -> [O,H,W,I]; also permutes the ROI FC weight [1024,(C,7,7)] -> [1024,(7,7,C)] */
+VBG_API int vbg_repack_oihw_to_ohwi(const float* w, int O, int I, int H, int W, float* out, vbg_stream_t stream);
+
+/* ---- a7: GridROIAlign (model/grid_roi_align.py:37-41,81 -> torchvision roi_align, aligned=False,
+ *          sampling_ratio=-1) over NHWC features; boxes are the int32 transformed coords.         */
+VBG_API int vbg_roi_align_fwd(const float* feat, int B, int Hf, int Wf, int C, const int32_t* boxes, const int32_t* seg_off,
+                      int K, float spatial_scale, int P, float* out /*[K,P,P,C]*/,
+                      int32_t* sample_grid /*[K,2] (gh,gw) or NULL*/, vbg_stream_t stream);
+
+/* ---- heads / outputs ---------------------------------------------------------------------- */
+VBG_API int vbg_softmax_rows(const float* x, int R, int C, float* y, vbg_stream_t stream);
+/* sigmoid cascade of the "full" head (field_type_classification_head.py:312-332) */
+VBG_API int vbg_full_head_scores(const float* pos_neg, const float* cls /*[R,C-1]*/, int R, int C, float* out /*[R,C]*/,
+                         vbg_stream_t stream);
+/* NHWC [B,h,w,Ct] --nearest x up--> NCHW out1 [B,c_split,h*up,w*up], out2 [B,Ct-c_split,h*up,w*up]
+ * (semantic_segmentation_head.py:73-78 with the 1x1 convs commuted before the upsample)          */
+VBG_API int vbg_upsample_split_nchw(const float* x, int B, int h, int w, int Ct, int up, int c_split, float* out1,
+                            float* out2, vbg_stream_t stream);
+VBG_API int vbg_nhwc_to_nchw(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream);
+/* Viterbi decode per sample (model/crf.py:96-146); tags written as float like the reference returns them */
+VBG_API int vbg_crf_viterbi(const float* feats /*[K,T]*/, const float* trans /*[T,T] to<-from*/, const int32_t* seg_off, int B,
+                    int K, int T, float* tags /*[K]*/, float* scores /*[B]*/, void* workspace /*>= K*T bytes*/,
+                    size_t ws_bytes, vbg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBG_H_ */

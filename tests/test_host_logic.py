@@ -1,0 +1,74 @@
+"""Host-side logic (no GPU): batch planning vs the oracle, and the forward
+engine's orchestration with the kernels replaced by test-only stand-ins
+(tests/mock_ops.py) against the reference fixtures."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import build_case, load_golden
+from test_oracle_golden import TINY, check_against_golden
+
+import mock_ops
+from oracle import oracle_ops
+from vibertgrid_pytorch_b200 import engine as engine_mod
+from vibertgrid_pytorch_b200 import plan as plan_mod
+
+
+def test_resize_geometry_matches_oracle():
+    for h, w, mn, mx in [(333, 777, 512, 800), (512, 512, 512, 800), (85, 107, 96, 128), (1000, 300, 704, 800), (40, 900, 320, 800)]:
+        sc = oracle_ops.resize_scale(h, w, mn, mx)
+        assert plan_mod.resize_geometry(h, w, mn, mx) == oracle_ops.resized_shape(h, w, sc)
+
+
+@pytest.mark.parametrize("L,ntoks", [(512, [512, 300, 2]), (510, [510, 7]), (40, [40, 25]), (1024, [1024, 511, 1020]), (515, [515, 510, 3])])
+def test_plan_windows_match_reference_windows(L, ntoks):
+    B = len(ntoks)
+    rng = np.random.default_rng(0)
+    corpus = np.zeros((B, L), np.int64)
+    for b, n in enumerate(ntoks):
+        corpus[b, :n] = rng.integers(1000, 2000, n)
+    mask = (corpus != 0).astype(np.int64)
+    pl = plan_mod.plan_batch([(64, 64)] * B, ntoks, [1] * B, L, 64, 64)
+    seq_tab, cu = pl.view("seq_tab").reshape(-1, 4), pl.view("cu")
+    ids, pos = mock_ops.bert_assemble(torch.from_numpy(corpus), torch.from_numpy(seq_tab.copy()), torch.from_numpy(cu.copy()), pl.nseq, pl.R)
+    wins = oracle_ops.bert_windows(corpus, mask)
+    # every packed row must equal the reference window's (id, position) at a mask==1 slot, in order
+    for q, (b, col0, n, sep) in enumerate(seq_tab):
+        w_ids, w_mask, _ = wins[col0 // 510]
+        keep = np.nonzero(w_mask[b])[0]
+        assert np.array_equal(ids[cu[q]:cu[q + 1]].numpy(), w_ids[b][keep])
+        assert np.array_equal(pos[cu[q]:cu[q + 1]].numpy(), keep)
+    # token -> packed row map: row holds that token's id
+    tok_row, tok_off = pl.view("tok_row"), pl.view("tok_off")
+    for b, n in enumerate(ntoks):
+        assert np.array_equal(ids[tok_row[tok_off[b]:tok_off[b + 1]]].numpy(), corpus[b, :n])
+    # windows without real tokens are dropped
+    assert pl.nseq == sum(1 for b in range(B) for w in range(L // 510 + 1) if min(max(ntoks[b] - 510 * w, 0), min(510, L - 510 * w)) > 0)
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_engine_orchestration_with_standins(name, tmp_path, monkeypatch):
+    fx = load_golden(name)
+    monkeypatch.chdir(tmp_path)
+    cfg, kw, net, batch = build_case(fx["meta"])
+    net.eval()
+    monkeypatch.setattr(engine_mod, "ops", mock_ops)
+    monkeypatch.setattr(engine_mod, "make_epilogue", mock_ops.make_epilogue)
+    eng = net._get_engine()
+    eng._test_standins = True
+    out = eng.run(*batch, want_seg=True)
+    assert int(out["status"]) == 0
+    nchw = lambda t: t.permute(0, 3, 1, 2)
+    so = out["plan"].view("seg_off")
+    o = dict(image_batch=nchw(out["image_batch"]), coors_t=[out["boxes"][so[b]:so[b + 1]].numpy() for b in range(len(so) - 1)],
+             index_map=out["index_map"].numpy(), seg_emb=[out["seg_emb"].numpy()], p_fuse=nchw(out["p_fuse"]),
+             roi=nchw(out["roi"]), late=out["late"], pred_label=out["pred_label"], pred_mask=out["pred_mask"],
+             pred_ss=out["pred_ss"], pos_neg_labels=out["pos_neg_labels"].numpy(),
+             class_labels=out["class_labels"].numpy(), gt_label=out["gt_label"].numpy())
+    if "logits" in fx:
+        o["logits"] = out["logits"]
+    check_against_golden(o, fx, {"default": 5e-5}, big=False)
+    # the loss path (host-side mirror of the reference's loss modules)
+    from vibertgrid_pytorch_b200 import losses
+    total = losses.main_loss(net, out) + net.loss_control_lambda * losses.aux_loss(net, out)
+    assert abs(float(total.reshape(-1)[0]) - float(fx["loss"][0])) <= 1e-4 * max(1.0, abs(float(fx["loss"][0])))

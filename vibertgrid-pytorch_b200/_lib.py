@@ -1,0 +1,95 @@
+"""ctypes binding of libvbg_sm100a.so (include/vbg.h).  Fails loudly when the
+library is absent: there is no eager / CPU fallback for the hot path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvbg_sm100a.so")
+
+VBG_OK, VBG_EINVAL, VBG_ECUDA, VBG_EUNSUPPORTED, VBG_EWORKSPACE = 0, -1, -2, -3, -4
+PREC_FP32, PREC_TF32 = 0, 1
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+RES_NONE, RES_SAME, RES_UP2 = 0, 1, 2
+AGG_MEAN, AGG_FIRST = 0, 1
+
+
+class Epilogue(C.Structure):
+    _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
+                ("res_mode", C.c_int), ("ldr", C.c_int), ("out_h", C.c_int), ("out_w", C.c_int),
+                ("act", C.c_int)]
+
+
+class VbgError(RuntimeError):
+    pass
+
+
+_p, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_EP = C.POINTER(Epilogue)
+
+# name -> argtypes, in include/vbg.h order
+SIGNATURES = {
+    "vbg_version": [],
+    "vbg_last_error": [C.c_char_p, _sz],
+    "vbg_tc_available": [],
+    "vbg_normalize_resize_pad": [_p, _i, _i, _p, _i, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _p],
+    "vbg_resize_coords": [_p, _p, _p, _i, _i, _p, _p],
+    "vbg_bert_assemble": [_p, _i, _p, _p, _i, _i, _p, _p, _p],
+    "vbg_embed_ln": [_p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _p, _p],
+    "vbg_layernorm": [_p, _p, _p, _f, _i, _i, _p, _p],
+    "vbg_attention_fwd": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
+    "vbg_segment_starts": [_p, _p, _i, _i, _i, _p, _p, _p],
+    "vbg_segment_reduce": [_p, _p, _p, _i, _i, _i, _p, _p],
+    "vbg_box_index_map": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "vbg_grid_scatter": [_p, _p, _p, _i, _i, _i, _p, _p],
+    "vbg_label_paint": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
+    "vbg_gemm": [_p, _i, _p, _i, _i, _p, _i, _p, _i, _i, _i, _i, _EP, _i, _p],
+    "vbg_conv2d": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _EP, _i, _p],
+    "vbg_maxpool3x3s2": [_p, _i, _i, _i, _i, _p, _p],
+    "vbg_avgpool2x2": [_p, _i, _i, _i, _i, _p, _p],
+    "vbg_bn_fold": [_p, _p, _p, _p, _f, _i, _p, _p, _p],
+    "vbg_repack_oihw_to_ohwi": [_p, _i, _i, _i, _i, _p, _p],
+    "vbg_roi_align_fwd": [_p, _i, _i, _i, _i, _p, _p, _i, _f, _i, _p, _p, _p],
+    "vbg_softmax_rows": [_p, _i, _i, _p, _p],
+    "vbg_full_head_scores": [_p, _p, _i, _i, _p, _p],
+    "vbg_upsample_split_nchw": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+    "vbg_nhwc_to_nchw": [_p, _i, _i, _i, _i, _p, _p],
+    "vbg_crf_viterbi": [_p, _p, _p, _i, _i, _i, _p, _p, _p, _sz, _p],
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and type the library.  No GPU is needed to load it."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the ViBERTgrid hot path has no fallback. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or python vibertgrid-pytorch_b200/csrc/build.py)")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == ABI drift, by design
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    buf = C.create_string_buffer(512)
+    load().vbg_last_error(buf, 512)
+    return buf.value.decode(errors="replace")
+
+
+launch_count = 0     # kernels enqueued through the C-ABI (bench.py reports it as gpu_launches)
+
+
+def check(rc: int, what: str = ""):
+    global launch_count
+    launch_count += 1
+    if rc != VBG_OK:
+        raise VbgError(f"{what or 'libvbg'} failed (code {rc}): {last_error()}")

@@ -1,0 +1,53 @@
+"""Build libvbg_sm100a.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python vibertgrid-pytorch_b200/csrc/build.py [--force] [--verbose]
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.dirname(HERE)
+LIB = os.path.join(PKG, "libvbg_sm100a.so")
+SOURCES = ["vbg_api.cu", "vbg_grid.cu", "vbg_roi.cu", "vbg_image.cu", "vbg_bert.cu", "vbg_gemm_simt.cu", "vbg_gemm_tc.cu"]
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+
+
+def _stale(target, deps):
+    if not os.path.isfile(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    hdrs = [os.path.join(HERE, "vbg_common.cuh"), os.path.join(PKG, "..", "include", "vbg.h")]
+    hdrs += [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")]
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs, procs = [], []
+    for src in SOURCES:
+        s = os.path.join(HERE, src)
+        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        objs.append(o)
+        if force or _stale(o, [s] + hdrs):
+            cmd = [nvcc, *FLAGS, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else [])
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            print(f"--- {src}\n{out}")
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    if procs or force or _stale(LIB, objs):
+        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

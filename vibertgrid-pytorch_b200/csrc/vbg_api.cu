@@ -1,0 +1,155 @@
+// C-ABI glue: error state, version, and the precision dispatch of the dense contractions.
+#include "vbg_common.cuh"
+#include <string.h>
+
+namespace vbg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int gemm_simt(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int ldw, float* C, int ldc,
+              int M, int N, int K, const vbg_epilogue_t* ep, cudaStream_t s);
+int conv_simt(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int kh, int kw, int stride, int pad,
+              float* y, const vbg_epilogue_t* ep, cudaStream_t s);
+// tcgen05 path: returns VBG_EUNSUPPORTED (and enqueues nothing) for shapes it does not take
+int gemm_tc(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int ldw, float* C, int ldc,
+            int M, int N, int K, const vbg_epilogue_t* ep, cudaStream_t s);
+int conv_tc(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int kh, int kw, int stride, int pad,
+            float* y, const vbg_epilogue_t* ep, cudaStream_t s);
+bool tc_available();
+
+// ------------------------------------------------------------------ CRF Viterbi (model/crf.py:96-146)
+// One warp per sample; lane t owns tag t (T <= 32).  Back-pointers live in global scratch-free form:
+// the path is re-derived by storing per-step argmax in shared memory in chunks is unnecessary for the
+// sequence lengths here (S <= 4096): back-pointers are packed 8-bit in dynamic shared memory.
+__global__ void crf_viterbi_kernel(const float* __restrict__ feats, const float* __restrict__ trans,
+                                   const int32_t* __restrict__ seg_off, int T, float* __restrict__ tags,
+                                   float* __restrict__ scores, unsigned char* __restrict__ bp_scratch) {
+  const int b = blockIdx.x, lane = threadIdx.x;
+  const int s0 = seg_off[b], n = seg_off[b + 1] - s0;
+  const int start = T - 2, stop = T - 1;
+  unsigned char* bp = bp_scratch + (size_t)s0 * T;
+  float tr[32];
+#pragma unroll
+  for (int p = 0; p < 32; ++p) tr[p] = (lane < T && p < T) ? trans[lane * T + p] : 0.f;   // to lane from p
+  float fv = (lane == start) ? 0.f : -10000.f;
+  for (int t = 0; t < n; ++t) {
+    float best = -INFINITY; int arg = 0;
+#pragma unroll
+    for (int p = 0; p < 32; ++p) {
+      float prev = __shfl_sync(0xffffffffu, fv, p);
+      if (p < T) {
+        float v = prev + tr[p];
+        if (v > best) { best = v; arg = p; }        // first max wins, like torch.max
+      }
+    }
+    if (lane < T) {
+      bp[(size_t)t * T + lane] = (unsigned char)arg;
+      fv = best + feats[(size_t)(s0 + t) * T + lane];
+    }
+  }
+  float term = (lane < T) ? fv + trans[stop * T + lane] : -INFINITY;
+  float best = term; int arg = lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    scores[b] = best;
+    int cur = arg;
+    for (int t = n - 1; t >= 0; --t) {
+      tags[s0 + t] = (float)cur;
+      cur = bp[(size_t)t * T + cur];
+    }
+  }
+}
+
+}  // namespace vbg
+
+using namespace vbg;
+
+extern "C" int vbg_version(void) { return VBG_VERSION; }
+
+extern "C" int vbg_last_error(char* buf, size_t n) {
+  size_t len = strlen(g_err);
+  if (buf && n > 0) {
+    size_t c = len < n - 1 ? len : n - 1;
+    memcpy(buf, g_err, c);
+    buf[c] = 0;
+  }
+  return (int)len;
+}
+
+extern "C" int vbg_tc_available(void) { return tc_available() ? 1 : 0; }
+
+static int check_epilogue(const vbg_epilogue_t* ep, const char* who) {
+  if (!ep) return VBG_OK;
+  VBG_REQUIRE(ep->act >= VBG_ACT_NONE && ep->act <= VBG_ACT_GELU, "%s: bad activation %d", who, ep->act);
+  VBG_REQUIRE(ep->res_mode >= VBG_RES_NONE && ep->res_mode <= VBG_RES_UP2, "%s: bad residual mode %d", who, ep->res_mode);
+  VBG_REQUIRE((ep->residual != nullptr) == (ep->res_mode != VBG_RES_NONE), "%s: residual pointer / mode mismatch", who);
+  return VBG_OK;
+}
+
+extern "C" int vbg_gemm(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int ldw, float* C,
+                        int ldc, int M, int N, int K, const vbg_epilogue_t* ep, int precision, vbg_stream_t stream) {
+  VBG_REQUIRE(A && W && C, "vbg_gemm: null pointer");
+  VBG_REQUIRE(M >= 0 && N > 0 && K > 0 && K1 > 0 && K1 <= K, "vbg_gemm: bad shape M=%d N=%d K=%d K1=%d", M, N, K, K1);
+  VBG_REQUIRE((K1 == K) || A2, "vbg_gemm: A2 required when K1 < K");
+  VBG_REQUIRE(lda >= K1 && ldw >= K && ldc >= N && (K1 == K || lda2 >= K - K1), "vbg_gemm: leading dimension too small");
+  VBG_REQUIRE(precision == VBG_PREC_FP32 || precision == VBG_PREC_TF32, "vbg_gemm: bad precision %d", precision);
+  int rc = check_epilogue(ep, "vbg_gemm");
+  if (rc) return rc;
+  if (ep && ep->res_mode == VBG_RES_UP2)
+    VBG_REQUIRE(ep->out_h > 0 && ep->out_w > 0 && M % (ep->out_h * ep->out_w) == 0 && ep->out_h % 2 == 0 && ep->out_w % 2 == 0,
+                "vbg_gemm: VBG_RES_UP2 needs even out_h/out_w dividing M");
+  if (ep && ep->res_mode == VBG_RES_SAME) VBG_REQUIRE(ep->ldr >= N, "vbg_gemm: ldr too small");
+  if (M == 0) return VBG_OK;
+  cudaStream_t s = as_stream(stream);
+  if (precision == VBG_PREC_TF32) {
+    rc = gemm_tc(A, lda, A2, lda2, K1, W, ldw, C, ldc, M, N, K, ep, s);
+    if (rc != VBG_EUNSUPPORTED) return rc;
+  }
+  return gemm_simt(A, lda, A2, lda2, K1, W, ldw, C, ldc, M, N, K, ep, s);
+}
+
+extern "C" int vbg_conv2d(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int kh, int kw,
+                          int stride, int pad, float* y, const vbg_epilogue_t* ep, int precision, vbg_stream_t stream) {
+  VBG_REQUIRE(x && w && y, "vbg_conv2d: null pointer");
+  VBG_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0,
+              "vbg_conv2d: bad geometry");
+  VBG_REQUIRE(H + 2 * pad >= kh && W + 2 * pad >= kw, "vbg_conv2d: kernel larger than padded input");
+  VBG_REQUIRE(precision == VBG_PREC_FP32 || precision == VBG_PREC_TF32, "vbg_conv2d: bad precision %d", precision);
+  int rc = check_epilogue(ep, "vbg_conv2d");
+  if (rc) return rc;
+  if (ep && ep->res_mode == VBG_RES_UP2) {
+    int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    VBG_REQUIRE(Ho % 2 == 0 && Wo % 2 == 0, "vbg_conv2d: VBG_RES_UP2 needs even output dims");
+  }
+  cudaStream_t s = as_stream(stream);
+  if (precision == VBG_PREC_TF32) {
+    rc = conv_tc(x, B, H, W, Cin, w, Cout, kh, kw, stride, pad, y, ep, s);
+    if (rc != VBG_EUNSUPPORTED) return rc;
+  }
+  return conv_simt(x, B, H, W, Cin, w, Cout, kh, kw, stride, pad, y, ep, s);
+}
+
+extern "C" int vbg_crf_viterbi(const float* feats, const float* trans, const int32_t* seg_off, int B, int K, int T,
+                                  float* tags, float* scores, void* workspace, size_t ws_bytes, vbg_stream_t stream) {
+  VBG_REQUIRE(feats && trans && seg_off && tags && scores && B > 0 && T >= 3 && T <= 32, "vbg_crf_viterbi: bad arguments (T<=32)");
+  if ((size_t)K * T > ws_bytes || !workspace) {
+    set_error("vbg_crf_viterbi: workspace of %zu bytes needed", (size_t)K * T);
+    return VBG_EWORKSPACE;
+  }
+  crf_viterbi_kernel<<<B, 32, 0, as_stream(stream)>>>(feats, trans, seg_off, T, tags, scores,
+                                                     reinterpret_cast<unsigned char*>(workspace));
+  return check_launch("vbg_crf_viterbi");
+}

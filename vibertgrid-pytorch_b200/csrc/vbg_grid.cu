@@ -1,0 +1,251 @@
+// BERTgrid construction: coordinate rescale, token->segment aggregation, box index map,
+// BERTgrid scatter, label painting.  All HBM/latency-bound integer + copy work:
+// coalesced 128-bit accesses, no atomics, deterministic ("last writer wins" == max covering id).
+//
+// Replaces the Python loops of reference model/BERTgrid_generator.py:148-189 (aggregation, one
+// .item() sync per token), :220-243 (scatter, 4 int() syncs per segment) and
+// model/semantic_segmentation_head.py:199-214 (label painting), plus pipeline/transform.py:163-169.
+#include "vbg_common.cuh"
+
+namespace vbg {
+
+// ------------------------------------------------------------------ coords
+__global__ void resize_coords_kernel(const int64_t* __restrict__ coors, const int32_t* __restrict__ seg_off,
+                                     const float* __restrict__ ratios, int B, int K, int32_t* __restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  int b = sample_of(seg_off, B, k);
+  float rh = ratios[2 * b], rw = ratios[2 * b + 1];
+  // x columns (0,2) use the HEIGHT ratio, y columns (1,3) the WIDTH ratio: reference quirk kept.
+  float v0 = __fmul_rn((float)coors[4 * k + 0], rh);
+  float v1 = __fmul_rn((float)coors[4 * k + 1], rw);
+  float v2 = __fmul_rn((float)coors[4 * k + 2], rh);
+  float v3 = __fmul_rn((float)coors[4 * k + 3], rw);
+  int4 o = make_int4((int)v0, (int)v1, (int)v2, (int)v3);  // float->int conversion truncates toward zero
+  reinterpret_cast<int4*>(out)[k] = o;
+}
+
+// ------------------------------------------------------------------ segment runs
+// One CTA scans all tokens in chunks of blockDim.x; flag = first token of a sample or id change.
+__global__ void segment_starts_kernel(const int32_t* __restrict__ seg_ids, const int32_t* __restrict__ tok_off, int B,
+                                      int n_tok, int K, int32_t* __restrict__ seg_start, int32_t* __restrict__ status) {
+  __shared__ int warp_tot[32];
+  __shared__ int base_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  if (tid == 0) base_s = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < n_tok; t0 += blockDim.x) {
+    int t = t0 + tid;
+    int flag = 0;
+    if (t < n_tok) {
+      int b = sample_of(tok_off, B, t);
+      flag = (t == tok_off[b]) || (seg_ids[t] != seg_ids[t - 1]);
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, flag);
+    int excl = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) warp_tot[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < nw; ++w) {
+      int c = warp_tot[w];
+      if (w < wid) before += c;
+      total += c;
+    }
+    int base = base_s;
+    if (flag) {
+      int s = base + before + excl;
+      if (s <= K) seg_start[s] = t;
+    }
+    __syncthreads();
+    if (tid == 0) base_s = base + total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (base_s == K) seg_start[K] = n_tok;
+    else if (status) atomicOr(status, 1);   // reference asserts #runs == #boxes (BERTgrid_generator.py:233)
+  }
+}
+
+// One CTA per segment; each thread owns 4 channels and adds the run's tokens in order
+// (bit-compatible with the reference's sequential `mean += e; mean /= n`).
+__global__ void segment_reduce_kernel(const float* __restrict__ hidden, const int32_t* __restrict__ tok_row,
+                                      const int32_t* __restrict__ seg_start, int C4, int mode,
+                                      float* __restrict__ out) {
+  const int k = blockIdx.x;
+  const int a = seg_start[k], e = seg_start[k + 1];
+  const float4* h4 = reinterpret_cast<const float4*>(hidden);
+  float4* o4 = reinterpret_cast<float4*>(out);
+  for (int c = threadIdx.x; c < C4; c += blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e > a) {
+      acc = __ldg(h4 + (size_t)tok_row[a] * C4 + c);
+      if (mode == VBG_AGG_MEAN) {
+        for (int t = a + 1; t < e; ++t) {
+          float4 v = __ldg(h4 + (size_t)tok_row[t] * C4 + c);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        float n = (float)(e - a);
+        acc.x = __fdiv_rn(acc.x, n); acc.y = __fdiv_rn(acc.y, n);
+        acc.z = __fdiv_rn(acc.z, n); acc.w = __fdiv_rn(acc.w, n);
+      }
+    }
+    o4[(size_t)k * C4 + c] = acc;
+  }
+}
+
+// ------------------------------------------------------------------ index map / label paint
+// CTA = 32x8 tile of cells of one sample.  Boxes are consumed in chunks of 256 from the LAST
+// segment backwards; each chunk is culled against the tile and compacted (order preserved) into
+// shared memory; a cell takes the first hit scanning backwards.  Early exit when the tile is full.
+constexpr int kTileW = 32, kTileH = 8;
+
+template <bool kPaint>
+__global__ void __launch_bounds__(256)
+box_map_kernel(const int32_t* __restrict__ boxes, const int32_t* __restrict__ seg_off,
+               const int32_t* __restrict__ seg_cls, int stride, int Hg, int Wg, int32_t* __restrict__ idx,
+               int64_t* __restrict__ pos_neg, int64_t* __restrict__ cls) {
+  __shared__ int4 hit_box[256];
+  __shared__ int hit_id[256];
+  __shared__ int warp_cnt[8];
+  const int b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  const int x = x0 + lane, y = y0 + wid;
+  const int s0 = seg_off[b], S = seg_off[b + 1] - s0;
+  int best = -1;
+  const bool live = (x < Wg) && (y < Hg);
+  for (int hi = S; hi > 0; hi -= 256) {
+    const int lo = hi > 256 ? hi - 256 : 0;
+    const int s = lo + tid;
+    int4 bx = make_int4(0, 0, 0, 0);
+    bool ov = false;
+    if (s < hi) {
+      int4 c = __ldg(reinterpret_cast<const int4*>(boxes) + s0 + s);   // (l, t, r, b)
+      bx.x = py_slice_bound(c.x / stride, Wg);
+      bx.y = py_slice_bound(c.y / stride, Hg);
+      bx.z = py_slice_bound(c.z / stride, Wg);
+      bx.w = py_slice_bound(c.w / stride, Hg);
+      ov = bx.x < bx.z && bx.y < bx.w && bx.x < x0 + kTileW && bx.z > x0 && bx.y < y0 + kTileH && bx.w > y0;
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, ov);
+    if (lane == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      int c = warp_cnt[w];
+      if (w < wid) before += c;
+      total += c;
+    }
+    if (ov) {
+      int p = before + __popc(bal & ((1u << lane) - 1));
+      hit_box[p] = bx;
+      hit_id[p] = s;
+    }
+    __syncthreads();
+    if (live && best < 0) {
+      for (int p = total - 1; p >= 0; --p) {
+        int4 q = hit_box[p];
+        if (x >= q.x && x < q.z && y >= q.y && y < q.w) { best = hit_id[p]; break; }
+      }
+    }
+    if (__syncthreads_and(best >= 0 || !live)) break;
+  }
+  if (!live) return;
+  const size_t o = ((size_t)b * Hg + y) * Wg + x;
+  if (kPaint) {
+    long long c = 0, pn = 0;
+    if (best >= 0) {
+      c = seg_cls[s0 + best];
+      pn = c > 0 ? 1 : 2;
+    }
+    pos_neg[o] = pn;
+    cls[o] = c;
+  } else {
+    idx[o] = best;
+  }
+}
+
+// ------------------------------------------------------------------ scatter
+// One warp per grid cell: 128-bit coalesced copy of the winning segment's embedding (L2 resident,
+// K*C*4 bytes) or zeros.  Pure write stream: B*Hg*Wg*C*4 bytes.
+__global__ void __launch_bounds__(256)
+grid_scatter_kernel(const float* __restrict__ seg_emb, const int32_t* __restrict__ idx,
+                    const int32_t* __restrict__ seg_off, int cells_per_img, long long total_cells, int C4,
+                    float* __restrict__ grid) {
+  const int lane = threadIdx.x & 31;
+  long long cell = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long step = (long long)gridDim.x * (blockDim.x >> 5);
+  for (; cell < total_cells; cell += step) {
+    const int b = (int)(cell / cells_per_img);
+    const int s = __ldg(idx + cell);
+    float4* dst = reinterpret_cast<float4*>(grid) + cell * C4;
+    if (s >= 0) {
+      const float4* src = reinterpret_cast<const float4*>(seg_emb) + (size_t)(__ldg(seg_off + b) + s) * C4;
+      for (int c = lane; c < C4; c += 32) dst[c] = __ldg(src + c);
+    } else {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = lane; c < C4; c += 32) dst[c] = z;
+    }
+  }
+}
+
+}  // namespace vbg
+
+using namespace vbg;
+
+extern "C" int vbg_resize_coords(const int64_t* coors, const int32_t* seg_off, const float* ratios, int B, int K,
+                                 int32_t* out, vbg_stream_t stream) {
+  VBG_REQUIRE(coors && seg_off && ratios && out && B > 0 && K >= 0, "vbg_resize_coords: bad arguments");
+  if (K == 0) return VBG_OK;
+  resize_coords_kernel<<<cdiv(K, 128), 128, 0, as_stream(stream)>>>(coors, seg_off, ratios, B, K, out);
+  return check_launch("vbg_resize_coords");
+}
+
+extern "C" int vbg_segment_starts(const int32_t* seg_ids, const int32_t* tok_off, int B, int n_tok, int K,
+                                  int32_t* seg_start, int32_t* status, vbg_stream_t stream) {
+  VBG_REQUIRE(seg_ids && tok_off && seg_start && B > 0 && n_tok >= 0 && K >= 0, "vbg_segment_starts: bad arguments");
+  segment_starts_kernel<<<1, 1024, 0, as_stream(stream)>>>(seg_ids, tok_off, B, n_tok, K, seg_start, status);
+  return check_launch("vbg_segment_starts");
+}
+
+extern "C" int vbg_segment_reduce(const float* hidden, const int32_t* tok_row, const int32_t* seg_start, int K, int C,
+                                  int mode, float* out, vbg_stream_t stream) {
+  VBG_REQUIRE(hidden && tok_row && seg_start && out, "vbg_segment_reduce: null pointer");
+  VBG_REQUIRE(C > 0 && C % 4 == 0 && aligned16(hidden) && aligned16(out), "vbg_segment_reduce: C %% 4 and 16B alignment required");
+  VBG_REQUIRE(mode == VBG_AGG_MEAN || mode == VBG_AGG_FIRST, "vbg_segment_reduce: bad mode %d", mode);
+  if (K == 0) return VBG_OK;
+  int threads = C / 4 >= 256 ? 256 : ((C / 4 + 31) / 32) * 32;
+  segment_reduce_kernel<<<K, threads, 0, as_stream(stream)>>>(hidden, tok_row, seg_start, C / 4, mode, out);
+  return check_launch("vbg_segment_reduce");
+}
+
+extern "C" int vbg_box_index_map(const int32_t* boxes, const int32_t* seg_off, int B, int stride, int Hg, int Wg,
+                                 int32_t* idx, vbg_stream_t stream) {
+  VBG_REQUIRE(boxes && seg_off && idx && B > 0 && stride > 0 && Hg > 0 && Wg > 0, "vbg_box_index_map: bad arguments");
+  VBG_REQUIRE(aligned16(boxes), "vbg_box_index_map: boxes must be 16B aligned");
+  dim3 g(cdiv(Wg, kTileW), cdiv(Hg, kTileH), B);
+  box_map_kernel<false><<<g, 256, 0, as_stream(stream)>>>(boxes, seg_off, nullptr, stride, Hg, Wg, idx, nullptr, nullptr);
+  return check_launch("vbg_box_index_map");
+}
+
+extern "C" int vbg_label_paint(const int32_t* boxes, const int32_t* seg_off, const int32_t* seg_cls, int B, int H, int W,
+                               int64_t* pos_neg, int64_t* cls, vbg_stream_t stream) {
+  VBG_REQUIRE(boxes && seg_off && seg_cls && pos_neg && cls && B > 0 && H > 0 && W > 0, "vbg_label_paint: bad arguments");
+  VBG_REQUIRE(aligned16(boxes), "vbg_label_paint: boxes must be 16B aligned");
+  dim3 g(cdiv(W, kTileW), cdiv(H, kTileH), B);
+  box_map_kernel<true><<<g, 256, 0, as_stream(stream)>>>(boxes, seg_off, seg_cls, 1, H, W, nullptr, pos_neg, cls);
+  return check_launch("vbg_label_paint");
+}
+
+extern "C" int vbg_grid_scatter(const float* seg_emb, const int32_t* idx, const int32_t* seg_off, int B, int cells, int C,
+                                float* grid, vbg_stream_t stream) {
+  VBG_REQUIRE(seg_emb && idx && seg_off && grid && B > 0 && cells > 0, "vbg_grid_scatter: bad arguments");
+  VBG_REQUIRE(C > 0 && C % 4 == 0 && aligned16(seg_emb) && aligned16(grid), "vbg_grid_scatter: C %% 4 and 16B alignment required");
+  long long total = (long long)B * cells;
+  int blocks = (int)((total + 7) / 8);
+  int cap = kNumSMs * 16;                      // 8 resident CTAs/SM x 2 waves, then grid-stride
+  if (blocks > cap) blocks = cap;
+  grid_scatter_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seg_emb, idx, seg_off, cells, total, C / 4, grid);
+  return check_launch("vbg_grid_scatter");
+}

@@ -1,0 +1,201 @@
+// Image-side memory-bound kernels: fused normalise+resize+pad (a1), pooling, BatchNorm folding,
+// weight repacking, seg-head broadcast store, layout conversion.
+#include "vbg_common.cuh"
+
+namespace vbg {
+
+// ------------------------------------------------------------------ a1
+// (x - mean)/std per tap, then bilinear (align_corners=False) exactly as ATen's
+// upsample_bilinear2d with scale = in/out; writes NHWC.  Replaces the per-image
+// normalize/interpolate/copy_ kernels of reference pipeline/transform.py:122,149-155,261-269.
+__global__ void normalize_resize_kernel(const float* __restrict__ img, int h, int w, float* __restrict__ out, int H,
+                                        int W, int oh, int ow, float3 mean, float3 stdv) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= ow || y >= oh) return;
+  const float sy = (float)h / (float)oh, sx = (float)w / (float)ow;
+  float fy = sy * ((float)y + 0.5f) - 0.5f; if (fy < 0.f) fy = 0.f;
+  float fx = sx * ((float)x + 0.5f) - 0.5f; if (fx < 0.f) fx = 0.f;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+  const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+  const float m[3] = {mean.x, mean.y, mean.z}, s[3] = {stdv.x, stdv.y, stdv.z};
+  float r[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* p = img + (size_t)c * h * w;
+    float p00 = __fdiv_rn(__ldg(p + (size_t)y0 * w + x0) - m[c], s[c]);
+    float p01 = __fdiv_rn(__ldg(p + (size_t)y0 * w + x1) - m[c], s[c]);
+    float p10 = __fdiv_rn(__ldg(p + (size_t)y1 * w + x0) - m[c], s[c]);
+    float p11 = __fdiv_rn(__ldg(p + (size_t)y1 * w + x1) - m[c], s[c]);
+    r[c] = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
+  }
+  float* o = out + ((size_t)y * W + x) * 3;
+  o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+}
+
+// ------------------------------------------------------------------ pooling (NHWC, float4 over channels)
+__global__ void maxpool3x3s2_kernel(const float4* __restrict__ x, int B, int H, int W, int C4, int Ho, int Wo,
+                                    float4* __restrict__ y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * Ho * Wo * C4;
+  if (i >= total) return;
+  int c = (int)(i % C4); long long t = i / C4;
+  int wo = (int)(t % Wo); t /= Wo;
+  int ho = (int)(t % Ho); int b = (int)(t / Ho);
+  float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    int hi = ho * 2 - 1 + dy;
+    if (hi < 0 || hi >= H) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      int wi = wo * 2 - 1 + dx;
+      if (wi < 0 || wi >= W) continue;
+      float4 v = __ldg(x + (((size_t)b * H + hi) * W + wi) * C4 + c);
+      m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+    }
+  }
+  y[i] = m;
+}
+
+__global__ void avgpool2x2_kernel(const float4* __restrict__ x, int B, int H, int W, int C4, float4* __restrict__ y) {
+  const int Ho = H / 2, Wo = W / 2;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * Ho * Wo * C4;
+  if (i >= total) return;
+  int c = (int)(i % C4); long long t = i / C4;
+  int wo = (int)(t % Wo); t /= Wo;
+  int ho = (int)(t % Ho); int b = (int)(t / Ho);
+  const float4* p = x + (((size_t)b * H + 2 * ho) * W + 2 * wo) * C4 + c;
+  float4 a = __ldg(p), bb = __ldg(p + C4), cc = __ldg(p + (size_t)W * C4), d = __ldg(p + (size_t)W * C4 + C4);
+  float4 r;
+  r.x = (a.x + bb.x + cc.x + d.x) * 0.25f; r.y = (a.y + bb.y + cc.y + d.y) * 0.25f;
+  r.z = (a.z + bb.z + cc.z + d.z) * 0.25f; r.w = (a.w + bb.w + cc.w + d.w) * 0.25f;
+  y[i] = r;
+}
+
+// ------------------------------------------------------------------ parameter preparation
+__global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ mean,
+                               const float* __restrict__ var, float eps, int C, float* __restrict__ scale,
+                               float* __restrict__ shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float inv = __fdiv_rn(1.0f, sqrtf(var[c] + eps));
+  float a = w[c] * inv;
+  scale[c] = a;
+  shift[c] = b[c] - mean[c] * a;
+}
+
+__global__ void repack_oihw_kernel(const float* __restrict__ w, int O, int I, int H, int W, float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)O * I * H * W;
+  if (i >= total) return;
+  int ci = (int)(i % I); long long t = i / I;     // out index = ((o*H + h)*W + w)*I + ci
+  int ww = (int)(t % W); t /= W;
+  int hh = (int)(t % H); int o = (int)(t / H);
+  out[i] = __ldg(w + (((size_t)o * I + ci) * H + hh) * W + ww);
+}
+
+// ------------------------------------------------------------------ outputs
+// One CTA per (sample, low-res row): stage the row's [w, Ct] logits in shared memory, then emit `up`
+// full-resolution rows per channel with coalesced stores into the two NCHW outputs.
+__global__ void upsample_split_kernel(const float* __restrict__ x, int h, int w, int Ct, int up, int c_split,
+                                      float* __restrict__ out1, float* __restrict__ out2) {
+  extern __shared__ float row[];          // [w][Ct]
+  const int b = blockIdx.y, yi = blockIdx.x;
+  const float* src = x + ((size_t)b * h + yi) * w * Ct;
+  for (int i = threadIdx.x; i < w * Ct; i += blockDim.x) row[i] = __ldg(src + i);
+  __syncthreads();
+  const int Wf = w * up, Hf = h * up;
+  const int n_out = Ct * up * Wf;
+  for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
+    int X = i % Wf; int t = i / Wf;
+    int dy = t % up; int c = t / up;
+    float v = row[(X / up) * Ct + c];
+    int Y = yi * up + dy;
+    if (c < c_split) out1[(((size_t)b * c_split + c) * Hf + Y) * Wf + X] = v;
+    else out2[(((size_t)b * (Ct - c_split) + (c - c_split)) * Hf + Y) * Wf + X] = v;
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int HW, int C, float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* src = x + (size_t)b * HW * C;
+  float* dst = y + (size_t)b * HW * C;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int p = p0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (p < HW && c < C) ? __ldg(src + (size_t)p * C + c) : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, p = p0 + threadIdx.x;
+    if (p < HW && c < C) dst[(size_t)c * HW + p] = tile[threadIdx.x][j];
+  }
+}
+
+}  // namespace vbg
+
+using namespace vbg;
+
+extern "C" int vbg_normalize_resize_pad(const float* img_chw, int h, int w, float* batch_nhwc, int b, int H, int W,
+                                        int oh, int ow, const float* h_mean3, const float* h_std3, vbg_stream_t stream) {
+  VBG_REQUIRE(img_chw && batch_nhwc && h_mean3 && h_std3, "vbg_normalize_resize_pad: null pointer");
+  VBG_REQUIRE(h > 0 && w > 0 && oh > 0 && ow > 0 && oh <= H && ow <= W && b >= 0,
+              "vbg_normalize_resize_pad: bad geometry h=%d w=%d oh=%d ow=%d H=%d W=%d", h, w, oh, ow, H, W);
+  dim3 blk(32, 8), grd(cdiv(ow, 32), cdiv(oh, 8));
+  normalize_resize_kernel<<<grd, blk, 0, as_stream(stream)>>>(
+      img_chw, h, w, batch_nhwc + (size_t)b * H * W * 3, H, W, oh, ow,
+      make_float3(h_mean3[0], h_mean3[1], h_mean3[2]), make_float3(h_std3[0], h_std3[1], h_std3[2]));
+  return check_launch("vbg_normalize_resize_pad");
+}
+
+extern "C" int vbg_maxpool3x3s2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream) {
+  VBG_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C % 4 == 0 && aligned16(x) && aligned16(y), "vbg_maxpool3x3s2: bad arguments");
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  long long total = (long long)B * Ho * Wo * (C / 4);
+  maxpool3x3s2_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(x), B, H, W, C / 4, Ho, Wo, reinterpret_cast<float4*>(y));
+  return check_launch("vbg_maxpool3x3s2");
+}
+
+extern "C" int vbg_avgpool2x2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream) {
+  VBG_REQUIRE(x && y && B > 0 && H > 1 && W > 1 && C % 4 == 0 && aligned16(x) && aligned16(y), "vbg_avgpool2x2: bad arguments");
+  long long total = (long long)B * (H / 2) * (W / 2) * (C / 4);
+  avgpool2x2_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(x), B, H, W, C / 4, reinterpret_cast<float4*>(y));
+  return check_launch("vbg_avgpool2x2");
+}
+
+extern "C" int vbg_bn_fold(const float* weight, const float* bias, const float* mean, const float* var, float eps, int C,
+                           float* scale, float* shift, vbg_stream_t stream) {
+  VBG_REQUIRE(weight && bias && mean && var && scale && shift && C > 0, "vbg_bn_fold: bad arguments");
+  bn_fold_kernel<<<cdiv(C, 128), 128, 0, as_stream(stream)>>>(weight, bias, mean, var, eps, C, scale, shift);
+  return check_launch("vbg_bn_fold");
+}
+
+extern "C" int vbg_repack_oihw_to_ohwi(const float* w, int O, int I, int H, int W, float* out, vbg_stream_t stream) {
+  VBG_REQUIRE(w && out && O > 0 && I > 0 && H > 0 && W > 0, "vbg_repack_oihw_to_ohwi: bad arguments");
+  long long total = (long long)O * I * H * W;
+  repack_oihw_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(w, O, I, H, W, out);
+  return check_launch("vbg_repack_oihw_to_ohwi");
+}
+
+extern "C" int vbg_upsample_split_nchw(const float* x, int B, int h, int w, int Ct, int up, int c_split, float* out1,
+                                       float* out2, vbg_stream_t stream) {
+  VBG_REQUIRE(x && out1 && out2 && B > 0 && h > 0 && w > 0 && Ct > 0 && up > 0 && c_split > 0 && c_split < Ct,
+              "vbg_upsample_split_nchw: bad arguments");
+  size_t smem = (size_t)w * Ct * sizeof(float);
+  VBG_REQUIRE(smem <= 48 * 1024, "vbg_upsample_split_nchw: row of %zu bytes exceeds 48 KiB", smem);
+  upsample_split_kernel<<<dim3(h, B), 256, smem, as_stream(stream)>>>(x, h, w, Ct, up, c_split, out1, out2);
+  return check_launch("vbg_upsample_split_nchw");
+}
+
+extern "C" int vbg_nhwc_to_nchw(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream) {
+  VBG_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0, "vbg_nhwc_to_nchw: bad arguments");
+  dim3 grd(cdiv((long long)H * W, 32), cdiv(C, 32), B), blk(32, 8);
+  nhwc_to_nchw_kernel<<<grd, blk, 0, as_stream(stream)>>>(x, H * W, C, y);
+  return check_launch("vbg_nhwc_to_nchw");
+}

@@ -1,0 +1,314 @@
+"""Forward engine: sequences the sm_100a kernels of the joint forward
+(reference model/ViBERTgrid_net.py:512-544) over one batch, with zero
+device->host synchronisations.
+
+Data layout in HBM: fp32, channels-last.  One-time
+parameter preparation (cached until a weight changes): conv weights repacked
+OIHW->OHWI, eval BatchNorm folded to per-channel (scale, shift), BERT Q/K/V
+weights packed to one [2304,768] operand, the two seg-head 1x1 convs packed,
+the ROI FC weight permuted to the NHWC flatten order.
+
+Algebraic restructurings (results equal up to fp32 re-association):
+  * BERT windows -> one packed varlen batch of real rows only (plan.py)
+  * cat(x, grid) -> 1x1 conv     ==  two-source K-split GEMM (no concat buffer)
+  * up(a) + lateral(b) -> conv   ==  lateral GEMM with nearest-x2 residual epilogue
+  * fuse(cat[up8,up4,up2,id])    ==  4 chained 1x1 GEMMs at native resolution (3x fewer FLOPs)
+  * 1x1(up4(x))                  ==  up4(1x1(x))  (seg head: 16x fewer FLOPs, no 268 MB/img tensor)
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from . import params as P
+from .ops import ACT_GELU, ACT_NONE, ACT_RELU, PREC_FP32, PREC_TF32, RES_NONE, RES_SAME, RES_UP2, make_epilogue
+from .plan import plan_batch
+
+
+class _Prepared:
+    def __init__(self):
+        self.convw: Dict[int, torch.Tensor] = {}
+        self.bn: Dict[int, tuple] = {}
+        self.bert_layers = []
+        self.misc: Dict[str, torch.Tensor] = {}
+
+
+class ForwardEngine:
+    def __init__(self, net):
+        self.net = net
+        self._prep: Optional[_Prepared] = None
+        self._fp = None
+        env = os.environ.get("VBG_PRECISION", "").lower()
+        self.precision = {"fp32": PREC_FP32, "tf32": PREC_TF32}.get(env)
+        self.launches = 0
+
+    # ------------------------------------------------------------------ parameter preparation
+    def invalidate(self):
+        self._prep, self._fp = None, None
+
+    def _fingerprint(self):
+        return tuple((t.data_ptr(), t._version) for t in self.net.state_dict(keep_vars=True).values())
+
+    def _prepare(self):
+        fp = self._fingerprint()
+        if self._prep is not None and fp == self._fp:
+            return self._prep
+        net, pr = self.net, _Prepared()
+        for m in net.modules():
+            if isinstance(m, nn.Conv2d):
+                w = m.weight.detach()
+                if w.shape[2] == 1 and w.shape[3] == 1:
+                    pr.convw[id(m)] = w.reshape(w.shape[0], 1, 1, w.shape[1]).contiguous()  # OIHW == OHWI for 1x1
+                else:
+                    pr.convw[id(m)] = ops.repack_oihw_to_ohwi(w)
+            elif isinstance(m, nn.modules.batchnorm._BatchNorm):
+                pr.bn[id(m)] = ops.bn_fold(m)
+        for lyr in net.bert_model.encoder.layer:
+            s = lyr.attention.self
+            pr.bert_layers.append(dict(
+                wqkv=torch.cat([s.query.weight, s.key.weight, s.value.weight], 0).detach().contiguous(),
+                bqkv=torch.cat([s.query.bias, s.key.bias, s.value.bias], 0).detach().contiguous()))
+        roi = net.late_fusion_net.ROI_embedding_net
+        Cc, Pp = net.p_fuse_channel, net.roi_shape
+        pr.misc["roi_fc_w"] = ops.repack_oihw_to_ohwi(
+            roi.linear.weight.detach().reshape(-1, Cc, Pp, Pp)).reshape(roi.linear.out_features, -1)
+        if net.semantic_segmentation_head is not None:
+            enc = net.semantic_segmentation_head.encoder
+            pr.misc["seg_w"] = torch.cat([enc.conv_3_1.weight.flatten(1), enc.conv_3_2.weight.flatten(1)], 0).detach().contiguous()
+            pr.misc["seg_b"] = torch.cat([enc.conv_3_1.bias, enc.conv_3_2.bias], 0).detach().contiguous()
+        head = net.field_type_classification_head
+        if isinstance(head, P.FullHeadParams) and net.layer_mode == "single":
+            nets = [getattr(head, f"category_classification_net_{i}") for i in range(net.num_tokens - 1)]
+            pr.misc["full_w"] = torch.cat([n.layer.linear.weight for n in nets], 0).detach().contiguous()
+            pr.misc["full_b"] = torch.cat([n.layer.linear.bias for n in nets], 0).detach().contiguous()
+        self._prep, self._fp = pr, fp
+        return pr
+
+    # ------------------------------------------------------------------ building blocks
+    def _prec(self):
+        if self.precision is None:
+            self.precision = PREC_TF32 if ops.tc_available() else PREC_FP32
+        return self.precision
+
+    def _conv(self, x, conv: nn.Conv2d, bn=None, act=ACT_NONE, residual=None, res_mode=RES_NONE):
+        pr = self._prep
+        w = pr.convw[id(conv)]
+        scale, shift = pr.bn[id(bn)] if bn is not None else (None, None if conv.bias is None else conv.bias.detach())
+        B, H, W, Cin = x.shape
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        Cout = conv.out_channels
+        if k == 1 and s == 1:
+            ep = make_epilogue(scale, shift, residual, res_mode, ldr=Cout, out_h=H, out_w=W, act=act)
+            y = ops.gemm(x.view(B * H * W, Cin), w.view(Cout, Cin), ep=ep, precision=self._prec())
+            return y.view(B, H, W, Cout)
+        ep = make_epilogue(scale, shift, residual, res_mode, ldr=Cout, act=act)
+        return ops.conv2d(x, w, s, p, ep=ep, precision=self._prec())
+
+    def _lin(self, x, lin: nn.Linear, act=ACT_NONE, residual=None, A2=None, W=None):
+        ep = make_epilogue(None, lin.bias.detach(), residual, RES_SAME if residual is not None else RES_NONE,
+                           ldr=lin.out_features, act=act)
+        return ops.gemm(x, lin.weight.detach() if W is None else W, A2=A2, ep=ep, precision=self._prec())
+
+    def _mlp_or_lin(self, x, m):
+        if hasattr(m, "linear_1"):
+            return self._lin(self._lin(x, m.linear_1, ACT_RELU), m.linear_2)
+        return self._lin(x, m.linear)
+
+    def _block(self, x, conv1, bn1, conv2, bn2, shortcut):
+        y = self._conv(x, conv1, bn1, ACT_RELU)
+        if shortcut is None:
+            sc = x
+        else:
+            kind, sconv, sbn = shortcut
+            sc = self._conv(ops.avgpool2x2(x) if kind == "avg" else x, sconv, sbn)
+        return self._conv(y, conv2, bn2, ACT_RELU, residual=sc, res_mode=RES_SAME)
+
+    def _our_block(self, x, blk: P.ResBlockParams):
+        sc = None
+        if blk.downsample:
+            sc = ("avg", blk.conv_shortcut[1], blk.conv_shortcut[2]) if blk.d_variant \
+                else ("conv", blk.conv_shortcut[0], blk.conv_shortcut[1])
+        return self._block(x, blk.conv_1, blk.bn_1, blk.conv_2, blk.bn_2, sc)
+
+    def _tv_block(self, x, blk):
+        sc = ("conv", blk.downsample[0], blk.downsample[1]) if hasattr(blk, "downsample") else None
+        return self._block(x, blk.conv1, blk.bn1, blk.conv2, blk.bn2, sc)
+
+    def _early_fusion(self, x2, grid, conv: nn.Conv2d):
+        B, H, W, C1 = x2.shape
+        ep = make_epilogue(None, None if conv.bias is None else conv.bias.detach())
+        y = ops.gemm(x2.view(-1, C1), self._prep.convw[id(conv)].view(conv.out_channels, -1), A2=grid.view(-1, grid.shape[-1]), ep=ep,
+                     precision=self._prec())
+        return y.view(B, H, W, conv.out_channels)
+
+    # ------------------------------------------------------------------ stages
+    def _bert(self, plan, dev_tab, corpus):
+        net, pr = self.net, self._prep
+        bm = net.bert_model
+        e = bm.embeddings
+        heads = bm.cfg["num_attention_heads"]
+        seq_tab, cu = dev_tab["seq_tab"], dev_tab["cu"]
+        ids, pos = ops.bert_assemble(corpus, seq_tab, cu, plan.nseq, plan.R)
+        x = ops.embed_ln(ids, pos, e.word_embeddings.weight.detach(), e.position_embeddings.weight.detach(),
+                         e.token_type_embeddings.weight.detach()[0], e.LayerNorm.weight.detach(),
+                         e.LayerNorm.bias.detach(), e.LayerNorm.eps)
+        prec = self._prec()
+        for lyr, pk in zip(bm.encoder.layer, pr.bert_layers):
+            qkv = ops.gemm(x, pk["wqkv"], ep=make_epilogue(None, pk["bqkv"]), precision=prec)
+            ctx = ops.attention(qkv, cu, plan.nseq, plan.max_len, heads, prec)
+            ao = lyr.attention.output
+            a = self._lin(ctx, ao.dense, residual=x)
+            x = ops.layernorm(a, ao.LayerNorm.weight.detach(), ao.LayerNorm.bias.detach(), ao.LayerNorm.eps, out=a)
+            h = self._lin(x, lyr.intermediate.dense, ACT_GELU)
+            o = self._lin(h, lyr.output.dense, residual=x)
+            x = ops.layernorm(o, lyr.output.LayerNorm.weight.detach(), lyr.output.LayerNorm.bias.detach(),
+                              lyr.output.LayerNorm.eps, out=o)
+        return x
+
+    def _backbone(self, img, grid):
+        bb = self.net.backbone
+        if bb.pretrained_layout:
+            r = bb.resnet
+            x1 = ops.maxpool3x3s2(self._conv(img, r.conv1, r.bn1, ACT_RELU))
+            for blk in r.layer1:
+                x1 = self._tv_block(x1, blk)
+            x2 = self._tv_block(x1, r.layer2[0])
+            x2 = self._early_fusion(x2, grid, bb.early_fusion)
+            for blk in list(r.layer2)[1:]:
+                x2 = self._tv_block(x2, blk)
+            x3 = x2
+            for blk in r.layer3:
+                x3 = self._tv_block(x3, blk)
+            x4 = x3
+            for blk in r.layer4:
+                x4 = self._tv_block(x4, blk)
+        else:
+            x1 = ops.maxpool3x3s2(self._conv(img, bb.conv_1[0], bb.conv_1[1], ACT_RELU))
+            for blk in bb.conv_2_x:
+                x1 = self._our_block(x1, blk)
+            x2 = self._our_block(x1, bb.conv_3_x.block_1)
+            x2 = self._early_fusion(x2, grid, bb.conv_3_x.early_fusion)
+            for blk in bb.conv_3_x.layers:
+                x2 = self._our_block(x2, blk)
+            x3 = x2
+            for blk in bb.conv_4_x:
+                x3 = self._our_block(x3, blk)
+            x4 = x3
+            for blk in bb.conv_5_x:
+                x4 = self._our_block(x4, blk)
+        # FPN top-down: lateral 1x1 GEMM with the nearest-x2 upsample-add fused in its epilogue
+        x4 = self._conv(x4, bb.conv_6_x)
+        x5 = self._conv(self._conv(x3, bb.skip_1, residual=x4, res_mode=RES_UP2), bb.merge_1)
+        x6 = self._conv(self._conv(x2, bb.skip_2, residual=x5, res_mode=RES_UP2), bb.merge_2)
+        x7 = self._conv(self._conv(x1, bb.skip_3, residual=x6, res_mode=RES_UP2), bb.merge_3)
+        # fuse(cat[up8 x4, up4 x5, up2 x6, x7]) as four chained K-slices of fuse.weight at native resolution
+        wf = self._prep.convw[id(bb.fuse)].view(bb.fuse.out_channels, -1)   # [256, 1024]
+        Pc = wf.shape[1] // 4
+        prec = self._prec()
+        t = None
+        for i, lvl in enumerate((x4, x5, x6, x7)):
+            B, H, W, Cc = lvl.shape
+            ep = make_epilogue(residual=t, res_mode=RES_UP2 if t is not None else RES_NONE, out_h=H, out_w=W)
+            t = ops.gemm(lvl.view(-1, Cc), wf, ep=ep, precision=prec, N=wf.shape[0], K=Pc, ldw=wf.shape[1],
+                         w_offset=i * Pc).view(B, H, W, wf.shape[0])
+        return t
+
+    def _seg_head(self, p_fuse):
+        enc = self.net.semantic_segmentation_head.encoder
+        x = self._conv(p_fuse, enc.conv_1, enc.bn_1, ACT_RELU)
+        x = self._conv(x, enc.conv_2, enc.bn_2, ACT_RELU)
+        B, H, W, Cc = x.shape
+        pr = self._prep
+        lg = ops.gemm(x.view(-1, Cc), pr.misc["seg_w"], ep=make_epilogue(None, pr.misc["seg_b"]), precision=self._prec())
+        return ops.upsample_split_nchw(lg.view(B, H, W, -1), self.net.p_fuse_downsampling_ratio, 3)
+
+    # ------------------------------------------------------------------ whole forward
+    @torch.no_grad()
+    def run(self, image, seg_indices, seg_classes, coors, corpus, mask, want_seg=True):
+        net = self.net
+        dev = corpus.device
+        if dev.type != "cuda" and not getattr(self, "_test_standins", False):
+            raise RuntimeError("ViBERTgridNet (B200) runs on CUDA tensors only; there is no CPU fallback")
+        pr = self._prepare()
+        B = len(image)
+        min_size = float(net.test_image_min_size)            # eval/inference branch of transform.py:192-196
+        plan = plan_batch([tuple(im.shape[-2:]) for im in image], [int(s.shape[0]) for s in seg_indices],
+                          [int(c.shape[0]) for c in coors], int(corpus.shape[1]), min_size, float(net.image_max_size))
+        tab = torch.from_numpy(plan.table).to(dev)          # the step's only H2D besides the inputs
+        dt = {k: tab[s:s + n] for k, (s, n) in plan.offsets.items()}
+        dt["ratios"] = dt["ratios"].view(torch.float32)
+        seg_off = dt["seg_off"]
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        out = {"plan": plan, "status": status}
+
+        # a1 transform
+        batch = torch.zeros((B, plan.H, plan.W, 3), dtype=torch.float32, device=dev)
+        for b, im in enumerate(image):
+            ops.normalize_resize_pad(im.contiguous(), batch, b, plan.sizes[b][0], plan.sizes[b][1], net.image_mean, net.image_std)
+        coors_cat = torch.cat([c.reshape(-1, 4) for c in coors], 0).to(torch.int64).contiguous()
+        boxes = ops.resize_coords(coors_cat, seg_off, dt["ratios"], B)
+        out["image_batch"], out["boxes"] = batch, boxes
+
+        # a2 / a3 BERT + segment aggregation
+        hidden = self._bert(plan, dt, corpus.contiguous())
+        seg_ids = torch.cat([s.reshape(-1) for s in seg_indices], 0).to(torch.int32).contiguous()
+        seg_start = ops.segment_starts(seg_ids, dt["tok_off"], B, plan.K, status)
+        seg_emb = ops.segment_reduce(hidden, dt["tok_row"], seg_start, plan.K,
+                                     ops.AGG_MEAN if net.grid_mode == "mean" else ops.AGG_FIRST)
+        out["seg_emb"] = seg_emb
+
+        # a4 BERTgrid
+        st = net.early_fusion_downsampling_ratio
+        idx = ops.box_index_map(boxes, seg_off, B, st, int(plan.H / st), int(plan.W / st))
+        grid = ops.grid_scatter(seg_emb, idx, seg_off)
+        out["index_map"], out["bertgrid"] = idx, grid
+
+        # a5 backbone
+        p_fuse = self._backbone(batch, grid)
+        out["p_fuse"] = p_fuse
+
+        # a6 auxiliary segmentation head
+        if want_seg and net.semantic_segmentation_head is not None:
+            out["pred_mask"], out["pred_ss"] = self._seg_head(p_fuse)
+            cls_cat = torch.cat([c.reshape(-1) for c in seg_classes], 0).to(torch.int32).contiguous()
+            out["pos_neg_labels"], out["class_labels"] = ops.label_paint(boxes, seg_off, cls_cat, B, plan.H, plan.W)
+            out["gt_label"] = cls_cat
+
+        # a7 ROI align, a8 late fusion
+        roi = ops.roi_align(p_fuse, boxes, seg_off, 1.0 / float(net.p_fuse_downsampling_ratio), net.roi_shape)
+        out["roi"] = roi
+        rn = net.late_fusion_net.ROI_embedding_net
+        r = self._conv(roi, rn.conv_1, rn.bn_1, ACT_RELU)
+        r = self._conv(r, rn.conv_2, rn.bn_2, ACT_RELU)
+        roi_emb = self._lin(r.view(plan.K, -1), rn.linear, W=pr.misc["roi_fc_w"])
+        late = self._lin(roi_emb, net.late_fusion_net.fuse_embedding_net.linear, A2=seg_emb)
+        out["late"] = late
+
+        # a9 / a10 field-type head
+        head = net.field_type_classification_head
+        if net.classifier_mode == "simp":
+            logits = self._mlp_or_lin(late, head.category_classification_net)
+            out["logits"] = logits
+            out["pred_label"] = ops.softmax_rows(logits)
+            if want_seg and hasattr(head, "pos_neg_classification_net"):
+                out["pos_neg_logits"] = self._mlp_or_lin(late, head.pos_neg_classification_net)
+        elif net.classifier_mode == "crf":
+            logits = self._mlp_or_lin(late, head.category_classification_net)
+            out["logits"] = logits
+            tags, scores = ops.crf_viterbi(logits, head.crf_layer.transitions.detach().contiguous(), seg_off, B)
+            out["pred_label"], out["crf_scores"] = tags[:, None], scores
+        else:
+            pn = self._mlp_or_lin(late, head.pos_neg_classification_net.layer)
+            if "full_w" in pr.misc:
+                cl = ops.gemm(late, pr.misc["full_w"], ep=make_epilogue(None, pr.misc["full_b"]), precision=self._prec())
+            else:
+                cl = torch.cat([self._mlp_or_lin(late, getattr(head, f"category_classification_net_{i}").layer)
+                                for i in range(net.num_tokens - 1)], 1).contiguous()
+            out["pos_neg_logits"], out["logits"] = pn, cl
+            out["pred_label"] = ops.full_head_scores(pn.reshape(-1).contiguous(), cl)
+        return out

@@ -1,0 +1,257 @@
+"""Python-side operator wrappers over the C-ABI (one function per ``vbg_*`` entry).
+
+torch is used for device memory and the current stream only; every wrapper
+passes raw device pointers and sizes to ``libvbg_sm100a.so``.  Activations are
+fp32 NHWC.  Wrappers raise ``VbgError`` with the library's message on failure
+and ``TypeError`` on a tensor that is not a contiguous CUDA tensor of the
+expected dtype (no silent copies, no eager fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, AGG_FIRST, AGG_MEAN, PREC_FP32, PREC_TF32, RES_NONE, RES_SAME,
+                   RES_UP2, Epilogue, VbgError)
+
+
+def _p(t: Optional[torch.Tensor], dtype=None, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA tensor (the hot path has no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise TypeError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t, name="tensor"):
+    return _p(t, torch.float32, name)
+
+
+def _i32(t, name="tensor"):
+    return _p(t, torch.int32, name)
+
+
+def tc_available() -> bool:
+    return bool(L.load().vbg_tc_available())
+
+
+def make_epilogue(scale=None, shift=None, residual=None, res_mode=RES_NONE, ldr=0, out_h=0, out_w=0, act=ACT_NONE):
+    ep = Epilogue(_f32(scale, "scale"), _f32(shift, "shift"), _f32(residual, "residual"), res_mode, ldr, out_h, out_w, act)
+    ep._keep = (scale, shift, residual)
+    return ep
+
+
+# ------------------------------------------------------------------ a1
+def normalize_resize_pad(img_chw, batch_nhwc, b, oh, ow, mean, std):
+    _, h, w = img_chw.shape
+    B, H, W, _ = batch_nhwc.shape
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    L.check(L.load().vbg_normalize_resize_pad(_f32(img_chw, "image"), h, w, _f32(batch_nhwc), b, H, W, oh, ow, m, s,
+                                              _stream()), "vbg_normalize_resize_pad")
+
+
+def resize_coords(coors_i64, seg_off, ratios, B):
+    K = coors_i64.shape[0]
+    out = torch.empty((K, 4), dtype=torch.int32, device=coors_i64.device)
+    L.check(L.load().vbg_resize_coords(_p(coors_i64, torch.int64, "coors"), _i32(seg_off), _f32(ratios), B, K,
+                                       _i32(out), _stream()), "vbg_resize_coords")
+    return out
+
+
+# ------------------------------------------------------------------ a2
+def bert_assemble(corpus, seq_tab, cu, nseq, R):
+    ids = torch.empty(R, dtype=torch.int32, device=corpus.device)
+    pos = torch.empty(R, dtype=torch.int32, device=corpus.device)
+    L.check(L.load().vbg_bert_assemble(_p(corpus, torch.int64, "corpus"), corpus.shape[1], _i32(seq_tab), _i32(cu),
+                                       nseq, R, _i32(ids), _i32(pos), _stream()), "vbg_bert_assemble")
+    return ids, pos
+
+
+def embed_ln(ids, pos, word, position, type_emb, gamma, beta, eps):
+    R, hidden = ids.shape[0], word.shape[1]
+    out = torch.empty((R, hidden), dtype=torch.float32, device=word.device)
+    L.check(L.load().vbg_embed_ln(_i32(ids), _i32(pos), _f32(word), _f32(position), _f32(type_emb), _f32(gamma),
+                                  _f32(beta), eps, R, hidden, word.shape[0], position.shape[0], _f32(out), _stream()),
+            "vbg_embed_ln")
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out=None):
+    R, hidden = x.shape
+    out = torch.empty_like(x) if out is None else out
+    L.check(L.load().vbg_layernorm(_f32(x), _f32(gamma), _f32(beta), eps, R, hidden, _f32(out), _stream()), "vbg_layernorm")
+    return out
+
+
+def attention(qkv, cu, nseq, max_len, heads, precision=PREC_FP32):
+    R, three_h = qkv.shape
+    hidden = three_h // 3
+    out = torch.empty((R, hidden), dtype=torch.float32, device=qkv.device)
+    L.check(L.load().vbg_attention_fwd(_f32(qkv), _i32(cu), nseq, max_len, heads, hidden // heads, _f32(out), precision,
+                                       _stream()), "vbg_attention_fwd")
+    return out
+
+
+# ------------------------------------------------------------------ a3
+def segment_starts(seg_ids, tok_off, B, K, status):
+    n_tok = seg_ids.shape[0]
+    out = torch.empty(K + 1, dtype=torch.int32, device=seg_ids.device)
+    L.check(L.load().vbg_segment_starts(_i32(seg_ids), _i32(tok_off), B, n_tok, K, _i32(out), _i32(status), _stream()),
+            "vbg_segment_starts")
+    return out
+
+
+def segment_reduce(hidden, tok_row, seg_start, K, mode=AGG_MEAN):
+    Cc = hidden.shape[1]
+    out = torch.empty((K, Cc), dtype=torch.float32, device=hidden.device)
+    L.check(L.load().vbg_segment_reduce(_f32(hidden), _i32(tok_row), _i32(seg_start), K, Cc, mode, _f32(out), _stream()),
+            "vbg_segment_reduce")
+    return out
+
+
+# ------------------------------------------------------------------ a4 / a6
+def box_index_map(boxes, seg_off, B, stride, Hg, Wg):
+    idx = torch.empty((B, Hg, Wg), dtype=torch.int32, device=boxes.device)
+    L.check(L.load().vbg_box_index_map(_i32(boxes), _i32(seg_off), B, stride, Hg, Wg, _i32(idx), _stream()),
+            "vbg_box_index_map")
+    return idx
+
+
+def grid_scatter(seg_emb, idx, seg_off):
+    B, Hg, Wg = idx.shape
+    Cc = seg_emb.shape[1]
+    grid = torch.empty((B, Hg, Wg, Cc), dtype=torch.float32, device=seg_emb.device)
+    L.check(L.load().vbg_grid_scatter(_f32(seg_emb), _i32(idx), _i32(seg_off), B, Hg * Wg, Cc, _f32(grid), _stream()),
+            "vbg_grid_scatter")
+    return grid
+
+
+def label_paint(boxes, seg_off, seg_cls, B, H, W):
+    pn = torch.empty((B, H, W), dtype=torch.int64, device=boxes.device)
+    cl = torch.empty((B, H, W), dtype=torch.int64, device=boxes.device)
+    L.check(L.load().vbg_label_paint(_i32(boxes), _i32(seg_off), _i32(seg_cls), B, H, W, _p(pn), _p(cl), _stream()),
+            "vbg_label_paint")
+    return pn, cl
+
+
+# ------------------------------------------------------------------ dense contractions
+def gemm(A, W, *, A2=None, ep: Optional[Epilogue] = None, precision=PREC_FP32, N=None, K=None, ldw=None, out=None,
+         w_offset=0):
+    """C[M,N] = epilogue([A | A2] @ W[N,K]^T).  ``w_offset``/``ldw``/``N``/``K`` select a sub-block of W."""
+    M, K1 = A.shape
+    K2 = 0 if A2 is None else A2.shape[1]
+    Kt = K1 + K2 if K is None else K
+    Nn = W.shape[0] if N is None else N
+    ldw_ = W.stride(0) if ldw is None else ldw
+    if out is None:
+        out = torch.empty((M, Nn), dtype=torch.float32, device=A.device)
+    wp = _f32(W, "W") + 4 * w_offset
+    L.check(L.load().vbg_gemm(_f32(A, "A"), A.stride(0), _f32(A2, "A2"), 0 if A2 is None else A2.stride(0), K1, wp, ldw_,
+                              _f32(out, "out"), out.stride(0), M, Nn, Kt, C.byref(ep) if ep is not None else None,
+                              precision, _stream()), "vbg_gemm")
+    return out
+
+
+def conv2d(x, w_ohwi, stride, pad, *, ep: Optional[Epilogue] = None, precision=PREC_FP32):
+    B, H, W, Cin = x.shape
+    Cout, kh, kw, Cin2 = w_ohwi.shape
+    if Cin2 != Cin:
+        raise ValueError(f"conv2d: weight expects Cin={Cin2}, input has {Cin}")
+    Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+    L.check(L.load().vbg_conv2d(_f32(x, "x"), B, H, W, Cin, _f32(w_ohwi, "w"), Cout, kh, kw, stride, pad, _f32(y),
+                                C.byref(ep) if ep is not None else None, precision, _stream()), "vbg_conv2d")
+    return y
+
+
+def maxpool3x3s2(x):
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), dtype=torch.float32, device=x.device)
+    L.check(L.load().vbg_maxpool3x3s2(_f32(x), B, H, W, Cc, _f32(y), _stream()), "vbg_maxpool3x3s2")
+    return y
+
+
+def avgpool2x2(x):
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.float32, device=x.device)
+    L.check(L.load().vbg_avgpool2x2(_f32(x), B, H, W, Cc, _f32(y), _stream()), "vbg_avgpool2x2")
+    return y
+
+
+def bn_fold(bn: torch.nn.modules.batchnorm._BatchNorm):
+    Cc = bn.num_features
+    out = torch.empty((2, Cc), dtype=torch.float32, device=bn.weight.device)
+    L.check(L.load().vbg_bn_fold(_f32(bn.weight.detach()), _f32(bn.bias.detach()), _f32(bn.running_mean),
+                                 _f32(bn.running_var), bn.eps, Cc, _f32(out[0]), _f32(out[1]), _stream()), "vbg_bn_fold")
+    return out[0], out[1]
+
+
+def repack_oihw_to_ohwi(w):
+    O, I, H, W = w.shape
+    out = torch.empty((O, H, W, I), dtype=torch.float32, device=w.device)
+    L.check(L.load().vbg_repack_oihw_to_ohwi(_f32(w.detach().contiguous()), O, I, H, W, _f32(out), _stream()),
+            "vbg_repack_oihw_to_ohwi")
+    return out
+
+
+# ------------------------------------------------------------------ a7
+def roi_align(feat, boxes, seg_off, spatial_scale, P, want_grid=False):
+    B, Hf, Wf, Cc = feat.shape
+    K = boxes.shape[0]
+    out = torch.empty((K, P, P, Cc), dtype=torch.float32, device=feat.device)
+    sg = torch.empty((K, 2), dtype=torch.int32, device=feat.device) if want_grid else None
+    L.check(L.load().vbg_roi_align_fwd(_f32(feat), B, Hf, Wf, Cc, _i32(boxes), _i32(seg_off), K, spatial_scale, P,
+                                       _f32(out), _i32(sg), _stream()), "vbg_roi_align_fwd")
+    return (out, sg) if want_grid else out
+
+
+# ------------------------------------------------------------------ heads / outputs
+def softmax_rows(x):
+    y = torch.empty_like(x)
+    L.check(L.load().vbg_softmax_rows(_f32(x), x.shape[0], x.shape[1], _f32(y), _stream()), "vbg_softmax_rows")
+    return y
+
+
+def full_head_scores(pos_neg, cls):
+    R, Cm1 = cls.shape
+    out = torch.empty((R, Cm1 + 1), dtype=torch.float32, device=cls.device)
+    L.check(L.load().vbg_full_head_scores(_f32(pos_neg), _f32(cls), R, Cm1 + 1, _f32(out), _stream()), "vbg_full_head_scores")
+    return out
+
+
+def upsample_split_nchw(x, up, c_split):
+    B, h, w, Ct = x.shape
+    o1 = torch.empty((B, c_split, h * up, w * up), dtype=torch.float32, device=x.device)
+    o2 = torch.empty((B, Ct - c_split, h * up, w * up), dtype=torch.float32, device=x.device)
+    L.check(L.load().vbg_upsample_split_nchw(_f32(x), B, h, w, Ct, up, c_split, _f32(o1), _f32(o2), _stream()),
+            "vbg_upsample_split_nchw")
+    return o1, o2
+
+
+def nhwc_to_nchw(x):
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    L.check(L.load().vbg_nhwc_to_nchw(_f32(x), B, H, W, Cc, _f32(y), _stream()), "vbg_nhwc_to_nchw")
+    return y
+
+
+def crf_viterbi(feats, trans, seg_off, B):
+    K, T = feats.shape
+    tags = torch.empty(K, dtype=torch.float32, device=feats.device)
+    scores = torch.empty(B, dtype=torch.float32, device=feats.device)
+    ws = torch.empty(max(K * T, 1), dtype=torch.uint8, device=feats.device)
+    L.check(L.load().vbg_crf_viterbi(_f32(feats), _f32(trans), _i32(seg_off), B, K, T, _f32(tags), _f32(scores),
+                                     _p(ws), ws.numel(), _stream()), "vbg_crf_viterbi")
+    return tags, scores
