@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Headline benchmark: doc-images/s of the ViBERTgrid joint forward (BASELINE.json metric) on
+N B200s, one process per GPU, documents sharded across ranks (no data-path collective).
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # CPU arm: the oracle restatement of the reference on host cores
+
+Prints ONE JSON line on rank 0 (contract in the task statement / DESIGN.md section 6).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "doc_images_per_sec"
+UNIT = "images/s"
+
+
+def fwd_flops_as_executed(cfg) -> float:
+    """Forward FLOPs per image AS THE REFERENCE EXECUTES THEM: every 510-token window
+    is a full 512-row BERT pass; the fuse / seg-head 1x1 convs run at full resolution."""
+    hw = cfg.height * cfg.width / (512.0 * 512.0)
+    wn = cfg.seq_len // 510 + 1
+    bert = wn * 96.6e9 * (cfg.bert_layers / 12.0)
+    backbone = (74.2e9 if "34" in cfg.backbone else 54.9e9) * hw
+    seg = 39.7e9 * hw
+    late = cfg.segments * 0.145e9
+    return bert + backbone + seg + late
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        smax = max((float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()), default=None)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_net(cfg, device=None):
+    from vibertgrid_pytorch_b200 import synth
+    from vibertgrid_pytorch_b200.net import ViBERTgridNet
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            synth.write_bert_dir(cfg, tmp)
+            kw = synth.model_kwargs(cfg, "eval")
+            net = ViBERTgridNet(**kw)
+        finally:
+            os.chdir(cwd)
+    synth.fill_state_dict_(net, 0)
+    if device is not None:
+        net = net.to(device)
+    return net.eval(), kw
+
+
+def to_device(batch, dev, non_blocking=True):
+    return [tuple(t.to(dev, non_blocking=non_blocking) for t in x) if isinstance(x, tuple) else x.to(dev, non_blocking=non_blocking)
+            for x in batch]
+
+
+def pin(batch):
+    return [tuple(t.pin_memory() for t in x) if isinstance(x, tuple) else x.pin_memory() for x in batch]
+
+
+def nbytes(batch):
+    return sum(sum(t.numel() * t.element_size() for t in x) if isinstance(x, tuple) else x.numel() * x.element_size() for x in batch)
+
+
+def cpu_reference_arm(cfg, steps, warmup, sample_images=1):
+    """The reference's CPU path = the oracle restatement (pinned to the live reference by tests/golden),
+    all host threads, on a bounded sample: `sample_images` documents of the workload per step."""
+    import dataclasses
+    from vibertgrid_pytorch_b200 import synth
+    from oracle import oracle_net
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c1 = dataclasses.replace(cfg, batch=sample_images)
+    net, kw = build_net(c1)
+    sd = {k: v for k, v in net.state_dict().items()}
+    ocfg = oracle_net.OracleConfig(backbone=c1.backbone, classifier_mode=c1.classifier_mode, num_classes=c1.num_classes,
+                                   min_size=kw["test_image_min_size"], max_size=kw["image_max_size"])
+    times = []
+    for i in range(warmup + steps):
+        batch = synth.make_batch(c1, i)
+        t0 = time.perf_counter()
+        oracle_net.forward(sd, ocfg, *batch)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"value": sample_images * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample_images} image(s)/step of {cfg.name} ({cfg.backbone}, {cfg.height}x{cfg.width}, L={cfg.seq_len}, "
+                      f"S={cfg.segments}), {len(times)} timed forwards, fp32, eval, torch {torch.__version__} CPU",
+            "ms_per_step": 1e3 * total / len(times)}
+
+
+def time_region(fn, steps, stream_sync, world):
+    """barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def kernel_rooflines(net, cfg, dev, peaks):
+    """Live CUDA-event timings of the dominant kernels, each launched alone on this stream with an L2 flush
+    (256 MiB write) between launches.  Algorithmic bytes / FLOPs per launch: DESIGN.md section 5."""
+    from vibertgrid_pytorch_b200 import ops, _lib
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, reps=10):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    B, Hg, Wg, C, S = cfg.batch, cfg.height // 8, cfg.width // 8, 768, cfg.segments
+    K = B * S
+    g = torch.Generator().manual_seed(1)
+    from vibertgrid_pytorch_b200 import synth
+    boxes = torch.cat([synth.make_boxes(S, cfg.height, cfg.width, g) for _ in range(B)], 0).int().to(dev)
+    seg_off = torch.arange(0, K + 1, S, dtype=torch.int32, device=dev)
+    emb = torch.randn(K, C, device=dev)
+    idx = ops.box_index_map(boxes, seg_off, B, 8, Hg, Wg)
+    ms = timed(lambda: ops.grid_scatter(emb, idx, seg_off))
+    by = B * C * Hg * Wg * 4 + K * C * 4 + K * 16 + B * Hg * Wg * 4
+    out["grid_scatter"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                           "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": ms, "bytes": by}
+    Hf, Wf = cfg.height // 4, cfg.width // 4
+    feat = torch.randn(B, Hf, Wf, 256, device=dev)
+    ms = timed(lambda: ops.roi_align(feat, boxes, seg_off, 0.25, 7))
+    by = B * 256 * Hf * Wf * 4 + K * 256 * 49 * 4 + K * 20
+    out["roi_align"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": ms, "bytes": by}
+    # dominant tensor-bound kernel: the BERT FFN-up GEMM of the packed batch (M = real rows, N=3072, K=768)
+    eng = net._get_engine()
+    prec = eng._prec()
+    M = B * (cfg.seq_len + 2 * (cfg.seq_len // 510 + 1))
+    A = torch.randn(M, 768, device=dev)
+    Wt = torch.randn(3072, 768, device=dev) * 0.03
+    bias = torch.zeros(3072, device=dev)
+    ep = ops.make_epilogue(None, bias, act=ops.ACT_GELU)
+    ms = timed(lambda: ops.gemm(A, Wt, ep=ep, precision=prec))
+    fl = 2.0 * M * 3072 * 768
+    peak = peaks["tf32_tflops"] if prec == ops.PREC_TF32 else peaks["fp32_simt_tflops"]
+    out["gemm_ffn_up"] = {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
+                          "frac": fl / ms / 1e9 / peak, "traffic": None, "ms": ms, "flops": fl,
+                          "path": "tcgen05 kind::tf32" if prec == ops.PREC_TF32 else "CUDA-core fp32 FFMA",
+                          "shape": [M, 3072, 768]}
+    return out
+
+
+def measured_peaks(dev):
+    """MEASURED_PEAKS.json (driver-written) + a live cuBLAS TF32 / fp32 GEMM measured the same way
+    (library call used ONLY as the roofline denominator, never on the hot path)."""
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            j = json.load(f)
+        peaks.update(hbm_gbs=j["hbm_gbs"], bf16_tflops=j["bf16_tflops"], bf16_tflops_sustained=j.get("bf16_tflops_sustained"),
+                     source="measured (MEASURED_PEAKS.json)")
+    n = 8192
+    a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+    best = {}
+    for name, allow in (("tf32_tflops", True), ("fp32_simt_tflops", False)):
+        torch.backends.cuda.matmul.allow_tf32 = allow
+        torch.matmul(a, b)
+        torch.cuda.synchronize()
+        t = []
+        for _ in range(5 if allow else 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, b); e1.record()
+            torch.cuda.synchronize()
+            t.append(e0.elapsed_time(e1))
+        best[name] = 2.0 * n ** 3 / min(t) / 1e9
+    torch.backends.cuda.matmul.allow_tf32 = False
+    peaks.update(best)
+    peaks["tf32_how"] = "torch.matmul fp32 8192^3 with allow_tf32 (cuBLAS), best of 5, this run"
+    return peaks
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    from vibertgrid_pytorch_b200 import synth
+    cfg = synth.CONFIGS[args.config]
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    workload = (f"{cfg.name}: eval-mode joint forward, {cfg.backbone} + bert-base({cfg.bert_layers}L), batch {cfg.batch}/GPU, "
+                f"{cfg.height}x{cfg.width} images, L={cfg.seq_len} tokens, S={cfg.segments} boxes, {cfg.classifier_mode} head")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_arm(cfg, max(args.steps, 1), args.warmup)
+        line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "impl": "reference",
+                "config": {"workload": workload, "arm": "CPU restatement of the reference forward (oracle/), pinned to the live reference by tests/golden"},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from vibertgrid_pytorch_b200 import _lib, ops
+    if args.precision:
+        os.environ["VBG_PRECISION"] = args.precision
+    net, kw = build_net(cfg, dev)
+    eng = net._get_engine()
+    prec = eng._prec()
+
+    n_rot = 4      # rotate distinct documents; weights (0.6 GB) + activations exceed the 126 MB L2 anyway
+    host = [pin(synth.make_batch(cfg, 1000 * rank + i)) for i in range(n_rot)]
+    resident = [to_device(b, dev, False) for b in host]
+    torch.cuda.synchronize()
+
+    def step_resident(i):
+        net(*resident[i % n_rot])
+
+    sink = {}
+
+    def step_e2e(i):
+        batch = to_device(host[i % n_rot], dev, True)
+        loss, pm, ps, gt, pred = net(*batch)
+        sink["pred"] = pred.cpu()               # D2H of the step's result (+ loss)
+        sink["loss"] = loss.detach().cpu()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    c0 = _lib.launch_count
+    ms = time_region(step_resident, args.steps, True, world)
+    launches = _lib.launch_count - c0
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = time_region(step_e2e, args.steps, True, world)
+    clocks = sampler.stop() if sampler else None
+
+    imgs = cfg.batch * args.steps * world
+    value = imgs / (ms / 1e3)
+    e2e = imgs / (ms_e2e / 1e3)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32" if prec == ops.PREC_TF32 else "f32", "data": "synthetic",
+            "config": {"workload": workload, "global_batch": cfg.batch * world, "parallelism": f"dp{world} (documents sharded, no data-path collective)",
+                       "l2": "working set (605 MB weights + activations) >> 126 MB L2; 4 input batches rotated",
+                       "scope_note": "forward only (eval mode): the training backward is not built yet (DESIGN.md section 7)"},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": nbytes(host[0]),
+                    "d2h_bytes_per_step": int(sink["pred"].numel() * 4 + sink["loss"].numel() * sink["loss"].element_size())},
+            "gpu_launches": launches, "clocks": clocks}
+    if rank == 0:
+        fl = fwd_flops_as_executed(cfg)
+        line["fwd_tflops_as_executed"] = fl * cfg.batch * args.steps / (ms / 1e3) / 1e12
+        if not args.no_roofline:
+            peaks = measured_peaks(dev)
+            kr = kernel_rooflines(net, cfg, dev, peaks)
+            line["roofline"] = kr["gemm_ffn_up"]
+            line["roofline_hbm_kernels"] = {k: kr[k] for k in ("grid_scatter", "roi_align")}
+            line["peaks"] = peaks
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_arm(cfg, 3, 1).items() if k != "ms_per_step"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

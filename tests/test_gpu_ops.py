@@ -1,0 +1,211 @@
+"""Per-kernel parity: each C-ABI entry point against the oracle (numpy) or a plain
+torch fp32 CPU computation of the same op, on seeded inputs.  Integer outputs are
+compared bit-exactly; fp32 outputs to the tolerance written in each test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import relerr
+
+from oracle import oracle_ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from vibertgrid_pytorch_b200 import ops as o
+    assert torch.cuda.is_available()
+    return o
+
+
+def _boxes(rng, S, H, W, tail=True):
+    l = rng.integers(0, W - 2, S); t = rng.integers(0, H - 2, S)
+    r = np.minimum(l + rng.integers(1, W // 2, S), W - 1); b = np.minimum(t + rng.integers(1, H // 3, S), H - 1)
+    bx = np.stack([l, t, r, b], 1).astype(np.int32)
+    if tail and S > 4:
+        bx[1] = [5, 5, 5, 9]          # empty slice
+        bx[2] = [0, 0, W + 40, H + 9]  # clipped by the array end
+        bx[3] = [9, 9, 3, 3]          # inverted -> empty
+    return bx
+
+
+def _dev_off(counts):
+    off = np.zeros(len(counts) + 1, np.int32); off[1:] = np.cumsum(counts)
+    return off, torch.from_numpy(off).cuda()
+
+
+@pytest.mark.parametrize("stride,H,W,counts", [(8, 512, 512, [128, 97]), (8, 96, 160, [9, 0, 300]), (4, 64, 64, [5]), (1, 96, 128, [40, 1])])
+def test_box_index_map_bit_exact(ops, stride, H, W, counts):
+    rng = np.random.default_rng(1)
+    per = [_boxes(rng, c, H, W) for c in counts]
+    off, doff = _dev_off(counts)
+    boxes = torch.from_numpy(np.concatenate(per + [np.zeros((0, 4), np.int32)], 0)).cuda()
+    if boxes.shape[0] == 0:
+        boxes = torch.zeros((1, 4), dtype=torch.int32).cuda()
+    idx = ops.box_index_map(boxes, doff, len(counts), stride, H // stride, W // stride)
+    assert np.array_equal(idx.cpu().numpy(), oracle_ops.box_index_map(per, H, W, stride))
+
+
+def test_scatter_and_label_paint(ops):
+    rng = np.random.default_rng(2)
+    H, W, counts, C = 128, 192, [33, 20], 768
+    per = [_boxes(rng, c, H, W) for c in counts]
+    off, doff = _dev_off(counts)
+    boxes = torch.from_numpy(np.concatenate(per, 0)).cuda()
+    emb = torch.randn(sum(counts), C)
+    idx = ops.box_index_map(boxes, doff, 2, 8, H // 8, W // 8)
+    grid = ops.grid_scatter(emb.cuda(), idx, doff)
+    want = oracle_ops.scatter_grid([emb[off[b]:off[b + 1]].numpy() for b in range(2)], idx.cpu().numpy())
+    assert np.array_equal(grid.permute(0, 3, 1, 2).cpu().numpy(), want)            # pure copy: bit-exact
+    cls = [rng.integers(0, 5, c).astype(np.int32) for c in counts]
+    pn, cl = ops.label_paint(boxes, doff, torch.from_numpy(np.concatenate(cls)).cuda(), 2, H, W)
+    wpn, wcl = oracle_ops.paint_labels(oracle_ops.box_index_map(per, H, W, 1), cls)
+    assert np.array_equal(pn.cpu().numpy(), wpn) and np.array_equal(cl.cpu().numpy(), wcl)
+
+
+@pytest.mark.parametrize("mode", ["mean", "first"])
+def test_segment_aggregate_bit_exact(ops, mode):
+    rng = np.random.default_rng(3)
+    ntoks, C = [37, 1, 300], 768
+    seg, runs = [], []
+    for n in ntoks:
+        ids = np.sort(rng.integers(0, max(2, n // 3), n)).astype(np.int32)
+        seg.append(ids); runs.append(len(oracle_ops.segment_runs(ids)) - 1)
+    hidden = torch.randn(sum(ntoks) + 11, C)
+    tok_row = torch.from_numpy(rng.permutation(sum(ntoks) + 11)[:sum(ntoks)].astype(np.int32))
+    toff, dtoff = _dev_off(ntoks)
+    K = sum(runs)
+    status = torch.zeros(1, dtype=torch.int32).cuda()
+    starts = ops.segment_starts(torch.from_numpy(np.concatenate(seg)).cuda(), dtoff, 3, K, status)
+    out = ops.segment_reduce(hidden.cuda(), tok_row.cuda(), starts, K, ops.AGG_MEAN if mode == "mean" else ops.AGG_FIRST)
+    assert int(status.item()) == 0
+    want = np.concatenate([oracle_ops.segment_aggregate(hidden[tok_row[toff[b]:toff[b + 1]].long()].numpy(), seg[b], mode) for b in range(3)], 0)
+    assert np.array_equal(out.cpu().numpy(), want)          # sequential fp32 sum + one divide: bit-exact
+    # run-count mismatch is flagged like the reference's assert (BERTgrid_generator.py:233)
+    ops.segment_starts(torch.from_numpy(np.concatenate(seg)).cuda(), dtoff, 3, K + 1, status)
+    assert int(status.item()) == 1
+
+
+def test_roi_align_matches_oracle(ops):
+    rng = np.random.default_rng(4)
+    B, Hf, Wf, C = 2, 32, 48, 256
+    feat = torch.randn(B, C, Hf, Wf)
+    counts = [9, 6]
+    per = [_boxes(rng, c, Hf * 4, Wf * 4, tail=False) for c in counts]
+    per[0][0] = [0, 0, Wf * 4 - 1, Hf * 4 - 1]     # full page -> large adaptive grid
+    per[0][1] = [10, 10, 10, 10]                   # zero size -> clamped to 1
+    per[1][0] = [Wf * 4 - 3, Hf * 4 - 3, Wf * 4 + 30, Hf * 4 + 30]   # runs off the map
+    off, doff = _dev_off(counts)
+    boxes = np.concatenate(per, 0)
+    out, sg = ops.roi_align(feat.permute(0, 2, 3, 1).contiguous().cuda(), torch.from_numpy(boxes).cuda(), doff, 0.25, 7, want_grid=True)
+    bidx = np.concatenate([np.full(c, b, np.int32) for b, c in enumerate(counts)])
+    want, grids = oracle_ops.roi_align(feat.numpy(), boxes.astype(np.float32), bidx, 0.25, 7)
+    assert np.array_equal(sg.cpu().numpy(), grids)                                   # sample grid: bit-exact
+    assert relerr(out.permute(0, 3, 1, 2).cpu().numpy(), want) < 1e-5               # values: <= 1e-5 rel
+
+
+def test_transform_kernels(ops):
+    g = torch.Generator().manual_seed(5)
+    mean, std = [0.9248, 0.9224, 0.9215], [0.1532, 0.1545, 0.1536]
+    for (h, w), (oh, ow) in [((64, 96), (64, 96)), ((85, 107), (96, 120)), ((333, 777), (342, 800))]:
+        img = torch.rand(3, h, w, generator=g)
+        H, W = ((oh + 31) // 32) * 32, ((ow + 31) // 32) * 32
+        batch = torch.zeros(1, H, W, 3).cuda()
+        ops.normalize_resize_pad(img.cuda(), batch, 0, oh, ow, mean, std)
+        x = (img - torch.tensor(mean)[:, None, None]) / torch.tensor(std)[:, None, None]
+        x = F.interpolate(x[None], size=(oh, ow), mode="bilinear", align_corners=False)[0]
+        want = torch.zeros(3, H, W); want[:, :oh, :ow] = x
+        assert relerr(batch[0].permute(2, 0, 1).cpu().numpy(), want.numpy()) < 2e-6
+    coors = torch.tensor([[100, 50, 300, 150], [0, 0, 776, 332], [5, 7, 9, 11]], dtype=torch.int64)
+    nh, nw = oracle_ops.resized_shape(333, 777, oracle_ops.resize_scale(333, 777, 512, 800))
+    ratios = torch.tensor([[nh / 333, nw / 777]], dtype=torch.float32)
+    got = ops.resize_coords(coors.cuda(), torch.tensor([0, 3], dtype=torch.int32).cuda(), ratios.cuda(), 1)
+    assert np.array_equal(got.cpu().numpy(), oracle_ops.resize_coords(coors.numpy(), (333, 777), (nh, nw)))
+    assert got.cpu().numpy()[0].tolist() == [102, 51, 308, 154]                       # SURVEY A.1 known answer
+
+
+@pytest.mark.parametrize("M,N,K,K1", [(300, 768, 768, 768), (4100, 3072, 768, 768), (128, 1024, 1792, 1024), (257, 5, 512, 512), (64, 2, 1024, 1024), (1000, 130, 36, 36)])
+def test_gemm_fp32(ops, M, N, K, K1):
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g); Wt = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g); res = torch.randn(M, N, generator=g)
+    want = F.gelu(A @ Wt.t() + bias + res)
+    a1, a2 = A[:, :K1].contiguous().cuda(), (A[:, K1:].contiguous().cuda() if K1 < K else None)
+    ep = ops.make_epilogue(None, bias.cuda(), res.cuda(), ops.RES_SAME, ldr=N, act=ops.ACT_GELU)
+    got = ops.gemm(a1, Wt.cuda(), A2=a2, ep=ep, precision=ops.PREC_FP32)
+    assert relerr(got.cpu().numpy(), want.numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(2, 32, 48, 64, 64, 3, 1, 1), (1, 64, 64, 3, 64, 7, 2, 3), (2, 16, 16, 128, 256, 3, 2, 1),
+                                                 (2, 16, 24, 64, 128, 1, 2, 0), (9, 7, 7, 256, 256, 3, 1, 1)])
+def test_conv2d_fp32(ops, B, H, W, Cin, Cout, k, s, p):
+    g = torch.Generator().manual_seed(Cin + Cout + k)
+    x = torch.randn(B, Cin, H, W, generator=g); w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5; shift = torch.randn(Cout, generator=g)
+    want = F.relu(F.conv2d(x, w, None, s, p) * scale[None, :, None, None] + shift[None, :, None, None])
+    w_ohwi = ops.repack_oihw_to_ohwi(w.cuda())
+    assert torch.equal(w_ohwi.cpu(), w.permute(0, 2, 3, 1).contiguous())
+    ep = ops.make_epilogue(scale.cuda(), shift.cuda(), act=ops.ACT_RELU)
+    got = ops.conv2d(x.permute(0, 2, 3, 1).contiguous().cuda(), w_ohwi, s, p, ep=ep, precision=ops.PREC_FP32)
+    assert relerr(got.permute(0, 3, 1, 2).cpu().numpy(), want.numpy()) < 2e-6
+
+
+def test_upsample_residual_epilogue_and_pools(ops):
+    g = torch.Generator().manual_seed(7)
+    B, H, W, Cin, N = 2, 8, 12, 64, 256
+    x = torch.randn(B, H, W, Cin, generator=g); Wt = torch.randn(N, Cin, generator=g) / 8
+    small = torch.randn(B, H // 2, W // 2, N, generator=g)
+    want = x.reshape(-1, Cin) @ Wt.t() + small.repeat_interleave(2, 1).repeat_interleave(2, 2).reshape(-1, N)
+    ep = ops.make_epilogue(residual=small.cuda(), res_mode=ops.RES_UP2, out_h=H, out_w=W)
+    got = ops.gemm(x.reshape(-1, Cin).cuda(), Wt.cuda(), ep=ep)
+    assert relerr(got.cpu().numpy(), want.numpy()) < 2e-6
+    y = torch.randn(2, 17, 23, 64, generator=g)
+    assert torch.equal(ops.maxpool3x3s2(y.cuda()).cpu(), F.max_pool2d(y.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1))
+    z = torch.randn(2, 16, 24, 64, generator=g)
+    assert relerr(ops.avgpool2x2(z.cuda()).cpu().numpy(), F.avg_pool2d(z.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).numpy()) < 1e-6
+    lg = torch.randn(2, 6, 5, 8, generator=g)
+    o1, o2 = ops.upsample_split_nchw(lg.cuda(), 4, 3)
+    up = lg.permute(0, 3, 1, 2).repeat_interleave(4, 2).repeat_interleave(4, 3)
+    assert torch.equal(o1.cpu(), up[:, :3]) and torch.equal(o2.cpu(), up[:, 3:])
+    assert torch.equal(ops.nhwc_to_nchw(z.cuda()).cpu(), z.permute(0, 3, 1, 2))
+
+
+def test_bert_kernels(ops):
+    g = torch.Generator().manual_seed(8)
+    hid, heads = 768, 12
+    lens = [512, 4, 77, 130]
+    cu = np.zeros(len(lens) + 1, np.int32); cu[1:] = np.cumsum(lens)
+    R = int(cu[-1])
+    qkv = torch.randn(R, 3 * hid, generator=g)
+    got = ops.attention(qkv.cuda(), torch.from_numpy(cu).cuda(), len(lens), max(lens), heads)
+    want = torch.empty(R, hid)
+    for q in range(len(lens)):
+        a, b = cu[q], cu[q + 1]
+        Q, K, V = [qkv[a:b, i * hid:(i + 1) * hid].reshape(b - a, heads, 64).transpose(0, 1) for i in range(3)]
+        want[a:b] = ((Q @ K.transpose(-1, -2) / 8).softmax(-1) @ V).transpose(0, 1).reshape(b - a, hid)
+    assert relerr(got.cpu().numpy(), want.numpy()) < 5e-6
+    x = torch.randn(333, hid, generator=g) * 3 + 1
+    gam, bet = torch.rand(hid, generator=g) + 0.5, torch.randn(hid, generator=g)
+    assert relerr(ops.layernorm(x.cuda(), gam.cuda(), bet.cuda(), 1e-12).cpu().numpy(), F.layer_norm(x, (hid,), gam, bet, 1e-12).numpy()) < 2e-6
+    word, posw, typ = torch.randn(500, hid, generator=g), torch.randn(512, hid, generator=g), torch.randn(2, hid, generator=g)
+    ids = torch.randint(0, 500, (97,), generator=g).int(); pos = torch.randint(0, 512, (97,), generator=g).int()
+    got = ops.embed_ln(ids.cuda(), pos.cuda(), word.cuda(), posw.cuda(), typ[0].contiguous().cuda(), gam.cuda(), bet.cuda(), 1e-12)
+    want = F.layer_norm(word[ids.long()] + typ[0] + posw[pos.long()], (hid,), gam, bet, 1e-12)
+    assert relerr(got.cpu().numpy(), want.numpy()) < 2e-6
+    lg = torch.randn(130, 5, generator=g) * 4
+    assert relerr(ops.softmax_rows(lg.cuda()).cpu().numpy(), lg.softmax(1).numpy()) < 2e-6
+
+
+def test_crf_viterbi_matches_oracle(ops):
+    g = torch.Generator().manual_seed(9)
+    T, counts = 7, [40, 1, 13]
+    feats = torch.randn(sum(counts), T, generator=g)
+    trans = torch.randn(T, T, generator=g); trans[T - 2, :] = -10000; trans[:, T - 1] = -10000
+    off, doff = _dev_off(counts)
+    tags, scores = ops.crf_viterbi(feats.cuda(), trans.cuda(), doff, 3)
+    for b in range(3):
+        s, path = oracle_ops.crf_viterbi(feats[off[b]:off[b + 1]].numpy(), trans.numpy(), T - 2, T - 1)
+        assert tags[off[b]:off[b + 1]].cpu().numpy().astype(int).tolist() == path
+        assert abs(float(scores[b]) - s) < 1e-3
