@@ -138,6 +138,47 @@ def test_gemm_fp32(ops, M, N, K, K1):
     assert relerr(got.cpu().numpy(), want.numpy()) < 2e-6
 
 
+def _trunc_tf32(x):
+    """What kind::tf32 sees: the low 13 mantissa bits of each fp32 operand are ignored."""
+    return (x.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M,N,K,K1", [(128, 64, 32, 32), (300, 768, 768, 768), (4100, 3072, 768, 768), (128, 1024, 1792, 1024),
+                                      (1000, 136, 64, 64), (77, 64, 96, 32), (4096, 128, 896, 128), (257, 5, 512, 512)])
+def test_gemm_tf32_tensor_core(ops, M, N, K, K1):
+    """tcgen05 path: exact against a float64 product of TF32-truncated operands (proves the tiling /
+    descriptors / epilogue), and within 2e-3 of the fp32 product (the precision the mode trades)."""
+    if not ops.tc_available():
+        pytest.fail("tcgen05 path unavailable on this GPU box: " + __import__("vibertgrid_pytorch_b200")._lib.last_error())
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g); Wt = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g); res = torch.randn(M, N, generator=g)
+    a1, a2 = A[:, :K1].contiguous().cuda(), (A[:, K1:].contiguous().cuda() if K1 < K else None)
+    ep = ops.make_epilogue(None, bias.cuda(), res.cuda(), ops.RES_SAME, ldr=N, act=ops.ACT_GELU)
+    got = ops.gemm(a1, Wt.cuda(), A2=a2, ep=ep, precision=ops.PREC_TF32).cpu()
+    want_t = F.gelu(_trunc_tf32(A).double() @ _trunc_tf32(Wt).double().t() + bias + res)
+    want = F.gelu(A.double() @ Wt.double().t() + bias + res)
+    if N >= 64:      # smaller N is served by the fp32 CUDA-core kernel
+        assert relerr(got.numpy(), want_t.numpy()) < 5e-6
+    assert relerr(got.numpy(), want.numpy()) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,p", [(2, 32, 48, 64, 64, 3, 1), (3, 16, 16, 512, 512, 3, 1), (9, 7, 7, 256, 256, 3, 1),
+                                               (2, 20, 12, 64, 128, 3, 1), (1, 128, 128, 64, 256, 3, 1), (2, 8, 8, 128, 64, 1, 0)])
+def test_conv2d_tf32_tensor_core(ops, B, H, W, Cin, Cout, k, p):
+    if not ops.tc_available():
+        pytest.fail("tcgen05 path unavailable on this GPU box")
+    g = torch.Generator().manual_seed(Cin + Cout + H)
+    x = torch.randn(B, Cin, H, W, generator=g); w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5; shift = torch.randn(Cout, generator=g)
+    res = torch.randn(B, Cout, H, W, generator=g)
+    conv = F.conv2d(_trunc_tf32(x).double(), _trunc_tf32(w).double(), None, 1, p)
+    want_t = F.relu(conv * scale[None, :, None, None] + shift[None, :, None, None] + res)
+    ep = ops.make_epilogue(scale.cuda(), shift.cuda(), res.permute(0, 2, 3, 1).contiguous().cuda(), ops.RES_SAME, ldr=Cout, act=ops.ACT_RELU)
+    got = ops.conv2d(x.permute(0, 2, 3, 1).contiguous().cuda(), ops.repack_oihw_to_ohwi(w.cuda()), 1, p, ep=ep, precision=ops.PREC_TF32)
+    assert relerr(got.permute(0, 3, 1, 2).cpu().numpy(), want_t.numpy()) < 5e-6
+
+
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(2, 32, 48, 64, 64, 3, 1, 1), (1, 64, 64, 3, 64, 7, 2, 3), (2, 16, 16, 128, 256, 3, 2, 1),
                                                  (2, 16, 24, 64, 128, 1, 2, 0), (9, 7, 7, 256, 256, 3, 1, 1)])
 def test_conv2d_fp32(ops, B, H, W, Cin, Cout, k, s, p):

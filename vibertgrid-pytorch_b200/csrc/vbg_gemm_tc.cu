@@ -21,6 +21,7 @@
 // VBG_EUNSUPPORTED and the dispatcher uses the fp32 CUDA-core kernel (vbg_gemm_simt.cu).
 #include "vbg_common.cuh"
 #include <cuda.h>
+#include <dlfcn.h>
 #include <mutex>
 
 namespace vbg {
@@ -272,14 +273,31 @@ static std::mutex g_tc_mu;
 bool tc_available() {
   std::lock_guard<std::mutex> lk(g_tc_mu);
   if (g_tc_state >= 0) return g_tc_state == 1;
-  g_tc_state = 0;
   int dev = 0, major = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return false; }
-  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess || major != 10) { cudaGetLastError(); return false; }
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { cudaGetLastError(); set_error("tcgen05 path: cudaGetDevice: %s", cudaGetErrorString(e)); return false; }  // not cached
+  g_tc_state = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess || major != 10) {
+    cudaGetLastError();
+    set_error("tcgen05 path: device %d has compute capability major %d (sm_100a required)", dev, major);
+    return false;
+  }
   void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
-      qres != cudaDriverEntryPointSuccess) { cudaGetLastError(); return false; }
+  cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+  e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    fn = nullptr;
+    // fall back to the driver library itself
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (h) fn = dlsym(h, "cuTensorMapEncodeTiled");
+    if (!fn) {
+      set_error("tcgen05 path: cuTensorMapEncodeTiled not found (cudaGetDriverEntryPoint: %s, query result %d)",
+                cudaGetErrorString(e), (int)qres);
+      return false;
+    }
+  }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   g_tc_state = 1;
   return true;
