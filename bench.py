@@ -200,12 +200,17 @@ def kernel_rooflines(net, cfg, dev, peaks):
     Wt = torch.randn(3072, 768, device=dev) * 0.03
     bias = torch.zeros(3072, device=dev)
     ep = ops.make_epilogue(None, bias, act=ops.ACT_GELU)
-    ms = timed(lambda: ops.gemm(A, Wt, ep=ep, precision=prec))
+    Ws = ops.split_bf16(Wt) if prec == ops.PREC_BF16X3 else None
+    ms = timed(lambda: ops.gemm(A, Wt, ep=ep, precision=prec, W_split=Ws))
     fl = 2.0 * M * 3072 * 768
-    peak = peaks["tf32_tflops"] if prec == ops.PREC_TF32 else peaks["fp32_simt_tflops"]
+    # bf16x3: every fp32-equivalent product costs three bf16 tensor-core products, so the mode's ceiling is bf16 peak / 3
+    peak, path = {ops.PREC_TF32: (peaks["tf32_tflops"], "tcgen05 kind::tf32 (measured cuBLAS TF32 peak)"),
+                  ops.PREC_BF16X3: (peaks["bf16_tflops"] / 3.0, "tcgen05 kind::f16, 3 bf16 products per fp32-equivalent product; "
+                                                                  "peak = measured bf16 peak / 3; frac == tensor-pipe share of bf16 peak"),
+                  ops.PREC_FP32: (peaks["fp32_simt_tflops"], "CUDA-core fp32 FFMA")}[prec]
     out["gemm_ffn_up"] = {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
-                          "frac": fl / ms / 1e9 / peak, "traffic": None, "ms": ms, "flops": fl,
-                          "path": "tcgen05 kind::tf32" if prec == ops.PREC_TF32 else "CUDA-core fp32 FFMA",
+                          "frac": fl / ms / 1e9 / peak, "traffic": None, "ms": ms, "flops": fl, "path": path,
+                          "executed_tensor_tflops": (3.0 if prec == ops.PREC_BF16X3 else 1.0) * fl / ms / 1e9,
                           "shape": [M, 3072, 768]}
     return out
 
@@ -247,7 +252,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2")
-    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32"])
+    ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
@@ -319,7 +324,8 @@ def main():
     e2e = imgs / (ms_e2e / 1e3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32" if prec == ops.PREC_TF32 else "f32", "data": "synthetic",
+            "dtype": {ops.PREC_TF32: "tf32", ops.PREC_BF16X3: "bf16x3 (hi/lo split, f32 accumulate)", ops.PREC_FP32: "f32"}[prec],
+            "data": "synthetic",
             "config": {"workload": workload, "global_batch": cfg.batch * world, "parallelism": f"dp{world} (documents sharded, no data-path collective)",
                        "l2": "working set (605 MB weights + activations) >> 126 MB L2; 4 input batches rotated",
                        "scope_note": "forward only (eval mode): the training backward is not built yet (DESIGN.md section 7)"},

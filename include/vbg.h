@@ -37,8 +37,10 @@ extern "C" {
 enum { VBG_OK = 0, VBG_EINVAL = -1, VBG_ECUDA = -2, VBG_EUNSUPPORTED = -3, VBG_EWORKSPACE = -4 };
 
 /* arithmetic path of the dense contractions */
-enum { VBG_PREC_FP32 = 0,  /* CUDA-core FFMA, fp32 operands and accumulate            */
-       VBG_PREC_TF32 = 1   /* tcgen05.mma kind::tf32, TMA-fed, TMEM fp32 accumulators  */ };
+enum { VBG_PREC_FP32 = 0,   /* CUDA-core FFMA, fp32 operands and accumulate                                   */
+       VBG_PREC_TF32 = 1,   /* tcgen05.mma kind::tf32 (operands truncated to 10-bit mantissa): fast, ~5e-3 fwd  */
+       VBG_PREC_BF16X3 = 2  /* 3 x tcgen05.mma kind::f16 on bf16 hi/lo splits, fp32 accumulate: fp32-class, the
+                               parity-grade tensor-core mode (needs the split weights of vbg_split_bf16)       */ };
 
 enum { VBG_ACT_NONE = 0, VBG_ACT_RELU = 1, VBG_ACT_GELU = 2 /* erf form, as HF "gelu" */ };
 enum { VBG_RES_NONE = 0, VBG_RES_SAME = 1, /* residual[m*ldr + n]                                  */
@@ -73,7 +75,8 @@ VBG_API int vbg_tc_available(void);
 /* ---- a1: GeneralizedViBERTgridTransform (pipeline/transform.py:104-171, 225-312) ---------- */
 /* One source image [3,h,w] (CHW, [0,1]) -> normalised, bilinearly resized to (oh,ow)
  * (align_corners=False, scale = in/out as F.interpolate(recompute_scale_factor=True) uses),
- * written into sample b of the zero-initialised NHWC batch [B,H,W,3].                          */
+ * written into sample b of the zero-initialised batch [B, H+6, W+6, 4]: NHWC with a 4th zero channel and a
+ * 3-pixel zero border (= the stem conv's padding), pixel (y,x) at [b, y+3, x+3, :].            */
 VBG_API int vbg_normalize_resize_pad(const float* img_chw, int h, int w, float* batch_nhwc, int b, int H, int W,
                              int oh, int ow, const float* h_mean3, const float* h_std3, vbg_stream_t stream);
 /* coords int64 [K,4] (l,t,r,b) -> int32 [K,4]: cols 0,2 *= ratio[b][0] (height ratio), cols 1,3 *= ratio[b][1]
@@ -120,11 +123,23 @@ VBG_API int vbg_label_paint(const int32_t* boxes, const int32_t* seg_off, const 
 /* C[M,N] = epilogue( [A | A2][M,K] * W[N,K]^T ).  A supplies columns [0,K1), A2 (may be NULL when
  * K1 == K) columns [K1,K): the torch.cat-free form of ResNetFPN_ViBERTgrid.py:317-318 and
  * field_type_classification_head.py:185-188.                                                     */
-VBG_API int vbg_gemm(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int ldw, float* C, int ldc,
-             int M, int N, int K, const vbg_epilogue_t* ep, int precision, vbg_stream_t stream);
+/* W_split (may be NULL unless precision == VBG_PREC_BF16X3): bf16 hi plane of vbg_split_bf16(W), same [N, ldw]
+ * geometry as W; the lo plane starts split_plane ELEMENTS after it.                                  */
+VBG_API int vbg_gemm(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int ldw, const void* W_split,
+             long long split_plane, float* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep, int precision,
+             vbg_stream_t stream);
 /* NHWC convolution as implicit GEMM: y[B,Ho,Wo,Cout] = epilogue(conv(x[B,H,W,Cin], w[Cout,kh,kw,Cin])) */
-VBG_API int vbg_conv2d(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int kh, int kw, int stride,
-               int pad, float* y, const vbg_epilogue_t* ep, int precision, vbg_stream_t stream);
+VBG_API int vbg_conv2d(const float* x, int B, int H, int W, int Cin, const float* w, const void* w_split, long long split_plane,
+               int Cout, int kh, int kw, int stride, int pad, float* y, const vbg_epilogue_t* ep, int precision,
+               vbg_stream_t stream);
+/* bf16 hi/lo split of n fp32 values: hi = bf16_rn(w), lo = bf16_rn(w - hi)  (one-time weight preparation) */
+VBG_API int vbg_split_bf16(const float* w, long long n, void* hi, void* lo, vbg_stream_t stream);
+/* ResNet stem (7x7, stride 2, pad 3, 3->Cout; model/ResNetFPN_ViBERTgrid.py:351-361 / torchvision conv1) over the
+ * padded NHWC4 batch of vbg_normalize_resize_pad.  w_ohwi4 [Cout,7,7,4] feeds the CUDA-core path; w_split
+ * (bf16 planes of the [Cout,256] operand from vbg_stem_pack_weights) the tensor-core path.            */
+VBG_API int vbg_stem_conv(const float* x4, int B, int H, int W, const float* w_ohwi4, const void* w_split, long long split_plane,
+                  int Cout, float* y, const vbg_epilogue_t* ep, int precision, vbg_stream_t stream);
+VBG_API int vbg_stem_pack_weights(const float* w_oihw, int Cout, float* w_ohwi4, float* w_k256, vbg_stream_t stream);
 VBG_API int vbg_maxpool3x3s2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream);
 VBG_API int vbg_avgpool2x2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream);
 /* eval-mode BatchNorm folded to y = x*scale + shift */

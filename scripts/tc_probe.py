@@ -115,12 +115,34 @@ def main():
         bias = torch.zeros(N, device=dev)
         ep = ops.make_epilogue(None, bias)
         out = torch.empty(M, N, device=dev)
+        Ws = ops.split_bf16(Wm)
         ms = timed(lambda: ops.gemm(A, Wm, ep=ep, precision=ops.PREC_TF32, out=out), 10)
+        ms3 = timed(lambda: ops.gemm(A, Wm, ep=ep, precision=ops.PREC_BF16X3, out=out, W_split=Ws), 10)
+        e3 = rel(out, A.double() @ Wm.double().t()) if M * N * K < 4e11 else float("nan")
         torch.backends.cuda.matmul.allow_tf32 = True
         ms_lib = timed(lambda: torch.matmul(A, Wm.t()), 10)
         torch.backends.cuda.matmul.allow_tf32 = False
         fl = 2.0 * M * N * K
-        print(f"[gemm {M}x{N}x{K}] ours {ms*1e3:8.1f} us {fl/ms/1e9:7.1f} TF/s | cuBLAS tf32 {ms_lib*1e3:8.1f} us {fl/ms_lib/1e9:7.1f} TF/s")
+        print(f"[gemm {M}x{N}x{K}] tf32 {ms*1e3:8.1f} us {fl/ms/1e9:7.1f} TF/s | bf16x3 {ms3*1e3:8.1f} us {fl/ms3/1e9:7.1f} TF/s (err {e3:.1e}) | "
+              f"cuBLAS tf32 {ms_lib*1e3:8.1f} us {fl/ms_lib/1e9:7.1f} TF/s")
+    # 6. conv shapes of the backbone / heads in bf16x3
+    for (B, H, W, Cin, Cout, k, s, p) in [(8, 128, 128, 64, 64, 3, 1, 1), (8, 64, 64, 128, 128, 3, 1, 1), (8, 32, 32, 256, 256, 3, 1, 1),
+                                          (8, 16, 16, 512, 512, 3, 1, 1), (8, 128, 128, 256, 256, 3, 1, 1), (1024, 7, 7, 256, 256, 3, 1, 1),
+                                          (8, 128, 128, 64, 128, 3, 2, 1), (8, 64, 64, 128, 256, 3, 2, 1), (8, 32, 32, 256, 512, 3, 2, 1)]:
+        x = torch.randn(B, H, W, Cin, device=dev); w = torch.randn(Cout, k, k, Cin, device=dev) / (Cin * k * k) ** 0.5
+        ws = ops.split_bf16(w)
+        ep = ops.make_epilogue(torch.ones(Cout, device=dev), torch.zeros(Cout, device=dev), act=ops.ACT_RELU)
+        ms3 = timed(lambda: ops.conv2d(x, w, s, p, ep=ep, precision=ops.PREC_BF16X3, W_split=ws), 10)
+        ms1 = timed(lambda: ops.conv2d(x, w, s, p, ep=ep, precision=ops.PREC_TF32), 10)
+        Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        fl = 2.0 * B * Ho * Wo * Cout * Cin * k * k
+        print(f"[conv B{B} {H}x{W} {Cin}->{Cout} k{k}s{s}] bf16x3 {ms3*1e3:8.1f} us {fl/ms3/1e9:7.1f} TF/s | tf32 {ms1*1e3:8.1f} us {fl/ms1/1e9:7.1f} TF/s")
+    x4 = torch.randn(8, 518, 518, 4, device=dev); w774, w256 = ops.stem_pack_weights(torch.randn(64, 3, 7, 7, device=dev))
+    ws = ops.split_bf16(w256)
+    ep = ops.make_epilogue(torch.ones(64, device=dev), torch.zeros(64, device=dev), act=ops.ACT_RELU)
+    ms3 = timed(lambda: ops.stem_conv(x4, w774, ep=ep, precision=ops.PREC_BF16X3, W_split=ws), 10)
+    ms0 = timed(lambda: ops.stem_conv(x4, w774, ep=ep, precision=ops.PREC_FP32), 5)
+    print(f"[stem B8 512x512] bf16x3 {ms3*1e3:8.1f} us | fp32 simt {ms0*1e3:8.1f} us")
     return 0
 
 

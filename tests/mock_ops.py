@@ -17,7 +17,7 @@ from oracle import oracle_ops
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 RES_NONE, RES_SAME, RES_UP2 = 0, 1, 2
 AGG_MEAN, AGG_FIRST = 0, 1
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_BF16X3 = 0, 1, 2
 
 
 def tc_available():
@@ -58,7 +58,7 @@ def normalize_resize_pad(img, batch, b, oh, ow, mean, std):
     x = (img - m) / s
     if (oh, ow) != tuple(x.shape[-2:]):
         x = F.interpolate(x[None], size=(oh, ow), mode="bilinear", align_corners=False)[0]
-    batch[b, :oh, :ow, :] = x.permute(1, 2, 0)
+    batch[b, 3:3 + oh, 3:3 + ow, :3] = x.permute(1, 2, 0)       # zero-bordered NHWC4 layout
 
 
 def resize_coords(coors, seg_off, ratios, B):
@@ -157,7 +157,7 @@ def label_paint(boxes, seg_off, seg_cls, B, H, W):
     return torch.from_numpy(pn), torch.from_numpy(cl)
 
 
-def gemm(A, W, *, A2=None, ep=None, precision=0, N=None, K=None, ldw=None, out=None, w_offset=0):
+def gemm(A, W, *, A2=None, ep=None, precision=0, N=None, K=None, ldw=None, out=None, w_offset=0, W_split=None):
     X = A if A2 is None else torch.cat([A, A2], 1)
     Kt = X.shape[1] if K is None else K
     Nn = W.shape[0] if N is None else N
@@ -166,11 +166,30 @@ def gemm(A, W, *, A2=None, ep=None, precision=0, N=None, K=None, ldw=None, out=N
     return _epilogue(X @ Wsub.t(), ep)
 
 
-def conv2d(x, w_ohwi, stride, pad, *, ep=None, precision=0):
+def conv2d(x, w_ohwi, stride, pad, *, ep=None, precision=0, W_split=None):
     y = F.conv2d(x.permute(0, 3, 1, 2), w_ohwi.permute(0, 3, 1, 2), None, stride, pad).permute(0, 2, 3, 1).contiguous()
     if ep is not None and ep.res_mode == RES_UP2:
         ep.out_h, ep.out_w = y.shape[1], y.shape[2]
     return _epilogue(y, ep)
+
+
+def split_bf16(w):
+    hi = w.detach().to(torch.bfloat16)
+    return torch.stack([hi, (w.detach() - hi.float()).to(torch.bfloat16)], 0)
+
+
+def stem_pack_weights(w):
+    O = w.shape[0]
+    w774 = torch.zeros(O, 7, 7, 4)
+    w774[..., :3] = w.detach().permute(0, 2, 3, 1)
+    w884 = torch.zeros(O, 8, 8, 4)
+    w884[:, :7, :7] = w774
+    return w774, w884.reshape(O, 256)
+
+
+def stem_conv(x4, w774, *, ep=None, precision=0, W_split=None):
+    # the 3-pixel border is already in x4: plain 7x7 / stride 2 / pad 0
+    return conv2d(x4, w774, 2, 0, ep=ep)
 
 
 def maxpool3x3s2(x):

@@ -27,7 +27,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_argument_validation_needs_no_gpu():
     lib = _lib.load()
-    rc = lib.vbg_gemm(None, 0, None, 0, 0, None, 0, None, 0, 1, 1, 1, None, 0, None)
+    rc = lib.vbg_gemm(None, 0, None, 0, 0, None, 0, None, 0, None, 0, 1, 1, 1, None, 0, None)
     assert rc == _lib.VBG_EINVAL and "null pointer" in _lib.last_error()
     rc = lib.vbg_roi_align_fwd(None, 1, 1, 1, 4, None, None, 0, 0.25, 7, None, None, None)
     assert rc == _lib.VBG_EINVAL

@@ -112,8 +112,11 @@ def test_transform_kernels(ops):
     for (h, w), (oh, ow) in [((64, 96), (64, 96)), ((85, 107), (96, 120)), ((333, 777), (342, 800))]:
         img = torch.rand(3, h, w, generator=g)
         H, W = ((oh + 31) // 32) * 32, ((ow + 31) // 32) * 32
-        batch = torch.zeros(1, H, W, 3).cuda()
+        batch = torch.zeros(1, H + 6, W + 6, 4).cuda()
         ops.normalize_resize_pad(img.cuda(), batch, 0, oh, ow, mean, std)
+        assert float(batch[0, :3].abs().sum() + batch[0, -3:].abs().sum() + batch[0, :, :3].abs().sum() + batch[0, :, -3:].abs().sum()
+                     + batch[..., 3].abs().sum()) == 0.0                      # border and 4th channel stay zero
+        batch = batch[:, 3:-3, 3:-3, :3]
         x = (img - torch.tensor(mean)[:, None, None]) / torch.tensor(std)[:, None, None]
         x = F.interpolate(x[None], size=(oh, ow), mode="bilinear", align_corners=False)[0]
         want = torch.zeros(3, H, W); want[:, :oh, :ow] = x
@@ -163,20 +166,72 @@ def test_gemm_tf32_tensor_core(ops, M, N, K, K1):
     assert relerr(got.numpy(), want.numpy()) < 2e-3
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout,k,p", [(2, 32, 48, 64, 64, 3, 1), (3, 16, 16, 512, 512, 3, 1), (9, 7, 7, 256, 256, 3, 1),
-                                               (2, 20, 12, 64, 128, 3, 1), (1, 128, 128, 64, 256, 3, 1), (2, 8, 8, 128, 64, 1, 0)])
-def test_conv2d_tf32_tensor_core(ops, B, H, W, Cin, Cout, k, p):
-    if not ops.tc_available():
-        pytest.fail("tcgen05 path unavailable on this GPU box")
-    g = torch.Generator().manual_seed(Cin + Cout + H)
+def _split_ref(x):
+    """bf16x3 operand model: x ~ hi + lo with hi = bf16(x), lo = bf16(x - hi)."""
+    hi = x.to(torch.bfloat16).float()
+    return hi, (x - hi).to(torch.bfloat16).float()
+
+
+def _bf16x3_product(A, Wt):
+    a1, a2 = _split_ref(A); w1, w2 = _split_ref(Wt)
+    return a1.double() @ w1.double().t() + a2.double() @ w1.double().t() + a1.double() @ w2.double().t()
+
+
+@pytest.mark.parametrize("M,N,K,K1", [(128, 64, 64, 64), (300, 768, 768, 768), (4100, 3072, 768, 768), (128, 1024, 1792, 1024),
+                                      (1000, 136, 64, 64), (77, 64, 192, 64), (4096, 128, 896, 128), (513, 256, 12544, 12544)])
+def test_gemm_bf16x3_tensor_core(ops, M, N, K, K1):
+    """Parity-grade tensor-core mode: three bf16 tcgen05 products on hi/lo splits.  (1) matches a float64 evaluation of
+    exactly those three products (proves TMA / converter / descriptors / epilogue); (2) within 2e-5 of the fp32 product."""
+    assert ops.tc_available(), "tcgen05 path unavailable on this GPU box"
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g); Wt = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g); res = torch.randn(M, N, generator=g)
+    a1, a2 = A[:, :K1].contiguous().cuda(), (A[:, K1:].contiguous().cuda() if K1 < K else None)
+    ep = ops.make_epilogue(None, bias.cuda(), res.cuda(), ops.RES_SAME, ldr=N, act=ops.ACT_GELU)
+    Wd = Wt.cuda()
+    got = ops.gemm(a1, Wd, A2=a2, ep=ep, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(Wd)).cpu()
+    want3 = F.gelu(_bf16x3_product(A, Wt) + bias + res)
+    want = F.gelu(A.double() @ Wt.double().t() + bias + res)
+    assert relerr(got.numpy(), want3.numpy()) < 5e-6
+    assert relerr(got.numpy(), want.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "tf32"])
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(2, 32, 48, 64, 64, 3, 1, 1), (3, 16, 16, 512, 512, 3, 1, 1), (9, 7, 7, 256, 256, 3, 1, 1),
+                                                 (2, 20, 12, 64, 128, 3, 1, 1), (1, 128, 128, 64, 256, 3, 1, 1), (2, 8, 8, 128, 64, 1, 1, 0),
+                                                 (2, 32, 32, 64, 128, 3, 2, 1), (8, 64, 64, 128, 256, 3, 2, 1), (2, 16, 24, 64, 128, 1, 2, 0),
+                                                 (1, 256, 256, 64, 128, 3, 2, 1)])
+def test_conv2d_tensor_core(ops, prec, B, H, W, Cin, Cout, k, s, p):
+    """Implicit-GEMM conv through 4-D TMA maps: padding by out-of-bounds zero fill, stride 2 by traversal stride."""
+    assert ops.tc_available()
+    g = torch.Generator().manual_seed(Cin + Cout + H + s)
     x = torch.randn(B, Cin, H, W, generator=g); w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
     scale = torch.rand(Cout, generator=g) + 0.5; shift = torch.randn(Cout, generator=g)
-    res = torch.randn(B, Cout, H, W, generator=g)
-    conv = F.conv2d(_trunc_tf32(x).double(), _trunc_tf32(w).double(), None, 1, p)
-    want_t = F.relu(conv * scale[None, :, None, None] + shift[None, :, None, None] + res)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    res = torch.randn(B, Cout, Ho, Wo, generator=g)
+    want = F.relu(F.conv2d(x.double(), w.double(), None, s, p) * scale[None, :, None, None] + shift[None, :, None, None] + res)
     ep = ops.make_epilogue(scale.cuda(), shift.cuda(), res.permute(0, 2, 3, 1).contiguous().cuda(), ops.RES_SAME, ldr=Cout, act=ops.ACT_RELU)
-    got = ops.conv2d(x.permute(0, 2, 3, 1).contiguous().cuda(), ops.repack_oihw_to_ohwi(w.cuda()), 1, p, ep=ep, precision=ops.PREC_TF32)
-    assert relerr(got.permute(0, 3, 1, 2).cpu().numpy(), want_t.numpy()) < 5e-6
+    w_ohwi = ops.repack_oihw_to_ohwi(w.cuda())
+    kw = dict(precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w_ohwi)) if prec == "bf16x3" else dict(precision=ops.PREC_TF32)
+    got = ops.conv2d(x.permute(0, 2, 3, 1).contiguous().cuda(), w_ohwi, s, p, ep=ep, **kw)
+    assert relerr(got.permute(0, 3, 1, 2).cpu().numpy(), want.numpy()) < (2e-5 if prec == "bf16x3" else 2e-3)
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp32"])
+@pytest.mark.parametrize("B,H,W", [(2, 64, 96), (1, 512, 512), (3, 32, 32)])
+def test_stem_conv(ops, prec, B, H, W):
+    """7x7/2 pad-3 stem over the zero-bordered NHWC4 batch: tensor-core GEMM over overlapping 32-float TMA windows."""
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.randn(B, 3, H, W, generator=g); w = torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5
+    scale = torch.rand(64, generator=g) + 0.5; shift = torch.randn(64, generator=g)
+    want = F.relu(F.conv2d(x.double(), w.double(), None, 2, 3) * scale[None, :, None, None] + shift[None, :, None, None])
+    x4 = torch.zeros(B, H + 6, W + 6, 4); x4[:, 3:-3, 3:-3, :3] = x.permute(0, 2, 3, 1)
+    w774, w256 = ops.stem_pack_weights(w.cuda())
+    assert torch.equal(w774.cpu()[..., :3], w.permute(0, 2, 3, 1)) and float(w774[..., 3].abs().sum()) == 0
+    ep = ops.make_epilogue(scale.cuda(), shift.cuda(), act=ops.ACT_RELU)
+    kw = dict(precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w256)) if prec == "bf16x3" else dict(precision=ops.PREC_FP32)
+    got = ops.stem_conv(x4.cuda(), w774, ep=ep, **kw)
+    assert relerr(got.permute(0, 3, 1, 2).cpu().numpy(), want.numpy()) < (2e-5 if prec == "bf16x3" else 2e-6)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(2, 32, 48, 64, 64, 3, 1, 1), (1, 64, 64, 3, 64, 7, 2, 3), (2, 16, 16, 128, 256, 3, 2, 1),

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvbg_sm100a.so")
 
 VBG_OK, VBG_EINVAL, VBG_ECUDA, VBG_EUNSUPPORTED, VBG_EWORKSPACE = 0, -1, -2, -3, -4
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_BF16X3 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 RES_NONE, RES_SAME, RES_UP2 = 0, 1, 2
 AGG_MEAN, AGG_FIRST = 0, 1
@@ -25,7 +25,7 @@ class VbgError(RuntimeError):
     pass
 
 
-_p, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_p, _i, _f, _sz, _ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 _EP = C.POINTER(Epilogue)
 
 # name -> argtypes, in include/vbg.h order
@@ -44,8 +44,11 @@ SIGNATURES = {
     "vbg_box_index_map": [_p, _p, _i, _i, _i, _i, _p, _p],
     "vbg_grid_scatter": [_p, _p, _p, _i, _i, _i, _p, _p],
     "vbg_label_paint": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
-    "vbg_gemm": [_p, _i, _p, _i, _i, _p, _i, _p, _i, _i, _i, _i, _EP, _i, _p],
-    "vbg_conv2d": [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _EP, _i, _p],
+    "vbg_gemm": [_p, _i, _p, _i, _i, _p, _i, _p, _ll, _p, _i, _i, _i, _i, _EP, _i, _p],
+    "vbg_conv2d": [_p, _i, _i, _i, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _EP, _i, _p],
+    "vbg_split_bf16": [_p, _ll, _p, _p, _p],
+    "vbg_stem_conv": [_p, _i, _i, _i, _p, _p, _ll, _i, _p, _EP, _i, _p],
+    "vbg_stem_pack_weights": [_p, _i, _p, _p, _p],
     "vbg_maxpool3x3s2": [_p, _i, _i, _i, _i, _p, _p],
     "vbg_avgpool2x2": [_p, _i, _i, _i, _i, _p, _p],
     "vbg_bn_fold": [_p, _p, _p, _p, _f, _i, _p, _p, _p],

@@ -22,6 +22,13 @@ int gemm_tc(const float* A, int lda, const float* A2, int lda2, int K1, const fl
             int M, int N, int K, const vbg_epilogue_t* ep, cudaStream_t s);
 int conv_tc(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int kh, int kw, int stride, int pad,
             float* y, const vbg_epilogue_t* ep, cudaStream_t s);
+int gemm_tc3(const float* A, int lda, const float* A2, int lda2, int K1, const void* w_split, long long plane, int ldw,
+             float* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep, cudaStream_t s);
+int conv_tc3(const float* x, int B, int H, int W, int Cin, const void* w_split, long long plane, int Cout, int kh, int kw,
+             int stride, int pad, float* y, const vbg_epilogue_t* ep, cudaStream_t s);
+int stem_tc3(const float* x4, int B, int H, int W, const void* w_split, long long plane, int Cout, float* y,
+             const vbg_epilogue_t* ep, cudaStream_t s);
+int split_bf16(const float* w, long long n, void* hi, void* lo, cudaStream_t s);
 bool tc_available();
 
 // ------------------------------------------------------------------ CRF Viterbi (model/crf.py:96-146)
@@ -99,13 +106,16 @@ static int check_epilogue(const vbg_epilogue_t* ep, const char* who) {
   return VBG_OK;
 }
 
-extern "C" int vbg_gemm(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int ldw, float* C,
-                        int ldc, int M, int N, int K, const vbg_epilogue_t* ep, int precision, vbg_stream_t stream) {
+static bool valid_precision(int p) { return p == VBG_PREC_FP32 || p == VBG_PREC_TF32 || p == VBG_PREC_BF16X3; }
+
+extern "C" int vbg_gemm(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int ldw, const void* W_split,
+                        long long split_plane, float* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep,
+                        int precision, vbg_stream_t stream) {
   VBG_REQUIRE(A && W && C, "vbg_gemm: null pointer");
   VBG_REQUIRE(M >= 0 && N > 0 && K > 0 && K1 > 0 && K1 <= K, "vbg_gemm: bad shape M=%d N=%d K=%d K1=%d", M, N, K, K1);
   VBG_REQUIRE((K1 == K) || A2, "vbg_gemm: A2 required when K1 < K");
   VBG_REQUIRE(lda >= K1 && ldw >= K && ldc >= N && (K1 == K || lda2 >= K - K1), "vbg_gemm: leading dimension too small");
-  VBG_REQUIRE(precision == VBG_PREC_FP32 || precision == VBG_PREC_TF32, "vbg_gemm: bad precision %d", precision);
+  VBG_REQUIRE(valid_precision(precision), "vbg_gemm: bad precision %d", precision);
   int rc = check_epilogue(ep, "vbg_gemm");
   if (rc) return rc;
   if (ep && ep->res_mode == VBG_RES_UP2)
@@ -114,20 +124,24 @@ extern "C" int vbg_gemm(const float* A, int lda, const float* A2, int lda2, int 
   if (ep && ep->res_mode == VBG_RES_SAME) VBG_REQUIRE(ep->ldr >= N, "vbg_gemm: ldr too small");
   if (M == 0) return VBG_OK;
   cudaStream_t s = as_stream(stream);
-  if (precision == VBG_PREC_TF32) {
+  if (precision == VBG_PREC_BF16X3) {
+    rc = gemm_tc3(A, lda, A2, lda2, K1, W_split, split_plane, ldw, C, ldc, M, N, K, ep, s);
+    if (rc != VBG_EUNSUPPORTED) return rc;
+  } else if (precision == VBG_PREC_TF32) {
     rc = gemm_tc(A, lda, A2, lda2, K1, W, ldw, C, ldc, M, N, K, ep, s);
     if (rc != VBG_EUNSUPPORTED) return rc;
   }
   return gemm_simt(A, lda, A2, lda2, K1, W, ldw, C, ldc, M, N, K, ep, s);
 }
 
-extern "C" int vbg_conv2d(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int kh, int kw,
-                          int stride, int pad, float* y, const vbg_epilogue_t* ep, int precision, vbg_stream_t stream) {
+extern "C" int vbg_conv2d(const float* x, int B, int H, int W, int Cin, const float* w, const void* w_split, long long split_plane,
+                          int Cout, int kh, int kw, int stride, int pad, float* y, const vbg_epilogue_t* ep, int precision,
+                          vbg_stream_t stream) {
   VBG_REQUIRE(x && w && y, "vbg_conv2d: null pointer");
   VBG_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0,
               "vbg_conv2d: bad geometry");
   VBG_REQUIRE(H + 2 * pad >= kh && W + 2 * pad >= kw, "vbg_conv2d: kernel larger than padded input");
-  VBG_REQUIRE(precision == VBG_PREC_FP32 || precision == VBG_PREC_TF32, "vbg_conv2d: bad precision %d", precision);
+  VBG_REQUIRE(valid_precision(precision), "vbg_conv2d: bad precision %d", precision);
   int rc = check_epilogue(ep, "vbg_conv2d");
   if (rc) return rc;
   if (ep && ep->res_mode == VBG_RES_UP2) {
@@ -135,11 +149,34 @@ extern "C" int vbg_conv2d(const float* x, int B, int H, int W, int Cin, const fl
     VBG_REQUIRE(Ho % 2 == 0 && Wo % 2 == 0, "vbg_conv2d: VBG_RES_UP2 needs even output dims");
   }
   cudaStream_t s = as_stream(stream);
-  if (precision == VBG_PREC_TF32) {
+  if (precision == VBG_PREC_BF16X3) {
+    rc = conv_tc3(x, B, H, W, Cin, w_split, split_plane, Cout, kh, kw, stride, pad, y, ep, s);
+    if (rc != VBG_EUNSUPPORTED) return rc;
+  } else if (precision == VBG_PREC_TF32) {
     rc = conv_tc(x, B, H, W, Cin, w, Cout, kh, kw, stride, pad, y, ep, s);
     if (rc != VBG_EUNSUPPORTED) return rc;
   }
   return conv_simt(x, B, H, W, Cin, w, Cout, kh, kw, stride, pad, y, ep, s);
+}
+
+extern "C" int vbg_stem_conv(const float* x4, int B, int H, int W, const float* w_ohwi4, const void* w_split, long long split_plane,
+                             int Cout, float* y, const vbg_epilogue_t* ep, int precision, vbg_stream_t stream) {
+  VBG_REQUIRE(x4 && w_ohwi4 && y && B > 0 && H > 0 && W > 0 && Cout > 0, "vbg_stem_conv: bad arguments");
+  VBG_REQUIRE(valid_precision(precision), "vbg_stem_conv: bad precision %d", precision);
+  int rc = check_epilogue(ep, "vbg_stem_conv");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  if (precision == VBG_PREC_BF16X3) {
+    rc = stem_tc3(x4, B, H, W, w_split, split_plane, Cout, y, ep, s);
+    if (rc != VBG_EUNSUPPORTED) return rc;
+  }
+  // the border is already in the buffer: a plain 7x7 / stride-2 / pad-0 conv over [B, H+6, W+6, 4]
+  return conv_simt(x4, B, H + 6, W + 6, 4, w_ohwi4, Cout, 7, 7, 2, 0, y, ep, s);
+}
+
+extern "C" int vbg_split_bf16(const float* w, long long n, void* hi, void* lo, vbg_stream_t stream) {
+  VBG_REQUIRE(w && hi && lo && n >= 0, "vbg_split_bf16: bad arguments");
+  return split_bf16(w, n, hi, lo, as_stream(stream));
 }
 
 extern "C" int vbg_crf_viterbi(const float* feats, const float* trans, const int32_t* seg_off, int B, int K, int T,

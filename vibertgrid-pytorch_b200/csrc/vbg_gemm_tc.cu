@@ -19,100 +19,18 @@
 //
 // Shapes this path does not take (K % 32, Cin % 32, N < 64, strided / 7x7 convs) return
 // VBG_EUNSUPPORTED and the dispatcher uses the fp32 CUDA-core kernel (vbg_gemm_simt.cu).
-#include "vbg_common.cuh"
-#include <cuda.h>
+#include "vbg_tc.cuh"
 #include <dlfcn.h>
 #include <mutex>
 
 namespace vbg {
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap, not hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { printf("vbg tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
-  }
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (tile base 1024-B aligned):
-//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64: 8 rows x 128 B)
-//   [46,48) version = 1 (Blackwell) | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-
-// ------------------------------------------------------------------ kernel
-constexpr int BM = 128, BKE = 32;          // 32 fp32 = one 128-byte swizzle row
-constexpr int kTcThreads = 192;
-
-struct TcParams {
-  float* C; int ldc;
-  int M, N, num_kb, kb_split;
-  // conv tiling (conv == 1)
-  int conv, tw, th, tb, tiles_w, tiles_h, Ho, Wo, Bn, cin_blocks, kw, pad;
-  vbg_epilogue_t ep;
-};
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kTcThreads)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmW, const TcParams p) {
   constexpr uint32_t A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  static_assert(4 * kEpiStageFloats * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the operand ring");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -121,18 +39,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * BN;
-
-  // ---- tile origin
-  int m0 = 0, w0 = 0, h0 = 0, b0 = 0;
-  if (p.conv) {
-    int t = blockIdx.x;
-    w0 = (t % p.tiles_w) * p.tw; t /= p.tiles_w;
-    h0 = (t % p.tiles_h) * p.th; t /= p.tiles_h;
-    b0 = t * p.tb;
-  } else {
-    m0 = blockIdx.x * BM;
-  }
+  const TcTile t = tc_tile_origin(p, BN);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmW);
@@ -166,20 +73,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.conv) {
           const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
           const int fr = tap / p.kw, fs = tap - fr * p.kw;
-          tma_load_4d(&tmA, &full_bar[s], sa, cb * BKE, w0 + fs - p.pad, h0 + fr - p.pad, b0);
+          tma_load_4d(&tmA, &full_bar[s], sa, cb * BKE, t.w0 * p.sw + fs - p.pad_w, t.h0 * p.sh + fr - p.pad_h, t.b0);
         } else if (kb < p.kb_split) {
-          tma_load_2d(&tmA, &full_bar[s], sa, kb * BKE, m0);
+          tma_load_2d(&tmA, &full_bar[s], sa, kb * BKE, t.m0);
         } else {
-          tma_load_2d(&tmA2, &full_bar[s], sa, (kb - p.kb_split) * BKE, m0);
+          tma_load_2d(&tmA2, &full_bar[s], sa, (kb - p.kb_split) * BKE, t.m0);
         }
-        tma_load_2d(&tmW, &full_bar[s], sb, kb * BKE, n0);
+        tma_load_2d(&tmW, &full_bar[s], sb, kb * BKE, t.n0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ===== MMA issuer.  Instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2,
-      // A,B K-major (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29).
-      constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // ===== MMA issuer
+      constexpr uint32_t idesc = make_idesc(kFmtTF32, BM, BN);
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const int s = kb % STAGES;
         mbar_wait(&full_bar[s], (kb / STAGES) & 1);
@@ -194,63 +100,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(tmem_full);                    // accumulator complete
     }
   } else {
-    // ===== epilogue: warp (w % 4) owns TMEM lanes [32*(w%4), +32); lane == accumulator row
+    // ===== epilogue (the operand ring is idle once tmem_full fires: reuse it as the transpose buffers)
     const int q = warp & 3;
-    const int r = q * 32 + lane;
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    long long m_out; bool row_ok;
-    if (p.conv) {
-      const int wi = w0 + r % p.tw, t = r / p.tw;
-      const int hi = h0 + t % p.th, bi = b0 + t / p.th;
-      row_ok = (r < p.tw * p.th * p.tb) && wi < p.Wo && hi < p.Ho && bi < p.Bn;
-      m_out = ((long long)bi * p.Ho + hi) * p.Wo + wi;
-    } else {
-      m_out = m0 + r;
-      row_ok = m_out < p.M;
-    }
-    const vbg_epilogue_t& ep = p.ep;
-    long long res_row = 0;
-    if (ep.residual && row_ok) {
-      if (ep.res_mode == VBG_RES_UP2) {
-        const int wo = (int)(m_out % ep.out_w); const long long t = m_out / ep.out_w;
-        const int ho = (int)(t % ep.out_h); const long long b = t / ep.out_h;
-        res_row = ((b * (ep.out_h >> 1) + (ho >> 1)) * (ep.out_w >> 1) + (wo >> 1)) * (long long)p.N;
-      } else {
-        res_row = m_out * ep.ldr;
-      }
-    }
-    float* crow = p.C + m_out * p.ldc;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.N & 3) == 0);
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);     // warp-collective: all lanes execute
-      if (!row_ok || n0 + c0 >= p.N) continue;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        const int n = n0 + c0 + j;
-        if (n >= p.N) break;
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float x = __uint_as_float(v[j + e]);
-          if (n + e < p.N) {
-            if (ep.scale) x *= __ldg(ep.scale + n + e);
-            if (ep.shift) x += __ldg(ep.shift + n + e);
-            if (ep.residual) x += __ldg(ep.residual + res_row + n + e);
-            x = apply_act(x, ep.act);
-          }
-          o[e] = x;
-        }
-        if (vec_ok && n + 3 < p.N) {
-          *reinterpret_cast<float4*>(crow + n) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) if (n + e < p.N) crow[n + e] = o[e];
-        }
-      }
-    }
+    tc_epilogue<BN>(p, t, tmem_base, q, lane, reinterpret_cast<float*>(smem) + q * kEpiStageFloats);
   }
 
   tc_fence_before();
@@ -303,14 +157,20 @@ bool tc_available() {
   return true;
 }
 
-static bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                   const cuuint32_t* box) {
+bool tc_encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, const cuuint32_t* elem_strides, bool dtype_bf16) {
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, ones,
+  CUresult r = g_encode(tm, dtype_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                        const_cast<void*>(base), dims, strides_bytes, box, elem_strides ? elem_strides : ones,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return false; }
   return true;
+}
+
+static bool encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                   const cuuint32_t* box) {
+  return tc_encode(tm, base, rank, dims, strides_bytes, box, nullptr, false);
 }
 
 static bool map_2d(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows) {
@@ -350,7 +210,7 @@ static int dispatch(const CUtensorMap& a, const CUtensorMap& a2, CUtensorMap& w,
   return launch<64, 4>(a, a2, w, p, grid, s);
 }
 
-static bool tc_disabled_by_env() {
+bool tc_disabled_by_env() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("VBG_DISABLE_TC"); v = (e && e[0] == '1') ? 1 : 0; }
   return v == 1;
@@ -370,31 +230,44 @@ int gemm_tc(const float* A, int lda, const float* A2, int lda2, int K1, const fl
   return dispatch(ta, ta2, tw, W, ldw, K, p, cdiv(M, BM), s);
 }
 
-int conv_tc(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int kh, int kw, int stride, int pad,
-            float* y, const vbg_epilogue_t* ep, cudaStream_t s) {
-  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
-  if (stride != 1 || Cin % BKE || Cout < 64 || !aligned16(x) || !aligned16(w)) return VBG_EUNSUPPORTED;
-  const int Ho = H + 2 * pad - kh + 1, Wo = W + 2 * pad - kw + 1;
-  if (Ho <= 0 || Wo <= 0) return VBG_EUNSUPPORTED;
-  TcParams p{};
-  p.conv = 1; p.Ho = Ho; p.Wo = Wo; p.Bn = B; p.kw = kw; p.pad = pad; p.cin_blocks = Cin / BKE;
+// Implicit-GEMM geometry shared by the kind::tf32 and bf16x3 conv paths.  Returns false for shapes TMA cannot tile.
+bool tc_conv_geometry(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, TcParams& p,
+                      cuuint64_t dims[4], cuuint64_t strides_b[3], cuuint32_t box[4], cuuint32_t estr[4]) {
+  if (stride < 1 || stride > 2) return false;
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  if (Ho <= 0 || Wo <= 0) return false;
+  p.conv = 1; p.Ho = Ho; p.Wo = Wo; p.Bn = B; p.kw = kw; p.pad_w = p.pad_h = pad; p.sw = p.sh = stride;
+  p.cin_blocks = Cin / BKE;
   p.tw = Wo < BM ? Wo : BM;
   p.th = (BM / p.tw) < Ho ? (BM / p.tw) : Ho;
   p.tb = (p.th == Ho && p.tw == Wo) ? ((BM / (p.tw * p.th)) < B ? (BM / (p.tw * p.th)) : B) : 1;
-  if (p.tw > 256 || p.th > 256 || p.tb > 256) return VBG_EUNSUPPORTED;
+  if (p.tw * stride > 256 || p.th * stride > 256 || p.tb > 256) return false;
   p.tiles_w = cdiv(Wo, p.tw); p.tiles_h = cdiv(Ho, p.th);
+  p.M = B * Ho * Wo; p.N = Cout; p.ldc = Cout;
+  dims[0] = (cuuint64_t)Cin; dims[1] = (cuuint64_t)W; dims[2] = (cuuint64_t)H; dims[3] = (cuuint64_t)B;
+  strides_b[0] = (cuuint64_t)Cin * 4; strides_b[1] = (cuuint64_t)W * Cin * 4; strides_b[2] = (cuuint64_t)H * W * Cin * 4;
+  // with a traversal stride s, TMA loads ceil(box / s) elements: box = n * s loads n
+  box[0] = (cuuint32_t)BKE; box[1] = (cuuint32_t)(p.tw * stride); box[2] = (cuuint32_t)(p.th * stride); box[3] = (cuuint32_t)p.tb;
+  estr[0] = 1; estr[1] = (cuuint32_t)stride; estr[2] = (cuuint32_t)stride; estr[3] = 1;
+  return true;
+}
+
+int conv_tc(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int kh, int kw, int stride, int pad,
+            float* y, const vbg_epilogue_t* ep, cudaStream_t s) {
+  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (Cin % BKE || Cout < 64 || !aligned16(x) || !aligned16(w)) return VBG_EUNSUPPORTED;
+  TcParams p{};
+  cuuint64_t dims[4], strides[3]; cuuint32_t box[4], estr[4];
+  if (!tc_conv_geometry(B, H, W, Cin, Cout, kh, kw, stride, pad, p, dims, strides, box, estr)) return VBG_EUNSUPPORTED;
   const int tiles_b = cdiv(B, p.tb);
-  p.C = y; p.ldc = Cout; p.M = B * Ho * Wo; p.N = Cout;
+  p.C = y;
   const int K = kh * kw * Cin;
   p.num_kb = K / BKE; p.kb_split = p.num_kb;
   if (ep) p.ep = *ep;
-  if (p.ep.res_mode == VBG_RES_UP2) { p.ep.out_h = Ho; p.ep.out_w = Wo; }
+  if (p.ep.res_mode == VBG_RES_UP2) { p.ep.out_h = p.Ho; p.ep.out_w = p.Wo; }
   if (p.ep.res_mode == VBG_RES_SAME && p.ep.ldr == 0) p.ep.ldr = Cout;
   CUtensorMap ta, tw;
-  cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4};
-  cuuint32_t box[4] = {(cuuint32_t)BKE, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.tb};
-  if (!encode(&ta, x, 4, dims, strides, box)) return VBG_ECUDA;
+  if (!tc_encode(&ta, x, 4, dims, strides, box, estr, false)) return VBG_EUNSUPPORTED;
   return dispatch(ta, ta, tw, w, K, K, p, p.tiles_w * p.tiles_h * tiles_b, s);
 }
 

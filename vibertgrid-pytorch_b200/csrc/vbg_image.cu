@@ -6,7 +6,9 @@ namespace vbg {
 
 // ------------------------------------------------------------------ a1
 // (x - mean)/std per tap, then bilinear (align_corners=False) exactly as ATen's
-// upsample_bilinear2d with scale = in/out; writes NHWC.  Replaces the per-image
+// upsample_bilinear2d with scale = in/out; writes the zero-bordered NHWC4 batch [B, H+6, W+6, 4] (3-pixel
+// border = the stem conv's padding, 4th channel = 0) that the tensor-core stem reads through one TMA map
+// (vbg_gemm_tc3.cu::stem_tc3).  Replaces the per-image
 // normalize/interpolate/copy_ kernels of reference pipeline/transform.py:122,149-155,261-269.
 __global__ void normalize_resize_kernel(const float* __restrict__ img, int h, int w, float* __restrict__ out, int H,
                                         int W, int oh, int ow, float3 mean, float3 stdv) {
@@ -30,8 +32,18 @@ __global__ void normalize_resize_kernel(const float* __restrict__ img, int h, in
     float p11 = __fdiv_rn(__ldg(p + (size_t)y1 * w + x1) - m[c], s[c]);
     r[c] = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
   }
-  float* o = out + ((size_t)y * W + x) * 3;
-  o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+  *reinterpret_cast<float4*>(out + ((size_t)(y + 3) * (W + 6) + (x + 3)) * 4) = make_float4(r[0], r[1], r[2], 0.f);
+}
+
+// PyTorch stem weight [O,3,7,7] -> (a) [O,7,7,4] (4th channel 0) for the CUDA-core path, (b) [O,8,8,4] with zero
+// 8th filter row / 8th pixel / 4th channel: the K = 256 operand of the tensor-core stem GEMM.
+__global__ void stem_pack_kernel(const float* __restrict__ w, int O, float* __restrict__ w774, float* __restrict__ w884) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= O * 256) return;
+  const int c = i & 3, px = (i >> 2) & 7, r = (i >> 5) & 7, o = i >> 8;
+  const float v = (c < 3 && px < 7 && r < 7) ? w[(((size_t)o * 3 + c) * 7 + r) * 7 + px] : 0.f;
+  w884[i] = v;
+  if (px < 7 && r < 7) w774[(((size_t)o * 7 + r) * 7 + px) * 4 + c] = v;
 }
 
 // ------------------------------------------------------------------ pooling (NHWC, float4 over channels)
@@ -142,14 +154,20 @@ using namespace vbg;
 
 extern "C" int vbg_normalize_resize_pad(const float* img_chw, int h, int w, float* batch_nhwc, int b, int H, int W,
                                         int oh, int ow, const float* h_mean3, const float* h_std3, vbg_stream_t stream) {
-  VBG_REQUIRE(img_chw && batch_nhwc && h_mean3 && h_std3, "vbg_normalize_resize_pad: null pointer");
+  VBG_REQUIRE(img_chw && batch_nhwc && h_mean3 && h_std3 && aligned16(batch_nhwc), "vbg_normalize_resize_pad: null / unaligned pointer");
   VBG_REQUIRE(h > 0 && w > 0 && oh > 0 && ow > 0 && oh <= H && ow <= W && b >= 0,
               "vbg_normalize_resize_pad: bad geometry h=%d w=%d oh=%d ow=%d H=%d W=%d", h, w, oh, ow, H, W);
   dim3 blk(32, 8), grd(cdiv(ow, 32), cdiv(oh, 8));
   normalize_resize_kernel<<<grd, blk, 0, as_stream(stream)>>>(
-      img_chw, h, w, batch_nhwc + (size_t)b * H * W * 3, H, W, oh, ow,
+      img_chw, h, w, batch_nhwc + (size_t)b * (H + 6) * (W + 6) * 4, H, W, oh, ow,
       make_float3(h_mean3[0], h_mean3[1], h_mean3[2]), make_float3(h_std3[0], h_std3[1], h_std3[2]));
   return check_launch("vbg_normalize_resize_pad");
+}
+
+extern "C" int vbg_stem_pack_weights(const float* w_oihw, int O, float* w_ohwi4, float* w_k256, vbg_stream_t stream) {
+  VBG_REQUIRE(w_oihw && w_ohwi4 && w_k256 && O > 0, "vbg_stem_pack_weights: bad arguments");
+  stem_pack_kernel<<<cdiv((long long)O * 256, 256), 256, 0, as_stream(stream)>>>(w_oihw, O, w_ohwi4, w_k256);
+  return check_launch("vbg_stem_pack_weights");
 }
 
 extern "C" int vbg_maxpool3x3s2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream) {

@@ -26,13 +26,15 @@ import torch.nn as nn
 
 from . import ops
 from . import params as P
-from .ops import ACT_GELU, ACT_NONE, ACT_RELU, PREC_FP32, PREC_TF32, RES_NONE, RES_SAME, RES_UP2, make_epilogue
+from .ops import (ACT_GELU, ACT_NONE, ACT_RELU, PREC_BF16X3, PREC_FP32, PREC_TF32, RES_NONE, RES_SAME, RES_UP2,
+                  make_epilogue)
 from .plan import plan_batch
 
 
 class _Prepared:
     def __init__(self):
-        self.convw: Dict[int, torch.Tensor] = {}
+        self.convw: Dict[int, torch.Tensor] = {}     # id(conv) -> fp32 weight, [Cout, kh, kw, Cin]
+        self.split: Dict[int, torch.Tensor] = {}     # id(module) or id(fp32 tensor) -> bf16 [2, ...] hi/lo planes
         self.bn: Dict[int, tuple] = {}
         self.bert_layers = []
         self.misc: Dict[str, torch.Tensor] = {}
@@ -44,7 +46,7 @@ class ForwardEngine:
         self._prep: Optional[_Prepared] = None
         self._fp = None
         env = os.environ.get("VBG_PRECISION", "").lower()
-        self.precision = {"fp32": PREC_FP32, "tf32": PREC_TF32}.get(env)
+        self.precision = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16x3": PREC_BF16X3}.get(env)
         self.launches = 0
 
     # ------------------------------------------------------------------ parameter preparation
@@ -59,28 +61,53 @@ class ForwardEngine:
         if self._prep is not None and fp == self._fp:
             return self._prep
         net, pr = self.net, _Prepared()
+        want_split = self._prec() == PREC_BF16X3
+
+        def split_of(key, w):
+            if want_split:
+                pr.split[key] = ops.split_bf16(w)
+
+        stem = net.backbone.resnet.conv1 if net.backbone.pretrained_layout else net.backbone.conv_1[0]
         for m in net.modules():
             if isinstance(m, nn.Conv2d):
                 w = m.weight.detach()
+                if m is stem:
+                    w774, w256 = ops.stem_pack_weights(w)
+                    pr.convw[id(m)] = w774
+                    split_of(id(m), w256)
+                    continue
                 if w.shape[2] == 1 and w.shape[3] == 1:
                     pr.convw[id(m)] = w.reshape(w.shape[0], 1, 1, w.shape[1]).contiguous()  # OIHW == OHWI for 1x1
                 else:
                     pr.convw[id(m)] = ops.repack_oihw_to_ohwi(w)
+                split_of(id(m), pr.convw[id(m)])
             elif isinstance(m, nn.modules.batchnorm._BatchNorm):
                 pr.bn[id(m)] = ops.bn_fold(m)
+            elif isinstance(m, nn.Linear) and m.out_features >= 64 and m.in_features % 64 == 0:
+                split_of(id(m), m.weight)
         for lyr in net.bert_model.encoder.layer:
-            s = lyr.attention.self
-            pr.bert_layers.append(dict(
-                wqkv=torch.cat([s.query.weight, s.key.weight, s.value.weight], 0).detach().contiguous(),
-                bqkv=torch.cat([s.query.bias, s.key.bias, s.value.bias], 0).detach().contiguous()))
+            sa = lyr.attention.self
+            pk = dict(wqkv=torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0).detach().contiguous(),
+                      bqkv=torch.cat([sa.query.bias, sa.key.bias, sa.value.bias], 0).detach().contiguous())
+            pk["wqkv_split"] = ops.split_bf16(pk["wqkv"]) if want_split else None
+            pr.bert_layers.append(pk)
+            for m in (sa.query, sa.key, sa.value):
+                pr.split.pop(id(m), None)          # only the packed QKV operand is used
+        bm = net.bert_model
+        if hasattr(bm, "pooler"):
+            pr.split.pop(id(bm.pooler.dense), None)  # never on the forward path
         roi = net.late_fusion_net.ROI_embedding_net
         Cc, Pp = net.p_fuse_channel, net.roi_shape
         pr.misc["roi_fc_w"] = ops.repack_oihw_to_ohwi(
             roi.linear.weight.detach().reshape(-1, Cc, Pp, Pp)).reshape(roi.linear.out_features, -1)
+        pr.split.pop(id(roi.linear), None)
+        split_of("roi_fc_w", pr.misc["roi_fc_w"])
         if net.semantic_segmentation_head is not None:
             enc = net.semantic_segmentation_head.encoder
             pr.misc["seg_w"] = torch.cat([enc.conv_3_1.weight.flatten(1), enc.conv_3_2.weight.flatten(1)], 0).detach().contiguous()
             pr.misc["seg_b"] = torch.cat([enc.conv_3_1.bias, enc.conv_3_2.bias], 0).detach().contiguous()
+            for m in (enc.conv_3_1, enc.conv_3_2):
+                pr.split.pop(id(m), None)          # N = 3 + C < 64: CUDA-core kernel
         head = net.field_type_classification_head
         if isinstance(head, P.FullHeadParams) and net.layer_mode == "single":
             nets = [getattr(head, f"category_classification_net_{i}") for i in range(net.num_tokens - 1)]
@@ -92,27 +119,35 @@ class ForwardEngine:
     # ------------------------------------------------------------------ building blocks
     def _prec(self):
         if self.precision is None:
-            self.precision = PREC_TF32 if ops.tc_available() else PREC_FP32
+            self.precision = PREC_BF16X3 if ops.tc_available() else PREC_FP32
         return self.precision
 
     def _conv(self, x, conv: nn.Conv2d, bn=None, act=ACT_NONE, residual=None, res_mode=RES_NONE):
         pr = self._prep
-        w = pr.convw[id(conv)]
+        w, ws = pr.convw[id(conv)], pr.split.get(id(conv))
         scale, shift = pr.bn[id(bn)] if bn is not None else (None, None if conv.bias is None else conv.bias.detach())
         B, H, W, Cin = x.shape
         k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         Cout = conv.out_channels
         if k == 1 and s == 1:
             ep = make_epilogue(scale, shift, residual, res_mode, ldr=Cout, out_h=H, out_w=W, act=act)
-            y = ops.gemm(x.view(B * H * W, Cin), w.view(Cout, Cin), ep=ep, precision=self._prec())
+            y = ops.gemm(x.view(B * H * W, Cin), w.view(Cout, Cin), ep=ep, precision=self._prec(), W_split=ws)
             return y.view(B, H, W, Cout)
         ep = make_epilogue(scale, shift, residual, res_mode, ldr=Cout, act=act)
-        return ops.conv2d(x, w, s, p, ep=ep, precision=self._prec())
+        return ops.conv2d(x, w, s, p, ep=ep, precision=self._prec(), W_split=ws)
 
-    def _lin(self, x, lin: nn.Linear, act=ACT_NONE, residual=None, A2=None, W=None):
+    def _stem(self, x4, conv: nn.Conv2d, bn):
+        pr = self._prep
+        scale, shift = pr.bn[id(bn)]
+        ep = make_epilogue(scale, shift, act=ACT_RELU)
+        return ops.stem_conv(x4, pr.convw[id(conv)], ep=ep, precision=self._prec(), W_split=pr.split.get(id(conv)))
+
+    def _lin(self, x, lin: nn.Linear, act=ACT_NONE, residual=None, A2=None, W=None, W_split=None):
         ep = make_epilogue(None, lin.bias.detach(), residual, RES_SAME if residual is not None else RES_NONE,
                            ldr=lin.out_features, act=act)
-        return ops.gemm(x, lin.weight.detach() if W is None else W, A2=A2, ep=ep, precision=self._prec())
+        if W is None:
+            W, W_split = lin.weight.detach(), self._prep.split.get(id(lin))
+        return ops.gemm(x, W, A2=A2, ep=ep, precision=self._prec(), W_split=W_split)
 
     def _mlp_or_lin(self, x, m):
         if hasattr(m, "linear_1"):
@@ -143,7 +178,7 @@ class ForwardEngine:
         B, H, W, C1 = x2.shape
         ep = make_epilogue(None, None if conv.bias is None else conv.bias.detach())
         y = ops.gemm(x2.view(-1, C1), self._prep.convw[id(conv)].view(conv.out_channels, -1), A2=grid.view(-1, grid.shape[-1]), ep=ep,
-                     precision=self._prec())
+                     precision=self._prec(), W_split=self._prep.split.get(id(conv)))
         return y.view(B, H, W, conv.out_channels)
 
     # ------------------------------------------------------------------ stages
@@ -159,7 +194,7 @@ class ForwardEngine:
                          e.LayerNorm.bias.detach(), e.LayerNorm.eps)
         prec = self._prec()
         for lyr, pk in zip(bm.encoder.layer, pr.bert_layers):
-            qkv = ops.gemm(x, pk["wqkv"], ep=make_epilogue(None, pk["bqkv"]), precision=prec)
+            qkv = ops.gemm(x, pk["wqkv"], ep=make_epilogue(None, pk["bqkv"]), precision=prec, W_split=pk["wqkv_split"])
             ctx = ops.attention(qkv, cu, plan.nseq, plan.max_len, heads, prec)
             ao = lyr.attention.output
             a = self._lin(ctx, ao.dense, residual=x)
@@ -174,7 +209,7 @@ class ForwardEngine:
         bb = self.net.backbone
         if bb.pretrained_layout:
             r = bb.resnet
-            x1 = ops.maxpool3x3s2(self._conv(img, r.conv1, r.bn1, ACT_RELU))
+            x1 = ops.maxpool3x3s2(self._stem(img, r.conv1, r.bn1))
             for blk in r.layer1:
                 x1 = self._tv_block(x1, blk)
             x2 = self._tv_block(x1, r.layer2[0])
@@ -188,7 +223,7 @@ class ForwardEngine:
             for blk in r.layer4:
                 x4 = self._tv_block(x4, blk)
         else:
-            x1 = ops.maxpool3x3s2(self._conv(img, bb.conv_1[0], bb.conv_1[1], ACT_RELU))
+            x1 = ops.maxpool3x3s2(self._stem(img, bb.conv_1[0], bb.conv_1[1]))
             for blk in bb.conv_2_x:
                 x1 = self._our_block(x1, blk)
             x2 = self._our_block(x1, bb.conv_3_x.block_1)
@@ -208,6 +243,7 @@ class ForwardEngine:
         x7 = self._conv(self._conv(x1, bb.skip_3, residual=x6, res_mode=RES_UP2), bb.merge_3)
         # fuse(cat[up8 x4, up4 x5, up2 x6, x7]) as four chained K-slices of fuse.weight at native resolution
         wf = self._prep.convw[id(bb.fuse)].view(bb.fuse.out_channels, -1)   # [256, 1024]
+        wfs = self._prep.split.get(id(bb.fuse))
         Pc = wf.shape[1] // 4
         prec = self._prec()
         t = None
@@ -215,7 +251,7 @@ class ForwardEngine:
             B, H, W, Cc = lvl.shape
             ep = make_epilogue(residual=t, res_mode=RES_UP2 if t is not None else RES_NONE, out_h=H, out_w=W)
             t = ops.gemm(lvl.view(-1, Cc), wf, ep=ep, precision=prec, N=wf.shape[0], K=Pc, ldw=wf.shape[1],
-                         w_offset=i * Pc).view(B, H, W, wf.shape[0])
+                         w_offset=i * Pc, W_split=wfs).view(B, H, W, wf.shape[0])
         return t
 
     def _seg_head(self, p_fuse):
@@ -247,12 +283,12 @@ class ForwardEngine:
         out = {"plan": plan, "status": status}
 
         # a1 transform
-        batch = torch.zeros((B, plan.H, plan.W, 3), dtype=torch.float32, device=dev)
+        batch = torch.zeros((B, plan.H + 6, plan.W + 6, 4), dtype=torch.float32, device=dev)   # zero-bordered NHWC4 stem input
         for b, im in enumerate(image):
             ops.normalize_resize_pad(im.contiguous(), batch, b, plan.sizes[b][0], plan.sizes[b][1], net.image_mean, net.image_std)
         coors_cat = torch.cat([c.reshape(-1, 4) for c in coors], 0).to(torch.int64).contiguous()
         boxes = ops.resize_coords(coors_cat, seg_off, dt["ratios"], B)
-        out["image_batch"], out["boxes"] = batch, boxes
+        out["image_batch"], out["boxes"] = batch[:, 3:-3, 3:-3, :3], boxes     # view without border / pad channel
 
         # a2 / a3 BERT + segment aggregation
         hidden = self._bert(plan, dt, corpus.contiguous())
@@ -285,7 +321,7 @@ class ForwardEngine:
         rn = net.late_fusion_net.ROI_embedding_net
         r = self._conv(roi, rn.conv_1, rn.bn_1, ACT_RELU)
         r = self._conv(r, rn.conv_2, rn.bn_2, ACT_RELU)
-        roi_emb = self._lin(r.view(plan.K, -1), rn.linear, W=pr.misc["roi_fc_w"])
+        roi_emb = self._lin(r.view(plan.K, -1), rn.linear, W=pr.misc["roi_fc_w"], W_split=pr.split.get("roi_fc_w"))
         late = self._lin(roi_emb, net.late_fusion_net.fuse_embedding_net.linear, A2=seg_emb)
         out["late"] = late
 

@@ -14,8 +14,8 @@ from typing import Optional
 import torch
 
 from . import _lib as L
-from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, AGG_FIRST, AGG_MEAN, PREC_FP32, PREC_TF32, RES_NONE, RES_SAME,
-                   RES_UP2, Epilogue, VbgError)
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, AGG_FIRST, AGG_MEAN, PREC_BF16X3, PREC_FP32, PREC_TF32, RES_NONE,
+                   RES_SAME, RES_UP2, Epilogue, VbgError)
 
 
 def _p(t: Optional[torch.Tensor], dtype=None, name="tensor"):
@@ -53,9 +53,13 @@ def make_epilogue(scale=None, shift=None, residual=None, res_mode=RES_NONE, ldr=
 
 
 # ------------------------------------------------------------------ a1
-def normalize_resize_pad(img_chw, batch_nhwc, b, oh, ow, mean, std):
+def normalize_resize_pad(img_chw, batch_nhwc4, b, oh, ow, mean, std):
+    """``batch_nhwc4`` is the zero-initialised [B, H+6, W+6, 4] stem input (3-pixel border, 4th channel 0)."""
     _, h, w = img_chw.shape
-    B, H, W, _ = batch_nhwc.shape
+    B, Hp, Wp, c4 = batch_nhwc4.shape
+    assert c4 == 4
+    H, W = Hp - 6, Wp - 6
+    batch_nhwc = batch_nhwc4
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
     L.check(L.load().vbg_normalize_resize_pad(_f32(img_chw, "image"), h, w, _f32(batch_nhwc), b, H, W, oh, ow, m, s,
@@ -147,9 +151,25 @@ def label_paint(boxes, seg_off, seg_cls, B, H, W):
 
 
 # ------------------------------------------------------------------ dense contractions
+def split_bf16(w):
+    """fp32 tensor -> bf16 [2, *w.shape]: plane 0 = bf16_rn(w), plane 1 = bf16_rn(w - plane 0)  (VBG_PREC_BF16X3 weights)."""
+    w = w.detach().contiguous()
+    out = torch.empty((2,) + tuple(w.shape), dtype=torch.bfloat16, device=w.device)
+    L.check(L.load().vbg_split_bf16(_f32(w, "w"), w.numel(), _p(out[0]), _p(out[1]), _stream()), "vbg_split_bf16")
+    return out
+
+
+def _split_args(W_split, w_offset):
+    if W_split is None:
+        return None, 0
+    if W_split.dtype != torch.bfloat16 or not W_split.is_contiguous() or W_split.shape[0] != 2:
+        raise TypeError("W_split must be the contiguous bf16 [2, ...] tensor returned by split_bf16")
+    return _p(W_split) + 2 * w_offset, W_split[0].numel()
+
+
 def gemm(A, W, *, A2=None, ep: Optional[Epilogue] = None, precision=PREC_FP32, N=None, K=None, ldw=None, out=None,
-         w_offset=0):
-    """C[M,N] = epilogue([A | A2] @ W[N,K]^T).  ``w_offset``/``ldw``/``N``/``K`` select a sub-block of W."""
+         w_offset=0, W_split=None):
+    """C[M,N] = epilogue([A | A2] @ W[N,K]^T).  ``w_offset``/``ldw``/``N``/``K`` select a sub-block of W (and W_split)."""
     M, K1 = A.shape
     K2 = 0 if A2 is None else A2.shape[1]
     Kt = K1 + K2 if K is None else K
@@ -158,21 +178,46 @@ def gemm(A, W, *, A2=None, ep: Optional[Epilogue] = None, precision=PREC_FP32, N
     if out is None:
         out = torch.empty((M, Nn), dtype=torch.float32, device=A.device)
     wp = _f32(W, "W") + 4 * w_offset
+    sp, plane = _split_args(W_split, w_offset)
     L.check(L.load().vbg_gemm(_f32(A, "A"), A.stride(0), _f32(A2, "A2"), 0 if A2 is None else A2.stride(0), K1, wp, ldw_,
-                              _f32(out, "out"), out.stride(0), M, Nn, Kt, C.byref(ep) if ep is not None else None,
-                              precision, _stream()), "vbg_gemm")
+                              sp, plane, _f32(out, "out"), out.stride(0), M, Nn, Kt,
+                              C.byref(ep) if ep is not None else None, precision, _stream()), "vbg_gemm")
     return out
 
 
-def conv2d(x, w_ohwi, stride, pad, *, ep: Optional[Epilogue] = None, precision=PREC_FP32):
+def conv2d(x, w_ohwi, stride, pad, *, ep: Optional[Epilogue] = None, precision=PREC_FP32, W_split=None):
     B, H, W, Cin = x.shape
     Cout, kh, kw, Cin2 = w_ohwi.shape
     if Cin2 != Cin:
         raise ValueError(f"conv2d: weight expects Cin={Cin2}, input has {Cin}")
     Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
     y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
-    L.check(L.load().vbg_conv2d(_f32(x, "x"), B, H, W, Cin, _f32(w_ohwi, "w"), Cout, kh, kw, stride, pad, _f32(y),
+    sp, plane = _split_args(W_split, 0)
+    L.check(L.load().vbg_conv2d(_f32(x, "x"), B, H, W, Cin, _f32(w_ohwi, "w"), sp, plane, Cout, kh, kw, stride, pad, _f32(y),
                                 C.byref(ep) if ep is not None else None, precision, _stream()), "vbg_conv2d")
+    return y
+
+
+def stem_pack_weights(w_oihw):
+    """[O,3,7,7] -> ([O,7,7,4] for the CUDA-core path, [O,256] zero-padded K operand of the tensor-core stem)."""
+    O = w_oihw.shape[0]
+    assert tuple(w_oihw.shape[1:]) == (3, 7, 7)
+    w774 = torch.empty((O, 7, 7, 4), dtype=torch.float32, device=w_oihw.device)
+    w256 = torch.empty((O, 256), dtype=torch.float32, device=w_oihw.device)
+    L.check(L.load().vbg_stem_pack_weights(_f32(w_oihw.detach().contiguous()), O, _f32(w774), _f32(w256), _stream()),
+            "vbg_stem_pack_weights")
+    return w774, w256
+
+
+def stem_conv(x4, w774, *, ep: Optional[Epilogue] = None, precision=PREC_FP32, W_split=None):
+    """7x7/2 pad-3 stem over the padded NHWC4 batch [B, H+6, W+6, 4] -> [B, H/2, W/2, Cout]."""
+    B, Hp, Wp, c4 = x4.shape
+    H, W = Hp - 6, Wp - 6
+    Cout = w774.shape[0]
+    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cout), dtype=torch.float32, device=x4.device)
+    sp, plane = _split_args(W_split, 0)
+    L.check(L.load().vbg_stem_conv(_f32(x4, "x4"), B, H, W, _f32(w774, "w"), sp, plane, Cout, _f32(y),
+                                   C.byref(ep) if ep is not None else None, precision, _stream()), "vbg_stem_conv")
     return y
 
 
