@@ -149,10 +149,9 @@ def time_region(fn, steps, stream_sync, world):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    return float(ms.item())
+    from vibertgrid_pytorch_b200 import shard
+    ms, _ = shard.aggregate_throughput(e0.elapsed_time(e1), 0, device="cuda")      # MAX over ranks
+    return ms
 
 
 def kernel_rooflines(net, cfg, dev, peaks):
@@ -291,7 +290,8 @@ def main():
     prec = eng._prec()
 
     n_rot = 4      # rotate distinct documents; weights (0.6 GB) + activations exceed the 126 MB L2 anyway
-    host = [pin(synth.make_batch(cfg, 1000 * rank + i)) for i in range(n_rot)]
+    from vibertgrid_pytorch_b200 import shard
+    host = [pin(synth.make_batch(cfg, shard.batch_seed(rank, world, i, n_rot))) for i in range(n_rot)]
     resident = [to_device(b, dev, False) for b in host]
     torch.cuda.synchronize()
 

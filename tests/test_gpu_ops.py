@@ -192,8 +192,9 @@ def test_gemm_bf16x3_tensor_core(ops, M, N, K, K1):
     got = ops.gemm(a1, Wd, A2=a2, ep=ep, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(Wd)).cpu()
     want3 = F.gelu(_bf16x3_product(A, Wt) + bias + res)
     want = F.gelu(A.double() @ Wt.double().t() + bias + res)
-    assert relerr(got.numpy(), want3.numpy()) < 5e-6
-    assert relerr(got.numpy(), want.numpy()) < 2e-5
+    # fp32 accumulation in TMEM: the rounding of 3K partial products grows with K
+    assert relerr(got.numpy(), want3.numpy()) < (5e-6 if K <= 3072 else 6e-5)
+    assert relerr(got.numpy(), want.numpy()) < (2e-5 if K <= 3072 else 8e-5)
 
 
 @pytest.mark.parametrize("prec", ["bf16x3", "tf32"])
@@ -292,6 +293,24 @@ def test_bert_kernels(ops):
     assert relerr(got.cpu().numpy(), want.numpy()) < 2e-6
     lg = torch.randn(130, 5, generator=g) * 4
     assert relerr(ops.softmax_rows(lg.cuda()).cpu().numpy(), lg.softmax(1).numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("lens", [[512, 4, 77, 130], [200, 64, 65, 1, 128, 129, 300]])
+def test_attention_tensor_core(ops, lens):
+    """tcgen05 attention (S in TMEM, exact two-pass softmax, 3-term bf16 split) against a float64 softmax(QK^T/8)V."""
+    assert ops.tc_available()
+    g = torch.Generator().manual_seed(len(lens))
+    hid, heads = 768, 12
+    cu = np.zeros(len(lens) + 1, np.int32); cu[1:] = np.cumsum(lens)
+    R = int(cu[-1])
+    qkv = torch.randn(R, 3 * hid, generator=g) * 1.5
+    got = ops.attention(qkv.cuda(), torch.from_numpy(cu).cuda(), len(lens), max(lens), heads, ops.PREC_BF16X3).cpu()
+    want = torch.empty(R, hid, dtype=torch.float64)
+    for q in range(len(lens)):
+        a, b = cu[q], cu[q + 1]
+        Q, K, V = [qkv[a:b, i * hid:(i + 1) * hid].double().reshape(b - a, heads, 64).transpose(0, 1) for i in range(3)]
+        want[a:b] = ((Q @ K.transpose(-1, -2) / 8).softmax(-1) @ V).transpose(0, 1).reshape(b - a, hid)
+    assert relerr(got.numpy(), want.numpy()) < 3e-5
 
 
 def test_crf_viterbi_matches_oracle(ops):

@@ -1,0 +1,256 @@
+// Variable-length multi-head attention on the 5th-generation tensor cores (VBG_PREC_BF16X3 / TF32 requests).
+//
+//   out[r, h*64:(h+1)*64] = softmax(Q K^T / 8) V      per (sequence, head), packed real rows only
+//
+// Replaces the eager attention inside HF BertModel as called by reference model/BERTgrid_generator.py:134.
+// One CTA = 128 queries of one (sequence, head); sequences hold at most 512 rows (BERT's position limit), so the
+// whole score row block S[128, len] lives in TMEM (<= 512 fp32 columns) and the softmax is exact two-pass
+// (row max, then exp / sum), not an online approximation schedule.
+//
+//   warp 0      one thread issues tcgen05.mma.kind::f16: S = Q K^T (N = 128 keys per step), later O += P V (N = 64)
+//   warps 1-4   128 threads, thread == query row == TMEM lane:
+//               phase A  load Q / K rows from HBM (256 B per thread), split fp32 -> bf16 hi/lo, write the K-major
+//                        SWIZZLE_128B operand tiles;
+//               phase B  row max over S (tcgen05.ld);
+//               phase C  per 64-key unit: p = exp2((s - max) * log2e/8) -> bf16 hi/lo -> P operand tiles; the matching
+//                        V rows are transposed into the V^T operand tiles by the same threads; row sum in fp32;
+//               phase D  O (TMEM) * 1/sum -> HBM.
+// Every product uses the 3-term bf16 split (a1*b1 + a2*b1 + a1*b2, fp32 accumulate) of vbg_gemm_tc3.cu, so the
+// result is fp32-class.  O re-uses TMEM columns [0,64) once unit 0 of S has been consumed.
+#include "vbg_tc.cuh"
+#include <cuda_bf16.h>
+
+namespace vbg {
+
+constexpr int kAtThreads = 160;
+constexpr uint32_t kTileQ = 128 * 128;       // one bf16 operand tile of 128 rows x 64 elements
+constexpr uint32_t kVtTile = 64 * 128;       // V^T tile: 64 d-rows x 64 keys (bf16)
+
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __bfloat162float(h.x), b - __bfloat162float(h.y));
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// 64 fp32 of one row (src, 256 B, or zeros) -> row r of the hi / lo operand tiles (128 B each, swizzled 16-byte chunks)
+__device__ __forceinline__ void load_split_row(const float* __restrict__ src, bool valid, uint8_t* t1, uint8_t* t2, int r) {
+  float4 v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = valid ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const uint32_t xr = (uint32_t)(r & 7);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {                 // bf16 chunk c = elements 8c .. 8c+7 = float4 2c, 2c+1
+    uint4 h, l;
+    split2(v[2 * c].x, v[2 * c].y, h.x, l.x); split2(v[2 * c].z, v[2 * c].w, h.y, l.y);
+    split2(v[2 * c + 1].x, v[2 * c + 1].y, h.z, l.z); split2(v[2 * c + 1].z, v[2 * c + 1].w, h.w, l.w);
+    const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)c) ^ xr) << 4);
+    *reinterpret_cast<uint4*>(t1 + off) = h;
+    *reinterpret_cast<uint4*>(t2 + off) = l;
+  }
+}
+
+__global__ void __launch_bounds__(kAtThreads)
+attention_tc_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ cu, int heads, float scale_log2e,
+                    float* __restrict__ out) {
+  const int seq = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * 128;
+  const int row0 = cu[seq], len = cu[seq + 1] - row0;
+  if (q0 >= len) return;                                        // whole CTA, before any barrier / allocation
+  const int n_chunks = (len + 127) >> 7, n_units = (len + 63) >> 6;
+  const int hidden = heads * 64, ld = 3 * hidden;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_op = smem;                                         // Q1 | Q2
+  uint8_t* kp = smem + 2 * kTileQ;                              // 2 x (K1 | K2), later 2 x (P1 | P2)
+  uint8_t* vt = kp + 4 * kTileQ;                                // 2 x (VT1 | VT2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(vt + 4 * kVtTile);
+  uint64_t *q_ready = bars, *k_ready = bars + 1, *k_empty = bars + 3, *s_full = bars + 5, *p_ready = bars + 6,
+           *p_empty = bars + 8, *o_full = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_init(q_ready, 128);
+      for (int i = 0; i < 2; ++i) { mbar_init(&k_ready[i], 128); mbar_init(&k_empty[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&p_empty[i], 1); }
+      mbar_init(s_full, 1); mbar_init(o_full, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== MMA issuer
+      constexpr uint32_t idesc_s = make_idesc(kFmtBF16, 128, 128), idesc_o = make_idesc(kFmtBF16, 128, 64);
+      const uint64_t q1 = make_sw128_desc(smem_u32(q_op)), q2 = make_sw128_desc(smem_u32(q_op + kTileQ));
+      mbar_wait(q_ready, 0);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int b = c & 1;
+        mbar_wait(&k_ready[b], (c >> 1) & 1);
+        tc_fence_after();
+        const uint32_t kb = smem_u32(kp + b * 2 * kTileQ);
+        const uint64_t k1 = make_sw128_desc(kb), k2 = make_sw128_desc(kb + kTileQ);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t o = (uint64_t)(2 * k);
+          umma_bf16(tmem_base + (uint32_t)(c * 128), q1 + o, k1 + o, idesc_s, k != 0);
+          umma_bf16(tmem_base + (uint32_t)(c * 128), q2 + o, k1 + o, idesc_s, 1);
+          umma_bf16(tmem_base + (uint32_t)(c * 128), q1 + o, k2 + o, idesc_s, 1);
+        }
+        umma_commit(&k_empty[b]);
+      }
+      umma_commit(s_full);
+      for (int u = 0; u < n_units; ++u) {
+        const int b = u & 1;
+        mbar_wait(&p_ready[b], (u >> 1) & 1);
+        tc_fence_after();
+        const uint32_t pb = smem_u32(kp + b * 2 * kTileQ), vb = smem_u32(vt + b * 2 * kVtTile);
+        const uint64_t p1 = make_sw128_desc(pb), p2 = make_sw128_desc(pb + kTileQ);
+        const uint64_t v1 = make_sw128_desc(vb), v2 = make_sw128_desc(vb + kVtTile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t o = (uint64_t)(2 * k);
+          umma_bf16(tmem_base, p1 + o, v1 + o, idesc_o, (u | k) != 0);
+          umma_bf16(tmem_base, p2 + o, v1 + o, idesc_o, 1);
+          umma_bf16(tmem_base, p1 + o, v2 + o, idesc_o, 1);
+        }
+        umma_commit(&p_empty[b]);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ===== loaders / softmax: thread == query row == TMEM lane
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int t = threadIdx.x - 32;                             // 0..127, used for the V^T transposer
+    const float* base = qkv + (size_t)row0 * ld + head * 64;
+    // --- phase A: Q, then K chunks
+    load_split_row(base + (size_t)(q0 + r) * ld, q0 + r < len, q_op, q_op + kTileQ, r);
+    fence_proxy_async_smem();
+    mbar_arrive(q_ready);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int b = c & 1;
+      if (c >= 2) mbar_wait(&k_empty[b], ((c >> 1) - 1) & 1);
+      const int key = c * 128 + r;
+      uint8_t* k1 = kp + b * 2 * kTileQ;
+      load_split_row(base + hidden + (size_t)key * ld, key < len, k1, k1 + kTileQ, r);
+      fence_proxy_async_smem();
+      mbar_arrive(&k_ready[b]);
+    }
+    // --- phase B: exact row max
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float m = -INFINITY;
+    for (int c0 = 0; c0 < n_chunks * 128; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (c0 + j < len) m = fmaxf(m, __uint_as_float(v[j]));
+    }
+    // --- phase C: probabilities and V^T, 64 keys per unit
+    float sum = 0.f;
+    const uint32_t xr = (uint32_t)(r & 7);
+    const int vkey = t & 63, vd0 = (t >> 6) * 32;
+    for (int u = 0; u < n_units; ++u) {
+      const int b = u & 1;
+      if (u >= 2) mbar_wait(&p_empty[b], ((u >> 1) - 1) & 1);
+      {   // V^T tiles of this unit: element (d, key) <- V[key][d]
+        const int key = u * 64 + vkey;
+        const float* vsrc = base + 2 * hidden + (size_t)key * ld + vd0;
+        float4 vv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vv[i] = key < len ? __ldg(reinterpret_cast<const float4*>(vsrc) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint8_t* v1 = vt + b * 2 * kVtTile;
+        const uint32_t kchunk = (uint32_t)(vkey >> 3), kin = (uint32_t)(vkey & 7) * 2u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float f[4] = {vv[i].x, vv[i].y, vv[i].z, vv[i].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int d = vd0 + 4 * i + e;
+            const __nv_bfloat16 h = __float2bfloat16_rn(f[e]);
+            const __nv_bfloat16 l = __float2bfloat16_rn(f[e] - __bfloat162float(h));
+            const uint32_t off = (uint32_t)d * 128u + ((kchunk ^ (uint32_t)(d & 7)) << 4) + kin;
+            *reinterpret_cast<__nv_bfloat16*>(v1 + off) = h;
+            *reinterpret_cast<__nv_bfloat16*>(v1 + kVtTile + off) = l;
+          }
+        }
+      }
+      uint8_t* p1 = kp + b * 2 * kTileQ + (uint32_t)r * 128u;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        const int c0 = u * 64 + half * 32;
+        tmem_ld32(lane_addr + (uint32_t)c0, v);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float pa = (c0 + 2 * j < len) ? exp2f((__uint_as_float(v[2 * j]) - m) * scale_log2e) : 0.f;
+          const float pb = (c0 + 2 * j + 1 < len) ? exp2f((__uint_as_float(v[2 * j + 1]) - m) * scale_log2e) : 0.f;
+          sum += pa + pb;
+          split2(pa, pb, hi[j], lo[j]);
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const uint32_t off = (((uint32_t)(4 * half + qd)) ^ xr) << 4;
+          *reinterpret_cast<uint4*>(p1 + off) = make_uint4(hi[4 * qd], hi[4 * qd + 1], hi[4 * qd + 2], hi[4 * qd + 3]);
+          *reinterpret_cast<uint4*>(p1 + kTileQ + off) = make_uint4(lo[4 * qd], lo[4 * qd + 1], lo[4 * qd + 2], lo[4 * qd + 3]);
+        }
+      }
+      tc_fence_before();                         // S columns of this unit are consumed before O may overwrite them
+      fence_proxy_async_smem();
+      mbar_arrive(&p_ready[b]);
+    }
+    // --- phase D: normalise and store
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = __fdiv_rn(1.0f, sum);
+    float* orow = out + (size_t)(row0 + q0 + r) * hidden + head * 64;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + (uint32_t)(half * 32), v);
+      if (q0 + r < len) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(orow + half * 32 + 4 * j) =
+              make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
+                          __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+int attention_tc(const float* qkv, const int32_t* cu, int nseq, int max_len, int heads, int head_dim, float* out,
+                 cudaStream_t s) {
+  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (head_dim != 64 || max_len > 512) return VBG_EUNSUPPORTED;
+  constexpr size_t smem = 2 * kTileQ + 4 * kTileQ + 4 * kVtTile + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("attention_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return VBG_ECUDA; }
+    attr = true;
+  }
+  dim3 grid(cdiv(max_len, 128), heads, nseq);
+  attention_tc_kernel<<<grid, kAtThreads, smem, s>>>(qkv, cu, heads, 0.125f * 1.4426950408889634f, out);
+  return check_launch("vbg_attention_fwd(tcgen05)");
+}
+
+}  // namespace vbg

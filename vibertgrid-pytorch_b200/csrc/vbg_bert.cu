@@ -231,6 +231,9 @@ __global__ void full_head_scores_kernel(const float* __restrict__ pn, const floa
     out[(size_t)r * C + c] = gate ? __fdiv_rn(1.0f, 1.0f + expf(-cls[(size_t)r * (C - 1) + c - 1])) : 0.f;
 }
 
+int attention_tc(const float* qkv, const int32_t* cu, int nseq, int max_len, int heads, int head_dim, float* out,
+                 cudaStream_t s);
+
 }  // namespace vbg
 
 using namespace vbg;
@@ -270,7 +273,10 @@ extern "C" int vbg_attention_fwd(const float* qkv, const int32_t* cu, int nseq, 
   VBG_REQUIRE(head_dim == kAttD, "vbg_attention_fwd: head_dim must be 64 (got %d)", head_dim);
   VBG_REQUIRE(aligned16(qkv) && aligned16(out), "vbg_attention_fwd: 16B alignment required");
   if (nseq == 0 || max_len == 0) return VBG_OK;
-  (void)precision;
+  if (precision != VBG_PREC_FP32) {              // tensor-core kernel (fp32-class 3-term bf16 split) when it takes the shape
+    int rc = attention_tc(qkv, cu, nseq, max_len, heads, head_dim, out, as_stream(stream));
+    if (rc != VBG_EUNSUPPORTED) return rc;
+  }
   dim3 g(cdiv(max_len, kAttQ), heads, nseq);
   constexpr size_t smem = sizeof(float) * (kAttK * kAttD + (kAttQ + kAttK) * (kAttD + 1) + kAttQ * (kAttK + 1));
   static bool attr_set = false;   // idempotent; a race only repeats the same call

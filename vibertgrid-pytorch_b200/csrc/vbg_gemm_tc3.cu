@@ -26,22 +26,18 @@
 
 namespace vbg {
 
-constexpr uint32_t kLandBytes = BM * 128;      // 128 rows x 32 fp32
-constexpr uint32_t kAopBytes = BM * 128;       // 128 rows x 64 bf16
+constexpr uint32_t kAopBytes = BM * 128;       // 128 rows x 128 B: one 32-wide fp32 landing block == one 64-wide bf16 operand tile
 
-template <int BN, int STAGES, int kLand>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(kTcThreads)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
   constexpr uint32_t B_BYTES = BN * 128;                              // one bf16 plane tile: BN rows x 64 bf16
-  constexpr uint32_t STAGE_BYTES = 2 * kAopBytes + 2 * B_BYTES;       // A1 | A2 | W1 | W2
+  constexpr uint32_t STAGE_BYTES = 2 * kAopBytes + 2 * B_BYTES;       // A (fp32 landing, then A1 | A2 in place) | W1 | W2
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* land = smem;                                               // kLand x 16 KB
-  uint8_t* ring = smem + kLand * kLandBytes;
-  uint64_t* land_full = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES);
-  uint64_t* land_empty = land_full + kLand;
-  uint64_t* b_full = land_empty + kLand;
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES);
+  uint64_t* b_full = a_full + STAGES;
   uint64_t* a_ready = b_full + STAGES;
   uint64_t* st_empty = a_ready + STAGES;
   uint64_t* tmem_full = st_empty + STAGES;
@@ -56,8 +52,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < kLand; ++i) { mbar_init(&land_full[i], 1); mbar_init(&land_empty[i], 128); }
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&a_ready[s], 256); mbar_init(&st_empty[s], 1); }
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&a_full[s], 1); mbar_init(&b_full[s], 1); mbar_init(&a_ready[s], 128); mbar_init(&st_empty[s], 1);
+      }
       mbar_init(tmem_full, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -69,35 +66,35 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int n_land = 2 * p.num_kb;
 
   if (warp == 0) {
     if (lane == 0) {
-      // ===== TMA producer
-      const uint32_t a_bytes = p.conv ? (uint32_t)(p.tw * p.th * p.tb) * 128u : kLandBytes;
+      // ===== TMA producer: per 64-wide K block, two fp32 A boxes (32 floats each) land in the A1 / A2 regions of the
+      // stage (the converters split them in place) and the two bf16 weight planes land in W1 / W2.
+      const uint32_t a_bytes = 2u * (p.conv ? (uint32_t)(p.tw * p.th * p.tb) * 128u : kAopBytes);
       for (int kb = 0; kb < p.num_kb; ++kb) {
         const int s = kb % STAGES;
-        mbar_wait(&st_empty[s], ((kb / STAGES) & 1) ^ 1);            // stage free: A1/A2 may be rewritten, W tiles reloaded
-        uint8_t* sb = ring + s * STAGE_BYTES + 2 * kAopBytes;
-        mbar_expect_tx(&b_full[s], 2 * B_BYTES);
-        tma_load_2d(&tmW1, &b_full[s], sb, kb * 64, t.n0);
-        tma_load_2d(&tmW2, &b_full[s], sb + B_BYTES, kb * 64, t.n0);
-#pragma unroll 1
+        mbar_wait(&st_empty[s], ((kb / STAGES) & 1) ^ 1);
+        uint8_t* sa = ring + s * STAGE_BYTES;
+        uint8_t* sb = sa + 2 * kAopBytes;
+        mbar_expect_tx(&a_full[s], a_bytes);
+#pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int j = 2 * kb + h, l = j % kLand;
-          mbar_wait(&land_empty[l], ((j / kLand) & 1) ^ 1);
-          uint8_t* dst = land + l * kLandBytes;
-          mbar_expect_tx(&land_full[l], a_bytes);
+          const int j = 2 * kb + h;
+          uint8_t* dst = sa + h * kAopBytes;
           if (p.conv) {
             const int tap = j / p.cin_blocks, cb = j - tap * p.cin_blocks;
             const int fr = tap / p.kw, fs = tap - fr * p.kw;
-            tma_load_4d(&tmA, &land_full[l], dst, cb * BKE, t.w0 * p.sw + fs - p.pad_w, t.h0 * p.sh + fr - p.pad_h, t.b0);
+            tma_load_4d(&tmA, &a_full[s], dst, cb * BKE, t.w0 * p.sw + fs - p.pad_w, t.h0 * p.sh + fr - p.pad_h, t.b0);
           } else if (kb < p.kb_split) {
-            tma_load_2d(&tmA, &land_full[l], dst, j * BKE, t.m0);
+            tma_load_2d(&tmA, &a_full[s], dst, j * BKE, t.m0);
           } else {
-            tma_load_2d(&tmA2, &land_full[l], dst, (j - 2 * p.kb_split) * BKE, t.m0);
+            tma_load_2d(&tmA2, &a_full[s], dst, (j - 2 * p.kb_split) * BKE, t.m0);
           }
         }
+        mbar_expect_tx(&b_full[s], 2 * B_BYTES);
+        tma_load_2d(&tmW1, &b_full[s], sb, kb * 64, t.n0);
+        tma_load_2d(&tmW2, &b_full[s], sb + B_BYTES, kb * 64, t.n0);
       }
     }
   } else if (warp == 1) {
@@ -125,41 +122,38 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       umma_commit(tmem_full);
     }
   } else {
-    // ===== converters, then epilogue
-    const int r = threadIdx.x - 64;                // tile row 0..127
+    // ===== converters (thread == tile row; each thread rewrites only its own two 128-byte rows), then epilogue
+    const int r = threadIdx.x - 64;
     const uint32_t xr = (uint32_t)(r & 7);
 #pragma unroll 1
-    for (int j = 0; j < n_land; ++j) {
-      const int l = j % kLand, kb = j >> 1, h = j & 1, s = kb % STAGES;
-      mbar_wait(&land_full[l], (j / kLand) & 1);
-      const uint8_t* src = land + l * kLandBytes + r * 128;
-      float4 v[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(src + (((uint32_t)c ^ xr) << 4));
-      uint32_t hi[16], lo[16];
+    for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(&a_full[s], (kb / STAGES) & 1);
+      uint8_t* row1 = ring + s * STAGE_BYTES + r * 128;       // fp32 K-block 0 of this row  -> bf16 hi of all 64
+      uint8_t* row2 = row1 + kAopBytes;                        // fp32 K-block 1 of this row  -> bf16 lo of all 64
+      float4 v[16];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        const float f[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);     // .x = even element (low half)
-          const float r0 = f[2 * e] - __bfloat162float(hh.x), r1 = f[2 * e + 1] - __bfloat162float(hh.y);
-          const __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
-          hi[2 * c + e] = *reinterpret_cast<const uint32_t*>(&hh);
-          lo[2 * c + e] = *reinterpret_cast<const uint32_t*>(&ll);
-        }
+        v[c] = *reinterpret_cast<const float4*>(row1 + (((uint32_t)c ^ xr) << 4));
+        v[8 + c] = *reinterpret_cast<const float4*>(row2 + (((uint32_t)c ^ xr) << 4));
       }
-      uint8_t* d1 = ring + s * STAGE_BYTES + r * 128;
-      uint8_t* d2 = d1 + kAopBytes;
 #pragma unroll
-      for (int qd = 0; qd < 4; ++qd) {             // 16-byte chunk (4h + qd) of the 128-byte bf16 row
-        const uint32_t off = (((uint32_t)(4 * h + qd)) ^ xr) << 4;
-        *reinterpret_cast<uint4*>(d1 + off) = make_uint4(hi[4 * qd], hi[4 * qd + 1], hi[4 * qd + 2], hi[4 * qd + 3]);
-        *reinterpret_cast<uint4*>(d2 + off) = make_uint4(lo[4 * qd], lo[4 * qd + 1], lo[4 * qd + 2], lo[4 * qd + 3]);
+      for (int qd = 0; qd < 8; ++qd) {                         // bf16 chunk qd = elements 8qd .. 8qd+7 = float4 2qd, 2qd+1
+        const float f[8] = {v[2 * qd].x, v[2 * qd].y, v[2 * qd].z, v[2 * qd].w, v[2 * qd + 1].x, v[2 * qd + 1].y, v[2 * qd + 1].z, v[2 * qd + 1].w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);     // .x = even element (low half)
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(f[2 * e] - __bfloat162float(hh.x), f[2 * e + 1] - __bfloat162float(hh.y));
+          hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        const uint32_t off = (((uint32_t)qd) ^ xr) << 4;
+        *reinterpret_cast<uint4*>(row1 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(row2 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
       fence_proxy_async_smem();                    // operand tiles are read by the tensor core through the async proxy
       mbar_arrive(&a_ready[s]);
-      mbar_arrive(&land_empty[l]);
     }
     const int q = warp & 3;
     mbar_wait(tmem_full, 0);
@@ -202,18 +196,18 @@ static bool map_a_f32(CUtensorMap* tm, const float* base, long long rows, long l
   return tc_encode(tm, base, 2, dims, strides, box, nullptr, false);
 }
 
-template <int BN, int STAGES, int kLand>
+template <int BN, int STAGES>
 static int launch3(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& w1, const CUtensorMap& w2, const TcParams& p,
                    dim3 grid, cudaStream_t s) {
-  constexpr size_t smem = (size_t)kLand * kLandBytes + (size_t)STAGES * (2 * kAopBytes + 2 * BN * 128) + 1024 + 256;
+  constexpr size_t smem = (size_t)STAGES * (2 * kAopBytes + 2 * BN * 128) + 1024 + 256;
   static_assert(smem <= 232448, "bf16x3 tile does not fit the 227 KB shared-memory limit");
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc3_kernel<BN, STAGES, kLand>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc3_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("gemm_tc3: smem opt-in failed: %s", cudaGetErrorString(e)); return VBG_ECUDA; }
     attr = true;
   }
-  gemm_tc3_kernel<BN, STAGES, kLand><<<grid, kTcThreads, smem, s>>>(a, a2, w1, w2, p);
+  gemm_tc3_kernel<BN, STAGES><<<grid, kTcThreads, smem, s>>>(a, a2, w1, w2, p);
   return check_launch("vbg_gemm(tcgen05 bf16x3)");
 }
 
@@ -230,9 +224,9 @@ static int dispatch3(const CUtensorMap& a, const CUtensorMap& a2, const void* w_
   const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(w_hi);
   if (!map_w_bf16(&w1, hi, p.N, K, ldw, bn) || !map_w_bf16(&w2, hi + plane, p.N, K, ldw, bn)) return VBG_EUNSUPPORTED;
   dim3 grid(m_tiles, cdiv(p.N, bn));
-  if (bn == 256) return launch3<256, 2, 2>(a, a2, w1, w2, p, grid, s);
-  if (bn == 128) return launch3<128, 2, 4>(a, a2, w1, w2, p, grid, s);
-  return launch3<64, 3, 4>(a, a2, w1, w2, p, grid, s);
+  if (bn == 256) return launch3<256, 2>(a, a2, w1, w2, p, grid, s);
+  if (bn == 128) return launch3<128, 3>(a, a2, w1, w2, p, grid, s);
+  return launch3<64, 4>(a, a2, w1, w2, p, grid, s);
 }
 
 bool tc_conv_geometry(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, TcParams& p,
