@@ -311,9 +311,9 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    c0 = _lib.launch_count
+    c0 = eng.kernel_launches
     ms = time_region(step_resident, args.steps, True, world)
-    launches = _lib.launch_count - c0
+    launches = eng.kernel_launches - c0
     for i in range(2):
         step_e2e(i)
     ms_e2e = time_region(step_e2e, args.steps, True, world)
@@ -331,7 +331,7 @@ def main():
                        "scope_note": "forward only (eval mode): the training backward is not built yet (DESIGN.md section 7)"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": nbytes(host[0]),
                     "d2h_bytes_per_step": int(sink["pred"].numel() * 4 + sink["loss"].numel() * sink["loss"].element_size())},
-            "gpu_launches": launches, "clocks": clocks}
+            "gpu_launches": launches, "cuda_graph_replays": eng.graph_replays, "clocks": clocks}
     if rank == 0:
         fl = fwd_flops_as_executed(cfg)
         line["fwd_tflops_as_executed"] = fl * cfg.batch * args.steps / (ms / 1e3) / 1e12

@@ -110,3 +110,34 @@ def test_full_size_properties_cfg2(tmp_path, monkeypatch):
     p = full["pred_label"]
     assert torch.allclose(p.sum(1), torch.ones_like(p[:, 0]), atol=1e-5) and bool((p >= 0).all())
     assert int(full["status"].item()) == 0
+
+
+def test_cuda_graph_replay_equals_eager(tmp_path, monkeypatch):
+    """A batch signature seen twice is captured into a CUDA graph; replays with NEW data of the same shapes must equal the
+    eager launches bit for bit, and returned tensors must not alias the graph's static buffers."""
+    import dataclasses
+    from vibertgrid_pytorch_b200 import synth
+    fx = load_golden("tiny_simp")
+    monkeypatch.chdir(tmp_path)
+    cfg, kw, net, batch0 = build_case(fx["meta"])
+    net = net.cuda().eval()
+    eng = net._get_engine()
+    batches = [_to_dev(synth.make_batch(cfg, s)) for s in (fx["meta"]["input_seed"], fx["meta"]["input_seed"], 77, 78)]
+    same_shapes = all(tuple(t.shape for t in b[0]) == tuple(t.shape for t in batches[0][0]) and
+                      tuple(t.shape for t in b[3]) == tuple(t.shape for t in batches[0][3]) and b[4].shape == batches[0][4].shape
+                      for b in batches)
+    eng.use_graphs = False
+    eager = [[t.clone() for t in net(*b)[1:]] + [net.last_intermediates["logits"].clone()] for b in batches]
+    eng.use_graphs = True
+    kept = []
+    for i, b in enumerate(batches):
+        res = net(*b)
+        kept.append(res)
+        got = list(res[1:]) + [net.last_intermediates["logits"]]
+        for g, e in zip(got, eager[i]):
+            assert torch.equal(g, e), f"graph/eager mismatch at call {i}"
+    if same_shapes:
+        assert eng.graph_replays >= 3                  # call 0 eager, call 1 capture(+replay), calls 2, 3 replay
+        assert not torch.equal(kept[2][4], kept[3][4]) or torch.equal(eager[2][3], eager[3][3])   # copies, not aliases
+        for r, e in zip(kept[2][1:], eager[2]):
+            assert torch.equal(r, e)                   # still intact after later replays

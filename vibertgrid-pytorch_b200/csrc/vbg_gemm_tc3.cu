@@ -27,24 +27,45 @@
 namespace vbg {
 
 constexpr uint32_t kAopBytes = BM * 128;       // 128 rows x 128 B: one 32-wide fp32 landing block == one 64-wide bf16 operand tile
+constexpr int kTc3Threads = 320;               // warp 0 TMA, warp 1 MMA, warps 2-5 converters, warps 6-9 epilogue
+constexpr uint32_t kEpiBytes = 4 * kEpiStageFloats * 4;
 
+__device__ __forceinline__ TcTile tc3_tile(const TcParams& p, int tile, int bn) {
+  const int xt = tile % p.m_tiles;             // m fastest: CTAs running together share the weight tile
+  TcTile t{0, (tile / p.m_tiles) * bn, 0, 0, 0};
+  if (p.conv) {
+    int i = xt;
+    t.w0 = (i % p.tiles_w) * p.tw; i /= p.tiles_w;
+    t.h0 = (i % p.tiles_h) * p.th; i /= p.tiles_h;
+    t.b0 = i * p.tb;
+  } else {
+    t.m0 = xt * BM;
+  }
+  return t;
+}
+
+// Persistent: grid = min(#tiles, #SMs); each CTA walks tiles blockIdx.x, += gridDim.x with the operand ring running
+// straight through tile boundaries and two TMEM accumulators, so the epilogue of tile i overlaps the mainloop of tile i+1.
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTc3Threads, 1)
 gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const TcParams p) {
   constexpr uint32_t B_BYTES = BN * 128;                              // one bf16 plane tile: BN rows x 64 bf16
   constexpr uint32_t STAGE_BYTES = 2 * kAopBytes + 2 * B_BYTES;       // A (fp32 landing, then A1 | A2 in place) | W1 | W2
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES);
+  float* epi = reinterpret_cast<float*>(ring + STAGES * STAGE_BYTES);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES + kEpiBytes);
   uint64_t* b_full = a_full + STAGES;
   uint64_t* a_ready = b_full + STAGES;
   uint64_t* st_empty = a_ready + STAGES;
-  uint64_t* tmem_full = st_empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = st_empty + STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TcTile t = tc_tile_origin(p, BN);
+  const int n_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmW1); prefetch_tmap(&tmW2);
@@ -55,11 +76,11 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&a_full[s], 1); mbar_init(&b_full[s], 1); mbar_init(&a_ready[s], 128); mbar_init(&st_empty[s], 1);
       }
-      mbar_init(tmem_full, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -72,100 +93,123 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // ===== TMA producer: per 64-wide K block, two fp32 A boxes (32 floats each) land in the A1 / A2 regions of the
       // stage (the converters split them in place) and the two bf16 weight planes land in W1 / W2.
       const uint32_t a_bytes = 2u * (p.conv ? (uint32_t)(p.tw * p.th * p.tb) * 128u : kAopBytes);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&st_empty[s], ((kb / STAGES) & 1) ^ 1);
-        uint8_t* sa = ring + s * STAGE_BYTES;
-        uint8_t* sb = sa + 2 * kAopBytes;
-        mbar_expect_tx(&a_full[s], a_bytes);
+      int g = 0;                                                       // K blocks issued so far (runs through tiles)
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TcTile t = tc3_tile(p, tile, BN);
+        for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(&st_empty[s], ((g / STAGES) & 1) ^ 1);
+          uint8_t* sa = ring + s * STAGE_BYTES;
+          uint8_t* sb = sa + 2 * kAopBytes;
+          mbar_expect_tx(&a_full[s], a_bytes);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int j = 2 * kb + h;
-          uint8_t* dst = sa + h * kAopBytes;
-          if (p.conv) {
-            const int tap = j / p.cin_blocks, cb = j - tap * p.cin_blocks;
-            const int fr = tap / p.kw, fs = tap - fr * p.kw;
-            tma_load_4d(&tmA, &a_full[s], dst, cb * BKE, t.w0 * p.sw + fs - p.pad_w, t.h0 * p.sh + fr - p.pad_h, t.b0);
-          } else if (kb < p.kb_split) {
-            tma_load_2d(&tmA, &a_full[s], dst, j * BKE, t.m0);
-          } else {
-            tma_load_2d(&tmA2, &a_full[s], dst, (j - 2 * p.kb_split) * BKE, t.m0);
+          for (int h = 0; h < 2; ++h) {
+            const int j = 2 * kb + h;
+            uint8_t* dst = sa + h * kAopBytes;
+            if (p.conv) {
+              const int tap = j / p.cin_blocks, cb = j - tap * p.cin_blocks;
+              const int fr = tap / p.kw, fs = tap - fr * p.kw;
+              tma_load_4d(&tmA, &a_full[s], dst, cb * BKE, t.w0 * p.sw + fs - p.pad_w, t.h0 * p.sh + fr - p.pad_h, t.b0);
+            } else if (kb < p.kb_split) {
+              tma_load_2d(&tmA, &a_full[s], dst, j * BKE, t.m0);
+            } else {
+              tma_load_2d(&tmA2, &a_full[s], dst, (j - 2 * p.kb_split) * BKE, t.m0);
+            }
           }
+          mbar_expect_tx(&b_full[s], 2 * B_BYTES);
+          tma_load_2d(&tmW1, &b_full[s], sb, kb * 64, t.n0);
+          tma_load_2d(&tmW2, &b_full[s], sb + B_BYTES, kb * 64, t.n0);
         }
-        mbar_expect_tx(&b_full[s], 2 * B_BYTES);
-        tma_load_2d(&tmW1, &b_full[s], sb, kb * 64, t.n0);
-        tma_load_2d(&tmW2, &b_full[s], sb + B_BYTES, kb * 64, t.n0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ===== MMA issuer: per 16-wide K step  D += A1*W1 ; D += A2*W1 ; D += A1*W2
       constexpr uint32_t idesc = make_idesc(kFmtBF16, BM, BN);
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&b_full[s], ph);
-        mbar_wait(&a_ready[s], ph);
+      int g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t base = smem_u32(ring + s * STAGE_BYTES);
-        const uint64_t a1 = make_sw128_desc(base), a2 = make_sw128_desc(base + kAopBytes);
-        const uint64_t w1 = make_sw128_desc(base + 2 * kAopBytes), w2 = make_sw128_desc(base + 2 * kAopBytes + B_BYTES);
+        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1;
+          mbar_wait(&b_full[s], ph);
+          mbar_wait(&a_ready[s], ph);
+          tc_fence_after();
+          const uint32_t base = smem_u32(ring + s * STAGE_BYTES);
+          const uint64_t a1 = make_sw128_desc(base), a2 = make_sw128_desc(base + kAopBytes);
+          const uint64_t w1 = make_sw128_desc(base + 2 * kAopBytes), w2 = make_sw128_desc(base + 2 * kAopBytes + B_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {              // 16 bf16 = 32 B per MMA: +2 in the (addr>>4) field
-          const uint64_t o = (uint64_t)(2 * k);
-          umma_bf16(tmem_base, a1 + o, w1 + o, idesc, (kb | k) != 0);
-          umma_bf16(tmem_base, a2 + o, w1 + o, idesc, 1);
-          umma_bf16(tmem_base, a1 + o, w2 + o, idesc, 1);
+          for (int k = 0; k < 4; ++k) {            // 16 bf16 = 32 B per MMA: +2 in the (addr>>4) field
+            const uint64_t o = (uint64_t)(2 * k);
+            umma_bf16(d, a1 + o, w1 + o, idesc, (kb | k) != 0);
+            umma_bf16(d, a2 + o, w1 + o, idesc, 1);
+            umma_bf16(d, a1 + o, w2 + o, idesc, 1);
+          }
+          umma_commit(&st_empty[s]);
         }
-        umma_commit(&st_empty[s]);
+        umma_commit(&tmem_full[acc]);
       }
-      umma_commit(tmem_full);
     }
-  } else {
-    // ===== converters (thread == tile row; each thread rewrites only its own two 128-byte rows), then epilogue
+  } else if (warp < 6) {
+    // ===== converters (thread == tile row; each thread rewrites only its own two 128-byte rows)
     const int r = threadIdx.x - 64;
     const uint32_t xr = (uint32_t)(r & 7);
+    int g = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll 1
-    for (int kb = 0; kb < p.num_kb; ++kb) {
-      const int s = kb % STAGES;
-      mbar_wait(&a_full[s], (kb / STAGES) & 1);
-      uint8_t* row1 = ring + s * STAGE_BYTES + r * 128;       // fp32 K-block 0 of this row  -> bf16 hi of all 64
-      uint8_t* row2 = row1 + kAopBytes;                        // fp32 K-block 1 of this row  -> bf16 lo of all 64
-      float4 v[16];
+      for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+        const int s = g % STAGES;
+        mbar_wait(&a_full[s], (g / STAGES) & 1);
+        uint8_t* row1 = ring + s * STAGE_BYTES + r * 128;     // fp32 K-block 0 of this row  -> bf16 hi of all 64
+        uint8_t* row2 = row1 + kAopBytes;                      // fp32 K-block 1 of this row  -> bf16 lo of all 64
+        float4 v[16];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        v[c] = *reinterpret_cast<const float4*>(row1 + (((uint32_t)c ^ xr) << 4));
-        v[8 + c] = *reinterpret_cast<const float4*>(row2 + (((uint32_t)c ^ xr) << 4));
-      }
-#pragma unroll
-      for (int qd = 0; qd < 8; ++qd) {                         // bf16 chunk qd = elements 8qd .. 8qd+7 = float4 2qd, 2qd+1
-        const float f[8] = {v[2 * qd].x, v[2 * qd].y, v[2 * qd].z, v[2 * qd].w, v[2 * qd + 1].x, v[2 * qd + 1].y, v[2 * qd + 1].z, v[2 * qd + 1].w};
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);     // .x = even element (low half)
-          const __nv_bfloat162 ll = __floats2bfloat162_rn(f[2 * e] - __bfloat162float(hh.x), f[2 * e + 1] - __bfloat162float(hh.y));
-          hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
-          lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        for (int c = 0; c < 8; ++c) {
+          v[c] = *reinterpret_cast<const float4*>(row1 + (((uint32_t)c ^ xr) << 4));
+          v[8 + c] = *reinterpret_cast<const float4*>(row2 + (((uint32_t)c ^ xr) << 4));
         }
-        const uint32_t off = (((uint32_t)qd) ^ xr) << 4;
-        *reinterpret_cast<uint4*>(row1 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(row2 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+        for (int qd = 0; qd < 8; ++qd) {                       // bf16 chunk qd = elements 8qd .. 8qd+7 = float4 2qd, 2qd+1
+          const float f[8] = {v[2 * qd].x, v[2 * qd].y, v[2 * qd].z, v[2 * qd].w, v[2 * qd + 1].x, v[2 * qd + 1].y, v[2 * qd + 1].z, v[2 * qd + 1].w};
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);   // .x = even element (low half)
+            const __nv_bfloat162 ll = __floats2bfloat162_rn(f[2 * e] - __bfloat162float(hh.x), f[2 * e + 1] - __bfloat162float(hh.y));
+            hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+            lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          const uint32_t off = (((uint32_t)qd) ^ xr) << 4;
+          *reinterpret_cast<uint4*>(row1 + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(row2 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_proxy_async_smem();                  // operand tiles are read by the tensor core through the async proxy
+        mbar_arrive(&a_ready[s]);
       }
-      fence_proxy_async_smem();                    // operand tiles are read by the tensor core through the async proxy
-      mbar_arrive(&a_ready[s]);
     }
+  } else {
+    // ===== epilogue warps: TMEM lanes [32q, 32q+32), q = warp & 3
     const int q = warp & 3;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    tc_epilogue<BN>(p, t, tmem_base, q, lane, reinterpret_cast<float*>(ring) + q * kEpiStageFloats);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const TcTile t = tc3_tile(p, tile, BN);
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      tc_epilogue<BN>(p, t, tmem_base + (uint32_t)(acc * BN), q, lane, epi + q * kEpiStageFloats);
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -198,8 +242,8 @@ static bool map_a_f32(CUtensorMap* tm, const float* base, long long rows, long l
 
 template <int BN, int STAGES>
 static int launch3(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& w1, const CUtensorMap& w2, const TcParams& p,
-                   dim3 grid, cudaStream_t s) {
-  constexpr size_t smem = (size_t)STAGES * (2 * kAopBytes + 2 * BN * 128) + 1024 + 256;
+                   cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (2 * kAopBytes + 2 * BN * 128) + kEpiBytes + 1024 + 256;
   static_assert(smem <= 232448, "bf16x3 tile does not fit the 227 KB shared-memory limit");
   static bool attr = false;
   if (!attr) {
@@ -207,14 +251,28 @@ static int launch3(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMa
     if (e != cudaSuccess) { set_error("gemm_tc3: smem opt-in failed: %s", cudaGetErrorString(e)); return VBG_ECUDA; }
     attr = true;
   }
-  gemm_tc3_kernel<BN, STAGES><<<grid, kTcThreads, smem, s>>>(a, a2, w1, w2, p);
+  const int tiles = p.m_tiles * p.n_tiles;
+  gemm_tc3_kernel<BN, STAGES><<<tiles < kNumSMs ? tiles : kNumSMs, kTc3Threads, smem, s>>>(a, a2, w1, w2, p);
   return check_launch("vbg_gemm(tcgen05 bf16x3)");
 }
 
+// N-tile width: the candidate with the best (wave efficiency x tile efficiency).  Wider tiles re-read A less often;
+// the persistent grid makes the cost of a partial last wave explicit.
 static int pick_bn3(int m_tiles, int N) {
-  if (N >= 256 && (long long)m_tiles * cdiv(N, 256) >= kNumSMs) return 256;
-  if (N >= 128 && (long long)m_tiles * cdiv(N, 128) >= kNumSMs / 2) return 128;
-  return (N >= 128 && N % 128 == 0 && (long long)m_tiles * (N / 64) > 2 * kNumSMs) ? 128 : 64;
+  const int cand[4] = {256, 192, 128, 64};
+  int best = 64; double best_score = -1.0;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    if (bn > 64 && N < bn - 32) continue;                           // mostly-empty tile
+    const long long tiles = (long long)m_tiles * cdiv(N, bn);
+    const double waves = (double)tiles / kNumSMs;
+    const double wave_eff = waves / (double)((tiles + kNumSMs - 1) / kNumSMs);
+    const double fill = (double)N / ((double)cdiv(N, bn) * bn);     // useful columns in the N tiling
+    const double tile_eff = (double)bn / (bn + 96.0);               // per-tile A re-read / fixed-cost model
+    const double score = wave_eff * fill * tile_eff;
+    if (score > best_score) { best_score = score; best = bn; }
+  }
+  return best;
 }
 
 static int dispatch3(const CUtensorMap& a, const CUtensorMap& a2, const void* w_hi, long long plane, int ldw, int K, TcParams& p,
@@ -223,10 +281,11 @@ static int dispatch3(const CUtensorMap& a, const CUtensorMap& a2, const void* w_
   CUtensorMap w1, w2;
   const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(w_hi);
   if (!map_w_bf16(&w1, hi, p.N, K, ldw, bn) || !map_w_bf16(&w2, hi + plane, p.N, K, ldw, bn)) return VBG_EUNSUPPORTED;
-  dim3 grid(m_tiles, cdiv(p.N, bn));
-  if (bn == 256) return launch3<256, 2>(a, a2, w1, w2, p, grid, s);
-  if (bn == 128) return launch3<128, 3>(a, a2, w1, w2, p, grid, s);
-  return launch3<64, 4>(a, a2, w1, w2, p, grid, s);
+  p.m_tiles = m_tiles; p.n_tiles = cdiv(p.N, bn);
+  if (bn == 256) return launch3<256, 2>(a, a2, w1, w2, p, s);
+  if (bn == 192) return launch3<192, 2>(a, a2, w1, w2, p, s);
+  if (bn == 128) return launch3<128, 3>(a, a2, w1, w2, p, s);
+  return launch3<64, 4>(a, a2, w1, w2, p, s);
 }
 
 bool tc_conv_geometry(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, TcParams& p,

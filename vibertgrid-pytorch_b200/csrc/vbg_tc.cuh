@@ -103,6 +103,7 @@ constexpr int kEpiStageFloats = 32 * 36;   // per-warp 32x32 transpose buffer, r
 struct TcParams {
   float* C; int ldc;
   int M, N;
+  int m_tiles, n_tiles;   // persistent kernels: tile grid (m_tiles = row / spatial tiles)
   int num_kb;      // K blocks: of 32 fp32 (kind::tf32 kernel) or of 64 (bf16x3 kernel)
   int kb_split;    // first K block served by the second A map (cat-free two-source GEMM); == num_kb when unused
   // implicit-GEMM conv (conv == 1): output tile = tb images x th rows x tw cols (tw*th*tb <= 128)

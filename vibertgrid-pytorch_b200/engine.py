@@ -40,21 +40,39 @@ class _Prepared:
         self.misc: Dict[str, torch.Tensor] = {}
 
 
+def _cat_into(dst, parts):
+    """torch.cat into a static graph input (dtype converted when the caller's tensors differ from the staged dtype)."""
+    if all(p.dtype == dst.dtype for p in parts):
+        torch.cat(parts, 0, out=dst)
+    else:
+        dst.copy_(torch.cat(parts, 0), non_blocking=True)
+
+
 class ForwardEngine:
     def __init__(self, net):
         self.net = net
         self._prep: Optional[_Prepared] = None
         self._fp = None
+        self._fp_tensors = None
+        self._prep_gen = 0
+        self.kernel_launches = 0          # C-ABI kernel launches executed on the device (graph replays included)
         env = os.environ.get("VBG_PRECISION", "").lower()
         self.precision = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16x3": PREC_BF16X3}.get(env)
         self.launches = 0
+        self.use_graphs = os.environ.get("VBG_CUDA_GRAPHS", "1") != "0"
+        self.max_graphs = 8
+        self._graphs: Dict[tuple, dict] = {}
+        self.graph_replays = 0
 
     # ------------------------------------------------------------------ parameter preparation
     def invalidate(self):
-        self._prep, self._fp = None, None
+        self._prep, self._fp, self._fp_tensors = None, None, None
+        self._graphs.clear()
 
     def _fingerprint(self):
-        return tuple((t.data_ptr(), t._version) for t in self.net.state_dict(keep_vars=True).values())
+        if self._fp_tensors is None:      # Parameter / buffer objects survive .to() and in-place loads; cache the list
+            self._fp_tensors = list(self.net.parameters()) + list(self.net.buffers())
+        return tuple((t.data_ptr(), t._version) for t in self._fp_tensors)
 
     def _prepare(self):
         fp = self._fingerprint()
@@ -114,6 +132,8 @@ class ForwardEngine:
             pr.misc["full_w"] = torch.cat([n.layer.linear.weight for n in nets], 0).detach().contiguous()
             pr.misc["full_b"] = torch.cat([n.layer.linear.bias for n in nets], 0).detach().contiguous()
         self._prep, self._fp = pr, fp
+        self._prep_gen += 1
+        self._graphs.clear()              # captured graphs hold pointers into the previous preparation
         return pr
 
     # ------------------------------------------------------------------ building blocks
@@ -266,16 +286,75 @@ class ForwardEngine:
     # ------------------------------------------------------------------ whole forward
     @torch.no_grad()
     def run(self, image, seg_indices, seg_classes, coors, corpus, mask, want_seg=True):
+        """One joint forward.  A batch signature (all tensor shapes) seen for the second time is captured into a CUDA
+        graph; from then on the step is: copy the inputs into the graph's static buffers, one graph launch.
+        Tensors in the returned dict are owned by the engine and are overwritten by the next call with the same
+        signature (``ViBERTgridNet.forward`` clones what it returns)."""
         net = self.net
         dev = corpus.device
-        if dev.type != "cuda" and not getattr(self, "_test_standins", False):
+        standins = getattr(self, "_test_standins", False)
+        if dev.type != "cuda" and not standins:
             raise RuntimeError("ViBERTgridNet (B200) runs on CUDA tensors only; there is no CPU fallback")
-        pr = self._prepare()
-        B = len(image)
+        self._prepare()
         min_size = float(net.test_image_min_size)            # eval/inference branch of transform.py:192-196
-        plan = plan_batch([tuple(im.shape[-2:]) for im in image], [int(s.shape[0]) for s in seg_indices],
-                          [int(c.shape[0]) for c in coors], int(corpus.shape[1]), min_size, float(net.image_max_size))
+        shapes = (tuple(tuple(im.shape[-2:]) for im in image), tuple(int(s.shape[0]) for s in seg_indices),
+                  tuple(int(c.shape[0]) for c in coors), int(corpus.shape[1]))
+        want_seg = bool(want_seg and net.semantic_segmentation_head is not None)
+        key = (shapes, want_seg, self._prec(), self._prep_gen, dev.index)
+        ent = self._graphs.get(key) if self.use_graphs and not standins else None
+        if ent is not None and ent.get("graph") is not None:
+            st = ent["static"]
+            for dst, src in zip(st["image"], image):
+                dst.copy_(src, non_blocking=True)
+            _cat_into(st["coors"], [c.reshape(-1, 4) for c in coors])
+            _cat_into(st["seg_ids"], [s.reshape(-1) for s in seg_indices])
+            if want_seg:
+                _cat_into(st["cls"], [c.reshape(-1) for c in seg_classes])
+            st["corpus"].copy_(corpus, non_blocking=True)
+            ent["graph"].replay()
+            self.graph_replays += 1
+            self.kernel_launches += ent["launches"]
+            return ent["out"]
+
+        plan = plan_batch(list(shapes[0]), list(shapes[1]), list(shapes[2]), shapes[3], min_size, float(net.image_max_size))
         tab = torch.from_numpy(plan.table).to(dev)          # the step's only H2D besides the inputs
+        static = dict(
+            image=[im.contiguous() for im in image],
+            coors=torch.cat([c.reshape(-1, 4) for c in coors], 0).to(torch.int64).contiguous(),
+            seg_ids=torch.cat([s.reshape(-1) for s in seg_indices], 0).to(torch.int32).contiguous(),
+            cls=torch.cat([c.reshape(-1) for c in seg_classes], 0).to(torch.int32).contiguous() if want_seg else None,
+            corpus=corpus.contiguous(), tab=tab)
+        if self.use_graphs and not standins:
+            if ent is None:                                   # first sighting: run eagerly (also warms up lazy kernel attributes)
+                self._graphs[key] = {"graph": None}
+                if len(self._graphs) > self.max_graphs:
+                    self._graphs.pop(next(iter(self._graphs)))
+            else:                                             # second sighting: capture
+                static = {k: ([t.clone() for t in v] if isinstance(v, list) else (None if v is None else v.clone()))
+                          for k, v in static.items()}
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                c0 = ops.L.launch_count
+                with torch.cuda.graph(g):
+                    out = self._forward(plan, static, want_seg)
+                out["static"] = True
+                ent.update(graph=g, static=static, out=out, launches=ops.L.launch_count - c0)
+                g.replay()
+                self.graph_replays += 1
+                self.kernel_launches += ent["launches"]
+                return out
+        c0 = ops.L.launch_count if not standins else 0
+        out = self._forward(plan, static, want_seg)
+        if not standins:
+            self.kernel_launches += ops.L.launch_count - c0
+        return out
+
+    def _forward(self, plan, st, want_seg):
+        """The kernel sequence of one forward over staged inputs (capturable: no host sync, no host-dependent control flow)."""
+        net, pr = self.net, self._prep
+        B = plan.B
+        tab = st["tab"]
+        dev = tab.device
         dt = {k: tab[s:s + n] for k, (s, n) in plan.offsets.items()}
         dt["ratios"] = dt["ratios"].view(torch.float32)
         seg_off = dt["seg_off"]
@@ -284,23 +363,22 @@ class ForwardEngine:
 
         # a1 transform
         batch = torch.zeros((B, plan.H + 6, plan.W + 6, 4), dtype=torch.float32, device=dev)   # zero-bordered NHWC4 stem input
-        for b, im in enumerate(image):
-            ops.normalize_resize_pad(im.contiguous(), batch, b, plan.sizes[b][0], plan.sizes[b][1], net.image_mean, net.image_std)
-        coors_cat = torch.cat([c.reshape(-1, 4) for c in coors], 0).to(torch.int64).contiguous()
-        boxes = ops.resize_coords(coors_cat, seg_off, dt["ratios"], B)
+        for b, im in enumerate(st["image"]):
+            ops.normalize_resize_pad(im, batch, b, plan.sizes[b][0], plan.sizes[b][1], net.image_mean, net.image_std)
+        boxes = ops.resize_coords(st["coors"], seg_off, dt["ratios"], B)
         out["image_batch"], out["boxes"] = batch[:, 3:-3, 3:-3, :3], boxes     # view without border / pad channel
+        corpus, seg_ids = st["corpus"], st["seg_ids"]
 
         # a2 / a3 BERT + segment aggregation
-        hidden = self._bert(plan, dt, corpus.contiguous())
-        seg_ids = torch.cat([s.reshape(-1) for s in seg_indices], 0).to(torch.int32).contiguous()
+        hidden = self._bert(plan, dt, corpus)
         seg_start = ops.segment_starts(seg_ids, dt["tok_off"], B, plan.K, status)
         seg_emb = ops.segment_reduce(hidden, dt["tok_row"], seg_start, plan.K,
                                      ops.AGG_MEAN if net.grid_mode == "mean" else ops.AGG_FIRST)
         out["seg_emb"] = seg_emb
 
         # a4 BERTgrid
-        st = net.early_fusion_downsampling_ratio
-        idx = ops.box_index_map(boxes, seg_off, B, st, int(plan.H / st), int(plan.W / st))
+        gs = net.early_fusion_downsampling_ratio
+        idx = ops.box_index_map(boxes, seg_off, B, gs, int(plan.H / gs), int(plan.W / gs))
         grid = ops.grid_scatter(seg_emb, idx, seg_off)
         out["index_map"], out["bertgrid"] = idx, grid
 
@@ -309,9 +387,9 @@ class ForwardEngine:
         out["p_fuse"] = p_fuse
 
         # a6 auxiliary segmentation head
-        if want_seg and net.semantic_segmentation_head is not None:
+        if want_seg:
             out["pred_mask"], out["pred_ss"] = self._seg_head(p_fuse)
-            cls_cat = torch.cat([c.reshape(-1) for c in seg_classes], 0).to(torch.int32).contiguous()
+            cls_cat = st["cls"]
             out["pos_neg_labels"], out["class_labels"] = ops.label_paint(boxes, seg_off, cls_cat, B, plan.H, plan.W)
             out["gt_label"] = cls_cat
 

@@ -220,7 +220,7 @@ class ViBERTgridNet(nn.Module):
 
     def inference(self, image, seg_indices, coors, corpus, mask):
         out = self._get_engine().run(image, seg_indices, None, coors, corpus, mask, want_seg=False)
-        return out["pred_label"]
+        return out["pred_label"].clone() if out.get("static") else out["pred_label"]
 
     def forward(self, image, seg_indices, segment_classes, coors, corpus, mask):
         if self.training:
@@ -234,4 +234,7 @@ class ViBERTgridNet(nn.Module):
         loss_c = losses.main_loss(self, out)
         total_loss = loss_c + self.loss_control_lambda * loss_aux
         self.last_intermediates = out
-        return total_loss, out["pred_mask"], out["pred_ss"], out["gt_label"], out["pred_label"]
+        ret = (out["pred_mask"], out["pred_ss"], out["gt_label"], out["pred_label"])
+        if out.get("static"):          # CUDA-graph buffers are rewritten by the next call: hand out copies
+            ret = tuple(t.clone() for t in ret)
+        return (total_loss,) + ret
