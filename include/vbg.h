@@ -46,6 +46,9 @@ enum { VBG_ACT_NONE = 0, VBG_ACT_RELU = 1, VBG_ACT_GELU = 2 /* erf form, as HF "
 enum { VBG_RES_NONE = 0, VBG_RES_SAME = 1, /* residual[m*ldr + n]                                  */
        VBG_RES_UP2 = 2   /* residual is NHWC [B, out_h/2, out_w/2, N]: nearest x2 upsample-add   */ };
 enum { VBG_AGG_MEAN = 0, VBG_AGG_FIRST = 1 };
+enum { VBG_OUT_F32 = 0,        /* C is float [M, ldc]                                                                  */
+       VBG_OUT_SPLIT_BF16 = 1  /* C is bf16: hi plane [M, ldc] at C, lo plane out_plane ELEMENTS after it (tensor-core
+                                  paths only): the operand format of vbg_attention_split_fwd                          */ };
 
 typedef void* vbg_stream_t;
 
@@ -64,6 +67,8 @@ typedef struct vbg_epilogue {
   int ldr;               /* row stride of residual for VBG_RES_SAME */
   int out_h, out_w;      /* output spatial dims, needed by VBG_RES_UP2 for vbg_gemm            */
   int act;               /* VBG_ACT_* */
+  int out_mode;          /* VBG_OUT_* */
+  long long out_plane;   /* VBG_OUT_SPLIT_BF16: elements between the hi and the lo plane */
 } vbg_epilogue_t;
 
 VBG_API int vbg_version(void);
@@ -98,6 +103,11 @@ VBG_API int vbg_layernorm(const float* x, const float* gamma, const float* beta,
 /* softmax(Q K^T / sqrt(d)) V per sequence and head over packed qkv [R, 3*heads*d] (q | k | v). */
 VBG_API int vbg_attention_fwd(const float* qkv, const int32_t* cu, int nseq, int max_len, int heads, int head_dim,
                       float* out, int precision, vbg_stream_t stream);
+
+/* Same attention over the bf16 hi/lo planes written by vbg_gemm(..., VBG_OUT_SPLIT_BF16): qkv_hi is bf16 [R, 3*heads*64],
+ * the lo plane starts `plane` elements later.  TMA-fed tcgen05 kernel, fp32-class 3-term products; out is fp32. */
+VBG_API int vbg_attention_split_fwd(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len,
+                            int heads, int head_dim, float* out, vbg_stream_t stream);
 
 /* ---- a3: token -> segment aggregation (model/BERTgrid_generator.py:148-189) ----------------- */
 /* Run starts of consecutive-equal ids inside each sample.  status[0] |= 1 if #runs != K.        */

@@ -157,7 +157,7 @@ def label_paint(boxes, seg_off, seg_cls, B, H, W):
     return torch.from_numpy(pn), torch.from_numpy(cl)
 
 
-def gemm(A, W, *, A2=None, ep=None, precision=0, N=None, K=None, ldw=None, out=None, w_offset=0, W_split=None):
+def gemm(A, W, *, A2=None, ep=None, precision=0, N=None, K=None, ldw=None, out=None, w_offset=0, W_split=None, split_out=False):
     X = A if A2 is None else torch.cat([A, A2], 1)
     Kt = X.shape[1] if K is None else K
     Nn = W.shape[0] if N is None else N

@@ -313,6 +313,32 @@ def test_attention_tensor_core(ops, lens):
     assert relerr(got.numpy(), want.numpy()) < 3e-5
 
 
+@pytest.mark.parametrize("lens", [[512, 4, 77, 130], [200, 64, 65, 1, 128, 129, 300]])
+def test_split_qkv_gemm_and_tma_attention(ops, lens):
+    """QKV projection writing bf16 hi/lo planes (VBG_OUT_SPLIT_BF16) feeding the TMA-fed attention kernel (V consumed as an
+    MN-major operand, no transpose) against float64."""
+    assert ops.tc_available()
+    g = torch.Generator().manual_seed(len(lens) + 11)
+    hid, heads = 768, 12
+    cu = np.zeros(len(lens) + 1, np.int32); cu[1:] = np.cumsum(lens)
+    R = int(cu[-1])
+    x = torch.randn(R, hid, generator=g); Wq = torch.randn(3 * hid, hid, generator=g) / hid ** 0.5 * 1.5
+    bq = torch.randn(3 * hid, generator=g) * 0.1
+    Wd = Wq.cuda()
+    planes = ops.gemm(x.cuda(), Wd, ep=ops.make_epilogue(None, bq.cuda()), precision=ops.PREC_BF16X3, W_split=ops.split_bf16(Wd),
+                      split_out=True)
+    qkv = x.double() @ Wq.double().t() + bq
+    rec = planes[0].float().double().cpu() + planes[1].float().double().cpu()
+    assert planes.shape == (2, R, 3 * hid) and relerr(rec.numpy(), qkv.numpy()) < 2e-5
+    got = ops.attention_split(planes, torch.from_numpy(cu).cuda(), len(lens), max(lens), heads).cpu()
+    want = torch.empty(R, hid, dtype=torch.float64)
+    for q in range(len(lens)):
+        a, b = cu[q], cu[q + 1]
+        Q, K, V = [qkv[a:b, i * hid:(i + 1) * hid].reshape(b - a, heads, 64).transpose(0, 1) for i in range(3)]
+        want[a:b] = ((Q @ K.transpose(-1, -2) / 8).softmax(-1) @ V).transpose(0, 1).reshape(b - a, hid)
+    assert relerr(got.numpy(), want.numpy()) < 5e-5
+
+
 def test_crf_viterbi_matches_oracle(ops):
     g = torch.Generator().manual_seed(9)
     T, counts = 7, [40, 1, 13]

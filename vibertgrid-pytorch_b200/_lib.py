@@ -13,12 +13,13 @@ PREC_FP32, PREC_TF32, PREC_BF16X3 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 RES_NONE, RES_SAME, RES_UP2 = 0, 1, 2
 AGG_MEAN, AGG_FIRST = 0, 1
+OUT_F32, OUT_SPLIT_BF16 = 0, 1
 
 
 class Epilogue(C.Structure):
     _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
                 ("res_mode", C.c_int), ("ldr", C.c_int), ("out_h", C.c_int), ("out_w", C.c_int),
-                ("act", C.c_int)]
+                ("act", C.c_int), ("out_mode", C.c_int), ("out_plane", C.c_longlong)]
 
 
 class VbgError(RuntimeError):
@@ -39,6 +40,7 @@ SIGNATURES = {
     "vbg_embed_ln": [_p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _p, _p],
     "vbg_layernorm": [_p, _p, _p, _f, _i, _i, _p, _p],
     "vbg_attention_fwd": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
+    "vbg_attention_split_fwd": [_p, _ll, _p, _i, _i, _i, _i, _i, _p, _p],
     "vbg_segment_starts": [_p, _p, _i, _i, _i, _p, _p, _p],
     "vbg_segment_reduce": [_p, _p, _p, _i, _i, _i, _p, _p],
     "vbg_box_index_map": [_p, _p, _i, _i, _i, _i, _p, _p],

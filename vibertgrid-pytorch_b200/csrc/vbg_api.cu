@@ -103,6 +103,7 @@ static int check_epilogue(const vbg_epilogue_t* ep, const char* who) {
   VBG_REQUIRE(ep->act >= VBG_ACT_NONE && ep->act <= VBG_ACT_GELU, "%s: bad activation %d", who, ep->act);
   VBG_REQUIRE(ep->res_mode >= VBG_RES_NONE && ep->res_mode <= VBG_RES_UP2, "%s: bad residual mode %d", who, ep->res_mode);
   VBG_REQUIRE((ep->residual != nullptr) == (ep->res_mode != VBG_RES_NONE), "%s: residual pointer / mode mismatch", who);
+  VBG_REQUIRE(ep->out_mode == VBG_OUT_F32 || ep->out_mode == VBG_OUT_SPLIT_BF16, "%s: bad out_mode %d", who, ep->out_mode);
   return VBG_OK;
 }
 
@@ -131,6 +132,7 @@ extern "C" int vbg_gemm(const float* A, int lda, const float* A2, int lda2, int 
     rc = gemm_tc(A, lda, A2, lda2, K1, W, ldw, C, ldc, M, N, K, ep, s);
     if (rc != VBG_EUNSUPPORTED) return rc;
   }
+  VBG_REQUIRE(!ep || ep->out_mode == VBG_OUT_F32, "vbg_gemm: VBG_OUT_SPLIT_BF16 needs a tensor-core path (shape / precision not eligible)");
   return gemm_simt(A, lda, A2, lda2, K1, W, ldw, C, ldc, M, N, K, ep, s);
 }
 
@@ -156,6 +158,7 @@ extern "C" int vbg_conv2d(const float* x, int B, int H, int W, int Cin, const fl
     rc = conv_tc(x, B, H, W, Cin, w, Cout, kh, kw, stride, pad, y, ep, s);
     if (rc != VBG_EUNSUPPORTED) return rc;
   }
+  VBG_REQUIRE(!ep || ep->out_mode == VBG_OUT_F32, "vbg_conv2d: VBG_OUT_SPLIT_BF16 needs a tensor-core path");
   return conv_simt(x, B, H, W, Cin, w, Cout, kh, kw, stride, pad, y, ep, s);
 }
 

@@ -237,6 +237,217 @@ attention_tc_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ c
   }
 }
 
+// ------------------------------------------------------------------ v2: operands arrive pre-split from the QKV GEMM
+// The QKV projection writes bf16 hi / lo planes (VBG_OUT_SPLIT_BF16), so nothing is converted here: TMA drops Q, K
+// (K-major: row = token, 64 head dims = 128 B) and V (the same rows, used as an MN-major B operand -- no transpose)
+// straight into SWIZZLE_128B operand tiles.  The 128 softmax threads only do row max, exp, and the hi/lo split of P.
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 softmax (thread == query row == TMEM lane)
+constexpr int kAt2Threads = 192;
+constexpr uint32_t kVTile = 64 * 128;        // 64 keys x 64 dims (bf16)
+
+__global__ void __launch_bounds__(kAt2Threads, 1)
+attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_constant__ CUtensorMap tmQKl,
+                       const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
+                       const int32_t* __restrict__ cu, int heads, float scale_log2e, float* __restrict__ out) {
+  const int seq = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * 128;
+  const int row0 = cu[seq], len = cu[seq + 1] - row0;
+  if (q0 >= len) return;
+  const int n_chunks = (len + 127) >> 7, n_units = (len + 63) >> 6;
+  const int hidden = heads * 64;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_op = smem;                                         // Q1 | Q2                32 KB
+  uint8_t* k_op = q_op + 2 * kTileQ;                            // 2 x (K1 | K2)          64 KB
+  uint8_t* v_op = k_op + 4 * kTileQ;                            // 2 x (V1 | V2)          32 KB
+  uint8_t* p_op = v_op + 4 * kVTile;                            // 2 x (P1 | P2)          64 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_op + 4 * kTileQ);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *s_full = bars + 5, *v_full = bars + 6,
+           *p_ready = bars + 8, *pv_done = bars + 10, *o_full = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmQKh); prefetch_tmap(&tmQKl); prefetch_tmap(&tmVh); prefetch_tmap(&tmVl); }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(o_full, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer
+      mbar_expect_tx(q_full, 2 * kTileQ);
+      tma_load_2d(&tmQKh, q_full, q_op, head * 64, row0 + q0);
+      tma_load_2d(&tmQKl, q_full, q_op + kTileQ, head * 64, row0 + q0);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int b = c & 1;
+        mbar_wait(&k_empty[b], ((c >> 1) & 1) ^ 1);
+        uint8_t* dst = k_op + b * 2 * kTileQ;
+        mbar_expect_tx(&k_full[b], 2 * kTileQ);
+        tma_load_2d(&tmQKh, &k_full[b], dst, hidden + head * 64, row0 + c * 128);
+        tma_load_2d(&tmQKl, &k_full[b], dst + kTileQ, hidden + head * 64, row0 + c * 128);
+      }
+      for (int u = 0; u < n_units; ++u) {
+        const int b = u & 1;
+        mbar_wait(&pv_done[b], ((u >> 1) & 1) ^ 1);
+        uint8_t* dst = v_op + b * 2 * kVTile;
+        mbar_expect_tx(&v_full[b], 2 * kVTile);
+        tma_load_2d(&tmVh, &v_full[b], dst, 2 * hidden + head * 64, row0 + u * 64);
+        tma_load_2d(&tmVl, &v_full[b], dst + kVTile, 2 * hidden + head * 64, row0 + u * 64);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer
+      constexpr uint32_t idesc_s = make_idesc(kFmtBF16, 128, 128);
+      constexpr uint32_t idesc_o = make_idesc(kFmtBF16, 128, 64, /*b_mn_major=*/1);
+      const uint64_t q1 = make_sw128_desc(smem_u32(q_op)), q2 = make_sw128_desc(smem_u32(q_op + kTileQ));
+      mbar_wait(q_full, 0);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int b = c & 1;
+        mbar_wait(&k_full[b], (c >> 1) & 1);
+        tc_fence_after();
+        const uint32_t kb = smem_u32(k_op + b * 2 * kTileQ);
+        const uint64_t k1 = make_sw128_desc(kb), k2 = make_sw128_desc(kb + kTileQ);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t o = (uint64_t)(2 * k);
+          umma_bf16(tmem_base + (uint32_t)(c * 128), q1 + o, k1 + o, idesc_s, k != 0);
+          umma_bf16(tmem_base + (uint32_t)(c * 128), q2 + o, k1 + o, idesc_s, 1);
+          umma_bf16(tmem_base + (uint32_t)(c * 128), q1 + o, k2 + o, idesc_s, 1);
+        }
+        umma_commit(&k_empty[b]);
+      }
+      umma_commit(s_full);
+      for (int u = 0; u < n_units; ++u) {
+        const int b = u & 1;
+        const uint32_t ph = (u >> 1) & 1;
+        mbar_wait(&v_full[b], ph);
+        mbar_wait(&p_ready[b], ph);
+        tc_fence_after();
+        const uint32_t pb = smem_u32(p_op + b * 2 * kTileQ), vb = smem_u32(v_op + b * 2 * kVTile);
+        const uint64_t p1 = make_sw128_desc(pb), p2 = make_sw128_desc(pb + kTileQ);
+        const uint64_t v1 = make_sw128_desc(vb), v2 = make_sw128_desc(vb + kVTile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t oa = (uint64_t)(2 * k);        // P: K-major, 16 keys = 32 B along the row
+          const uint64_t ob = (uint64_t)(128 * k);      // V: MN-major, 16 keys = 16 rows x 128 B = 2048 B
+          umma_bf16(tmem_base, p1 + oa, v1 + ob, idesc_o, (u | k) != 0);
+          umma_bf16(tmem_base, p2 + oa, v1 + ob, idesc_o, 1);
+          umma_bf16(tmem_base, p1 + oa, v2 + ob, idesc_o, 1);
+        }
+        umma_commit(&pv_done[b]);
+      }
+      umma_commit(o_full);
+    }
+  } else {
+    // ===== softmax
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+    float m = -INFINITY;
+    for (int c0 = 0; c0 < n_chunks * 128; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (c0 + j < len) m = fmaxf(m, __uint_as_float(v[j]));
+    }
+    float sum = 0.f;
+    const uint32_t xr = (uint32_t)(r & 7);
+    for (int u = 0; u < n_units; ++u) {
+      const int b = u & 1;
+      if (u >= 2) mbar_wait(&pv_done[b], ((u >> 1) - 1) & 1);
+      uint8_t* p1 = p_op + b * 2 * kTileQ + (uint32_t)r * 128u;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        const int c0 = u * 64 + half * 32;
+        tmem_ld32(lane_addr + (uint32_t)c0, v);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float pa = (c0 + 2 * j < len) ? exp2f((__uint_as_float(v[2 * j]) - m) * scale_log2e) : 0.f;
+          const float pb = (c0 + 2 * j + 1 < len) ? exp2f((__uint_as_float(v[2 * j + 1]) - m) * scale_log2e) : 0.f;
+          sum += pa + pb;
+          split2(pa, pb, hi[j], lo[j]);
+        }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const uint32_t off = (((uint32_t)(4 * half + qd)) ^ xr) << 4;
+          *reinterpret_cast<uint4*>(p1 + off) = make_uint4(hi[4 * qd], hi[4 * qd + 1], hi[4 * qd + 2], hi[4 * qd + 3]);
+          *reinterpret_cast<uint4*>(p1 + kTileQ + off) = make_uint4(lo[4 * qd], lo[4 * qd + 1], lo[4 * qd + 2], lo[4 * qd + 3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      mbar_arrive(&p_ready[b]);
+    }
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = __fdiv_rn(1.0f, sum);
+    float* orow = out + (size_t)(row0 + q0 + r) * hidden + head * 64;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      tmem_ld32(lane_addr + (uint32_t)(half * 32), v);
+      if (q0 + r < len) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(orow + half * 32 + 4 * j) =
+              make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
+                          __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len, int heads,
+                    int head_dim, float* out, cudaStream_t s) {
+  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (head_dim != 64 || max_len > 512 || !aligned16(qkv_hi) || ((plane * 2) & 15)) return VBG_EUNSUPPORTED;
+  const long long ld = 3LL * heads * 64;
+  const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(qkv_hi);
+  CUtensorMap mq[2], mv[2];
+  for (int i = 0; i < 2; ++i) {
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)R};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box_qk[2] = {64u, 128u}, box_v[2] = {64u, 64u};
+    if (!tc_encode(&mq[i], hi + i * plane, 2, dims, strides, box_qk, nullptr, true)) return VBG_EUNSUPPORTED;
+    if (!tc_encode(&mv[i], hi + i * plane, 2, dims, strides, box_v, nullptr, true)) return VBG_EUNSUPPORTED;
+  }
+  constexpr size_t smem = 2 * kTileQ + 4 * kTileQ + 4 * kVTile + 4 * kTileQ + 1024 + 256;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("attention_split: smem opt-in failed: %s", cudaGetErrorString(e)); return VBG_ECUDA; }
+    attr = true;
+  }
+  dim3 grid(cdiv(max_len, 128), heads, nseq);
+  attention_split_kernel<<<grid, kAt2Threads, smem, s>>>(mq[0], mq[1], mv[0], mv[1], cu, heads, 0.125f * 1.4426950408889634f, out);
+  return check_launch("vbg_attention_split_fwd(tcgen05)");
+}
+
 int attention_tc(const float* qkv, const int32_t* cu, int nseq, int max_len, int heads, int head_dim, float* out,
                  cudaStream_t s) {
   if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;

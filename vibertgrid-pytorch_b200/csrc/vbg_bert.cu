@@ -233,6 +233,8 @@ __global__ void full_head_scores_kernel(const float* __restrict__ pn, const floa
 
 int attention_tc(const float* qkv, const int32_t* cu, int nseq, int max_len, int heads, int head_dim, float* out,
                  cudaStream_t s);
+int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len, int heads,
+                    int head_dim, float* out, cudaStream_t s);
 
 }  // namespace vbg
 
@@ -287,6 +289,16 @@ extern "C" int vbg_attention_fwd(const float* qkv, const int32_t* cu, int nseq, 
   }
   attention_simt_kernel<<<g, 256, smem, as_stream(stream)>>>(qkv, cu, heads, 1.0f / sqrtf((float)head_dim), out);
   return check_launch("vbg_attention_fwd");
+}
+
+extern "C" int vbg_attention_split_fwd(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len,
+                                       int heads, int head_dim, float* out, vbg_stream_t stream) {
+  VBG_REQUIRE(qkv_hi && cu && out && nseq >= 0 && R >= 0 && heads > 0 && plane > 0, "vbg_attention_split_fwd: bad arguments");
+  if (nseq == 0 || max_len == 0) return VBG_OK;
+  int rc = attention_split(qkv_hi, plane, cu, nseq, R, max_len, heads, head_dim, out, as_stream(stream));
+  if (rc == VBG_EUNSUPPORTED)
+    set_error("vbg_attention_split_fwd: needs sm_100a, head_dim 64, max_len <= 512 (got head_dim %d, max_len %d)", head_dim, max_len);
+  return rc;
 }
 
 extern "C" int vbg_softmax_rows(const float* x, int R, int C, float* y, vbg_stream_t stream) {

@@ -2,6 +2,7 @@
 #pragma once
 #include "vbg_common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 namespace vbg {
 
@@ -90,8 +91,8 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 // Instruction descriptor (32-bit): D=f32 [4,6)=1; A fmt [7,10), B fmt [10,13) (kind::tf32: TF32=2; kind::f16: F16=0, BF16=1);
 // A,B K-major (bits 15,16 = 0); N>>3 at [17,23); M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_fmt, int m, int n) {
-  return (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_fmt, int m, int n, uint32_t b_mn_major = 0) {
+  return (1u << 4) | (ab_fmt << 7) | (ab_fmt << 10) | (b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 constexpr uint32_t kFmtTF32 = 2, kFmtBF16 = 1;
 
@@ -207,6 +208,23 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const TcTile& t, 
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[e] = apply_act(o[e], ep.act);
+      if (ep.out_mode == VBG_OUT_SPLIT_BF16) {          // bf16 hi / lo planes (operands of the split attention kernel)
+        __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(p.C) + out_off[it] + n;
+        __nv_bfloat16* lp = hp + ep.out_plane;
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { h[e] = __float2bfloat16_rn(o[e]); l[e] = __float2bfloat16_rn(o[e] - __bfloat162float(h[e])); }
+        if (vec_ok && n + 3 < p.N && (ep.out_plane & 3) == 0) {
+          *reinterpret_cast<uint2*>(hp) = make_uint2((uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
+                                                     (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
+          *reinterpret_cast<uint2*>(lp) = make_uint2((uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
+                                                     (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) if (n + e < p.N) { hp[e] = h[e]; lp[e] = l[e]; }
+        }
+        continue;
+      }
       float* cp = p.C + out_off[it] + n;
       if (vec_ok && n + 3 < p.N) {
         *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);

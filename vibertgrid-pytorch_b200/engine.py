@@ -213,9 +213,17 @@ class ForwardEngine:
                          e.token_type_embeddings.weight.detach()[0], e.LayerNorm.weight.detach(),
                          e.LayerNorm.bias.detach(), e.LayerNorm.eps)
         prec = self._prec()
+        hid = bm.cfg["hidden_size"]
+        split_attn = (prec == PREC_BF16X3 and hid // heads == 64 and hid % 64 == 0 and plan.max_len <= 512
+                      and os.environ.get("VBG_ATTN_SPLIT", "1") != "0")
         for lyr, pk in zip(bm.encoder.layer, pr.bert_layers):
-            qkv = ops.gemm(x, pk["wqkv"], ep=make_epilogue(None, pk["bqkv"]), precision=prec, W_split=pk["wqkv_split"])
-            ctx = ops.attention(qkv, cu, plan.nseq, plan.max_len, heads, prec)
+            if split_attn:      # QKV projection writes bf16 hi/lo planes; TMA-fed tcgen05 attention consumes them directly
+                qkv = ops.gemm(x, pk["wqkv"], ep=make_epilogue(None, pk["bqkv"]), precision=prec, W_split=pk["wqkv_split"],
+                               split_out=True)
+                ctx = ops.attention_split(qkv, cu, plan.nseq, plan.max_len, heads)
+            else:
+                qkv = ops.gemm(x, pk["wqkv"], ep=make_epilogue(None, pk["bqkv"]), precision=prec, W_split=pk["wqkv_split"])
+                ctx = ops.attention(qkv, cu, plan.nseq, plan.max_len, heads, prec)
             ao = lyr.attention.output
             a = self._lin(ctx, ao.dense, residual=x)
             x = ops.layernorm(a, ao.LayerNorm.weight.detach(), ao.LayerNorm.bias.detach(), ao.LayerNorm.eps, out=a)

@@ -108,6 +108,18 @@ def attention(qkv, cu, nseq, max_len, heads, precision=PREC_FP32):
     return out
 
 
+def attention_split(qkv_split, cu, nseq, max_len, heads):
+    """Attention over the bf16 [2, R, 3*hidden] hi/lo planes of ``gemm(..., split_out=True)`` -> fp32 [R, hidden]."""
+    if qkv_split.dtype != torch.bfloat16 or qkv_split.dim() != 3 or qkv_split.shape[0] != 2 or not qkv_split.is_contiguous():
+        raise TypeError("attention_split expects the contiguous bf16 [2, R, 3*hidden] tensor of gemm(..., split_out=True)")
+    _, R, three_h = qkv_split.shape
+    hidden = three_h // 3
+    out = torch.empty((R, hidden), dtype=torch.float32, device=qkv_split.device)
+    L.check(L.load().vbg_attention_split_fwd(_p(qkv_split), R * three_h, _i32(cu), nseq, R, max_len, heads, hidden // heads,
+                                             _f32(out), _stream()), "vbg_attention_split_fwd")
+    return out
+
+
 # ------------------------------------------------------------------ a3
 def segment_starts(seg_ids, tok_off, B, K, status):
     n_tok = seg_ids.shape[0]
@@ -168,19 +180,28 @@ def _split_args(W_split, w_offset):
 
 
 def gemm(A, W, *, A2=None, ep: Optional[Epilogue] = None, precision=PREC_FP32, N=None, K=None, ldw=None, out=None,
-         w_offset=0, W_split=None):
-    """C[M,N] = epilogue([A | A2] @ W[N,K]^T).  ``w_offset``/``ldw``/``N``/``K`` select a sub-block of W (and W_split)."""
+         w_offset=0, W_split=None, split_out=False):
+    """C[M,N] = epilogue([A | A2] @ W[N,K]^T).  ``w_offset``/``ldw``/``N``/``K`` select a sub-block of W (and W_split).
+    ``split_out``: return bf16 [2, M, N] hi/lo planes instead of fp32 (tensor-core paths only)."""
     M, K1 = A.shape
     K2 = 0 if A2 is None else A2.shape[1]
     Kt = K1 + K2 if K is None else K
     Nn = W.shape[0] if N is None else N
     ldw_ = W.stride(0) if ldw is None else ldw
-    if out is None:
-        out = torch.empty((M, Nn), dtype=torch.float32, device=A.device)
+    if split_out:
+        if ep is None:
+            ep = make_epilogue()
+        out = torch.empty((2, M, Nn), dtype=torch.bfloat16, device=A.device)
+        ep.out_mode, ep.out_plane = L.OUT_SPLIT_BF16, M * Nn
+        optr, ldc = _p(out), Nn
+    else:
+        if out is None:
+            out = torch.empty((M, Nn), dtype=torch.float32, device=A.device)
+        optr, ldc = _f32(out, "out"), out.stride(0)
     wp = _f32(W, "W") + 4 * w_offset
     sp, plane = _split_args(W_split, w_offset)
     L.check(L.load().vbg_gemm(_f32(A, "A"), A.stride(0), _f32(A2, "A2"), 0 if A2 is None else A2.stride(0), K1, wp, ldw_,
-                              sp, plane, _f32(out, "out"), out.stride(0), M, Nn, Kt,
+                              sp, plane, optr, ldc, M, Nn, Kt,
                               C.byref(ep) if ep is not None else None, precision, _stream()), "vbg_gemm")
     return out
 
