@@ -10,6 +10,7 @@
 // each bilinear tap is a fully coalesced C*4-byte read (C=256 -> 1 KiB) instead of torchvision's
 // one-thread-per-output NCHW gather.  Geometry is computed once per warp (uniform registers).
 #include "vbg_common.cuh"
+#include <stdlib.h>
 
 namespace vbg {
 
@@ -87,6 +88,94 @@ roi_align_kernel(const float* __restrict__ feat, int B, int Hf, int Wf, int C, c
   }
 }
 
+// ------------------------------------------------------------------ separable form (the default for P == 7)
+// Bilinear weights factor (w = wy * wx) and so do the skip / clamp rules (each depends on one coordinate only), hence
+//   out[ph,pw,c] = 1/count * sum_yy Wy[ph][yy] * ( sum_xx Wx[pw][xx] * f[yy][xx][c] ),
+// with Wy[ph][.] / Wx[pw][.] the per-bin sums of the samples' row / column weights.  One CTA per ROI builds the two small
+// weight tables in shared memory (same coordinate arithmetic, operation for operation, as the direct kernel, so the
+// sample-grid table stays bit-exact), then every thread owns 4 channels and streams the rows of its bin-row: each
+// feature value is loaded once per (bin-row, bin-column) it contributes to instead of once per sample -- about half the
+// L1 traffic of the direct form at typical line boxes, which is what bounds that kernel (ncu: 33% L1, 42% of HBM peak).
+// Values differ from torchvision's summation order by fp32 re-association only (<= 1e-6 rel).
+template <int P>
+__global__ void __launch_bounds__(256)
+roi_align_sep_kernel(const float* __restrict__ feat, int B, int Hf, int Wf, int C, const int32_t* __restrict__ boxes,
+                     const int32_t* __restrict__ seg_off, float scale, float* __restrict__ out,
+                     int32_t* __restrict__ sample_grid, int tab_stride) {
+  extern __shared__ float tab[];                  // [2][P][tab_stride]: x weights, then y weights
+  __shared__ int t_start[2][P], t_cnt[2][P];
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const int b = sample_of(seg_off, B, k);
+  const int4 bx = __ldg(reinterpret_cast<const int4*>(boxes) + k);
+  const float sw = __fmul_rn((float)bx.x, scale), sh = __fmul_rn((float)bx.y, scale);
+  const float ew = __fmul_rn((float)bx.z, scale), eh = __fmul_rn((float)bx.w, scale);
+  const float rw = fmaxf(__fsub_rn(ew, sw), 1.0f), rh = fmaxf(__fsub_rn(eh, sh), 1.0f);
+  const float bw = __fdiv_rn(rw, (float)P), bh = __fdiv_rn(rh, (float)P);
+  const int gh = (int)ceilf(__fdiv_rn(rh, (float)P));
+  const int gw = (int)ceilf(__fdiv_rn(rw, (float)P));
+  if (sample_grid && tid == 0) { sample_grid[2 * k] = gh; sample_grid[2 * k + 1] = gw; }
+  const float count = (float)max(gh * gw, 1);
+
+  for (int i = tid; i < 2 * P * tab_stride; i += blockDim.x) tab[i] = 0.f;
+  __syncthreads();
+  if (tid < 2 * P) {
+    const int axis = tid / P, pb = tid - axis * P;            // axis 0: x (columns), 1: y (rows)
+    const int g = axis ? gh : gw, dim = axis ? Hf : Wf;
+    const float start = axis ? sh : sw, bin = axis ? bh : bw;
+    float* w = tab + (size_t)(axis * P + pb) * tab_stride;
+    int base = 0, cnt = 0;
+    for (int i = 0; i < g; ++i) {
+      float c = __fadd_rn(__fadd_rn(start, __fmul_rn((float)pb, bin)), __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)g));
+      if (c < -1.0f || c > (float)dim) continue;
+      c = fmaxf(c, 0.f);
+      int lo = (int)c, hi;
+      if (lo >= dim - 1) { hi = lo = dim - 1; c = (float)lo; } else { hi = lo + 1; }
+      const float l = c - (float)lo, h = 1.f - l;
+      if (cnt == 0) base = lo;
+      w[lo - base] += h;
+      w[hi - base] += l;
+      cnt = hi - base + 1;
+    }
+    t_start[axis][pb] = base;
+    t_cnt[axis][pb] = cnt;
+  }
+  __syncthreads();
+
+  const int C4 = C >> 2, c4 = tid % C4, grp = tid / C4, G = blockDim.x / C4;
+  const float4* f4 = reinterpret_cast<const float4*>(feat) + (size_t)b * Hf * Wf * C4 + c4;
+  float4* o4 = reinterpret_cast<float4*>(out) + (size_t)k * P * P * C4 + c4;
+  for (int ph = grp; ph < P; ph += G) {
+    float4 acc[P];
+#pragma unroll
+    for (int pw = 0; pw < P; ++pw) acc[pw] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* wyp = tab + (size_t)(P + ph) * tab_stride;
+    const int y0 = t_start[1][ph], ny = t_cnt[1][ph];
+    for (int j = 0; j < ny; ++j) {
+      const float wy = wyp[j];
+      const float4* rowp = f4 + (size_t)(y0 + j) * Wf * C4;
+#pragma unroll
+      for (int pw = 0; pw < P; ++pw) {
+        const float* wxp = tab + (size_t)pw * tab_stride;
+        const int x0 = t_start[0][pw], nx = t_cnt[0][pw];
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < nx; ++i) {
+          const float w = wxp[i];
+          const float4 v = __ldg(rowp + (size_t)(x0 + i) * C4);
+          t.x = fmaf(w, v.x, t.x); t.y = fmaf(w, v.y, t.y); t.z = fmaf(w, v.z, t.z); t.w = fmaf(w, v.w, t.w);
+        }
+        acc[pw].x = fmaf(wy, t.x, acc[pw].x); acc[pw].y = fmaf(wy, t.y, acc[pw].y);
+        acc[pw].z = fmaf(wy, t.z, acc[pw].z); acc[pw].w = fmaf(wy, t.w, acc[pw].w);
+      }
+    }
+#pragma unroll
+    for (int pw = 0; pw < P; ++pw) {
+      float4 r = acc[pw];
+      r.x = __fdiv_rn(r.x, count); r.y = __fdiv_rn(r.y, count); r.z = __fdiv_rn(r.z, count); r.w = __fdiv_rn(r.w, count);
+      o4[(size_t)(ph * P + pw) * C4] = r;
+    }
+  }
+}
+
 }  // namespace vbg
 
 using namespace vbg;
@@ -99,6 +188,17 @@ extern "C" int vbg_roi_align_fwd(const float* feat, int B, int Hf, int Wf, int C
   VBG_REQUIRE(C > 0 && C % 4 == 0 && C <= 1024 && aligned16(feat) && aligned16(out) && aligned16(boxes),
               "vbg_roi_align_fwd: C %% 4 == 0, C <= 1024 and 16B alignment required (C=%d)", C);
   if (K == 0) return VBG_OK;
+  {
+    const int C4 = C / 4;
+    static const bool direct = [] { const char* e = getenv("VBG_ROI_DIRECT"); return e && e[0] == '1'; }();
+    const int tab_stride = (Hf > Wf ? Hf : Wf) + 1;
+    const size_t smem = (size_t)2 * 7 * tab_stride * sizeof(float);
+    if (!direct && P == 7 && C4 <= 256 && 256 % C4 == 0 && smem <= 48 * 1024) {
+      roi_align_sep_kernel<7><<<K, 256, smem, as_stream(stream)>>>(feat, B, Hf, Wf, C, boxes, seg_off, spatial_scale, out,
+                                                                  sample_grid, tab_stride);
+      return check_launch("vbg_roi_align_fwd");
+    }
+  }
   long long warps = (long long)K * P * P;
   int blocks = (int)((warps + 7) / 8);
   cudaStream_t s = as_stream(stream);
