@@ -80,13 +80,15 @@ class ClockSampler(threading.Thread):
 def build_net(cfg, device=None):
     from vibertgrid_pytorch_b200 import synth
     from vibertgrid_pytorch_b200.net import ViBERTgridNet
+    import contextlib
     cwd = os.getcwd()
     with tempfile.TemporaryDirectory() as tmp:
         os.chdir(tmp)
         try:
             synth.write_bert_dir(cfg, tmp)
             kw = synth.model_kwargs(cfg, "eval")
-            net = ViBERTgridNet(**kw)
+            with contextlib.redirect_stdout(sys.stderr):      # the constructor prints like the reference's; stdout carries ONE JSON line
+                net = ViBERTgridNet(**kw)
         finally:
             os.chdir(cwd)
     synth.fill_state_dict_(net, 0)

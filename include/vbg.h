@@ -129,6 +129,14 @@ VBG_API int vbg_grid_scatter(const float* seg_emb, const int32_t* idx, const int
 VBG_API int vbg_label_paint(const int32_t* boxes, const int32_t* seg_off, const int32_t* seg_cls, int B, int H, int W,
                     int64_t* pos_neg, int64_t* cls, vbg_stream_t stream);
 
+/* Fused auxiliary-segmentation loss (model/semantic_segmentation_head.py:199-214 labels + :343-347 / :216-233 CE, default
+ * mean reduction, no class weights / sampling): out2[0] = mean CE(pred_mask, pos_neg), out2[1] = mean CE(pred_ss, class)
+ * over all B*H*W pixels, computed from the LOW-resolution logits [B, H/up, W/up, Ct] (channels [0,c_split) = mask head)
+ * without materialising the label maps.  workspace: >= 2 * ceil(W/32) * ceil(H/8) * B floats.          */
+VBG_API int vbg_seg_ce_loss(const int32_t* boxes, const int32_t* seg_off, const int32_t* seg_cls, const float* logits, int B,
+                    int H, int W, int up, int Ct, int c_split, float* workspace, size_t ws_bytes, float* out2,
+                    vbg_stream_t stream);
+
 /* ---- a5 / a6 / a8 / a9: dense contractions ------------------------------------------------- */
 /* C[M,N] = epilogue( [A | A2][M,K] * W[N,K]^T ).  A supplies columns [0,K1), A2 (may be NULL when
  * K1 == K) columns [K1,K): the torch.cat-free form of ResNetFPN_ViBERTgrid.py:317-318 and

@@ -157,6 +157,12 @@ def label_paint(boxes, seg_off, seg_cls, B, H, W):
     return torch.from_numpy(pn), torch.from_numpy(cl)
 
 
+def seg_ce_loss(boxes, seg_off, seg_cls, lg, B, H, W, up, c_split):
+    pn, cl = label_paint(boxes, seg_off, seg_cls, B, H, W)
+    full = lg.permute(0, 3, 1, 2).repeat_interleave(up, 2).repeat_interleave(up, 3)
+    return torch.stack([F.cross_entropy(full[:, :c_split], pn), F.cross_entropy(full[:, c_split:], cl)])
+
+
 def gemm(A, W, *, A2=None, ep=None, precision=0, N=None, K=None, ldw=None, out=None, w_offset=0, W_split=None, split_out=False):
     X = A if A2 is None else torch.cat([A, A2], 1)
     Kt = X.shape[1] if K is None else K

@@ -50,6 +50,7 @@ def test_forward_matches_reference_fixture(name, precision, tmp_path, monkeypatc
     cfg, kw, net, batch = build_case(fx["meta"])
     net = net.cuda().eval()
     net._get_engine().precision = PREC[precision]
+    net._get_engine().fuse_aux_loss = False          # this run also checks the painted label maps
     loss, pred_mask, pred_ss, gt, pred = net(*_to_dev(batch))
     out = net.last_intermediates
     assert int(out["status"].item()) == 0
@@ -57,7 +58,14 @@ def test_forward_matches_reference_fixture(name, precision, tmp_path, monkeypatc
     print(f"[{name}/{precision}] " + ", ".join(f"{k}={v:.1e}" for k, v in errs.items()))
     assert pred.shape == tuple(fx["pred_label"].shape) and pred_mask.shape[1] == 3
     want = float(fx["loss"][0])
-    assert abs(float(loss.detach().reshape(-1)[0]) - want) <= {"fp32": 1e-4, "bf16x3": 1e-3, "tf32": 2e-2}[precision] * max(1.0, abs(want))
+    tol_loss = {"fp32": 1e-4, "bf16x3": 1e-3, "tf32": 2e-2}[precision] * max(1.0, abs(want))
+    assert abs(float(loss.detach().reshape(-1)[0]) - want) <= tol_loss
+    # default product path: the auxiliary CE is fused with the label painting (labels never materialised)
+    net._get_engine().fuse_aux_loss = True
+    loss2 = net(*_to_dev(batch))[0]
+    if fx["meta"]["classifier_mode"] == "simp":
+        assert "aux_ce" in net.last_intermediates and "pos_neg_labels" not in net.last_intermediates
+    assert abs(float(loss2.detach().reshape(-1)[0]) - want) <= tol_loss
 
 
 def test_inference_entry_point_and_mode_quirk(tmp_path, monkeypatch):
@@ -162,6 +170,7 @@ def test_full_size_tensor_core_vs_exact_fp32_path(name, batch, tmp_path, monkeyp
     net = net.cuda().eval()
     eng = net._get_engine()
     eng.use_graphs = False
+    eng.fuse_aux_loss = False
     dev = _to_dev(synth.make_batch(cfg, 11))
     res = {}
     for prec in ("fp32", "bf16x3"):

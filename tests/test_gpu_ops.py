@@ -65,6 +65,23 @@ def test_scatter_and_label_paint(ops):
     assert np.array_equal(pn.cpu().numpy(), wpn) and np.array_equal(cl.cpu().numpy(), wcl)
 
 
+def test_fused_seg_ce_loss(ops):
+    """vbg_seg_ce_loss == F.cross_entropy of the x4-upsampled logits against the painted label maps (mean over pixels)."""
+    rng = np.random.default_rng(6)
+    g = torch.Generator().manual_seed(6)
+    H, W, counts, Cn, up = 64, 96, [23, 7], 5, 4
+    per = [_boxes(rng, c, H, W) for c in counts]
+    off, doff = _dev_off(counts)
+    boxes = torch.from_numpy(np.concatenate(per, 0)).cuda()
+    cls = torch.from_numpy(np.concatenate([rng.integers(0, Cn, c).astype(np.int32) for c in counts])).cuda()
+    lg = (torch.randn(2, H // up, W // up, 3 + Cn, generator=g) * 3).cuda()
+    got = ops.seg_ce_loss(boxes, doff, cls, lg, 2, H, W, up, 3).cpu()
+    pn, cl = ops.label_paint(boxes, doff, cls, 2, H, W)
+    full = lg.permute(0, 3, 1, 2).repeat_interleave(up, 2).repeat_interleave(up, 3).double()
+    want = torch.stack([F.cross_entropy(full[:, :3], pn), F.cross_entropy(full[:, 3:], cl)]).cpu()
+    assert relerr(got.numpy(), want.numpy()) < 2e-6
+
+
 @pytest.mark.parametrize("mode", ["mean", "first"])
 def test_segment_aggregate_bit_exact(ops, mode):
     rng = np.random.default_rng(3)

@@ -56,6 +56,7 @@ def test_engine_orchestration_with_standins(name, tmp_path, monkeypatch):
     monkeypatch.setattr(engine_mod, "make_epilogue", mock_ops.make_epilogue)
     eng = net._get_engine()
     eng._test_standins = True
+    eng.fuse_aux_loss = False          # this test also checks the painted label maps
     out = eng.run(*batch, want_seg=True)
     assert int(out["status"]) == 0
     nchw = lambda t: t.permute(0, 3, 1, 2)
@@ -72,3 +73,10 @@ def test_engine_orchestration_with_standins(name, tmp_path, monkeypatch):
     from vibertgrid_pytorch_b200 import losses
     total = losses.main_loss(net, out) + net.loss_control_lambda * losses.aux_loss(net, out)
     assert abs(float(total.reshape(-1)[0]) - float(fx["loss"][0])) <= 1e-4 * max(1.0, abs(float(fx["loss"][0])))
+    # fused auxiliary-loss wiring (the product default): same total loss without materialised label maps
+    eng.fuse_aux_loss = True
+    out2 = eng.run(*batch, want_seg=True)
+    if cfg.classifier_mode == "simp":
+        assert "aux_ce" in out2 and "pos_neg_labels" not in out2
+    total2 = losses.main_loss(net, out2) + net.loss_control_lambda * losses.aux_loss(net, out2)
+    assert abs(float(total2.reshape(-1)[0]) - float(fx["loss"][0])) <= 1e-4 * max(1.0, abs(float(fx["loss"][0])))

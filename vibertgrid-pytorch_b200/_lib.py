@@ -46,6 +46,7 @@ SIGNATURES = {
     "vbg_box_index_map": [_p, _p, _i, _i, _i, _i, _p, _p],
     "vbg_grid_scatter": [_p, _p, _p, _i, _i, _i, _p, _p],
     "vbg_label_paint": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
+    "vbg_seg_ce_loss": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p],
     "vbg_gemm": [_p, _i, _p, _i, _i, _p, _i, _p, _ll, _p, _i, _i, _i, _i, _EP, _i, _p],
     "vbg_conv2d": [_p, _i, _i, _i, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _EP, _i, _p],
     "vbg_split_bf16": [_p, _ll, _p, _p, _p],

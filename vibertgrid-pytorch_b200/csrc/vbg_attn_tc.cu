@@ -241,8 +241,8 @@ attention_tc_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ c
 // The QKV projection writes bf16 hi / lo planes (VBG_OUT_SPLIT_BF16), so nothing is converted here: TMA drops Q, K
 // (K-major: row = token, 64 head dims = 128 B) and V (the same rows, used as an MN-major B operand -- no transpose)
 // straight into SWIZZLE_128B operand tiles.  The 128 softmax threads only do row max, exp, and the hi/lo split of P.
-//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 softmax (thread == query row == TMEM lane)
-constexpr int kAt2Threads = 192;
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-9 softmax (two groups; thread == query row == TMEM lane)
+constexpr int kAt2Threads = 320;
 constexpr uint32_t kVTile = 64 * 128;        // 64 keys x 64 dims (bf16)
 
 __global__ void __launch_bounds__(kAt2Threads, 1)
@@ -265,6 +265,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
   uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *s_full = bars + 5, *v_full = bars + 6,
            *p_ready = bars + 8, *pv_done = bars + 10, *o_full = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* xch = reinterpret_cast<float*>(bars + 14);             // [2][128] row max / row sum exchange between the groups
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmQKh); prefetch_tmap(&tmQKl); prefetch_tmap(&tmVh); prefetch_tmap(&tmVl); }
@@ -353,25 +354,32 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
       umma_commit(o_full);
     }
   } else {
-    // ===== softmax
-    const int q = warp & 3;
+    // ===== softmax: two groups of 4 warps (one warp of each group per scheduler, so TMEM-load and exp latencies of one
+    // group hide behind the other).  Group g owns key chunks / 64-key units with index == g (mod 2) and P buffer g.
+    const int q = warp & 3, grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     mbar_wait(s_full, 0);
     tc_fence_after();
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     float m = -INFINITY;
-    for (int c0 = 0; c0 < n_chunks * 128; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(lane_addr + (uint32_t)c0, v);
+    for (int c = grp; c < n_chunks; c += 2) {
+#pragma unroll 1
+      for (int c0 = c * 128; c0 < c * 128 + 128; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + (uint32_t)c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) if (c0 + j < len) m = fmaxf(m, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j) if (c0 + j < len) m = fmaxf(m, __uint_as_float(v[j]));
+      }
     }
+    xch[grp * 128 + r] = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    m = fmaxf(xch[r], xch[128 + r]);
+    asm volatile("bar.sync 1, 256;" ::: "memory");               // xch is reused for the row sums below
     float sum = 0.f;
     const uint32_t xr = (uint32_t)(r & 7);
-    for (int u = 0; u < n_units; ++u) {
-      const int b = u & 1;
-      if (u >= 2) mbar_wait(&pv_done[b], ((u >> 1) - 1) & 1);
-      uint8_t* p1 = p_op + b * 2 * kTileQ + (uint32_t)r * 128u;
+    uint8_t* p1 = p_op + grp * 2 * kTileQ + (uint32_t)r * 128u;
+    for (int u = grp, it = 0; u < n_units; u += 2, ++it) {
+      if (it >= 1) mbar_wait(&pv_done[grp], (it - 1) & 1);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
@@ -394,20 +402,22 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(&p_ready[b]);
+      mbar_arrive(&p_ready[grp]);
     }
+    xch[grp * 128 + r] = sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    sum = xch[r] + xch[128 + r];
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv = __fdiv_rn(1.0f, sum);
-    float* orow = out + (size_t)(row0 + q0 + r) * hidden + head * 64;
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    float* orow = out + (size_t)(row0 + q0 + r) * hidden + head * 64 + grp * 32;     // group g stores dims [32g, 32g+32)
+    {
       uint32_t v[32];
-      tmem_ld32(lane_addr + (uint32_t)(half * 32), v);
+      tmem_ld32(lane_addr + (uint32_t)(grp * 32), v);
       if (q0 + r < len) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(orow + half * 32 + 4 * j) =
+          *reinterpret_cast<float4*>(orow + 4 * j) =
               make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
                           __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv);
       }
@@ -436,7 +446,7 @@ int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int 
     if (!tc_encode(&mq[i], hi + i * plane, 2, dims, strides, box_qk, nullptr, true)) return VBG_EUNSUPPORTED;
     if (!tc_encode(&mv[i], hi + i * plane, 2, dims, strides, box_v, nullptr, true)) return VBG_EUNSUPPORTED;
   }
-  constexpr size_t smem = 2 * kTileQ + 4 * kTileQ + 4 * kVTile + 4 * kTileQ + 1024 + 256;
+  constexpr size_t smem = 2 * kTileQ + 4 * kTileQ + 4 * kVTile + 4 * kTileQ + 1024 + 256 + 1024;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attention_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -99,11 +99,16 @@ __global__ void segment_reduce_kernel(const float* __restrict__ hidden, const in
 // shared memory; a cell takes the first hit scanning backwards.  Early exit when the tile is full.
 constexpr int kTileW = 32, kTileH = 8;
 
-template <bool kPaint>
+// kMode 0: index map; 1: paint the two label maps; 2: fused auxiliary-segmentation cross entropy -- the labels are
+// consumed in registers (never written) against the low-resolution logits, per-CTA partial sums go to `partial`.
+struct SegCeArgs { const float* logits; int h, w, Ct, up, c_split; float* partial; };
+
+template <int kMode>
 __global__ void __launch_bounds__(256)
 box_map_kernel(const int32_t* __restrict__ boxes, const int32_t* __restrict__ seg_off,
                const int32_t* __restrict__ seg_cls, int stride, int Hg, int Wg, int32_t* __restrict__ idx,
-               int64_t* __restrict__ pos_neg, int64_t* __restrict__ cls) {
+               int64_t* __restrict__ pos_neg, int64_t* __restrict__ cls, const SegCeArgs ce) {
+  constexpr bool kPaint = kMode == 1;
   __shared__ int4 hit_box[256];
   __shared__ int hit_id[256];
   __shared__ int warp_cnt[8];
@@ -151,6 +156,36 @@ box_map_kernel(const int32_t* __restrict__ boxes, const int32_t* __restrict__ se
     }
     if (__syncthreads_and(best >= 0 || !live)) break;
   }
+  if (kMode == 2) {
+    // CE of this pixel for the 3-way mask head and the C-way class head (semantic_segmentation_head.py:343-347 with the
+    // default mean reduction): logits of low-res pixel (y/up, x/up); nearest upsampling commutes with the 1x1 heads.
+    float l1 = 0.f, l2 = 0.f;
+    if (live) {
+      int c = 0, pn = 0;
+      if (best >= 0) { c = seg_cls[s0 + best]; pn = c > 0 ? 1 : 2; }
+      const float* z = ce.logits + (((size_t)b * ce.h + y / ce.up) * ce.w + x / ce.up) * ce.Ct;
+      float m1 = -INFINITY, m2 = -INFINITY;
+      for (int i = 0; i < ce.c_split; ++i) m1 = fmaxf(m1, __ldg(z + i));
+      for (int i = ce.c_split; i < ce.Ct; ++i) m2 = fmaxf(m2, __ldg(z + i));
+      float e1 = 0.f, e2 = 0.f;
+      for (int i = 0; i < ce.c_split; ++i) e1 += expf(__ldg(z + i) - m1);
+      for (int i = ce.c_split; i < ce.Ct; ++i) e2 += expf(__ldg(z + i) - m2);
+      l1 = (m1 + logf(e1)) - __ldg(z + pn);
+      l2 = (m2 + logf(e2)) - __ldg(z + ce.c_split + c);
+    }
+    l1 = warp_sum(l1); l2 = warp_sum(l2);
+    __shared__ float red[2][8];
+    if (lane == 0) { red[0][wid] = l1; red[1][wid] = l2; }
+    __syncthreads();
+    if (tid == 0) {
+      float a = 0.f, c2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { a += red[0][w]; c2 += red[1][w]; }
+      const size_t blk = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      ce.partial[2 * blk] = a; ce.partial[2 * blk + 1] = c2;
+    }
+    return;
+  }
   if (!live) return;
   const size_t o = ((size_t)b * Hg + y) * Wg + x;
   if (kPaint) {
@@ -164,6 +199,20 @@ box_map_kernel(const int32_t* __restrict__ boxes, const int32_t* __restrict__ se
   } else {
     idx[o] = best;
   }
+}
+
+// deterministic final reduction of the per-CTA partial sums (fixed order, double accumulator)
+__global__ void seg_ce_finish_kernel(const float* __restrict__ partial, int nblk, double inv_n, float* __restrict__ out2) {
+  __shared__ double sh[2][256];
+  double a = 0.0, c = 0.0;
+  for (int i = threadIdx.x; i < nblk; i += 256) { a += (double)partial[2 * i]; c += (double)partial[2 * i + 1]; }
+  sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = c;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out2[0] = (float)(sh[0][0] * inv_n); out2[1] = (float)(sh[1][0] * inv_n); }
 }
 
 // ------------------------------------------------------------------ scatter
@@ -225,7 +274,7 @@ extern "C" int vbg_box_index_map(const int32_t* boxes, const int32_t* seg_off, i
   VBG_REQUIRE(boxes && seg_off && idx && B > 0 && stride > 0 && Hg > 0 && Wg > 0, "vbg_box_index_map: bad arguments");
   VBG_REQUIRE(aligned16(boxes), "vbg_box_index_map: boxes must be 16B aligned");
   dim3 g(cdiv(Wg, kTileW), cdiv(Hg, kTileH), B);
-  box_map_kernel<false><<<g, 256, 0, as_stream(stream)>>>(boxes, seg_off, nullptr, stride, Hg, Wg, idx, nullptr, nullptr);
+  box_map_kernel<0><<<g, 256, 0, as_stream(stream)>>>(boxes, seg_off, nullptr, stride, Hg, Wg, idx, nullptr, nullptr, SegCeArgs{});
   return check_launch("vbg_box_index_map");
 }
 
@@ -234,8 +283,28 @@ extern "C" int vbg_label_paint(const int32_t* boxes, const int32_t* seg_off, con
   VBG_REQUIRE(boxes && seg_off && seg_cls && pos_neg && cls && B > 0 && H > 0 && W > 0, "vbg_label_paint: bad arguments");
   VBG_REQUIRE(aligned16(boxes), "vbg_label_paint: boxes must be 16B aligned");
   dim3 g(cdiv(W, kTileW), cdiv(H, kTileH), B);
-  box_map_kernel<true><<<g, 256, 0, as_stream(stream)>>>(boxes, seg_off, seg_cls, 1, H, W, nullptr, pos_neg, cls);
+  box_map_kernel<1><<<g, 256, 0, as_stream(stream)>>>(boxes, seg_off, seg_cls, 1, H, W, nullptr, pos_neg, cls, SegCeArgs{});
   return check_launch("vbg_label_paint");
+}
+
+extern "C" int vbg_seg_ce_loss(const int32_t* boxes, const int32_t* seg_off, const int32_t* seg_cls, const float* logits, int B,
+                               int H, int W, int up, int Ct, int c_split, float* workspace, size_t ws_bytes, float* out2,
+                               vbg_stream_t stream) {
+  VBG_REQUIRE(boxes && seg_off && seg_cls && logits && out2 && B > 0 && H > 0 && W > 0 && up > 0 && H % up == 0 && W % up == 0,
+              "vbg_seg_ce_loss: bad arguments");
+  VBG_REQUIRE(c_split > 0 && c_split < Ct && aligned16(boxes), "vbg_seg_ce_loss: bad channel split / alignment");
+  dim3 g(cdiv(W, kTileW), cdiv(H, kTileH), B);
+  const size_t nblk = (size_t)g.x * g.y * g.z;
+  if (!workspace || ws_bytes < nblk * 2 * sizeof(float)) {
+    set_error("vbg_seg_ce_loss: workspace of %zu bytes needed", nblk * 2 * sizeof(float));
+    return VBG_EWORKSPACE;
+  }
+  SegCeArgs ce{logits, H / up, W / up, Ct, up, c_split, workspace};
+  box_map_kernel<2><<<g, 256, 0, as_stream(stream)>>>(boxes, seg_off, seg_cls, 1, H, W, nullptr, nullptr, nullptr, ce);
+  int rc = check_launch("vbg_seg_ce_loss");
+  if (rc) return rc;
+  seg_ce_finish_kernel<<<1, 256, 0, as_stream(stream)>>>(workspace, (int)nblk, 1.0 / ((double)B * H * W), out2);
+  return check_launch("vbg_seg_ce_loss(finish)");
 }
 
 extern "C" int vbg_grid_scatter(const float* seg_emb, const int32_t* idx, const int32_t* seg_off, int B, int cells, int C,

@@ -60,6 +60,7 @@ class ForwardEngine:
         self.precision = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16x3": PREC_BF16X3}.get(env)
         self.launches = 0
         self.use_graphs = os.environ.get("VBG_CUDA_GRAPHS", "1") != "0"
+        self.fuse_aux_loss = os.environ.get("VBG_FUSED_AUX_LOSS", "1") != "0"
         self.max_graphs = 8
         self._graphs: Dict[tuple, dict] = {}
         self.graph_replays = 0
@@ -135,6 +136,14 @@ class ForwardEngine:
         self._prep_gen += 1
         self._graphs.clear()              # captured graphs hold pointers into the previous preparation
         return pr
+
+    def _aux_loss_is_default(self):
+        """True when the auxiliary loss is the plain mean cross entropy of the `simp` head (no sampling / OHEM / weights):
+        the configuration vbg_seg_ce_loss implements."""
+        net = self.net
+        cfg = net.loss_cfg
+        return (net.classifier_mode == "simp" and cfg["aux_sample_list"] is None and tuple(cfg["aux"]) == (-1, -1)
+                and net.loss_weights is None)
 
     # ------------------------------------------------------------------ building blocks
     def _prec(self):
@@ -289,7 +298,8 @@ class ForwardEngine:
         B, H, W, Cc = x.shape
         pr = self._prep
         lg = ops.gemm(x.view(-1, Cc), pr.misc["seg_w"], ep=make_epilogue(None, pr.misc["seg_b"]), precision=self._prec())
-        return ops.upsample_split_nchw(lg.view(B, H, W, -1), self.net.p_fuse_downsampling_ratio, 3)
+        lg = lg.view(B, H, W, -1)
+        return ops.upsample_split_nchw(lg, self.net.p_fuse_downsampling_ratio, 3) + (lg,)
 
     # ------------------------------------------------------------------ whole forward
     @torch.no_grad()
@@ -308,7 +318,7 @@ class ForwardEngine:
         shapes = (tuple(tuple(im.shape[-2:]) for im in image), tuple(int(s.shape[0]) for s in seg_indices),
                   tuple(int(c.shape[0]) for c in coors), int(corpus.shape[1]))
         want_seg = bool(want_seg and net.semantic_segmentation_head is not None)
-        key = (shapes, want_seg, self._prec(), self._prep_gen, dev.index)
+        key = (shapes, want_seg, self._prec(), self._prep_gen, dev.index, self.fuse_aux_loss)
         ent = self._graphs.get(key) if self.use_graphs and not standins else None
         if ent is not None and ent.get("graph") is not None:
             st = ent["static"]
@@ -396,9 +406,14 @@ class ForwardEngine:
 
         # a6 auxiliary segmentation head
         if want_seg:
-            out["pred_mask"], out["pred_ss"] = self._seg_head(p_fuse)
+            out["pred_mask"], out["pred_ss"], lg = self._seg_head(p_fuse)
             cls_cat = st["cls"]
-            out["pos_neg_labels"], out["class_labels"] = ops.label_paint(boxes, seg_off, cls_cat, B, plan.H, plan.W)
+            if self.fuse_aux_loss and self._aux_loss_is_default():
+                # labels are consumed in registers by the fused CE kernel; the int64 label maps are never written
+                out["aux_ce"] = ops.seg_ce_loss(boxes, seg_off, cls_cat, lg, B, plan.H, plan.W,
+                                                net.p_fuse_downsampling_ratio, 3)
+            else:
+                out["pos_neg_labels"], out["class_labels"] = ops.label_paint(boxes, seg_off, cls_cat, B, plan.H, plan.W)
             out["gt_label"] = cls_cat
 
         # a7 ROI align, a8 late fusion

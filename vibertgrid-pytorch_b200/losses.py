@@ -102,6 +102,8 @@ def _w(net, like):
 
 def aux_loss(net, out):
     cfg = net.loss_cfg
+    if "aux_ce" in out:                 # fused kernel (vbg_seg_ce_loss): [mean CE mask head, mean CE class head]
+        return out["aux_ce"][0] + out["aux_ce"][1]
     pm, ps = out["pred_mask"], out["pred_ss"]
     l1 = ce_random_sample(pm, out["pos_neg_labels"], cfg["aux_sample_list"])
     n_pos, n_neg = cfg["aux"]

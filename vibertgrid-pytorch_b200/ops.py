@@ -162,6 +162,17 @@ def label_paint(boxes, seg_off, seg_cls, B, H, W):
     return pn, cl
 
 
+def seg_ce_loss(boxes, seg_off, seg_cls, logits_lowres, B, H, W, up, c_split):
+    """(mean CE of the 3-way mask head, mean CE of the class head) over all pixels, from the low-res NHWC logits; fp32 [2]."""
+    Ct = logits_lowres.shape[-1]
+    nblk = ((W + 31) // 32) * ((H + 7) // 8) * B
+    ws = torch.empty(2 * nblk, dtype=torch.float32, device=boxes.device)
+    out = torch.empty(2, dtype=torch.float32, device=boxes.device)
+    L.check(L.load().vbg_seg_ce_loss(_i32(boxes), _i32(seg_off), _i32(seg_cls), _f32(logits_lowres), B, H, W, up, Ct, c_split,
+                                     _f32(ws), ws.numel() * 4, _f32(out), _stream()), "vbg_seg_ce_loss")
+    return out
+
+
 # ------------------------------------------------------------------ dense contractions
 def split_bf16(w):
     """fp32 tensor -> bf16 [2, *w.shape]: plane 0 = bf16_rn(w), plane 1 = bf16_rn(w - plane 0)  (VBG_PREC_BF16X3 weights)."""
