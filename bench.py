@@ -183,13 +183,17 @@ def kernel_rooflines(net, cfg, dev, peaks):
     seg_off = torch.arange(0, K + 1, S, dtype=torch.int32, device=dev)
     emb = torch.randn(K, C, device=dev)
     idx = ops.box_index_map(boxes, seg_off, B, 8, Hg, Wg)
-    ms = timed(lambda: ops.grid_scatter(emb, idx, seg_off))
+    ps = net._get_engine()._ps()        # pre-split mode: the kernels run in the storage formats the engine uses (same bytes)
+    emb_src = ops.to_split(emb) if ps else emb
+    ms = timed(lambda: ops.grid_scatter(emb_src, idx, seg_off))
     by = B * C * Hg * Wg * 4 + K * C * 4 + K * 16 + B * Hg * Wg * 4
     out["grid_scatter"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                            "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": ms, "bytes": by}
     Hf, Wf = cfg.height // 4, cfg.width // 4
     feat = torch.randn(B, Hf, Wf, 256, device=dev)
-    ms = timed(lambda: ops.roi_align(feat, boxes, seg_off, 0.25, 7))
+    if ps:
+        feat = ops.to_split(feat)
+    ms = timed(lambda: ops.roi_align(feat, boxes, seg_off, 0.25, 7, split_out=ps))
     by = B * 256 * Hf * Wf * 4 + K * 256 * 49 * 4 + K * 20
     out["roi_align"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": ms, "bytes": by}
@@ -202,12 +206,15 @@ def kernel_rooflines(net, cfg, dev, peaks):
     bias = torch.zeros(3072, device=dev)
     ep = ops.make_epilogue(None, bias, act=ops.ACT_GELU)
     Ws = ops.split_bf16(Wt) if prec == ops.PREC_BF16X3 else None
-    ms = timed(lambda: ops.gemm(A, Wt, ep=ep, precision=prec, W_split=Ws))
+    if ps:
+        A = ops.to_split(A)
+    ms = timed(lambda: ops.gemm(A, Wt, ep=ep, precision=prec, W_split=Ws, split_out=ps))
     fl = 2.0 * M * 3072 * 768
     # bf16x3: every fp32-equivalent product costs three bf16 tensor-core products, so the mode's ceiling is bf16 peak / 3
     peak, path = {ops.PREC_TF32: (peaks["tf32_tflops"], "tcgen05 kind::tf32 (measured cuBLAS TF32 peak)"),
-                  ops.PREC_BF16X3: (peaks["bf16_tflops"] / 3.0, "tcgen05 kind::f16, 3 bf16 products per fp32-equivalent product; "
-                                                                  "peak = measured bf16 peak / 3; frac == tensor-pipe share of bf16 peak"),
+                  ops.PREC_BF16X3: (peaks["bf16_tflops"] / 3.0, "tcgen05 kind::f16, 3 bf16 products per fp32-equivalent product"
+                                                                  + (", operands pre-split in HBM (TMA-fed, no in-kernel conversion)" if ps else "")
+                                                                  + "; peak = measured bf16 peak / 3; frac == tensor-pipe share of bf16 peak"),
                   ops.PREC_FP32: (peaks["fp32_simt_tflops"], "CUDA-core fp32 FFMA")}[prec]
     out["gemm_ffn_up"] = {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
                           "frac": fl / ms / 1e9 / peak, "traffic": None, "ms": ms, "flops": fl, "path": path,

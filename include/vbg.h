@@ -16,9 +16,13 @@
  *     allocates nothing persistent.
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*); the legacy
  *     default stream is never used implicitly.  Functions are re-entrant.
- *   - activations are fp32, channels-last (NHWC); weights of convolutions are
- *     [Cout, kh, kw, Cin] (see vbg_repack_oihw_to_ohwi); linear weights keep
- *     PyTorch's [out, in] layout.
+ *   - activations are channels-last (NHWC), stored as fp32 or -- between the
+ *     tensor-core kernels of VBG_PREC_BF16X3 -- as a PAIR OF BF16 PLANES
+ *     (hi = bf16_rn(x), lo = bf16_rn(x - hi); the lo plane starts `plane`
+ *     ELEMENTS after the hi plane, plane % 8 == 0).  Entry points ending in _x
+ *     and _ps take (pointer, plane) pairs: plane == 0 means fp32.  Weights of
+ *     convolutions are [Cout, kh, kw, Cin] (see vbg_repack_oihw_to_ohwi);
+ *     linear weights keep PyTorch's [out, in] layout.
  *   - "seg_off" is an int32 [B+1] exclusive prefix sum of segments per sample,
  *     built by the host from tensor SHAPES (no device sync).
  */
@@ -69,6 +73,8 @@ typedef struct vbg_epilogue {
   int act;               /* VBG_ACT_* */
   int out_mode;          /* VBG_OUT_* */
   long long out_plane;   /* VBG_OUT_SPLIT_BF16: elements between the hi and the lo plane */
+  long long res_plane;   /* > 0: `residual` points at the bf16 hi plane of a split activation (same indexing), the lo
+                            plane res_plane elements later (tensor-core paths only); 0: residual is float */
 } vbg_epilogue_t;
 
 VBG_API int vbg_version(void);
@@ -100,14 +106,21 @@ VBG_API int vbg_embed_ln(const int32_t* ids, const int32_t* pos, const float* wo
                  int vocab, int max_pos, float* out, vbg_stream_t stream);
 VBG_API int vbg_layernorm(const float* x, const float* gamma, const float* beta, float eps, int R, int hidden, float* out,
                   vbg_stream_t stream);
+/* same two kernels writing either storage format (out_plane == 0: fp32) */
+VBG_API int vbg_embed_ln_x(const int32_t* ids, const int32_t* pos, const float* word, const float* position,
+                   const float* type0, const float* gamma, const float* beta, float eps, int R, int hidden,
+                   int vocab, int max_pos, void* out, long long out_plane, vbg_stream_t stream);
+VBG_API int vbg_layernorm_x(const float* x, const float* gamma, const float* beta, float eps, int R, int hidden, void* out,
+                    long long out_plane, vbg_stream_t stream);
 /* softmax(Q K^T / sqrt(d)) V per sequence and head over packed qkv [R, 3*heads*d] (q | k | v). */
 VBG_API int vbg_attention_fwd(const float* qkv, const int32_t* cu, int nseq, int max_len, int heads, int head_dim,
                       float* out, int precision, vbg_stream_t stream);
 
 /* Same attention over the bf16 hi/lo planes written by vbg_gemm(..., VBG_OUT_SPLIT_BF16): qkv_hi is bf16 [R, 3*heads*64],
- * the lo plane starts `plane` elements later.  TMA-fed tcgen05 kernel, fp32-class 3-term products; out is fp32. */
+ * the lo plane starts `plane` elements later.  TMA-fed tcgen05 kernel, fp32-class 3-term products; out [R, heads*64] in
+ * either storage format (out_plane == 0: fp32). */
 VBG_API int vbg_attention_split_fwd(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len,
-                            int heads, int head_dim, float* out, vbg_stream_t stream);
+                            int heads, int head_dim, void* out, long long out_plane, vbg_stream_t stream);
 
 /* ---- a3: token -> segment aggregation (model/BERTgrid_generator.py:148-189) ----------------- */
 /* Run starts of consecutive-equal ids inside each sample.  status[0] |= 1 if #runs != K.        */
@@ -125,6 +138,9 @@ VBG_API int vbg_box_index_map(const int32_t* boxes, const int32_t* seg_off, int 
 /* grid[b,y,x,:] = idx<0 ? 0 : seg_emb[seg_off[b]+idx]   (NHWC BERTgrid, C % 4 == 0)             */
 VBG_API int vbg_grid_scatter(const float* seg_emb, const int32_t* idx, const int32_t* seg_off, int B, int cells, int C,
                      float* grid, vbg_stream_t stream);
+/* either storage format for the source rows and the grid (a bf16-plane source needs a bf16-plane grid: plane-wise copy) */
+VBG_API int vbg_grid_scatter_x(const void* seg_emb, long long emb_plane, const int32_t* idx, const int32_t* seg_off, int B,
+                       int cells, int C, void* grid, long long grid_plane, vbg_stream_t stream);
 /* full-resolution labels (model/semantic_segmentation_head.py:199-214): pos_neg = 1 if cls>0 else 2. */
 VBG_API int vbg_label_paint(const int32_t* boxes, const int32_t* seg_off, const int32_t* seg_cls, int B, int H, int W,
                     int64_t* pos_neg, int64_t* cls, vbg_stream_t stream);
@@ -146,6 +162,18 @@ VBG_API int vbg_seg_ce_loss(const int32_t* boxes, const int32_t* seg_off, const 
 VBG_API int vbg_gemm(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int ldw, const void* W_split,
              long long split_plane, float* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep, int precision,
              vbg_stream_t stream);
+/* The same contraction with A (and A2) already stored as bf16 hi/lo planes (VBG_PREC_BF16X3 arithmetic, tensor cores only:
+ * N >= 64, K % 64 == 0, K1 % 64 == 0): TMA drops the planes straight into the tcgen05 operand tiles, nothing is converted in
+ * the kernel.  W_hi / w_plane: planes of vbg_split_bf16(W).  C is float [M, ldc] or, with ep->out_mode ==
+ * VBG_OUT_SPLIT_BF16, bf16 planes; ep->res_plane > 0 reads the residual from planes too.                          */
+VBG_API int vbg_gemm_ps(const void* A_hi, long long a_plane, int lda, const void* A2_hi, long long a2_plane, int lda2, int K1,
+                const void* W_hi, long long w_plane, int ldw, void* C, int ldc, int M, int N, int K,
+                const vbg_epilogue_t* ep, vbg_stream_t stream);
+/* implicit-GEMM convolution over a split NHWC activation (Cin % 64 == 0, Cout >= 64, stride 1 or 2) */
+VBG_API int vbg_conv2d_ps(const void* x_hi, long long x_plane, int B, int H, int W, int Cin, const void* w_hi, long long w_plane,
+                  int Cout, int kh, int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, vbg_stream_t stream);
+/* out[i] = float(hi[i]) + float(lo[i])  (inspection / tests: split activation -> fp32) */
+VBG_API int vbg_merge_bf16(const void* hi, const void* lo, long long n, float* out, vbg_stream_t stream);
 /* NHWC convolution as implicit GEMM: y[B,Ho,Wo,Cout] = epilogue(conv(x[B,H,W,Cin], w[Cout,kh,kw,Cin])) */
 VBG_API int vbg_conv2d(const float* x, int B, int H, int W, int Cin, const float* w, const void* w_split, long long split_plane,
                int Cout, int kh, int kw, int stride, int pad, float* y, const vbg_epilogue_t* ep, int precision,
@@ -160,6 +188,10 @@ VBG_API int vbg_stem_conv(const float* x4, int B, int H, int W, const float* w_o
 VBG_API int vbg_stem_pack_weights(const float* w_oihw, int Cout, float* w_ohwi4, float* w_k256, vbg_stream_t stream);
 VBG_API int vbg_maxpool3x3s2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream);
 VBG_API int vbg_avgpool2x2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream);
+VBG_API int vbg_maxpool3x3s2_x(const void* x, long long x_plane, int B, int H, int W, int C, void* y, long long y_plane,
+                       vbg_stream_t stream);
+VBG_API int vbg_avgpool2x2_x(const void* x, long long x_plane, int B, int H, int W, int C, void* y, long long y_plane,
+                     vbg_stream_t stream);
 /* eval-mode BatchNorm folded to y = x*scale + shift */
 VBG_API int vbg_bn_fold(const float* weight, const float* bias, const float* mean, const float* var, float eps, int C,
                 float* scale, float* shift, vbg_stream_t stream);
@@ -171,6 +203,10 @@ VBG_API int vbg_repack_oihw_to_ohwi(const float* w, int O, int I, int H, int W, 
 VBG_API int vbg_roi_align_fwd(const float* feat, int B, int Hf, int Wf, int C, const int32_t* boxes, const int32_t* seg_off,
                       int K, float spatial_scale, int P, float* out /*[K,P,P,C]*/,
                       int32_t* sample_grid /*[K,2] (gh,gw) or NULL*/, vbg_stream_t stream);
+
+VBG_API int vbg_roi_align_x(const void* feat, long long feat_plane, int B, int Hf, int Wf, int C, const int32_t* boxes,
+                    const int32_t* seg_off, int K, float spatial_scale, int P, void* out, long long out_plane,
+                    int32_t* sample_grid, vbg_stream_t stream);
 
 /* ---- heads / outputs ---------------------------------------------------------------------- */
 VBG_API int vbg_softmax_rows(const float* x, int R, int C, float* y, vbg_stream_t stream);

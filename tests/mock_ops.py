@@ -86,12 +86,12 @@ def bert_assemble(corpus, seq_tab, cu, nseq, R):
     return ids, pos
 
 
-def embed_ln(ids, pos, word, position, type0, gamma, beta, eps):
+def embed_ln(ids, pos, word, position, type0, gamma, beta, eps, split=False):
     x = word[ids.long()] + type0 + position[pos.long()]
     return F.layer_norm(x, x.shape[-1:], gamma, beta, eps)
 
 
-def layernorm(x, gamma, beta, eps, out=None):
+def layernorm(x, gamma, beta, eps, out=None, split=False):
     return F.layer_norm(x, x.shape[-1:], gamma, beta, eps)
 
 
@@ -144,7 +144,7 @@ def box_index_map(boxes, seg_off, B, stride, Hg, Wg):
     return torch.from_numpy(oracle_ops.box_index_map(_split(boxes, seg_off, B), Hg * stride, Wg * stride, stride))
 
 
-def grid_scatter(seg_emb, idx, seg_off):
+def grid_scatter(seg_emb, idx, seg_off, split=False):
     B = idx.shape[0]
     so = seg_off.numpy()
     g = oracle_ops.scatter_grid([seg_emb[so[b]:so[b + 1]].numpy() for b in range(B)], idx.numpy())
@@ -172,7 +172,7 @@ def gemm(A, W, *, A2=None, ep=None, precision=0, N=None, K=None, ldw=None, out=N
     return _epilogue(X @ Wsub.t(), ep)
 
 
-def conv2d(x, w_ohwi, stride, pad, *, ep=None, precision=0, W_split=None):
+def conv2d(x, w_ohwi, stride, pad, *, ep=None, precision=0, W_split=None, split_out=False):
     y = F.conv2d(x.permute(0, 3, 1, 2), w_ohwi.permute(0, 3, 1, 2), None, stride, pad).permute(0, 2, 3, 1).contiguous()
     if ep is not None and ep.res_mode == RES_UP2:
         ep.out_h, ep.out_w = y.shape[1], y.shape[2]
@@ -198,11 +198,11 @@ def stem_conv(x4, w774, *, ep=None, precision=0, W_split=None):
     return conv2d(x4, w774, 2, 0, ep=ep)
 
 
-def maxpool3x3s2(x):
+def maxpool3x3s2(x, split_out=False):
     return F.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).contiguous()
 
 
-def avgpool2x2(x):
+def avgpool2x2(x, split_out=None):
     return F.avg_pool2d(x.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).contiguous()
 
 
@@ -215,7 +215,7 @@ def repack_oihw_to_ohwi(w):
     return w.detach().permute(0, 2, 3, 1).contiguous()
 
 
-def roi_align(feat, boxes, seg_off, spatial_scale, P, want_grid=False):
+def roi_align(feat, boxes, seg_off, spatial_scale, P, want_grid=False, split_out=False):
     B = feat.shape[0]
     so = seg_off.numpy()
     bidx = np.concatenate([np.full(so[b + 1] - so[b], b, np.int32) for b in range(B)])

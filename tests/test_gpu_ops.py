@@ -345,9 +345,11 @@ def test_split_qkv_gemm_and_tma_attention(ops, lens):
     planes = ops.gemm(x.cuda(), Wd, ep=ops.make_epilogue(None, bq.cuda()), precision=ops.PREC_BF16X3, W_split=ops.split_bf16(Wd),
                       split_out=True)
     qkv = x.double() @ Wq.double().t() + bq
-    rec = planes[0].float().double().cpu() + planes[1].float().double().cpu()
-    assert planes.shape == (2, R, 3 * hid) and relerr(rec.numpy(), qkv.numpy()) < 2e-5
+    rec = planes.t[0].float().double().cpu() + planes.t[1].float().double().cpu()
+    assert planes.shape == (R, 3 * hid) and relerr(rec.numpy(), qkv.numpy()) < 2e-5
     got = ops.attention_split(planes, torch.from_numpy(cu).cuda(), len(lens), max(lens), heads).cpu()
+    got_s = ops.attention_split(planes, torch.from_numpy(cu).cuda(), len(lens), max(lens), heads, split_out=True)
+    assert relerr(got_s.float().cpu().numpy(), got.numpy()) < 2 ** -15          # same kernel, Split output
     want = torch.empty(R, hid, dtype=torch.float64)
     for q in range(len(lens)):
         a, b = cu[q], cu[q + 1]
@@ -367,3 +369,109 @@ def test_crf_viterbi_matches_oracle(ops):
         s, path = oracle_ops.crf_viterbi(feats[off[b]:off[b + 1]].numpy(), trans.numpy(), T - 2, T - 1)
         assert tags[off[b]:off[b + 1]].cpu().numpy().astype(int).tolist() == path
         assert abs(float(scores[b]) - s) < 1e-3
+
+
+# ------------------------------------------------------------------ pre-split activations (bf16 hi/lo planes end to end)
+def _merged(x):
+    """What a Split of x holds: hi + lo."""
+    hi, lo = _split_ref(x)
+    return hi + lo
+
+
+@pytest.fixture(params=["64", "32"])
+def ps_kb(request, monkeypatch):
+    """Both ring-stage variants of the pre-split kernel: K=64 (SWIZZLE_128B) and K=32 (SWIZZLE_64B)."""
+    monkeypatch.setenv("VBG_PS_KB", request.param)
+    return int(request.param)
+
+
+def test_split_merge_roundtrip(ops):
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1000, 64, generator=g) * 3
+    s = ops.to_split(x.cuda())
+    assert torch.equal(s.t[0].float().cpu(), _split_ref(x)[0]) and torch.equal(s.t[1].float().cpu(), _split_ref(x)[1])
+    assert torch.equal(s.float().cpu(), _merged(x))
+    assert relerr(s.float().cpu().numpy(), x.numpy()) < 2 ** -16
+
+
+@pytest.mark.parametrize("M,N,K,K1", [(128, 64, 64, 64), (300, 768, 768, 768), (4128, 3072, 768, 768), (4128, 768, 3072, 3072),
+                                      (128, 1024, 1792, 1024), (1000, 136, 64, 64), (77, 64, 192, 64), (4096, 128, 896, 128),
+                                      (513, 256, 12544, 12544), (20000, 256, 256, 256)])
+@pytest.mark.parametrize("out_split", [False, True])
+def test_gemm_presplit(ops, ps_kb, M, N, K, K1, out_split):
+    """TMA-fed bf16x3 GEMM over Split operands (no in-kernel conversion): equals a float64 evaluation of the three
+    products it issues; residual read from bf16 planes; fp32 or Split output."""
+    assert ops.tc_available()
+    g = torch.Generator().manual_seed(M * 7 + N + K)
+    A = torch.randn(M, K, generator=g); Wt = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g); res = torch.randn(M, N, generator=g)
+    a1 = ops.to_split(A[:, :K1].contiguous().cuda())
+    a2 = ops.to_split(A[:, K1:].contiguous().cuda()) if K1 < K else None
+    ep = ops.make_epilogue(None, bias.cuda(), ops.to_split(res.cuda()), ops.RES_SAME, ldr=N, act=ops.ACT_GELU)
+    Wd = Wt.cuda()
+    got = ops.gemm(a1, Wd, A2=a2, ep=ep, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(Wd), split_out=out_split)
+    want3 = F.gelu(_bf16x3_product(A, Wt) + bias + _merged(res))
+    if out_split:
+        assert isinstance(got, ops.Split) and got.shape == (M, N)
+        assert relerr(got.float().cpu().numpy(), want3.numpy()) < (2e-5 if K <= 3072 else 7e-5)    # + 2^-17 storage rounding
+    else:
+        assert relerr(got.cpu().numpy(), want3.numpy()) < (5e-6 if K <= 768 else (1e-5 if K <= 3072 else 6e-5))
+        assert relerr(got.cpu().numpy(), F.gelu(A.double() @ Wt.double().t() + bias + res).numpy()) < (3e-5 if K <= 3072 else 9e-5)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s,p", [(2, 32, 48, 64, 64, 3, 1, 1), (3, 16, 16, 512, 512, 3, 1, 1), (9, 7, 7, 256, 256, 3, 1, 1),
+                                                 (2, 20, 12, 64, 128, 3, 1, 1), (1, 128, 128, 64, 256, 3, 1, 1), (2, 32, 32, 64, 128, 3, 2, 1),
+                                                 (8, 64, 64, 128, 256, 3, 2, 1), (2, 16, 24, 64, 128, 1, 2, 0), (1, 256, 256, 64, 128, 3, 2, 1)])
+@pytest.mark.parametrize("res_mode", ["same", "up2"])
+def test_conv2d_presplit(ops, ps_kb, B, H, W, Cin, Cout, k, s, p, res_mode):
+    """Implicit-GEMM conv over a Split NHWC activation through a rank-5 TMA map (c, w, h, b, plane)."""
+    assert ops.tc_available()
+    g = torch.Generator().manual_seed(Cin + Cout + H + s)
+    x = torch.randn(B, Cin, H, W, generator=g); w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5; shift = torch.randn(Cout, generator=g)
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    if res_mode == "up2" and (Ho % 2 or Wo % 2):
+        pytest.skip("nearest-x2 residual needs even output dims")
+    rs = (B, Cout, Ho, Wo) if res_mode == "same" else (B, Cout, Ho // 2, Wo // 2)
+    res = torch.randn(*rs, generator=g)
+    rfull = _merged(res) if res_mode == "same" else _merged(res).repeat_interleave(2, 2).repeat_interleave(2, 3)
+    want = F.relu(F.conv2d(_merged(x).double(), _merged(w).double(), None, s, p) * scale[None, :, None, None]
+                  + shift[None, :, None, None] + rfull)
+    ep = ops.make_epilogue(scale.cuda(), shift.cuda(), ops.to_split(res.permute(0, 2, 3, 1).contiguous().cuda()),
+                           ops.RES_SAME if res_mode == "same" else ops.RES_UP2, ldr=Cout, act=ops.ACT_RELU)
+    w_ohwi = ops.repack_oihw_to_ohwi(w.cuda())
+    xs = ops.to_split(x.permute(0, 2, 3, 1).contiguous().cuda())
+    got = ops.conv2d(xs, w_ohwi, s, p, ep=ep, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w_ohwi), split_out=True)
+    assert isinstance(got, ops.Split) and got.shape == (B, Ho, Wo, Cout)
+    assert relerr(got.float().permute(0, 3, 1, 2).cpu().numpy(), want.numpy()) < 3e-5
+
+
+def test_format_aware_memory_kernels(ops):
+    """LayerNorm / pools / scatter / ROI-align writing (and reading) bf16 planes agree with their fp32 forms to the storage
+    rounding of the Split format (2^-16 relative per element)."""
+    g = torch.Generator().manual_seed(11)
+    tol = 2 ** -15
+    x = torch.randn(300, 768, generator=g).cuda(); gam = torch.randn(768, generator=g).cuda(); bet = torch.randn(768, generator=g).cuda()
+    assert relerr(ops.layernorm(x, gam, bet, 1e-12, split=True).float().cpu().numpy(), ops.layernorm(x, gam, bet, 1e-12).cpu().numpy()) < tol
+    a = torch.randn(2, 30, 44, 64, generator=g).cuda()
+    mp = ops.maxpool3x3s2(a)
+    assert torch.equal(ops.maxpool3x3s2(a, split_out=True).float(), ops.to_split(mp).float())
+    sa = ops.to_split(a)
+    assert relerr(ops.maxpool3x3s2(sa, split_out=True).float().cpu().numpy(), mp.cpu().numpy()) < tol
+    assert relerr(ops.avgpool2x2(sa).float().cpu().numpy(), ops.avgpool2x2(a).cpu().numpy()) < tol
+    # scatter
+    rng = np.random.default_rng(3)
+    H, W, counts = 128, 192, [33, 20]
+    per = [_boxes(rng, c, H, W) for c in counts]
+    off, doff = _dev_off(counts)
+    boxes = torch.from_numpy(np.concatenate(per, 0)).cuda()
+    emb = torch.randn(sum(counts), 768, generator=g).cuda()
+    idx = ops.box_index_map(boxes, doff, 2, 8, H // 8, W // 8)
+    assert torch.equal(ops.grid_scatter(emb, idx, doff, split=True).float(), ops.to_split(ops.grid_scatter(emb, idx, doff)).float())
+    assert torch.equal(ops.grid_scatter(ops.to_split(emb), idx, doff).t, ops.to_split(ops.grid_scatter(emb, idx, doff)).t)   # plane copy
+    # ROI align from / to planes: same sample grid, values to storage rounding
+    feat = torch.randn(2, H // 4, W // 4, 256, generator=g).cuda()
+    r32, g32 = ops.roi_align(feat, boxes, doff, 0.25, 7, want_grid=True)
+    rs, gs = ops.roi_align(ops.to_split(feat), boxes, doff, 0.25, 7, want_grid=True, split_out=True)
+    assert torch.equal(g32, gs)
+    assert relerr(rs.float().cpu().numpy(), r32.cpu().numpy()) < 2 * tol

@@ -19,7 +19,7 @@ OUT_F32, OUT_SPLIT_BF16 = 0, 1
 class Epilogue(C.Structure):
     _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
                 ("res_mode", C.c_int), ("ldr", C.c_int), ("out_h", C.c_int), ("out_w", C.c_int),
-                ("act", C.c_int), ("out_mode", C.c_int), ("out_plane", C.c_longlong)]
+                ("act", C.c_int), ("out_mode", C.c_int), ("out_plane", C.c_longlong), ("res_plane", C.c_longlong)]
 
 
 class VbgError(RuntimeError):
@@ -40,23 +40,32 @@ SIGNATURES = {
     "vbg_embed_ln": [_p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _p, _p],
     "vbg_layernorm": [_p, _p, _p, _f, _i, _i, _p, _p],
     "vbg_attention_fwd": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
-    "vbg_attention_split_fwd": [_p, _ll, _p, _i, _i, _i, _i, _i, _p, _p],
+    "vbg_embed_ln_x": [_p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _p, _ll, _p],
+    "vbg_layernorm_x": [_p, _p, _p, _f, _i, _i, _p, _ll, _p],
+    "vbg_attention_split_fwd": [_p, _ll, _p, _i, _i, _i, _i, _i, _p, _ll, _p],
     "vbg_segment_starts": [_p, _p, _i, _i, _i, _p, _p, _p],
     "vbg_segment_reduce": [_p, _p, _p, _i, _i, _i, _p, _p],
     "vbg_box_index_map": [_p, _p, _i, _i, _i, _i, _p, _p],
     "vbg_grid_scatter": [_p, _p, _p, _i, _i, _i, _p, _p],
+    "vbg_grid_scatter_x": [_p, _ll, _p, _p, _i, _i, _i, _p, _ll, _p],
     "vbg_label_paint": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
     "vbg_seg_ce_loss": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p],
     "vbg_gemm": [_p, _i, _p, _i, _i, _p, _i, _p, _ll, _p, _i, _i, _i, _i, _EP, _i, _p],
+    "vbg_gemm_ps": [_p, _ll, _i, _p, _ll, _i, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _EP, _p],
+    "vbg_conv2d_ps": [_p, _ll, _i, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p, _EP, _p],
+    "vbg_merge_bf16": [_p, _p, _ll, _p, _p],
     "vbg_conv2d": [_p, _i, _i, _i, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _EP, _i, _p],
     "vbg_split_bf16": [_p, _ll, _p, _p, _p],
     "vbg_stem_conv": [_p, _i, _i, _i, _p, _p, _ll, _i, _p, _EP, _i, _p],
     "vbg_stem_pack_weights": [_p, _i, _p, _p, _p],
     "vbg_maxpool3x3s2": [_p, _i, _i, _i, _i, _p, _p],
     "vbg_avgpool2x2": [_p, _i, _i, _i, _i, _p, _p],
+    "vbg_maxpool3x3s2_x": [_p, _ll, _i, _i, _i, _i, _p, _ll, _p],
+    "vbg_avgpool2x2_x": [_p, _ll, _i, _i, _i, _i, _p, _ll, _p],
     "vbg_bn_fold": [_p, _p, _p, _p, _f, _i, _p, _p, _p],
     "vbg_repack_oihw_to_ohwi": [_p, _i, _i, _i, _i, _p, _p],
     "vbg_roi_align_fwd": [_p, _i, _i, _i, _i, _p, _p, _i, _f, _i, _p, _p, _p],
+    "vbg_roi_align_x": [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _f, _i, _p, _ll, _p, _p],
     "vbg_softmax_rows": [_p, _i, _i, _p, _p],
     "vbg_full_head_scores": [_p, _p, _i, _i, _p, _p],
     "vbg_upsample_split_nchw": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p],

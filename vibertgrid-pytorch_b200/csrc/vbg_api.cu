@@ -29,6 +29,11 @@ int conv_tc3(const float* x, int B, int H, int W, int Cin, const void* w_split, 
 int stem_tc3(const float* x4, int B, int H, int W, const void* w_split, long long plane, int Cout, float* y,
              const vbg_epilogue_t* ep, cudaStream_t s);
 int split_bf16(const float* w, long long n, void* hi, void* lo, cudaStream_t s);
+int merge_bf16(const void* hi, const void* lo, long long n, float* out, cudaStream_t s);
+int gemm_ps(const void* A, long long a_plane, int lda, const void* A2, long long a2_plane, int lda2, int K1, const void* w_hi,
+            long long w_plane, int ldw, void* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep, cudaStream_t s);
+int conv_ps(const void* x, long long x_plane, int B, int H, int W, int Cin, const void* w_hi, long long w_plane, int Cout, int kh,
+            int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, cudaStream_t s);
 bool tc_available();
 
 // ------------------------------------------------------------------ CRF Viterbi (model/crf.py:96-146)
@@ -104,6 +109,8 @@ static int check_epilogue(const vbg_epilogue_t* ep, const char* who) {
   VBG_REQUIRE(ep->res_mode >= VBG_RES_NONE && ep->res_mode <= VBG_RES_UP2, "%s: bad residual mode %d", who, ep->res_mode);
   VBG_REQUIRE((ep->residual != nullptr) == (ep->res_mode != VBG_RES_NONE), "%s: residual pointer / mode mismatch", who);
   VBG_REQUIRE(ep->out_mode == VBG_OUT_F32 || ep->out_mode == VBG_OUT_SPLIT_BF16, "%s: bad out_mode %d", who, ep->out_mode);
+  VBG_REQUIRE(ep->out_mode == VBG_OUT_F32 || (ep->out_plane > 0 && ep->out_plane % 8 == 0), "%s: out_plane must be a positive multiple of 8", who);
+  VBG_REQUIRE(ep->res_plane >= 0 && ep->res_plane % 8 == 0 && (ep->res_plane == 0 || ep->residual), "%s: bad res_plane", who);
   return VBG_OK;
 }
 
@@ -132,7 +139,8 @@ extern "C" int vbg_gemm(const float* A, int lda, const float* A2, int lda2, int 
     rc = gemm_tc(A, lda, A2, lda2, K1, W, ldw, C, ldc, M, N, K, ep, s);
     if (rc != VBG_EUNSUPPORTED) return rc;
   }
-  VBG_REQUIRE(!ep || ep->out_mode == VBG_OUT_F32, "vbg_gemm: VBG_OUT_SPLIT_BF16 needs a tensor-core path (shape / precision not eligible)");
+  VBG_REQUIRE(!ep || (ep->out_mode == VBG_OUT_F32 && ep->res_plane == 0),
+              "vbg_gemm: bf16-plane output / residual needs a tensor-core path (shape / precision not eligible)");
   return gemm_simt(A, lda, A2, lda2, K1, W, ldw, C, ldc, M, N, K, ep, s);
 }
 
@@ -158,8 +166,52 @@ extern "C" int vbg_conv2d(const float* x, int B, int H, int W, int Cin, const fl
     rc = conv_tc(x, B, H, W, Cin, w, Cout, kh, kw, stride, pad, y, ep, s);
     if (rc != VBG_EUNSUPPORTED) return rc;
   }
-  VBG_REQUIRE(!ep || ep->out_mode == VBG_OUT_F32, "vbg_conv2d: VBG_OUT_SPLIT_BF16 needs a tensor-core path");
+  VBG_REQUIRE(!ep || (ep->out_mode == VBG_OUT_F32 && ep->res_plane == 0), "vbg_conv2d: bf16-plane output / residual needs a tensor-core path");
   return conv_simt(x, B, H, W, Cin, w, Cout, kh, kw, stride, pad, y, ep, s);
+}
+
+extern "C" int vbg_gemm_ps(const void* A_hi, long long a_plane, int lda, const void* A2_hi, long long a2_plane, int lda2, int K1,
+                           const void* W_hi, long long w_plane, int ldw, void* C, int ldc, int M, int N, int K,
+                           const vbg_epilogue_t* ep, vbg_stream_t stream) {
+  VBG_REQUIRE(A_hi && W_hi && C, "vbg_gemm_ps: null pointer");
+  VBG_REQUIRE(M >= 0 && N > 0 && K > 0 && K1 > 0 && K1 <= K, "vbg_gemm_ps: bad shape M=%d N=%d K=%d K1=%d", M, N, K, K1);
+  VBG_REQUIRE((K1 == K) || A2_hi, "vbg_gemm_ps: A2 required when K1 < K");
+  VBG_REQUIRE(lda >= K1 && ldw >= K && ldc >= N && (K1 == K || lda2 >= K - K1), "vbg_gemm_ps: leading dimension too small");
+  int rc = check_epilogue(ep, "vbg_gemm_ps");
+  if (rc) return rc;
+  if (ep && ep->res_mode == VBG_RES_UP2)
+    VBG_REQUIRE(ep->out_h > 0 && ep->out_w > 0 && M % (ep->out_h * ep->out_w) == 0 && ep->out_h % 2 == 0 && ep->out_w % 2 == 0,
+                "vbg_gemm_ps: VBG_RES_UP2 needs even out_h/out_w dividing M");
+  if (ep && ep->res_mode == VBG_RES_SAME) VBG_REQUIRE(ep->ldr >= N, "vbg_gemm_ps: ldr too small");
+  if (M == 0) return VBG_OK;
+  rc = gemm_ps(A_hi, a_plane, lda, A2_hi, a2_plane, lda2, K1, W_hi, w_plane, ldw, C, ldc, M, N, K, ep, as_stream(stream));
+  if (rc == VBG_EUNSUPPORTED)
+    set_error("vbg_gemm_ps: needs sm_100a, N >= 64, K %% 64 == 0, K1 %% 64 == 0, lda/ldw %% 8 == 0, 16B-aligned planes with plane %% 8 == 0 "
+              "(M=%d N=%d K=%d K1=%d)", M, N, K, K1);
+  return rc;
+}
+
+extern "C" int vbg_conv2d_ps(const void* x_hi, long long x_plane, int B, int H, int W, int Cin, const void* w_hi, long long w_plane,
+                             int Cout, int kh, int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, vbg_stream_t stream) {
+  VBG_REQUIRE(x_hi && w_hi && y, "vbg_conv2d_ps: null pointer");
+  VBG_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "vbg_conv2d_ps: bad geometry");
+  VBG_REQUIRE(H + 2 * pad >= kh && W + 2 * pad >= kw, "vbg_conv2d_ps: kernel larger than padded input");
+  int rc = check_epilogue(ep, "vbg_conv2d_ps");
+  if (rc) return rc;
+  if (ep && ep->res_mode == VBG_RES_UP2) {
+    int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+    VBG_REQUIRE(Ho % 2 == 0 && Wo % 2 == 0, "vbg_conv2d_ps: VBG_RES_UP2 needs even output dims");
+  }
+  rc = conv_ps(x_hi, x_plane, B, H, W, Cin, w_hi, w_plane, Cout, kh, kw, stride, pad, y, ep, as_stream(stream));
+  if (rc == VBG_EUNSUPPORTED)
+    set_error("vbg_conv2d_ps: needs sm_100a, Cin %% 64 == 0, Cout >= 64, stride 1 or 2, 16B-aligned planes (Cin=%d Cout=%d stride=%d)",
+              Cin, Cout, stride);
+  return rc;
+}
+
+extern "C" int vbg_merge_bf16(const void* hi, const void* lo, long long n, float* out, vbg_stream_t stream) {
+  VBG_REQUIRE(hi && lo && out && n >= 0, "vbg_merge_bf16: bad arguments");
+  return merge_bf16(hi, lo, n, out, as_stream(stream));
 }
 
 extern "C" int vbg_stem_conv(const float* x4, int B, int H, int W, const float* w_ohwi4, const void* w_split, long long split_plane,

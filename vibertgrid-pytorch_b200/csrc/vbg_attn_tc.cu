@@ -26,13 +26,6 @@ constexpr int kAtThreads = 160;
 constexpr uint32_t kTileQ = 128 * 128;       // one bf16 operand tile of 128 rows x 64 elements
 constexpr uint32_t kVtTile = 64 * 128;       // V^T tile: 64 d-rows x 64 keys (bf16)
 
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __bfloat162float(h.x), b - __bfloat162float(h.y));
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 // 64 fp32 of one row (src, 256 B, or zeros) -> row r of the hi / lo operand tiles (128 B each, swizzled 16-byte chunks)
 __device__ __forceinline__ void load_split_row(const float* __restrict__ src, bool valid, uint8_t* t1, uint8_t* t2, int r) {
   float4 v[16];
@@ -248,7 +241,8 @@ constexpr uint32_t kVTile = 64 * 128;        // 64 keys x 64 dims (bf16)
 __global__ void __launch_bounds__(kAt2Threads, 1)
 attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_constant__ CUtensorMap tmQKl,
                        const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
-                       const int32_t* __restrict__ cu, int heads, float scale_log2e, float* __restrict__ out) {
+                       const int32_t* __restrict__ cu, int heads, float scale_log2e, void* __restrict__ out,
+                       long long out_plane) {
   const int seq = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * 128;
   const int row0 = cu[seq], len = cu[seq + 1] - row0;
   if (q0 >= len) return;
@@ -410,16 +404,16 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
     mbar_wait(o_full, 0);
     tc_fence_after();
     const float inv = __fdiv_rn(1.0f, sum);
-    float* orow = out + (size_t)(row0 + q0 + r) * hidden + head * 64 + grp * 32;     // group g stores dims [32g, 32g+32)
+    const size_t o4 = ((size_t)(row0 + q0 + r) * hidden + head * 64 + grp * 32) >> 2;   // group g stores dims [32g, 32g+32)
     {
       uint32_t v[32];
       tmem_ld32(lane_addr + (uint32_t)(grp * 32), v);
       if (q0 + r < len) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(orow + 4 * j) =
-              make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
-                          __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv);
+          st4_fmt(out, out_plane, o4 + j,
+                  make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
+                              __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv));
       }
     }
   }
@@ -433,7 +427,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
 }
 
 int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len, int heads,
-                    int head_dim, float* out, cudaStream_t s) {
+                    int head_dim, void* out, long long out_plane, cudaStream_t s) {
   if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
   if (head_dim != 64 || max_len > 512 || !aligned16(qkv_hi) || ((plane * 2) & 15)) return VBG_EUNSUPPORTED;
   const long long ld = 3LL * heads * 64;
@@ -454,7 +448,7 @@ int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int 
     attr = true;
   }
   dim3 grid(cdiv(max_len, 128), heads, nseq);
-  attention_split_kernel<<<grid, kAt2Threads, smem, s>>>(mq[0], mq[1], mv[0], mv[1], cu, heads, 0.125f * 1.4426950408889634f, out);
+  attention_split_kernel<<<grid, kAt2Threads, smem, s>>>(mq[0], mq[1], mv[0], mv[1], cu, heads, 0.125f * 1.4426950408889634f, out, out_plane);
   return check_launch("vbg_attention_split_fwd(tcgen05)");
 }
 

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256)
 ln_kernel(const float* __restrict__ x, const int32_t* __restrict__ ids, const int32_t* __restrict__ pos,
           const float* __restrict__ word, const float* __restrict__ position, const float* __restrict__ type0,
           const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int R, int H4, int vocab,
-          int max_pos, float* __restrict__ out) {
+          int max_pos, void* __restrict__ out, long long out_plane) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
@@ -82,7 +82,6 @@ ln_kernel(const float* __restrict__ x, const int32_t* __restrict__ ids, const in
   const float rstd = __fdiv_rn(1.0f, sqrtf(warp_sum(sq) / n + eps));
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
-  float4* o4 = reinterpret_cast<float4*>(out) + (size_t)r * H4;
 #pragma unroll
   for (int i = 0; i < kMax; ++i) {
     const int c = lane + 32 * i;
@@ -90,7 +89,7 @@ ln_kernel(const float* __restrict__ x, const int32_t* __restrict__ ids, const in
       float4 g = __ldg(g4 + c), b = __ldg(b4 + c), o;
       o.x = (v[i].x - mean) * rstd * g.x + b.x; o.y = (v[i].y - mean) * rstd * g.y + b.y;
       o.z = (v[i].z - mean) * rstd * g.z + b.z; o.w = (v[i].w - mean) * rstd * g.w + b.w;
-      o4[c] = o;
+      st4_fmt(out, out_plane, (size_t)r * H4 + c, o);
     }
   }
 }
@@ -234,7 +233,7 @@ __global__ void full_head_scores_kernel(const float* __restrict__ pn, const floa
 int attention_tc(const float* qkv, const int32_t* cu, int nseq, int max_len, int heads, int head_dim, float* out,
                  cudaStream_t s);
 int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len, int heads,
-                    int head_dim, float* out, cudaStream_t s);
+                    int head_dim, void* out, long long out_plane, cudaStream_t s);
 
 }  // namespace vbg
 
@@ -248,25 +247,38 @@ extern "C" int vbg_bert_assemble(const int64_t* corpus, int L, const int32_t* se
   return check_launch("vbg_bert_assemble");
 }
 
+extern "C" int vbg_embed_ln_x(const int32_t* ids, const int32_t* pos, const float* word, const float* position,
+                              const float* type0, const float* gamma, const float* beta, float eps, int R, int hidden,
+                              int vocab, int max_pos, void* out, long long out_plane, vbg_stream_t stream) {
+  VBG_REQUIRE(ids && pos && word && position && type0 && gamma && beta && out, "vbg_embed_ln: null pointer");
+  VBG_REQUIRE(hidden % 4 == 0 && hidden <= 1024 && vocab > 0 && max_pos > 0, "vbg_embed_ln: hidden %% 4 == 0 and <= 1024 required");
+  VBG_REQUIRE(fmt_ok(out, out_plane), "vbg_embed_ln: output must be 16B aligned, plane %% 8 == 0");
+  if (R == 0) return VBG_OK;
+  ln_kernel<true><<<cdiv(R, 8), 256, 0, as_stream(stream)>>>(nullptr, ids, pos, word, position, type0, gamma, beta, eps,
+                                                            R, hidden / 4, vocab, max_pos, out, out_plane);
+  return check_launch("vbg_embed_ln");
+}
+
 extern "C" int vbg_embed_ln(const int32_t* ids, const int32_t* pos, const float* word, const float* position,
                             const float* type0, const float* gamma, const float* beta, float eps, int R, int hidden,
                             int vocab, int max_pos, float* out, vbg_stream_t stream) {
-  VBG_REQUIRE(ids && pos && word && position && type0 && gamma && beta && out, "vbg_embed_ln: null pointer");
-  VBG_REQUIRE(hidden % 4 == 0 && hidden <= 1024 && vocab > 0 && max_pos > 0, "vbg_embed_ln: hidden %% 4 == 0 and <= 1024 required");
+  return vbg_embed_ln_x(ids, pos, word, position, type0, gamma, beta, eps, R, hidden, vocab, max_pos, out, 0, stream);
+}
+
+extern "C" int vbg_layernorm_x(const float* x, const float* gamma, const float* beta, float eps, int R, int hidden,
+                               void* out, long long out_plane, vbg_stream_t stream) {
+  VBG_REQUIRE(x && gamma && beta && out, "vbg_layernorm: null pointer");
+  VBG_REQUIRE(hidden % 4 == 0 && hidden <= 1024 && aligned16(x) && fmt_ok(out, out_plane),
+              "vbg_layernorm: hidden %% 4 == 0, <= 1024, 16B alignment, plane %% 8 == 0");
   if (R == 0) return VBG_OK;
-  ln_kernel<true><<<cdiv(R, 8), 256, 0, as_stream(stream)>>>(nullptr, ids, pos, word, position, type0, gamma, beta, eps,
-                                                            R, hidden / 4, vocab, max_pos, out);
-  return check_launch("vbg_embed_ln");
+  ln_kernel<false><<<cdiv(R, 8), 256, 0, as_stream(stream)>>>(x, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta,
+                                                             eps, R, hidden / 4, 0, 0, out, out_plane);
+  return check_launch("vbg_layernorm");
 }
 
 extern "C" int vbg_layernorm(const float* x, const float* gamma, const float* beta, float eps, int R, int hidden,
                              float* out, vbg_stream_t stream) {
-  VBG_REQUIRE(x && gamma && beta && out, "vbg_layernorm: null pointer");
-  VBG_REQUIRE(hidden % 4 == 0 && hidden <= 1024 && aligned16(x) && aligned16(out), "vbg_layernorm: hidden %% 4 == 0, <= 1024, 16B alignment");
-  if (R == 0) return VBG_OK;
-  ln_kernel<false><<<cdiv(R, 8), 256, 0, as_stream(stream)>>>(x, nullptr, nullptr, nullptr, nullptr, nullptr, gamma, beta,
-                                                             eps, R, hidden / 4, 0, 0, out);
-  return check_launch("vbg_layernorm");
+  return vbg_layernorm_x(x, gamma, beta, eps, R, hidden, out, 0, stream);
 }
 
 extern "C" int vbg_attention_fwd(const float* qkv, const int32_t* cu, int nseq, int max_len, int heads, int head_dim,
@@ -292,10 +304,11 @@ extern "C" int vbg_attention_fwd(const float* qkv, const int32_t* cu, int nseq, 
 }
 
 extern "C" int vbg_attention_split_fwd(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len,
-                                       int heads, int head_dim, float* out, vbg_stream_t stream) {
+                                       int heads, int head_dim, void* out, long long out_plane, vbg_stream_t stream) {
   VBG_REQUIRE(qkv_hi && cu && out && nseq >= 0 && R >= 0 && heads > 0 && plane > 0, "vbg_attention_split_fwd: bad arguments");
+  VBG_REQUIRE(fmt_ok(out, out_plane), "vbg_attention_split_fwd: output must be 16B aligned, plane %% 8 == 0");
   if (nseq == 0 || max_len == 0) return VBG_OK;
-  int rc = attention_split(qkv_hi, plane, cu, nseq, R, max_len, heads, head_dim, out, as_stream(stream));
+  int rc = attention_split(qkv_hi, plane, cu, nseq, R, max_len, heads, head_dim, out, out_plane, as_stream(stream));
   if (rc == VBG_EUNSUPPORTED)
     set_error("vbg_attention_split_fwd: needs sm_100a, head_dim 64, max_len <= 512 (got head_dim %d, max_len %d)", head_dim, max_len);
   return rc;

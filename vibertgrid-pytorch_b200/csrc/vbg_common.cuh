@@ -1,6 +1,7 @@
 // Shared helpers for libvbg_sm100a (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -61,6 +62,45 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == VBG_ACT_GELU) return gelu_erf(v);
   return v;
 }
+
+// ------------------------------------------------------------------ activation storage formats
+// An activation is either fp32 (plane == 0: `base` is float*) or a pair of bf16 planes (plane > 0: `base` is the hi
+// plane = bf16_rn(x), the lo plane = bf16_rn(x - hi) starts `plane` ELEMENTS later): hi + lo carries 16 mantissa bits
+// and is the operand format the bf16x3 tensor-core kernels consume without conversion.  i4 indexes groups of 4 elements.
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// (a, b) -> packed bf16 pairs hi = bf16_rn(.), lo = bf16_rn(. - hi): two packed F2FP conversions, no scalar F2F
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                 // .x = a in the low half
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
+  split2(v.x, v.y, hi.x, lo.x);
+  split2(v.z, v.w, hi.y, lo.y);
+}
+__device__ __forceinline__ float bf16lo_f(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi_f(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ float4 merge4(const uint2 hi, const uint2 lo) {
+  return make_float4(bf16lo_f(hi.x) + bf16lo_f(lo.x), bf16hi_f(hi.x) + bf16hi_f(lo.x),
+                     bf16lo_f(hi.y) + bf16lo_f(lo.y), bf16hi_f(hi.y) + bf16hi_f(lo.y));
+}
+__device__ __forceinline__ float4 ld4_fmt(const void* __restrict__ base, long long plane, size_t i4) {
+  if (plane == 0) return __ldg(reinterpret_cast<const float4*>(base) + i4);
+  const uint2* h = reinterpret_cast<const uint2*>(base);
+  const uint2* l = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(base) + plane);
+  return merge4(__ldg(h + i4), __ldg(l + i4));
+}
+__device__ __forceinline__ void st4_fmt(void* __restrict__ base, long long plane, size_t i4, const float4 v) {
+  if (plane == 0) { reinterpret_cast<float4*>(base)[i4] = v; return; }
+  uint2 hi, lo;
+  split4(v, hi, lo);
+  reinterpret_cast<uint2*>(base)[i4] = hi;
+  reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + plane)[i4] = lo;
+}
+inline bool fmt_ok(const void* p, long long plane) { return p && plane >= 0 && (plane % 8) == 0 && aligned16(p); }
 
 // Python slice index normalisation for one bound: i<0 -> i+dim, then clamp to [0,dim]
 __device__ __forceinline__ int py_slice_bound(int i, int dim) {

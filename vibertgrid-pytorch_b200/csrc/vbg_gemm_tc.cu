@@ -158,11 +158,12 @@ bool tc_available() {
 }
 
 bool tc_encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box, const cuuint32_t* elem_strides, bool dtype_bf16) {
+               const cuuint32_t* box, const cuuint32_t* elem_strides, bool dtype_bf16, bool swizzle64) {
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r = g_encode(tm, dtype_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
                         const_cast<void*>(base), dims, strides_bytes, box, elem_strides ? elem_strides : ones,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return false; }
   return true;

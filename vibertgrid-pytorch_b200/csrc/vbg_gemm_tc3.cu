@@ -259,7 +259,7 @@ static int launch3(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMa
 
 // N-tile width: the candidate with the best (wave efficiency x tile efficiency).  Wider tiles re-read A less often;
 // the persistent grid makes the cost of a partial last wave explicit.
-static int pick_bn3(int m_tiles, int N) {
+int pick_bn3(int m_tiles, int N) {
   static const int forced = [] { const char* e = getenv("VBG_TC3_BN"); return e ? atoi(e) : 0; }();   // tuning experiments only
   if ((forced == 64 || forced == 128 || forced == 192 || forced == 256) && N >= forced - 32) return forced;
   const int cand[4] = {256, 192, 128, 64};

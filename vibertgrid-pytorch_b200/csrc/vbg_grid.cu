@@ -221,20 +221,45 @@ __global__ void seg_ce_finish_kernel(const float* __restrict__ partial, int nblk
 __global__ void __launch_bounds__(256)
 grid_scatter_kernel(const float* __restrict__ seg_emb, const int32_t* __restrict__ idx,
                     const int32_t* __restrict__ seg_off, int cells_per_img, long long total_cells, int C4,
-                    float* __restrict__ grid) {
+                    void* __restrict__ grid, long long grid_plane) {
   const int lane = threadIdx.x & 31;
   long long cell = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long step = (long long)gridDim.x * (blockDim.x >> 5);
   for (; cell < total_cells; cell += step) {
     const int b = (int)(cell / cells_per_img);
     const int s = __ldg(idx + cell);
-    float4* dst = reinterpret_cast<float4*>(grid) + cell * C4;
+    const size_t dst = (size_t)cell * C4;
     if (s >= 0) {
       const float4* src = reinterpret_cast<const float4*>(seg_emb) + (size_t)(__ldg(seg_off + b) + s) * C4;
-      for (int c = lane; c < C4; c += 32) dst[c] = __ldg(src + c);
+      for (int c = lane; c < C4; c += 32) st4_fmt(grid, grid_plane, dst + c, __ldg(src + c));
     } else {
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int c = lane; c < C4; c += 32) dst[c] = z;
+      for (int c = lane; c < C4; c += 32) st4_fmt(grid, grid_plane, dst + c, z);
+    }
+  }
+}
+
+// Split source -> Split grid: a pure copy of the two bf16 planes, 16 bytes (8 elements) per lane.
+__global__ void __launch_bounds__(256)
+grid_scatter_planes_kernel(const __nv_bfloat16* __restrict__ seg_emb, long long emb_plane, const int32_t* __restrict__ idx,
+                           const int32_t* __restrict__ seg_off, int cells_per_img, long long total_cells, int C8,
+                           __nv_bfloat16* __restrict__ grid, long long grid_plane) {
+  const int lane = threadIdx.x & 31;
+  long long cell = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long step = (long long)gridDim.x * (blockDim.x >> 5);
+  for (; cell < total_cells; cell += step) {
+    const int b = (int)(cell / cells_per_img);
+    const int s = __ldg(idx + cell);
+    uint4* d0 = reinterpret_cast<uint4*>(grid) + cell * C8;
+    uint4* d1 = reinterpret_cast<uint4*>(grid + grid_plane) + cell * C8;
+    if (s >= 0) {
+      const size_t row = (size_t)(__ldg(seg_off + b) + s) * C8;
+      const uint4* s0 = reinterpret_cast<const uint4*>(seg_emb) + row;
+      const uint4* s1 = reinterpret_cast<const uint4*>(seg_emb + emb_plane) + row;
+      for (int c = lane; c < C8; c += 32) { d0[c] = __ldg(s0 + c); d1[c] = __ldg(s1 + c); }
+    } else {
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      for (int c = lane; c < C8; c += 32) { d0[c] = z; d1[c] = z; }
     }
   }
 }
@@ -309,12 +334,27 @@ extern "C" int vbg_seg_ce_loss(const int32_t* boxes, const int32_t* seg_off, con
 
 extern "C" int vbg_grid_scatter(const float* seg_emb, const int32_t* idx, const int32_t* seg_off, int B, int cells, int C,
                                 float* grid, vbg_stream_t stream) {
-  VBG_REQUIRE(seg_emb && idx && seg_off && grid && B > 0 && cells > 0, "vbg_grid_scatter: bad arguments");
-  VBG_REQUIRE(C > 0 && C % 4 == 0 && aligned16(seg_emb) && aligned16(grid), "vbg_grid_scatter: C %% 4 and 16B alignment required");
+  return vbg_grid_scatter_x(seg_emb, 0, idx, seg_off, B, cells, C, grid, 0, stream);
+}
+
+extern "C" int vbg_grid_scatter_x(const void* seg_emb_v, long long emb_plane, const int32_t* idx, const int32_t* seg_off, int B,
+                                  int cells, int C, void* grid, long long grid_plane, vbg_stream_t stream) {
+  VBG_REQUIRE(seg_emb_v && idx && seg_off && grid && B > 0 && cells > 0, "vbg_grid_scatter: bad arguments");
+  VBG_REQUIRE(C > 0 && C % 4 == 0 && fmt_ok(seg_emb_v, emb_plane) && fmt_ok(grid, grid_plane), "vbg_grid_scatter: C %% 4 and 16B alignment required");
+  VBG_REQUIRE(emb_plane == 0 || (grid_plane > 0 && C % 8 == 0), "vbg_grid_scatter: a bf16-plane source needs a bf16-plane grid and C %% 8 == 0");
+  if (emb_plane > 0) {
+    long long total = (long long)B * cells;
+    int blocks = (int)((total + 7) / 8);
+    if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+    grid_scatter_planes_kernel<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(seg_emb_v), emb_plane, idx, seg_off,
+                                                                     cells, total, C / 8, reinterpret_cast<__nv_bfloat16*>(grid), grid_plane);
+    return check_launch("vbg_grid_scatter");
+  }
+  const float* seg_emb = reinterpret_cast<const float*>(seg_emb_v);
   long long total = (long long)B * cells;
   int blocks = (int)((total + 7) / 8);
   int cap = kNumSMs * 16;                      // 8 resident CTAs/SM x 2 waves, then grid-stride
   if (blocks > cap) blocks = cap;
-  grid_scatter_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seg_emb, idx, seg_off, cells, total, C / 4, grid);
+  grid_scatter_kernel<<<blocks, 256, 0, as_stream(stream)>>>(seg_emb, idx, seg_off, cells, total, C / 4, grid, grid_plane);
   return check_launch("vbg_grid_scatter");
 }

@@ -47,8 +47,8 @@ __global__ void stem_pack_kernel(const float* __restrict__ w, int O, float* __re
 }
 
 // ------------------------------------------------------------------ pooling (NHWC, float4 over channels)
-__global__ void maxpool3x3s2_kernel(const float4* __restrict__ x, int B, int H, int W, int C4, int Ho, int Wo,
-                                    float4* __restrict__ y) {
+__global__ void maxpool3x3s2_kernel(const void* __restrict__ x, long long x_plane, int B, int H, int W, int C4, int Ho, int Wo,
+                                    void* __restrict__ y, long long y_plane) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * Ho * Wo * C4;
   if (i >= total) return;
@@ -64,14 +64,15 @@ __global__ void maxpool3x3s2_kernel(const float4* __restrict__ x, int B, int H, 
     for (int dx = 0; dx < 3; ++dx) {
       int wi = wo * 2 - 1 + dx;
       if (wi < 0 || wi >= W) continue;
-      float4 v = __ldg(x + (((size_t)b * H + hi) * W + wi) * C4 + c);
+      float4 v = ld4_fmt(x, x_plane, (((size_t)b * H + hi) * W + wi) * C4 + c);
       m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
     }
   }
-  y[i] = m;
+  st4_fmt(y, y_plane, (size_t)i, m);
 }
 
-__global__ void avgpool2x2_kernel(const float4* __restrict__ x, int B, int H, int W, int C4, float4* __restrict__ y) {
+__global__ void avgpool2x2_kernel(const void* __restrict__ x, long long x_plane, int B, int H, int W, int C4,
+                                  void* __restrict__ y, long long y_plane) {
   const int Ho = H / 2, Wo = W / 2;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * Ho * Wo * C4;
@@ -79,12 +80,13 @@ __global__ void avgpool2x2_kernel(const float4* __restrict__ x, int B, int H, in
   int c = (int)(i % C4); long long t = i / C4;
   int wo = (int)(t % Wo); t /= Wo;
   int ho = (int)(t % Ho); int b = (int)(t / Ho);
-  const float4* p = x + (((size_t)b * H + 2 * ho) * W + 2 * wo) * C4 + c;
-  float4 a = __ldg(p), bb = __ldg(p + C4), cc = __ldg(p + (size_t)W * C4), d = __ldg(p + (size_t)W * C4 + C4);
+  const size_t p = (((size_t)b * H + 2 * ho) * W + 2 * wo) * C4 + c;
+  float4 a = ld4_fmt(x, x_plane, p), bb = ld4_fmt(x, x_plane, p + C4), cc = ld4_fmt(x, x_plane, p + (size_t)W * C4),
+         d = ld4_fmt(x, x_plane, p + (size_t)W * C4 + C4);
   float4 r;
   r.x = (a.x + bb.x + cc.x + d.x) * 0.25f; r.y = (a.y + bb.y + cc.y + d.y) * 0.25f;
   r.z = (a.z + bb.z + cc.z + d.z) * 0.25f; r.w = (a.w + bb.w + cc.w + d.w) * 0.25f;
-  y[i] = r;
+  st4_fmt(y, y_plane, (size_t)i, r);
 }
 
 // ------------------------------------------------------------------ parameter preparation
@@ -170,21 +172,29 @@ extern "C" int vbg_stem_pack_weights(const float* w_oihw, int O, float* w_ohwi4,
   return check_launch("vbg_stem_pack_weights");
 }
 
-extern "C" int vbg_maxpool3x3s2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream) {
-  VBG_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C % 4 == 0 && aligned16(x) && aligned16(y), "vbg_maxpool3x3s2: bad arguments");
+extern "C" int vbg_maxpool3x3s2_x(const void* x, long long x_plane, int B, int H, int W, int C, void* y, long long y_plane,
+                                  vbg_stream_t stream) {
+  VBG_REQUIRE(B > 0 && H > 0 && W > 0 && C % 4 == 0 && fmt_ok(x, x_plane) && fmt_ok(y, y_plane), "vbg_maxpool3x3s2: bad arguments");
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   long long total = (long long)B * Ho * Wo * (C / 4);
-  maxpool3x3s2_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(x), B, H, W, C / 4, Ho, Wo, reinterpret_cast<float4*>(y));
+  maxpool3x3s2_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(x, x_plane, B, H, W, C / 4, Ho, Wo, y, y_plane);
   return check_launch("vbg_maxpool3x3s2");
 }
 
-extern "C" int vbg_avgpool2x2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream) {
-  VBG_REQUIRE(x && y && B > 0 && H > 1 && W > 1 && C % 4 == 0 && aligned16(x) && aligned16(y), "vbg_avgpool2x2: bad arguments");
+extern "C" int vbg_maxpool3x3s2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream) {
+  return vbg_maxpool3x3s2_x(x, 0, B, H, W, C, y, 0, stream);
+}
+
+extern "C" int vbg_avgpool2x2_x(const void* x, long long x_plane, int B, int H, int W, int C, void* y, long long y_plane,
+                                vbg_stream_t stream) {
+  VBG_REQUIRE(B > 0 && H > 1 && W > 1 && C % 4 == 0 && fmt_ok(x, x_plane) && fmt_ok(y, y_plane), "vbg_avgpool2x2: bad arguments");
   long long total = (long long)B * (H / 2) * (W / 2) * (C / 4);
-  avgpool2x2_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const float4*>(x), B, H, W, C / 4, reinterpret_cast<float4*>(y));
+  avgpool2x2_kernel<<<cdiv(total, 256), 256, 0, as_stream(stream)>>>(x, x_plane, B, H, W, C / 4, y, y_plane);
   return check_launch("vbg_avgpool2x2");
+}
+
+extern "C" int vbg_avgpool2x2(const float* x, int B, int H, int W, int C, float* y, vbg_stream_t stream) {
+  return vbg_avgpool2x2_x(x, 0, B, H, W, C, y, 0, stream);
 }
 
 extern "C" int vbg_bn_fold(const float* weight, const float* bias, const float* mean, const float* var, float eps, int C,

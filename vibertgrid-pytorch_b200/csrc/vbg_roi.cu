@@ -16,9 +16,9 @@ namespace vbg {
 
 template <int kVec>  // float4 vectors per lane (C = 128 * kVec)
 __global__ void __launch_bounds__(256)
-roi_align_kernel(const float* __restrict__ feat, int B, int Hf, int Wf, int C, const int32_t* __restrict__ boxes,
-                 const int32_t* __restrict__ seg_off, int K, float scale, int P, float* __restrict__ out,
-                 int32_t* __restrict__ sample_grid) {
+roi_align_kernel(const void* __restrict__ feat, long long feat_plane, int B, int Hf, int Wf, int C,
+                 const int32_t* __restrict__ boxes, const int32_t* __restrict__ seg_off, int K, float scale, int P,
+                 void* __restrict__ out, long long out_plane, int32_t* __restrict__ sample_grid) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long total = (long long)K * P * P;
@@ -39,7 +39,7 @@ roi_align_kernel(const float* __restrict__ feat, int B, int Hf, int Wf, int C, c
   const float count = (float)max(gh * gw, 1);
 
   const int C4 = C >> 2;
-  const float4* f4 = reinterpret_cast<const float4*>(feat) + (size_t)b * Hf * Wf * C4;
+  const size_t f0 = (size_t)b * Hf * Wf * C4;
   float4 acc[kVec];
 #pragma unroll
   for (int v = 0; v < kVec; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -58,15 +58,16 @@ roi_align_kernel(const float* __restrict__ feat, int B, int Hf, int Wf, int C, c
       if (xl >= Wf - 1) { xh = xl = Wf - 1; xx = (float)xl; } else { xh = xl + 1; }
       const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
       const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-      const float4* p1 = f4 + ((size_t)yl * Wf + xl) * C4;
-      const float4* p2 = f4 + ((size_t)yl * Wf + xh) * C4;
-      const float4* p3 = f4 + ((size_t)yh * Wf + xl) * C4;
-      const float4* p4 = f4 + ((size_t)yh * Wf + xh) * C4;
+      const size_t p1 = f0 + ((size_t)yl * Wf + xl) * C4;
+      const size_t p2 = f0 + ((size_t)yl * Wf + xh) * C4;
+      const size_t p3 = f0 + ((size_t)yh * Wf + xl) * C4;
+      const size_t p4 = f0 + ((size_t)yh * Wf + xh) * C4;
 #pragma unroll
       for (int v = 0; v < kVec; ++v) {
         const int c = lane + 32 * v;
         if (c < C4) {
-          float4 a = __ldg(p1 + c), bb = __ldg(p2 + c), cc = __ldg(p3 + c), d = __ldg(p4 + c);
+          float4 a = ld4_fmt(feat, feat_plane, p1 + c), bb = ld4_fmt(feat, feat_plane, p2 + c),
+                 cc = ld4_fmt(feat, feat_plane, p3 + c), d = ld4_fmt(feat, feat_plane, p4 + c);
           acc[v].x += w1 * a.x + w2 * bb.x + w3 * cc.x + w4 * d.x;
           acc[v].y += w1 * a.y + w2 * bb.y + w3 * cc.y + w4 * d.y;
           acc[v].z += w1 * a.z + w2 * bb.z + w3 * cc.z + w4 * d.z;
@@ -75,7 +76,7 @@ roi_align_kernel(const float* __restrict__ feat, int B, int Hf, int Wf, int C, c
       }
     }
   }
-  float4* o4 = reinterpret_cast<float4*>(out) + (size_t)warp * C4;   // [K,P,P,C]
+  const size_t o4 = (size_t)warp * C4;                                 // [K,P,P,C]
 #pragma unroll
   for (int v = 0; v < kVec; ++v) {
     const int c = lane + 32 * v;
@@ -83,7 +84,7 @@ roi_align_kernel(const float* __restrict__ feat, int B, int Hf, int Wf, int C, c
       float4 r = acc[v];
       r.x = __fdiv_rn(r.x, count); r.y = __fdiv_rn(r.y, count);
       r.z = __fdiv_rn(r.z, count); r.w = __fdiv_rn(r.w, count);
-      o4[c] = r;
+      st4_fmt(out, out_plane, o4 + c, r);
     }
   }
 }
@@ -176,6 +177,96 @@ roi_align_sep_kernel(const float* __restrict__ feat, int B, int Hf, int Wf, int 
   }
 }
 
+// ------------------------------------------------------------------ windowed form (the default)
+// One CTA per (ROI, 64-channel chunk).  The feature window the ROI's samples can touch -- rows [y_lo, y_hi] x columns
+// [x_lo, x_hi] -- is staged ONCE into shared memory with coalesced 256-byte reads (either storage format, merged to fp32
+// on the way in), then every (bin, channel-quad) item accumulates its gh x gw samples from shared memory in exactly the
+// direct kernel's operation order (same sample-grid table, same summation order => identical values).  HBM / L2 -> SM
+// traffic per ROI drops from (samples x 4 taps x C) per bin -- ~24 KB per 1 KB of output at line-sized boxes -- to the
+// window itself.  ROIs whose window does not fit `win_floats` fall back to global taps inside the same kernel.
+constexpr int kRoiCh = 64, kRoiCq = kRoiCh / 4;
+
+__global__ void __launch_bounds__(256)
+roi_align_win_kernel(const void* __restrict__ feat, long long feat_plane, int B, int Hf, int Wf, int C,
+                     const int32_t* __restrict__ boxes, const int32_t* __restrict__ seg_off, float scale, int P,
+                     void* __restrict__ out, long long out_plane, int32_t* __restrict__ sample_grid, int win_floats) {
+  extern __shared__ __align__(16) float win[];
+  const int k = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+  const int b = sample_of(seg_off, B, k);
+  const int4 bx = __ldg(reinterpret_cast<const int4*>(boxes) + k);
+  const float sw = __fmul_rn((float)bx.x, scale), sh = __fmul_rn((float)bx.y, scale);
+  const float ew = __fmul_rn((float)bx.z, scale), eh = __fmul_rn((float)bx.w, scale);
+  const float rw = fmaxf(__fsub_rn(ew, sw), 1.0f), rh = fmaxf(__fsub_rn(eh, sh), 1.0f);
+  const float bw = __fdiv_rn(rw, (float)P), bh = __fdiv_rn(rh, (float)P);
+  const int gh = (int)ceilf(__fdiv_rn(rh, (float)P));
+  const int gw = (int)ceilf(__fdiv_rn(rw, (float)P));
+  if (sample_grid && chunk == 0 && tid == 0) { sample_grid[2 * k] = gh; sample_grid[2 * k + 1] = gw; }
+  const float count = (float)max(gh * gw, 1);
+
+  // window bounds from the first / last sample coordinate of each axis (coordinates are monotone in (bin, sample))
+  const float y_first = __fadd_rn(sh, __fdiv_rn(__fmul_rn(0.5f, bh), (float)gh));
+  const float y_last = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)(P - 1), bh)), __fdiv_rn(__fmul_rn((float)gh - 0.5f, bh), (float)gh));
+  const float x_first = __fadd_rn(sw, __fdiv_rn(__fmul_rn(0.5f, bw), (float)gw));
+  const float x_last = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)(P - 1), bw)), __fdiv_rn(__fmul_rn((float)gw - 0.5f, bw), (float)gw));
+  const int y_lo = min(max((int)fmaxf(y_first, 0.f), 0), Hf - 1), y_hi = min(max((int)fmaxf(y_last, 0.f) + 1, y_lo), Hf - 1);
+  const int x_lo = min(max((int)fmaxf(x_first, 0.f), 0), Wf - 1), x_hi = min(max((int)fmaxf(x_last, 0.f) + 1, x_lo), Wf - 1);
+  const int rows = y_hi - y_lo + 1, cols = x_hi - x_lo + 1;
+  const bool staged = (long long)rows * cols * kRoiCh <= (long long)win_floats;
+
+  const int C4 = C >> 2;
+  const size_t f0 = (size_t)b * Hf * Wf * C4 + (size_t)chunk * kRoiCq;
+  if (staged) {
+    const int n4 = rows * cols * kRoiCq;
+    for (int i = tid; i < n4; i += 256) {
+      const int pix = i / kRoiCq, cq = i - pix * kRoiCq;
+      const int y = y_lo + pix / cols, x = x_lo + pix % cols;
+      reinterpret_cast<float4*>(win)[i] = ld4_fmt(feat, feat_plane, f0 + ((size_t)y * Wf + x) * C4 + cq);
+    }
+    __syncthreads();
+  }
+
+  const int items = P * P * kRoiCq;
+  for (int item = tid; item < items; item += 256) {
+    const int bin = item / kRoiCq, cq = item - bin * kRoiCq;
+    const int ph = bin / P, pw = bin - ph * P;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int iy = 0; iy < gh; ++iy) {
+      float y = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)ph, bh)), __fdiv_rn(__fmul_rn((float)iy + 0.5f, bh), (float)gh));
+      for (int ix = 0; ix < gw; ++ix) {
+        float x = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)pw, bw)), __fdiv_rn(__fmul_rn((float)ix + 0.5f, bw), (float)gw));
+        if (y < -1.0f || y > (float)Hf || x < -1.0f || x > (float)Wf) continue;
+        float yy = fmaxf(y, 0.f), xx = fmaxf(x, 0.f);
+        int yl = (int)yy, xl = (int)xx, yh, xh;
+        if (yl >= Hf - 1) { yh = yl = Hf - 1; yy = (float)yl; } else { yh = yl + 1; }
+        if (xl >= Wf - 1) { xh = xl = Wf - 1; xx = (float)xl; } else { xh = xl + 1; }
+        const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+        float4 a, bb, cc, d;
+        if (staged) {
+          // clamped into the window: never out of bounds even if a rounding corner case widened the sample range
+          const int r0 = min(max(yl, y_lo), y_hi) - y_lo, r1 = min(max(yh, y_lo), y_hi) - y_lo;
+          const int c0 = min(max(xl, x_lo), x_hi) - x_lo, c1 = min(max(xh, x_lo), x_hi) - x_lo;
+          const float4* w4p = reinterpret_cast<const float4*>(win) + cq;
+          a = w4p[(r0 * cols + c0) * kRoiCq]; bb = w4p[(r0 * cols + c1) * kRoiCq];
+          cc = w4p[(r1 * cols + c0) * kRoiCq]; d = w4p[(r1 * cols + c1) * kRoiCq];
+        } else {
+          a = ld4_fmt(feat, feat_plane, f0 + ((size_t)yl * Wf + xl) * C4 + cq);
+          bb = ld4_fmt(feat, feat_plane, f0 + ((size_t)yl * Wf + xh) * C4 + cq);
+          cc = ld4_fmt(feat, feat_plane, f0 + ((size_t)yh * Wf + xl) * C4 + cq);
+          d = ld4_fmt(feat, feat_plane, f0 + ((size_t)yh * Wf + xh) * C4 + cq);
+        }
+        acc.x += w1 * a.x + w2 * bb.x + w3 * cc.x + w4 * d.x;
+        acc.y += w1 * a.y + w2 * bb.y + w3 * cc.y + w4 * d.y;
+        acc.z += w1 * a.z + w2 * bb.z + w3 * cc.z + w4 * d.z;
+        acc.w += w1 * a.w + w2 * bb.w + w3 * cc.w + w4 * d.w;
+      }
+    }
+    acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);
+    acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
+    st4_fmt(out, out_plane, ((size_t)k * P * P + bin) * C4 + (size_t)chunk * kRoiCq + cq, acc);
+  }
+}
+
 }  // namespace vbg
 
 using namespace vbg;
@@ -183,27 +274,43 @@ using namespace vbg;
 extern "C" int vbg_roi_align_fwd(const float* feat, int B, int Hf, int Wf, int C, const int32_t* boxes,
                                  const int32_t* seg_off, int K, float spatial_scale, int P, float* out,
                                  int32_t* sample_grid, vbg_stream_t stream) {
+  return vbg_roi_align_x(feat, 0, B, Hf, Wf, C, boxes, seg_off, K, spatial_scale, P, out, 0, sample_grid, stream);
+}
+
+extern "C" int vbg_roi_align_x(const void* feat, long long feat_plane, int B, int Hf, int Wf, int C, const int32_t* boxes,
+                               const int32_t* seg_off, int K, float spatial_scale, int P, void* out, long long out_plane,
+                               int32_t* sample_grid, vbg_stream_t stream) {
   VBG_REQUIRE(feat && boxes && seg_off && out && B > 0 && Hf > 0 && Wf > 0 && P > 0 && K >= 0,
               "vbg_roi_align_fwd: bad arguments");
-  VBG_REQUIRE(C > 0 && C % 4 == 0 && C <= 1024 && aligned16(feat) && aligned16(out) && aligned16(boxes),
+  VBG_REQUIRE(C > 0 && C % 4 == 0 && C <= 1024 && fmt_ok(feat, feat_plane) && fmt_ok(out, out_plane) && aligned16(boxes),
               "vbg_roi_align_fwd: C %% 4 == 0, C <= 1024 and 16B alignment required (C=%d)", C);
   if (K == 0) return VBG_OK;
-  {
+  if (feat_plane == 0 && out_plane == 0) {
+    // The separable form measured SLOWER than the direct one on B200 (cfg2: 101 us vs 67 us): opt-in for experiments only.
     const int C4 = C / 4;
-    static const bool direct = [] { const char* e = getenv("VBG_ROI_DIRECT"); return e && e[0] == '1'; }();
+    static const bool sep = [] { const char* e = getenv("VBG_ROI_SEPARABLE"); return e && e[0] == '1'; }();
     const int tab_stride = (Hf > Wf ? Hf : Wf) + 1;
     const size_t smem = (size_t)2 * 7 * tab_stride * sizeof(float);
-    if (!direct && P == 7 && C4 <= 256 && 256 % C4 == 0 && smem <= 48 * 1024) {
-      roi_align_sep_kernel<7><<<K, 256, smem, as_stream(stream)>>>(feat, B, Hf, Wf, C, boxes, seg_off, spatial_scale, out,
-                                                                  sample_grid, tab_stride);
+    if (sep && P == 7 && C4 <= 256 && 256 % C4 == 0 && smem <= 48 * 1024) {
+      roi_align_sep_kernel<7><<<K, 256, smem, as_stream(stream)>>>(reinterpret_cast<const float*>(feat), B, Hf, Wf, C, boxes, seg_off,
+                                                                  spatial_scale, reinterpret_cast<float*>(out), sample_grid, tab_stride);
       return check_launch("vbg_roi_align_fwd");
     }
   }
+  cudaStream_t s = as_stream(stream);
+  static const bool direct = [] { const char* e = getenv("VBG_ROI_DIRECT"); return e && e[0] == '1'; }();
+  if (!direct && C % kRoiCh == 0) {
+    // 48 KB window (four resident CTAs per SM): a line-sized ROI at stride 4 needs ~46 KB per 64-channel chunk
+    constexpr int win_floats = 48 * 1024 / 4;
+    roi_align_win_kernel<<<dim3(K, C / kRoiCh), 256, win_floats * sizeof(float), s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off,
+                                                                                       spatial_scale, P, out, out_plane, sample_grid,
+                                                                                       win_floats);
+    return check_launch("vbg_roi_align_fwd");
+  }
   long long warps = (long long)K * P * P;
   int blocks = (int)((warps + 7) / 8);
-  cudaStream_t s = as_stream(stream);
   int vec = (C / 4 + 31) / 32;
-#define LAUNCH(V) roi_align_kernel<V><<<blocks, 256, 0, s>>>(feat, B, Hf, Wf, C, boxes, seg_off, K, spatial_scale, P, out, sample_grid)
+#define LAUNCH(V) roi_align_kernel<V><<<blocks, 256, 0, s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off, K, spatial_scale, P, out, out_plane, sample_grid)
   if (vec <= 1) LAUNCH(1);
   else if (vec == 2) LAUNCH(2);
   else if (vec <= 4) LAUNCH(4);

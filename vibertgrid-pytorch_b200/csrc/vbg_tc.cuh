@@ -40,6 +40,14 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* tm, uint64_t* bar
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
@@ -74,6 +82,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
          ((uint64_t)2 << 61);
+}
+
+// K-major SWIZZLE_64B variant (rows of 64 B = 32 bf16; 8-row atom = 512 B, tile base 512-B aligned): layout = 4, SBO = 512 B
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)32 << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -131,52 +145,71 @@ __device__ __forceinline__ TcTile tc_tile_origin(const TcParams& p, int bn) {
   return t;
 }
 
-// Epilogue of one 128 x BN accumulator tile (called by warps 2-5; q = warp & 3 owns TMEM lanes [32q, 32q+32)).
-// Phase 1: tcgen05.ld 32x32b (lane == accumulator row) -> per-warp smem transpose buffer.
-// Phase 2: lane owns 4 consecutive columns of 4 rows per pass -> scale/shift/residual/activation with 128-bit
-//          loads and fully coalesced 128-bit stores (each 8-lane group writes one 128-byte row segment).
+// Epilogue of one 128 x BN accumulator tile (called by 4 warps; q = warp & 3 owns TMEM lanes [32q, 32q+32)).
+// Per 32-column chunk: tcgen05.ld 32x32b (lane == accumulator row) -> per-warp smem transpose buffer -> each lane owns
+// 4 consecutive columns of 8 rows, so scale / shift are two 128-bit loads per chunk, residual reads and output stores are
+// 128-bit (fp32) or 64-bit x 2 planes (bf16 hi/lo) and every 8-lane group writes one contiguous row segment.
+// The generic variant (any N / alignment) is kept out of line; the fast variant needs N % 4 == 0 and 16-byte aligned
+// pointers, which every shape of the joint forward has.  The tile time of short-K GEMMs is THIS function (the mainloop of
+// a K = 64 tile is 1.5k cycles), so it is written for instruction count: flags hoisted, no per-element branches.
+// Output / residual element offsets of the 8 rows a lane owns after the transpose (row = 32q + 4it + lane/8); bit `it` of the
+// returned mask is set when that row exists.
+__device__ __forceinline__ uint32_t tc_row_offsets(const TcParams& p, const TcTile& t, int q, int sub, long long (&out_off)[8],
+                                                   long long (&res_off)[8]) {
+  const vbg_epilogue_t& ep = p.ep;
+  const bool up2 = ep.residual && ep.res_mode == VBG_RES_UP2, same = ep.residual && ep.res_mode == VBG_RES_SAME;
+  uint32_t ok_mask = 0;
+  const int r0 = q * 32 + sub;
+  // one division per lane, then rows advance by 4 with carries (integer division is ~25 instructions each; this runs
+  // once per tile per lane and used to cost more than the mainloop of a short-K tile)
+  if (p.conv) {
+    int w = r0 % p.tw, tt = r0 / p.tw;
+    int h = tt % p.th, b = tt / p.th;
+    const int Ho2 = p.Ho >> 1, Wo2 = p.Wo >> 1;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int wi = t.w0 + w, hi = t.h0 + h, bi = t.b0 + b;
+      const bool ok = b < p.tb && wi < p.Wo && hi < p.Ho && bi < p.Bn;
+      const long long m_out = ((long long)bi * p.Ho + hi) * p.Wo + wi;
+      out_off[it] = m_out * p.ldc;
+      res_off[it] = up2 ? (((long long)bi * Ho2 + (hi >> 1)) * Wo2 + (wi >> 1)) * (long long)p.N : (same ? m_out * ep.ldr : 0);
+      if (ok) ok_mask |= 1u << it;
+      w += 4;
+      while (w >= p.tw) { w -= p.tw; if (++h == p.th) { h = 0; ++b; } }
+    }
+  } else {
+    const int m0 = t.m0 + r0;
+    int wo = 0, ho = 0, b = 0;
+    if (up2) { wo = m0 % ep.out_w; const int u = m0 / ep.out_w; ho = u % ep.out_h; b = u / ep.out_h; }
+    const int oh2 = ep.out_h >> 1, ow2 = ep.out_w >> 1;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const long long m_out = m0 + 4 * it;
+      out_off[it] = m_out * p.ldc;
+      res_off[it] = up2 ? (((long long)b * oh2 + (ho >> 1)) * ow2 + (wo >> 1)) * (long long)p.N : (same ? m_out * ep.ldr : 0);
+      if (m_out < p.M) ok_mask |= 1u << it;
+      if (up2) {
+        wo += 4;
+        while (wo >= ep.out_w) { wo -= ep.out_w; if (++ho == ep.out_h) { ho = 0; ++b; } }
+      }
+    }
+  }
+  return ok_mask;
+}
+
 template <int BN>
-__device__ __forceinline__ void tc_epilogue(const TcParams& p, const TcTile& t, uint32_t tmem_base, int q, int lane,
-                                            float* __restrict__ stage) {
+__device__ __noinline__ void tc_epilogue_generic(const TcParams& p, const TcTile& t, uint32_t tmem_base, int q, int lane,
+                                                 float* __restrict__ stage) {
   const vbg_epilogue_t& ep = p.ep;
   const int sub = lane >> 3, c4 = (lane & 7) * 4;
   long long out_off[8], res_off[8];
-  uint32_t ok_mask = 0;
-#pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = q * 32 + it * 4 + sub;
-    long long m_out; bool ok;
-    if (p.conv) {
-      const int wi = t.w0 + r % p.tw, tt = r / p.tw;
-      const int hi = t.h0 + tt % p.th, bi = t.b0 + tt / p.th;
-      ok = (r < p.tw * p.th * p.tb) && wi < p.Wo && hi < p.Ho && bi < p.Bn;
-      m_out = ((long long)bi * p.Ho + hi) * p.Wo + wi;
-    } else {
-      m_out = t.m0 + r;
-      ok = m_out < p.M;
-    }
-    long long rr = 0;
-    if (ep.residual && ok) {
-      if (ep.res_mode == VBG_RES_UP2) {
-        const int wo = (int)(m_out % ep.out_w); const long long u = m_out / ep.out_w;
-        const int ho = (int)(u % ep.out_h); const long long b = u / ep.out_h;
-        rr = ((b * (ep.out_h >> 1) + (ho >> 1)) * (ep.out_w >> 1) + (wo >> 1)) * (long long)p.N;
-      } else {
-        rr = m_out * ep.ldr;
-      }
-    }
-    out_off[it] = m_out * p.ldc; res_off[it] = rr;
-    if (ok) ok_mask |= 1u << it;
-  }
-  const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.N & 3) == 0) &&
-                      (!ep.residual || (((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) &&
-                                        (ep.res_mode == VBG_RES_UP2 || (ep.ldr & 3) == 0)));
+  const uint32_t ok_mask = tc_row_offsets(p, t, q, sub, out_off, res_off);
 #pragma unroll 1
   for (int c0 = 0; c0 < BN; c0 += 32) {
     if (t.n0 + c0 >= p.N) break;                       // warp-uniform
     uint32_t v[32];
     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-    __syncwarp();                                      // previous pass finished reading the buffer
+    __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       *reinterpret_cast<float4*>(stage + lane * 36 + j * 4) =
@@ -184,54 +217,120 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const TcTile& t, 
     __syncwarp();
     const int n = t.n0 + c0 + c4;
     if (n >= p.N) continue;
-    float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int e = 0; e < 4; ++e)
-      if (n + e < p.N) {
-        if (ep.scale) sc[e] = __ldg(ep.scale + n + e);
-        if (ep.shift) sh[e] = __ldg(ep.shift + n + e);
-      }
-#pragma unroll
+#pragma unroll 1
     for (int it = 0; it < 8; ++it) {
       if (!((ok_mask >> it) & 1u)) continue;
+#pragma unroll 1
+      for (int e = 0; e < 4; ++e) {
+        if (n + e >= p.N) break;
+        float o = stage[(it * 4 + sub) * 36 + c4 + e];
+        o = o * (ep.scale ? __ldg(ep.scale + n + e) : 1.f) + (ep.shift ? __ldg(ep.shift + n + e) : 0.f);
+        if (ep.residual) {
+          if (ep.res_plane > 0) {
+            const __nv_bfloat16* hp = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + res_off[it] + n + e;
+            o += __bfloat162float(hp[0]) + __bfloat162float(hp[ep.res_plane]);
+          } else {
+            o += __ldg(ep.residual + res_off[it] + n + e);
+          }
+        }
+        o = apply_act(o, ep.act);
+        if (ep.out_mode == VBG_OUT_SPLIT_BF16) {
+          __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(p.C) + out_off[it] + n + e;
+          const __nv_bfloat16 h = __float2bfloat16_rn(o);
+          hp[0] = h;
+          hp[ep.out_plane] = __float2bfloat16_rn(o - __bfloat162float(h));
+        } else {
+          p.C[out_off[it] + n + e] = o;
+        }
+      }
+    }
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, const TcTile& t, uint32_t tmem_base, int q, int lane,
+                                            float* __restrict__ stage) {
+  const vbg_epilogue_t& ep = p.ep;
+  const int sub = lane >> 3, c4 = (lane & 7) * 4;
+  long long out_off[8], res_off[8];
+  const uint32_t ok_mask = tc_row_offsets(p, t, q, sub, out_off, res_off);
+  const bool split_out = ep.out_mode == VBG_OUT_SPLIT_BF16;
+  const int res_kind = !ep.residual ? 0 : (ep.res_plane > 0 ? 2 : 1);
+  const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.N & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(ep.scale) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ep.shift) & 15) == 0) &&
+                      (!split_out || (ep.out_plane & 3) == 0) &&
+                      (res_kind == 0 || (((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) && (ep.res_plane & 3) == 0 &&
+                                         (ep.res_mode == VBG_RES_UP2 || (ep.ldr & 3) == 0)));
+  if (!vec_ok) {
+    tc_epilogue_generic<BN>(p, t, tmem_base, q, lane, stage);
+    return;
+  }
+  const float* __restrict__ scale = ep.scale;
+  const float* __restrict__ shift = ep.shift;
+  const int act = ep.act;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 32) {
+    if (t.n0 + c0 >= p.N) break;                       // warp-uniform
+    uint32_t v[32];
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+    __syncwarp();                                      // previous chunk finished reading the buffer
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(stage + lane * 36 + j * 4) =
+          make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    __syncwarp();
+    const int n = t.n0 + c0 + c4;
+    if (n >= p.N) continue;                            // N % 4 == 0: a 4-column group is entirely in or out
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + n));
+    if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + n));
+    float4 o[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
       const float4 a = *reinterpret_cast<const float4*>(stage + (it * 4 + sub) * 36 + c4);
-      float o[4] = {a.x * sc[0] + sh[0], a.y * sc[1] + sh[1], a.z * sc[2] + sh[2], a.w * sc[3] + sh[3]};
-      if (ep.residual) {
-        const float* rp = ep.residual + res_off[it] + n;
-        if (vec_ok && n + 3 < p.N) {
-          const float4 rv = __ldg(reinterpret_cast<const float4*>(rp));
-          o[0] += rv.x; o[1] += rv.y; o[2] += rv.z; o[3] += rv.w;
-        } else {
+      o[it] = make_float4(fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y), fmaf(a.z, sc.z, sh.z), fmaf(a.w, sc.w, sh.w));
+    }
+    if (res_kind == 1) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) if (n + e < p.N) o[e] += __ldg(rp + e);
+      for (int it = 0; it < 8; ++it)
+        if ((ok_mask >> it) & 1u) {
+          const float4 rv = __ldg(reinterpret_cast<const float4*>(ep.residual + res_off[it] + n));
+          o[it].x += rv.x; o[it].y += rv.y; o[it].z += rv.z; o[it].w += rv.w;
         }
-      }
+    } else if (res_kind == 2) {
+      const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + n;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = apply_act(o[e], ep.act);
-      if (ep.out_mode == VBG_OUT_SPLIT_BF16) {          // bf16 hi / lo planes (operands of the split attention kernel)
-        __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(p.C) + out_off[it] + n;
-        __nv_bfloat16* lp = hp + ep.out_plane;
-        __nv_bfloat16 h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { h[e] = __float2bfloat16_rn(o[e]); l[e] = __float2bfloat16_rn(o[e] - __bfloat162float(h[e])); }
-        if (vec_ok && n + 3 < p.N && (ep.out_plane & 3) == 0) {
-          *reinterpret_cast<uint2*>(hp) = make_uint2((uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
-                                                     (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
-          *reinterpret_cast<uint2*>(lp) = make_uint2((uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
-                                                     (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) if (n + e < p.N) { hp[e] = h[e]; lp[e] = l[e]; }
+      for (int it = 0; it < 8; ++it)
+        if ((ok_mask >> it) & 1u) {
+          const float4 rv = merge4(__ldg(reinterpret_cast<const uint2*>(rh + res_off[it])),
+                                   __ldg(reinterpret_cast<const uint2*>(rh + res_off[it] + ep.res_plane)));
+          o[it].x += rv.x; o[it].y += rv.y; o[it].z += rv.z; o[it].w += rv.w;
         }
-        continue;
-      }
-      float* cp = p.C + out_off[it] + n;
-      if (vec_ok && n + 3 < p.N) {
-        *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
-      } else {
+    }
+    if (act == VBG_ACT_RELU) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) if (n + e < p.N) cp[e] = o[e];
-      }
+      for (int it = 0; it < 8; ++it)
+        o[it] = make_float4(fmaxf(o[it].x, 0.f), fmaxf(o[it].y, 0.f), fmaxf(o[it].z, 0.f), fmaxf(o[it].w, 0.f));
+    } else if (act == VBG_ACT_GELU) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        o[it] = make_float4(gelu_erf(o[it].x), gelu_erf(o[it].y), gelu_erf(o[it].z), gelu_erf(o[it].w));
+    }
+    if (split_out) {
+      __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(p.C) + n;
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if ((ok_mask >> it) & 1u) {
+          uint2 hi, lo;
+          split4(o[it], hi, lo);
+          *reinterpret_cast<uint2*>(hp + out_off[it]) = hi;
+          *reinterpret_cast<uint2*>(hp + out_off[it] + ep.out_plane) = lo;
+        }
+    } else {
+      float* cp = p.C + n;
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if ((ok_mask >> it) & 1u) *reinterpret_cast<float4*>(cp + out_off[it]) = o[it];
     }
   }
 }
@@ -241,6 +340,6 @@ bool tc_available();
 bool tc_disabled_by_env();
 // rank-N tiled map with SWIZZLE_128B; dtype_bf16 selects 2-byte elements
 bool tc_encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-               const cuuint32_t* box, const cuuint32_t* elem_strides, bool dtype_bf16);
+               const cuuint32_t* box, const cuuint32_t* elem_strides, bool dtype_bf16, bool swizzle64 = false);
 
 }  // namespace vbg

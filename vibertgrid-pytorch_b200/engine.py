@@ -27,7 +27,7 @@ import torch.nn as nn
 from . import ops
 from . import params as P
 from .ops import (ACT_GELU, ACT_NONE, ACT_RELU, PREC_BF16X3, PREC_FP32, PREC_TF32, RES_NONE, RES_SAME, RES_UP2,
-                  make_epilogue)
+                  Split, make_epilogue)
 from .plan import plan_batch
 
 
@@ -48,6 +48,19 @@ def _cat_into(dst, parts):
         dst.copy_(torch.cat(parts, 0), non_blocking=True)
 
 
+class Intermediates(dict):
+    """Engine outputs keyed by name.  Activations that live as bf16 hi/lo planes between the pre-split tensor-core
+    kernels (P_fuse, ROI features, BERTgrid ...) are merged to fp32 on access -- inspection and tests only, never on
+    the hot path.  ``raw(key)`` returns the stored object."""
+
+    def __getitem__(self, k):
+        v = dict.__getitem__(self, k)
+        return v.float() if isinstance(v, Split) else v
+
+    def raw(self, k):
+        return dict.__getitem__(self, k)
+
+
 class ForwardEngine:
     def __init__(self, net):
         self.net = net
@@ -61,6 +74,8 @@ class ForwardEngine:
         self.launches = 0
         self.use_graphs = os.environ.get("VBG_CUDA_GRAPHS", "1") != "0"
         self.fuse_aux_loss = os.environ.get("VBG_FUSED_AUX_LOSS", "1") != "0"
+        # bf16x3 only: keep activations as bf16 hi/lo planes between the tensor-core kernels (no in-kernel conversion)
+        self.presplit = os.environ.get("VBG_PRESPLIT", "1") != "0"
         self.max_graphs = 8
         self._graphs: Dict[tuple, dict] = {}
         self.graph_replays = 0
@@ -151,19 +166,31 @@ class ForwardEngine:
             self.precision = PREC_BF16X3 if ops.tc_available() else PREC_FP32
         return self.precision
 
-    def _conv(self, x, conv: nn.Conv2d, bn=None, act=ACT_NONE, residual=None, res_mode=RES_NONE):
+    def _ps(self):
+        return self.presplit and self._prec() == PREC_BF16X3
+
+    @staticmethod
+    def _tc_shape(N, K):
+        return N >= 64 and K % 64 == 0
+
+    def _conv(self, x, conv: nn.Conv2d, bn=None, act=ACT_NONE, residual=None, res_mode=RES_NONE, out_f32=False):
+        """``x`` / ``residual``: fp32 NHWC tensors, or Splits in pre-split mode (then the result is a Split unless out_f32)."""
         pr = self._prep
         w, ws = pr.convw[id(conv)], pr.split.get(id(conv))
         scale, shift = pr.bn[id(bn)] if bn is not None else (None, None if conv.bias is None else conv.bias.detach())
         B, H, W, Cin = x.shape
         k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         Cout = conv.out_channels
+        if isinstance(x, Split) and not (self._tc_shape(Cout, Cin) and ws is not None):
+            x = x.float()                       # shape the tensor-core kernels do not take: CUDA-core path, fp32 in / out
+            residual = ops.as_f32(residual)
+        so = isinstance(x, Split) and not out_f32
         if k == 1 and s == 1:
             ep = make_epilogue(scale, shift, residual, res_mode, ldr=Cout, out_h=H, out_w=W, act=act)
-            y = ops.gemm(x.view(B * H * W, Cin), w.view(Cout, Cin), ep=ep, precision=self._prec(), W_split=ws)
+            y = ops.gemm(x.view(B * H * W, Cin), w.view(Cout, Cin), ep=ep, precision=self._prec(), W_split=ws, split_out=so)
             return y.view(B, H, W, Cout)
         ep = make_epilogue(scale, shift, residual, res_mode, ldr=Cout, act=act)
-        return ops.conv2d(x, w, s, p, ep=ep, precision=self._prec(), W_split=ws)
+        return ops.conv2d(x, w, s, p, ep=ep, precision=self._prec(), W_split=ws, split_out=so)
 
     def _stem(self, x4, conv: nn.Conv2d, bn):
         pr = self._prep
@@ -171,17 +198,28 @@ class ForwardEngine:
         ep = make_epilogue(scale, shift, act=ACT_RELU)
         return ops.stem_conv(x4, pr.convw[id(conv)], ep=ep, precision=self._prec(), W_split=pr.split.get(id(conv)))
 
-    def _lin(self, x, lin: nn.Linear, act=ACT_NONE, residual=None, A2=None, W=None, W_split=None):
+    def _lin(self, x, lin: nn.Linear, act=ACT_NONE, residual=None, A2=None, W=None, W_split=None, out_f32=False):
         ep = make_epilogue(None, lin.bias.detach(), residual, RES_SAME if residual is not None else RES_NONE,
                            ldr=lin.out_features, act=act)
         if W is None:
             W, W_split = lin.weight.detach(), self._prep.split.get(id(lin))
-        return ops.gemm(x, W, A2=A2, ep=ep, precision=self._prec(), W_split=W_split)
+        if isinstance(x, Split) and not (self._tc_shape(W.shape[0], W.shape[1]) and W_split is not None):
+            x, A2 = x.float(), ops.as_f32(A2)
+            ep = make_epilogue(None, lin.bias.detach(), ops.as_f32(residual), RES_SAME if residual is not None else RES_NONE,
+                               ldr=lin.out_features, act=act)
+        so = isinstance(x, Split) and not out_f32
+        return ops.gemm(x, W, A2=A2, ep=ep, precision=self._prec(), W_split=W_split, split_out=so)
 
-    def _mlp_or_lin(self, x, m):
+    def _pick(self, x, xs, lin: nn.Linear):
+        """The storage format a linear's kernel wants: the Split for tensor-core shapes, fp32 for the CUDA-core ones."""
+        return xs if (xs is not None and self._tc_shape(lin.out_features, lin.in_features)) else x
+
+    def _mlp_or_lin(self, x, m, xs=None):
+        """Head MLPs; ``xs`` is the Split twin of the fp32 ``x`` (pre-split mode).  Results are fp32."""
         if hasattr(m, "linear_1"):
-            return self._lin(self._lin(x, m.linear_1, ACT_RELU), m.linear_2)
-        return self._lin(x, m.linear)
+            h = self._lin(self._pick(x, xs, m.linear_1), m.linear_1, ACT_RELU, out_f32=True)
+            return self._lin(h, m.linear_2, out_f32=True)
+        return self._lin(self._pick(x, xs, m.linear), m.linear, out_f32=True)
 
     def _block(self, x, conv1, bn1, conv2, bn2, shortcut):
         y = self._conv(x, conv1, bn1, ACT_RELU)
@@ -206,8 +244,9 @@ class ForwardEngine:
     def _early_fusion(self, x2, grid, conv: nn.Conv2d):
         B, H, W, C1 = x2.shape
         ep = make_epilogue(None, None if conv.bias is None else conv.bias.detach())
-        y = ops.gemm(x2.view(-1, C1), self._prep.convw[id(conv)].view(conv.out_channels, -1), A2=grid.view(-1, grid.shape[-1]), ep=ep,
-                     precision=self._prec(), W_split=self._prep.split.get(id(conv)))
+        y = ops.gemm(x2.view(B * H * W, C1), self._prep.convw[id(conv)].view(conv.out_channels, -1),
+                     A2=grid.view(B * H * W, grid.shape[-1]), ep=ep,
+                     precision=self._prec(), W_split=self._prep.split.get(id(conv)), split_out=isinstance(x2, Split))
         return y.view(B, H, W, conv.out_channels)
 
     # ------------------------------------------------------------------ stages
@@ -218,35 +257,43 @@ class ForwardEngine:
         heads = bm.cfg["num_attention_heads"]
         seq_tab, cu = dev_tab["seq_tab"], dev_tab["cu"]
         ids, pos = ops.bert_assemble(corpus, seq_tab, cu, plan.nseq, plan.R)
+        prec = self._prec()
+        ps = self._ps()
         x = ops.embed_ln(ids, pos, e.word_embeddings.weight.detach(), e.position_embeddings.weight.detach(),
                          e.token_type_embeddings.weight.detach()[0], e.LayerNorm.weight.detach(),
-                         e.LayerNorm.bias.detach(), e.LayerNorm.eps)
-        prec = self._prec()
+                         e.LayerNorm.bias.detach(), e.LayerNorm.eps, split=ps)
         hid = bm.cfg["hidden_size"]
         split_attn = (prec == PREC_BF16X3 and hid // heads == 64 and hid % 64 == 0 and plan.max_len <= 512
                       and os.environ.get("VBG_ATTN_SPLIT", "1") != "0")
-        for lyr, pk in zip(bm.encoder.layer, pr.bert_layers):
+        n_layers = len(bm.encoder.layer)
+        for li, (lyr, pk) in enumerate(zip(bm.encoder.layer, pr.bert_layers)):
+            # pre-split mode: x, ctx and the FFN intermediate are bf16 hi/lo planes (GEMM A operands and residuals);
+            # only the two LayerNorm inputs per layer and the final hidden state are fp32.
             if split_attn:      # QKV projection writes bf16 hi/lo planes; TMA-fed tcgen05 attention consumes them directly
                 qkv = ops.gemm(x, pk["wqkv"], ep=make_epilogue(None, pk["bqkv"]), precision=prec, W_split=pk["wqkv_split"],
                                split_out=True)
-                ctx = ops.attention_split(qkv, cu, plan.nseq, plan.max_len, heads)
+                ctx = ops.attention_split(qkv, cu, plan.nseq, plan.max_len, heads, split_out=ps)
             else:
                 qkv = ops.gemm(x, pk["wqkv"], ep=make_epilogue(None, pk["bqkv"]), precision=prec, W_split=pk["wqkv_split"])
                 ctx = ops.attention(qkv, cu, plan.nseq, plan.max_len, heads, prec)
+                if ps:
+                    ctx = ops.to_split(ctx)
             ao = lyr.attention.output
-            a = self._lin(ctx, ao.dense, residual=x)
-            x = ops.layernorm(a, ao.LayerNorm.weight.detach(), ao.LayerNorm.bias.detach(), ao.LayerNorm.eps, out=a)
+            a = self._lin(ctx, ao.dense, residual=x, out_f32=True)
+            x = ops.layernorm(a, ao.LayerNorm.weight.detach(), ao.LayerNorm.bias.detach(), ao.LayerNorm.eps,
+                              out=None if ps else a, split=ps)
             h = self._lin(x, lyr.intermediate.dense, ACT_GELU)
-            o = self._lin(h, lyr.output.dense, residual=x)
+            o = self._lin(h, lyr.output.dense, residual=x, out_f32=True)
+            last = li == n_layers - 1
             x = ops.layernorm(o, lyr.output.LayerNorm.weight.detach(), lyr.output.LayerNorm.bias.detach(),
-                              lyr.output.LayerNorm.eps, out=o)
+                              lyr.output.LayerNorm.eps, out=o if (last or not ps) else None, split=ps and not last)
         return x
 
     def _backbone(self, img, grid):
         bb = self.net.backbone
         if bb.pretrained_layout:
             r = bb.resnet
-            x1 = ops.maxpool3x3s2(self._stem(img, r.conv1, r.bn1))
+            x1 = ops.maxpool3x3s2(self._stem(img, r.conv1, r.bn1), split_out=self._ps())
             for blk in r.layer1:
                 x1 = self._tv_block(x1, blk)
             x2 = self._tv_block(x1, r.layer2[0])
@@ -260,7 +307,7 @@ class ForwardEngine:
             for blk in r.layer4:
                 x4 = self._tv_block(x4, blk)
         else:
-            x1 = ops.maxpool3x3s2(self._stem(img, bb.conv_1[0], bb.conv_1[1]))
+            x1 = ops.maxpool3x3s2(self._stem(img, bb.conv_1[0], bb.conv_1[1]), split_out=self._ps())
             for blk in bb.conv_2_x:
                 x1 = self._our_block(x1, blk)
             x2 = self._our_block(x1, bb.conv_3_x.block_1)
@@ -287,14 +334,14 @@ class ForwardEngine:
         for i, lvl in enumerate((x4, x5, x6, x7)):
             B, H, W, Cc = lvl.shape
             ep = make_epilogue(residual=t, res_mode=RES_UP2 if t is not None else RES_NONE, out_h=H, out_w=W)
-            t = ops.gemm(lvl.view(-1, Cc), wf, ep=ep, precision=prec, N=wf.shape[0], K=Pc, ldw=wf.shape[1],
-                         w_offset=i * Pc, W_split=wfs).view(B, H, W, wf.shape[0])
+            t = ops.gemm(lvl.view(B * H * W, Cc), wf, ep=ep, precision=prec, N=wf.shape[0], K=Pc, ldw=wf.shape[1],
+                         w_offset=i * Pc, W_split=wfs, split_out=isinstance(lvl, Split)).view(B, H, W, wf.shape[0])
         return t
 
     def _seg_head(self, p_fuse):
         enc = self.net.semantic_segmentation_head.encoder
         x = self._conv(p_fuse, enc.conv_1, enc.bn_1, ACT_RELU)
-        x = self._conv(x, enc.conv_2, enc.bn_2, ACT_RELU)
+        x = self._conv(x, enc.conv_2, enc.bn_2, ACT_RELU, out_f32=True)     # feeds the N = 3 + C CUDA-core GEMM
         B, H, W, Cc = x.shape
         pr = self._prep
         lg = ops.gemm(x.view(-1, Cc), pr.misc["seg_w"], ep=make_epilogue(None, pr.misc["seg_b"]), precision=self._prec())
@@ -377,7 +424,7 @@ class ForwardEngine:
         dt["ratios"] = dt["ratios"].view(torch.float32)
         seg_off = dt["seg_off"]
         status = torch.zeros(1, dtype=torch.int32, device=dev)
-        out = {"plan": plan, "status": status}
+        out = Intermediates({"plan": plan, "status": status})
 
         # a1 transform
         batch = torch.zeros((B, plan.H + 6, plan.W + 6, 4), dtype=torch.float32, device=dev)   # zero-bordered NHWC4 stem input
@@ -397,7 +444,9 @@ class ForwardEngine:
         # a4 BERTgrid
         gs = net.early_fusion_downsampling_ratio
         idx = ops.box_index_map(boxes, seg_off, B, gs, int(plan.H / gs), int(plan.W / gs))
-        grid = ops.grid_scatter(seg_emb, idx, seg_off)
+        ps = self._ps()
+        seg_emb_s = ops.to_split(seg_emb) if ps else None      # [K, 768]: scatter source and late-fusion operand
+        grid = ops.grid_scatter(seg_emb_s if ps else seg_emb, idx, seg_off)
         out["index_map"], out["bertgrid"] = idx, grid
 
         # a5 backbone
@@ -417,34 +466,36 @@ class ForwardEngine:
             out["gt_label"] = cls_cat
 
         # a7 ROI align, a8 late fusion
-        roi = ops.roi_align(p_fuse, boxes, seg_off, 1.0 / float(net.p_fuse_downsampling_ratio), net.roi_shape)
+        roi = ops.roi_align(p_fuse, boxes, seg_off, 1.0 / float(net.p_fuse_downsampling_ratio), net.roi_shape, split_out=ps)
         out["roi"] = roi
         rn = net.late_fusion_net.ROI_embedding_net
         r = self._conv(roi, rn.conv_1, rn.bn_1, ACT_RELU)
         r = self._conv(r, rn.conv_2, rn.bn_2, ACT_RELU)
         roi_emb = self._lin(r.view(plan.K, -1), rn.linear, W=pr.misc["roi_fc_w"], W_split=pr.split.get("roi_fc_w"))
-        late = self._lin(roi_emb, net.late_fusion_net.fuse_embedding_net.linear, A2=seg_emb)
+        late = self._lin(roi_emb, net.late_fusion_net.fuse_embedding_net.linear, A2=seg_emb_s if ps else seg_emb,
+                         out_f32=True)
+        late_s = ops.to_split(late) if ps else None      # [K, 1024]: the heads' tensor-core operand
         out["late"] = late
 
         # a9 / a10 field-type head
         head = net.field_type_classification_head
         if net.classifier_mode == "simp":
-            logits = self._mlp_or_lin(late, head.category_classification_net)
+            logits = self._mlp_or_lin(late, head.category_classification_net, late_s)
             out["logits"] = logits
             out["pred_label"] = ops.softmax_rows(logits)
             if want_seg and hasattr(head, "pos_neg_classification_net"):
-                out["pos_neg_logits"] = self._mlp_or_lin(late, head.pos_neg_classification_net)
+                out["pos_neg_logits"] = self._mlp_or_lin(late, head.pos_neg_classification_net, late_s)
         elif net.classifier_mode == "crf":
-            logits = self._mlp_or_lin(late, head.category_classification_net)
+            logits = self._mlp_or_lin(late, head.category_classification_net, late_s)
             out["logits"] = logits
             tags, scores = ops.crf_viterbi(logits, head.crf_layer.transitions.detach().contiguous(), seg_off, B)
             out["pred_label"], out["crf_scores"] = tags[:, None], scores
         else:
-            pn = self._mlp_or_lin(late, head.pos_neg_classification_net.layer)
+            pn = self._mlp_or_lin(late, head.pos_neg_classification_net.layer, late_s)
             if "full_w" in pr.misc:
                 cl = ops.gemm(late, pr.misc["full_w"], ep=make_epilogue(None, pr.misc["full_b"]), precision=self._prec())
             else:
-                cl = torch.cat([self._mlp_or_lin(late, getattr(head, f"category_classification_net_{i}").layer)
+                cl = torch.cat([self._mlp_or_lin(late, getattr(head, f"category_classification_net_{i}").layer, late_s)
                                 for i in range(net.num_tokens - 1)], 1).contiguous()
             out["pos_neg_logits"], out["logits"] = pn, cl
             out["pred_label"] = ops.full_head_scores(pn.reshape(-1).contiguous(), cl)

@@ -34,6 +34,68 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class Split:
+    """An activation stored as two bf16 planes (include/vbg.h "storage formats"): ``t`` is a contiguous bf16
+    ``[2, *shape]`` tensor, ``t[0] = bf16_rn(x)``, ``t[1] = bf16_rn(x - t[0])``.  The operand format the pre-split
+    bf16x3 tensor-core kernels consume without conversion; ``shape`` / ``view`` / ``float`` mirror a tensor."""
+    __slots__ = ("t",)
+
+    def __init__(self, t: torch.Tensor):
+        if t.dtype != torch.bfloat16 or t.dim() < 2 or t.shape[0] != 2 or not t.is_contiguous():
+            raise TypeError("Split expects a contiguous bf16 [2, ...] tensor")
+        if t[0].numel() % 8:
+            raise ValueError("Split: elements per plane must be a multiple of 8 (TMA stride alignment)")
+        self.t = t
+
+    @staticmethod
+    def empty(shape, device):
+        return Split(torch.empty((2,) + tuple(shape), dtype=torch.bfloat16, device=device))
+
+    @property
+    def shape(self):
+        return tuple(self.t.shape[1:])
+
+    @property
+    def device(self):
+        return self.t.device
+
+    @property
+    def plane(self):
+        return self.t[0].numel()
+
+    def dim(self):
+        return self.t.dim() - 1
+
+    def view(self, *shape):
+        return Split(self.t.view(2, *shape))
+
+    def float(self):
+        """fp32 copy (hi + lo) -- inspection and tests only."""
+        out = torch.empty(self.shape, dtype=torch.float32, device=self.t.device)
+        L.check(L.load().vbg_merge_bf16(_p(self.t[0]), _p(self.t[1]), self.plane, _f32(out), _stream()), "vbg_merge_bf16")
+        return out
+
+
+def to_split(x: torch.Tensor) -> Split:
+    """fp32 tensor -> Split (one extra pass; producers normally write the planes themselves)."""
+    return Split(split_bf16(x))
+
+
+def as_f32(x):
+    return x.float() if isinstance(x, Split) else x
+
+
+def _act(x, name="tensor"):
+    """(device pointer, plane) of an activation in either storage format; plane == 0 means fp32."""
+    if isinstance(x, Split):
+        return _p(x.t), x.plane
+    return _f32(x, name), 0
+
+
+def _new_act(shape, device, split):
+    return Split.empty(shape, device) if split else torch.empty(tuple(shape), dtype=torch.float32, device=device)
+
+
 def _f32(t, name="tensor"):
     return _p(t, torch.float32, name)
 
@@ -47,7 +109,10 @@ def tc_available() -> bool:
 
 
 def make_epilogue(scale=None, shift=None, residual=None, res_mode=RES_NONE, ldr=0, out_h=0, out_w=0, act=ACT_NONE):
-    ep = Epilogue(_f32(scale, "scale"), _f32(shift, "shift"), _f32(residual, "residual"), res_mode, ldr, out_h, out_w, act)
+    """``residual`` may be an fp32 tensor or a Split (read from its bf16 planes by the tensor-core epilogues)."""
+    rp, rplane = _act(residual, "residual") if residual is not None else (None, 0)
+    ep = Epilogue(_f32(scale, "scale"), _f32(shift, "shift"), rp, res_mode, ldr, out_h, out_w, act)
+    ep.res_plane = rplane
     ep._keep = (scale, shift, residual)
     return ep
 
@@ -83,19 +148,23 @@ def bert_assemble(corpus, seq_tab, cu, nseq, R):
     return ids, pos
 
 
-def embed_ln(ids, pos, word, position, type_emb, gamma, beta, eps):
+def embed_ln(ids, pos, word, position, type_emb, gamma, beta, eps, split=False):
     R, hidden = ids.shape[0], word.shape[1]
-    out = torch.empty((R, hidden), dtype=torch.float32, device=word.device)
-    L.check(L.load().vbg_embed_ln(_i32(ids), _i32(pos), _f32(word), _f32(position), _f32(type_emb), _f32(gamma),
-                                  _f32(beta), eps, R, hidden, word.shape[0], position.shape[0], _f32(out), _stream()),
+    out = _new_act((R, hidden), word.device, split)
+    op, oplane = _act(out)
+    L.check(L.load().vbg_embed_ln_x(_i32(ids), _i32(pos), _f32(word), _f32(position), _f32(type_emb), _f32(gamma),
+                                    _f32(beta), eps, R, hidden, word.shape[0], position.shape[0], op, oplane, _stream()),
             "vbg_embed_ln")
     return out
 
 
-def layernorm(x, gamma, beta, eps, out=None):
+def layernorm(x, gamma, beta, eps, out=None, split=False):
+    """``split``: write bf16 hi/lo planes (a Split) instead of fp32; ``out`` may be the fp32 input (in place)."""
     R, hidden = x.shape
-    out = torch.empty_like(x) if out is None else out
-    L.check(L.load().vbg_layernorm(_f32(x), _f32(gamma), _f32(beta), eps, R, hidden, _f32(out), _stream()), "vbg_layernorm")
+    if out is None:
+        out = _new_act((R, hidden), x.device, split)
+    op, oplane = _act(out)
+    L.check(L.load().vbg_layernorm_x(_f32(x), _f32(gamma), _f32(beta), eps, R, hidden, op, oplane, _stream()), "vbg_layernorm")
     return out
 
 
@@ -108,15 +177,18 @@ def attention(qkv, cu, nseq, max_len, heads, precision=PREC_FP32):
     return out
 
 
-def attention_split(qkv_split, cu, nseq, max_len, heads):
-    """Attention over the bf16 [2, R, 3*hidden] hi/lo planes of ``gemm(..., split_out=True)`` -> fp32 [R, hidden]."""
-    if qkv_split.dtype != torch.bfloat16 or qkv_split.dim() != 3 or qkv_split.shape[0] != 2 or not qkv_split.is_contiguous():
-        raise TypeError("attention_split expects the contiguous bf16 [2, R, 3*hidden] tensor of gemm(..., split_out=True)")
-    _, R, three_h = qkv_split.shape
+def attention_split(qkv_split, cu, nseq, max_len, heads, split_out=False):
+    """Attention over the Split [R, 3*hidden] of ``gemm(..., split_out=True)`` -> [R, hidden] (fp32, or a Split)."""
+    if not isinstance(qkv_split, Split):
+        qkv_split = Split(qkv_split)
+    if qkv_split.dim() != 2:
+        raise TypeError("attention_split expects the Split [R, 3*hidden] of gemm(..., split_out=True)")
+    R, three_h = qkv_split.shape
     hidden = three_h // 3
-    out = torch.empty((R, hidden), dtype=torch.float32, device=qkv_split.device)
-    L.check(L.load().vbg_attention_split_fwd(_p(qkv_split), R * three_h, _i32(cu), nseq, R, max_len, heads, hidden // heads,
-                                             _f32(out), _stream()), "vbg_attention_split_fwd")
+    out = _new_act((R, hidden), qkv_split.device, split_out)
+    op, oplane = _act(out)
+    L.check(L.load().vbg_attention_split_fwd(_p(qkv_split.t), R * three_h, _i32(cu), nseq, R, max_len, heads, hidden // heads,
+                                             op, oplane, _stream()), "vbg_attention_split_fwd")
     return out
 
 
@@ -145,11 +217,13 @@ def box_index_map(boxes, seg_off, B, stride, Hg, Wg):
     return idx
 
 
-def grid_scatter(seg_emb, idx, seg_off):
+def grid_scatter(seg_emb, idx, seg_off, split=False):
     B, Hg, Wg = idx.shape
     Cc = seg_emb.shape[1]
-    grid = torch.empty((B, Hg, Wg, Cc), dtype=torch.float32, device=seg_emb.device)
-    L.check(L.load().vbg_grid_scatter(_f32(seg_emb), _i32(idx), _i32(seg_off), B, Hg * Wg, Cc, _f32(grid), _stream()),
+    split = split or isinstance(seg_emb, Split)         # a Split source is copied plane-wise into a Split grid
+    grid = _new_act((B, Hg, Wg, Cc), seg_emb.device, split)
+    (sp, splane), (gp, gplane) = _act(seg_emb), _act(grid)
+    L.check(L.load().vbg_grid_scatter_x(sp, splane, _i32(idx), _i32(seg_off), B, Hg * Wg, Cc, gp, gplane, _stream()),
             "vbg_grid_scatter")
     return grid
 
@@ -202,30 +276,56 @@ def gemm(A, W, *, A2=None, ep: Optional[Epilogue] = None, precision=PREC_FP32, N
     if split_out:
         if ep is None:
             ep = make_epilogue()
-        out = torch.empty((2, M, Nn), dtype=torch.bfloat16, device=A.device)
-        ep.out_mode, ep.out_plane = L.OUT_SPLIT_BF16, M * Nn
-        optr, ldc = _p(out), Nn
+        out = Split.empty((M, Nn), A.device)
+        ep.out_mode, ep.out_plane = L.OUT_SPLIT_BF16, out.plane
+        optr, ldc = _p(out.t), Nn
     else:
         if out is None:
             out = torch.empty((M, Nn), dtype=torch.float32, device=A.device)
         optr, ldc = _f32(out, "out"), out.stride(0)
-    wp = _f32(W, "W") + 4 * w_offset
     sp, plane = _split_args(W_split, w_offset)
+    if isinstance(A, Split):      # pre-split activations: TMA-fed bf16x3 kernel, no in-kernel conversion
+        if sp is None:
+            raise TypeError("gemm over a Split activation needs W_split (the bf16 planes of the weight)")
+        if A2 is not None and not isinstance(A2, Split):
+            raise TypeError("gemm: A and A2 must use the same storage format")
+        ap, aplane = _act(A)
+        a2p, a2plane = _act(A2) if A2 is not None else (None, 0)
+        L.check(L.load().vbg_gemm_ps(ap, aplane, K1, a2p, a2plane, K2, K1, sp, plane, ldw_, optr, ldc, M, Nn, Kt,
+                                     C.byref(ep) if ep is not None else None, _stream()), "vbg_gemm_ps")
+        return out
+    wp = _f32(W, "W") + 4 * w_offset
     L.check(L.load().vbg_gemm(_f32(A, "A"), A.stride(0), _f32(A2, "A2"), 0 if A2 is None else A2.stride(0), K1, wp, ldw_,
                               sp, plane, optr, ldc, M, Nn, Kt,
                               C.byref(ep) if ep is not None else None, precision, _stream()), "vbg_gemm")
     return out
 
 
-def conv2d(x, w_ohwi, stride, pad, *, ep: Optional[Epilogue] = None, precision=PREC_FP32, W_split=None):
+def conv2d(x, w_ohwi, stride, pad, *, ep: Optional[Epilogue] = None, precision=PREC_FP32, W_split=None, split_out=False):
+    """``x`` fp32 NHWC tensor or Split; ``split_out`` returns a Split (tensor-core paths only)."""
     B, H, W, Cin = x.shape
     Cout, kh, kw, Cin2 = w_ohwi.shape
     if Cin2 != Cin:
         raise ValueError(f"conv2d: weight expects Cin={Cin2}, input has {Cin}")
     Ho, Wo = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
-    y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
     sp, plane = _split_args(W_split, 0)
-    L.check(L.load().vbg_conv2d(_f32(x, "x"), B, H, W, Cin, _f32(w_ohwi, "w"), sp, plane, Cout, kh, kw, stride, pad, _f32(y),
+    if split_out:
+        if ep is None:
+            ep = make_epilogue()
+        y = Split.empty((B, Ho, Wo, Cout), x.device)
+        ep.out_mode, ep.out_plane = L.OUT_SPLIT_BF16, y.plane
+        yp = _p(y.t)
+    else:
+        y = torch.empty((B, Ho, Wo, Cout), dtype=torch.float32, device=x.device)
+        yp = _f32(y)
+    if isinstance(x, Split):
+        if sp is None:
+            raise TypeError("conv2d over a Split activation needs W_split")
+        xp, xplane = _act(x)
+        L.check(L.load().vbg_conv2d_ps(xp, xplane, B, H, W, Cin, sp, plane, Cout, kh, kw, stride, pad, yp,
+                                       C.byref(ep) if ep is not None else None, _stream()), "vbg_conv2d_ps")
+        return y
+    L.check(L.load().vbg_conv2d(_f32(x, "x"), B, H, W, Cin, _f32(w_ohwi, "w"), sp, plane, Cout, kh, kw, stride, pad, yp,
                                 C.byref(ep) if ep is not None else None, precision, _stream()), "vbg_conv2d")
     return y
 
@@ -253,17 +353,19 @@ def stem_conv(x4, w774, *, ep: Optional[Epilogue] = None, precision=PREC_FP32, W
     return y
 
 
-def maxpool3x3s2(x):
+def maxpool3x3s2(x, split_out=False):
     B, H, W, Cc = x.shape
-    y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), dtype=torch.float32, device=x.device)
-    L.check(L.load().vbg_maxpool3x3s2(_f32(x), B, H, W, Cc, _f32(y), _stream()), "vbg_maxpool3x3s2")
+    y = _new_act((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, Cc), x.device, split_out)
+    (xp, xpl), (yp, ypl) = _act(x), _act(y)
+    L.check(L.load().vbg_maxpool3x3s2_x(xp, xpl, B, H, W, Cc, yp, ypl, _stream()), "vbg_maxpool3x3s2")
     return y
 
 
-def avgpool2x2(x):
+def avgpool2x2(x, split_out=None):
     B, H, W, Cc = x.shape
-    y = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.float32, device=x.device)
-    L.check(L.load().vbg_avgpool2x2(_f32(x), B, H, W, Cc, _f32(y), _stream()), "vbg_avgpool2x2")
+    y = _new_act((B, H // 2, W // 2, Cc), x.device, isinstance(x, Split) if split_out is None else split_out)
+    (xp, xpl), (yp, ypl) = _act(x), _act(y)
+    L.check(L.load().vbg_avgpool2x2_x(xp, xpl, B, H, W, Cc, yp, ypl, _stream()), "vbg_avgpool2x2")
     return y
 
 
@@ -284,13 +386,15 @@ def repack_oihw_to_ohwi(w):
 
 
 # ------------------------------------------------------------------ a7
-def roi_align(feat, boxes, seg_off, spatial_scale, P, want_grid=False):
+def roi_align(feat, boxes, seg_off, spatial_scale, P, want_grid=False, split_out=False):
+    """``feat`` fp32 NHWC tensor or Split; ``split_out`` writes the [K,P,P,C] result as a Split."""
     B, Hf, Wf, Cc = feat.shape
     K = boxes.shape[0]
-    out = torch.empty((K, P, P, Cc), dtype=torch.float32, device=feat.device)
+    out = _new_act((K, P, P, Cc), feat.device, split_out)
     sg = torch.empty((K, 2), dtype=torch.int32, device=feat.device) if want_grid else None
-    L.check(L.load().vbg_roi_align_fwd(_f32(feat), B, Hf, Wf, Cc, _i32(boxes), _i32(seg_off), K, spatial_scale, P,
-                                       _f32(out), _i32(sg), _stream()), "vbg_roi_align_fwd")
+    (fp, fpl), (op, opl) = _act(feat), _act(out)
+    L.check(L.load().vbg_roi_align_x(fp, fpl, B, Hf, Wf, Cc, _i32(boxes), _i32(seg_off), K, spatial_scale, P,
+                                     op, opl, _i32(sg), _stream()), "vbg_roi_align_fwd")
     return (out, sg) if want_grid else out
 
 
