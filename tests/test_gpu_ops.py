@@ -396,7 +396,9 @@ def test_split_merge_roundtrip(ops):
 
 @pytest.mark.parametrize("M,N,K,K1", [(128, 64, 64, 64), (300, 768, 768, 768), (4128, 3072, 768, 768), (4128, 768, 3072, 3072),
                                       (128, 1024, 1792, 1024), (1000, 136, 64, 64), (77, 64, 192, 64), (4096, 128, 896, 128),
-                                      (513, 256, 12544, 12544), (20000, 256, 256, 256)])
+                                      (513, 256, 12544, 12544), (20000, 256, 256, 256),
+                                      # M tails that leave a warp with both fully-valid and partially-valid lanes
+                                      (94, 384, 128, 128), (222, 192, 64, 64)])
 @pytest.mark.parametrize("out_split", [False, True])
 def test_gemm_presplit(ops, ps_kb, M, N, K, K1, out_split):
     """TMA-fed bf16x3 GEMM over Split operands (no in-kernel conversion): equals a float64 evaluation of the three

@@ -13,7 +13,8 @@
 //                              per K block, conv padding = TMA out-of-bounds zero fill, stride 2 = traversal stride
 //                              W planes: rank-3 map (k, n, plane)
 //   warp 1      MMA issuer     3 x tcgen05.mma (M=128, N=BN, K=16) per K step into one of two TMEM accumulators
-//   warps 2-5   epilogue       tcgen05.ld -> scale/shift/residual/activation -> fp32 or bf16 hi/lo planes (vbg_tc.cuh)
+//   warps 2-9   epilogue       tcgen05.ld -> scale/shift/residual/activation -> fp32 or bf16 hi/lo planes (vbg_tc.cuh);
+//                              two warps per TMEM lane quarter, alternating 32-column chunks
 //
 // Persistent over output tiles (grid = min(tiles, 148)); the operand ring runs straight through tile boundaries and the
 // epilogue of tile i overlaps the mainloop of tile i+1.  KB = K elements per ring stage: 64 (SWIZZLE_128B rows) or
@@ -23,8 +24,8 @@
 
 namespace vbg {
 
-constexpr int kPsThreads = 192;
-constexpr uint32_t kPsEpiBytes = 4 * kEpiStageFloats * 4;
+constexpr int kPsThreads = 320;                  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr uint32_t kPsEpiBytes = 8 * kEpiStageFloats * 4;
 constexpr int kPsDefaultKB = 64;
 
 __device__ __forceinline__ TcTile ps_tile(const TcParams& p, int tile, int bn) {
@@ -71,7 +72,7 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 128); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 256); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -82,6 +83,11 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may run while
+  // the previous kernel of the stream is still draining; nothing below touches global memory before that kernel has
+  // completed and flushed.  Our own dependents may be scheduled as soon as SMs free up (they wait the same way).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     if (lane == 0) {
@@ -145,15 +151,15 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===== epilogue warps: TMEM lanes [32q, 32q+32), q = warp & 3
-    const int q = warp & 3;
+    // ===== epilogue warps: TMEM lanes [32q, 32q+32), q = warp & 3; warps 2-5 take the even 32-column chunks, 6-9 the odd ones
+    const int q = warp & 3, half = (warp - 2) >> 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const TcTile t = ps_tile(p, tile, BN);
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
-      tc_epilogue<BN>(p, t, tmem_base + (uint32_t)(acc * BN), q, lane, epi + q * kEpiStageFloats);
+      tc_epilogue<BN>(p, t, tmem_base + (uint32_t)(acc * BN), q, lane, epi + (warp - 2) * kEpiStageFloats, half * 32, 64);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
@@ -204,7 +210,15 @@ static int launch_ps(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
     attr = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
-  gemm_ps_kernel<BN, KB, STAGES><<<tiles < kNumSMs ? tiles : kNumSMs, kPsThreads, smem, s>>>(a, a2, w, p);
+  static const bool pdl = [] { const char* e = getenv("VBG_PDL"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(tiles < kNumSMs ? tiles : kNumSMs); cfg.blockDim = dim3(kPsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_ps_kernel<BN, KB, STAGES>, a, a2, w, p);
+  if (e != cudaSuccess) { set_error("vbg_gemm_ps launch failed: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return VBG_ECUDA; }
   return check_launch("vbg_gemm_ps(tcgen05 bf16x3, pre-split)");
 }
 
@@ -223,7 +237,7 @@ static int dispatch_ps(const CUtensorMap& a, const CUtensorMap& a2, const void* 
     return launch_ps<64, 64, 4>(a, a2, w, p, s);
   }
   if (bn == 256) return launch_ps<256, 32, 4>(a, a2, w, p, s);
-  if (bn == 192) return launch_ps<192, 32, 5>(a, a2, w, p, s);
+  if (bn == 192) return launch_ps<192, 32, 4>(a, a2, w, p, s);
   if (bn == 128) return launch_ps<128, 32, 6>(a, a2, w, p, s);
   return launch_ps<64, 32, 8>(a, a2, w, p, s);
 }

@@ -184,7 +184,7 @@ roi_align_sep_kernel(const float* __restrict__ feat, int B, int Hf, int Wf, int 
 // direct kernel's operation order (same sample-grid table, same summation order => identical values).  HBM / L2 -> SM
 // traffic per ROI drops from (samples x 4 taps x C) per bin -- ~24 KB per 1 KB of output at line-sized boxes -- to the
 // window itself.  ROIs whose window does not fit `win_floats` fall back to global taps inside the same kernel.
-constexpr int kRoiCh = 64, kRoiCq = kRoiCh / 4;
+constexpr int kRoiCh = 64, kRoiCq = kRoiCh / 4, kRoiTab = 7 * 24;
 
 __global__ void __launch_bounds__(256)
 roi_align_win_kernel(const void* __restrict__ feat, long long feat_plane, int B, int Hf, int Wf, int C,
@@ -215,6 +215,27 @@ roi_align_win_kernel(const void* __restrict__ feat, long long feat_plane, int B,
 
   const int C4 = C >> 2;
   const size_t f0 = (size_t)b * Hf * Wf * C4 + (size_t)chunk * kRoiCq;
+  // per-axis sample tables (one entry per (bin, sample) coordinate): the coordinate arithmetic -- two IEEE divisions and the
+  // clamp / skip rules per sample -- is done once per ROI instead of once per (bin, channel-quad, sample)
+  __shared__ int4 tab_y[kRoiTab], tab_x[kRoiTab];      // (valid, low tap, high tap, bits of the low-side weight l)
+  const bool tabled = staged && P * gh <= kRoiTab && P * gw <= kRoiTab;
+  if (tabled) {
+    for (int i = tid; i < P * gh + P * gw; i += 256) {
+      const bool is_y = i < P * gh;
+      const int j = is_y ? i : i - P * gh;
+      const int g = is_y ? gh : gw, dim = is_y ? Hf : Wf, lo_w = is_y ? y_lo : x_lo, hi_w = is_y ? y_hi : x_hi;
+      const float start = is_y ? sh : sw, bin = is_y ? bh : bw;
+      const int pb = j / g, is = j - pb * g;
+      float c = __fadd_rn(__fadd_rn(start, __fmul_rn((float)pb, bin)), __fdiv_rn(__fmul_rn((float)is + 0.5f, bin), (float)g));
+      const int valid = !(c < -1.0f || c > (float)dim);
+      c = fmaxf(c, 0.f);
+      int lo = (int)c, hi;
+      if (lo >= dim - 1) { hi = lo = dim - 1; c = (float)lo; } else { hi = lo + 1; }
+      const float l = c - (float)lo;
+      const int4 e = make_int4(valid, min(max(lo, lo_w), hi_w) - lo_w, min(max(hi, lo_w), hi_w) - lo_w, __float_as_int(l));
+      if (is_y) tab_y[j] = e; else tab_x[j] = e;
+    }
+  }
   if (staged) {
     const int n4 = rows * cols * kRoiCq;
     for (int i = tid; i < n4; i += 256) {
@@ -230,35 +251,57 @@ roi_align_win_kernel(const void* __restrict__ feat, long long feat_plane, int B,
     const int bin = item / kRoiCq, cq = item - bin * kRoiCq;
     const int ph = bin / P, pw = bin - ph * P;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int iy = 0; iy < gh; ++iy) {
-      float y = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)ph, bh)), __fdiv_rn(__fmul_rn((float)iy + 0.5f, bh), (float)gh));
-      for (int ix = 0; ix < gw; ++ix) {
-        float x = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)pw, bw)), __fdiv_rn(__fmul_rn((float)ix + 0.5f, bw), (float)gw));
-        if (y < -1.0f || y > (float)Hf || x < -1.0f || x > (float)Wf) continue;
-        float yy = fmaxf(y, 0.f), xx = fmaxf(x, 0.f);
-        int yl = (int)yy, xl = (int)xx, yh, xh;
-        if (yl >= Hf - 1) { yh = yl = Hf - 1; yy = (float)yl; } else { yh = yl + 1; }
-        if (xl >= Wf - 1) { xh = xl = Wf - 1; xx = (float)xl; } else { xh = xl + 1; }
-        const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
-        const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-        float4 a, bb, cc, d;
-        if (staged) {
-          // clamped into the window: never out of bounds even if a rounding corner case widened the sample range
-          const int r0 = min(max(yl, y_lo), y_hi) - y_lo, r1 = min(max(yh, y_lo), y_hi) - y_lo;
-          const int c0 = min(max(xl, x_lo), x_hi) - x_lo, c1 = min(max(xh, x_lo), x_hi) - x_lo;
-          const float4* w4p = reinterpret_cast<const float4*>(win) + cq;
-          a = w4p[(r0 * cols + c0) * kRoiCq]; bb = w4p[(r0 * cols + c1) * kRoiCq];
-          cc = w4p[(r1 * cols + c0) * kRoiCq]; d = w4p[(r1 * cols + c1) * kRoiCq];
-        } else {
-          a = ld4_fmt(feat, feat_plane, f0 + ((size_t)yl * Wf + xl) * C4 + cq);
-          bb = ld4_fmt(feat, feat_plane, f0 + ((size_t)yl * Wf + xh) * C4 + cq);
-          cc = ld4_fmt(feat, feat_plane, f0 + ((size_t)yh * Wf + xl) * C4 + cq);
-          d = ld4_fmt(feat, feat_plane, f0 + ((size_t)yh * Wf + xh) * C4 + cq);
+    if (tabled) {
+      const float4* w4p = reinterpret_cast<const float4*>(win) + cq;
+      for (int iy = 0; iy < gh; ++iy) {
+        const int4 ey = tab_y[ph * gh + iy];
+        if (!ey.x) continue;
+        const float ly = __int_as_float(ey.w), hy = 1.f - ly;
+        const float4* r0p = w4p + ey.y * cols * kRoiCq;
+        const float4* r1p = w4p + ey.z * cols * kRoiCq;
+        for (int ix = 0; ix < gw; ++ix) {
+          const int4 ex = tab_x[pw * gw + ix];
+          if (!ex.x) continue;
+          const float lx = __int_as_float(ex.w), hx = 1.f - lx;
+          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+          const float4 a = r0p[ex.y * kRoiCq], bb = r0p[ex.z * kRoiCq], cc = r1p[ex.y * kRoiCq], d = r1p[ex.z * kRoiCq];
+          acc.x += w1 * a.x + w2 * bb.x + w3 * cc.x + w4 * d.x;
+          acc.y += w1 * a.y + w2 * bb.y + w3 * cc.y + w4 * d.y;
+          acc.z += w1 * a.z + w2 * bb.z + w3 * cc.z + w4 * d.z;
+          acc.w += w1 * a.w + w2 * bb.w + w3 * cc.w + w4 * d.w;
         }
-        acc.x += w1 * a.x + w2 * bb.x + w3 * cc.x + w4 * d.x;
-        acc.y += w1 * a.y + w2 * bb.y + w3 * cc.y + w4 * d.y;
-        acc.z += w1 * a.z + w2 * bb.z + w3 * cc.z + w4 * d.z;
-        acc.w += w1 * a.w + w2 * bb.w + w3 * cc.w + w4 * d.w;
+      }
+    } else {
+      for (int iy = 0; iy < gh; ++iy) {
+        float y = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)ph, bh)), __fdiv_rn(__fmul_rn((float)iy + 0.5f, bh), (float)gh));
+        for (int ix = 0; ix < gw; ++ix) {
+          float x = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)pw, bw)), __fdiv_rn(__fmul_rn((float)ix + 0.5f, bw), (float)gw));
+          if (y < -1.0f || y > (float)Hf || x < -1.0f || x > (float)Wf) continue;
+          float yy = fmaxf(y, 0.f), xx = fmaxf(x, 0.f);
+          int yl = (int)yy, xl = (int)xx, yh, xh;
+          if (yl >= Hf - 1) { yh = yl = Hf - 1; yy = (float)yl; } else { yh = yl + 1; }
+          if (xl >= Wf - 1) { xh = xl = Wf - 1; xx = (float)xl; } else { xh = xl + 1; }
+          const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+          float4 a, bb, cc, d;
+          if (staged) {
+            // clamped into the window: never out of bounds even if a rounding corner case widened the sample range
+            const int r0 = min(max(yl, y_lo), y_hi) - y_lo, r1 = min(max(yh, y_lo), y_hi) - y_lo;
+            const int c0 = min(max(xl, x_lo), x_hi) - x_lo, c1 = min(max(xh, x_lo), x_hi) - x_lo;
+            const float4* w4p = reinterpret_cast<const float4*>(win) + cq;
+            a = w4p[(r0 * cols + c0) * kRoiCq]; bb = w4p[(r0 * cols + c1) * kRoiCq];
+            cc = w4p[(r1 * cols + c0) * kRoiCq]; d = w4p[(r1 * cols + c1) * kRoiCq];
+          } else {
+            a = ld4_fmt(feat, feat_plane, f0 + ((size_t)yl * Wf + xl) * C4 + cq);
+            bb = ld4_fmt(feat, feat_plane, f0 + ((size_t)yl * Wf + xh) * C4 + cq);
+            cc = ld4_fmt(feat, feat_plane, f0 + ((size_t)yh * Wf + xl) * C4 + cq);
+            d = ld4_fmt(feat, feat_plane, f0 + ((size_t)yh * Wf + xh) * C4 + cq);
+          }
+          acc.x += w1 * a.x + w2 * bb.x + w3 * cc.x + w4 * d.x;
+          acc.y += w1 * a.y + w2 * bb.y + w3 * cc.y + w4 * d.y;
+          acc.z += w1 * a.z + w2 * bb.z + w3 * cc.z + w4 * d.z;
+          acc.w += w1 * a.w + w2 * bb.w + w3 * cc.w + w4 * d.w;
+        }
       }
     }
     acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);
@@ -300,8 +343,14 @@ extern "C" int vbg_roi_align_x(const void* feat, long long feat_plane, int B, in
   cudaStream_t s = as_stream(stream);
   static const bool direct = [] { const char* e = getenv("VBG_ROI_DIRECT"); return e && e[0] == '1'; }();
   if (!direct && C % kRoiCh == 0) {
-    // 48 KB window (four resident CTAs per SM): a line-sized ROI at stride 4 needs ~46 KB per 64-channel chunk
-    constexpr int win_floats = 48 * 1024 / 4;
+    // 60 KB window (three resident CTAs per SM): a line-sized ROI at stride 4 needs 30-46 KB per 64-channel chunk
+    constexpr int win_floats = 60 * 1024 / 4;
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(roi_align_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, win_floats * 4);
+      if (e != cudaSuccess) { set_error("vbg_roi_align_fwd: smem opt-in failed: %s", cudaGetErrorString(e)); return VBG_ECUDA; }
+      attr = true;
+    }
     roi_align_win_kernel<<<dim3(K, C / kRoiCh), 256, win_floats * sizeof(float), s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off,
                                                                                        spatial_scale, P, out, out_plane, sample_grid,
                                                                                        win_floats);

@@ -113,7 +113,7 @@ constexpr uint32_t kFmtTF32 = 2, kFmtBF16 = 1;
 // ------------------------------------------------------------------ tile geometry shared by the tcgen05 GEMM kernels
 constexpr int BM = 128, BKE = 32;          // 32 fp32 = one 128-byte swizzle row
 constexpr int kTcThreads = 192;            // warp 0 TMA, warp 1 MMA, warps 2-5 convert / epilogue
-constexpr int kEpiStageFloats = 32 * 36;   // per-warp 32x32 transpose buffer, row stride 36 floats (conflict-free float4)
+constexpr int kEpiStageFloats = 32 * 32;   // per-warp 32x32 transpose buffer; 16-byte chunks XOR-swizzled by row (conflict-free float4)
 
 struct TcParams {
   float* C; int ldc;
@@ -197,22 +197,25 @@ __device__ __forceinline__ uint32_t tc_row_offsets(const TcParams& p, const TcTi
   return ok_mask;
 }
 
+// staging buffer addressing: element (row, 4-column group g) lives at row*32 + ((g ^ (row & 7)) << 2)
+__device__ __forceinline__ int epi_sw(int row, int g) { return row * 32 + ((g ^ (row & 7)) << 2); }
+
 template <int BN>
 __device__ __noinline__ void tc_epilogue_generic(const TcParams& p, const TcTile& t, uint32_t tmem_base, int q, int lane,
-                                                 float* __restrict__ stage) {
+                                                 float* __restrict__ stage, int c_begin, int c_step) {
   const vbg_epilogue_t& ep = p.ep;
-  const int sub = lane >> 3, c4 = (lane & 7) * 4;
+  const int sub = lane >> 3, g = lane & 7, c4 = g * 4;
   long long out_off[8], res_off[8];
   const uint32_t ok_mask = tc_row_offsets(p, t, q, sub, out_off, res_off);
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = c_begin; c0 < BN; c0 += c_step) {
     if (t.n0 + c0 >= p.N) break;                       // warp-uniform
     uint32_t v[32];
     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(stage + lane * 36 + j * 4) =
+      *reinterpret_cast<float4*>(stage + epi_sw(lane, j)) =
           make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
     __syncwarp();
     const int n = t.n0 + c0 + c4;
@@ -223,7 +226,7 @@ __device__ __noinline__ void tc_epilogue_generic(const TcParams& p, const TcTile
 #pragma unroll 1
       for (int e = 0; e < 4; ++e) {
         if (n + e >= p.N) break;
-        float o = stage[(it * 4 + sub) * 36 + c4 + e];
+        float o = stage[epi_sw(it * 4 + sub, g) + e];
         o = o * (ep.scale ? __ldg(ep.scale + n + e) : 1.f) + (ep.shift ? __ldg(ep.shift + n + e) : 0.f);
         if (ep.residual) {
           if (ep.res_plane > 0) {
@@ -247,92 +250,122 @@ __device__ __noinline__ void tc_epilogue_generic(const TcParams& p, const TcTile
   }
 }
 
-template <int BN>
-__device__ __forceinline__ void tc_epilogue(const TcParams& p, const TcTile& t, uint32_t tmem_base, int q, int lane,
-                                            float* __restrict__ stage) {
+// kAllOk: all 8 rows of the lane exist (every full tile) -> no per-row predication.
+template <int BN, bool kAllOk>
+__device__ __forceinline__ void tc_epilogue_fast(const TcParams& p, const TcTile& t, uint32_t tmem_base, int q, int lane,
+                                                 float* __restrict__ stage, int c_begin, int c_step, const long long (&out_off)[8],
+                                                 const long long (&res_off)[8], uint32_t ok_mask) {
   const vbg_epilogue_t& ep = p.ep;
-  const int sub = lane >> 3, c4 = (lane & 7) * 4;
-  long long out_off[8], res_off[8];
-  const uint32_t ok_mask = tc_row_offsets(p, t, q, sub, out_off, res_off);
+  const int sub = lane >> 3, g = lane & 7, c4 = g * 4;
   const bool split_out = ep.out_mode == VBG_OUT_SPLIT_BF16;
   const int res_kind = !ep.residual ? 0 : (ep.res_plane > 0 ? 2 : 1);
-  const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.N & 3) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(ep.scale) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ep.shift) & 15) == 0) &&
-                      (!split_out || (ep.out_plane & 3) == 0) &&
-                      (res_kind == 0 || (((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) && (ep.res_plane & 3) == 0 &&
-                                         (ep.res_mode == VBG_RES_UP2 || (ep.ldr & 3) == 0)));
-  if (!vec_ok) {
-    tc_epilogue_generic<BN>(p, t, tmem_base, q, lane, stage);
-    return;
-  }
   const float* __restrict__ scale = ep.scale;
   const float* __restrict__ shift = ep.shift;
   const int act = ep.act;
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  // scale / shift of the first chunk; the next chunk's are fetched while this one is processed
+  float4 sc = one, sh = zero;
+  {
+    const int n = t.n0 + c_begin + c4;
+    if (c_begin < BN && n < p.N) {
+      if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + n));
+      if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + n));
+    }
+  }
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 32) {
+  for (int c0 = c_begin; c0 < BN; c0 += c_step) {
     if (t.n0 + c0 >= p.N) break;                       // warp-uniform
+    float4 sc_n = one, sh_n = zero;
+    {
+      const int nn = t.n0 + c0 + c_step + c4;
+      if (c0 + c_step < BN && nn < p.N) {
+        if (scale) sc_n = __ldg(reinterpret_cast<const float4*>(scale + nn));
+        if (shift) sh_n = __ldg(reinterpret_cast<const float4*>(shift + nn));
+      }
+    }
     uint32_t v[32];
     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
     __syncwarp();                                      // previous chunk finished reading the buffer
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      *reinterpret_cast<float4*>(stage + lane * 36 + j * 4) =
+      *reinterpret_cast<float4*>(stage + epi_sw(lane, j)) =
           make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
     __syncwarp();
     const int n = t.n0 + c0 + c4;
-    if (n >= p.N) continue;                            // N % 4 == 0: a 4-column group is entirely in or out
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + n));
-    if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + n));
-    float4 o[8];
+    if (n < p.N) {                                     // N % 4 == 0: a 4-column group is entirely in or out
+      float4 o[8];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const float4 a = *reinterpret_cast<const float4*>(stage + (it * 4 + sub) * 36 + c4);
-      o[it] = make_float4(fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y), fmaf(a.z, sc.z, sh.z), fmaf(a.w, sc.w, sh.w));
+      for (int it = 0; it < 8; ++it) {
+        const float4 a = *reinterpret_cast<const float4*>(stage + epi_sw(it * 4 + sub, g));
+        o[it] = make_float4(fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y), fmaf(a.z, sc.z, sh.z), fmaf(a.w, sc.w, sh.w));
+      }
+      if (res_kind == 1) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (kAllOk || ((ok_mask >> it) & 1u)) {
+            const float4 rv = __ldg(reinterpret_cast<const float4*>(ep.residual + res_off[it] + n));
+            o[it].x += rv.x; o[it].y += rv.y; o[it].z += rv.z; o[it].w += rv.w;
+          }
+      } else if (res_kind == 2) {
+        const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + n;
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (kAllOk || ((ok_mask >> it) & 1u)) {
+            const float4 rv = merge4(__ldg(reinterpret_cast<const uint2*>(rh + res_off[it])),
+                                     __ldg(reinterpret_cast<const uint2*>(rh + res_off[it] + ep.res_plane)));
+            o[it].x += rv.x; o[it].y += rv.y; o[it].z += rv.z; o[it].w += rv.w;
+          }
+      }
+      if (act == VBG_ACT_RELU) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          o[it] = make_float4(fmaxf(o[it].x, 0.f), fmaxf(o[it].y, 0.f), fmaxf(o[it].z, 0.f), fmaxf(o[it].w, 0.f));
+      } else if (act == VBG_ACT_GELU) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          o[it] = make_float4(gelu_erf(o[it].x), gelu_erf(o[it].y), gelu_erf(o[it].z), gelu_erf(o[it].w));
+      }
+      if (split_out) {
+        __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(p.C) + n;
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (kAllOk || ((ok_mask >> it) & 1u)) {
+            uint2 hi, lo;
+            split4(o[it], hi, lo);
+            *reinterpret_cast<uint2*>(hp + out_off[it]) = hi;
+            *reinterpret_cast<uint2*>(hp + out_off[it] + ep.out_plane) = lo;
+          }
+      } else {
+        float* cp = p.C + n;
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (kAllOk || ((ok_mask >> it) & 1u)) *reinterpret_cast<float4*>(cp + out_off[it]) = o[it];
+      }
     }
-    if (res_kind == 1) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        if ((ok_mask >> it) & 1u) {
-          const float4 rv = __ldg(reinterpret_cast<const float4*>(ep.residual + res_off[it] + n));
-          o[it].x += rv.x; o[it].y += rv.y; o[it].z += rv.z; o[it].w += rv.w;
-        }
-    } else if (res_kind == 2) {
-      const __nv_bfloat16* rh = reinterpret_cast<const __nv_bfloat16*>(ep.residual) + n;
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        if ((ok_mask >> it) & 1u) {
-          const float4 rv = merge4(__ldg(reinterpret_cast<const uint2*>(rh + res_off[it])),
-                                   __ldg(reinterpret_cast<const uint2*>(rh + res_off[it] + ep.res_plane)));
-          o[it].x += rv.x; o[it].y += rv.y; o[it].z += rv.z; o[it].w += rv.w;
-        }
-    }
-    if (act == VBG_ACT_RELU) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        o[it] = make_float4(fmaxf(o[it].x, 0.f), fmaxf(o[it].y, 0.f), fmaxf(o[it].z, 0.f), fmaxf(o[it].w, 0.f));
-    } else if (act == VBG_ACT_GELU) {
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        o[it] = make_float4(gelu_erf(o[it].x), gelu_erf(o[it].y), gelu_erf(o[it].z), gelu_erf(o[it].w));
-    }
-    if (split_out) {
-      __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(p.C) + n;
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        if ((ok_mask >> it) & 1u) {
-          uint2 hi, lo;
-          split4(o[it], hi, lo);
-          *reinterpret_cast<uint2*>(hp + out_off[it]) = hi;
-          *reinterpret_cast<uint2*>(hp + out_off[it] + ep.out_plane) = lo;
-        }
-    } else {
-      float* cp = p.C + n;
-#pragma unroll
-      for (int it = 0; it < 8; ++it)
-        if ((ok_mask >> it) & 1u) *reinterpret_cast<float4*>(cp + out_off[it]) = o[it];
-    }
+    sc = sc_n; sh = sh_n;
   }
+}
+
+// Columns [c_begin, BN) in steps of c_step (32 = this warp does every chunk; 64 with two warps per TMEM lane quarter).
+template <int BN>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, const TcTile& t, uint32_t tmem_base, int q, int lane,
+                                            float* __restrict__ stage, int c_begin = 0, int c_step = 32) {
+  const vbg_epilogue_t& ep = p.ep;
+  const bool split_out = ep.out_mode == VBG_OUT_SPLIT_BF16;
+  const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && ((p.N & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(ep.scale) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ep.shift) & 15) == 0) &&
+                      (!split_out || (ep.out_plane & 3) == 0) &&
+                      (!ep.residual || (((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) && (ep.res_plane & 3) == 0 &&
+                                        (ep.res_mode == VBG_RES_UP2 || (ep.ldr & 3) == 0)));
+  if (!vec_ok) {
+    tc_epilogue_generic<BN>(p, t, tmem_base, q, lane, stage, c_begin, c_step);
+    return;
+  }
+  long long out_off[8], res_off[8];
+  const uint32_t ok_mask = tc_row_offsets(p, t, q, lane >> 3, out_off, res_off);
+  // warp-uniform choice: both variants execute tcgen05.ld.sync.aligned / __syncwarp, so the warp must not split here
+  if (__all_sync(0xffffffffu, ok_mask == 0xffu)) tc_epilogue_fast<BN, true>(p, t, tmem_base, q, lane, stage, c_begin, c_step, out_off, res_off, ok_mask);
+  else tc_epilogue_fast<BN, false>(p, t, tmem_base, q, lane, stage, c_begin, c_step, out_off, res_off, ok_mask);
 }
 
 // ---- host helpers (vbg_gemm_tc.cu)
