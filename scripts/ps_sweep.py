@@ -15,7 +15,7 @@ def timed(fn, reps=20):
     return e0.elapsed_time(e1) / reps
 
 dev = "cuda"
-GEMMS = [(4128, 2304, 768), (4128, 768, 768), (4128, 3072, 768), (4128, 768, 3072), (33024, 3072, 768), (131072, 256, 256),
+GEMMS = [(8256, 2304, 768), (8256, 3072, 768), (4128, 2304, 768), (4128, 768, 768), (4128, 3072, 768), (4128, 768, 3072), (33024, 3072, 768), (131072, 256, 256),
          (131072, 256, 64), (32768, 256, 128), (1024, 1024, 12544)]
 for (M, N, K) in GEMMS:
     A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev) * 0.02
@@ -23,10 +23,10 @@ for (M, N, K) in GEMMS:
     ep = ops.make_epilogue(None, torch.zeros(N, device=dev))
     ms = timed(lambda: ops.gemm(A, W, ep=ep, precision=ops.PREC_BF16X3, W_split=Ws))
     line = f"[gemm {M}x{N}x{K}] fp32-A {ms*1e3:7.1f} us {2.0*M*N*K/ms/1e9:6.1f} TF/s |"
-    for kb in ("64", "32"):
-        os.environ["VBG_PS_KB"] = kb
+    for kb, cg in (("64", "0"), ("64", "1"), ("32", "0")):
+        os.environ["VBG_PS_KB"] = kb; os.environ["VBG_PS_CG2"] = cg
         ms = timed(lambda: ops.gemm(As, W, ep=ep, precision=ops.PREC_BF16X3, W_split=Ws, split_out=True))
-        line += f" ps{kb} {ms*1e3:7.1f} us {2.0*M*N*K/ms/1e9:6.1f} TF/s |"
+        line += f" ps{kb}{'x2' if cg == '1' else ''} {ms*1e3:7.1f} us {2.0*M*N*K/ms/1e9:6.1f} TF/s |"
     print(line, flush=True)
 
 CONVS = [(8, 128, 128, 256, 256, 3, 1), (8, 128, 128, 64, 64, 3, 1), (8, 64, 64, 128, 128, 3, 1), (8, 32, 32, 256, 256, 3, 1),
@@ -39,8 +39,8 @@ for (B, H, Wd, Cin, Cout, k, s) in CONVS:
     fl = 2.0 * B * Ho * Wo * Cout * Cin * k * k
     ms = timed(lambda: ops.conv2d(x, w, s, 1, ep=ep, precision=ops.PREC_BF16X3, W_split=ws))
     line = f"[conv B{B} {H}x{Wd} {Cin}->{Cout} k{k} s{s}] fp32-A {ms*1e3:7.1f} us {fl/ms/1e9:6.1f} TF/s |"
-    for kb in ("64", "32"):
-        os.environ["VBG_PS_KB"] = kb
+    for kb, cg in (("64", "0"), ("64", "1"), ("32", "0")):
+        os.environ["VBG_PS_KB"] = kb; os.environ["VBG_PS_CG2"] = cg
         ms = timed(lambda: ops.conv2d(xs, w, s, 1, ep=ep, precision=ops.PREC_BF16X3, W_split=ws, split_out=True))
-        line += f" ps{kb} {ms*1e3:7.1f} us {fl/ms/1e9:6.1f} TF/s |"
+        line += f" ps{kb}{'x2' if cg == '1' else ''} {ms*1e3:7.1f} us {fl/ms/1e9:6.1f} TF/s |"
     print(line, flush=True)

@@ -385,6 +385,13 @@ def ps_kb(request, monkeypatch):
     return int(request.param)
 
 
+@pytest.fixture(params=["0", "1"])
+def ps_cg2(request, monkeypatch):
+    """Single-CTA tiles (128 x BN) and CTA-pair tiles (tcgen05 cta_group::2, 256 x BN over a cluster of two)."""
+    monkeypatch.setenv("VBG_PS_CG2", request.param)
+    return int(request.param)
+
+
 def test_split_merge_roundtrip(ops):
     g = torch.Generator().manual_seed(5)
     x = torch.randn(1000, 64, generator=g) * 3
@@ -400,7 +407,7 @@ def test_split_merge_roundtrip(ops):
                                       # M tails that leave a warp with both fully-valid and partially-valid lanes
                                       (94, 384, 128, 128), (222, 192, 64, 64)])
 @pytest.mark.parametrize("out_split", [False, True])
-def test_gemm_presplit(ops, ps_kb, M, N, K, K1, out_split):
+def test_gemm_presplit(ops, ps_kb, ps_cg2, M, N, K, K1, out_split):
     """TMA-fed bf16x3 GEMM over Split operands (no in-kernel conversion): equals a float64 evaluation of the three
     products it issues; residual read from bf16 planes; fp32 or Split output."""
     assert ops.tc_available()
@@ -425,7 +432,7 @@ def test_gemm_presplit(ops, ps_kb, M, N, K, K1, out_split):
                                                  (2, 20, 12, 64, 128, 3, 1, 1), (1, 128, 128, 64, 256, 3, 1, 1), (2, 32, 32, 64, 128, 3, 2, 1),
                                                  (8, 64, 64, 128, 256, 3, 2, 1), (2, 16, 24, 64, 128, 1, 2, 0), (1, 256, 256, 64, 128, 3, 2, 1)])
 @pytest.mark.parametrize("res_mode", ["same", "up2"])
-def test_conv2d_presplit(ops, ps_kb, B, H, W, Cin, Cout, k, s, p, res_mode):
+def test_conv2d_presplit(ops, ps_kb, ps_cg2, B, H, W, Cin, Cout, k, s, p, res_mode):
     """Implicit-GEMM conv over a Split NHWC activation through a rank-5 TMA map (c, w, h, b, plane)."""
     assert ops.tc_available()
     g = torch.Generator().manual_seed(Cin + Cout + H + s)

@@ -173,6 +173,198 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------------------ CTA-pair variant (tcgen05 cta_group::2)
+// Two CTAs of a cluster (the two SMs of a TPC) compute one 256 x BN tile: each loads ITS 128 rows of the A planes and
+// HALF of the weight tile (BN/2 rows); the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), which reads A from each
+// CTA's own shared memory and the two B halves from both, and accumulates rows [0,128) into the leader's TMEM and rows
+// [128,256) into the peer's.  Per CTA and K block that is 64 KB of L2 -> SM traffic instead of 96 KB and 8 KB instead of
+// 12 KB of operand reads per MMA -- the single-CTA kernel is bound by exactly those two (shared-memory bandwidth:
+// 96 B/clk operand reads + 64 B/clk TMA writes > 128 B/clk).
+//   both CTAs   warp 0: TMA producer (own A rows + own B half; completion bytes land on the LEADER's full barrier)
+//               warps 2-9: epilogue of the CTA's own 128 rows (own TMEM), then a remote arrive on the leader's tmem_empty
+//   leader      warp 1: MMA issuer; tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t a;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(local_smem_addr), "r"(rank));
+  return a;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: data into the executing CTA's smem, completion bytes on the barrier at cluster address `bar`
+__device__ __forceinline__ void tma2_load_3d(const CUtensorMap* tm, uint32_t bar, void* dst, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(const CUtensorMap* tm, uint32_t bar, void* dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once the MMAs issued so far complete) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+template <int BN, int KB, int STAGES>
+__global__ void __launch_bounds__(kPsThreads, 1)
+gemm_ps2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmW, const TcParams p) {
+  constexpr int BH = BN / 2;                                          // weight rows held by each CTA
+  constexpr uint32_t A_BYTES = BM * KB * 2;
+  constexpr uint32_t B_BYTES = BH * KB * 2;
+  constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;         // A1 | A2 | W1 half | W2 half
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 128) ? 128 : (2 * BN <= 256 ? 256 : 512);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* epi = reinterpret_cast<float*>(ring + STAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES + kPsEpiBytes);   // used in the leader only
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;        // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2], used in the leader only
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int pm_tiles = (p.m_tiles + 1) >> 1;                          // pairs of 128-row tiles
+  const int n_tiles = pm_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmW);
+    if (p.kb_split < p.num_kb) prefetch_tmap(&tmA2);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 512); }   // 2 CTAs x 256 epilogue threads
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();                          // both CTAs' barriers are initialised before any remote arrive / complete_tx
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // this CTA's 128-row tile inside pair tile pt
+  auto my_tile = [&](int pt) {
+    const int pm = pt % pm_tiles, nt = pt / pm_tiles;
+    const int xt = 2 * pm + (int)rank;         // may be == m_tiles for the odd tail: every load is then out of bounds (zero
+    TcTile t{0, nt * BN, 0, 0, 0};             // fill) and every epilogue row is masked
+    if (p.conv) {
+      int i = xt;
+      t.w0 = (i % p.tiles_w) * p.tw; i /= p.tiles_w;
+      t.h0 = (i % p.tiles_h) * p.th; i /= p.tiles_h;
+      t.b0 = i * p.tb;
+    } else {
+      t.m0 = xt * BM;
+    }
+    return t;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer (both CTAs)
+      const uint32_t a_rows = p.conv ? (uint32_t)(p.tw * p.th * p.tb) : (uint32_t)BM;
+      const uint32_t tx_pair = 2u * (2u * a_rows * (uint32_t)(KB * 2) + 2u * B_BYTES);
+      int g = 0;
+      for (int pt = cluster_id; pt < n_tiles; pt += n_clusters) {
+        const TcTile t = my_tile(pt);
+        const int nb = t.n0 + (int)rank * BH;
+        for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+          uint8_t* sa = ring + s * STAGE_BYTES;
+          uint8_t* sb = sa + 2 * A_BYTES;
+          if (rank == 0) mbar_expect_tx(&full[s], tx_pair);
+          const uint32_t bar = mapa_rank(smem_u32(&full[s]), 0);
+          if (p.conv) {
+            const int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+            const int fr = tap / p.kw, fs = tap - fr * p.kw;
+            const int cw = t.w0 * p.sw + fs - p.pad_w, ch = t.h0 * p.sh + fr - p.pad_h;
+            tma2_load_5d(&tmA, bar, sa, cb * KB, cw, ch, t.b0, 0);
+            tma2_load_5d(&tmA, bar, sa + A_BYTES, cb * KB, cw, ch, t.b0, 1);
+          } else if (kb < p.kb_split) {
+            tma2_load_3d(&tmA, bar, sa, kb * KB, t.m0, 0);
+            tma2_load_3d(&tmA, bar, sa + A_BYTES, kb * KB, t.m0, 1);
+          } else {
+            tma2_load_3d(&tmA2, bar, sa, (kb - p.kb_split) * KB, t.m0, 0);
+            tma2_load_3d(&tmA2, bar, sa + A_BYTES, (kb - p.kb_split) * KB, t.m0, 1);
+          }
+          tma2_load_3d(&tmW, bar, sb, kb * KB, nb, 0);
+          tma2_load_3d(&tmW, bar, sb + B_BYTES, kb * KB, nb, 1);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ===== MMA issuer (leader): per 16-wide K step  D += A1*W1 ; D += A2*W1 ; D += A1*W2, M = 256 over the pair
+      constexpr uint32_t idesc = make_idesc(kFmtBF16, 2 * BM, BN);
+      int g = 0, it = 0;
+      for (int pt = cluster_id; pt < n_tiles; pt += n_clusters, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);             // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+          const int s = g % STAGES;
+          mbar_wait(&full[s], (g / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t base = smem_u32(ring + s * STAGE_BYTES);
+          const uint64_t a1 = ps_desc<KB>(base), a2 = ps_desc<KB>(base + A_BYTES);
+          const uint64_t w1 = ps_desc<KB>(base + 2 * A_BYTES), w2 = ps_desc<KB>(base + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+          for (int k = 0; k < KB / 16; ++k) {
+            const uint64_t o = (uint64_t)(2 * k);
+            umma2_bf16(d, a1 + o, w1 + o, idesc, (kb | k) != 0);
+            umma2_bf16(d, a2 + o, w1 + o, idesc, 1);
+            umma2_bf16(d, a1 + o, w2 + o, idesc, 1);
+          }
+          umma2_commit_both(&empty[s]);
+        }
+        umma2_commit_both(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs): own 128 rows from own TMEM
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    int it = 0;
+    for (int pt = cluster_id; pt < n_tiles; pt += n_clusters, ++it) {
+      const int acc = it & 1;
+      const TcTile t = my_tile(pt);
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      tc_epilogue<BN>(p, t, tmem_base + (uint32_t)(acc * BN), q, lane, epi + (warp - 2) * kEpiStageFloats, half * 32, 64);
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0));
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                          // the peer's smem / TMEM / barriers stay alive until both CTAs are done
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ split -> fp32 (inspection / tests)
 __global__ void merge_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long n,
                                   float* __restrict__ out) {
@@ -224,12 +416,75 @@ static int launch_ps(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
 
 int pick_bn3(int m_tiles, int N);
 
+template <int BN, int KB, int STAGES>
+static int launch_ps2(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& w, const TcParams& p, cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (2 * BM * KB * 2 + 2 * (BN / 2) * KB * 2) + kPsEpiBytes + 1024 + 256;
+  static_assert(smem <= 232448, "pre-split pair tile does not fit the 227 KB shared-memory limit");
+  static_assert(8 * (2 * STAGES + 4) + 4 <= 256, "barrier block overflows its 256 bytes");
+  static int max_clusters = 0;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kPsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  static const bool pdl = [] { const char* e = getenv("VBG_PDL"); return !(e && e[0] == '0'); }();
+  cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
+  if (max_clusters == 0) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_ps2_kernel<BN, KB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("gemm_ps2: smem opt-in failed: %s", cudaGetErrorString(e)); return VBG_ECUDA; }
+    cfg.gridDim = dim3(kNumSMs);
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, gemm_ps2_kernel<BN, KB, STAGES>, &cfg);
+    if (e != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = kNumSMs / 2; }
+    max_clusters = n < kNumSMs / 2 ? n : kNumSMs / 2;
+  }
+  const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  cfg.gridDim = dim3(2 * (pair_tiles < max_clusters ? pair_tiles : max_clusters));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_ps2_kernel<BN, KB, STAGES>, a, a2, w, p);
+  if (e != cudaSuccess) { set_error("vbg_gemm_ps (CTA pair) launch failed: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return VBG_ECUDA; }
+  return check_launch("vbg_gemm_ps(tcgen05 bf16x3, pre-split, cta_group::2)");
+}
+
+// CTA-pair tiles pay off when the kernel is bound by L2 -> SM feed / shared-memory bandwidth (which the pair cuts by a third /
+// halves for the weight tile): a grid that fills most of the chip, a K long enough that the mainloop -- not the epilogue --
+// sets the tile time, and a weight tile wide enough to matter next to the A tile.  Measured on B200 (profiles/
+// r1_gemm_presplit_pairs_k.log): +10..25 % on the BERT GEMMs and the 256-channel convs, -4..8 % on N <= 128 / short-K shapes.
+// VBG_PS_CG2 = 0 / 1 forces the choice (tests run both).
+static bool use_pairs(int m_tiles, int n_tiles_1cta, int N, int num_kb) {
+  const char* e = getenv("VBG_PS_CG2");
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1' && m_tiles >= 2;
+  return m_tiles >= 2 && N >= 192 && num_kb >= 8 && (long long)m_tiles * n_tiles_1cta >= 96;
+}
+
 static int dispatch_ps(const CUtensorMap& a, const CUtensorMap& a2, const void* w_hi, long long w_plane, int ldw, int K, TcParams& p,
                        int m_tiles, int kb, cudaStream_t s) {
   const int bn = pick_bn3(m_tiles, p.N);
   CUtensorMap w;
-  if (!map_ps_2d(&w, w_hi, w_plane, p.N, K, ldw, bn, kb)) return VBG_EUNSUPPORTED;
   p.m_tiles = m_tiles; p.n_tiles = cdiv(p.N, bn);
+  if (kb == 64 && use_pairs(m_tiles, p.n_tiles, p.N, p.num_kb)) {
+    // pair tiles: same (wave efficiency x column fill x tile efficiency) score as pick_bn3, over clusters of two SMs
+    const int pm_tiles = (m_tiles + 1) / 2, n_cl = kNumSMs / 2;
+    const int cand[4] = {256, 192, 128, 64};
+    int b2 = 64; double best = -1.0;
+    for (int i = 0; i < 4; ++i) {
+      const int bn_c = cand[i];
+      if (bn_c > 64 && p.N < bn_c - 32) continue;
+      const long long tiles = (long long)pm_tiles * cdiv(p.N, bn_c);
+      const double waves = (double)tiles / n_cl;
+      const double score = waves / (double)((tiles + n_cl - 1) / n_cl) * ((double)p.N / ((double)cdiv(p.N, bn_c) * bn_c)) *
+                           ((double)bn_c / (bn_c + 64.0));
+      if (score > best) { best = score; b2 = bn_c; }
+    }
+    if (!map_ps_2d(&w, w_hi, w_plane, p.N, K, ldw, b2 / 2, kb)) return VBG_EUNSUPPORTED;
+    p.n_tiles = cdiv(p.N, b2);
+    if (b2 == 256) return launch_ps2<256, 64, 3>(a, a2, w, p, s);
+    if (b2 == 192) return launch_ps2<192, 64, 3>(a, a2, w, p, s);
+    if (b2 == 128) return launch_ps2<128, 64, 4>(a, a2, w, p, s);
+    return launch_ps2<64, 64, 4>(a, a2, w, p, s);
+  }
+  if (!map_ps_2d(&w, w_hi, w_plane, p.N, K, ldw, bn, kb)) return VBG_EUNSUPPORTED;
   if (kb == 64) {
     if (bn == 256) return launch_ps<256, 64, 2>(a, a2, w, p, s);
     if (bn == 192) return launch_ps<192, 64, 2>(a, a2, w, p, s);

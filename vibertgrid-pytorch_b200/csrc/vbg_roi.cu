@@ -237,11 +237,22 @@ roi_align_win_kernel(const void* __restrict__ feat, long long feat_plane, int B,
     }
   }
   if (staged) {
-    const int n4 = rows * cols * kRoiCq;
-    for (int i = tid; i < n4; i += 256) {
-      const int pix = i / kRoiCq, cq = i - pix * kRoiCq;
-      const int y = y_lo + pix / cols, x = x_lo + pix % cols;
-      reinterpret_cast<float4*>(win)[i] = ld4_fmt(feat, feat_plane, f0 + ((size_t)y * Wf + x) * C4 + cq);
+    // 16 lanes cover one pixel's 64 channels (256 contiguous bytes); a thread walks pixels slot, slot + 16, ... and keeps
+    // four loads in flight (the window load is latency-bound otherwise: ~9 dependent round trips per CTA)
+    const int cq = tid & (kRoiCq - 1), slot = tid >> 4, npix = rows * cols;
+    int y = slot / cols, x = slot - y * cols;
+    for (int pix = slot; pix < npix; pix += 64) {
+      float4 v[4]; int px[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        px[u] = pix + 16 * u;
+        if (px[u] < npix) v[u] = ld4_fmt(feat, feat_plane, f0 + ((size_t)(y_lo + y) * Wf + (x_lo + x)) * C4 + cq);
+        x += 16;
+        while (x >= cols) { x -= cols; ++y; }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (px[u] < npix) reinterpret_cast<float4*>(win)[px[u] * kRoiCq + cq] = v[u];
     }
     __syncthreads();
   }
