@@ -162,6 +162,12 @@ def kernel_rooflines(net, cfg, dev, peaks):
     from vibertgrid_pytorch_b200 import ops, _lib
     out = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture of these same launches
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.isfile(tp):
+        with open(tp) as f:
+            traffic = {k: v.get("dram_bytes") for k, v in json.load(f).items() if isinstance(v, dict)}
 
     def timed(fn, reps=10):
         fn()
@@ -188,7 +194,7 @@ def kernel_rooflines(net, cfg, dev, peaks):
     ms = timed(lambda: ops.grid_scatter(emb_src, idx, seg_off))
     by = B * C * Hg * Wg * 4 + K * C * 4 + K * 16 + B * Hg * Wg * 4
     out["grid_scatter"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                           "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": ms, "bytes": by}
+                           "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": traffic.get("grid_scatter"), "ms": ms, "bytes": by}
     Hf, Wf = cfg.height // 4, cfg.width // 4
     feat = torch.randn(B, Hf, Wf, 256, device=dev)
     if ps:
@@ -196,7 +202,7 @@ def kernel_rooflines(net, cfg, dev, peaks):
     ms = timed(lambda: ops.roi_align(feat, boxes, seg_off, 0.25, 7, split_out=ps))
     by = B * 256 * Hf * Wf * 4 + K * 256 * 49 * 4 + K * 20
     out["roi_align"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": None, "ms": ms, "bytes": by}
+                        "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": traffic.get("roi_align"), "ms": ms, "bytes": by}
     # dominant tensor-bound kernel: the BERT FFN-up GEMM of the packed batch (M = real rows, N=3072, K=768)
     eng = net._get_engine()
     prec = eng._prec()
@@ -213,11 +219,11 @@ def kernel_rooflines(net, cfg, dev, peaks):
     # bf16x3: every fp32-equivalent product costs three bf16 tensor-core products, so the mode's ceiling is bf16 peak / 3
     peak, path = {ops.PREC_TF32: (peaks["tf32_tflops"], "tcgen05 kind::tf32 (measured cuBLAS TF32 peak)"),
                   ops.PREC_BF16X3: (peaks["bf16_tflops"] / 3.0, "tcgen05 kind::f16, 3 bf16 products per fp32-equivalent product"
-                                                                  + (", operands pre-split in HBM (TMA-fed, no in-kernel conversion)" if ps else "")
+                                                                  + (", operands pre-split in HBM (TMA-fed, no in-kernel conversion), CTA-pair tiles (cta_group::2)" if ps else "")
                                                                   + "; peak = measured bf16 peak / 3; frac == tensor-pipe share of bf16 peak"),
                   ops.PREC_FP32: (peaks["fp32_simt_tflops"], "CUDA-core fp32 FFMA")}[prec]
     out["gemm_ffn_up"] = {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
-                          "frac": fl / ms / 1e9 / peak, "traffic": None, "ms": ms, "flops": fl, "path": path,
+                          "frac": fl / ms / 1e9 / peak, "traffic": traffic.get("gemm_ffn_up"), "ms": ms, "flops": fl, "path": path,
                           "executed_tensor_tflops": (3.0 if prec == ops.PREC_BF16X3 else 1.0) * fl / ms / 1e9,
                           "shape": [M, 3072, 768]}
     return out
