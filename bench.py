@@ -158,10 +158,12 @@ def time_region(fn, steps, stream_sync, world):
 
 def kernel_rooflines(net, cfg, dev, peaks):
     """Live CUDA-event timings of the dominant kernels, each launched alone on this stream with an L2 flush
-    (256 MiB write) between launches.  Algorithmic bytes / FLOPs per launch: DESIGN.md section 5."""
+    (512 MiB write) between launches.  Algorithmic bytes / FLOPs per launch: DESIGN.md section 5."""
     from vibertgrid_pytorch_b200 import ops, _lib
     out = {}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # 512 MiB write between launches: flushes the 126 MB L2 and keeps the GPU busy (~80 us) while the host enqueues the
+    # event + launch behind it, so the event pair brackets the kernel alone, not the Python launch latency
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
     # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture of these same launches
     traffic = {}
     tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
@@ -271,6 +273,13 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     from vibertgrid_pytorch_b200 import synth
     cfg = synth.CONFIGS[args.config]
@@ -289,7 +298,7 @@ def main():
                 "config": {"workload": workload, "arm": "CPU restatement of the reference forward (oracle/), pinned to the live reference by tests/golden"},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     assert torch.cuda.is_available(), "bench.py (impl=ours) needs a GPU; there is no CPU fallback"
@@ -315,11 +324,21 @@ def main():
 
     sink = {}
 
+    from vibertgrid_pytorch_b200.prefetch import DevicePrefetcher, HostResultQueue
+    feed, results = {}, HostResultQueue()
+
     def step_e2e(i):
-        batch = to_device(host[i % n_rot], dev, True)
+        # the package's input pipeline: every step's batch is copied from pinned host memory inside the timed region, on a
+        # side stream, overlapping the previous step's kernels (the first next() of a feed uploads batches 0 and 1)
+        batch = next(feed["it"])
         loss, pm, ps, gt, pred = net(*batch)
-        sink["pred"] = pred.cpu()               # D2H of the step's result (+ loss)
-        sink["loss"] = loss.detach().cpu()
+        results.push(pred, loss)                # D2H of THIS step's result (+ loss), asynchronously into pinned memory ...
+        if len(results) > 1 or i == feed["n"] - 1:
+            while len(results) > (0 if i == feed["n"] - 1 else 1):
+                sink["pred"], sink["loss"] = results.pop()     # ... read on the host one step later (last step: at once)
+
+    def new_feed(n):
+        feed["it"], feed["n"] = iter(DevicePrefetcher((host[i % n_rot] for i in range(n)), dev)), n
 
     for i in range(args.warmup):
         step_resident(i)
@@ -329,8 +348,10 @@ def main():
     c0 = eng.kernel_launches
     ms = time_region(step_resident, args.steps, True, world)
     launches = eng.kernel_launches - c0
+    new_feed(2)
     for i in range(2):
         step_e2e(i)
+    new_feed(args.steps)
     ms_e2e = time_region(step_e2e, args.steps, True, world)
     clocks = sampler.stop() if sampler else None
 
@@ -358,7 +379,7 @@ def main():
             line["peaks"] = peaks
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_arm(cfg, 3, 1).items() if k != "ms_per_step"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

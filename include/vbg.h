@@ -172,6 +172,10 @@ VBG_API int vbg_gemm_ps(const void* A_hi, long long a_plane, int lda, const void
 /* implicit-GEMM convolution over a split NHWC activation (Cin % 64 == 0, Cout >= 64, stride 1 or 2) */
 VBG_API int vbg_conv2d_ps(const void* x_hi, long long x_plane, int B, int H, int W, int Cin, const void* w_hi, long long w_plane,
                   int Cout, int kh, int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, vbg_stream_t stream);
+/* Tuning aid: when dev_buf (>= 16 int64, device memory) is non-NULL, CTA 0 of every following CTA-pair GEMM launch writes
+ * clock64 stamps of its pipeline milestones into it (entry, setup done, first TMA issued, first operands landed, last MMA
+ * committed, epilogue start / end, exit).  NULL (the default) disables it.  Not thread safe; never used on the hot path. */
+VBG_API int vbg_debug_set_timeline(long long* dev_buf);
 /* out[i] = float(hi[i]) + float(lo[i])  (inspection / tests: split activation -> fp32) */
 VBG_API int vbg_merge_bf16(const void* hi, const void* lo, long long n, float* out, vbg_stream_t stream);
 /* NHWC convolution as implicit GEMM: y[B,Ho,Wo,Cout] = epilogue(conv(x[B,H,W,Cin], w[Cout,kh,kw,Cin])) */

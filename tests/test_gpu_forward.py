@@ -191,3 +191,32 @@ def test_full_size_tensor_core_vs_exact_fp32_path(name, batch, tmp_path, monkeyp
         assert torch.equal(a["pred_label"], b["pred_label"])          # identical Viterbi paths
     else:
         assert torch.equal(a["pred_label"].argmax(1), b["pred_label"].argmax(1))
+
+
+def test_two_stream_forward_equals_single_stream_and_prefetcher(tmp_path, monkeypatch):
+    """The fork/join of the forward over two streams (BERT || early backbone, seg head || ROI path) only reorders independent
+    kernels: outputs are bit-identical to the single-stream order, eagerly and under graph replay.  DevicePrefetcher yields
+    the same batches in order."""
+    from vibertgrid_pytorch_b200.prefetch import DevicePrefetcher
+    fx = load_golden("tiny_simp")
+    monkeypatch.chdir(tmp_path)
+    cfg, kw, net, batch = build_case(fx["meta"])
+    net = net.cuda().eval()
+    eng = net._get_engine()
+    ref = None
+    for multi in (False, True):
+        eng.multi_stream = multi
+        eng.invalidate()
+        outs = []
+        for dev_batch in DevicePrefetcher([batch, batch, batch], torch.device("cuda")):     # eager, capture, replay
+            res = net(*dev_batch)
+            outs.append([t.clone() for t in res] + [net.last_intermediates["logits"].clone(), net.last_intermediates["p_fuse"].clone()])
+        torch.cuda.synchronize()
+        for o in outs[1:]:
+            for a, b in zip(o, outs[0]):
+                assert torch.equal(a, b)
+        if ref is None:
+            ref = outs[0]
+        else:
+            for a, b in zip(outs[0], ref):
+                assert torch.equal(a, b)

@@ -53,6 +53,7 @@ SIGNATURES = {
     "vbg_gemm": [_p, _i, _p, _i, _i, _p, _i, _p, _ll, _p, _i, _i, _i, _i, _EP, _i, _p],
     "vbg_gemm_ps": [_p, _ll, _i, _p, _ll, _i, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _EP, _p],
     "vbg_conv2d_ps": [_p, _ll, _i, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p, _EP, _p],
+    "vbg_debug_set_timeline": [_p],
     "vbg_merge_bf16": [_p, _p, _ll, _p, _p],
     "vbg_conv2d": [_p, _i, _i, _i, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _EP, _i, _p],
     "vbg_split_bf16": [_p, _ll, _p, _p, _p],

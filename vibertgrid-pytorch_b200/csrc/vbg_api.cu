@@ -209,6 +209,12 @@ extern "C" int vbg_conv2d_ps(const void* x_hi, long long x_plane, int B, int H, 
   return rc;
 }
 
+namespace vbg { void tc_debug_set_timeline(long long* buf); }
+extern "C" int vbg_debug_set_timeline(long long* dev_buf) {
+  tc_debug_set_timeline(dev_buf);
+  return VBG_OK;
+}
+
 extern "C" int vbg_merge_bf16(const void* hi, const void* lo, long long n, float* out, vbg_stream_t stream) {
   VBG_REQUIRE(hi && lo && out && n >= 0, "vbg_merge_bf16: bad arguments");
   return merge_bf16(hi, lo, n, out, as_stream(stream));

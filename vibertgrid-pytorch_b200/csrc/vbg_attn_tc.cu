@@ -23,6 +23,7 @@
 namespace vbg {
 
 constexpr int kAtThreads = 160;
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 constexpr uint32_t kTileQ = 128 * 128;       // one bf16 operand tile of 128 rows x 64 elements
 constexpr uint32_t kVtTile = 64 * 128;       // V^T tile: 64 d-rows x 64 keys (bf16)
 
@@ -151,6 +152,7 @@ attention_tc_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ c
     }
     // --- phase C: probabilities and V^T, 64 keys per unit
     float sum = 0.f;
+    const float m_scaled = m * scale_log2e;
     const uint32_t xr = (uint32_t)(r & 7);
     const int vkey = t & 63, vd0 = (t >> 6) * 32;
     for (int u = 0; u < n_units; ++u) {
@@ -185,12 +187,23 @@ attention_tc_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ c
         const int c0 = u * 64 + half * 32;
         tmem_ld32(lane_addr + (uint32_t)c0, v);
         uint32_t hi[16], lo[16];
+        if (c0 + 32 <= len) {                     // CTA-uniform fast path: arguments are <= 0, ex2.approx underflows to 0
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float pa = (c0 + 2 * j < len) ? exp2f((__uint_as_float(v[2 * j]) - m) * scale_log2e) : 0.f;
-          const float pb = (c0 + 2 * j + 1 < len) ? exp2f((__uint_as_float(v[2 * j + 1]) - m) * scale_log2e) : 0.f;
-          sum += pa + pb;
-          split2(pa, pb, hi[j], lo[j]);
+          for (int j = 0; j < 16; ++j) {
+            const float pa = ex2_approx(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled));
+            const float pb = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled));
+            sum += pa + pb;
+            split2(pa, pb, hi[j], lo[j]);
+          }
+        } else {                                  // chunk holding the sequence end: masked keys get exponent -inf -> p = 0
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float xa = (c0 + 2 * j < len) ? fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled) : -INFINITY;
+            const float xb = (c0 + 2 * j + 1 < len) ? fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled) : -INFINITY;
+            const float pa = ex2_approx(xa), pb = ex2_approx(xb);
+            sum += pa + pb;
+            split2(pa, pb, hi[j], lo[j]);
+          }
         }
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
@@ -242,7 +255,8 @@ __global__ void __launch_bounds__(kAt2Threads, 1)
 attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_constant__ CUtensorMap tmQKl,
                        const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
                        const int32_t* __restrict__ cu, int heads, float scale_log2e, void* __restrict__ out,
-                       long long out_plane) {
+                       long long out_plane, long long* __restrict__ dbg) {
+#define AT_STAMP(slot) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) dbg[slot] = clock64(); } while (0)
   const int seq = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * 128;
   const int row0 = cu[seq], len = cu[seq + 1] - row0;
   if (q0 >= len) return;
@@ -262,6 +276,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
   float* xch = reinterpret_cast<float*>(bars + 14);             // [2][128] row max / row sum exchange between the groups
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) AT_STAMP(0);
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmQKh); prefetch_tmap(&tmQKl); prefetch_tmap(&tmVh); prefetch_tmap(&tmVl); }
   if (warp == 1) {
     if (lane == 0) {
@@ -283,6 +298,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       // ===== TMA producer
+      AT_STAMP(1);
       mbar_expect_tx(q_full, 2 * kTileQ);
       tma_load_2d(&tmQKh, q_full, q_op, head * 64, row0 + q0);
       tma_load_2d(&tmQKl, q_full, q_op + kTileQ, head * 64, row0 + q0);
@@ -310,6 +326,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
       constexpr uint32_t idesc_o = make_idesc(kFmtBF16, 128, 64, /*b_mn_major=*/1);
       const uint64_t q1 = make_sw128_desc(smem_u32(q_op)), q2 = make_sw128_desc(smem_u32(q_op + kTileQ));
       mbar_wait(q_full, 0);
+      AT_STAMP(2);
       for (int c = 0; c < n_chunks; ++c) {
         const int b = c & 1;
         mbar_wait(&k_full[b], (c >> 1) & 1);
@@ -326,6 +343,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
         umma_commit(&k_empty[b]);
       }
       umma_commit(s_full);
+      AT_STAMP(3);
       for (int u = 0; u < n_units; ++u) {
         const int b = u & 1;
         const uint32_t ph = (u >> 1) & 1;
@@ -346,6 +364,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
         umma_commit(&pv_done[b]);
       }
       umma_commit(o_full);
+      AT_STAMP(4);
     }
   } else {
     // ===== softmax: two groups of 4 warps (one warp of each group per scheduler, so TMEM-load and exp latencies of one
@@ -354,6 +373,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
     const int r = q * 32 + lane;
     mbar_wait(s_full, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) AT_STAMP(5);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     float m = -INFINITY;
     for (int c = grp; c < n_chunks; c += 2) {
@@ -361,31 +381,52 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
       for (int c0 = c * 128; c0 < c * 128 + 128; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(lane_addr + (uint32_t)c0, v);
+        if (c0 + 32 <= len) {                     // CTA-uniform: interior chunks carry no key mask (no predicate chains)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (c0 + j < len) m = fmaxf(m, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, (c0 + j < len) ? __uint_as_float(v[j]) : -INFINITY);
+        }
       }
     }
     xch[grp * 128 + r] = m;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     m = fmaxf(xch[r], xch[128 + r]);
     asm volatile("bar.sync 1, 256;" ::: "memory");               // xch is reused for the row sums below
+    if (threadIdx.x == 64) AT_STAMP(6);
     float sum = 0.f;
+    const float m_scaled = m * scale_log2e;       // p = 2^(s * scale - m * scale): one FFMA + one MUFU.EX2 per element
     const uint32_t xr = (uint32_t)(r & 7);
     uint8_t* p1 = p_op + grp * 2 * kTileQ + (uint32_t)r * 128u;
     for (int u = grp, it = 0; u < n_units; u += 2, ++it) {
       if (it >= 1) mbar_wait(&pv_done[grp], (it - 1) & 1);
+      uint32_t vv[2][32];                         // both 32-column halves of the unit in flight, one wait
+      tmem_ld32_nowait(lane_addr + (uint32_t)(u * 64), vv[0]);
+      tmem_ld32_nowait(lane_addr + (uint32_t)(u * 64 + 32), vv[1]);
+      tmem_wait_ld();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
+        uint32_t (&v)[32] = vv[half];
         const int c0 = u * 64 + half * 32;
-        tmem_ld32(lane_addr + (uint32_t)c0, v);
         uint32_t hi[16], lo[16];
+        if (c0 + 32 <= len) {                     // CTA-uniform fast path: arguments are <= 0, ex2.approx underflows to 0
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float pa = (c0 + 2 * j < len) ? exp2f((__uint_as_float(v[2 * j]) - m) * scale_log2e) : 0.f;
-          const float pb = (c0 + 2 * j + 1 < len) ? exp2f((__uint_as_float(v[2 * j + 1]) - m) * scale_log2e) : 0.f;
-          sum += pa + pb;
-          split2(pa, pb, hi[j], lo[j]);
+          for (int j = 0; j < 16; ++j) {
+            const float pa = ex2_approx(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled));
+            const float pb = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled));
+            sum += pa + pb;
+            split2(pa, pb, hi[j], lo[j]);
+          }
+        } else {                                  // chunk holding the sequence end: masked keys get exponent -inf -> p = 0
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float xa = (c0 + 2 * j < len) ? fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled) : -INFINITY;
+            const float xb = (c0 + 2 * j + 1 < len) ? fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled) : -INFINITY;
+            const float pa = ex2_approx(xa), pb = ex2_approx(xb);
+            sum += pa + pb;
+            split2(pa, pb, hi[j], lo[j]);
+          }
         }
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
@@ -401,29 +442,48 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
     xch[grp * 128 + r] = sum;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     sum = xch[r] + xch[128 + r];
+    if (threadIdx.x == 64) AT_STAMP(7);
     mbar_wait(o_full, 0);
     tc_fence_after();
+    if (threadIdx.x == 64) AT_STAMP(8);
     const float inv = __fdiv_rn(1.0f, sum);
     const size_t o4 = ((size_t)(row0 + q0 + r) * hidden + head * 64 + grp * 32) >> 2;   // group g stores dims [32g, 32g+32)
     {
       uint32_t v[32];
       tmem_ld32(lane_addr + (uint32_t)(grp * 32), v);
       if (q0 + r < len) {
+        if (out_plane > 0) {                      // bf16 planes: 16-byte stores (8 elements), full 32-byte sectors per thread
+          uint4* hp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + o4 * 4);
+          uint4* lp = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + out_plane + o4 * 4);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          st4_fmt(out, out_plane, o4 + j,
-                  make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
-                              __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv));
+          for (int j = 0; j < 4; ++j) {
+            uint4 h, l;
+            split2(__uint_as_float(v[8 * j]) * inv, __uint_as_float(v[8 * j + 1]) * inv, h.x, l.x);
+            split2(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv, h.y, l.y);
+            split2(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv, h.z, l.z);
+            split2(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv, h.w, l.w);
+            hp[j] = h; lp[j] = l;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st4_fmt(out, out_plane, o4 + j,
+                    make_float4(__uint_as_float(v[4 * j]) * inv, __uint_as_float(v[4 * j + 1]) * inv,
+                                __uint_as_float(v[4 * j + 2]) * inv, __uint_as_float(v[4 * j + 3]) * inv));
+        }
       }
     }
   }
 
   tc_fence_before();
+  if (threadIdx.x == 64) AT_STAMP(9);
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (lane == 0) AT_STAMP(10);
   }
+#undef AT_STAMP
 }
 
 int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len, int heads,
@@ -448,7 +508,7 @@ int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int 
     attr = true;
   }
   dim3 grid(cdiv(max_len, 128), heads, nseq);
-  attention_split_kernel<<<grid, kAt2Threads, smem, s>>>(mq[0], mq[1], mv[0], mv[1], cu, heads, 0.125f * 1.4426950408889634f, out, out_plane);
+  attention_split_kernel<<<grid, kAt2Threads, smem, s>>>(mq[0], mq[1], mv[0], mv[1], cu, heads, 0.125f * 1.4426950408889634f, out, out_plane, tc_debug_timeline());
   return check_launch("vbg_attention_split_fwd(tcgen05)");
 }
 

@@ -241,6 +241,7 @@ gemm_ps2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int pm_tiles = (p.m_tiles + 1) >> 1;                          // pairs of 128-row tiles
   const int n_tiles = pm_tiles * p.n_tiles;
+  if (threadIdx.x == 0) tc_stamp(p, 0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmW);
@@ -260,8 +261,10 @@ gemm_ps2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();                          // both CTAs' barriers are initialised before any remote arrive / complete_tx
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) tc_stamp(p, 1);
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (threadIdx.x == 0) tc_stamp(p, 2);
 
   // this CTA's 128-row tile inside pair tile pt
   auto my_tile = [&](int pt) {
@@ -310,6 +313,7 @@ gemm_ps2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           tma2_load_3d(&tmW, bar, sb, kb * KB, nb, 0);
           tma2_load_3d(&tmW, bar, sb + B_BYTES, kb * KB, nb, 1);
+          if (g == 0) tc_stamp(p, 3);
         }
       }
     }
@@ -327,6 +331,7 @@ gemm_ps2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int s = g % STAGES;
           mbar_wait(&full[s], (g / STAGES) & 1);
           tc_fence_after();
+          if (g == 0) tc_stamp(p, 4);
           const uint32_t base = smem_u32(ring + s * STAGE_BYTES);
           const uint64_t a1 = ps_desc<KB>(base), a2 = ps_desc<KB>(base + A_BYTES);
           const uint64_t w1 = ps_desc<KB>(base + 2 * A_BYTES), w2 = ps_desc<KB>(base + 2 * A_BYTES + B_BYTES);
@@ -340,6 +345,7 @@ gemm_ps2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           umma2_commit_both(&empty[s]);
         }
         umma2_commit_both(&tmem_full[acc]);
+        if (it == 0) tc_stamp(p, 5);
       }
     }
   } else {
@@ -351,17 +357,21 @@ gemm_ps2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const TcTile t = my_tile(pt);
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
+      if (it == 0 && threadIdx.x == 64) tc_stamp(p, 6);
       tc_epilogue<BN>(p, t, tmem_base + (uint32_t)(acc * BN), q, lane, epi + (warp - 2) * kEpiStageFloats, half * 32, 64);
       tc_fence_before();
+      if (it == 0 && threadIdx.x == 64) tc_stamp(p, 7);
       mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0));
     }
   }
 
   tc_fence_before();
+  if (threadIdx.x == 0) tc_stamp(p, 8);
   cluster_sync_all();                          // the peer's smem / TMEM / barriers stay alive until both CTAs are done
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if (lane == 0) tc_stamp(p, 9);
   }
 }
 
@@ -458,8 +468,13 @@ static bool use_pairs(int m_tiles, int n_tiles_1cta, int N, int num_kb) {
   return m_tiles >= 2 && N >= 192 && num_kb >= 8 && (long long)m_tiles * n_tiles_1cta >= 96;
 }
 
+static long long* g_timeline = nullptr;
+long long* tc_debug_timeline() { return g_timeline; }
+void tc_debug_set_timeline(long long* buf) { g_timeline = buf; }
+
 static int dispatch_ps(const CUtensorMap& a, const CUtensorMap& a2, const void* w_hi, long long w_plane, int ldw, int K, TcParams& p,
                        int m_tiles, int kb, cudaStream_t s) {
+  p.dbg = g_timeline;
   const int bn = pick_bn3(m_tiles, p.N);
   CUtensorMap w;
   p.m_tiles = m_tiles; p.n_tiles = cdiv(p.N, bn);

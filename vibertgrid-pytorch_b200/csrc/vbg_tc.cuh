@@ -76,6 +76,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// the same load without the wait: issue several, then tmem_wait_ld() once
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (tile base 1024-B aligned):
 //   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (=64: 8 rows x 128 B)
 //   [46,48) version = 1 (Blackwell) | [61,64) layout = 2 (SWIZZLE_128B)
@@ -128,7 +142,13 @@ struct TcParams {
   int sw, sh;      // TMA start-coordinate stride of the output tile origin along W / H
   int pad_w, pad_h;
   vbg_epilogue_t ep;
+  long long* dbg;  // optional device buffer for clock64 stamps of CTA 0 (vbg_debug_set_timeline); nullptr in production
 };
+
+__device__ __forceinline__ void tc_stamp(const TcParams& p, int slot) {
+  if (p.dbg && blockIdx.x == 0) p.dbg[slot] = clock64();
+}
+long long* tc_debug_timeline();
 
 struct TcTile { int m0, n0, w0, h0, b0; };
 

@@ -76,6 +76,9 @@ class ForwardEngine:
         self.fuse_aux_loss = os.environ.get("VBG_FUSED_AUX_LOSS", "1") != "0"
         # bf16x3 only: keep activations as bf16 hi/lo planes between the tensor-core kernels (no in-kernel conversion)
         self.presplit = os.environ.get("VBG_PRESPLIT", "1") != "0"
+        # run the two independent branches of the forward (BERT || early backbone, seg head || ROI path) on two streams
+        self.multi_stream = os.environ.get("VBG_STREAMS", "2") != "1"
+        self._side = {}
         self.max_graphs = 8
         self._graphs: Dict[tuple, dict] = {}
         self.graph_replays = 0
@@ -168,6 +171,12 @@ class ForwardEngine:
 
     def _ps(self):
         return self.presplit and self._prec() == PREC_BF16X3
+
+    def _side_stream(self, dev):
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        if key not in self._side:
+            self._side[key] = torch.cuda.Stream(dev)
+        return self._side[key]
 
     @staticmethod
     def _tc_shape(N, K):
@@ -289,7 +298,9 @@ class ForwardEngine:
                               lyr.output.LayerNorm.eps, out=o if (last or not ps) else None, split=ps and not last)
         return x
 
-    def _backbone(self, img, grid):
+    def _backbone_pre(self, img):
+        """Stem .. first block of stage 3 (conv_3_x.block_1 / layer2[0]): everything before the early fusion, i.e. the part
+        of the backbone that does not depend on the BERTgrid and can run beside the BERT encoder."""
         bb = self.net.backbone
         if bb.pretrained_layout:
             r = bb.resnet
@@ -297,6 +308,17 @@ class ForwardEngine:
             for blk in r.layer1:
                 x1 = self._tv_block(x1, blk)
             x2 = self._tv_block(x1, r.layer2[0])
+        else:
+            x1 = ops.maxpool3x3s2(self._stem(img, bb.conv_1[0], bb.conv_1[1]), split_out=self._ps())
+            for blk in bb.conv_2_x:
+                x1 = self._our_block(x1, blk)
+            x2 = self._our_block(x1, bb.conv_3_x.block_1)
+        return x1, x2
+
+    def _backbone_post(self, x1, x2, grid):
+        bb = self.net.backbone
+        if bb.pretrained_layout:
+            r = bb.resnet
             x2 = self._early_fusion(x2, grid, bb.early_fusion)
             for blk in list(r.layer2)[1:]:
                 x2 = self._tv_block(x2, blk)
@@ -307,10 +329,6 @@ class ForwardEngine:
             for blk in r.layer4:
                 x4 = self._tv_block(x4, blk)
         else:
-            x1 = ops.maxpool3x3s2(self._stem(img, bb.conv_1[0], bb.conv_1[1]), split_out=self._ps())
-            for blk in bb.conv_2_x:
-                x1 = self._our_block(x1, blk)
-            x2 = self._our_block(x1, bb.conv_3_x.block_1)
             x2 = self._early_fusion(x2, grid, bb.conv_3_x.early_fusion)
             for blk in bb.conv_3_x.layers:
                 x2 = self._our_block(x2, blk)
@@ -426,36 +444,56 @@ class ForwardEngine:
         status = torch.zeros(1, dtype=torch.int32, device=dev)
         out = Intermediates({"plan": plan, "status": status})
 
-        # a1 transform
+        # Two independent branches run on two streams and join where the reference's data flow joins them (in a captured
+        # graph these are parallel branches): every tensor-core kernel here is persistent with one CTA per SM, so a single
+        # stream leaves SMs idle during each kernel's ramp-up and tail; a second stream's CTAs fill those slots.
+        #   fork 1:  side = BERT encoder -> segment mean -> index map -> BERTgrid      main = transform -> stem .. stage-3 block 1
+        #   fork 2:  side = auxiliary segmentation head (+ its loss kernel)             main = ROI-align -> late fusion -> heads
+        main = torch.cuda.current_stream(dev) if dev.type == "cuda" else None
+        side = self._side_stream(dev) if (main is not None and self.multi_stream) else None
+        ps = self._ps()
+        corpus, seg_ids = st["corpus"], st["seg_ids"]
+        gs = net.early_fusion_downsampling_ratio
+
+        # a1 transform (coords first: both branches read the boxes)
+        boxes = ops.resize_coords(st["coors"], seg_off, dt["ratios"], B)
+        out["boxes"] = boxes
+
+        def bert_branch():
+            # a2 / a3 BERT + segment aggregation, a4 BERTgrid
+            hidden = self._bert(plan, dt, corpus)
+            seg_start = ops.segment_starts(seg_ids, dt["tok_off"], B, plan.K, status)
+            seg_emb = ops.segment_reduce(hidden, dt["tok_row"], seg_start, plan.K,
+                                         ops.AGG_MEAN if net.grid_mode == "mean" else ops.AGG_FIRST)
+            out["seg_emb"] = seg_emb
+            idx = ops.box_index_map(boxes, seg_off, B, gs, int(plan.H / gs), int(plan.W / gs))
+            seg_emb_s = ops.to_split(seg_emb) if ps else None      # [K, 768]: scatter source and late-fusion operand
+            out["seg_emb_split"] = seg_emb_s                       # kept alive: crosses streams
+            out["index_map"], out["bertgrid"] = idx, ops.grid_scatter(seg_emb_s if ps else seg_emb, idx, seg_off)
+
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                bert_branch()
+        else:
+            bert_branch()
         batch = torch.zeros((B, plan.H + 6, plan.W + 6, 4), dtype=torch.float32, device=dev)   # zero-bordered NHWC4 stem input
         for b, im in enumerate(st["image"]):
             ops.normalize_resize_pad(im, batch, b, plan.sizes[b][0], plan.sizes[b][1], net.image_mean, net.image_std)
-        boxes = ops.resize_coords(st["coors"], seg_off, dt["ratios"], B)
-        out["image_batch"], out["boxes"] = batch[:, 3:-3, 3:-3, :3], boxes     # view without border / pad channel
-        corpus, seg_ids = st["corpus"], st["seg_ids"]
+        out["image_batch"] = batch[:, 3:-3, 3:-3, :3]              # view without border / pad channel
+        x1, x2 = self._backbone_pre(batch)                         # a5, the part before the early fusion
+        if side is not None:
+            main.wait_stream(side)
+        seg_emb, seg_emb_s, grid = out["seg_emb"], dict.__getitem__(out, "seg_emb_split"), dict.__getitem__(out, "bertgrid")
 
-        # a2 / a3 BERT + segment aggregation
-        hidden = self._bert(plan, dt, corpus)
-        seg_start = ops.segment_starts(seg_ids, dt["tok_off"], B, plan.K, status)
-        seg_emb = ops.segment_reduce(hidden, dt["tok_row"], seg_start, plan.K,
-                                     ops.AGG_MEAN if net.grid_mode == "mean" else ops.AGG_FIRST)
-        out["seg_emb"] = seg_emb
-
-        # a4 BERTgrid
-        gs = net.early_fusion_downsampling_ratio
-        idx = ops.box_index_map(boxes, seg_off, B, gs, int(plan.H / gs), int(plan.W / gs))
-        ps = self._ps()
-        seg_emb_s = ops.to_split(seg_emb) if ps else None      # [K, 768]: scatter source and late-fusion operand
-        grid = ops.grid_scatter(seg_emb_s if ps else seg_emb, idx, seg_off)
-        out["index_map"], out["bertgrid"] = idx, grid
-
-        # a5 backbone
-        p_fuse = self._backbone(batch, grid)
+        # a5 backbone from the early fusion on
+        p_fuse = self._backbone_post(x1, x2, grid)
         out["p_fuse"] = p_fuse
 
         # a6 auxiliary segmentation head
-        if want_seg:
+        def seg_branch():
             out["pred_mask"], out["pred_ss"], lg = self._seg_head(p_fuse)
+            out["seg_logits_lowres"] = lg
             cls_cat = st["cls"]
             if self.fuse_aux_loss and self._aux_loss_is_default():
                 # labels are consumed in registers by the fused CE kernel; the int64 label maps are never written
@@ -464,6 +502,14 @@ class ForwardEngine:
             else:
                 out["pos_neg_labels"], out["class_labels"] = ops.label_paint(boxes, seg_off, cls_cat, B, plan.H, plan.W)
             out["gt_label"] = cls_cat
+
+        if want_seg:
+            if side is not None:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    seg_branch()
+            else:
+                seg_branch()
 
         # a7 ROI align, a8 late fusion
         roi = ops.roi_align(p_fuse, boxes, seg_off, 1.0 / float(net.p_fuse_downsampling_ratio), net.roi_shape, split_out=ps)
@@ -499,4 +545,6 @@ class ForwardEngine:
                                 for i in range(net.num_tokens - 1)], 1).contiguous()
             out["pos_neg_logits"], out["logits"] = pn, cl
             out["pred_label"] = ops.full_head_scores(pn.reshape(-1).contiguous(), cl)
+        if side is not None and want_seg:
+            main.wait_stream(side)
         return out
