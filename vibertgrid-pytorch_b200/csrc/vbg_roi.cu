@@ -14,6 +14,9 @@
 
 namespace vbg {
 
+long long* tc_debug_timeline();
+static long long* roi_debug_timeline() { return tc_debug_timeline(); }
+
 template <int kVec>  // float4 vectors per lane (C = 128 * kVec)
 __global__ void __launch_bounds__(256)
 roi_align_kernel(const void* __restrict__ feat, long long feat_plane, int B, int Hf, int Wf, int C,
@@ -180,19 +183,30 @@ roi_align_sep_kernel(const float* __restrict__ feat, int B, int Hf, int Wf, int 
 // ------------------------------------------------------------------ windowed form (the default)
 // One CTA per (ROI, 64-channel chunk).  The feature window the ROI's samples can touch -- rows [y_lo, y_hi] x columns
 // [x_lo, x_hi] -- is staged ONCE into shared memory with coalesced 256-byte reads (either storage format, merged to fp32
-// on the way in), then every (bin, channel-quad) item accumulates its gh x gw samples from shared memory in exactly the
-// direct kernel's operation order (same sample-grid table, same summation order => identical values).  HBM / L2 -> SM
-// traffic per ROI drops from (samples x 4 taps x C) per bin -- ~24 KB per 1 KB of output at line-sized boxes -- to the
-// window itself.  ROIs whose window does not fit `win_floats` fall back to global taps inside the same kernel.
-constexpr int kRoiCh = 64, kRoiCq = kRoiCh / 4, kRoiTab = 7 * 24;
+// on the way in), then every (bin, channel-quad) item accumulates from shared memory with per-bin SEPARABLE weight tables
+// (see below: each window pixel is read once per bin it contributes to, not once per sample tap).  HBM / L2 -> SM traffic
+// per ROI drops from (samples x 4 taps x C) per bin -- ~24 KB per 1 KB of output at line-sized boxes -- to the window
+// itself.  ROIs whose window does not fit `win_floats` fall back to per-sample global taps inside the same kernel.
+constexpr int kRoiCh = 64, kRoiCq = kRoiCh / 4, kRoiP = 8, kRoiSpan = 32;
 
 __global__ void __launch_bounds__(256)
 roi_align_win_kernel(const void* __restrict__ feat, long long feat_plane, int B, int Hf, int Wf, int C,
                      const int32_t* __restrict__ boxes, const int32_t* __restrict__ seg_off, float scale, int P,
-                     void* __restrict__ out, long long out_plane, int32_t* __restrict__ sample_grid, int win_floats) {
+                     void* __restrict__ out, long long out_plane, int32_t* __restrict__ sample_grid, int win_floats,
+                     long long* __restrict__ dbg) {
+#define ROI_STAMP(slot) do { if (dbg && blockIdx.x == 2000 && threadIdx.x == 0) dbg[slot] = clock64(); } while (0)
   extern __shared__ __align__(16) float win[];
-  const int k = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
-  const int b = sample_of(seg_off, B, k);
+  ROI_STAMP(0);
+  // the channel chunks of one ROI are neighbouring CTAs: they run together, so each 512-byte pixel row is fetched once
+  const int nchunk = C / kRoiCh, k = blockIdx.x / nchunk, chunk = blockIdx.x - k * nchunk, tid = threadIdx.x;
+  int b;
+  if (B <= 31) {       // one load latency instead of a dependent binary search: lane i holds seg_off[i]; b = #(seg_off[1..B-1] <= k)
+    const int lane = tid & 31;
+    const int so = (lane >= 1 && lane < B) ? __ldg(seg_off + lane) : 0x7fffffff;
+    b = __popc(__ballot_sync(0xffffffffu, so <= k));
+  } else {
+    b = sample_of(seg_off, B, k);
+  }
   const int4 bx = __ldg(reinterpret_cast<const int4*>(boxes) + k);
   const float sw = __fmul_rn((float)bx.x, scale), sh = __fmul_rn((float)bx.y, scale);
   const float ew = __fmul_rn((float)bx.z, scale), eh = __fmul_rn((float)bx.w, scale);
@@ -215,71 +229,135 @@ roi_align_win_kernel(const void* __restrict__ feat, long long feat_plane, int B,
 
   const int C4 = C >> 2;
   const size_t f0 = (size_t)b * Hf * Wf * C4 + (size_t)chunk * kRoiCq;
-  // per-axis sample tables (one entry per (bin, sample) coordinate): the coordinate arithmetic -- two IEEE divisions and the
-  // clamp / skip rules per sample -- is done once per ROI instead of once per (bin, channel-quad, sample)
-  __shared__ int4 tab_y[kRoiTab], tab_x[kRoiTab];      // (valid, low tap, high tap, bits of the low-side weight l)
-  const bool tabled = staged && P * gh <= kRoiTab && P * gw <= kRoiTab;
-  if (tabled) {
-    for (int i = tid; i < P * gh + P * gw; i += 256) {
-      const bool is_y = i < P * gh;
-      const int j = is_y ? i : i - P * gh;
-      const int g = is_y ? gh : gw, dim = is_y ? Hf : Wf, lo_w = is_y ? y_lo : x_lo, hi_w = is_y ? y_hi : x_hi;
-      const float start = is_y ? sh : sw, bin = is_y ? bh : bw;
-      const int pb = j / g, is = j - pb * g;
-      float c = __fadd_rn(__fadd_rn(start, __fmul_rn((float)pb, bin)), __fdiv_rn(__fmul_rn((float)is + 0.5f, bin), (float)g));
-      const int valid = !(c < -1.0f || c > (float)dim);
-      c = fmaxf(c, 0.f);
-      int lo = (int)c, hi;
-      if (lo >= dim - 1) { hi = lo = dim - 1; c = (float)lo; } else { hi = lo + 1; }
-      const float l = c - (float)lo;
-      const int4 e = make_int4(valid, min(max(lo, lo_w), hi_w) - lo_w, min(max(hi, lo_w), hi_w) - lo_w, __float_as_int(l));
-      if (is_y) tab_y[j] = e; else tab_x[j] = e;
+  // Separable form: bilinear weights factor (w = wy * wx) and so do the skip / clamp rules, hence
+  //   out[ph,pw,c] = 1/count * sum_j Wy[ph][j] * ( sum_i Wx[pw][i] * f[y0+j][x0+i][c] )
+  // with Wy[ph][.] / Wx[pw][.] the per-bin sums of the samples' row / column weights.  The tables are built once per ROI
+  // (same coordinate arithmetic, operation for operation, as the direct kernel: the sample-grid table stays bit-exact);
+  // every feature value is then read once per bin it contributes to, not once per sample tap.  Values differ from
+  // torchvision's summation order by fp32 re-association only (<= 1e-6 rel).
+  __shared__ float wtab[2][kRoiP][kRoiSpan];
+  __shared__ int t_start[2][kRoiP], t_cnt[2][kRoiP];
+  __shared__ int t_ok;
+  ROI_STAMP(1);
+  const bool try_tab = staged && P <= kRoiP;
+  if (try_tab) {
+    if (tid == 0) t_ok = 1;
+    for (int i = tid; i < 2 * kRoiP * kRoiSpan; i += 256) (&wtab[0][0][0])[i] = 0.f;
+    __syncthreads();
+    if (tid < 2 * P) {
+      const int axis = tid / P, pb = tid - axis * P;            // axis 0: x (columns), 1: y (rows)
+      const int g = axis ? gh : gw, dim = axis ? Hf : Wf, lo_w = axis ? y_lo : x_lo, hi_w = axis ? y_hi : x_hi;
+      const float start = axis ? sh : sw, bin = axis ? bh : bw;
+      float* w = wtab[axis][pb];
+      int base = 0, cnt = 0, ok = 1;
+      for (int i = 0; i < g; ++i) {
+        float c = __fadd_rn(__fadd_rn(start, __fmul_rn((float)pb, bin)), __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)g));
+        if (c < -1.0f || c > (float)dim) continue;
+        c = fmaxf(c, 0.f);
+        int lo = (int)c, hi;
+        if (lo >= dim - 1) { hi = lo = dim - 1; c = (float)lo; } else { hi = lo + 1; }
+        const float l = c - (float)lo, h = 1.f - l;
+        if (cnt == 0) base = lo;
+        if (hi - base >= kRoiSpan || lo < base || lo < lo_w || hi > hi_w) { ok = 0; break; }   // span / window assumptions
+        w[lo - base] += h;
+        w[hi - base] += l;
+        cnt = hi - base + 1;
+      }
+      t_start[axis][pb] = base - lo_w;
+      t_cnt[axis][pb] = cnt;
+      if (!ok) t_ok = 0;
     }
+    __syncthreads();
   }
+  const bool tabled = try_tab && t_ok;
+  ROI_STAMP(2);
   if (staged) {
-    // 16 lanes cover one pixel's 64 channels (256 contiguous bytes); a thread walks pixels slot, slot + 16, ... and keeps
-    // four loads in flight (the window load is latency-bound otherwise: ~9 dependent round trips per CTA)
+    // Window load with cp.async: every 8 / 16-byte piece is issued before anything is waited for (the register-staged
+    // version exposed one DRAM round trip per batch of 4 loads: 12.5 us per CTA, ncu: 41 % of stalls on the merge right
+    // after the loads).  16 lanes cover one pixel's 64 channels; pixel p of the window lives at win + p * 64 floats.
+    // fp32 source: 16-byte copies straight into place.  bf16-plane source: the hi / lo halves of the pixel (128 B each) land
+    // in the two halves of the pixel's 256 bytes and are merged to fp32 in place afterwards.
     const int cq = tid & (kRoiCq - 1), slot = tid >> 4, npix = rows * cols;
-    int y = slot / cols, x = slot - y * cols;
-    for (int pix = slot; pix < npix; pix += 64) {
-      float4 v[4]; int px[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        px[u] = pix + 16 * u;
-        if (px[u] < npix) v[u] = ld4_fmt(feat, feat_plane, f0 + ((size_t)(y_lo + y) * Wf + (x_lo + x)) * C4 + cq);
+    const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(win);
+    {
+      int y = slot / cols, x = slot - y * cols;
+      for (int pix = slot; pix < npix; pix += 16) {
+        const size_t g4 = f0 + ((size_t)(y_lo + y) * Wf + (x_lo + x)) * C4 + cq;       // index in units of 4 elements
+        const uint32_t dst = win_s + (uint32_t)pix * 256u;
+        if (feat_plane == 0) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)cq * 16u),
+                       "l"(reinterpret_cast<const float4*>(feat) + g4) : "memory");
+        } else {
+          const uint2* hp = reinterpret_cast<const uint2*>(feat) + g4;
+          const uint2* lp = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(feat) + feat_plane) + g4;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (uint32_t)cq * 8u), "l"(hp) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 128u + (uint32_t)cq * 8u), "l"(lp) : "memory");
+        }
         x += 16;
         while (x >= cols) { x -= cols; ++y; }
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (px[u] < npix) reinterpret_cast<float4*>(win)[px[u] * kRoiCq + cq] = v[u];
+    }
+    ROI_STAMP(3);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    ROI_STAMP(4);
+    if (feat_plane != 0) {
+      // in-place merge: a half-warp owns one pixel; all 16 lanes read their hi / lo pieces before any of them writes
+      // (the loop trip count is warp-uniform up to the last pass, so the full-mask __syncwarp is reached by every lane)
+      const int passes = (npix + 15) >> 4;
+      for (int it = 0; it < passes; ++it) {
+        const int pix = slot + 16 * it;
+        uint2 h = make_uint2(0u, 0u), l = h;
+        uint8_t* base = reinterpret_cast<uint8_t*>(win) + (size_t)pix * 256;
+        if (pix < npix) {
+          h = *reinterpret_cast<const uint2*>(base + cq * 8);
+          l = *reinterpret_cast<const uint2*>(base + 128 + cq * 8);
+        }
+        __syncwarp();
+        if (pix < npix) *reinterpret_cast<float4*>(base + cq * 16) = merge4(h, l);
+        __syncwarp();
+      }
     }
     __syncthreads();
   }
 
+  ROI_STAMP(5);
   const int items = P * P * kRoiCq;
   for (int item = tid; item < items; item += 256) {
     const int bin = item / kRoiCq, cq = item - bin * kRoiCq;
     const int ph = bin / P, pw = bin - ph * P;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tabled) {
-      const float4* w4p = reinterpret_cast<const float4*>(win) + cq;
-      for (int iy = 0; iy < gh; ++iy) {
-        const int4 ey = tab_y[ph * gh + iy];
-        if (!ey.x) continue;
-        const float ly = __int_as_float(ey.w), hy = 1.f - ly;
-        const float4* r0p = w4p + ey.y * cols * kRoiCq;
-        const float4* r1p = w4p + ey.z * cols * kRoiCq;
-        for (int ix = 0; ix < gw; ++ix) {
-          const int4 ex = tab_x[pw * gw + ix];
-          if (!ex.x) continue;
-          const float lx = __int_as_float(ex.w), hx = 1.f - lx;
-          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-          const float4 a = r0p[ex.y * kRoiCq], bb = r0p[ex.z * kRoiCq], cc = r1p[ex.y * kRoiCq], d = r1p[ex.z * kRoiCq];
-          acc.x += w1 * a.x + w2 * bb.x + w3 * cc.x + w4 * d.x;
-          acc.y += w1 * a.y + w2 * bb.y + w3 * cc.y + w4 * d.y;
-          acc.z += w1 * a.z + w2 * bb.z + w3 * cc.z + w4 * d.z;
-          acc.w += w1 * a.w + w2 * bb.w + w3 * cc.w + w4 * d.w;
+      const int y0 = t_start[1][ph], ny = t_cnt[1][ph], x0 = t_start[0][pw], nx = t_cnt[0][pw];
+      const float* wy = wtab[1][ph];
+      const float* wx = wtab[0][pw];
+      const float4* base4 = reinterpret_cast<const float4*>(win) + ((size_t)y0 * cols + x0) * kRoiCq + cq;
+      if (nx > 0 && nx <= 4) {
+        // the common case (bins narrower than 3 px): four independent taps per row, weights hoisted out of the row loop;
+        // taps beyond nx re-read the last valid column with weight 0
+        const float w0 = wx[0], w1 = nx > 1 ? wx[1] : 0.f, w2 = nx > 2 ? wx[2] : 0.f, w3 = nx > 3 ? wx[3] : 0.f;
+        const int o1 = min(1, nx - 1) * kRoiCq, o2 = min(2, nx - 1) * kRoiCq, o3 = min(3, nx - 1) * kRoiCq;
+        for (int j = 0; j < ny; ++j) {
+          const float4* rowp = base4 + (size_t)j * cols * kRoiCq;
+          const float4 v0 = rowp[0], v1 = rowp[o1], v2 = rowp[o2], v3 = rowp[o3];
+          const float wj = wy[j];
+          float4 t;
+          t.x = fmaf(w3, v3.x, fmaf(w2, v2.x, fmaf(w1, v1.x, w0 * v0.x)));
+          t.y = fmaf(w3, v3.y, fmaf(w2, v2.y, fmaf(w1, v1.y, w0 * v0.y)));
+          t.z = fmaf(w3, v3.z, fmaf(w2, v2.z, fmaf(w1, v1.z, w0 * v0.z)));
+          t.w = fmaf(w3, v3.w, fmaf(w2, v2.w, fmaf(w1, v1.w, w0 * v0.w)));
+          acc.x = fmaf(wj, t.x, acc.x); acc.y = fmaf(wj, t.y, acc.y); acc.z = fmaf(wj, t.z, acc.z); acc.w = fmaf(wj, t.w, acc.w);
+        }
+      } else {
+        for (int j = 0; j < ny; ++j) {
+          const float4* rowp = base4 + (size_t)j * cols * kRoiCq;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < nx; ++i) {
+            const float w = wx[i];
+            const float4 v = rowp[i * kRoiCq];
+            t.x = fmaf(w, v.x, t.x); t.y = fmaf(w, v.y, t.y); t.z = fmaf(w, v.z, t.z); t.w = fmaf(w, v.w, t.w);
+          }
+          const float wj = wy[j];
+          acc.x = fmaf(wj, t.x, acc.x); acc.y = fmaf(wj, t.y, acc.y); acc.z = fmaf(wj, t.z, acc.z); acc.w = fmaf(wj, t.w, acc.w);
         }
       }
     } else {
@@ -319,6 +397,8 @@ roi_align_win_kernel(const void* __restrict__ feat, long long feat_plane, int B,
     acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
     st4_fmt(out, out_plane, ((size_t)k * P * P + bin) * C4 + (size_t)chunk * kRoiCq + cq, acc);
   }
+  ROI_STAMP(6);
+#undef ROI_STAMP
 }
 
 }  // namespace vbg
@@ -362,9 +442,9 @@ extern "C" int vbg_roi_align_x(const void* feat, long long feat_plane, int B, in
       if (e != cudaSuccess) { set_error("vbg_roi_align_fwd: smem opt-in failed: %s", cudaGetErrorString(e)); return VBG_ECUDA; }
       attr = true;
     }
-    roi_align_win_kernel<<<dim3(K, C / kRoiCh), 256, win_floats * sizeof(float), s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off,
+    roi_align_win_kernel<<<(unsigned)((long long)K * (C / kRoiCh)), 256, win_floats * sizeof(float), s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off,
                                                                                        spatial_scale, P, out, out_plane, sample_grid,
-                                                                                       win_floats);
+                                                                                       win_floats, roi_debug_timeline());
     return check_launch("vbg_roi_align_fwd");
   }
   long long warps = (long long)K * P * P;
