@@ -208,7 +208,7 @@ def test_two_stream_forward_equals_single_stream_and_prefetcher(tmp_path, monkey
         eng.multi_stream = multi
         eng.invalidate()
         outs = []
-        for dev_batch in DevicePrefetcher([batch, batch, batch], torch.device("cuda")):     # eager, capture, replay
+        for dev_batch in DevicePrefetcher([batch] * 8, torch.device("cuda")):     # eager, capture, replays; ring slots reused
             res = net(*dev_batch)
             outs.append([t.clone() for t in res] + [net.last_intermediates["logits"].clone(), net.last_intermediates["p_fuse"].clone()])
         torch.cuda.synchronize()

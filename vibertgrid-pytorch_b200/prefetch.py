@@ -19,25 +19,60 @@ def _map(batch, fn):
 
 
 class DevicePrefetcher:
-    def __init__(self, batches, device):
+    """Uploads into a small ring of persistent device buffers (one ring per batch signature) instead of allocating per batch:
+    tensors allocated on a side stream and recorded on the compute stream cannot be reused by the caching allocator until
+    their cross-stream events retire, which turned every upload into fresh cudaMallocs (measured: 7.7 ms of host time per
+    batch against 0.2 ms for the copies themselves).  A slot is overwritten only after an event recorded on the compute
+    stream once the consumer has asked for a later batch, i.e. after all work on the slot's batch has been enqueued."""
+
+    def __init__(self, batches, device, depth=3):
         self.batches = batches
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("DevicePrefetcher uploads to a CUDA device")
+        self.depth = max(2, int(depth))
+        self._rings = {}
+
+    @staticmethod
+    def _sig(batch):
+        return tuple(tuple((tuple(t.shape), t.dtype) for t in x) if isinstance(x, (tuple, list)) else (tuple(x.shape), x.dtype)
+                     for x in batch)
+
+    def _next_slot(self, batch):
+        ring = self._rings.setdefault(self._sig(batch), {"slots": [], "n": 0})
+        idx = ring["n"] % self.depth
+        ring["n"] += 1
+        if idx >= len(ring["slots"]):
+            # fresh memory from the caching allocator may still be read by kernels already queued on the compute stream
+            # (the allocator orders reuse only within a stream): the first upload waits for the compute stream's present tail
+            free = torch.cuda.Event()
+            free.record(torch.cuda.current_stream(self.device))
+            ring["slots"].append({"t": _map(batch, lambda t: torch.empty(t.shape, dtype=t.dtype, device=self.device)), "free": free})
+        return ring["slots"][idx]
 
     def _upload(self, batch, stream):
+        slot = self._next_slot(batch)
+        if slot["free"] is not None:
+            stream.wait_event(slot["free"])             # the consumer's kernels on this slot's previous batch are done
         with torch.cuda.stream(stream):
-            dev = _map(batch, lambda t: t.to(self.device, non_blocking=True))
+            for dst, src in zip(slot["t"], batch):
+                if isinstance(dst, tuple):
+                    for d, s_ in zip(dst, src):
+                        d.copy_(s_, non_blocking=True)
+                else:
+                    dst.copy_(src, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(stream)
-        return dev, ev
+        return slot, ev
 
-    def _hand_over(self, item):
-        dev, ev = item
+    def _hand_over(self, item, prev_slot):
+        slot, ev = item
         cur = torch.cuda.current_stream(self.device)
+        if prev_slot is not None:                       # everything the consumer does with the previous batch is enqueued by now
+            prev_slot["free"] = torch.cuda.Event()
+            prev_slot["free"].record(cur)
         cur.wait_event(ev)
-        _map(dev, lambda t: t.record_stream(cur))       # allocated on the copy stream, consumed on the compute stream
-        return dev
+        return slot
 
     def __iter__(self):
         stream = torch.cuda.Stream(self.device)
@@ -46,11 +81,14 @@ class DevicePrefetcher:
             nxt = self._upload(next(it), stream)
         except StopIteration:
             return
+        prev = None
         for b in it:
-            cur = self._hand_over(nxt)
+            cur = self._hand_over(nxt, prev)
             nxt = self._upload(b, stream)               # in flight while the caller computes on `cur`
-            yield cur
-        yield self._hand_over(nxt)
+            yield cur["t"]
+            prev = cur
+        last = self._hand_over(nxt, prev)
+        yield last["t"]
 
 
 class HostResultQueue:
