@@ -168,10 +168,18 @@ VBG_API int vbg_gemm(const float* A, int lda, const float* A2, int lda2, int K1,
  * VBG_OUT_SPLIT_BF16, bf16 planes; ep->res_plane > 0 reads the residual from planes too.                          */
 VBG_API int vbg_gemm_ps(const void* A_hi, long long a_plane, int lda, const void* A2_hi, long long a2_plane, int lda2, int K1,
                 const void* W_hi, long long w_plane, int ldw, void* C, int ldc, int M, int N, int K,
-                const vbg_epilogue_t* ep, vbg_stream_t stream);
+                const vbg_epilogue_t* ep, void* workspace, size_t ws_bytes, vbg_stream_t stream);
 /* implicit-GEMM convolution over a split NHWC activation (Cin % 64 == 0, Cout >= 64, stride 1 or 2) */
 VBG_API int vbg_conv2d_ps(const void* x_hi, long long x_plane, int B, int H, int W, int Cin, const void* w_hi, long long w_plane,
-                  int Cout, int kh, int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, vbg_stream_t stream);
+                  int Cout, int kh, int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, void* workspace,
+                  size_t ws_bytes, vbg_stream_t stream);
+/* Split-K: a shape with few output tiles and a long K (the 16x16 / 32x32 ResNet stages, the ROI FC) is computed as
+ * (tile, K-range) work units whose fp32 partial tiles go to `workspace` and are summed in a fixed order by a finishing
+ * kernel that applies the epilogue (deterministic).  These return the workspace bytes such a call can use (0 = the shape
+ * never splits); passing NULL / fewer bytes just disables the split.  Host-only arithmetic, no device work.  Opt-in via
+ * VBG_PS_SPLITK=1 (measured slower than the CTA-pair tiles at the BASELINE shapes, so off by default: these return 0). */
+VBG_API long long vbg_gemm_ps_workspace(int M, int N, int K);
+VBG_API long long vbg_conv2d_ps_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad);
 /* Tuning aid: when dev_buf (>= 16 int64, device memory) is non-NULL, CTA 0 of every following CTA-pair GEMM launch writes
  * clock64 stamps of its pipeline milestones into it (entry, setup done, first TMA issued, first operands landed, last MMA
  * committed, epilogue start / end, exit).  NULL (the default) disables it.  Not thread safe; never used on the hot path. */

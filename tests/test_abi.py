@@ -12,7 +12,7 @@ from vibertgrid_pytorch_b200 import _lib
 
 def _header_symbols():
     with open(os.path.join(ROOT, "include", "vbg.h")) as f:
-        return re.findall(r"^VBG_API int (vbg_\w+)\(", f.read(), flags=re.M)
+        return re.findall(r"^VBG_API (?:int|long long) (vbg_\w+)\(", f.read(), flags=re.M)
 
 
 def test_library_loads_and_exports_every_declared_symbol():

@@ -484,3 +484,49 @@ def test_format_aware_memory_kernels(ops):
     rs, gs = ops.roi_align(ops.to_split(feat), boxes, doff, 0.25, 7, want_grid=True, split_out=True)
     assert torch.equal(g32, gs)
     assert relerr(rs.float().cpu().numpy(), r32.cpu().numpy()) < 2 * tol
+
+
+@pytest.mark.parametrize("M,N,K", [(2048, 512, 4608), (1024, 1024, 12544), (640, 256, 2304), (300, 512, 1024)])
+def test_gemm_presplit_split_k(ops, monkeypatch, M, N, K):
+    """Under-filled shapes run as (tile, K-range) work units + a deterministic finishing kernel: same result as the unsplit
+    kernel up to fp32 re-association of the K sum, residual / activation / plane output applied once at the end."""
+    from vibertgrid_pytorch_b200 import _lib
+    monkeypatch.setenv("VBG_PS_SPLITK", "1")
+    assert _lib.load().vbg_gemm_ps_workspace(M, N, K) > 0, "shape expected to split"
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g); Wt = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g); res = torch.randn(M, N, generator=g)
+    Wd = Wt.cuda(); Ws = ops.split_bf16(Wd); As = ops.to_split(A.cuda()); rs = ops.to_split(res.cuda())
+    outs = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VBG_PS_SPLITK", flag)
+        mk = lambda: ops.make_epilogue(None, bias.cuda(), rs, ops.RES_SAME, ldr=N, act=ops.ACT_RELU)   # gemm(split_out) edits its ep
+        outs[flag] = (ops.gemm(As, Wd, ep=mk(), precision=ops.PREC_BF16X3, W_split=Ws, split_out=True).float().cpu(),
+                      ops.gemm(As, Wd, ep=mk(), precision=ops.PREC_BF16X3, W_split=Ws).cpu())
+    want3 = F.relu(_bf16x3_product(A, Wt) + bias + _merged(res))
+    for flag in ("0", "1"):
+        assert relerr(outs[flag][1].numpy(), want3.numpy()) < (1e-5 if K <= 3072 else 6e-5), flag
+        assert relerr(outs[flag][0].numpy(), want3.numpy()) < (3e-5 if K <= 3072 else 7e-5), flag
+    again = ops.gemm(As, Wd, ep=ops.make_epilogue(None, bias.cuda(), rs, ops.RES_SAME, ldr=N, act=ops.ACT_RELU),
+                     precision=ops.PREC_BF16X3, W_split=Ws).cpu()
+    assert torch.equal(again, outs["1"][1]), "split-K must be deterministic"
+
+
+def test_conv2d_presplit_split_k(ops, monkeypatch):
+    B, H, W, Cin, Cout = 8, 16, 16, 512, 512
+    from vibertgrid_pytorch_b200 import _lib
+    monkeypatch.setenv("VBG_PS_SPLITK", "1")
+    assert _lib.load().vbg_conv2d_ps_workspace(B, H, W, Cin, Cout, 3, 3, 1, 1) > 0
+    g = torch.Generator().manual_seed(99)
+    x = torch.randn(B, Cin, H, W, generator=g); w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    scale = torch.rand(Cout, generator=g) + 0.5; shift = torch.randn(Cout, generator=g); res = torch.randn(B, Cout, H, W, generator=g)
+    want = F.relu(F.conv2d(_merged(x).double(), _merged(w).double(), None, 1, 1) * scale[None, :, None, None]
+                  + shift[None, :, None, None] + _merged(res))
+    w_ohwi = ops.repack_oihw_to_ohwi(w.cuda()); ws = ops.split_bf16(w_ohwi)
+    xs = ops.to_split(x.permute(0, 2, 3, 1).contiguous().cuda()); rs = ops.to_split(res.permute(0, 2, 3, 1).contiguous().cuda())
+    got = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("VBG_PS_SPLITK", flag)
+        ep = ops.make_epilogue(scale.cuda(), shift.cuda(), rs, ops.RES_SAME, ldr=Cout, act=ops.ACT_RELU)
+        got[flag] = ops.conv2d(xs, w_ohwi, 1, 1, ep=ep, precision=ops.PREC_BF16X3, W_split=ws, split_out=True).float().permute(0, 3, 1, 2).cpu()
+        assert relerr(got[flag].numpy(), want.numpy()) < 3e-5

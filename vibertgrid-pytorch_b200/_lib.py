@@ -51,8 +51,10 @@ SIGNATURES = {
     "vbg_label_paint": [_p, _p, _p, _i, _i, _i, _p, _p, _p],
     "vbg_seg_ce_loss": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p],
     "vbg_gemm": [_p, _i, _p, _i, _i, _p, _i, _p, _ll, _p, _i, _i, _i, _i, _EP, _i, _p],
-    "vbg_gemm_ps": [_p, _ll, _i, _p, _ll, _i, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _EP, _p],
-    "vbg_conv2d_ps": [_p, _ll, _i, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p, _EP, _p],
+    "vbg_gemm_ps": [_p, _ll, _i, _p, _ll, _i, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _EP, _p, _sz, _p],
+    "vbg_conv2d_ps": [_p, _ll, _i, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p, _EP, _p, _sz, _p],
+    "vbg_gemm_ps_workspace": [_i, _i, _i],
+    "vbg_conv2d_ps_workspace": [_i, _i, _i, _i, _i, _i, _i, _i, _i],
     "vbg_debug_set_timeline": [_p],
     "vbg_merge_bf16": [_p, _p, _ll, _p, _p],
     "vbg_conv2d": [_p, _i, _i, _i, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _EP, _i, _p],
@@ -90,7 +92,7 @@ def load():
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here == ABI drift, by design
         fn.argtypes = args
-        fn.restype = C.c_int
+        fn.restype = C.c_longlong if name.endswith("_workspace") else C.c_int
     _lib = lib
     return lib
 

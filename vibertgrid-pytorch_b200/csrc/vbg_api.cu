@@ -31,9 +31,12 @@ int stem_tc3(const float* x4, int B, int H, int W, const void* w_split, long lon
 int split_bf16(const float* w, long long n, void* hi, void* lo, cudaStream_t s);
 int merge_bf16(const void* hi, const void* lo, long long n, float* out, cudaStream_t s);
 int gemm_ps(const void* A, long long a_plane, int lda, const void* A2, long long a2_plane, int lda2, int K1, const void* w_hi,
-            long long w_plane, int ldw, void* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep, cudaStream_t s);
+            long long w_plane, int ldw, void* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep, void* workspace,
+            size_t ws_bytes, cudaStream_t s);
 int conv_ps(const void* x, long long x_plane, int B, int H, int W, int Cin, const void* w_hi, long long w_plane, int Cout, int kh,
-            int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, cudaStream_t s);
+            int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, void* workspace, size_t ws_bytes, cudaStream_t s);
+size_t ps_workspace_bytes(int m_tiles, long long M, int N, int K);
+size_t conv_ps_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad);
 bool tc_available();
 
 // ------------------------------------------------------------------ CRF Viterbi (model/crf.py:96-146)
@@ -172,7 +175,7 @@ extern "C" int vbg_conv2d(const float* x, int B, int H, int W, int Cin, const fl
 
 extern "C" int vbg_gemm_ps(const void* A_hi, long long a_plane, int lda, const void* A2_hi, long long a2_plane, int lda2, int K1,
                            const void* W_hi, long long w_plane, int ldw, void* C, int ldc, int M, int N, int K,
-                           const vbg_epilogue_t* ep, vbg_stream_t stream) {
+                           const vbg_epilogue_t* ep, void* workspace, size_t ws_bytes, vbg_stream_t stream) {
   VBG_REQUIRE(A_hi && W_hi && C, "vbg_gemm_ps: null pointer");
   VBG_REQUIRE(M >= 0 && N > 0 && K > 0 && K1 > 0 && K1 <= K, "vbg_gemm_ps: bad shape M=%d N=%d K=%d K1=%d", M, N, K, K1);
   VBG_REQUIRE((K1 == K) || A2_hi, "vbg_gemm_ps: A2 required when K1 < K");
@@ -184,7 +187,8 @@ extern "C" int vbg_gemm_ps(const void* A_hi, long long a_plane, int lda, const v
                 "vbg_gemm_ps: VBG_RES_UP2 needs even out_h/out_w dividing M");
   if (ep && ep->res_mode == VBG_RES_SAME) VBG_REQUIRE(ep->ldr >= N, "vbg_gemm_ps: ldr too small");
   if (M == 0) return VBG_OK;
-  rc = gemm_ps(A_hi, a_plane, lda, A2_hi, a2_plane, lda2, K1, W_hi, w_plane, ldw, C, ldc, M, N, K, ep, as_stream(stream));
+  rc = gemm_ps(A_hi, a_plane, lda, A2_hi, a2_plane, lda2, K1, W_hi, w_plane, ldw, C, ldc, M, N, K, ep, workspace, ws_bytes,
+               as_stream(stream));
   if (rc == VBG_EUNSUPPORTED)
     set_error("vbg_gemm_ps: needs sm_100a, N >= 64, K %% 64 == 0, K1 %% 64 == 0, lda/ldw %% 8 == 0, 16B-aligned planes with plane %% 8 == 0 "
               "(M=%d N=%d K=%d K1=%d)", M, N, K, K1);
@@ -192,7 +196,8 @@ extern "C" int vbg_gemm_ps(const void* A_hi, long long a_plane, int lda, const v
 }
 
 extern "C" int vbg_conv2d_ps(const void* x_hi, long long x_plane, int B, int H, int W, int Cin, const void* w_hi, long long w_plane,
-                             int Cout, int kh, int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, vbg_stream_t stream) {
+                             int Cout, int kh, int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, void* workspace,
+                             size_t ws_bytes, vbg_stream_t stream) {
   VBG_REQUIRE(x_hi && w_hi && y, "vbg_conv2d_ps: null pointer");
   VBG_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0, "vbg_conv2d_ps: bad geometry");
   VBG_REQUIRE(H + 2 * pad >= kh && W + 2 * pad >= kw, "vbg_conv2d_ps: kernel larger than padded input");
@@ -202,7 +207,7 @@ extern "C" int vbg_conv2d_ps(const void* x_hi, long long x_plane, int B, int H, 
     int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
     VBG_REQUIRE(Ho % 2 == 0 && Wo % 2 == 0, "vbg_conv2d_ps: VBG_RES_UP2 needs even output dims");
   }
-  rc = conv_ps(x_hi, x_plane, B, H, W, Cin, w_hi, w_plane, Cout, kh, kw, stride, pad, y, ep, as_stream(stream));
+  rc = conv_ps(x_hi, x_plane, B, H, W, Cin, w_hi, w_plane, Cout, kh, kw, stride, pad, y, ep, workspace, ws_bytes, as_stream(stream));
   if (rc == VBG_EUNSUPPORTED)
     set_error("vbg_conv2d_ps: needs sm_100a, Cin %% 64 == 0, Cout >= 64, stride 1 or 2, 16B-aligned planes (Cin=%d Cout=%d stride=%d)",
               Cin, Cout, stride);
@@ -213,6 +218,15 @@ namespace vbg { void tc_debug_set_timeline(long long* buf); }
 extern "C" int vbg_debug_set_timeline(long long* dev_buf) {
   tc_debug_set_timeline(dev_buf);
   return VBG_OK;
+}
+
+extern "C" long long vbg_gemm_ps_workspace(int M, int N, int K) {
+  return (M > 0 && N > 0 && K > 0) ? (long long)ps_workspace_bytes(cdiv(M, 128), M, N, K) : 0;
+}
+
+extern "C" long long vbg_conv2d_ps_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad) {
+  if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0) return 0;
+  return (long long)conv_ps_workspace_bytes(B, H, W, Cin, Cout, kh, kw, stride, pad);
 }
 
 extern "C" int vbg_merge_bf16(const void* hi, const void* lo, long long n, float* out, vbg_stream_t stream) {

@@ -28,9 +28,16 @@ constexpr int kPsThreads = 320;                  // warp 0 TMA, warp 1 MMA, warp
 constexpr uint32_t kPsEpiBytes = 8 * kEpiStageFloats * 4;
 constexpr int kPsDefaultKB = 64;
 
-__device__ __forceinline__ TcTile ps_tile(const TcParams& p, int tile, int bn) {
+__device__ __forceinline__ TcTile ps_tile(const TcParams& p, int unit, int bn) {
+  const int n_tiles = p.m_tiles * p.n_tiles;
+  const int tile = unit % n_tiles, split = unit / n_tiles;       // the splits of a tile run in different waves' worth of CTAs
   const int xt = tile % p.m_tiles;             // m fastest: CTAs running together share the weight tile
-  TcTile t{0, (tile / p.m_tiles) * bn, 0, 0, 0};
+  TcTile t{0, (tile / p.m_tiles) * bn, 0, 0, 0, 0, p.num_kb, 0};
+  if (p.splits > 1) {
+    t.kb0 = split * p.kb_per_split;
+    t.kb1 = min(t.kb0 + p.kb_per_split, p.num_kb);
+    t.row_shift = (long long)split * p.M;
+  }
   if (p.conv) {
     int i = xt;
     t.w0 = (i % p.tiles_w) * p.tw; i /= p.tiles_w;
@@ -63,7 +70,7 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = p.m_tiles * p.n_tiles;
+  const int n_tiles = p.m_tiles * p.n_tiles * (p.splits > 1 ? p.splits : 1);      // work units
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmW);
@@ -97,7 +104,7 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int g = 0;                                                       // K blocks issued so far (runs through tiles)
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const TcTile t = ps_tile(p, tile, BN);
-        for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+        for (int kb = t.kb0; kb < t.kb1; ++kb, ++g) {
           const int s = g % STAGES;
           mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
           uint8_t* sa = ring + s * STAGE_BYTES;
@@ -131,7 +138,8 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);             // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < p.num_kb; ++kb, ++g) {
+        const TcTile t = ps_tile(p, tile, BN);
+        for (int kb = t.kb0; kb < t.kb1; ++kb, ++g) {
           const int s = g % STAGES;
           mbar_wait(&full[s], (g / STAGES) & 1);
           tc_fence_after();
@@ -141,7 +149,7 @@ gemm_ps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < KB / 16; ++k) {          // 16 bf16 = 32 B per MMA: +2 in the (addr>>4) field
             const uint64_t o = (uint64_t)(2 * k);
-            umma_bf16(d, a1 + o, w1 + o, idesc, (kb | k) != 0);
+            umma_bf16(d, a1 + o, w1 + o, idesc, (kb != t.kb0) || (k != 0));
             umma_bf16(d, a2 + o, w1 + o, idesc, 1);
             umma_bf16(d, a1 + o, w2 + o, idesc, 1);
           }
@@ -270,7 +278,7 @@ gemm_ps2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto my_tile = [&](int pt) {
     const int pm = pt % pm_tiles, nt = pt / pm_tiles;
     const int xt = 2 * pm + (int)rank;         // may be == m_tiles for the odd tail: every load is then out of bounds (zero
-    TcTile t{0, nt * BN, 0, 0, 0};             // fill) and every epilogue row is masked
+    TcTile t{0, nt * BN, 0, 0, 0, 0, p.num_kb, 0};   // fill) and every epilogue row is masked
     if (p.conv) {
       int i = xt;
       t.w0 = (i % p.tiles_w) * p.tw; i /= p.tiles_w;
@@ -375,6 +383,42 @@ gemm_ps2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------ split-K finish
+// out[m, n] = epilogue( sum_s ws[s][m][n] ), splits added in a fixed order (deterministic, unlike fp32 atomics): the partial
+// accumulators of an under-filled GEMM (few output tiles, long K) come from `splits` work units that ran on different SMs.
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ ws, int splits, long long M, int N, vbg_epilogue_t ep, void* __restrict__ C, int ldc) {
+  const int N4 = N >> 2;
+  const long long total = M * N4, plane = M * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / N4;
+    const int n = (int)(i - m * N4) * 4;
+    float4 a = __ldg(reinterpret_cast<const float4*>(ws + m * N + n));
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(ws + s * plane + m * N + n));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.scale) sc = __ldg(reinterpret_cast<const float4*>(ep.scale + n));
+    if (ep.shift) sh = __ldg(reinterpret_cast<const float4*>(ep.shift + n));
+    float4 o = make_float4(fmaf(a.x, sc.x, sh.x), fmaf(a.y, sc.y, sh.y), fmaf(a.z, sc.z, sh.z), fmaf(a.w, sc.w, sh.w));
+    if (ep.residual) {
+      long long r;
+      if (ep.res_mode == VBG_RES_UP2) {
+        const int wo = (int)(m % ep.out_w); const long long u = m / ep.out_w;
+        const int ho = (int)(u % ep.out_h); const long long b = u / ep.out_h;
+        r = ((b * (ep.out_h >> 1) + (ho >> 1)) * (ep.out_w >> 1) + (wo >> 1)) * (long long)N + n;
+      } else {
+        r = m * ep.ldr + n;
+      }
+      const float4 rv = ld4_fmt(ep.residual, ep.res_plane, (size_t)(r >> 2));
+      o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+    }
+    o.x = apply_act(o.x, ep.act); o.y = apply_act(o.y, ep.act); o.z = apply_act(o.z, ep.act); o.w = apply_act(o.w, ep.act);
+    st4_fmt(C, ep.out_mode == VBG_OUT_SPLIT_BF16 ? ep.out_plane : 0, (size_t)((m * ldc + n) >> 2), o);
+  }
+}
+
 // ------------------------------------------------------------------ split -> fp32 (inspection / tests)
 __global__ void merge_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long n,
                                   float* __restrict__ out) {
@@ -426,6 +470,10 @@ static int launch_ps(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
 
 int pick_bn3(int m_tiles, int N);
 
+static long long* g_timeline = nullptr;
+long long* tc_debug_timeline() { return g_timeline; }
+void tc_debug_set_timeline(long long* buf) { g_timeline = buf; }
+
 template <int BN, int KB, int STAGES>
 static int launch_ps2(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMap& w, const TcParams& p, cudaStream_t s) {
   constexpr size_t smem = (size_t)STAGES * (2 * BM * KB * 2 + 2 * (BN / 2) * KB * 2) + kPsEpiBytes + 1024 + 256;
@@ -468,17 +516,53 @@ static bool use_pairs(int m_tiles, int n_tiles_1cta, int N, int num_kb) {
   return m_tiles >= 2 && N >= 192 && num_kb >= 8 && (long long)m_tiles * n_tiles_1cta >= 96;
 }
 
-static long long* g_timeline = nullptr;
-long long* tc_debug_timeline() { return g_timeline; }
-void tc_debug_set_timeline(long long* buf) { g_timeline = buf; }
+// Single-CTA tiles: N tile width and split-K factor chosen together.  An under-filled grid (layer-3/4 convs at 32x32 / 16x16,
+// the ROI FC: 8 - 64 row tiles) used to shrink BN to get more CTAs, which quadruples the A traffic per FLOP; splitting K
+// instead keeps wide tiles and fills the SMs with (tile, split) work units.  Needs a workspace of splits * M * N floats.
+static void pick_bn_splits(int m_tiles, int N, int num_kb, bool allow_split, int* bn_out, int* splits_out) {
+  static const int forced_bn = [] { const char* e = getenv("VBG_TC3_BN"); return e ? atoi(e) : 0; }();
+  // Opt-in (VBG_PS_SPLITK=1): measured on B200 at cfg2 the split form (single-CTA units + finishing kernel) is SLOWER than
+  // the narrow CTA-pair tiles it replaces (6.67 vs 6.37 ms/step) -- kept, with its parity tests, as a tuning experiment.
+  const char* es = getenv("VBG_PS_SPLITK");
+  if (!(es && es[0] == '1')) allow_split = false;
+  const int cand[4] = {256, 192, 128, 64};
+  const int scand[6] = {1, 2, 3, 4, 6, 8};
+  int best_bn = 64, best_s = 1; double best = -1.0;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    if (forced_bn && bn != forced_bn) continue;
+    if (bn > 64 && N < bn - 32) continue;
+    for (int j = 0; j < 6; ++j) {
+      const int sp = scand[j];
+      if (sp > 1 && (!allow_split || num_kb / sp < 8 || (N & 3))) break;
+      const long long units = (long long)m_tiles * cdiv(N, bn) * sp;
+      const double waves = (double)units / kNumSMs;
+      const double wave_eff = waves / (double)((units + kNumSMs - 1) / kNumSMs);
+      const double fill = (double)N / ((double)cdiv(N, bn) * bn);
+      const double tile_eff = (double)bn / (bn + 96.0);
+      const double kb_unit = (double)num_kb / sp;
+      const double split_eff = sp == 1 ? 1.0 : kb_unit / (kb_unit + 6.0);          // per-unit ramp / drain + the finishing pass
+      const double score = wave_eff * fill * tile_eff * split_eff;
+      if (score > best) { best = score; best_bn = bn; best_s = sp; }
+    }
+  }
+  *bn_out = best_bn; *splits_out = best_s;
+}
 
 static int dispatch_ps(const CUtensorMap& a, const CUtensorMap& a2, const void* w_hi, long long w_plane, int ldw, int K, TcParams& p,
-                       int m_tiles, int kb, cudaStream_t s) {
+                       int m_tiles, int kb, void* workspace, size_t ws_bytes, cudaStream_t s) {
   p.dbg = g_timeline;
-  const int bn = pick_bn3(m_tiles, p.N);
+  p.splits = 1; p.kb_per_split = p.num_kb;
   CUtensorMap w;
-  p.m_tiles = m_tiles; p.n_tiles = cdiv(p.N, bn);
-  if (kb == 64 && use_pairs(m_tiles, p.n_tiles, p.N, p.num_kb)) {
+  p.m_tiles = m_tiles;
+  int bn = 64, splits = 1;
+  const bool ws_ok = workspace && aligned16(workspace);
+  pick_bn_splits(m_tiles, p.N, p.num_kb, ws_ok, &bn, &splits);
+  // a grid that stays under one wave even with the widest tile is a split-K case, not a pair case
+  const bool underfilled = (long long)m_tiles * cdiv(p.N, 256) * 2 <= kNumSMs;
+  if (!(underfilled && splits > 1)) {
+  const int bn_pairs_probe = pick_bn3(m_tiles, p.N);
+  if (kb == 64 && use_pairs(m_tiles, cdiv(p.N, bn_pairs_probe), p.N, p.num_kb)) {
     // pair tiles: same (wave efficiency x column fill x tile efficiency) score as pick_bn3, over clusters of two SMs
     const int pm_tiles = (m_tiles + 1) / 2, n_cl = kNumSMs / 2;
     const int cand[4] = {256, 192, 128, 64};
@@ -499,23 +583,58 @@ static int dispatch_ps(const CUtensorMap& a, const CUtensorMap& a2, const void* 
     if (b2 == 128) return launch_ps2<128, 64, 4>(a, a2, w, p, s);
     return launch_ps2<64, 64, 4>(a, a2, w, p, s);
   }
-  if (!map_ps_2d(&w, w_hi, w_plane, p.N, K, ldw, bn, kb)) return VBG_EUNSUPPORTED;
-  if (kb == 64) {
-    if (bn == 256) return launch_ps<256, 64, 2>(a, a2, w, p, s);
-    if (bn == 192) return launch_ps<192, 64, 2>(a, a2, w, p, s);
-    if (bn == 128) return launch_ps<128, 64, 3>(a, a2, w, p, s);
-    return launch_ps<64, 64, 4>(a, a2, w, p, s);
   }
-  if (bn == 256) return launch_ps<256, 32, 4>(a, a2, w, p, s);
-  if (bn == 192) return launch_ps<192, 32, 4>(a, a2, w, p, s);
-  if (bn == 128) return launch_ps<128, 32, 6>(a, a2, w, p, s);
-  return launch_ps<64, 32, 8>(a, a2, w, p, s);
+  if (splits > 1) {
+    const int per = cdiv(p.num_kb, splits);
+    splits = cdiv(p.num_kb, per);                                   // no empty split
+    if (splits < 2 || (size_t)splits * (size_t)p.M * (size_t)p.N * 4 > ws_bytes) splits = 1;
+    else p.kb_per_split = per;
+  }
+  if (splits == 1) pick_bn_splits(m_tiles, p.N, p.num_kb, false, &bn, &splits);
+  if (!map_ps_2d(&w, w_hi, w_plane, p.N, K, ldw, bn, kb)) return VBG_EUNSUPPORTED;
+  p.n_tiles = cdiv(p.N, bn);
+  TcParams q = p;                                                   // what the GEMM kernel sees
+  if (splits > 1) {
+    q.splits = splits;
+    q.C = reinterpret_cast<float*>(workspace); q.ldc = p.N;
+    q.ep = vbg_epilogue_t{};                                        // raw fp32 partial accumulators
+  }
+  int rc;
+  if (kb == 64) {
+    if (bn == 256) rc = launch_ps<256, 64, 2>(a, a2, w, q, s);
+    else if (bn == 192) rc = launch_ps<192, 64, 2>(a, a2, w, q, s);
+    else if (bn == 128) rc = launch_ps<128, 64, 3>(a, a2, w, q, s);
+    else rc = launch_ps<64, 64, 4>(a, a2, w, q, s);
+  } else {
+    if (bn == 256) rc = launch_ps<256, 32, 4>(a, a2, w, q, s);
+    else if (bn == 192) rc = launch_ps<192, 32, 4>(a, a2, w, q, s);
+    else if (bn == 128) rc = launch_ps<128, 32, 6>(a, a2, w, q, s);
+    else rc = launch_ps<64, 32, 8>(a, a2, w, q, s);
+  }
+  if (rc != VBG_OK || splits == 1) return rc;
+  const long long total4 = (long long)p.M * (p.N / 4);
+  int blocks = (int)((total4 + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  splitk_finish_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float*>(workspace), splits, p.M, p.N, p.ep, p.C, p.ldc);
+  return check_launch("vbg_gemm_ps(split-K finish)");
+}
+
+// Workspace a caller should provide so that under-filled shapes may split K (0: the shape never splits).
+size_t ps_workspace_bytes(int m_tiles, long long M, int N, int K) {
+  if (K % 64 || N < 64 || (N & 3)) return 0;
+  const int num_kb = K / 64;
+  int bn, splits;
+  pick_bn_splits(m_tiles, N, num_kb, true, &bn, &splits);
+  const bool underfilled = (long long)m_tiles * cdiv(N, 256) * 2 <= kNumSMs;
+  if (!(underfilled && splits > 1) && use_pairs(m_tiles, cdiv(N, pick_bn3(m_tiles, N)), N, num_kb)) return 0;
+  return splits > 1 ? (size_t)splits * (size_t)M * (size_t)N * 4 : 0;
 }
 
 static bool planes_ok(const void* p, long long plane) { return p && aligned16(p) && plane > 0 && (plane % 8) == 0; }
 
 int gemm_ps(const void* A, long long a_plane, int lda, const void* A2, long long a2_plane, int lda2, int K1, const void* w_hi,
-            long long w_plane, int ldw, void* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep, cudaStream_t s) {
+            long long w_plane, int ldw, void* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep, void* workspace,
+            size_t ws_bytes, cudaStream_t s) {
   if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
   if (N < 64 || K % 64 || K1 % 64 || (lda & 7) || (ldw & 7) || !planes_ok(A, a_plane) || !planes_ok(w_hi, w_plane)) return VBG_EUNSUPPORTED;
   if (K1 < K && ((lda2 & 7) || !planes_ok(A2, a2_plane))) return VBG_EUNSUPPORTED;
@@ -526,14 +645,21 @@ int gemm_ps(const void* A, long long a_plane, int lda, const void* A2, long long
   TcParams p{};
   p.C = reinterpret_cast<float*>(C); p.ldc = ldc; p.M = M; p.N = N; p.num_kb = K / kb; p.kb_split = K1 / kb; p.conv = 0;
   if (ep) p.ep = *ep;
-  return dispatch_ps(ta, ta2, w_hi, w_plane, ldw, K, p, cdiv(M, BM), kb, s);
+  return dispatch_ps(ta, ta2, w_hi, w_plane, ldw, K, p, cdiv(M, BM), kb, workspace, ws_bytes, s);
 }
 
 bool tc_conv_geometry(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, TcParams& p,
                       cuuint64_t dims[4], cuuint64_t strides_b[3], cuuint32_t box[4], cuuint32_t estr[4]);
 
+size_t conv_ps_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad) {
+  TcParams p{};
+  cuuint64_t d4[4], s4[3]; cuuint32_t b4[4], e4[4];
+  if (Cin % 64 || !tc_conv_geometry(B, H, W, Cin, Cout, kh, kw, stride, pad, p, d4, s4, b4, e4)) return 0;
+  return ps_workspace_bytes(p.tiles_w * p.tiles_h * cdiv(B, p.tb), p.M, Cout, kh * kw * Cin);
+}
+
 int conv_ps(const void* x, long long x_plane, int B, int H, int W, int Cin, const void* w_hi, long long w_plane, int Cout, int kh,
-            int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, cudaStream_t s) {
+            int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, void* workspace, size_t ws_bytes, cudaStream_t s) {
   if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
   if (Cin % 64 || Cout < 64 || !planes_ok(x, x_plane) || !planes_ok(w_hi, w_plane)) return VBG_EUNSUPPORTED;
   const int kb = ps_kb();
@@ -554,7 +680,7 @@ int conv_ps(const void* x, long long x_plane, int B, int H, int W, int Cin, cons
   if (p.ep.res_mode == VBG_RES_SAME && p.ep.ldr == 0) p.ep.ldr = Cout;
   CUtensorMap ta;
   if (!tc_encode(&ta, x, 5, dims, strides, box, estr, true, kb == 32)) return VBG_EUNSUPPORTED;
-  return dispatch_ps(ta, ta, w_hi, w_plane, K, K, p, p.tiles_w * p.tiles_h * cdiv(B, p.tb), kb, s);
+  return dispatch_ps(ta, ta, w_hi, w_plane, K, K, p, p.tiles_w * p.tiles_h * cdiv(B, p.tb), kb, workspace, ws_bytes, s);
 }
 
 int merge_bf16(const void* hi, const void* lo, long long n, float* out, cudaStream_t s) {

@@ -142,6 +142,7 @@ struct TcParams {
   int sw, sh;      // TMA start-coordinate stride of the output tile origin along W / H
   int pad_w, pad_h;
   vbg_epilogue_t ep;
+  int splits, kb_per_split;   // split-K (single-CTA pre-split kernel): work unit = (tile, split)
   long long* dbg;  // optional device buffer for clock64 stamps of CTA 0 (vbg_debug_set_timeline); nullptr in production
 };
 
@@ -150,7 +151,11 @@ __device__ __forceinline__ void tc_stamp(const TcParams& p, int slot) {
 }
 long long* tc_debug_timeline();
 
-struct TcTile { int m0, n0, w0, h0, b0; };
+struct TcTile {
+  int m0, n0, w0, h0, b0;
+  int kb0, kb1;          // K-block range of this work unit (split-K; [0, num_kb) otherwise)
+  long long row_shift;   // split-K: partial results of split s go to rows [s * M, (s+1) * M) of the workspace
+};
 
 __device__ __forceinline__ TcTile tc_tile_origin(const TcParams& p, int bn) {
   TcTile t{0, (int)blockIdx.y * bn, 0, 0, 0};
@@ -191,7 +196,7 @@ __device__ __forceinline__ uint32_t tc_row_offsets(const TcParams& p, const TcTi
       const int wi = t.w0 + w, hi = t.h0 + h, bi = t.b0 + b;
       const bool ok = b < p.tb && wi < p.Wo && hi < p.Ho && bi < p.Bn;
       const long long m_out = ((long long)bi * p.Ho + hi) * p.Wo + wi;
-      out_off[it] = m_out * p.ldc;
+      out_off[it] = (m_out + t.row_shift) * p.ldc;
       res_off[it] = up2 ? (((long long)bi * Ho2 + (hi >> 1)) * Wo2 + (wi >> 1)) * (long long)p.N : (same ? m_out * ep.ldr : 0);
       if (ok) ok_mask |= 1u << it;
       w += 4;
@@ -205,7 +210,7 @@ __device__ __forceinline__ uint32_t tc_row_offsets(const TcParams& p, const TcTi
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const long long m_out = m0 + 4 * it;
-      out_off[it] = m_out * p.ldc;
+      out_off[it] = (m_out + t.row_shift) * p.ldc;
       res_off[it] = up2 ? (((long long)b * oh2 + (ho >> 1)) * ow2 + (wo >> 1)) * (long long)p.N : (same ? m_out * ep.ldr : 0);
       if (m_out < p.M) ok_mask |= 1u << it;
       if (up2) {

@@ -92,6 +92,11 @@ def _act(x, name="tensor"):
     return _f32(x, name), 0
 
 
+def _workspace(nbytes, device):
+    """Caller-owned scratch for the split-K form of an under-filled GEMM (the library never allocates); None when unused."""
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device) if nbytes > 0 else None
+
+
 def _new_act(shape, device, split):
     return Split.empty(shape, device) if split else torch.empty(tuple(shape), dtype=torch.float32, device=device)
 
@@ -291,8 +296,10 @@ def gemm(A, W, *, A2=None, ep: Optional[Epilogue] = None, precision=PREC_FP32, N
             raise TypeError("gemm: A and A2 must use the same storage format")
         ap, aplane = _act(A)
         a2p, a2plane = _act(A2) if A2 is not None else (None, 0)
+        ws = _workspace(L.load().vbg_gemm_ps_workspace(M, Nn, Kt), A.device)
         L.check(L.load().vbg_gemm_ps(ap, aplane, K1, a2p, a2plane, K2, K1, sp, plane, ldw_, optr, ldc, M, Nn, Kt,
-                                     C.byref(ep) if ep is not None else None, _stream()), "vbg_gemm_ps")
+                                     C.byref(ep) if ep is not None else None, _p(ws), 0 if ws is None else ws.numel(), _stream()),
+                "vbg_gemm_ps")
         return out
     wp = _f32(W, "W") + 4 * w_offset
     L.check(L.load().vbg_gemm(_f32(A, "A"), A.stride(0), _f32(A2, "A2"), 0 if A2 is None else A2.stride(0), K1, wp, ldw_,
@@ -322,8 +329,10 @@ def conv2d(x, w_ohwi, stride, pad, *, ep: Optional[Epilogue] = None, precision=P
         if sp is None:
             raise TypeError("conv2d over a Split activation needs W_split")
         xp, xplane = _act(x)
+        ws = _workspace(L.load().vbg_conv2d_ps_workspace(B, H, W, Cin, Cout, kh, kw, stride, pad), x.device)
         L.check(L.load().vbg_conv2d_ps(xp, xplane, B, H, W, Cin, sp, plane, Cout, kh, kw, stride, pad, yp,
-                                       C.byref(ep) if ep is not None else None, _stream()), "vbg_conv2d_ps")
+                                       C.byref(ep) if ep is not None else None, _p(ws), 0 if ws is None else ws.numel(), _stream()),
+                "vbg_conv2d_ps")
         return y
     L.check(L.load().vbg_conv2d(_f32(x, "x"), B, H, W, Cin, _f32(w_ohwi, "w"), sp, plane, Cout, kh, kw, stride, pad, yp,
                                 C.byref(ep) if ep is not None else None, precision, _stream()), "vbg_conv2d")
