@@ -90,6 +90,9 @@ VBG_API int vbg_tc_available(void);
  * 3-pixel zero border (= the stem conv's padding), pixel (y,x) at [b, y+3, x+3, :].            */
 VBG_API int vbg_normalize_resize_pad(const float* img_chw, int h, int w, float* batch_nhwc, int b, int H, int W,
                              int oh, int ow, const float* h_mean3, const float* h_std3, vbg_stream_t stream);
+/* the same for n same-shape images [n,3,h,w] (contiguous) resized to the same (oh,ow): samples b0 .. b0+n-1, one launch */
+VBG_API int vbg_normalize_resize_pad_batch(const float* imgs, int n, int h, int w, float* batch_nhwc, int b0, int H, int W,
+                                   int oh, int ow, const float* h_mean3, const float* h_std3, vbg_stream_t stream);
 /* coords int64 [K,4] (l,t,r,b) -> int32 [K,4]: cols 0,2 *= ratio[b][0] (height ratio), cols 1,3 *= ratio[b][1]
  * (width ratio) in fp32, then truncation (pipeline/transform.py:163-169, axis swap included).    */
 VBG_API int vbg_resize_coords(const int64_t* coors, const int32_t* seg_off, const float* ratios /*[B,2]*/, int B, int K,

@@ -35,6 +35,7 @@ SIGNATURES = {
     "vbg_last_error": [C.c_char_p, _sz],
     "vbg_tc_available": [],
     "vbg_normalize_resize_pad": [_p, _i, _i, _p, _i, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _p],
+    "vbg_normalize_resize_pad_batch": [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _p],
     "vbg_resize_coords": [_p, _p, _p, _i, _i, _p, _p],
     "vbg_bert_assemble": [_p, _i, _p, _p, _i, _i, _p, _p, _p],
     "vbg_embed_ln": [_p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _p, _p],

@@ -636,7 +636,9 @@ int gemm_ps(const void* A, long long a_plane, int lda, const void* A2, long long
             long long w_plane, int ldw, void* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep, void* workspace,
             size_t ws_bytes, cudaStream_t s) {
   if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
-  if (N < 64 || K % 64 || K1 % 64 || (lda & 7) || (ldw & 7) || !planes_ok(A, a_plane) || !planes_ok(w_hi, w_plane)) return VBG_EUNSUPPORTED;
+  // N < 64: one 64-wide tile with N live columns (weight rows beyond N are TMA zero fill) -- worth it only for tall problems
+  if ((N < 64 && ((N & 3) || M < 8192)) || K % 64 || K1 % 64 || (lda & 7) || (ldw & 7) || !planes_ok(A, a_plane) || !planes_ok(w_hi, w_plane))
+    return VBG_EUNSUPPORTED;
   if (K1 < K && ((lda2 & 7) || !planes_ok(A2, a2_plane))) return VBG_EUNSUPPORTED;
   const int kb = ps_kb();
   CUtensorMap ta, ta2;

@@ -12,6 +12,9 @@ namespace vbg {
 // normalize/interpolate/copy_ kernels of reference pipeline/transform.py:122,149-155,261-269.
 __global__ void normalize_resize_kernel(const float* __restrict__ img, int h, int w, float* __restrict__ out, int H,
                                         int W, int oh, int ow, float3 mean, float3 stdv) {
+  // blockIdx.z = image of a same-shape batch ([n,3,h,w] contiguous in, consecutive samples of the padded batch out)
+  img += (size_t)blockIdx.z * 3 * h * w;
+  out += (size_t)blockIdx.z * (H + 6) * (W + 6) * 4;
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y * blockDim.y + threadIdx.y;
   if (x >= ow || y >= oh) return;
@@ -164,6 +167,18 @@ extern "C" int vbg_normalize_resize_pad(const float* img_chw, int h, int w, floa
       img_chw, h, w, batch_nhwc + (size_t)b * (H + 6) * (W + 6) * 4, H, W, oh, ow,
       make_float3(h_mean3[0], h_mean3[1], h_mean3[2]), make_float3(h_std3[0], h_std3[1], h_std3[2]));
   return check_launch("vbg_normalize_resize_pad");
+}
+
+extern "C" int vbg_normalize_resize_pad_batch(const float* imgs, int n, int h, int w, float* batch_nhwc, int b0, int H, int W,
+                                              int oh, int ow, const float* h_mean3, const float* h_std3, vbg_stream_t stream) {
+  VBG_REQUIRE(imgs && batch_nhwc && h_mean3 && h_std3 && aligned16(batch_nhwc), "vbg_normalize_resize_pad_batch: null / unaligned pointer");
+  VBG_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0 && oh > 0 && ow > 0 && oh <= H && ow <= W && b0 >= 0,
+              "vbg_normalize_resize_pad_batch: bad geometry n=%d h=%d w=%d oh=%d ow=%d H=%d W=%d", n, h, w, oh, ow, H, W);
+  dim3 blk(32, 8), grd(cdiv(ow, 32), cdiv(oh, 8), n);
+  normalize_resize_kernel<<<grd, blk, 0, as_stream(stream)>>>(
+      imgs, h, w, batch_nhwc + (size_t)b0 * (H + 6) * (W + 6) * 4, H, W, oh, ow,
+      make_float3(h_mean3[0], h_mean3[1], h_mean3[2]), make_float3(h_std3[0], h_std3[1], h_std3[2]));
+  return check_launch("vbg_normalize_resize_pad_batch");
 }
 
 extern "C" int vbg_stem_pack_weights(const float* w_oihw, int O, float* w_ohwi4, float* w_k256, vbg_stream_t stream) {

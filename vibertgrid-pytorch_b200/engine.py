@@ -143,6 +143,7 @@ class ForwardEngine:
             enc = net.semantic_segmentation_head.encoder
             pr.misc["seg_w"] = torch.cat([enc.conv_3_1.weight.flatten(1), enc.conv_3_2.weight.flatten(1)], 0).detach().contiguous()
             pr.misc["seg_b"] = torch.cat([enc.conv_3_1.bias, enc.conv_3_2.bias], 0).detach().contiguous()
+            split_of("seg_w", pr.misc["seg_w"])
             for m in (enc.conv_3_1, enc.conv_3_2):
                 pr.split.pop(id(m), None)          # N = 3 + C < 64: CUDA-core kernel
         head = net.field_type_classification_head
@@ -359,10 +360,15 @@ class ForwardEngine:
     def _seg_head(self, p_fuse):
         enc = self.net.semantic_segmentation_head.encoder
         x = self._conv(p_fuse, enc.conv_1, enc.bn_1, ACT_RELU)
-        x = self._conv(x, enc.conv_2, enc.bn_2, ACT_RELU, out_f32=True)     # feeds the N = 3 + C CUDA-core GEMM
-        B, H, W, Cc = x.shape
         pr = self._prep
-        lg = ops.gemm(x.view(-1, Cc), pr.misc["seg_w"], ep=make_epilogue(None, pr.misc["seg_b"]), precision=self._prec())
+        # the packed 1x1 heads have N = 3 + C outputs: on the tensor cores (a 64-wide tile with 3 + C live columns) when the
+        # pre-split kernel takes the shape (N % 4 == 0), else the CUDA-core GEMM over an fp32 copy
+        tc_heads = (pr.split.get("seg_w") is not None and pr.misc["seg_w"].shape[0] % 4 == 0 and self._ps()
+                    and x.shape[0] * x.shape[1] * x.shape[2] >= 8192)      # vbg_gemm_ps takes N < 64 only for tall problems
+        x = self._conv(x, enc.conv_2, enc.bn_2, ACT_RELU, out_f32=not tc_heads)
+        B, H, W, Cc = x.shape
+        lg = ops.gemm(x.view(B * H * W, Cc), pr.misc["seg_w"], ep=make_epilogue(None, pr.misc["seg_b"]), precision=self._prec(),
+                      W_split=pr.split.get("seg_w") if tc_heads else None)
         lg = lg.view(B, H, W, -1)
         return ops.upsample_split_nchw(lg, self.net.p_fuse_downsampling_ratio, 3) + (lg,)
 
@@ -401,8 +407,10 @@ class ForwardEngine:
 
         plan = plan_batch(list(shapes[0]), list(shapes[1]), list(shapes[2]), shapes[3], min_size, float(net.image_max_size))
         tab = torch.from_numpy(plan.table).to(dev)          # the step's only H2D besides the inputs
+        uniform = len({tuple(im.shape) for im in image}) == 1 and len(set(plan.sizes)) == 1 and not standins
+        stack = torch.stack([im for im in image], 0).contiguous() if uniform else None     # one normalise launch for the batch
         static = dict(
-            image=[im.contiguous() for im in image],
+            image=[stack[b] for b in range(len(image))] if uniform else [im.contiguous() for im in image], image_stack=stack,
             coors=torch.cat([c.reshape(-1, 4) for c in coors], 0).to(torch.int64).contiguous(),
             seg_ids=torch.cat([s.reshape(-1) for s in seg_indices], 0).to(torch.int32).contiguous(),
             cls=torch.cat([c.reshape(-1) for c in seg_classes], 0).to(torch.int32).contiguous() if want_seg else None,
@@ -415,6 +423,8 @@ class ForwardEngine:
             else:                                             # second sighting: capture
                 static = {k: ([t.clone() for t in v] if isinstance(v, list) else (None if v is None else v.clone()))
                           for k, v in static.items()}
+                if static["image_stack"] is not None:             # the per-image static inputs are views of the stacked buffer
+                    static["image"] = [static["image_stack"][b] for b in range(len(image))]
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 c0 = ops.L.launch_count
@@ -478,8 +488,11 @@ class ForwardEngine:
         else:
             bert_branch()
         batch = torch.zeros((B, plan.H + 6, plan.W + 6, 4), dtype=torch.float32, device=dev)   # zero-bordered NHWC4 stem input
-        for b, im in enumerate(st["image"]):
-            ops.normalize_resize_pad(im, batch, b, plan.sizes[b][0], plan.sizes[b][1], net.image_mean, net.image_std)
+        if st.get("image_stack") is not None:
+            ops.normalize_resize_pad_batch(st["image_stack"], batch, 0, plan.sizes[0][0], plan.sizes[0][1], net.image_mean, net.image_std)
+        else:
+            for b, im in enumerate(st["image"]):
+                ops.normalize_resize_pad(im, batch, b, plan.sizes[b][0], plan.sizes[b][1], net.image_mean, net.image_std)
         out["image_batch"] = batch[:, 3:-3, 3:-3, :3]              # view without border / pad channel
         x1, x2 = self._backbone_pre(batch)                         # a5, the part before the early fusion
         if side is not None:

@@ -136,6 +136,17 @@ def normalize_resize_pad(img_chw, batch_nhwc4, b, oh, ow, mean, std):
                                               _stream()), "vbg_normalize_resize_pad")
 
 
+def normalize_resize_pad_batch(imgs_nchw, batch_nhwc4, b0, oh, ow, mean, std):
+    """n same-shape images [n,3,h,w] -> samples b0..b0+n-1 of the padded batch, one launch."""
+    n, _, h, w = imgs_nchw.shape
+    B, Hp, Wp, c4 = batch_nhwc4.shape
+    assert c4 == 4 and b0 + n <= B
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    L.check(L.load().vbg_normalize_resize_pad_batch(_f32(imgs_nchw, "images"), n, h, w, _f32(batch_nhwc4), b0, Hp - 6, Wp - 6, oh, ow,
+                                                    m, s, _stream()), "vbg_normalize_resize_pad_batch")
+
+
 def resize_coords(coors_i64, seg_off, ratios, B):
     K = coors_i64.shape[0]
     out = torch.empty((K, 4), dtype=torch.int32, device=coors_i64.device)
