@@ -10,9 +10,10 @@ dev = "cuda"
 buf = torch.zeros(16, dtype=torch.int64, device=dev)
 names = ["entry", "setup_done", "after_pdl_wait", "first_tma_issued", "first_operands_landed", "last_mma_committed(tile0)",
          "epi_start(tile0)", "epi_end(tile0)", "before_final_sync", "exit"]
-for (M, N, K) in [(256, 768, 768), (4128, 768, 768), (4128, 2304, 768), (4128, 3072, 768), (4128, 768, 3072)]:
+for (M, N, K, act) in [(256, 768, 768, 0), (4128, 768, 768, 0), (4128, 2304, 768, 0), (4128, 3072, 768, 0), (4128, 3072, 768, ops.ACT_GELU),
+                       (4128, 768, 3072, 0)]:
     A = ops.to_split(torch.randn(M, K, device=dev)); W = torch.randn(N, K, device=dev) * 0.02
-    Ws = ops.split_bf16(W); ep = ops.make_epilogue(None, torch.zeros(N, device=dev))
+    Ws = ops.split_bf16(W); ep = ops.make_epilogue(None, torch.zeros(N, device=dev), act=act)
     f = lambda: ops.gemm(A, W, ep=ep, precision=ops.PREC_BF16X3, W_split=Ws, split_out=True)
     for _ in range(3): f()
     torch.cuda.synchronize()
@@ -25,7 +26,7 @@ for (M, N, K) in [(256, 768, 768), (4128, 768, 768), (4128, 2304, 768), (4128, 3
     f(); torch.cuda.synchronize()
     _lib.load().vbg_debug_set_timeline(None)
     t = buf.cpu().tolist()
-    print(f"[{M}x{N}x{K}] back-to-back {us:.1f} us/launch; CTA 0 milestones (cycles since entry, us at 1.9 GHz):")
+    print(f"[{M}x{N}x{K} act={act}] back-to-back {us:.1f} us/launch; CTA 0 milestones (cycles since entry, us at 1.9 GHz):")
     for i, n in enumerate(names):
         d = t[i] - t[0]
         print(f"    {n:28s} {d:9d}  {d/1900.0:7.2f} us")
