@@ -57,6 +57,23 @@ __device__ __forceinline__ float warp_max(float v) {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// erf-GELU for the tensor-core epilogues: Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7, i.e. <= 5e-7 absolute on the
+// output -- far inside the tensor-core mode's own error), branch-free: rcp.approx + ex2.approx + ~10 FMA-pipe
+// instructions per element instead of erff's two divergent branches (~26).  The exact-fp32 CUDA-core path keeps erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  const float q = p * t * e;                                   // 1 - erf(|x| / sqrt 2)
+  const float h = 0.5f * x;
+  return x >= 0.f ? fmaf(-h, q, x) : h * q;                    // x >= 0: 0.5x(2 - q);  x < 0: 0.5x q
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == VBG_ACT_RELU) return fmaxf(v, 0.0f);
   if (act == VBG_ACT_GELU) return gelu_erf(v);

@@ -348,7 +348,7 @@ __device__ __forceinline__ void tc_epilogue_fast(const TcParams& p, const TcTile
       } else if (act == VBG_ACT_GELU) {
 #pragma unroll
         for (int it = 0; it < 8; ++it)
-          o[it] = make_float4(gelu_erf(o[it].x), gelu_erf(o[it].y), gelu_erf(o[it].z), gelu_erf(o[it].w));
+          o[it] = make_float4(gelu_fast(o[it].x), gelu_fast(o[it].y), gelu_fast(o[it].z), gelu_fast(o[it].w));
       }
       if (split_out) {
         __nv_bfloat16* hp = reinterpret_cast<__nv_bfloat16*>(p.C) + n;
