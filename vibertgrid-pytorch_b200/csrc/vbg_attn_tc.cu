@@ -400,7 +400,6 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
     const uint32_t xr = (uint32_t)(r & 7);
     uint8_t* p1 = p_op + grp * 2 * kTileQ + (uint32_t)r * 128u;
     for (int u = grp, it = 0; u < n_units; u += 2, ++it) {
-      if (it >= 1) mbar_wait(&pv_done[grp], (it - 1) & 1);
       uint32_t vv[2][32];                         // both 32-column halves of the unit in flight, one wait
       tmem_ld32_nowait(lane_addr + (uint32_t)(u * 64), vv[0]);
       tmem_ld32_nowait(lane_addr + (uint32_t)(u * 64 + 32), vv[1]);
@@ -428,6 +427,9 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
             split2(pa, pb, hi[j], lo[j]);
           }
         }
+        // the group's P buffer is free once the PV MMAs of its previous unit have read it: wait only now, after the first
+        // half's exponentials are already in registers, so the wait overlaps that arithmetic
+        if (half == 0 && it >= 1) mbar_wait(&pv_done[grp], (it - 1) & 1);
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           const uint32_t off = (((uint32_t)(4 * half + qd)) ^ xr) << 4;
