@@ -213,6 +213,17 @@ VBG_API int vbg_bn_fold(const float* weight, const float* bias, const float* mea
 /* PyTorch conv weight [O,I,H,W] -> [O,H,W,I]; also permutes the ROI FC weight [1024,(C,7,7)] -> [1024,(7,7,C)] */
 VBG_API int vbg_repack_oihw_to_ohwi(const float* w, int O, int I, int H, int W, float* out, vbg_stream_t stream);
 
+/* ---- first bricks of the training step (linear-layer backward) --------------------------------
+ * out[c][r] = x[r][c] written as bf16 hi/lo planes with leading dimension ld_out >= rows (the tail is zero filled): the
+ * K-major operand of a GEMM that reduces over `rows`.  x is fp32 (x_plane == 0) or bf16 planes.  With these,
+ *   dgrad  dX[M,K] = vbg_gemm_ps(A = dY planes [M,N],          W = transpose_split(W [N,K])       -> [K,N] planes)
+ *   wgrad  dW[N,K] = vbg_gemm_ps(A = transpose_split(dY) [N,Mp], W = transpose_split(X) [K,Mp]), Mp = M rounded up to 64
+ *   bgrad  db[N]   = vbg_colsum(dY)
+ * replace torch.autograd's addmm backward of nn.Linear (HF BertSelfOutput / BertIntermediate / ..., head MLPs).      */
+VBG_API int vbg_transpose_split(const void* x, long long x_plane, int rows, int cols, void* out_hi, long long out_plane, int ld_out,
+                        vbg_stream_t stream);
+VBG_API int vbg_colsum(const void* x, long long x_plane, int rows, int cols, float* out, vbg_stream_t stream);
+
 /* ---- a7: GridROIAlign (model/grid_roi_align.py:37-41,81 -> torchvision roi_align, aligned=False,
  *          sampling_ratio=-1) over NHWC features; boxes are the int32 transformed coords.         */
 VBG_API int vbg_roi_align_fwd(const float* feat, int B, int Hf, int Wf, int C, const int32_t* boxes, const int32_t* seg_off,

@@ -153,6 +153,62 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int HW, int C, 
   }
 }
 
+// ------------------------------------------------------------------ backward building blocks (first bricks of the training step)
+// out[c][r] = x[r][c] as bf16 hi/lo planes with leading dimension ld_out >= rows (columns rows .. ld_out-1 zero): turns a
+// [rows, cols] activation / gradient / weight into the K-major operand of a GEMM that reduces over `rows` (wgrad:
+// dW = dY^T X) or of the dgrad GEMM (W^T).  32x32 tiles through shared memory, coalesced on both sides.
+__global__ void __launch_bounds__(256)
+transpose_split_kernel(const void* __restrict__ x, long long x_plane, int rows, int cols, __nv_bfloat16* __restrict__ out,
+                       long long out_plane, int ld_out) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + tx;
+    float v = 0.f;
+    if (r < rows && c < cols) {
+      const size_t idx = (size_t)r * cols + c;
+      v = x_plane == 0 ? __ldg(reinterpret_cast<const float*>(x) + idx)
+                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[idx]) +
+                             __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[idx + x_plane]);
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + tx;                              // output row = input column
+    if (c < cols && r < ld_out) {
+      const float v = tile[tx][i];
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      out[(size_t)c * ld_out + r] = h;
+      out[(size_t)c * ld_out + r + out_plane] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+// out[c] = sum_r x[r][c], rows added in a fixed order (bias gradient)
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ x, long long x_plane, int rows, int cols, float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (c < cols)
+    for (int r = ty; r < rows; r += 8) {
+      const size_t idx = (size_t)r * cols + c;
+      acc += x_plane == 0 ? __ldg(reinterpret_cast<const float*>(x) + idx)
+                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[idx]) +
+                                __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[idx + x_plane]);
+    }
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += part[i][tx];
+    out[c] = s;
+  }
+}
+
 }  // namespace vbg
 
 using namespace vbg;
@@ -241,4 +297,18 @@ extern "C" int vbg_nhwc_to_nchw(const float* x, int B, int H, int W, int C, floa
   dim3 grd(cdiv((long long)H * W, 32), cdiv(C, 32), B), blk(32, 8);
   nhwc_to_nchw_kernel<<<grd, blk, 0, as_stream(stream)>>>(x, H * W, C, y);
   return check_launch("vbg_nhwc_to_nchw");
+}
+
+extern "C" int vbg_transpose_split(const void* x, long long x_plane, int rows, int cols, void* out_hi, long long out_plane, int ld_out,
+                                   vbg_stream_t stream) {
+  VBG_REQUIRE(x && out_hi && rows > 0 && cols > 0 && ld_out >= rows && x_plane >= 0 && out_plane > 0, "vbg_transpose_split: bad arguments");
+  dim3 grd(cdiv(cols, 32), cdiv(ld_out, 32));
+  transpose_split_kernel<<<grd, 256, 0, as_stream(stream)>>>(x, x_plane, rows, cols, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane, ld_out);
+  return check_launch("vbg_transpose_split");
+}
+
+extern "C" int vbg_colsum(const void* x, long long x_plane, int rows, int cols, float* out, vbg_stream_t stream) {
+  VBG_REQUIRE(x && out && rows > 0 && cols > 0 && x_plane >= 0, "vbg_colsum: bad arguments");
+  colsum_kernel<<<cdiv(cols, 32), 256, 0, as_stream(stream)>>>(x, x_plane, rows, cols, out);
+  return check_launch("vbg_colsum");
 }

@@ -456,3 +456,22 @@ def crf_viterbi(feats, trans, seg_off, B):
     L.check(L.load().vbg_crf_viterbi(_f32(feats), _f32(trans), _i32(seg_off), B, K, T, _f32(tags), _f32(scores),
                                      _p(ws), ws.numel(), _stream()), "vbg_crf_viterbi")
     return tags, scores
+
+
+# ------------------------------------------------------------------ backward building blocks
+def transpose_split(x, ld_out=None):
+    """[rows, cols] (fp32 tensor or Split) -> Split [cols, ld_out] holding x^T, columns rows..ld_out-1 zero."""
+    rows, cols = x.shape
+    ld = rows if ld_out is None else ld_out
+    out = Split.empty((cols, ld), x.device)
+    xp, xpl = _act(x)
+    L.check(L.load().vbg_transpose_split(xp, xpl, rows, cols, _p(out.t), out.plane, ld, _stream()), "vbg_transpose_split")
+    return out
+
+
+def colsum(x):
+    rows, cols = x.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    xp, xpl = _act(x)
+    L.check(L.load().vbg_colsum(xp, xpl, rows, cols, _f32(out), _stream()), "vbg_colsum")
+    return out
