@@ -119,17 +119,34 @@ __global__ void repack_oihw_kernel(const float* __restrict__ w, int O, int I, in
 // full-resolution rows per channel with coalesced stores into the two NCHW outputs.
 __global__ void upsample_split_kernel(const float* __restrict__ x, int h, int w, int Ct, int up, int c_split,
                                       float* __restrict__ out1, float* __restrict__ out2) {
-  extern __shared__ float row[];          // [w][Ct]
+  extern __shared__ float row[];          // [Ct][w] (channel-major: the emit loop reads consecutive x)
   const int b = blockIdx.y, yi = blockIdx.x;
   const float* src = x + ((size_t)b * h + yi) * w * Ct;
-  for (int i = threadIdx.x; i < w * Ct; i += blockDim.x) row[i] = __ldg(src + i);
+  for (int i = threadIdx.x; i < w * Ct; i += blockDim.x) {
+    const int xs = i / Ct, c = i - xs * Ct;
+    row[c * w + xs] = __ldg(src + i);
+  }
   __syncthreads();
   const int Wf = w * up, Hf = h * up;
+  if ((up & 3) == 0) {
+    // 128-bit stores: the `up` output columns of one source pixel hold the same value, up/4 float4 per pixel
+    const int q = up >> 2, n4 = Ct * up * w * q;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const int xq = i % (w * q); int t = i / (w * q);
+      const int dy = t % up, c = t / up;
+      const float v = row[c * w + xq / q];
+      const int Y = yi * up + dy;
+      float* dst = c < c_split ? out1 + (((size_t)b * c_split + c) * Hf + Y) * Wf
+                               : out2 + (((size_t)b * (Ct - c_split) + (c - c_split)) * Hf + Y) * Wf;
+      reinterpret_cast<float4*>(dst)[xq] = make_float4(v, v, v, v);
+    }
+    return;
+  }
   const int n_out = Ct * up * Wf;
   for (int i = threadIdx.x; i < n_out; i += blockDim.x) {
     int X = i % Wf; int t = i / Wf;
     int dy = t % up; int c = t / up;
-    float v = row[(X / up) * Ct + c];
+    float v = row[c * w + X / up];
     int Y = yi * up + dy;
     if (c < c_split) out1[(((size_t)b * c_split + c) * Hf + Y) * Wf + X] = v;
     else out2[(((size_t)b * (Ct - c_split) + (c - c_split)) * Hf + Y) * Wf + X] = v;
