@@ -223,6 +223,14 @@ VBG_API int vbg_repack_oihw_to_ohwi(const float* w, int O, int I, int H, int W, 
 VBG_API int vbg_transpose_split(const void* x, long long x_plane, int rows, int cols, void* out_hi, long long out_plane, int ld_out,
                         vbg_stream_t stream);
 VBG_API int vbg_colsum(const void* x, long long x_plane, int rows, int cols, float* out, vbg_stream_t stream);
+/* planes of w'[Cin,kh,kw,Cout] = w[Cout,kh,kw,Cin] flipped in (kh,kw): with it the data gradient of a stride-1 convolution is
+ * vbg_conv2d_ps(dY planes, w' planes, stride 1, pad k-1-p)  (replaces torch's conv2d backward-input of the ResNet / FPN convs) */
+VBG_API int vbg_conv_dgrad_weight(const float* w_ohwi, int Cout, int kh, int kw, int Cin, void* out_hi, long long out_plane,
+                          vbg_stream_t stream);
+/* LayerNorm backward (HF BertSelfOutput / BertOutput / embeddings LayerNorm): dx [R,hidden]; dgamma / dbeta [hidden] (may be
+ * NULL together) through `workspace` >= ceil(R/256) * 2 * hidden floats, summed in a fixed order.                     */
+VBG_API int vbg_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, int R, int hidden, float* dx,
+                      float* dgamma, float* dbeta, float* workspace, size_t ws_bytes, vbg_stream_t stream);
 
 /* ---- a7: GridROIAlign (model/grid_roi_align.py:37-41,81 -> torchvision roi_align, aligned=False,
  *          sampling_ratio=-1) over NHWC features; boxes are the int32 transformed coords.         */

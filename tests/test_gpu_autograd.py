@@ -42,3 +42,40 @@ def test_transpose_split_and_colsum():
     t2 = ops.transpose_split(ops.to_split(x.cuda()))                      # planes in, planes out
     assert relerr(t2.float().cpu().numpy(), x.t().numpy()) < 2 ** -15
     assert relerr(ops.colsum(x.cuda()).cpu().numpy(), x.double().sum(0).numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("R,H", [(4128, 768), (37, 128), (1000, 1024)])
+def test_layernorm_ps_backward(R, H):
+    from vibertgrid_pytorch_b200.autograd import LayerNormPS
+    g = torch.Generator().manual_seed(R + H)
+    x = torch.randn(R, H, generator=g) * 2 + 0.3; gam = torch.randn(H, generator=g); bet = torch.randn(H, generator=g)
+    dy = torch.randn(R, H, generator=g)
+    xd, gd, bd = (t.double().requires_grad_(True) for t in (x, gam, bet))
+    torch.nn.functional.layer_norm(xd, (H,), gd, bd, 1e-12).backward(dy.double())
+    xc, gc, bc = (t.cuda().requires_grad_(True) for t in (x, gam, bet))
+    y = LayerNormPS.apply(xc, gc, bc, 1e-12)
+    y.backward(dy.cuda())
+    torch.cuda.synchronize()
+    assert relerr(xc.grad.cpu().numpy(), xd.grad.numpy()) < 1e-5
+    assert relerr(gc.grad.cpu().numpy(), gd.grad.numpy()) < 1e-5
+    assert relerr(bc.grad.cpu().numpy(), bd.grad.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,p", [(2, 32, 48, 64, 64, 3, 1), (8, 16, 16, 512, 512, 3, 1), (2, 20, 12, 128, 64, 1, 0), (1, 128, 128, 64, 256, 3, 1)])
+def test_conv2d_ps_data_gradient(B, H, W, Cin, Cout, k, p):
+    import torch.nn.functional as F
+    from vibertgrid_pytorch_b200 import ops
+    from vibertgrid_pytorch_b200.autograd import Conv2dS1PS
+    g = torch.Generator().manual_seed(Cin + Cout + H)
+    x = torch.randn(B, Cin, H, W, generator=g); w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    dy = torch.randn(B, Cout, H, W, generator=g)
+    xd = x.double().requires_grad_(True)
+    yd = F.conv2d(xd, w.double(), None, 1, p)
+    yd.backward(dy.double())
+    xc = x.permute(0, 2, 3, 1).contiguous().cuda().requires_grad_(True)
+    w_ohwi = ops.repack_oihw_to_ohwi(w.cuda())
+    y = Conv2dS1PS.apply(xc, w_ohwi, p)
+    y.backward(dy.permute(0, 2, 3, 1).contiguous().cuda())
+    torch.cuda.synchronize()
+    assert relerr(y.detach().permute(0, 3, 1, 2).cpu().numpy(), yd.detach().numpy()) < 3e-5
+    assert relerr(xc.grad.permute(0, 3, 1, 2).cpu().numpy(), xd.grad.numpy()) < 3e-5

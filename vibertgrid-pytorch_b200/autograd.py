@@ -50,3 +50,45 @@ class LinearPS(torch.autograd.Function):
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy)
         return dx, dw, db
+
+
+class LayerNormPS(torch.autograd.Function):
+    """LayerNorm over the last dimension of a [R, hidden] fp32 tensor (vbg_layernorm / vbg_layernorm_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        y = ops.layernorm(x.detach().contiguous(), gamma.detach(), beta.detach(), eps)
+        ctx.save_for_backward(x, gamma)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(x.detach().contiguous(), dy.contiguous(), gamma.detach(), ctx.eps,
+                                       want_params=ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        return dx, dg, db, None
+
+
+class Conv2dS1PS(torch.autograd.Function):
+    """Stride-1 NHWC convolution, forward and DATA gradient on the pre-split implicit-GEMM conv (the weight gradient needs
+    the MN-major wgrad kernel of DESIGN.md section 8 and is not built: ``weight`` must not require grad)."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, w_ohwi, pad):
+        xs = ops.to_split(x_nhwc.detach().contiguous())
+        y = ops.conv2d(xs, w_ohwi.detach(), 1, pad, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w_ohwi.detach()))
+        ctx.save_for_backward(w_ohwi)
+        ctx.pad = pad
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (w,) = ctx.saved_tensors
+        if ctx.needs_input_grad[1]:
+            raise NotImplementedError("Conv2dS1PS: the weight gradient is not built yet")
+        Cout, kh, kw, Cin = w.shape
+        wd = ops.conv_dgrad_weight(w.detach())                              # planes [2, Cin, kh, kw, Cout]
+        dys = ops.to_split(dy.contiguous())
+        dx = ops.conv2d(dys, wd[0].float(), 1, kh - 1 - ctx.pad, precision=ops.PREC_BF16X3, W_split=wd)
+        return dx, None, None

@@ -226,6 +226,120 @@ colsum_kernel(const void* __restrict__ x, long long x_plane, int rows, int cols,
   }
 }
 
+// w [Cout, kh, kw, Cin] fp32 -> planes of w'[Cin, kh, kw, Cout] with w'[ci, r, s, co] = w[co, kh-1-r, kw-1-s, ci]: the weight of
+// the data-gradient convolution dX = conv(dY, w', stride 1, pad k-1-p) of a stride-1 convolution
+__global__ void conv_dgrad_weight_kernel(const float* __restrict__ w, int Cout, int kh, int kw, int Cin, __nv_bfloat16* __restrict__ out,
+                                         long long out_plane) {
+  const long long total = (long long)Cin * kh * kw * Cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout); long long t = i / Cout;
+    const int s_ = (int)(t % kw); t /= kw;
+    const int r = (int)(t % kh); const int ci = (int)(t / kh);
+    const float v = __ldg(w + (((size_t)co * kh + (kh - 1 - r)) * kw + (kw - 1 - s_)) * Cin + ci);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = h;
+    out[i + out_plane] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// LayerNorm backward, data gradient: one warp per row, row in registers (hidden <= 1024); statistics recomputed from x
+__global__ void __launch_bounds__(256)
+ln_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma, float eps, int R,
+                 int H4, float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= R) return;
+  constexpr int kMax = 8;
+  float4 xv[kMax], gv[kMax];
+  const float4* x4 = reinterpret_cast<const float4*>(x) + (size_t)r * H4;
+  const float4* d4 = reinterpret_cast<const float4*>(dy) + (size_t)r * H4;
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H4) { xv[i] = __ldg(x4 + c); sum += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w); }
+  }
+  const float n = (float)(H4 * 4);
+  const float mean = warp_sum(sum) / n;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H4) {
+      xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+      sq += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
+    }
+  }
+  const float rstd = __fdiv_rn(1.0f, sqrtf(warp_sum(sq) / n + eps));
+  float s1 = 0.f, s2 = 0.f;                 // sum(dxhat), sum(dxhat * xhat)
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H4) {
+      const float4 d = __ldg(d4 + c), g = __ldg(g4 + c);
+      xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;          // xhat
+      gv[i] = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);              // dxhat
+      s1 += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+      s2 += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+    }
+  }
+  const float m1 = warp_sum(s1) / n, m2 = warp_sum(s2) / n;
+  float4* o4 = reinterpret_cast<float4*>(dx) + (size_t)r * H4;
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int c = lane + 32 * i;
+    if (c < H4)
+      o4[c] = make_float4(rstd * (gv[i].x - m1 - xv[i].x * m2), rstd * (gv[i].y - m1 - xv[i].y * m2),
+                          rstd * (gv[i].z - m1 - xv[i].z * m2), rstd * (gv[i].w - m1 - xv[i].w * m2));
+  }
+}
+
+// LayerNorm backward, parameter gradients: partial[blk][2][H] over blocks of rows (each CTA: 32 columns x its row block),
+// summed in block order by ln_bwd_param_finish_kernel => deterministic
+__global__ void __launch_bounds__(256)
+ln_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ dy, float eps, int R, int H, int rows_per_blk,
+                    float* __restrict__ partial) {
+  __shared__ float pg[8][33], pb[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_blk, r1 = min(r0 + rows_per_blk, R);
+  float ag = 0.f, ab = 0.f;
+  for (int r = r0 + ty; r < r1; r += 8) {
+    // row statistics: every warp-row (32 lanes = 32 columns of this CTA) needs the full-row mean / rstd -> recompute by
+    // striding the row with the 32 lanes (H / 32 loads per lane; rows are L2-resident across the column CTAs)
+    const float* xr = x + (size_t)r * H;
+    float s = 0.f;
+    for (int k = tx; k < H; k += 32) s += __ldg(xr + k);
+    const float mean = warp_sum(s) / (float)H;
+    float q = 0.f;
+    for (int k = tx; k < H; k += 32) { const float d = __ldg(xr + k) - mean; q += d * d; }
+    const float rstd = __fdiv_rn(1.0f, sqrtf(warp_sum(q) / (float)H + eps));
+    if (c < H) {
+      const float d = __ldg(dy + (size_t)r * H + c);
+      ag += d * ((__ldg(xr + c) - mean) * rstd);
+      ab += d;
+    }
+  }
+  pg[ty][tx] = ag; pb[ty][tx] = ab;
+  __syncthreads();
+  if (ty == 0 && c < H) {
+    float g = 0.f, b = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g += pg[i][tx]; b += pb[i][tx]; }
+    partial[((size_t)blockIdx.y * 2 + 0) * H + c] = g;
+    partial[((size_t)blockIdx.y * 2 + 1) * H + c] = b;
+  }
+}
+
+__global__ void ln_bwd_param_finish_kernel(const float* __restrict__ partial, int nblk, int H, float* __restrict__ dgamma,
+                                           float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= H) return;
+  float g = 0.f, b = 0.f;
+  for (int k = 0; k < nblk; ++k) { g += partial[((size_t)k * 2 + 0) * H + c]; b += partial[((size_t)k * 2 + 1) * H + c]; }
+  dgamma[c] = g; dbeta[c] = b;
+}
+
 }  // namespace vbg
 
 using namespace vbg;
@@ -328,4 +442,35 @@ extern "C" int vbg_colsum(const void* x, long long x_plane, int rows, int cols, 
   VBG_REQUIRE(x && out && rows > 0 && cols > 0 && x_plane >= 0, "vbg_colsum: bad arguments");
   colsum_kernel<<<cdiv(cols, 32), 256, 0, as_stream(stream)>>>(x, x_plane, rows, cols, out);
   return check_launch("vbg_colsum");
+}
+
+extern "C" int vbg_conv_dgrad_weight(const float* w_ohwi, int Cout, int kh, int kw, int Cin, void* out_hi, long long out_plane,
+                                     vbg_stream_t stream) {
+  VBG_REQUIRE(w_ohwi && out_hi && Cout > 0 && kh > 0 && kw > 0 && Cin > 0 && out_plane > 0, "vbg_conv_dgrad_weight: bad arguments");
+  const long long total = (long long)Cin * kh * kw * Cout;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  conv_dgrad_weight_kernel<<<blocks, 256, 0, as_stream(stream)>>>(w_ohwi, Cout, kh, kw, Cin, reinterpret_cast<__nv_bfloat16*>(out_hi), out_plane);
+  return check_launch("vbg_conv_dgrad_weight");
+}
+
+extern "C" int vbg_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, int R, int hidden, float* dx,
+                                 float* dgamma, float* dbeta, float* workspace, size_t ws_bytes, vbg_stream_t stream) {
+  VBG_REQUIRE(x && dy && gamma && dx && R > 0 && hidden % 4 == 0 && hidden <= 1024 && aligned16(x) && aligned16(dy) && aligned16(dx),
+              "vbg_layernorm_bwd: hidden %% 4 == 0, <= 1024, 16B alignment");
+  cudaStream_t s = as_stream(stream);
+  ln_bwd_dx_kernel<<<cdiv(R, 8), 256, 0, s>>>(x, dy, gamma, eps, R, hidden / 4, dx);
+  int rc = check_launch("vbg_layernorm_bwd(dx)");
+  if (rc || !dgamma) return rc;
+  VBG_REQUIRE(dbeta && workspace, "vbg_layernorm_bwd: dbeta and workspace required with dgamma");
+  const int rows_per_blk = 256, nblk = cdiv(R, rows_per_blk);
+  if ((size_t)nblk * 2 * hidden * sizeof(float) > ws_bytes) {
+    set_error("vbg_layernorm_bwd: workspace of %zu bytes needed", (size_t)nblk * 2 * hidden * sizeof(float));
+    return VBG_EWORKSPACE;
+  }
+  ln_bwd_param_kernel<<<dim3(cdiv(hidden, 32), nblk), 256, 0, s>>>(x, dy, eps, R, hidden, rows_per_blk, workspace);
+  rc = check_launch("vbg_layernorm_bwd(params)");
+  if (rc) return rc;
+  ln_bwd_param_finish_kernel<<<cdiv(hidden, 128), 128, 0, s>>>(workspace, nblk, hidden, dgamma, dbeta);
+  return check_launch("vbg_layernorm_bwd(finish)");
 }

@@ -475,3 +475,27 @@ def colsum(x):
     xp, xpl = _act(x)
     L.check(L.load().vbg_colsum(xp, xpl, rows, cols, _f32(out), _stream()), "vbg_colsum")
     return out
+
+
+def conv_dgrad_weight(w_ohwi):
+    """[Cout,kh,kw,Cin] fp32 -> bf16 planes [2, Cin,kh,kw,Cout] of the flipped / transposed weight of the data-gradient conv."""
+    Cout, kh, kw, Cin = w_ohwi.shape
+    out = torch.empty((2, Cin, kh, kw, Cout), dtype=torch.bfloat16, device=w_ohwi.device)
+    L.check(L.load().vbg_conv_dgrad_weight(_f32(w_ohwi.contiguous()), Cout, kh, kw, Cin, _p(out), out[0].numel(), _stream()),
+            "vbg_conv_dgrad_weight")
+    return out
+
+
+def layernorm_bwd(x, dy, gamma, eps, want_params=True):
+    R, hidden = x.shape
+    dx = torch.empty_like(x)
+    if not want_params:
+        L.check(L.load().vbg_layernorm_bwd(_f32(x), _f32(dy), _f32(gamma), eps, R, hidden, _f32(dx), None, None, None, 0, _stream()),
+                "vbg_layernorm_bwd")
+        return dx, None, None
+    dg = torch.empty(hidden, dtype=torch.float32, device=x.device)
+    db = torch.empty(hidden, dtype=torch.float32, device=x.device)
+    ws = torch.empty(((R + 255) // 256) * 2 * hidden, dtype=torch.float32, device=x.device)
+    L.check(L.load().vbg_layernorm_bwd(_f32(x), _f32(dy), _f32(gamma), eps, R, hidden, _f32(dx), _f32(dg), _f32(db), _f32(ws),
+                                       ws.numel() * 4, _stream()), "vbg_layernorm_bwd")
+    return dx, dg, db
