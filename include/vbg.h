@@ -223,6 +223,12 @@ VBG_API int vbg_repack_oihw_to_ohwi(const float* w, int O, int I, int H, int W, 
 VBG_API int vbg_transpose_split(const void* x, long long x_plane, int rows, int cols, void* out_hi, long long out_plane, int ld_out,
                         vbg_stream_t stream);
 VBG_API int vbg_colsum(const void* x, long long x_plane, int rows, int cols, float* out, vbg_stream_t stream);
+/* dW[N,K] = dY[M,N]^T X[M,K] without transposes: both plane operands are read as MN-major tcgen05 operands (reduction index =
+ * the slow, row index), split over the row range with a deterministic finish.  N % 128 == 0, K % 64 == 0; workspace bytes from
+ * vbg_linear_wgrad_workspace (0: none needed).                                                                      */
+VBG_API long long vbg_linear_wgrad_workspace(int M, int N, int K);
+VBG_API int vbg_linear_wgrad(const void* dY_hi, long long y_plane, const void* X_hi, long long x_plane, int M, int N, int K, float* dW,
+                     void* workspace, size_t ws_bytes, vbg_stream_t stream);
 /* planes of w'[Cin,kh,kw,Cout] = w[Cout,kh,kw,Cin] flipped in (kh,kw): with it the data gradient of a stride-1 convolution is
  * vbg_conv2d_ps(dY planes, w' planes, stride 1, pad k-1-p)  (replaces torch's conv2d backward-input of the ResNet / FPN convs) */
 VBG_API int vbg_conv_dgrad_weight(const float* w_ohwi, int Cout, int kh, int kw, int Cin, void* out_hi, long long out_plane,

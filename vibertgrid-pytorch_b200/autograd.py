@@ -5,8 +5,9 @@ every ``nn.Linear`` on the path (HF ``BertSelfOutput`` / ``BertIntermediate`` / 
     y = LinearPS.apply(x, weight, bias)          # x [M, K] fp32 CUDA, weight [N, K], bias [N]; N, K multiples of 64
 
 backward:  dX = dY . W          (the forward GEMM over dY planes and the planes of W^T)
-           dW = dY^T . X        (the same GEMM over the transposed planes of dY and X, reduction over the M rows, M padded
-                                 to a multiple of 64 with zeros)
+           dW = dY^T . X        (vbg_linear_wgrad: both plane operands fed to tcgen05 as MN-major tiles, the row range split
+                                 over CTAs with a deterministic finish; N % 128 != 0 falls back to transposed planes + the
+                                 forward GEMM)
            db = column sums of dY (fixed order)
 All three are bf16x3 products with fp32 accumulation (fp32-class).  Not yet wired into ViBERTgridNet: the training-mode
 forward of the whole module is the next milestone.
@@ -43,10 +44,13 @@ class LinearPS(torch.autograd.Function):
             wt = ops.transpose_split(weight.detach().contiguous())                 # [K, N] planes
             dx = ops.gemm(dys, weight.detach().t(), precision=ops.PREC_BF16X3, W_split=wt.t, N=K, K=N, ldw=N)
         if ctx.needs_input_grad[1]:
-            Mp = (M + 63) // 64 * 64
-            dyt = ops.transpose_split(dys, Mp)                                     # [N, Mp] planes
-            xt = ops.transpose_split(x.detach().contiguous(), Mp)                  # [K, Mp] planes
-            dw = ops.gemm(dyt, x.detach(), precision=ops.PREC_BF16X3, W_split=xt.t, N=K, K=Mp, ldw=Mp)
+            if N % 128 == 0:                       # MN-major tcgen05 operands straight from the row-major planes
+                dw = ops.linear_wgrad(dys, ops.to_split(x.detach().contiguous()))
+            else:                                  # transposed-operand route through the forward GEMM
+                Mp = (M + 63) // 64 * 64
+                dyt = ops.transpose_split(dys, Mp)                                 # [N, Mp] planes
+                xt = ops.transpose_split(x.detach().contiguous(), Mp)              # [K, Mp] planes
+                dw = ops.gemm(dyt, x.detach(), precision=ops.PREC_BF16X3, W_split=xt.t, N=K, K=Mp, ldw=Mp)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy)
         return dx, dw, db

@@ -36,6 +36,9 @@ int gemm_ps(const void* A, long long a_plane, int lda, const void* A2, long long
 int conv_ps(const void* x, long long x_plane, int B, int H, int W, int Cin, const void* w_hi, long long w_plane, int Cout, int kh,
             int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, void* workspace, size_t ws_bytes, cudaStream_t s);
 size_t ps_workspace_bytes(int m_tiles, long long M, int N, int K);
+size_t linear_wgrad_workspace(int M, int N, int K);
+int linear_wgrad(const void* dY, long long y_plane, const void* X, long long x_plane, int M, int N, int K, float* dW, void* workspace,
+                 size_t ws_bytes, cudaStream_t s);
 size_t conv_ps_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad);
 bool tc_available();
 
@@ -227,6 +230,17 @@ extern "C" long long vbg_gemm_ps_workspace(int M, int N, int K) {
 extern "C" long long vbg_conv2d_ps_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad) {
   if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0) return 0;
   return (long long)conv_ps_workspace_bytes(B, H, W, Cin, Cout, kh, kw, stride, pad);
+}
+
+extern "C" long long vbg_linear_wgrad_workspace(int M, int N, int K) { return (long long)linear_wgrad_workspace(M, N, K); }
+
+extern "C" int vbg_linear_wgrad(const void* dY_hi, long long y_plane, const void* X_hi, long long x_plane, int M, int N, int K, float* dW,
+                                void* workspace, size_t ws_bytes, vbg_stream_t stream) {
+  VBG_REQUIRE(dY_hi && X_hi && dW && M > 0 && N > 0 && K > 0, "vbg_linear_wgrad: bad arguments");
+  int rc = linear_wgrad(dY_hi, y_plane, X_hi, x_plane, M, N, K, dW, workspace, ws_bytes, as_stream(stream));
+  if (rc == VBG_EUNSUPPORTED)
+    set_error("vbg_linear_wgrad: needs sm_100a, N %% 128 == 0, K %% 64 == 0, 16B-aligned bf16 planes (M=%d N=%d K=%d)", M, N, K);
+  return rc;
 }
 
 extern "C" int vbg_merge_bf16(const void* hi, const void* lo, long long n, float* out, vbg_stream_t stream) {

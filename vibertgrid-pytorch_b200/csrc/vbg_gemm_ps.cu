@@ -419,6 +419,14 @@ splitk_finish_kernel(const float* __restrict__ ws, int splits, long long M, int 
   }
 }
 
+int splitk_finish(const float* ws, int splits, long long M, int N, const vbg_epilogue_t& ep, void* C, int ldc, cudaStream_t s) {
+  const long long total4 = M * (N / 4);
+  int blocks = (int)((total4 + 255) / 256);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  splitk_finish_kernel<<<blocks, 256, 0, s>>>(ws, splits, M, N, ep, C, ldc);
+  return check_launch("split-K finish");
+}
+
 // ------------------------------------------------------------------ split -> fp32 (inspection / tests)
 __global__ void merge_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long n,
                                   float* __restrict__ out) {

@@ -1,0 +1,189 @@
+// Weight gradient of a linear layer on the tensor cores, no transposes:
+//
+//   dW[N, K] = dY[M, N]^T . X[M, K]          (reduction over the M rows; bf16x3: dY1 X1 + dY2 X1 + dY1 X2, fp32 accumulate)
+//
+// Both operands are stored with the REDUCTION index as the slow one (dY rows / X rows are the GEMM's K), i.e. they are
+// "MN-major" in tcgen05 terms: a TMA box of 64 rows x 64 columns lands as 64 rows of 128 bytes (SWIZZLE_128B) and is used as is
+// through an MN-major shared-memory descriptor (LBO = the 8 KB between 64-column blocks, SBO = the 1 KB between 8-row groups) with
+// the a_major / b_major bits of the instruction descriptor set -- the layout the attention kernel already uses for V.  The
+// forward's transposed-operand route (vbg_transpose_split twice + the forward GEMM) costs two extra passes over dY and X.
+//
+// Few output tiles (N/128 x K/BN) and a long reduction: the row range is split over `splits` CTAs per tile, partial tiles go to a
+// workspace and are summed in a fixed order by splitk_finish_kernel (deterministic).
+//   warp 0 TMA producer | warp 1 MMA issuer | warps 2-5 epilogue (vbg_tc.cuh::tc_epilogue)
+#include "vbg_tc.cuh"
+
+namespace vbg {
+
+constexpr int kWgThreads = 192;
+constexpr uint32_t kWgBox = 64 * 128;                 // one 64-row x 64-column bf16 box
+constexpr uint32_t kWgEpiBytes = 4 * kEpiStageFloats * 4;
+
+// MN-major SWIZZLE_128B descriptor: 64-element (128-byte) column blocks `lbo_bytes` apart, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)64 << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+struct WgParams {
+  TcParams tc;          // epilogue view: C = out or workspace, ldc, M = N (rows of dW), N = K (columns of dW)
+  int rows;             // reduction length (rows of dY / X)
+  int blocks_per_split; // 64-row blocks per split
+  int n_tiles, k_tiles; // output tiles
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const WgParams wp) {
+  constexpr uint32_t A_PLANE = 2 * kWgBox;                        // 128 dW rows = two 64-column boxes of dY
+  constexpr uint32_t B_PLANE = (BN / 64) * kWgBox;
+  constexpr uint32_t STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;     // Y1 | Y2 | X1 | X2
+  constexpr uint32_t TMEM_COLS = BN <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* epi = reinterpret_cast<float*>(ring + STAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES + kWgEpiBytes);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = wp.n_tiles * wp.k_tiles;
+  const int tile = blockIdx.x % tiles, split = blockIdx.x / tiles;
+  const int n0 = (tile % wp.n_tiles) * 128, k0 = (tile / wp.n_tiles) * BN;
+  const int n_blocks = (wp.rows + 63) >> 6;
+  const int b0 = split * wp.blocks_per_split, b1 = min(b0 + wp.blocks_per_split, n_blocks);
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmY); prefetch_tmap(&tmX); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+      mbar_init(acc_full, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int b = b0, g = 0; b < b1; ++b, ++g) {
+        const int s = g % STAGES;
+        mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+        uint8_t* sy = ring + s * STAGE_BYTES;
+        uint8_t* sx = sy + 2 * A_PLANE;
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) tma_load_3d(&tmY, &full[s], sy + pl * A_PLANE + j * kWgBox, n0 + 64 * j, b * 64, pl);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_3d(&tmX, &full[s], sx + pl * B_PLANE + j * kWgBox, k0 + 64 * j, b * 64, pl);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kFmtBF16, 128, BN, 1) | (1u << 15);        // A and B MN-major
+      for (int b = b0, g = 0; b < b1; ++b, ++g) {
+        const int s = g % STAGES;
+        mbar_wait(&full[s], (g / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(ring + s * STAGE_BYTES);
+        const uint64_t y1 = make_sw128_mn_desc(base, kWgBox), y2 = make_sw128_mn_desc(base + A_PLANE, kWgBox);
+        const uint64_t x1 = make_sw128_mn_desc(base + 2 * A_PLANE, kWgBox), x2 = make_sw128_mn_desc(base + 2 * A_PLANE + B_PLANE, kWgBox);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {              // 16 reduction rows = 16 x 128 B = 2048 B: +128 in the (addr >> 4) field
+          const uint64_t o = (uint64_t)(128 * k);
+          umma_bf16(tmem_base, y1 + o, x1 + o, idesc, (b != b0) || (k != 0));
+          umma_bf16(tmem_base, y2 + o, x1 + o, idesc, 1);
+          umma_bf16(tmem_base, y1 + o, x2 + o, idesc, 1);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    TcTile t{n0, k0, 0, 0, 0, 0, 0, (long long)split * wp.tc.M};
+    if (b1 > b0) tc_epilogue<BN>(wp.tc, t, tmem_base, q, lane, epi + q * kEpiStageFloats);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+int splitk_finish(const float* ws, int splits, long long M, int N, const vbg_epilogue_t& ep, void* C, int ldc, cudaStream_t s);   // vbg_gemm_ps.cu
+
+static bool map_rows(CUtensorMap* tm, const void* hi, long long plane, long long rows, long long cols, long long ld) {
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, 2};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane * 2};
+  cuuint32_t box[3] = {64u, 64u, 1u};
+  return tc_encode(tm, hi, 3, dims, strides, box, nullptr, true);
+}
+
+template <int BN, int STAGES>
+static int launch_wg(const CUtensorMap& ty, const CUtensorMap& tx, const WgParams& wp, int ctas, cudaStream_t s) {
+  constexpr size_t smem = (size_t)STAGES * (2 * 2 * kWgBox + 2 * (BN / 64) * kWgBox) + kWgEpiBytes + 1024 + 256;
+  static_assert(smem <= 232448, "wgrad tile does not fit shared memory");
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("wgrad: smem opt-in failed: %s", cudaGetErrorString(e)); return VBG_ECUDA; }
+    attr = true;
+  }
+  wgrad_kernel<BN, STAGES><<<ctas, kWgThreads, smem, s>>>(ty, tx, wp);
+  return check_launch("vbg_linear_wgrad(tcgen05 bf16x3, MN-major operands)");
+}
+
+// splits chosen so that tiles * splits fills the chip, each split keeping >= 4 row blocks
+static int wg_splits(int tiles, int n_blocks) {
+  int s = kNumSMs / (tiles > 0 ? tiles : 1);
+  if (s < 1) s = 1;
+  if (s > n_blocks / 4) s = n_blocks / 4 > 0 ? n_blocks / 4 : 1;
+  if (s > 64) s = 64;
+  return s;
+}
+
+size_t linear_wgrad_workspace(int M, int N, int K) {
+  if (N % 128 || K % 64 || M <= 0) return 0;
+  const int bn = K % 128 == 0 ? 128 : 64;
+  const int tiles = (N / 128) * cdiv(K, bn), n_blocks = cdiv(M, 64);
+  const int s = wg_splits(tiles, n_blocks);
+  return s > 1 ? (size_t)s * N * K * 4 : 0;
+}
+
+int linear_wgrad(const void* dY, long long y_plane, const void* X, long long x_plane, int M, int N, int K, float* dW, void* workspace,
+                 size_t ws_bytes, cudaStream_t s) {
+  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (N % 128 || K % 64 || !aligned16(dY) || !aligned16(X) || !aligned16(dW) || (y_plane & 7) || (x_plane & 7) || y_plane <= 0 || x_plane <= 0)
+    return VBG_EUNSUPPORTED;
+  const int bn = K % 128 == 0 ? 128 : 64;
+  CUtensorMap ty, tx;
+  if (!map_rows(&ty, dY, y_plane, M, N, N) || !map_rows(&tx, X, x_plane, M, K, K)) return VBG_EUNSUPPORTED;
+  WgParams wp{};
+  wp.rows = M; wp.n_tiles = N / 128; wp.k_tiles = cdiv(K, bn);
+  const int tiles = wp.n_tiles * wp.k_tiles, n_blocks = cdiv(M, 64);
+  int splits = wg_splits(tiles, n_blocks);
+  if (splits > 1 && (!workspace || !aligned16(workspace) || (size_t)splits * N * K * 4 > ws_bytes)) splits = 1;
+  wp.blocks_per_split = cdiv(n_blocks, splits);
+  splits = cdiv(n_blocks, wp.blocks_per_split);
+  wp.tc.M = N; wp.tc.N = K; wp.tc.ldc = K; wp.tc.conv = 0; wp.tc.num_kb = 0;
+  wp.tc.C = splits > 1 ? reinterpret_cast<float*>(workspace) : dW;
+  int rc = bn == 128 ? launch_wg<128, 3>(ty, tx, wp, tiles * splits, s) : launch_wg<64, 4>(ty, tx, wp, tiles * splits, s);
+  if (rc != VBG_OK || splits == 1) return rc;
+  return splitk_finish(reinterpret_cast<const float*>(workspace), splits, N, K, vbg_epilogue_t{}, dW, K, s);
+}
+
+}  // namespace vbg

@@ -499,3 +499,15 @@ def layernorm_bwd(x, dy, gamma, eps, want_params=True):
     L.check(L.load().vbg_layernorm_bwd(_f32(x), _f32(dy), _f32(gamma), eps, R, hidden, _f32(dx), _f32(dg), _f32(db), _f32(ws),
                                        ws.numel() * 4, _stream()), "vbg_layernorm_bwd")
     return dx, dg, db
+
+
+def linear_wgrad(dy_split, x_split):
+    """dW [N, K] = dY^T X over Split operands [M, N] and [M, K] (MN-major tcgen05 operands, no transposes)."""
+    M, N = dy_split.shape
+    M2, K = x_split.shape
+    assert M == M2
+    dw = torch.empty((N, K), dtype=torch.float32, device=dy_split.device)
+    ws = _workspace(L.load().vbg_linear_wgrad_workspace(M, N, K), dy_split.device)
+    L.check(L.load().vbg_linear_wgrad(_p(dy_split.t), dy_split.plane, _p(x_split.t), x_split.plane, M, N, K, _f32(dw), _p(ws),
+                                      0 if ws is None else ws.numel(), _stream()), "vbg_linear_wgrad")
+    return dw
