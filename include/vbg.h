@@ -226,6 +226,13 @@ VBG_API int vbg_colsum(const void* x, long long x_plane, int rows, int cols, flo
 /* dW[N,K] = dY[M,N]^T X[M,K] without transposes: both plane operands are read as MN-major tcgen05 operands (reduction index =
  * the slow, row index), split over the row range with a deterministic finish.  N % 128 == 0, K % 64 == 0; workspace bytes from
  * vbg_linear_wgrad_workspace (0: none needed).                                                                      */
+/* the same for an NHWC convolution: dW[Cout,kh,kw,Cin] from dY planes [B,Ho,Wo,Cout] and X planes [B,H,W,Cin] (the X tile of a
+ * filter tap is the tap-shifted window through a rank-5 TMA map: padding = out-of-bounds zero fill).  Cout % 128 == 0,
+ * Cin % 64 == 0, stride 1 or 2, output rows tiled in 64-pixel blocks (Wo >= 64, or Wo * k == 64).                       */
+VBG_API long long vbg_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad);
+VBG_API int vbg_conv2d_wgrad(const void* dY_hi, long long y_plane, const void* X_hi, long long x_plane, int B, int H, int W, int Cin,
+                     int Cout, int kh, int kw, int stride, int pad, float* dW, void* workspace, size_t ws_bytes,
+                     vbg_stream_t stream);
 VBG_API long long vbg_linear_wgrad_workspace(int M, int N, int K);
 VBG_API int vbg_linear_wgrad(const void* dY_hi, long long y_plane, const void* X_hi, long long x_plane, int M, int N, int K, float* dW,
                      void* workspace, size_t ws_bytes, vbg_stream_t stream);

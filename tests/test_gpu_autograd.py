@@ -93,3 +93,47 @@ def test_linear_wgrad_mn_major(M, N, K):
     want = dys.float().double().t() @ xs.float().double()
     assert relerr(got.cpu().numpy(), want.cpu().numpy()) < 2e-5
     assert torch.equal(got, ops.linear_wgrad(dys, xs))
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,stride,pad", [
+    (2, 16, 64, 64, 128, 3, 1, 1),      # one image row per 64-pixel block
+    (3, 24, 80, 128, 128, 3, 1, 1),     # W tail: the second block of a row is mostly out of bounds
+    (5, 8, 8, 64, 256, 3, 1, 1),        # a block is one whole image; B odd
+    (9, 7, 7, 128, 128, 3, 1, 1),       # ROI-sized: 49-row boxes, the rest of a stage stays zero
+    (2, 20, 42, 64, 128, 1, 1, 0),      # 1x1, short rows (42 < 64)
+    (2, 32, 64, 64, 128, 3, 2, 1),      # stride 2 through the traversal stride
+    (1, 16, 32, 192, 128, 1, 1, 0),     # Cin = 3 x 64
+])
+def test_conv2d_wgrad_mn_major(B, H, W, Cin, Cout, k, stride, pad):
+    """dW of an NHWC convolution from the plane operands (vbg_conv2d_wgrad) against torch float64 autograd; two runs agree
+    bit for bit (fixed-order finish)."""
+    from vibertgrid_pytorch_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(B * 131 + H * 7 + Cin + k + stride)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g)
+    dy = torch.randn(B, Ho, Wo, Cout, device="cuda", generator=g)
+    dw = ops.conv2d_wgrad(ops.to_split(dy), ops.to_split(x), k, k, stride, pad)
+    dw2 = ops.conv2d_wgrad(ops.to_split(dy), ops.to_split(x), k, k, stride, pad)
+    assert torch.equal(dw, dw2)
+    w = torch.zeros(Cout, Cin, k, k, device="cuda", dtype=torch.float64, requires_grad=True)
+    y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w, stride=stride, padding=pad)
+    (ref,) = torch.autograd.grad(y, w, dy.permute(0, 3, 1, 2).double())
+    ref = ref.permute(0, 2, 3, 1)                                              # OHWI
+    err = (dw.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err
+
+
+def test_conv2d_s1_ps_weight_grad():
+    from vibertgrid_pytorch_b200.autograd import Conv2dS1PS
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(2, 16, 64, 64, device="cuda", generator=g, requires_grad=True)
+    w = (torch.randn(128, 3, 3, 64, device="cuda", generator=g) * 0.05).requires_grad_()
+    y = Conv2dS1PS.apply(x, w, 1)
+    dy = torch.randn_like(y)
+    dx, dw = torch.autograd.grad(y, (x, w), dy)
+    xr = x.detach().double().permute(0, 3, 1, 2).requires_grad_()
+    wr = w.detach().double().permute(0, 3, 1, 2).requires_grad_()
+    yr = torch.nn.functional.conv2d(xr, wr, padding=1)
+    dxr, dwr = torch.autograd.grad(yr, (xr, wr), dy.double().permute(0, 3, 1, 2))
+    assert (dx.double() - dxr.permute(0, 2, 3, 1)).abs().max().item() / dxr.abs().max().item() < 2e-5
+    assert (dw.double() - dwr.permute(0, 2, 3, 1)).abs().max().item() / dwr.abs().max().item() < 2e-5

@@ -73,6 +73,8 @@ SIGNATURES = {
     "vbg_transpose_split": [_p, _ll, _i, _i, _p, _ll, _i, _p],
     "vbg_colsum": [_p, _ll, _i, _i, _p, _p],
     "vbg_linear_wgrad_workspace": [_i, _i, _i],
+    "vbg_conv2d_wgrad_workspace": [_i, _i, _i, _i, _i, _i, _i, _i, _i],
+    "vbg_conv2d_wgrad": [_p, _ll, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p],
     "vbg_linear_wgrad": [_p, _ll, _p, _ll, _i, _i, _i, _p, _p, _sz, _p],
     "vbg_conv_dgrad_weight": [_p, _i, _i, _i, _i, _p, _ll, _p],
     "vbg_layernorm_bwd": [_p, _p, _p, _f, _i, _i, _p, _p, _p, _p, _sz, _p],

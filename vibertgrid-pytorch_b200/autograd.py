@@ -75,24 +75,26 @@ class LayerNormPS(torch.autograd.Function):
 
 
 class Conv2dS1PS(torch.autograd.Function):
-    """Stride-1 NHWC convolution, forward and DATA gradient on the pre-split implicit-GEMM conv (the weight gradient needs
-    the MN-major wgrad kernel of DESIGN.md section 8 and is not built: ``weight`` must not require grad)."""
+    """Stride-1 NHWC convolution: forward and data gradient on the pre-split implicit-GEMM conv, weight gradient on the
+    MN-major wgrad kernel (``vbg_conv2d_wgrad``: Cout % 128 == 0, Cin % 64 == 0)."""
 
     @staticmethod
     def forward(ctx, x_nhwc, w_ohwi, pad):
         xs = ops.to_split(x_nhwc.detach().contiguous())
         y = ops.conv2d(xs, w_ohwi.detach(), 1, pad, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w_ohwi.detach()))
-        ctx.save_for_backward(w_ohwi)
+        ctx.save_for_backward(x_nhwc, w_ohwi)
         ctx.pad = pad
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (w,) = ctx.saved_tensors
-        if ctx.needs_input_grad[1]:
-            raise NotImplementedError("Conv2dS1PS: the weight gradient is not built yet")
+        x, w = ctx.saved_tensors
         Cout, kh, kw, Cin = w.shape
-        wd = ops.conv_dgrad_weight(w.detach())                              # planes [2, Cin, kh, kw, Cout]
         dys = ops.to_split(dy.contiguous())
-        dx = ops.conv2d(dys, wd[0].float(), 1, kh - 1 - ctx.pad, precision=ops.PREC_BF16X3, W_split=wd)
-        return dx, None, None
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            wd = ops.conv_dgrad_weight(w.detach())                          # planes [2, Cin, kh, kw, Cout]
+            dx = ops.conv2d(dys, wd[0].float(), 1, kh - 1 - ctx.pad, precision=ops.PREC_BF16X3, W_split=wd)
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv2d_wgrad(dys, ops.to_split(x.detach().contiguous()), kh, kw, 1, ctx.pad)
+        return dx, dw, None

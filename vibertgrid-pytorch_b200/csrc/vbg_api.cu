@@ -37,6 +37,9 @@ int conv_ps(const void* x, long long x_plane, int B, int H, int W, int Cin, cons
             int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, void* workspace, size_t ws_bytes, cudaStream_t s);
 size_t ps_workspace_bytes(int m_tiles, long long M, int N, int K);
 size_t linear_wgrad_workspace(int M, int N, int K);
+size_t conv_wgrad_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad);
+int conv_wgrad(const void* dY, long long y_plane, const void* X, long long x_plane, int B, int H, int W, int Cin, int Cout, int kh, int kw,
+               int stride, int pad, float* dW, void* workspace, size_t ws_bytes, cudaStream_t s);
 int linear_wgrad(const void* dY, long long y_plane, const void* X, long long x_plane, int M, int N, int K, float* dW, void* workspace,
                  size_t ws_bytes, cudaStream_t s);
 size_t conv_ps_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad);
@@ -240,6 +243,22 @@ extern "C" int vbg_linear_wgrad(const void* dY_hi, long long y_plane, const void
   int rc = linear_wgrad(dY_hi, y_plane, X_hi, x_plane, M, N, K, dW, workspace, ws_bytes, as_stream(stream));
   if (rc == VBG_EUNSUPPORTED)
     set_error("vbg_linear_wgrad: needs sm_100a, N %% 128 == 0, K %% 64 == 0, 16B-aligned bf16 planes (M=%d N=%d K=%d)", M, N, K);
+  return rc;
+}
+
+extern "C" long long vbg_conv2d_wgrad_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad) {
+  return (long long)conv_wgrad_workspace(B, H, W, Cin, Cout, kh, kw, stride, pad);
+}
+
+extern "C" int vbg_conv2d_wgrad(const void* dY_hi, long long y_plane, const void* X_hi, long long x_plane, int B, int H, int W, int Cin,
+                                int Cout, int kh, int kw, int stride, int pad, float* dW, void* workspace, size_t ws_bytes,
+                                vbg_stream_t stream) {
+  VBG_REQUIRE(dY_hi && X_hi && dW && B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && kh > 0 && kw > 0 && stride > 0 && pad >= 0,
+              "vbg_conv2d_wgrad: bad arguments");
+  int rc = conv_wgrad(dY_hi, y_plane, X_hi, x_plane, B, H, W, Cin, Cout, kh, kw, stride, pad, dW, workspace, ws_bytes, as_stream(stream));
+  if (rc == VBG_EUNSUPPORTED)
+    set_error("vbg_conv2d_wgrad: needs sm_100a, Cout %% 128 == 0, Cin %% 64 == 0, stride 1 or 2, output tiles of exactly 64 pixels "
+              "(Cin=%d Cout=%d H=%d W=%d)", Cin, Cout, H, W);
   return rc;
 }
 

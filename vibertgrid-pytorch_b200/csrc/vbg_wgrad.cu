@@ -27,9 +27,13 @@ __device__ __forceinline__ uint64_t make_sw128_mn_desc(uint32_t smem_addr, uint3
 
 struct WgParams {
   TcParams tc;          // epilogue view: C = out or workspace, ldc, M = N (rows of dW), N = K (columns of dW)
-  int rows;             // reduction length (rows of dY / X)
+  int rows;             // reduction length (rows of dY / X); conv: number of 64-pixel blocks * 64
   int blocks_per_split; // 64-row blocks per split
   int n_tiles, k_tiles; // output tiles
+  // conv (conv == 1): a 64-row block is tb images x th rows x tw columns of OUTPUT pixels (tw*th*tb == 64); the X operand of
+  // output-column tile kt is the input window of filter tap kt / cin_tiles shifted by (r - pad, s - pad), stride `st`
+  int conv, tw, th, tb, tiles_w, tiles_h, kw, cin_tiles, st, pad;
+  int box_rows;         // rows one TMA box delivers (64, or tw*th*tb < 64: the remaining rows of a stage are zeroed once and never written)
 };
 
 template <int BN, int STAGES>
@@ -55,6 +59,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
   const int b0 = split * wp.blocks_per_split, b1 = min(b0 + wp.blocks_per_split, n_blocks);
 
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmY); prefetch_tmap(&tmX); }
+  if (wp.box_rows < 64) {                          // short boxes: rows past the box stay zero for the whole launch
+    uint4* z = reinterpret_cast<uint4*>(ring);
+    for (uint32_t i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += kWgThreads) z[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -77,13 +86,29 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
         uint8_t* sy = ring + s * STAGE_BYTES;
         uint8_t* sx = sy + 2 * A_PLANE;
-        mbar_expect_tx(&full[s], STAGE_BYTES);
+        mbar_expect_tx(&full[s], (STAGE_BYTES / 64) * (uint32_t)wp.box_rows);
+        if (wp.conv) {
+          int i = b;
+          const int w0 = (i % wp.tiles_w) * wp.tw; i /= wp.tiles_w;
+          const int h0 = (i % wp.tiles_h) * wp.th; const int bb = (i / wp.tiles_h) * wp.tb;
+          const int kt = k0 / BN, tap = kt / wp.cin_tiles, c0 = (kt - tap * wp.cin_tiles) * BN;
+          const int fr = tap / wp.kw, fs = tap - fr * wp.kw;
+          const int xw = w0 * wp.st + fs - wp.pad, xh = h0 * wp.st + fr - wp.pad;
 #pragma unroll
-        for (int pl = 0; pl < 2; ++pl) {
+          for (int pl = 0; pl < 2; ++pl) {
 #pragma unroll
-          for (int j = 0; j < 2; ++j) tma_load_3d(&tmY, &full[s], sy + pl * A_PLANE + j * kWgBox, n0 + 64 * j, b * 64, pl);
+            for (int j = 0; j < 2; ++j) tma_load_5d(&tmY, &full[s], sy + pl * A_PLANE + j * kWgBox, n0 + 64 * j, w0, h0, bb, pl);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_3d(&tmX, &full[s], sx + pl * B_PLANE + j * kWgBox, k0 + 64 * j, b * 64, pl);
+            for (int j = 0; j < BN / 64; ++j) tma_load_5d(&tmX, &full[s], sx + pl * B_PLANE + j * kWgBox, c0 + 64 * j, xw, xh, bb, pl);
+          }
+        } else {
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) tma_load_3d(&tmY, &full[s], sy + pl * A_PLANE + j * kWgBox, n0 + 64 * j, b * 64, pl);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_3d(&tmX, &full[s], sx + pl * B_PLANE + j * kWgBox, k0 + 64 * j, b * 64, pl);
+          }
         }
       }
     }
@@ -173,7 +198,7 @@ int linear_wgrad(const void* dY, long long y_plane, const void* X, long long x_p
   CUtensorMap ty, tx;
   if (!map_rows(&ty, dY, y_plane, M, N, N) || !map_rows(&tx, X, x_plane, M, K, K)) return VBG_EUNSUPPORTED;
   WgParams wp{};
-  wp.rows = M; wp.n_tiles = N / 128; wp.k_tiles = cdiv(K, bn);
+  wp.rows = M; wp.box_rows = 64; wp.n_tiles = N / 128; wp.k_tiles = cdiv(K, bn);
   const int tiles = wp.n_tiles * wp.k_tiles, n_blocks = cdiv(M, 64);
   int splits = wg_splits(tiles, n_blocks);
   if (splits > 1 && (!workspace || !aligned16(workspace) || (size_t)splits * N * K * 4 > ws_bytes)) splits = 1;
@@ -184,6 +209,68 @@ int linear_wgrad(const void* dY, long long y_plane, const void* X, long long x_p
   int rc = bn == 128 ? launch_wg<128, 3>(ty, tx, wp, tiles * splits, s) : launch_wg<64, 4>(ty, tx, wp, tiles * splits, s);
   if (rc != VBG_OK || splits == 1) return rc;
   return splitk_finish(reinterpret_cast<const float*>(workspace), splits, N, K, vbg_epilogue_t{}, dW, K, s);
+}
+
+// dW[Cout, kh, kw, Cin] = sum over output pixels of dY[b,ho,wo,Cout] x X[b, ho*st + r - pad, wo*st + s - pad, Cin]: the same kernel, the
+// X boxes come from a rank-5 NHWC map at the tap's shift (padding = TMA out-of-bounds zero fill, stride = traversal stride).
+static bool wg_conv_geometry(int B, int Ho, int Wo, WgParams& wp) {
+  wp.tw = Wo < 64 ? Wo : 64;
+  wp.th = (64 / wp.tw) < Ho ? (64 / wp.tw) : Ho;
+  wp.tb = (wp.th == Ho && wp.tw == Wo) ? ((64 / (wp.tw * wp.th)) < B ? (64 / (wp.tw * wp.th)) : B) : 1;
+  wp.box_rows = wp.tw * wp.th * wp.tb;                  // <= 64 by construction
+  wp.tiles_w = cdiv(Wo, wp.tw); wp.tiles_h = cdiv(Ho, wp.th);
+  wp.rows = wp.tiles_w * wp.tiles_h * cdiv(B, wp.tb) * 64;
+  return true;
+}
+
+size_t conv_wgrad_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad) {
+  if (Cout % 128 || Cin % 64 || stride < 1 || stride > 2) return 0;
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  WgParams wp{};
+  if (Ho <= 0 || Wo <= 0 || !wg_conv_geometry(B, Ho, Wo, wp)) return 0;
+  const int bn = Cin % 128 == 0 ? 128 : 64;
+  const int tiles = (Cout / 128) * kh * kw * (Cin / bn);
+  const int s = wg_splits(tiles, wp.rows / 64);
+  return s > 1 ? (size_t)s * Cout * kh * kw * Cin * 4 : 0;
+}
+
+int conv_wgrad(const void* dY, long long y_plane, const void* X, long long x_plane, int B, int H, int W, int Cin, int Cout, int kh, int kw,
+               int stride, int pad, float* dW, void* workspace, size_t ws_bytes, cudaStream_t s) {
+  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (Cout % 128 || Cin % 64 || stride < 1 || stride > 2 || !aligned16(dY) || !aligned16(X) || !aligned16(dW) || (y_plane & 7) ||
+      (x_plane & 7) || y_plane <= 0 || x_plane <= 0)
+    return VBG_EUNSUPPORTED;
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  WgParams wp{};
+  if (Ho <= 0 || Wo <= 0 || !wg_conv_geometry(B, Ho, Wo, wp)) return VBG_EUNSUPPORTED;
+  if (wp.tw * stride > 256 || wp.th * stride > 256) return VBG_EUNSUPPORTED;
+  const int bn = Cin % 128 == 0 ? 128 : 64, Kt = kh * kw * Cin;
+  wp.conv = 1; wp.kw = kw; wp.cin_tiles = Cin / bn; wp.st = stride; wp.pad = pad;
+  wp.n_tiles = Cout / 128; wp.k_tiles = kh * kw * wp.cin_tiles;
+  CUtensorMap ty, tx;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B, 2};
+    cuuint64_t str[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)Wo * Cout * 2, (cuuint64_t)Ho * Wo * Cout * 2, (cuuint64_t)y_plane * 2};
+    cuuint32_t box[5] = {64u, (cuuint32_t)wp.tw, (cuuint32_t)wp.th, (cuuint32_t)wp.tb, 1u};
+    if (!tc_encode(&ty, dY, 5, dims, str, box, nullptr, true)) return VBG_EUNSUPPORTED;
+  }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 2};
+    cuuint64_t str[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2, (cuuint64_t)x_plane * 2};
+    cuuint32_t box[5] = {64u, (cuuint32_t)(wp.tw * stride), (cuuint32_t)(wp.th * stride), (cuuint32_t)wp.tb, 1u};
+    cuuint32_t estr[5] = {1u, (cuuint32_t)stride, (cuuint32_t)stride, 1u, 1u};
+    if (!tc_encode(&tx, X, 5, dims, str, box, estr, true)) return VBG_EUNSUPPORTED;
+  }
+  const int tiles = wp.n_tiles * wp.k_tiles, n_blocks = wp.rows / 64;
+  int splits = wg_splits(tiles, n_blocks);
+  if (splits > 1 && (!workspace || !aligned16(workspace) || (size_t)splits * Cout * Kt * 4 > ws_bytes)) splits = 1;
+  wp.blocks_per_split = cdiv(n_blocks, splits);
+  splits = cdiv(n_blocks, wp.blocks_per_split);
+  wp.tc.M = Cout; wp.tc.N = Kt; wp.tc.ldc = Kt; wp.tc.conv = 0; wp.tc.num_kb = 0;
+  wp.tc.C = splits > 1 ? reinterpret_cast<float*>(workspace) : dW;
+  int rc = bn == 128 ? launch_wg<128, 3>(ty, tx, wp, tiles * splits, s) : launch_wg<64, 4>(ty, tx, wp, tiles * splits, s);
+  if (rc != VBG_OK || splits == 1) return rc;
+  return splitk_finish(reinterpret_cast<const float*>(workspace), splits, Cout, Kt, vbg_epilogue_t{}, dW, Kt, s);
 }
 
 }  // namespace vbg

@@ -511,3 +511,14 @@ def linear_wgrad(dy_split, x_split):
     L.check(L.load().vbg_linear_wgrad(_p(dy_split.t), dy_split.plane, _p(x_split.t), x_split.plane, M, N, K, _f32(dw), _p(ws),
                                       0 if ws is None else ws.numel(), _stream()), "vbg_linear_wgrad")
     return dw
+
+
+def conv2d_wgrad(dy_split, x_split, kh, kw, stride, pad):
+    """dW [Cout, kh, kw, Cin] from Split dY [B,Ho,Wo,Cout] and Split X [B,H,W,Cin]."""
+    B, H, W, Cin = x_split.shape
+    Cout = dy_split.shape[-1]
+    dw = torch.empty((Cout, kh, kw, Cin), dtype=torch.float32, device=x_split.device)
+    ws = _workspace(L.load().vbg_conv2d_wgrad_workspace(B, H, W, Cin, Cout, kh, kw, stride, pad), x_split.device)
+    L.check(L.load().vbg_conv2d_wgrad(_p(dy_split.t), dy_split.plane, _p(x_split.t), x_split.plane, B, H, W, Cin, Cout, kh, kw, stride,
+                                      pad, _f32(dw), _p(ws), 0 if ws is None else ws.numel(), _stream()), "vbg_conv2d_wgrad")
+    return dw
