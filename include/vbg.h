@@ -245,6 +245,66 @@ VBG_API int vbg_conv_dgrad_weight(const float* w_ohwi, int Cout, int kh, int kw,
 VBG_API int vbg_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, int R, int hidden, float* dx,
                       float* dgamma, float* dbeta, float* workspace, size_t ws_bytes, vbg_stream_t stream);
 
+/* ---- training step: the backward of loss.backward() (pipeline/train_val_utils.py:277) through the modules of the path, and the
+ *      training-mode forward pieces (batch-statistics BatchNorm, dropout).  fp32 channels-last; reductions have a fixed order;
+ *      the only atomics are the scatter-adds of vbg_roi_align_bwd and vbg_embed_bwd.                                          */
+/* nn.BatchNorm2d in train mode (model/ResNetFPN_ViBERTgrid.py:106-186, semantic_segmentation_head.py:66, field_type_..._head.py:64)
+ * over [rows, C]: batch mean / biased variance / 1/sqrt(var+eps); C = 4 * a divisor of 256; workspace from vbg_bn_workspace     */
+VBG_API long long vbg_bn_workspace(long long rows, int C);
+VBG_API int vbg_bn_stats(const float* x, long long rows, int C, float eps, float* mean, float* var, float* rstd, float* workspace,
+                 size_t ws_bytes, vbg_stream_t stream);
+/* y = (x - mean) * rstd * gamma + beta (+ residual) (ReLU when relu != 0) */
+VBG_API int vbg_bn_apply(const float* x, long long rows, int C, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                 const float* residual, int relu, float* y, vbg_stream_t stream);
+/* backward of vbg_bn_apply(+stats): y_relu = the forward output when ReLU was applied (mask), else NULL; dres (may be NULL) receives
+ * the masked dy = the gradient of the residual input                                                                       */
+VBG_API int vbg_bn_bwd(const float* x, const float* dy, const float* y_relu, long long rows, int C, const float* mean, const float* rstd,
+               const float* gamma, float* dx, float* dres, float* dgamma, float* dbeta, float* workspace, size_t ws_bytes,
+               vbg_stream_t stream);
+/* dX of max_pool2d(3, 2, 1) (first-maximum rule), x [B,H,W,C], dy [B,Ho,Wo,C] */
+VBG_API int vbg_maxpool3x3s2_bwd(const float* x, const float* dy, int B, int H, int W, int C, float* dx, vbg_stream_t stream);
+/* y [B,H/2,W/2,C] = scale * 2x2 block sums: backward of the nearest-x2 upsample (scale 1) */
+VBG_API int vbg_sumpool2x2(const float* x, int B, int H, int W, int C, float scale, float* y, vbg_stream_t stream);
+/* y [B,H,W,C] from x [B,Hi,Wi,C]: nearest x2 times scale (backward of avg_pool2d(2): scale 0.25), or zero insertion (zero_insert != 0:
+ * dY of a stride-2 convolution spread onto the stride-1 lattice)                                                           */
+VBG_API int vbg_expand2x(const float* x, int B, int Hi, int Wi, int C, int H, int W, float scale, int zero_insert, float* y,
+                 vbg_stream_t stream);
+/* erf-GELU: out = gelu(x) when dy == NULL, else out = dy * gelu'(x) */
+VBG_API int vbg_gelu(const float* x, const float* dy, long long n, float* out, vbg_stream_t stream);
+/* inverted dropout with a counter-based mask: y[i] = x[i] * keep(seed, i) / (1 - p); the same call is its own backward */
+VBG_API int vbg_dropout(const float* x, long long n, float p, unsigned long long seed, float* y, vbg_stream_t stream);
+/* backward of vbg_grid_scatter: demb[k] = sum of dgrid over the cells segment k won (row stride ld floats between cells) */
+VBG_API int vbg_grid_scatter_bwd(const float* dgrid, long long ld, const int32_t* idx, const int32_t* boxes, const int32_t* seg_off, int B,
+                         int K, int stride, int Hg, int Wg, int C, float* demb, vbg_stream_t stream);
+/* backward of vbg_segment_reduce into the rows of dhidden that belong to a segment (caller zero-fills dhidden) */
+VBG_API int vbg_segment_reduce_bwd(const float* dseg, const int32_t* tok_row, const int32_t* seg_start, int K, int C, int mode,
+                           float* dhidden, vbg_stream_t stream);
+/* embedding tables: dword[ids[r]] += dx[r], dpos[pos[r]] += dx[r] (caller zero-fills the tables) */
+VBG_API int vbg_embed_bwd(const float* dx, const int32_t* ids, const int32_t* pos, int R, int hidden, float* dword, float* dpos,
+                  vbg_stream_t stream);
+/* backward of vbg_roi_align_fwd into dfeat [B,Hf,Wf,C] (caller zero-fills) */
+VBG_API int vbg_roi_align_bwd(const float* dout, int B, int Hf, int Wf, int C, const int32_t* boxes, const int32_t* seg_off, int K,
+                      float spatial_scale, int P, float* dfeat, vbg_stream_t stream);
+/* gradient of gscale[0] * mean CE(mask head) + gscale[1] * mean CE(class head) (semantic_segmentation_head.py:343-347) w.r.t. the
+ * LOW-resolution logits [B,H/up,W/up,Ct], labels = the int64 maps of vbg_label_paint                                       */
+VBG_API int vbg_seg_ce_bwd(const float* logits, const long long* pos_neg, const long long* cls, int B, int H, int W, int up, int Ct,
+                   int c_split, const float* gscale, float* dlogits, vbg_stream_t stream);
+/* backward of vbg_upsample_split_nchw */
+VBG_API int vbg_upsample_split_bwd(const float* d1, const float* d2, int B, int h, int w, int Ct, int up, int c_split, float* dlogits,
+                           vbg_stream_t stream);
+/* dW[N<=16, K] = dY^T X for the narrow heads (row strides ldy / ldx) */
+VBG_API long long vbg_small_wgrad_workspace(long long M, int N, int K);
+VBG_API int vbg_small_wgrad(const float* dy, int ldy, const float* x, int ldx, long long M, int N, int K, float* dw, float* workspace,
+                    size_t ws_bytes, vbg_stream_t stream);
+/* weight gradient of the 7x7/2 stem over the zero-bordered NHWC4 batch [B,Hp,Wp,4]: dw774 [64,7,7,4] */
+VBG_API long long vbg_stem_wgrad_workspace(void);
+VBG_API int vbg_stem_wgrad(const float* x4, const float* dy, int B, int Hp, int Wp, int Ho, int Wo, float* dw774, float* workspace,
+                   size_t ws_bytes, vbg_stream_t stream);
+/* self-attention backward over the packed varlen batch (head dimension 64): dqkv [rows, 3*heads*64] from qkv, the forward output
+ * and its gradient; workspace >= rows * heads * 2 floats (row log-sum-exp and delta)                                      */
+VBG_API int vbg_attention_bwd(const float* qkv, const float* out, const float* d_out, const int32_t* cu, int nseq, int max_len, int heads,
+                      int head_dim, long long rows, float* dqkv, float* workspace, size_t ws_bytes, vbg_stream_t stream);
+
 /* ---- a7: GridROIAlign (model/grid_roi_align.py:37-41,81 -> torchvision roi_align, aligned=False,
  *          sampling_ratio=-1) over NHWC features; boxes are the int32 transformed coords.         */
 VBG_API int vbg_roi_align_fwd(const float* feat, int B, int Hf, int Wf, int C, const int32_t* boxes, const int32_t* seg_off,

@@ -81,7 +81,7 @@ def test_conv2d_ps_data_gradient(B, H, W, Cin, Cout, k, p):
     assert relerr(xc.grad.permute(0, 3, 1, 2).cpu().numpy(), xd.grad.numpy()) < 3e-5
 
 
-@pytest.mark.parametrize("M,N,K", [(4128, 768, 768), (516, 3072, 768), (1000, 768, 3072), (130, 128, 64), (64, 128, 128), (8256, 256, 192)])
+@pytest.mark.parametrize("M,N,K", [(4128, 768, 768), (516, 3072, 768), (1000, 768, 3072), (130, 128, 64), (64, 128, 128), (8256, 256, 192), (700, 64, 128), (300, 192, 64)])
 def test_linear_wgrad_mn_major(M, N, K):
     """dW = dY^T X with both operands fed to tcgen05 as MN-major tiles (no transposes), row range split over CTAs with a
     deterministic finish: equals the float64 product of the plane operands; bit-identical run to run."""
@@ -103,6 +103,8 @@ def test_linear_wgrad_mn_major(M, N, K):
     (2, 20, 42, 64, 128, 1, 1, 0),      # 1x1, short rows (42 < 64)
     (2, 32, 64, 64, 128, 3, 2, 1),      # stride 2 through the traversal stride
     (1, 16, 32, 192, 128, 1, 1, 0),     # Cin = 3 x 64
+    (2, 16, 64, 64, 64, 3, 1, 1),       # Cout = 64: the upper half of the 128-row tile is TMA zero fill
+    (2, 16, 16, 128, 192, 3, 2, 1),     # Cout = 192 = 128 + 64
 ])
 def test_conv2d_wgrad_mn_major(B, H, W, Cin, Cout, k, stride, pad):
     """dW of an NHWC convolution from the plane operands (vbg_conv2d_wgrad) against torch float64 autograd; two runs agree

@@ -78,6 +78,26 @@ SIGNATURES = {
     "vbg_linear_wgrad": [_p, _ll, _p, _ll, _i, _i, _i, _p, _p, _sz, _p],
     "vbg_conv_dgrad_weight": [_p, _i, _i, _i, _i, _p, _ll, _p],
     "vbg_layernorm_bwd": [_p, _p, _p, _f, _i, _i, _p, _p, _p, _p, _sz, _p],
+    "vbg_bn_workspace": [_ll, _i],
+    "vbg_bn_stats": [_p, _ll, _i, _f, _p, _p, _p, _p, _sz, _p],
+    "vbg_bn_apply": [_p, _ll, _i, _p, _p, _p, _p, _p, _i, _p, _p],
+    "vbg_bn_bwd": [_p, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
+    "vbg_maxpool3x3s2_bwd": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "vbg_sumpool2x2": [_p, _i, _i, _i, _i, _f, _p, _p],
+    "vbg_expand2x": [_p, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p],
+    "vbg_gelu": [_p, _p, _ll, _p, _p],
+    "vbg_dropout": [_p, _ll, _f, C.c_ulonglong, _p, _p],
+    "vbg_grid_scatter_bwd": [_p, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
+    "vbg_segment_reduce_bwd": [_p, _p, _p, _i, _i, _i, _p, _p],
+    "vbg_embed_bwd": [_p, _p, _p, _i, _i, _p, _p, _p],
+    "vbg_roi_align_bwd": [_p, _i, _i, _i, _i, _p, _p, _i, _f, _i, _p, _p],
+    "vbg_seg_ce_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p],
+    "vbg_upsample_split_bwd": [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
+    "vbg_small_wgrad_workspace": [_ll, _i, _i],
+    "vbg_small_wgrad": [_p, _i, _p, _i, _ll, _i, _i, _p, _p, _sz, _p],
+    "vbg_stem_wgrad_workspace": [],
+    "vbg_stem_wgrad": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p],
+    "vbg_attention_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _ll, _p, _p, _sz, _p],
     "vbg_softmax_rows": [_p, _i, _i, _p, _p],
     "vbg_full_head_scores": [_p, _p, _i, _i, _p, _p],
     "vbg_upsample_split_nchw": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p],

@@ -182,9 +182,9 @@ static int wg_splits(int tiles, int n_blocks) {
 }
 
 size_t linear_wgrad_workspace(int M, int N, int K) {
-  if (N % 128 || K % 64 || M <= 0) return 0;
+  if (N % 64 || K % 64 || M <= 0) return 0;
   const int bn = K % 128 == 0 ? 128 : 64;
-  const int tiles = (N / 128) * cdiv(K, bn), n_blocks = cdiv(M, 64);
+  const int tiles = cdiv(N, 128) * cdiv(K, bn), n_blocks = cdiv(M, 64);
   const int s = wg_splits(tiles, n_blocks);
   return s > 1 ? (size_t)s * N * K * 4 : 0;
 }
@@ -192,13 +192,13 @@ size_t linear_wgrad_workspace(int M, int N, int K) {
 int linear_wgrad(const void* dY, long long y_plane, const void* X, long long x_plane, int M, int N, int K, float* dW, void* workspace,
                  size_t ws_bytes, cudaStream_t s) {
   if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
-  if (N % 128 || K % 64 || !aligned16(dY) || !aligned16(X) || !aligned16(dW) || (y_plane & 7) || (x_plane & 7) || y_plane <= 0 || x_plane <= 0)
+  if (N % 64 || K % 64 || !aligned16(dY) || !aligned16(X) || !aligned16(dW) || (y_plane & 7) || (x_plane & 7) || y_plane <= 0 || x_plane <= 0)
     return VBG_EUNSUPPORTED;
   const int bn = K % 128 == 0 ? 128 : 64;
   CUtensorMap ty, tx;
   if (!map_rows(&ty, dY, y_plane, M, N, N) || !map_rows(&tx, X, x_plane, M, K, K)) return VBG_EUNSUPPORTED;
   WgParams wp{};
-  wp.rows = M; wp.box_rows = 64; wp.n_tiles = N / 128; wp.k_tiles = cdiv(K, bn);
+  wp.rows = M; wp.box_rows = 64; wp.n_tiles = cdiv(N, 128); wp.k_tiles = cdiv(K, bn);
   const int tiles = wp.n_tiles * wp.k_tiles, n_blocks = cdiv(M, 64);
   int splits = wg_splits(tiles, n_blocks);
   if (splits > 1 && (!workspace || !aligned16(workspace) || (size_t)splits * N * K * 4 > ws_bytes)) splits = 1;
@@ -224,12 +224,12 @@ static bool wg_conv_geometry(int B, int Ho, int Wo, WgParams& wp) {
 }
 
 size_t conv_wgrad_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad) {
-  if (Cout % 128 || Cin % 64 || stride < 1 || stride > 2) return 0;
+  if (Cout % 64 || Cin % 64 || stride < 1 || stride > 2) return 0;
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
   WgParams wp{};
   if (Ho <= 0 || Wo <= 0 || !wg_conv_geometry(B, Ho, Wo, wp)) return 0;
   const int bn = Cin % 128 == 0 ? 128 : 64;
-  const int tiles = (Cout / 128) * kh * kw * (Cin / bn);
+  const int tiles = cdiv(Cout, 128) * kh * kw * (Cin / bn);
   const int s = wg_splits(tiles, wp.rows / 64);
   return s > 1 ? (size_t)s * Cout * kh * kw * Cin * 4 : 0;
 }
@@ -237,7 +237,7 @@ size_t conv_wgrad_workspace(int B, int H, int W, int Cin, int Cout, int kh, int 
 int conv_wgrad(const void* dY, long long y_plane, const void* X, long long x_plane, int B, int H, int W, int Cin, int Cout, int kh, int kw,
                int stride, int pad, float* dW, void* workspace, size_t ws_bytes, cudaStream_t s) {
   if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
-  if (Cout % 128 || Cin % 64 || stride < 1 || stride > 2 || !aligned16(dY) || !aligned16(X) || !aligned16(dW) || (y_plane & 7) ||
+  if (Cout % 64 || Cin % 64 || stride < 1 || stride > 2 || !aligned16(dY) || !aligned16(X) || !aligned16(dW) || (y_plane & 7) ||
       (x_plane & 7) || y_plane <= 0 || x_plane <= 0)
     return VBG_EUNSUPPORTED;
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
@@ -246,7 +246,7 @@ int conv_wgrad(const void* dY, long long y_plane, const void* X, long long x_pla
   if (wp.tw * stride > 256 || wp.th * stride > 256) return VBG_EUNSUPPORTED;
   const int bn = Cin % 128 == 0 ? 128 : 64, Kt = kh * kw * Cin;
   wp.conv = 1; wp.kw = kw; wp.cin_tiles = Cin / bn; wp.st = stride; wp.pad = pad;
-  wp.n_tiles = Cout / 128; wp.k_tiles = kh * kw * wp.cin_tiles;
+  wp.n_tiles = cdiv(Cout, 128); wp.k_tiles = kh * kw * wp.cin_tiles;   // Cout % 128 == 64: the upper half tile is TMA zero fill
   CUtensorMap ty, tx;
   {
     cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)B, 2};

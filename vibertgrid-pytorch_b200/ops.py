@@ -522,3 +522,162 @@ def conv2d_wgrad(dy_split, x_split, kh, kw, stride, pad):
     L.check(L.load().vbg_conv2d_wgrad(_p(dy_split.t), dy_split.plane, _p(x_split.t), x_split.plane, B, H, W, Cin, Cout, kh, kw, stride,
                                       pad, _f32(dw), _p(ws), 0 if ws is None else ws.numel(), _stream()), "vbg_conv2d_wgrad")
     return dw
+
+
+# ------------------------------------------------------------------ training-step kernels (csrc/vbg_train.cu, vbg_attn_bwd.cu)
+def _raw(t, name="tensor"):
+    """fp32 CUDA tensor whose last dimension is dense (row-strided views allowed)."""
+    if not t.is_cuda or t.dtype != torch.float32 or t.stride(-1) != 1:
+        raise TypeError(f"{name} must be an fp32 CUDA tensor with a dense last dimension")
+    return t.data_ptr()
+
+
+def _ws_f32(nbytes, device):
+    return torch.empty(max(int(nbytes) // 4, 1), dtype=torch.float32, device=device)
+
+
+def bn_stats(x2d, eps):
+    """Batch statistics of [rows, C]: (mean, biased var, rstd)."""
+    rows, Cc = x2d.shape
+    mean, var, rstd = (torch.empty(Cc, dtype=torch.float32, device=x2d.device) for _ in range(3))
+    ws = _ws_f32(L.load().vbg_bn_workspace(rows, Cc), x2d.device)
+    L.check(L.load().vbg_bn_stats(_f32(x2d), rows, Cc, eps, _f32(mean), _f32(var), _f32(rstd), _f32(ws), ws.numel() * 4, _stream()),
+            "vbg_bn_stats")
+    return mean, var, rstd
+
+
+def bn_apply(x2d, mean, rstd, gamma, beta, residual=None, relu=False):
+    rows, Cc = x2d.shape
+    y = torch.empty_like(x2d)
+    L.check(L.load().vbg_bn_apply(_f32(x2d), rows, Cc, _f32(mean), _f32(rstd), _f32(gamma), _f32(beta),
+                                  None if residual is None else _f32(residual), int(relu), _f32(y), _stream()), "vbg_bn_apply")
+    return y
+
+
+def bn_bwd(x2d, dy2d, y_relu, mean, rstd, gamma, want_dres=False):
+    """-> (dx, dres or None, dgamma, dbeta)."""
+    rows, Cc = x2d.shape
+    dx = torch.empty_like(x2d)
+    dres = torch.empty_like(x2d) if want_dres else None
+    dg, db = (torch.empty(Cc, dtype=torch.float32, device=x2d.device) for _ in range(2))
+    ws = _ws_f32(L.load().vbg_bn_workspace(rows, Cc), x2d.device)
+    L.check(L.load().vbg_bn_bwd(_f32(x2d), _f32(dy2d), None if y_relu is None else _f32(y_relu), rows, Cc, _f32(mean), _f32(rstd),
+                                _f32(gamma), _f32(dx), None if dres is None else _f32(dres), _f32(dg), _f32(db), _f32(ws),
+                                ws.numel() * 4, _stream()), "vbg_bn_bwd")
+    return dx, dres, dg, db
+
+
+def maxpool3x3s2_bwd(x, dy):
+    B, H, W, Cc = x.shape
+    dx = torch.empty_like(x)
+    L.check(L.load().vbg_maxpool3x3s2_bwd(_f32(x), _f32(dy), B, H, W, Cc, _f32(dx), _stream()), "vbg_maxpool3x3s2_bwd")
+    return dx
+
+
+def sumpool2x2(x, scale=1.0):
+    B, H, W, Cc = x.shape
+    y = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.float32, device=x.device)
+    L.check(L.load().vbg_sumpool2x2(_f32(x), B, H, W, Cc, scale, _f32(y), _stream()), "vbg_sumpool2x2")
+    return y
+
+
+def expand2x(x, H, W, scale=1.0, zero_insert=False):
+    B, Hi, Wi, Cc = x.shape
+    y = torch.empty((B, H, W, Cc), dtype=torch.float32, device=x.device)
+    L.check(L.load().vbg_expand2x(_f32(x), B, Hi, Wi, Cc, H, W, scale, int(zero_insert), _f32(y), _stream()), "vbg_expand2x")
+    return y
+
+
+def gelu(x, dy=None):
+    out = torch.empty_like(x)
+    L.check(L.load().vbg_gelu(_f32(x), None if dy is None else _f32(dy), x.numel(), _f32(out), _stream()), "vbg_gelu")
+    return out
+
+
+def dropout(x, p, seed):
+    y = torch.empty_like(x)
+    L.check(L.load().vbg_dropout(_f32(x), x.numel(), p, seed, _f32(y), _stream()), "vbg_dropout")
+    return y
+
+
+def grid_scatter_bwd(dgrid_cells, ld, idx, boxes, seg_off, B, K, stride, Cc):
+    """``dgrid_cells``: fp32 view whose cell rows are ``ld`` floats apart (a column slice of a wider gradient is fine)."""
+    Hg, Wg = idx.shape[1], idx.shape[2]
+    demb = torch.empty((K, Cc), dtype=torch.float32, device=idx.device)
+    L.check(L.load().vbg_grid_scatter_bwd(_raw(dgrid_cells), ld, _i32(idx), _i32(boxes), _i32(seg_off), B, K, stride, Hg, Wg, Cc,
+                                          _f32(demb), _stream()), "vbg_grid_scatter_bwd")
+    return demb
+
+
+def segment_reduce_bwd(dseg, tok_row, seg_start, R, mode=AGG_MEAN):
+    K, Cc = dseg.shape
+    dh = torch.zeros((R, Cc), dtype=torch.float32, device=dseg.device)
+    L.check(L.load().vbg_segment_reduce_bwd(_f32(dseg), _i32(tok_row), _i32(seg_start), K, Cc, mode, _f32(dh), _stream()),
+            "vbg_segment_reduce_bwd")
+    return dh
+
+
+def embed_bwd(dx, ids, pos, vocab, max_pos):
+    R, Hd = dx.shape
+    dword = torch.zeros((vocab, Hd), dtype=torch.float32, device=dx.device)
+    dpos = torch.zeros((max_pos, Hd), dtype=torch.float32, device=dx.device)
+    L.check(L.load().vbg_embed_bwd(_f32(dx), _i32(ids), _i32(pos), R, Hd, _f32(dword), _f32(dpos), _stream()), "vbg_embed_bwd")
+    return dword, dpos
+
+
+def roi_align_bwd(dout, boxes, seg_off, B, Hf, Wf, spatial_scale):
+    K, Pp, _, Cc = dout.shape
+    dfeat = torch.zeros((B, Hf, Wf, Cc), dtype=torch.float32, device=dout.device)
+    L.check(L.load().vbg_roi_align_bwd(_f32(dout), B, Hf, Wf, Cc, _i32(boxes), _i32(seg_off), K, spatial_scale, Pp, _f32(dfeat),
+                                       _stream()), "vbg_roi_align_bwd")
+    return dfeat
+
+
+def seg_ce_bwd(logits_lowres, pos_neg, cls, H, W, up, c_split, gscale):
+    B, h, w, Ct = logits_lowres.shape
+    dl = torch.empty_like(logits_lowres)
+    L.check(L.load().vbg_seg_ce_bwd(_f32(logits_lowres), _p(pos_neg, torch.int64), _p(cls, torch.int64), B, H, W, up, Ct, c_split,
+                                    _f32(gscale), _f32(dl), _stream()), "vbg_seg_ce_bwd")
+    return dl
+
+
+def upsample_split_bwd(d1, d2, up):
+    B, c_split, H, W = d1.shape
+    Ct = c_split + d2.shape[1]
+    dl = torch.empty((B, H // up, W // up, Ct), dtype=torch.float32, device=d1.device)
+    L.check(L.load().vbg_upsample_split_bwd(_f32(d1.contiguous()), _f32(d2.contiguous()), B, H // up, W // up, Ct, up, c_split,
+                                            _f32(dl), _stream()), "vbg_upsample_split_bwd")
+    return dl
+
+
+def small_wgrad(dy2d, x2d):
+    """dW [N <= 16, K] = dY^T X (row strides taken from the tensors: column slices are fine)."""
+    M, N = dy2d.shape
+    K = x2d.shape[1]
+    dw = torch.empty((N, K), dtype=torch.float32, device=x2d.device)
+    ws = _ws_f32(L.load().vbg_small_wgrad_workspace(M, N, K), x2d.device)
+    L.check(L.load().vbg_small_wgrad(_raw(dy2d), dy2d.stride(0), _raw(x2d), x2d.stride(0), M, N, K, _f32(dw), _f32(ws),
+                                     ws.numel() * 4, _stream()), "vbg_small_wgrad")
+    return dw
+
+
+def stem_wgrad(x4, dy):
+    """dW [64,7,7,4] of the 7x7/2 stem from the zero-bordered NHWC4 batch and dY [B,Ho,Wo,64]."""
+    B, Hp, Wp, _ = x4.shape
+    _, Ho, Wo, Cout = dy.shape
+    assert Cout == 64
+    dw = torch.empty((64, 7, 7, 4), dtype=torch.float32, device=dy.device)
+    ws = _ws_f32(L.load().vbg_stem_wgrad_workspace(), dy.device)
+    L.check(L.load().vbg_stem_wgrad(_f32(x4), _f32(dy), B, Hp, Wp, Ho, Wo, _f32(dw), _f32(ws), ws.numel() * 4, _stream()),
+            "vbg_stem_wgrad")
+    return dw
+
+
+def attention_bwd(qkv, out, d_out, cu, nseq, max_len, heads):
+    R, three_hid = qkv.shape
+    hid = three_hid // 3
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty(R * heads * 2, dtype=torch.float32, device=qkv.device)
+    L.check(L.load().vbg_attention_bwd(_f32(qkv), _f32(out), _f32(d_out), _i32(cu), nseq, max_len, heads, hid // heads, R, _f32(dqkv),
+                                       _f32(ws), ws.numel() * 4, _stream()), "vbg_attention_bwd")
+    return dqkv
