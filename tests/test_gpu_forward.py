@@ -78,9 +78,9 @@ def test_inference_entry_point_and_mode_quirk(tmp_path, monkeypatch):
     img, seg, cls, coors, corpus, mask = _to_dev(batch)
     pred = net.inference(img, seg, coors, corpus, mask)
     assert relerr(pred.cpu().numpy(), fx["pred_label"]) < 1e-3
-    net.train()
-    with pytest.raises(NotImplementedError):
-        net(img, seg, cls, coors, corpus, mask)
+    net.train()                                                  # training mode returns the loss alone (ViBERTgrid_net.py:541)
+    loss = net(img, seg, cls, coors, corpus, mask)
+    assert isinstance(loss, torch.Tensor) and loss.dim() == 0 and loss.requires_grad
 
 
 def test_full_size_properties_cfg2(tmp_path, monkeypatch):

@@ -87,3 +87,38 @@ def test_known_answers_from_survey():
     g = [oracle_ops.roi_geometry(np.array(b, np.float32), 0.25, 7)[4:] for b in
          ([0, 0, 40, 40], [8, 8, 8, 8], [0, 0, 75, 110], [0, 0, 28, 56])]
     assert g == [(2, 2), (1, 1), (3, 4), (1, 2)]
+
+
+@pytest.mark.parametrize("name", ["train_tiny", "train_mid", "train_tiny_d", "train_tiny_pre"])
+def test_train_oracle_matches_reference(name, tmp_path, monkeypatch):
+    """The training-step restatement (oracle/oracle_train.py, float64) against the unmodified reference's loss and parameter
+    gradients (fixtures of oracle/make_train_golden.py)."""
+    import torch
+    from conftest import build_case
+    from oracle import oracle_net, oracle_train
+    fx = load_golden(name)
+    monkeypatch.chdir(tmp_path)
+    cfg, kw, net, batch = build_case(fx["meta"])
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    ocfg = oracle_net.OracleConfig(backbone=cfg.backbone, classifier_mode="simp", num_classes=cfg.num_classes,
+                                   min_size=kw["image_min_size"][0], max_size=kw["image_max_size"])
+    loss, grads, _ = oracle_train.train_step(sd, ocfg, *batch)
+    torch.set_grad_enabled(True)
+    want = float(fx["loss"][0])
+    assert abs(float(loss) - want) <= 2e-5 * max(1.0, abs(want))
+    bad = []
+    for k in fx["grad_names"]:
+        k = str(k)
+        ref = fx["g:" + k]
+        f = grads[k].double().reshape(-1)
+        idx = torch.linspace(0, f.numel() - 1, min(64, f.numel())).long()
+        scale = max(np.abs(ref[2:]).max(), ref[1] / np.sqrt(f.numel()), 1e-12)
+        err = np.abs(f[idx].numpy() - ref[2:]).max() / scale
+        nerr = abs(float(f.norm()) - ref[1]) / max(ref[1], 1e-12)
+        if k.endswith("attention.self.key.bias"):      # exactly zero (softmax shift invariance); the reference holds rounding noise
+            assert float(f.abs().max()) < 1e-12 and ref[1] < 1e-5
+            continue
+        # the fp32 reference itself is 1e-3 (median) .. 1.6e-2 away from this float64 restatement (ill-conditioned tiny batches)
+        if err > 2.5e-2 or nerr > 2e-3:
+            bad.append((k, float(err), float(nerr)))
+    assert not bad, bad[:10]

@@ -1,6 +1,10 @@
-"""First brick of the training step: a linear layer whose forward AND backward run on the pre-split
-tcgen05 GEMM -- the autograd boundary the reference's ``loss.backward()`` (``pipeline/train_val_utils.py:277``) will cross for
-every ``nn.Linear`` on the path (HF ``BertSelfOutput`` / ``BertIntermediate`` / ``BertOutput``, the head MLPs).
+"""The autograd boundary of the training step (SURVEY.md 8b "Autograd"): one ``torch.autograd.Function`` per CUDA stage, so
+the reference's ``loss.backward()`` (``pipeline/train_val_utils.py:277``) lands gradients in the ``.grad`` of the registered
+parameters.  Every forward and backward below is a kernel of libvbg_sm100a (tensors are fp32, channels-last); torch is the
+tape, the allocator and the handful of residual adds / concatenations between stages.
+
+The first brick, a linear layer on the pre-split tcgen05 GEMM (HF ``BertSelfOutput`` / ``BertIntermediate`` / ``BertOutput``,
+the head MLPs, every 1x1 convolution):
 
     y = LinearPS.apply(x, weight, bias)          # x [M, K] fp32 CUDA, weight [N, K], bias [N]; N, K multiples of 64
 
@@ -9,14 +13,23 @@ backward:  dX = dY . W          (the forward GEMM over dY planes and the planes 
                                  over CTAs with a deterministic finish; N % 128 != 0 falls back to transposed planes + the
                                  forward GEMM)
            db = column sums of dY (fixed order)
-All three are bf16x3 products with fp32 accumulation (fp32-class).  Not yet wired into ViBERTgridNet: the training-mode
-forward of the whole module is the next milestone.
+All three are bf16x3 products with fp32 accumulation (fp32-class).  ``train_engine.py`` wires these into the training-mode
+forward of ViBERTgridNet.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
 from . import ops
+
+
+def _fp32():
+    """VBG_PRECISION=fp32 (the exact CUDA-core mode of the eval engine): forward and data-gradient contractions run on the fp32
+    SIMT kernels; weight gradients stay on the tensor cores (their error does not propagate).  Used to separate rounding noise
+    from wiring errors when comparing a training step with the reference."""
+    return os.environ.get("VBG_PRECISION", "").lower() == "fp32"
 
 
 class LinearPS(torch.autograd.Function):
@@ -24,10 +37,12 @@ class LinearPS(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         if x.dim() != 2 or weight.shape[1] != x.shape[1] or weight.shape[0] % 64 or weight.shape[1] % 64:
             raise ValueError("LinearPS: x [M, K], weight [N, K] with N and K multiples of 64")
-        xs = ops.to_split(x.detach().contiguous())
         w = weight.detach().contiguous()
-        y = ops.gemm(xs, w, ep=ops.make_epilogue(None, None if bias is None else bias.detach()), precision=ops.PREC_BF16X3,
-                     W_split=ops.split_bf16(w))
+        ep = ops.make_epilogue(None, None if bias is None else bias.detach())
+        if _fp32():
+            y = ops.gemm(x.detach().contiguous(), w, ep=ep, precision=ops.PREC_FP32)
+        else:
+            y = ops.gemm(ops.to_split(x.detach().contiguous()), w, ep=ep, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w))
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         return y
@@ -40,17 +55,14 @@ class LinearPS(torch.autograd.Function):
         dy = dy.contiguous()
         dys = ops.to_split(dy)
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and _fp32():
+            dx = ops.gemm(dy, weight.detach().t().contiguous(), precision=ops.PREC_FP32)
+        elif ctx.needs_input_grad[0]:
             wt = ops.transpose_split(weight.detach().contiguous())                 # [K, N] planes
             dx = ops.gemm(dys, weight.detach().t(), precision=ops.PREC_BF16X3, W_split=wt.t, N=K, K=N, ldw=N)
         if ctx.needs_input_grad[1]:
-            if N % 128 == 0:                       # MN-major tcgen05 operands straight from the row-major planes
-                dw = ops.linear_wgrad(dys, ops.to_split(x.detach().contiguous()))
-            else:                                  # transposed-operand route through the forward GEMM
-                Mp = (M + 63) // 64 * 64
-                dyt = ops.transpose_split(dys, Mp)                                 # [N, Mp] planes
-                xt = ops.transpose_split(x.detach().contiguous(), Mp)              # [K, Mp] planes
-                dw = ops.gemm(dyt, x.detach(), precision=ops.PREC_BF16X3, W_split=xt.t, N=K, K=Mp, ldw=Mp)
+            # MN-major tcgen05 operands straight from the row-major planes (no transposes)
+            dw = ops.linear_wgrad(dys, ops.to_split(x.detach().contiguous()))
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy)
         return dx, dw, db
@@ -98,3 +110,306 @@ class Conv2dS1PS(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = ops.conv2d_wgrad(dys, ops.to_split(x.detach().contiguous()), kh, kw, 1, ctx.pad)
         return dx, dw, None
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class LinearSmall(torch.autograd.Function):
+    """Linear layers the tensor-core kernels do not take (N <= 16 outputs: the 2 / C-way heads, the packed 1x1 segmentation
+    heads): CUDA-core GEMM forward and data gradient, ``vbg_small_wgrad`` weight gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        if weight.shape[0] > 16:
+            raise ValueError("LinearSmall: at most 16 outputs (wider layers go through LinearPS)")
+        x = _c(x.detach())
+        y = ops.gemm(x, _c(weight.detach()), ep=ops.make_epilogue(None, None if bias is None else bias.detach()),
+                     precision=ops.PREC_FP32)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _c(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.gemm(dy, _c(weight.detach().t()), precision=ops.PREC_FP32)
+        if ctx.needs_input_grad[1]:
+            dw = ops.small_wgrad(dy, x)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(dy)
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    """[M, K] x [N, K]^T (+ bias) on whichever kernel takes the shape."""
+    if weight.shape[0] % 64 == 0 and weight.shape[1] % 64 == 0:
+        return LinearPS.apply(x, weight, bias)
+    return LinearSmall.apply(x, weight, bias)
+
+
+class ConvPS(torch.autograd.Function):
+    """NHWC convolution (OIHW parameter, optional bias), stride 1 or 2, on the pre-split implicit-GEMM kernels:
+    forward ``vbg_conv2d_ps``; data gradient = the stride-1 convolution of dY (zero-inserted for stride 2) with the flipped /
+    transposed weight; weight gradient ``vbg_conv2d_wgrad``.  Replaces ``nn.Conv2d`` forward/backward of the ResNet / FPN /
+    head convolutions (model/ResNetFPN_ViBERTgrid.py:106-186)."""
+
+    @staticmethod
+    def forward(ctx, x, w_oihw, bias, stride, pad):
+        w = w_oihw.detach()
+        Cout, Cin, kh, kw = w.shape
+        w_ohwi = ops.repack_oihw_to_ohwi(_c(w)) if kh * kw > 1 else _c(w.reshape(Cout, 1, 1, Cin))
+        xs = ops.to_split(_c(x.detach()))
+        ep = ops.make_epilogue(None, bias.detach()) if bias is not None else None
+        if _fp32():
+            y = ops.conv2d(_c(x.detach()), w_ohwi, stride, pad, ep=ep, precision=ops.PREC_FP32)
+        else:
+            y = ops.conv2d(xs, w_ohwi, stride, pad, ep=ep, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w_ohwi))
+        ctx.save_for_backward(xs.t, w_ohwi)
+        ctx.cfg = (stride, pad, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xs_t, w_ohwi = ctx.saved_tensors
+        stride, pad, has_bias = ctx.cfg
+        xs = ops.Split(xs_t)
+        B, H, W, Cin = xs.shape
+        Cout, kh, kw, _ = w_ohwi.shape
+        dy = _c(dy)
+        _, Ho, Wo, _ = dy.shape
+        dys = ops.to_split(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0] and _fp32():
+            wf = w_ohwi.flip(1, 2).permute(3, 1, 2, 0).contiguous()         # fp32 twin of conv_dgrad_weight
+            src = dy if stride == 1 else ops.expand2x(dy, H - kh + 1 + 2 * pad, W - kw + 1 + 2 * pad, 1.0, zero_insert=True)
+            dx = ops.conv2d(src, wf, 1, kh - 1 - pad, precision=ops.PREC_FP32)
+        elif ctx.needs_input_grad[0]:
+            wd = ops.conv_dgrad_weight(w_ohwi)                              # planes [2, Cin, kh, kw, Cout]
+            if stride == 1:
+                dx = ops.conv2d(dys, wd[0], 1, kh - 1 - pad, precision=ops.PREC_BF16X3, W_split=wd)
+            elif kh == 1 and kw == 1 and pad == 0:                          # 1x1 / 2: a GEMM on the coarse lattice, then spread
+                d = ops.gemm(dys.view(B * Ho * Wo, Cout), wd[0].view(Cin, Cout), precision=ops.PREC_BF16X3,
+                             W_split=wd.view(2, Cin, Cout))
+                dx = ops.expand2x(d.view(B, Ho, Wo, Cin), H, W, 1.0, zero_insert=True)
+            else:                                                           # dY onto the stride-1 lattice, then a stride-1 conv
+                dyz = ops.expand2x(dy, H - kh + 1 + 2 * pad, W - kw + 1 + 2 * pad, 1.0, zero_insert=True)
+                dx = ops.conv2d(ops.to_split(dyz), wd[0], 1, kh - 1 - pad, precision=ops.PREC_BF16X3, W_split=wd)
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv2d_wgrad(dys, xs, kh, kw, stride, pad).permute(0, 3, 1, 2).contiguous()
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(dy.view(-1, Cout))
+        return dx, dw, db, None, None
+
+
+class StemF(torch.autograd.Function):
+    """7x7/2 stem over the zero-bordered NHWC4 batch (no data gradient: the input is the image)."""
+
+    @staticmethod
+    def forward(ctx, x4, w_oihw):
+        w774, w256 = ops.stem_pack_weights(w_oihw.detach())
+        if _fp32():
+            y = ops.stem_conv(x4, w774, precision=ops.PREC_FP32)
+        else:
+            y = ops.stem_conv(x4, w774, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w256))
+        ctx.save_for_backward(x4)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x4,) = ctx.saved_tensors
+        dw = ops.stem_wgrad(x4, _c(dy))                                     # [64, 7, 7, 4]
+        return None, dw[..., :3].permute(0, 3, 1, 2).contiguous()
+
+
+class BatchNormTrainF(torch.autograd.Function):
+    """nn.BatchNorm2d in train mode over NHWC, with the residual add and ReLU that follow it in the ResNet blocks fused.
+    ``stats`` (a list) receives (mean, biased var, rows) so the caller can update the running statistics."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, relu, eps, stats):
+        Cc = x.shape[-1]
+        x2 = _c(x.detach()).view(-1, Cc)
+        mean, var, rstd = ops.bn_stats(x2, eps)
+        g = _c(gamma.detach())
+        y = ops.bn_apply(x2, mean, rstd, g, _c(beta.detach()), None if residual is None else _c(residual.detach()).view(-1, Cc), relu)
+        stats.append((mean, var, x2.shape[0]))
+        ctx.save_for_backward(x2, y if relu else None, mean, rstd, g)
+        ctx.has_res = residual is not None
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, y, mean, rstd, g = ctx.saved_tensors
+        Cc = x2.shape[1]
+        dx, dres, dg, db = ops.bn_bwd(x2, _c(dy).view(-1, Cc), y, mean, rstd, g, want_dres=ctx.has_res)
+        return dx.view(dy.shape), dg, db, (dres.view(dy.shape) if dres is not None else None), None, None, None
+
+
+class MaxPoolF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x.detach())
+        ctx.save_for_backward(x)
+        return ops.maxpool3x3s2(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.maxpool3x3s2_bwd(ctx.saved_tensors[0], _c(dy))
+
+
+class AvgPoolF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.hw = (x.shape[1], x.shape[2])
+        return ops.avgpool2x2(_c(x.detach()))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.expand2x(_c(dy), ctx.hw[0], ctx.hw[1], 0.25)
+
+
+class Up2F(torch.autograd.Function):
+    """Nearest x2 (the FPN top-down path); backward = 2x2 block sums."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.expand2x(_c(x.detach()), 2 * x.shape[1], 2 * x.shape[2], 1.0)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.sumpool2x2(_c(dy), 1.0)
+
+
+class GeluF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x.detach())
+        ctx.save_for_backward(x)
+        return ops.gelu(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.gelu(ctx.saved_tensors[0], _c(dy))
+
+
+class DropoutF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        ctx.ps = (p, seed)
+        return ops.dropout(_c(x.detach()), p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.dropout(_c(dy), *ctx.ps), None, None
+
+
+class AttentionF(torch.autograd.Function):
+    """Self-attention over the packed varlen batch: forward on the tcgen05 kernel (vbg_attention_split_fwd), backward
+    vbg_attention_bwd (probabilities recomputed from the row log-sum-exp)."""
+
+    @staticmethod
+    def forward(ctx, qkv, cu, nseq, max_len, heads):
+        qkv = _c(qkv.detach())
+        hid = qkv.shape[1] // 3
+        if hid // heads != 64:
+            raise NotImplementedError("training attention: head dimension 64 only")
+        if max_len <= 512 and ops.tc_available() and not _fp32():
+            out = ops.attention_split(ops.to_split(qkv), cu, nseq, max_len, heads, split_out=False)
+        else:
+            out = ops.attention(qkv, cu, nseq, max_len, heads, ops.PREC_FP32)
+        ctx.save_for_backward(qkv, out, cu)
+        ctx.cfg = (nseq, max_len, heads)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        qkv, out, cu = ctx.saved_tensors
+        return ops.attention_bwd(qkv, out, _c(d_out), cu, *ctx.cfg), None, None, None, None
+
+
+class EmbedSumF(torch.autograd.Function):
+    """word[ids] + position[pos] + token_type[0] (HF BertEmbeddings before its LayerNorm).  The forward is a row gather; the
+    backward scatter-adds into the tables (vbg_embed_bwd) and column-sums into token_type row 0."""
+
+    @staticmethod
+    def forward(ctx, word, position, type_emb, ids, pos):
+        ctx.save_for_backward(ids, pos)
+        ctx.shapes = (word.shape[0], position.shape[0], type_emb.shape)
+        idl, pol = ids.long(), pos.long()
+        return word.detach().index_select(0, idl) + position.detach().index_select(0, pol) + type_emb.detach()[0]
+
+    @staticmethod
+    def backward(ctx, dx):
+        ids, pos = ctx.saved_tensors
+        V, Pm, tshape = ctx.shapes
+        dx = _c(dx)
+        dword, dpos = ops.embed_bwd(dx, ids, pos, V, Pm)
+        dtype = torch.zeros(tshape, dtype=torch.float32, device=dx.device)
+        dtype[0] = ops.colsum(dx)
+        return dword, dpos, dtype, None, None
+
+
+class SegmentReduceF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, tok_row, seg_start, K, mode):
+        ctx.save_for_backward(tok_row, seg_start)
+        ctx.cfg = (hidden.shape[0], mode)
+        return ops.segment_reduce(_c(hidden.detach()), tok_row, seg_start, K, mode)
+
+    @staticmethod
+    def backward(ctx, dseg):
+        tok_row, seg_start = ctx.saved_tensors
+        return ops.segment_reduce_bwd(_c(dseg), tok_row, seg_start, *ctx.cfg), None, None, None, None
+
+
+class GridScatterF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, seg_emb, idx, boxes, seg_off, B, stride):
+        ctx.save_for_backward(idx, boxes, seg_off)
+        ctx.cfg = (B, seg_emb.shape[0], stride, seg_emb.shape[1])
+        return ops.grid_scatter(_c(seg_emb.detach()), idx, seg_off)
+
+    @staticmethod
+    def backward(ctx, dgrid):
+        idx, boxes, seg_off = ctx.saved_tensors
+        B, K, stride, Cc = ctx.cfg
+        dgrid = _c(dgrid)
+        return ops.grid_scatter_bwd(dgrid.view(-1, Cc), Cc, idx, boxes, seg_off, B, K, stride, Cc), None, None, None, None, None
+
+
+class RoiAlignF(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, boxes, seg_off, scale, P):
+        ctx.save_for_backward(boxes, seg_off)
+        ctx.cfg = (feat.shape[0], feat.shape[1], feat.shape[2], scale)
+        return ops.roi_align(_c(feat.detach()), boxes, seg_off, scale, P)
+
+    @staticmethod
+    def backward(ctx, dout):
+        boxes, seg_off = ctx.saved_tensors
+        return ops.roi_align_bwd(_c(dout), boxes, seg_off, *ctx.cfg), None, None, None, None
+
+
+class SegCEF(torch.autograd.Function):
+    """The two mean cross entropies of the auxiliary segmentation head (semantic_segmentation_head.py:343-347, default
+    reduction) from the LOW-resolution logits: forward vbg_seg_ce_loss (labels painted in registers), backward
+    vbg_seg_ce_bwd against the painted label maps.  Returns a [2] tensor (mask-head CE, class-head CE)."""
+
+    @staticmethod
+    def forward(ctx, logits, boxes, seg_off, seg_cls, B, H, W, up, c_split):
+        logits = _c(logits.detach())
+        out = ops.seg_ce_loss(boxes, seg_off, seg_cls, logits, B, H, W, up, c_split)
+        pos_neg, cls = ops.label_paint(boxes, seg_off, seg_cls, B, H, W)
+        ctx.save_for_backward(logits, pos_neg, cls)
+        ctx.cfg = (H, W, up, c_split)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, pos_neg, cls = ctx.saved_tensors
+        return (ops.seg_ce_bwd(logits, pos_neg, cls, *ctx.cfg, _c(g.float())),) + (None,) * 8

@@ -32,7 +32,8 @@ _BERT_NAMES = {
     "hfl/chinese-bert-wwm": 768,
 }
 _BERT_DEFAULT_CFG = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
-                         intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2)
+                         intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2,
+                         hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
 
 
 def _bert_config(name: str) -> dict:
@@ -121,6 +122,7 @@ class ViBERTgridNet(nn.Module):
         self.tokenizer = _load_tokenizer(bert_model, tokenizer)
         self.bert_cfg = _bert_config(bert_model)
         self.bert_model = P.BertParams(**self.bert_cfg)
+        self.bert_hidden_dropout = float(self.bert_cfg["hidden_dropout_prob"])      # training-mode forward only
         if work_mode in ("train", "inference"):
             print("loading pretrained")
             self._load_pretrained_bert(bert_model)
@@ -181,6 +183,7 @@ class ViBERTgridNet(nn.Module):
                              aux_sample_list=loss_aux_sample_list,
                              aux=(num_hard_positive_aux, num_hard_negative_aux), random=ohem_random)
         self._engine = None
+        self._train_engine = None
 
     # ------------------------------------------------------------------ construction helpers
     def _load_pretrained_bert(self, name):
@@ -224,9 +227,11 @@ class ViBERTgridNet(nn.Module):
 
     def forward(self, image, seg_indices, segment_classes, coors, corpus, mask):
         if self.training:
-            raise NotImplementedError(
-                "training-mode forward/backward (batch-statistics BN, dropout, autograd) is the next "
-                "milestone (DESIGN.md section 7); call .eval() -- the eval/inference forward is built")
+            # model/ViBERTgrid_net.py:541: in training the module returns the loss alone (a differentiable 0-d tensor)
+            if self._train_engine is None:
+                from .train_engine import TrainEngine
+                self._train_engine = TrainEngine(self)
+            return self._train_engine.loss(image, seg_indices, segment_classes, coors, corpus, mask)
         eng = self._get_engine()
         out = eng.run(image, seg_indices, segment_classes, coors, corpus, mask, want_seg=True)
         from . import losses

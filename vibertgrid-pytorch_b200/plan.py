@@ -60,7 +60,10 @@ def plan_batch(image_shapes: Sequence[Tuple[int, int]], n_toks: Sequence[int], n
                min_size: float, max_size: float, size_divisible: int = 32) -> BatchPlan:
     B = len(image_shapes)
     assert B == len(n_toks) == len(n_segs) and B > 0
-    sizes = [resize_geometry(h, w, min_size, max_size) for h, w in image_shapes]
+    # ``min_size``: one value (eval: test_image_min_size) or one per image (training: transform.py:192-194 draws per image)
+    mins = list(min_size) if isinstance(min_size, (list, tuple)) else [min_size] * B
+    assert len(mins) == B
+    sizes = [resize_geometry(h, w, m, max_size) for (h, w), m in zip(image_shapes, mins)]
     H = int(math.ceil(float(max(s[0] for s in sizes)) / size_divisible) * size_divisible)
     W = int(math.ceil(float(max(s[1] for s in sizes)) / size_divisible) * size_divisible)
     ratios = np.asarray([[oh / h, ow / w] for (h, w), (oh, ow) in zip(image_shapes, sizes)], dtype=np.float32)

@@ -52,6 +52,7 @@ CONFIGS = {
                       tag_to_idx={"O": 0, "B-q": 1, "B-a": 2, "B-h": 3}),
     # small shapes for the CPU suite / golden fixtures
     "tiny": DocConfig("tiny", 2, 96, 128, 40, 9, 5, "resnet_18_fpn", vocab_size=2000, bert_layers=2, ragged=True),
+    "mid": DocConfig("mid", 4, 160, 192, 64, 12, 5, "resnet_18_fpn", vocab_size=2000, bert_layers=2, ragged=True),
     "tiny_d": DocConfig("tiny_d", 2, 64, 96, 24, 6, 4, "resnet_18_D_fpn", vocab_size=2000, bert_layers=1, ragged=True),
     "tiny_pre": DocConfig("tiny_pre", 1, 64, 64, 16, 5, 5, "resnet_18_fpn_pretrained", vocab_size=2000, bert_layers=1),
     "tiny_win": DocConfig("tiny_win", 2, 64, 64, 515, 12, 5, "resnet_18_fpn", vocab_size=2000, bert_layers=1, ragged=True),

@@ -1,0 +1,233 @@
+"""Training-mode joint forward of ViBERTgridNet as a differentiable sequence of sm_100a kernel stages
+(reference ``model/ViBERTgrid_net.py:512-544`` under ``model.train()``, driven by ``pipeline/train_val_utils.py:265-281``:
+``loss = model(...)``, ``loss.backward()``, optimizer steps).
+
+What differs from the eval engine (engine.py):
+  * every stage is a ``torch.autograd.Function`` of ``autograd.py`` (fp32 channels-last tensors between stages), so
+    ``loss.backward()`` fills ``.grad`` of the registered parameters -- DDP hooks, ``clip_grad_norm`` and the optimizers of the
+    reference's training loop see ordinary gradients;
+  * BatchNorm uses batch statistics and updates ``running_mean / running_var / num_batches_tracked`` (momentum form);
+  * the BERT hidden-state dropouts are applied (counter-based mask kernel).  NOT applied: the dropout on the attention
+    probabilities (it lives inside the attention kernel; listed in DESIGN.md as a deviation of the training path);
+  * the image min-size is drawn per image like ``transform.py:124-131,192-194`` (same torch CPU RNG consumption);
+  * no CUDA graphs, no stream forking: the tape is rebuilt every step.
+
+Scope of this first training path: the ``simp`` classifier with the default (un-sampled, un-weighted) auxiliary loss -- the
+configuration of BASELINE configs[1] / configs[2].  Other heads raise NotImplementedError in training mode.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import autograd as A
+from . import ops
+from .plan import plan_batch
+
+
+def _rand_seed():
+    return int(torch.empty((), dtype=torch.int64).random_(0, 2 ** 62).item())       # CPU generator: no device sync
+
+
+class TrainEngine:
+    def __init__(self, net):
+        self.net = net
+
+    # ------------------------------------------------------------------ building blocks
+    def _bn(self, x, bn: nn.modules.batchnorm._BatchNorm, relu=False, residual=None):
+        stats = []
+        y = A.BatchNormTrainF.apply(x, bn.weight, bn.bias, residual, relu, bn.eps, stats)
+        if bn.track_running_stats and bn.running_mean is not None:
+            mean, var, n = stats[0]
+            with torch.no_grad():
+                bn.num_batches_tracked += 1
+                m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                bn.running_mean.mul_(1.0 - m).add_(mean, alpha=m)
+                bn.running_var.mul_(1.0 - m).add_(var, alpha=m * n / max(n - 1, 1))
+        return y
+
+    @staticmethod
+    def _conv(x, conv: nn.Conv2d):
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        if k == 1 and s == 1 and p == 0:
+            B, H, W, Cin = x.shape
+            y = A.linear(x.reshape(B * H * W, Cin), conv.weight.view(conv.out_channels, Cin), conv.bias)
+            return y.view(B, H, W, conv.out_channels)
+        return A.ConvPS.apply(x, conv.weight, conv.bias, s, p)
+
+    def _block(self, x, conv1, bn1, conv2, bn2, shortcut):
+        y = self._bn(self._conv(x, conv1), bn1, relu=True)
+        if shortcut is None:
+            sc = x
+        else:
+            kind, sconv, sbn = shortcut
+            sc = self._bn(self._conv(A.AvgPoolF.apply(x) if kind == "avg" else x, sconv), sbn)
+        return self._bn(self._conv(y, conv2), bn2, relu=True, residual=sc)
+
+    def _our_block(self, x, blk):
+        sc = None
+        if blk.downsample:
+            sc = ("avg", blk.conv_shortcut[1], blk.conv_shortcut[2]) if blk.d_variant \
+                else ("conv", blk.conv_shortcut[0], blk.conv_shortcut[1])
+        return self._block(x, blk.conv_1, blk.bn_1, blk.conv_2, blk.bn_2, sc)
+
+    def _tv_block(self, x, blk):
+        sc = ("conv", blk.downsample[0], blk.downsample[1]) if hasattr(blk, "downsample") else None
+        return self._block(x, blk.conv1, blk.bn1, blk.conv2, blk.bn2, sc)
+
+    # ------------------------------------------------------------------ stages
+    def _bert(self, plan, dt, corpus):
+        bm = self.net.bert_model
+        e = bm.embeddings
+        cfg = bm.cfg
+        heads = cfg["num_attention_heads"]
+        p_drop = float(getattr(self.net, "bert_hidden_dropout", 0.1))
+        cu = dt["cu"]
+        ids, pos = ops.bert_assemble(corpus, dt["seq_tab"], cu, plan.nseq, plan.R)
+        x = A.EmbedSumF.apply(e.word_embeddings.weight, e.position_embeddings.weight, e.token_type_embeddings.weight, ids, pos)
+        x = A.LayerNormPS.apply(x, e.LayerNorm.weight, e.LayerNorm.bias, e.LayerNorm.eps)
+
+        def drop(t):
+            return A.DropoutF.apply(t, p_drop, _rand_seed()) if p_drop > 0.0 else t
+
+        x = drop(x)
+        for lyr in bm.encoder.layer:
+            sa = lyr.attention.self
+            wqkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0)
+            bqkv = torch.cat([sa.query.bias, sa.key.bias, sa.value.bias], 0)
+            qkv = A.linear(x, wqkv, bqkv)
+            ctx = A.AttentionF.apply(qkv, cu, plan.nseq, plan.max_len, heads)
+            ao = lyr.attention.output
+            a = drop(A.linear(ctx, ao.dense.weight, ao.dense.bias)) + x
+            x = A.LayerNormPS.apply(a, ao.LayerNorm.weight, ao.LayerNorm.bias, ao.LayerNorm.eps)
+            h = A.GeluF.apply(A.linear(x, lyr.intermediate.dense.weight, lyr.intermediate.dense.bias))
+            o = drop(A.linear(h, lyr.output.dense.weight, lyr.output.dense.bias)) + x
+            x = A.LayerNormPS.apply(o, lyr.output.LayerNorm.weight, lyr.output.LayerNorm.bias, lyr.output.LayerNorm.eps)
+        return x
+
+    def _backbone(self, img4, grid):
+        bb = self.net.backbone
+        if bb.pretrained_layout:
+            r = bb.resnet
+            x1 = A.MaxPoolF.apply(self._bn(A.StemF.apply(img4, r.conv1.weight), r.bn1, relu=True))
+            for blk in r.layer1:
+                x1 = self._tv_block(x1, blk)
+            x2 = self._tv_block(x1, r.layer2[0])
+            x2 = self._conv(torch.cat([x2, grid], -1), bb.early_fusion)
+            for blk in list(r.layer2)[1:]:
+                x2 = self._tv_block(x2, blk)
+            x3 = x2
+            for blk in r.layer3:
+                x3 = self._tv_block(x3, blk)
+            x4 = x3
+            for blk in r.layer4:
+                x4 = self._tv_block(x4, blk)
+        else:
+            x1 = A.MaxPoolF.apply(self._bn(A.StemF.apply(img4, bb.conv_1[0].weight), bb.conv_1[1], relu=True))
+            for blk in bb.conv_2_x:
+                x1 = self._our_block(x1, blk)
+            x2 = self._our_block(x1, bb.conv_3_x.block_1)
+            x2 = self._conv(torch.cat([x2, grid], -1), bb.conv_3_x.early_fusion)
+            for blk in bb.conv_3_x.layers:
+                x2 = self._our_block(x2, blk)
+            x3 = x2
+            for blk in bb.conv_4_x:
+                x3 = self._our_block(x3, blk)
+            x4 = x3
+            for blk in bb.conv_5_x:
+                x4 = self._our_block(x4, blk)
+        # FPN top-down (no BN / bias / activation)
+        x4 = self._conv(x4, bb.conv_6_x)
+        x5 = self._conv(self._conv(x3, bb.skip_1) + A.Up2F.apply(x4), bb.merge_1)
+        x6 = self._conv(self._conv(x2, bb.skip_2) + A.Up2F.apply(x5), bb.merge_2)
+        x7 = self._conv(self._conv(x1, bb.skip_3) + A.Up2F.apply(x6), bb.merge_3)
+        # fuse(cat[up8 x4, up4 x5, up2 x6, x7]) == chained K-slices of the fuse weight at native resolution (engine.py)
+        wf = bb.fuse.weight.view(bb.fuse.out_channels, -1)
+        Pc = wf.shape[1] // 4
+        t = None
+        for i, lvl in enumerate((x4, x5, x6, x7)):
+            B, H, W, Cc = lvl.shape
+            y = A.linear(lvl.reshape(B * H * W, Cc), wf[:, i * Pc:(i + 1) * Pc], None).view(B, H, W, -1)
+            t = y if t is None else y + A.Up2F.apply(t)
+        return t
+
+    # ------------------------------------------------------------------ the step's forward
+    def loss(self, image, seg_indices, seg_classes, coors, corpus, mask):
+        net = self.net
+        dev = corpus.device
+        if dev.type != "cuda":
+            raise RuntimeError("ViBERTgridNet (B200) trains on CUDA tensors only; there is no CPU fallback")
+        if net.classifier_mode != "simp" or net.loss_cfg["aux_sample_list"] is not None or tuple(net.loss_cfg["aux"]) != (-1, -1) \
+                or net.loss_weights is not None:
+            raise NotImplementedError("training-mode forward: the `simp` classifier with the default auxiliary loss is built; "
+                                      "`full` / `crf` heads and sampled / weighted auxiliary losses are not (DESIGN.md section 8)")
+        sizes = list(net.image_min_size)
+        # transform.py:124-131,192-194: one draw per image from the training min-size list
+        min_sizes = [float(sizes[int(torch.empty(1).uniform_(0.0, float(len(sizes))).item())]) for _ in image]
+        plan = plan_batch([tuple(im.shape[-2:]) for im in image], [int(s.shape[0]) for s in seg_indices],
+                          [int(c.shape[0]) for c in coors], int(corpus.shape[1]), min_sizes, float(net.image_max_size))
+        tab = torch.from_numpy(plan.table).to(dev)
+        dt = {k: tab[s:s + n] for k, (s, n) in plan.offsets.items()}
+        dt["ratios"] = dt["ratios"].view(torch.float32)
+        seg_off = dt["seg_off"]
+        B = plan.B
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        coors_cat = torch.cat([c.reshape(-1, 4) for c in coors], 0).to(torch.int64).contiguous()
+        seg_ids = torch.cat([s.reshape(-1) for s in seg_indices], 0).to(torch.int32).contiguous()
+        cls_cat = torch.cat([c.reshape(-1) for c in seg_classes], 0).to(torch.int32).contiguous()
+
+        # a1 transform
+        boxes = ops.resize_coords(coors_cat, seg_off, dt["ratios"], B)
+        img4 = torch.zeros((B, plan.H + 6, plan.W + 6, 4), dtype=torch.float32, device=dev)
+        for b, im in enumerate(image):
+            ops.normalize_resize_pad(im.contiguous(), img4, b, plan.sizes[b][0], plan.sizes[b][1], net.image_mean, net.image_std)
+
+        # a2 - a4 BERT, segment aggregation, BERTgrid
+        hidden = self._bert(plan, dt, corpus.contiguous())
+        seg_start = ops.segment_starts(seg_ids, dt["tok_off"], B, plan.K, status)
+        seg_emb = A.SegmentReduceF.apply(hidden, dt["tok_row"], seg_start, plan.K,
+                                         ops.AGG_MEAN if net.grid_mode == "mean" else ops.AGG_FIRST)
+        gs = net.early_fusion_downsampling_ratio
+        idx = ops.box_index_map(boxes, seg_off, B, gs, int(plan.H / gs), int(plan.W / gs))
+        grid = A.GridScatterF.apply(seg_emb, idx, boxes, seg_off, B, gs)
+
+        # a5 backbone
+        p_fuse = self._backbone(img4, grid)
+
+        # a6 auxiliary segmentation head: conv-BN-ReLU x2, the packed 1x1 heads at low resolution, fused CE
+        enc = net.semantic_segmentation_head.encoder
+        s = self._bn(self._conv(p_fuse, enc.conv_1), enc.bn_1, relu=True)
+        s = self._bn(self._conv(s, enc.conv_2), enc.bn_2, relu=True)
+        seg_w = torch.cat([enc.conv_3_1.weight.flatten(1), enc.conv_3_2.weight.flatten(1)], 0)
+        seg_b = torch.cat([enc.conv_3_1.bias, enc.conv_3_2.bias], 0)
+        Bs, Hs, Ws, Cs = s.shape
+        lg = A.linear(s.reshape(Bs * Hs * Ws, Cs), seg_w, seg_b).view(Bs, Hs, Ws, -1)
+        aux = A.SegCEF.apply(lg, boxes, seg_off, cls_cat, B, plan.H, plan.W, net.p_fuse_downsampling_ratio, 3)
+        loss_aux = aux[0] + aux[1]
+
+        # a7 / a8 ROI align, late fusion
+        roi = A.RoiAlignF.apply(p_fuse, boxes, seg_off, 1.0 / float(net.p_fuse_downsampling_ratio), net.roi_shape)
+        rn = net.late_fusion_net.ROI_embedding_net
+        r = self._bn(self._conv(roi, rn.conv_1), rn.bn_1, relu=True)
+        r = self._bn(self._conv(r, rn.conv_2), rn.bn_2, relu=True)
+        Cc, Pp = net.p_fuse_channel, net.roi_shape
+        # the FC weight is stored for the (C, H, W) flatten of the reference; the kernels flatten (H, W, C)
+        w_fc = rn.linear.weight.view(-1, Cc, Pp, Pp).permute(0, 2, 3, 1).reshape(rn.linear.out_features, -1)
+        roi_emb = A.linear(r.reshape(plan.K, -1), w_fc, rn.linear.bias)
+        fl = net.late_fusion_net.fuse_embedding_net.linear
+        late = A.linear(torch.cat([roi_emb, seg_emb], 1), fl.weight, fl.bias)
+
+        # a9 field-type head + losses (tiny [K, C] tensors: torch ops, see losses.py)
+        head = net.field_type_classification_head
+
+        def mlp(m, x):
+            h = torch.relu(A.linear(x, m.linear_1.weight, m.linear_1.bias))
+            return A.linear(h, m.linear_2.weight, m.linear_2.bias)
+
+        out = {"logits": mlp(head.category_classification_net, late), "gt_label": cls_cat, "plan": plan}
+        if hasattr(head, "pos_neg_classification_net"):
+            out["pos_neg_logits"] = mlp(head.pos_neg_classification_net, late)
+        from . import losses
+        loss_c = losses.main_loss(net, out)
+        self.last = dict(status=status, loss_aux=loss_aux.detach(), loss_c=loss_c.detach())
+        return loss_c + net.loss_control_lambda * loss_aux
