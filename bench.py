@@ -279,6 +279,43 @@ def measured_peaks(dev):
     return peaks
 
 
+def train_step_arm(net, cfg, resident, n_rot, world, steps, warmup=3):
+    """One training step = the reference's loop body (pipeline/train_val_utils.py:265-281): loss = model(batch) in train mode,
+    zero_grad, loss.backward(), SGD step for the CNN / heads and AdamW step for the ``bert_model`` parameters
+    (train_SROIE.py:217-235); at N > 1 the gradients are averaged over ranks with NCCL (shard.allreduce_gradients) before the
+    optimizer steps.  Timed like the forward: CUDA events, barrier + synchronize on both sides, max over ranks."""
+    from vibertgrid_pytorch_b200 import _lib, shard
+    net.train()
+    bert = [p for n, p in net.named_parameters() if "bert_model" in n]
+    cnn = [p for n, p in net.named_parameters() if "bert_model" not in n]
+    params = list(net.parameters())
+    opt_cnn = torch.optim.SGD(cnn, lr=1e-4, momentum=0.9, weight_decay=5e-4)
+    opt_bert = torch.optim.AdamW(bert, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    losses = []
+
+    def step(i):
+        loss = net(*resident[i % n_rot])
+        opt_cnn.zero_grad()
+        opt_bert.zero_grad()
+        loss.backward()
+        shard.allreduce_gradients(params)
+        opt_cnn.step()
+        opt_bert.step()
+        losses.append(loss.detach())
+
+    for i in range(warmup):
+        step(i)
+    c0 = _lib.launch_count
+    ms = time_region(step, steps, True, world)
+    launches = _lib.launch_count - c0
+    vals = [float(l) for l in losses]
+    return {"value": cfg.batch * steps * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+            "includes": "train-mode forward (batch-stat BN, dropout) + backward + SGD/AdamW steps"
+                        + (" + NCCL gradient all-reduce" if world > 1 else ""),
+            "gpu_launches": launches, "loss_first": vals[0], "loss_last": vals[-1],
+            "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -289,6 +326,7 @@ def main():
     ap.add_argument("--precision", default=None, choices=[None, "fp32", "tf32", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement (the `train_step` object)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there) go to stderr
@@ -373,6 +411,11 @@ def main():
     ms_e2e = time_region(step_e2e, args.steps, True, world)
     clocks = sampler.stop() if sampler else None
 
+    train = None
+    if not args.no_train and cfg.classifier_mode == "simp":
+        train = train_step_arm(net, cfg, resident, n_rot, world, min(args.steps, 10))
+        net.eval()
+
     imgs = cfg.batch * args.steps * world
     value = imgs / (ms / 1e3)
     e2e = imgs / (ms_e2e / 1e3)
@@ -382,10 +425,13 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload, "global_batch": cfg.batch * world, "parallelism": f"dp{world} (documents sharded, no data-path collective)",
                        "l2": "working set (605 MB weights + activations) >> 126 MB L2; 4 input batches rotated",
-                       "scope_note": "forward only (eval mode): the training backward is not built yet (DESIGN.md section 7)"},
+                       "scope_note": "value / e2e: eval-mode joint forward (the reference arm's workload); the training step "
+                                     "(forward + backward + optimizers, configs[1] 'forward+backward') is the train_step object"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": nbytes(host[0]),
                     "d2h_bytes_per_step": int(sink["pred"].numel() * 4 + sink["loss"].numel() * sink["loss"].element_size())},
             "gpu_launches": launches, "cuda_graph_replays": eng.graph_replays, "clocks": clocks}
+    if train is not None:
+        line["train_step"] = train
     if rank == 0:
         fl = fwd_flops_as_executed(cfg)
         line["fwd_tflops_as_executed"] = fl * cfg.batch * args.steps / (ms / 1e3) / 1e12

@@ -222,7 +222,9 @@ VBG_API int vbg_repack_oihw_to_ohwi(const float* w, int O, int I, int H, int W, 
  * replace torch.autograd's addmm backward of nn.Linear (HF BertSelfOutput / BertIntermediate / ..., head MLPs).      */
 VBG_API int vbg_transpose_split(const void* x, long long x_plane, int rows, int cols, void* out_hi, long long out_plane, int ld_out,
                         vbg_stream_t stream);
-VBG_API int vbg_colsum(const void* x, long long x_plane, int rows, int cols, float* out, vbg_stream_t stream);
+VBG_API long long vbg_colsum_workspace(long long rows, int cols);
+VBG_API int vbg_colsum(const void* x, long long x_plane, long long rows, int cols, float* out, float* workspace, size_t ws_bytes,
+               vbg_stream_t stream);
 /* dW[N,K] = dY[M,N]^T X[M,K] without transposes: both plane operands are read as MN-major tcgen05 operands (reduction index =
  * the slow, row index), split over the row range with a deterministic finish.  N % 128 == 0, K % 64 == 0; workspace bytes from
  * vbg_linear_wgrad_workspace (0: none needed).                                                                      */
@@ -241,7 +243,7 @@ VBG_API int vbg_linear_wgrad(const void* dY_hi, long long y_plane, const void* X
 VBG_API int vbg_conv_dgrad_weight(const float* w_ohwi, int Cout, int kh, int kw, int Cin, void* out_hi, long long out_plane,
                           vbg_stream_t stream);
 /* LayerNorm backward (HF BertSelfOutput / BertOutput / embeddings LayerNorm): dx [R,hidden]; dgamma / dbeta [hidden] (may be
- * NULL together) through `workspace` >= ceil(R/256) * 2 * hidden floats, summed in a fixed order.                     */
+ * NULL together) through `workspace` >= ceil(R/64) * 2 * hidden + 2 * R floats, summed in a fixed order.               */
 VBG_API int vbg_layernorm_bwd(const float* x, const float* dy, const float* gamma, float eps, int R, int hidden, float* dx,
                       float* dgamma, float* dbeta, float* workspace, size_t ws_bytes, vbg_stream_t stream);
 

@@ -44,3 +44,23 @@ n = steps
 print(f"{cfg_name}: forward {t_f / n:.2f} ms, backward {t_b / n:.2f} ms, optimizers {t_o / n:.2f} ms, "
       f"step {(t_f + t_b + t_o) / n:.2f} ms = {cfg.batch / ((t_f + t_b + t_o) / n / 1e3):.1f} images/s; "
       f"peak memory {torch.cuda.max_memory_allocated() / 2**30:.2f} GiB")
+if os.environ.get("VBG_TRAIN_PROFILE"):
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        loss = net(*dev)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        opt_cnn.zero_grad(); opt_bert.zero_grad()
+        loss.backward()
+        t1 = time.time()
+        opt_cnn.step(); opt_bert.step()
+        torch.cuda.synchronize()
+    print(f"host time of backward() call: {(t1 - t0) * 1e3:.1f} ms")
+    rows = [(e.key, e.device_time_total / 1e3, e.count) for e in prof.key_averages() if e.device_time_total > 0 and e.device_type.name == "CUDA"]
+    if not rows:
+        rows = [(e.key, e.device_time_total / 1e3, e.count) for e in prof.key_averages() if e.device_time_total > 0]
+    rows.sort(key=lambda r: -r[1])
+    tot = sum(r[1] for r in rows)
+    print(f"profiled one step: {tot:.2f} ms of device time over {sum(r[2] for r in rows)} kernels")
+    for k, t, n in rows[:45]:
+        print(f"{t:8.3f} ms {100 * t / tot:5.1f}% x{n:<5d} {k[:110]}")

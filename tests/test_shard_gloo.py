@@ -22,7 +22,15 @@ def _worker(rank, world, port, q):
         docs = shard.shard_documents(11, rank, world)
         ms, total = shard.aggregate_throughput(10.0 + 5.0 * rank, len(docs))
         seeds = [shard.batch_seed(rank, world, s, 4) for s in range(6)]
-        q.put((rank, docs, ms, total, seeds))
+        # gradient averaging of the training step: same parameter list on both ranks, one parameter without a gradient
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 70000, 3, 9)]
+        for i, p in enumerate(ps):
+            if i != 2:
+                p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+        nb = shard.allreduce_gradients(ps, bucket_bytes=100000)
+        avg = [None if p.grad is None else float(p.grad.mean()) for p in ps]
+        q.put((rank, docs, ms, total, seeds, nb, avg))
     finally:
         dist.destroy_process_group()
 
@@ -38,7 +46,8 @@ def test_world2_sharding_and_max_over_ranks():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (r0, d0, ms0, n0, s0), (r1, d1, ms1, n1, s1) = res
+    (r0, d0, ms0, n0, s0, nb0, a0), (r1, d1, ms1, n1, s1, nb1, a1) = res
+    assert nb0 == nb1 and nb0 >= 2 and a0 == a1 == [1.5, 3.0, None, 6.0]     # mean over ranks of (rank + 1) * (i + 1)
     assert sorted(d0 + d1) == list(range(11)) and not set(d0) & set(d1)      # a partition: every document exactly once
     assert ms0 == ms1 == 15.0                                                # MAX over ranks, identical on both
     assert n0 == n1 == 11                                                    # whole-job document count

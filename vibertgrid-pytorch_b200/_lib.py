@@ -71,7 +71,8 @@ SIGNATURES = {
     "vbg_roi_align_fwd": [_p, _i, _i, _i, _i, _p, _p, _i, _f, _i, _p, _p, _p],
     "vbg_roi_align_x": [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _f, _i, _p, _ll, _p, _p],
     "vbg_transpose_split": [_p, _ll, _i, _i, _p, _ll, _i, _p],
-    "vbg_colsum": [_p, _ll, _i, _i, _p, _p],
+    "vbg_colsum_workspace": [_ll, _i],
+    "vbg_colsum": [_p, _ll, _ll, _i, _p, _p, _sz, _p],
     "vbg_linear_wgrad_workspace": [_i, _i, _i],
     "vbg_conv2d_wgrad_workspace": [_i, _i, _i, _i, _i, _i, _i, _i, _i],
     "vbg_conv2d_wgrad": [_p, _ll, _p, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p],

@@ -41,16 +41,20 @@ class LinearPS(torch.autograd.Function):
         ep = ops.make_epilogue(None, None if bias is None else bias.detach())
         if _fp32():
             y = ops.gemm(x.detach().contiguous(), w, ep=ep, precision=ops.PREC_FP32)
+            ctx.save_for_backward(x, weight)
         else:
-            y = ops.gemm(ops.to_split(x.detach().contiguous()), w, ep=ep, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w))
-        ctx.save_for_backward(x, weight)
+            xs = ops.to_split(x.detach().contiguous())
+            y = ops.gemm(xs, w, ep=ep, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w))
+            ctx.save_for_backward(xs.t, weight)          # the planes are what the weight-gradient kernel reads (same bytes as x)
+        ctx.planes = not _fp32()
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, weight = ctx.saved_tensors
-        M, K = x.shape
+        xs = ops.Split(x) if ctx.planes else ops.to_split(x.detach().contiguous())
+        M, K = xs.shape
         N = weight.shape[0]
         dy = dy.contiguous()
         dys = ops.to_split(dy)
@@ -62,7 +66,7 @@ class LinearPS(torch.autograd.Function):
             dx = ops.gemm(dys, weight.detach().t(), precision=ops.PREC_BF16X3, W_split=wt.t, N=K, K=N, ldw=N)
         if ctx.needs_input_grad[1]:
             # MN-major tcgen05 operands straight from the row-major planes (no transposes)
-            dw = ops.linear_wgrad(dys, ops.to_split(x.detach().contiguous()))
+            dw = ops.linear_wgrad(dys, xs)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy)
         return dx, dw, db

@@ -203,28 +203,6 @@ transpose_split_kernel(const void* __restrict__ x, long long x_plane, int rows, 
   }
 }
 
-// out[c] = sum_r x[r][c], rows added in a fixed order (bias gradient)
-__global__ void __launch_bounds__(256)
-colsum_kernel(const void* __restrict__ x, long long x_plane, int rows, int cols, float* __restrict__ out) {
-  __shared__ float part[8][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
-  float acc = 0.f;
-  if (c < cols)
-    for (int r = ty; r < rows; r += 8) {
-      const size_t idx = (size_t)r * cols + c;
-      acc += x_plane == 0 ? __ldg(reinterpret_cast<const float*>(x) + idx)
-                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[idx]) +
-                                __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[idx + x_plane]);
-    }
-  part[ty][tx] = acc;
-  __syncthreads();
-  if (ty == 0 && c < cols) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s += part[i][tx];
-    out[c] = s;
-  }
-}
 
 // w [Cout, kh, kw, Cin] fp32 -> planes of w'[Cin, kh, kw, Cout] with w'[ci, r, s, co] = w[co, kh-1-r, kw-1-s, ci]: the weight of
 // the data-gradient convolution dX = conv(dY, w', stride 1, pad k-1-p) of a stride-1 convolution
@@ -245,7 +223,7 @@ __global__ void conv_dgrad_weight_kernel(const float* __restrict__ w, int Cout, 
 // LayerNorm backward, data gradient: one warp per row, row in registers (hidden <= 1024); statistics recomputed from x
 __global__ void __launch_bounds__(256)
 ln_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma, float eps, int R,
-                 int H4, float* __restrict__ dx) {
+                 int H4, float* __restrict__ dx, float2* __restrict__ stats) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= R) return;
@@ -272,6 +250,7 @@ ln_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
     }
   }
   const float rstd = __fdiv_rn(1.0f, sqrtf(warp_sum(sq) / n + eps));
+  if (stats && lane == 0) stats[r] = make_float2(mean, rstd);        // reused by the parameter-gradient reduction
   float s1 = 0.f, s2 = 0.f;                 // sum(dxhat), sum(dxhat * xhat)
 #pragma unroll
   for (int i = 0; i < kMax; ++i) {
@@ -295,31 +274,22 @@ ln_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, cons
   }
 }
 
-// LayerNorm backward, parameter gradients: partial[blk][2][H] over blocks of rows (each CTA: 32 columns x its row block),
-// summed in block order by ln_bwd_param_finish_kernel => deterministic
+// LayerNorm backward, parameter gradients: partial[blk][2][H] over blocks of rows (each CTA: 32 columns x its row block, the row
+// statistics come from ln_bwd_dx_kernel), summed in block order by ln_bwd_param_finish_kernel => deterministic
 __global__ void __launch_bounds__(256)
-ln_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ dy, float eps, int R, int H, int rows_per_blk,
+ln_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float2* __restrict__ stats, int R, int H, int rows_per_blk,
                     float* __restrict__ partial) {
   __shared__ float pg[8][33], pb[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   const int r0 = blockIdx.y * rows_per_blk, r1 = min(r0 + rows_per_blk, R);
   float ag = 0.f, ab = 0.f;
-  for (int r = r0 + ty; r < r1; r += 8) {
-    // row statistics: every warp-row (32 lanes = 32 columns of this CTA) needs the full-row mean / rstd -> recompute by
-    // striding the row with the 32 lanes (H / 32 loads per lane; rows are L2-resident across the column CTAs)
-    const float* xr = x + (size_t)r * H;
-    float s = 0.f;
-    for (int k = tx; k < H; k += 32) s += __ldg(xr + k);
-    const float mean = warp_sum(s) / (float)H;
-    float q = 0.f;
-    for (int k = tx; k < H; k += 32) { const float d = __ldg(xr + k) - mean; q += d * d; }
-    const float rstd = __fdiv_rn(1.0f, sqrtf(warp_sum(q) / (float)H + eps));
-    if (c < H) {
+  if (c < H)
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const float2 st = __ldg(stats + r);
       const float d = __ldg(dy + (size_t)r * H + c);
-      ag += d * ((__ldg(xr + c) - mean) * rstd);
+      ag = fmaf(d, (__ldg(x + (size_t)r * H + c) - st.x) * st.y, ag);
       ab += d;
     }
-  }
   pg[ty][tx] = ag; pb[ty][tx] = ab;
   __syncthreads();
   if (ty == 0 && c < H) {
@@ -438,12 +408,6 @@ extern "C" int vbg_transpose_split(const void* x, long long x_plane, int rows, i
   return check_launch("vbg_transpose_split");
 }
 
-extern "C" int vbg_colsum(const void* x, long long x_plane, int rows, int cols, float* out, vbg_stream_t stream) {
-  VBG_REQUIRE(x && out && rows > 0 && cols > 0 && x_plane >= 0, "vbg_colsum: bad arguments");
-  colsum_kernel<<<cdiv(cols, 32), 256, 0, as_stream(stream)>>>(x, x_plane, rows, cols, out);
-  return check_launch("vbg_colsum");
-}
-
 extern "C" int vbg_conv_dgrad_weight(const float* w_ohwi, int Cout, int kh, int kw, int Cin, void* out_hi, long long out_plane,
                                      vbg_stream_t stream) {
   VBG_REQUIRE(w_ohwi && out_hi && Cout > 0 && kh > 0 && kw > 0 && Cin > 0 && out_plane > 0, "vbg_conv_dgrad_weight: bad arguments");
@@ -459,16 +423,18 @@ extern "C" int vbg_layernorm_bwd(const float* x, const float* dy, const float* g
   VBG_REQUIRE(x && dy && gamma && dx && R > 0 && hidden % 4 == 0 && hidden <= 1024 && aligned16(x) && aligned16(dy) && aligned16(dx),
               "vbg_layernorm_bwd: hidden %% 4 == 0, <= 1024, 16B alignment");
   cudaStream_t s = as_stream(stream);
-  ln_bwd_dx_kernel<<<cdiv(R, 8), 256, 0, s>>>(x, dy, gamma, eps, R, hidden / 4, dx);
+  // workspace = [nblk][2][hidden] partial sums, then [R] (mean, rstd) pairs
+  const int rows_per_blk = 64, nblk = cdiv(R, rows_per_blk);
+  const size_t need = ((size_t)nblk * 2 * hidden + 2 * (size_t)R) * sizeof(float);
+  if (dgamma) {
+    VBG_REQUIRE(dbeta && workspace && aligned16(workspace), "vbg_layernorm_bwd: dbeta and a 16B-aligned workspace required with dgamma");
+    if (need > ws_bytes) { set_error("vbg_layernorm_bwd: workspace of %zu bytes needed", need); return VBG_EWORKSPACE; }
+  }
+  float2* stats = dgamma ? reinterpret_cast<float2*>(workspace + (size_t)nblk * 2 * hidden) : nullptr;
+  ln_bwd_dx_kernel<<<cdiv(R, 8), 256, 0, s>>>(x, dy, gamma, eps, R, hidden / 4, dx, stats);
   int rc = check_launch("vbg_layernorm_bwd(dx)");
   if (rc || !dgamma) return rc;
-  VBG_REQUIRE(dbeta && workspace, "vbg_layernorm_bwd: dbeta and workspace required with dgamma");
-  const int rows_per_blk = 256, nblk = cdiv(R, rows_per_blk);
-  if ((size_t)nblk * 2 * hidden * sizeof(float) > ws_bytes) {
-    set_error("vbg_layernorm_bwd: workspace of %zu bytes needed", (size_t)nblk * 2 * hidden * sizeof(float));
-    return VBG_EWORKSPACE;
-  }
-  ln_bwd_param_kernel<<<dim3(cdiv(hidden, 32), nblk), 256, 0, s>>>(x, dy, eps, R, hidden, rows_per_blk, workspace);
+  ln_bwd_param_kernel<<<dim3(cdiv(hidden, 32), nblk), 256, 0, s>>>(x, dy, stats, R, hidden, rows_per_blk, workspace);
   rc = check_launch("vbg_layernorm_bwd(params)");
   if (rc) return rc;
   ln_bwd_param_finish_kernel<<<cdiv(hidden, 128), 128, 0, s>>>(workspace, nblk, hidden, dgamma, dbeta);

@@ -67,13 +67,17 @@ __global__ void __launch_bounds__(256) colreduce2_kernel(F f, long long rows, in
   }
 }
 
-// mode 0: (mean, biased var, rstd) from (sum, sumsq); mode 1: plain sums (dbeta, dgamma)
+// mode 0: (mean, biased var, rstd) from (sum, sumsq); mode 1: plain sums (dbeta, dgamma).  One warp per channel: lanes stride the
+// partials, double accumulators, fixed-order shuffle tree.
 __global__ void colreduce2_finish_kernel(const float* __restrict__ partial, int nblk, int C, double inv_rows, float eps, int mode,
                                          float* __restrict__ o0, float* __restrict__ o1, float* __restrict__ o2) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (c >= C) return;
   double a = 0.0, b = 0.0;
-  for (int i = 0; i < nblk; ++i) { a += (double)partial[(size_t)i * 2 * C + c]; b += (double)partial[(size_t)i * 2 * C + C + c]; }
+  for (int i = lane; i < nblk; i += 32) { a += (double)partial[(size_t)i * 2 * C + c]; b += (double)partial[(size_t)i * 2 * C + C + c]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if (lane) return;
   if (mode == 0) {
     const double m = a * inv_rows;
     double v = b * inv_rows - m * m; if (v < 0.0) v = 0.0;
@@ -420,6 +424,32 @@ small_wgrad_kernel(const float* __restrict__ dy, int ldy, const float* __restric
   }
 }
 
+// column sums of [rows, cols] (fp32, or bf16 hi/lo planes): (cols / 32) x G CTAs, each 8 row lanes x 32 columns over a row chunk;
+// the G partial rows are summed in order by sum_slabs_kernel
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ x, long long x_plane, long long rows, int cols, long long rows_per_cta, float* __restrict__ partial) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  long long r1 = r0 + rows_per_cta; if (r1 > rows) r1 = rows;
+  float acc = 0.f;
+  if (c < cols)
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      const size_t idx = (size_t)r * cols + c;
+      acc += x_plane == 0 ? __ldg(reinterpret_cast<const float*>(x) + idx)
+                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[idx]) +
+                                __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[idx + x_plane]);
+    }
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i][tx];
+    partial[(size_t)blockIdx.y * cols + c] = t;
+  }
+}
+
 __global__ void sum_slabs_kernel(const float* __restrict__ partial, int slabs, long long n, float* __restrict__ out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float a = 0.f;
@@ -504,7 +534,7 @@ extern "C" int vbg_bn_stats(const float* x, long long rows, int C, float eps, fl
   if ((size_t)nblk * 2 * C * 4 > ws_bytes) { set_error("vbg_bn_stats: workspace of %zu bytes needed", (size_t)nblk * 2 * C * 4); return VBG_EWORKSPACE; }
   cudaStream_t s = as_stream(stream);
   colreduce2_kernel<<<nblk, 256, 0, s>>>(BnStatsF{reinterpret_cast<const float4*>(x)}, rows, C / 4, rpc, workspace);
-  colreduce2_finish_kernel<<<cdiv(C, 128), 128, 0, s>>>(workspace, nblk, C, 1.0 / (double)rows, eps, 0, mean, var, rstd);
+  colreduce2_finish_kernel<<<cdiv(C, 8), 256, 0, s>>>(workspace, nblk, C, 1.0 / (double)rows, eps, 0, mean, var, rstd);
   return check_launch("vbg_bn_stats");
 }
 
@@ -540,7 +570,7 @@ extern "C" int vbg_bn_bwd(const float* x, const float* dy, const float* y_relu, 
   BnBwdF f{reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y_relu),
            reinterpret_cast<const float4*>(mean), reinterpret_cast<const float4*>(rstd)};
   colreduce2_kernel<<<nblk, 256, 0, s>>>(f, rows, C / 4, rpc, workspace);
-  colreduce2_finish_kernel<<<cdiv(C, 128), 128, 0, s>>>(workspace, nblk, C, 0.0, 0.f, 1, dbeta, dgamma, nullptr);
+  colreduce2_finish_kernel<<<cdiv(C, 8), 256, 0, s>>>(workspace, nblk, C, 0.0, 0.f, 1, dbeta, dgamma, nullptr);
   const long long n4 = rows * (C / 4);
   bn_bwd_dx_kernel<<<grid_for(n4, 256), 256, 0, s>>>(
       reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y_relu), n4, C / 4,
@@ -640,6 +670,32 @@ extern "C" int vbg_upsample_split_bwd(const float* d1, const float* d2, int B, i
   VBG_REQUIRE(d1 && d2 && dlogits && B > 0 && h > 0 && w > 0 && up > 0 && Ct > c_split && c_split > 0, "vbg_upsample_split_bwd: bad arguments");
   upsample_split_bwd_kernel<<<grid_for((long long)B * h * w * Ct, 256), 256, 0, as_stream(stream)>>>(d1, d2, B, h, w, Ct, up, c_split, dlogits);
   return check_launch("vbg_upsample_split_bwd");
+}
+
+static int colsum_geometry(long long rows, int cols, long long& rows_per_cta) {
+  const int col_tiles = cdiv(cols, 32);
+  long long g = (kNumSMs * 8 + col_tiles - 1) / col_tiles;
+  const long long max_g = (rows + 63) / 64;
+  if (g > max_g) g = max_g;
+  if (g < 1) g = 1;
+  rows_per_cta = ((rows + g - 1) / g + 7) / 8 * 8;
+  return (int)((rows + rows_per_cta - 1) / rows_per_cta);
+}
+
+extern "C" long long vbg_colsum_workspace(long long rows, int cols) {
+  long long rpc; const int g = colsum_geometry(rows, cols, rpc);
+  return g > 1 ? (long long)g * cols * 4 : 0;
+}
+
+extern "C" int vbg_colsum(const void* x, long long x_plane, long long rows, int cols, float* out, float* workspace, size_t ws_bytes,
+                          vbg_stream_t stream) {
+  VBG_REQUIRE(x && out && rows > 0 && cols > 0 && x_plane >= 0, "vbg_colsum: bad arguments");
+  long long rpc; int g = colsum_geometry(rows, cols, rpc);
+  if (g > 1 && (!workspace || (size_t)g * cols * 4 > ws_bytes)) { g = 1; rpc = rows; }       // no workspace: one CTA row per column tile
+  cudaStream_t s = as_stream(stream);
+  colsum_kernel<<<dim3(cdiv(cols, 32), g), 256, 0, s>>>(x, x_plane, rows, cols, rpc, g > 1 ? workspace : out);
+  if (g > 1) sum_slabs_kernel<<<grid_for(cols, 256), 256, 0, s>>>(workspace, g, cols, out);
+  return check_launch("vbg_colsum");
 }
 
 static int small_wgrad_geometry(long long M, long long& rows_per_cta) {

@@ -473,7 +473,9 @@ def colsum(x):
     rows, cols = x.shape
     out = torch.empty(cols, dtype=torch.float32, device=x.device)
     xp, xpl = _act(x)
-    L.check(L.load().vbg_colsum(xp, xpl, rows, cols, _f32(out), _stream()), "vbg_colsum")
+    nb = L.load().vbg_colsum_workspace(rows, cols)
+    ws = torch.empty(nb // 4, dtype=torch.float32, device=out.device) if nb else None
+    L.check(L.load().vbg_colsum(xp, xpl, rows, cols, _f32(out), None if ws is None else _f32(ws), nb, _stream()), "vbg_colsum")
     return out
 
 
@@ -495,7 +497,7 @@ def layernorm_bwd(x, dy, gamma, eps, want_params=True):
         return dx, None, None
     dg = torch.empty(hidden, dtype=torch.float32, device=x.device)
     db = torch.empty(hidden, dtype=torch.float32, device=x.device)
-    ws = torch.empty(((R + 255) // 256) * 2 * hidden, dtype=torch.float32, device=x.device)
+    ws = torch.empty(((R + 63) // 64) * 2 * hidden + 2 * R, dtype=torch.float32, device=x.device)
     L.check(L.load().vbg_layernorm_bwd(_f32(x), _f32(dy), _f32(gamma), eps, R, hidden, _f32(dx), _f32(dg), _f32(db), _f32(ws),
                                        ws.numel() * 4, _stream()), "vbg_layernorm_bwd")
     return dx, dg, db

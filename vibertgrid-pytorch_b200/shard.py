@@ -4,6 +4,9 @@ The forward has no cross-document term: rank r of W simply owns d
 stream -- the same assignment the reference's ``DistributedSampler(shuffle=False)`` makes
 (reference data/SROIE_dataset.py:314-318) -- and no data-path collective exists.  The only collectives are the
 bookkeeping ones below: MAX over ranks of the timed region, SUM of the documents processed.
+
+The training step adds the one real exchange of the path: the gradient average over ranks after ``loss.backward()``
+(``allreduce_gradients`` -- what DistributedDataParallel does for the reference, train_SROIE.py:203-207), NCCL over NVLink.
 """
 from __future__ import annotations
 
@@ -35,3 +38,29 @@ def aggregate_throughput(ms_local: float, docs_local: int, device=None) -> Tuple
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(n, op=dist.ReduceOp.SUM)
     return float(t.item()), int(n.item())
+
+
+def allreduce_gradients(params, bucket_bytes: int = 128 << 20) -> int:
+    """Average ``.grad`` of ``params`` over the ranks of the default process group, in flat buckets of about ``bucket_bytes``
+    (few large NCCL all-reduces: NVSwitch bandwidth, not launch latency).  Parameters without a gradient are skipped -- every
+    rank skips the same ones (the BERT pooler and the torchvision ``fc`` never receive one).  Returns the number of buckets."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    world = dist.get_world_size()
+    grads = [p.grad for p in params if p.grad is not None]
+    buckets, cur, size = [], [], 0
+    for g in grads:
+        if cur and (size + g.numel() * g.element_size() > bucket_bytes or g.dtype != cur[0].dtype):
+            buckets.append(cur)
+            cur, size = [], 0
+        cur.append(g)
+        size += g.numel() * g.element_size()
+    if cur:
+        buckets.append(cur)
+    for b in buckets:
+        flat = torch._utils._flatten_dense_tensors(b)
+        dist.all_reduce(flat)
+        flat.div_(world)
+        for g, f in zip(b, torch._utils._unflatten_dense_tensors(flat, b)):
+            g.copy_(f)
+    return len(buckets)
