@@ -29,12 +29,31 @@ from vibertgrid_pytorch_b200.net import ViBERTgridNet as OurNet  # noqa: E402  (
 from oracle.make_golden import seed_hub, write_bert_dir  # noqa: E402
 
 CASES = {
-    # fixture -> (config, weight seed, input seed)
+    # fixture -> (config, weight seed, input seed[, classifier mode, extra constructor kwargs])
     "train_tiny": ("tiny", 0, 0),
     "train_tiny_d": ("tiny_d", 3, 3),
     "train_tiny_pre": ("tiny_pre", 4, 4),
     "train_mid": ("mid", 6, 6),                 # larger BatchNorm populations: the better-conditioned case
+    # the other heads / loss configurations of the training step
+    "train_tiny_crf": ("tiny", 7, 7, "crf", {}),                                  # CRF negative log-likelihood
+    "train_tiny_crf_multi": ("tiny_d", 8, 8, "crf", {"layer_mode": "multi"}),
+    "train_tiny_full": ("tiny", 9, 9, "full", {}),                                # two-stage heads, single-layer classifiers
+    "train_tiny_full_multi": ("tiny_d", 10, 10, "full", {"layer_mode": "multi"}),
+    # simp head with the rounding-robust loss knobs on: index-sampled aux-1 (Python `random` draws), class weights
+    "train_tiny_sampled": ("tiny", 11, 11, "simp", {"loss_aux_sample_list": [300, 200, 100],
+                                                    "loss_weights": [0.5, 1.0, 2.0, 1.5, 0.75]}),
+    # OHEM everywhere.  The reference indexes the SORTED losses with ORIGINAL indices (custom_loss.py:174-176), which makes
+    # the kept set -- and the loss -- jump under 1e-6 perturbations of tied pixel losses, so these two bind the host logic
+    # only (tests/test_train_host_logic.py, same fp32 CPU arithmetic as the reference), not the GPU kernels.
+    "train_tiny_ohem": ("tiny", 11, 11, "simp", {"loss_aux_sample_list": [300, 200, 100], "num_hard_positive_aux": 150,
+                                                 "num_hard_negative_aux": 250, "num_hard_positive_main_1": 3,
+                                                 "num_hard_negative_main_1": 2, "num_hard_positive_main_2": 4,
+                                                 "num_hard_negative_main_2": 2,
+                                                 "loss_weights": [0.5, 1.0, 2.0, 1.5, 0.75]}),
+    "train_tiny_full_ohem": ("tiny_d", 10, 10, "full", {"layer_mode": "multi", "num_hard_positive_main_2": 2,
+                                                        "num_hard_negative_main_2": 3}),
 }
+PY_RANDOM_SEED = 4321
 N_SAMPLES = 64
 
 
@@ -44,15 +63,19 @@ def summarize(t):
     return np.concatenate([[float(f.sum()), float(f.norm())], f[idx].numpy()])
 
 
-def run_one(name, cfg_name, wseed, iseed, outdir):
-    cfg = dataclasses.replace(synth.CONFIGS[cfg_name], classifier_mode="simp")
+def run_one(name, cfg_name, wseed, iseed, mode="simp", extra=None, outdir=None):
+    import random
+    extra = dict(extra or {})
+    cfg = dataclasses.replace(synth.CONFIGS[cfg_name], classifier_mode=mode)
+    if mode == "crf" and cfg.tag_to_idx is None:
+        cfg.tag_to_idx = {f"T{i}": i for i in range(cfg.num_classes)}
     with tempfile.TemporaryDirectory() as tmp:
         cwd = os.getcwd()
         os.chdir(tmp)
         try:
             write_bert_dir(cfg, tmp)
             seed_hub(tmp)
-            kw = synth.model_kwargs(cfg, "eval")
+            kw = {**synth.model_kwargs(cfg, "eval"), **extra}
             ours = OurNet(**kw)
             synth.fill_state_dict_(ours, wseed)
             sd = {k: v.clone() for k, v in ours.state_dict().items()}
@@ -60,7 +83,7 @@ def run_one(name, cfg_name, wseed, iseed, outdir):
             for m in [m for m in sys.modules if m.split(".")[0] in ("model", "pipeline")]:
                 del sys.modules[m]
             from model.ViBERTgrid_net import ViBERTgridNet as RefNet
-            ref = RefNet(**synth.model_kwargs(cfg, "eval"))
+            ref = RefNet(**{**synth.model_kwargs(cfg, "eval"), **extra})
             ref.load_state_dict(sd, strict=True)
             sys.path.remove(REF)
             ref.train()
@@ -75,19 +98,22 @@ def run_one(name, cfg_name, wseed, iseed, outdir):
                     c.hidden_dropout_prob = 0.0
             batch = synth.make_batch(cfg, iseed)
             torch.manual_seed(0)
+            random.seed(PY_RANDOM_SEED)
             loss = ref(*batch)
             assert isinstance(loss, torch.Tensor), "training mode must return the loss alone"
             loss.backward()
             bufs = {k: summarize(v.float()) for k, v in ref.named_buffers() if "running_" in k or "num_batches" in k}
             # determinism check (dropout really off): a second forward gives the same loss (BN running stats do not enter)
             torch.manual_seed(1)
+            random.seed(PY_RANDOM_SEED)
             loss2 = ref(*batch)
             assert abs(float(loss2) - float(loss)) < 1e-6 * max(1.0, abs(float(loss))), (float(loss), float(loss2))
         finally:
             os.chdir(cwd)
-    fx = dict(meta=json.dumps(dict(name=name, cfg=cfg_name, classifier_mode="simp", weight_seed=wseed, input_seed=iseed,
+    fx = dict(meta=json.dumps(dict(name=name, cfg=cfg_name, classifier_mode=mode, extra_kwargs=extra, py_random_seed=PY_RANDOM_SEED,
+                                   weight_seed=wseed, input_seed=iseed,
                                    torch=torch.__version__, dropouts_zeroed=n_drop)),
-              loss=np.asarray([float(loss)]))
+              loss=np.asarray([float(loss)]), loss_shape=np.asarray(list(loss.shape), dtype=np.int64))
     names, no_grad = [], []
     for k, p in ref.named_parameters():
         if p.grad is None:
@@ -110,4 +136,4 @@ if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count() or 1)
     out = os.path.join(ROOT, "tests", "golden")
     for n in (sys.argv[1:] or list(CASES)):
-        run_one(n, *CASES[n], out)
+        run_one(n, *CASES[n], outdir=out)

@@ -260,3 +260,23 @@ def crf_nll(feats: np.ndarray, tags: np.ndarray, trans: np.ndarray, start: int, 
         prev = int(t)
     gold += float(trans[stop, prev])
     return (logz - gold) / max(len(feats), 1)
+
+
+def crf_nll_torch(feats, tags, trans, start: int, stop: int):
+    """Differentiable float64 restatement of model/crf.py:47-93,148-152 for ONE sequence (torch autograd supplies the
+    gradients the reference's own backward produces).  feats [n, T], tags int [n], trans [T, T] (to <- from)."""
+    import torch
+    feats, trans = feats.double(), trans.double()
+    T = trans.shape[0]
+    fv = torch.full((T,), -10000.0, dtype=torch.float64)
+    fv[start] = 0.0
+    for feat in feats:
+        fv = torch.logsumexp(fv[None, :] + trans, dim=1) + feat
+    logz = torch.logsumexp(fv + trans[stop], dim=0)
+    gold = feats.new_zeros(())
+    prev = start
+    for feat, t in zip(feats, tags.tolist()):
+        gold = gold + trans[t, prev] + feat[t]
+        prev = t
+    gold = gold + trans[stop, prev]
+    return (logz - gold) / feats.shape[0]

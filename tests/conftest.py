@@ -43,7 +43,7 @@ def build_case(meta):
     if meta["classifier_mode"] == "crf" and cfg.tag_to_idx is None:
         cfg.tag_to_idx = {f"T{i}": i for i in range(cfg.num_classes)}
     synth.write_bert_dir(cfg, os.getcwd())
-    kw = synth.model_kwargs(cfg, "eval")
+    kw = {**synth.model_kwargs(cfg, "eval"), **meta.get("extra_kwargs", {})}
     net = ViBERTgridNet(**kw)
     synth.fill_state_dict_(net, meta["weight_seed"])
     batch = synth.make_batch(cfg, meta["input_seed"])

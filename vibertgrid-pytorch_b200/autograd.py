@@ -417,3 +417,24 @@ class SegCEF(torch.autograd.Function):
     def backward(ctx, g):
         logits, pos_neg, cls = ctx.saved_tensors
         return (ops.seg_ce_bwd(logits, pos_neg, cls, *ctx.cfg, _c(g.float())),) + (None,) * 8
+
+
+class CrfNllF(torch.autograd.Function):
+    """Per-sample negative log-likelihood [B] of the linear-chain CRF (model/crf.py:148-152; the training branch of
+    CRFFieldTypeClassification.forward, field_type_classification_head.py:686-699) from the emissions [K, T], the transition
+    parameter [T, T] and the gold tags: vbg_crf_nll_fwd keeps the forward variables, vbg_crf_nll_bwd turns them into posterior
+    marginals minus gold counts."""
+
+    @staticmethod
+    def forward(ctx, feats, trans, tags, seg_off, B):
+        feats, trans = _c(feats.detach()), _c(trans.detach())
+        nll, alpha, logz = ops.crf_nll_fwd(feats, trans, tags, seg_off, B)
+        ctx.save_for_backward(feats, trans, tags, seg_off, alpha, logz)
+        ctx.B = B
+        return nll
+
+    @staticmethod
+    def backward(ctx, g):
+        feats, trans, tags, seg_off, alpha, logz = ctx.saved_tensors
+        dfeats, dtrans = ops.crf_nll_bwd(feats, trans, tags, seg_off, ctx.B, alpha, logz, _c(g.float()))
+        return dfeats, dtrans, None, None, None

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libvbg_sm100a.so")
-SOURCES = ["vbg_api.cu", "vbg_grid.cu", "vbg_roi.cu", "vbg_image.cu", "vbg_bert.cu", "vbg_gemm_simt.cu", "vbg_gemm_tc.cu", "vbg_gemm_tc3.cu", "vbg_gemm_ps.cu", "vbg_wgrad.cu", "vbg_attn_tc.cu", "vbg_train.cu", "vbg_attn_bwd.cu"]
+SOURCES = ["vbg_api.cu", "vbg_grid.cu", "vbg_roi.cu", "vbg_image.cu", "vbg_bert.cu", "vbg_gemm_simt.cu", "vbg_gemm_tc.cu", "vbg_gemm_tc3.cu", "vbg_gemm_ps.cu", "vbg_wgrad.cu", "vbg_attn_tc.cu", "vbg_train.cu", "vbg_attn_bwd.cu", "vbg_crf.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -24,7 +24,7 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     hdrs = [os.path.join(HERE, "vbg_common.cuh"), os.path.join(PKG, "..", "include", "vbg.h")]
-    hdrs += [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(".cuh")]
+    hdrs += [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))]
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     objs, procs = [], []

@@ -178,6 +178,19 @@ class ViBERTgridNet(nn.Module):
         else:
             self.semantic_segmentation_head = P.SegHeadParams(self.p_fuse_channel, self.num_tokens,
                                                               simplified=(classifier_mode == "simp"))
+        if self.loss_weights is not None:
+            # the reference's weighted loss modules are nn.CrossEntropyLoss / nn.BCEWithLogitsLoss subclasses: their class-weight
+            # tensor is a registered buffer, so it shows up in state_dict() (pipeline/custom_loss.py:13-20,109-117,298-304;
+            # semantic_segmentation_head.py:140-149,270-277; field_type_classification_head.py:262-283,486-500)
+            seg, head = self.semantic_segmentation_head, self.field_type_classification_head
+            if classifier_mode == "simp":
+                seg.add_module("aux_loss_2", P.LossWeightParams(self.loss_weights))
+                head.add_module("field_type_classification_loss", P.LossWeightParams(self.loss_weights))
+            else:
+                for i in range(self.num_tokens - 1):
+                    seg.add_module(f"aux_loss_2_{i}", P.LossWeightParams(self.loss_weights))
+                    if classifier_mode == "full":
+                        head.add_module(f"field_type_classification_loss_{i}", P.LossWeightParams(self.loss_weights))
         self.loss_cfg = dict(main_1=(num_hard_positive_main_1, num_hard_negative_main_1),
                              main_2=(num_hard_positive_main_2, num_hard_negative_main_2),
                              aux_sample_list=loss_aux_sample_list,

@@ -458,6 +458,29 @@ def crf_viterbi(feats, trans, seg_off, B):
     return tags, scores
 
 
+def crf_nll_fwd(feats, trans, tags, seg_off, B):
+    """Per-sample CRF negative log-likelihood (model/crf.py:148-152) -> (nll [B], alpha [K,T], logz [B]); tags int32 [K]."""
+    K, T = feats.shape
+    dev = feats.device
+    alpha = torch.empty((K, T), dtype=torch.float32, device=dev)
+    logz = torch.empty(B, dtype=torch.float32, device=dev)
+    nll = torch.empty(B, dtype=torch.float32, device=dev)
+    L.check(L.load().vbg_crf_nll_fwd(_f32(feats), _f32(trans), _i32(tags), _i32(seg_off), B, K, T, _f32(alpha), _f32(logz),
+                                     _f32(nll), _stream()), "vbg_crf_nll_fwd")
+    return nll, alpha, logz
+
+
+def crf_nll_bwd(feats, trans, tags, seg_off, B, alpha, logz, dnll):
+    """Gradient of sum_b dnll[b] * nll[b] -> (dfeats [K,T], dtrans [T,T])."""
+    K, T = feats.shape
+    dev = feats.device
+    dfeats = torch.empty((K, T), dtype=torch.float32, device=dev)
+    part = torch.empty((B, T, T), dtype=torch.float32, device=dev)
+    L.check(L.load().vbg_crf_nll_bwd(_f32(feats), _f32(trans), _i32(tags), _i32(seg_off), B, K, T, _f32(alpha), _f32(logz),
+                                     _f32(dnll), _f32(dfeats), _f32(part), _stream()), "vbg_crf_nll_bwd")
+    return dfeats, part.sum(0)
+
+
 # ------------------------------------------------------------------ backward building blocks
 def transpose_split(x, ld_out=None):
     """[rows, cols] (fp32 tensor or Split) -> Split [cols, ld_out] holding x^T, columns rows..ld_out-1 zero."""

@@ -336,6 +336,14 @@ class SegEncoderParams(_NoForward):
         self.conv_3_2 = _conv(c, num_classes, 1, 1, 0, bias=True)
 
 
+class LossWeightParams(_NoForward):
+    """State-dict stand-in of a weighted loss module of the reference (``<loss>.weight`` buffer)."""
+
+    def __init__(self, weight):
+        super().__init__()
+        self.register_buffer("weight", weight)
+
+
 class _SegBinary(_NoForward):
     def __init__(self, cin):
         super().__init__()

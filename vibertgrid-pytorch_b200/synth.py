@@ -140,6 +140,8 @@ def fill_state_dict_(module: torch.nn.Module, seed: int = 0) -> None:
             if leaf == "num_batches_tracked":
                 t.fill_(1)
                 continue
+            if type(parent).__name__ == "LossWeightParams":     # class weights of the loss modules: constructor values
+                continue
             if leaf == "running_mean":
                 new = torch.randn(t.shape, generator=g) * 0.1
             elif leaf == "running_var":

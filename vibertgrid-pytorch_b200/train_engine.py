@@ -12,8 +12,11 @@ What differs from the eval engine (engine.py):
   * the image min-size is drawn per image like ``transform.py:124-131,192-194`` (same torch CPU RNG consumption);
   * no CUDA graphs, no stream forking: the tape is rebuilt every step.
 
-Scope of this first training path: the ``simp`` classifier with the default (un-sampled, un-weighted) auxiliary loss -- the
-configuration of BASELINE configs[1] / configs[2].  Other heads raise NotImplementedError in training mode.
+Heads: ``simp`` (BASELINE configs[1]-[3]), ``full`` (binary gate + C-1 binary heads) and ``crf`` (emissions + the CRF
+negative log-likelihood kernel, BASELINE configs[4]).  The ``simp`` head with the default auxiliary loss uses the fused
+label-paint + cross-entropy kernel on the low-resolution logits; every other auxiliary-loss configuration (the two-stage
+segmentation head of ``full`` / ``crf``, sampled / OHEM / class-weighted losses) paints the label maps with vbg_label_paint and
+applies the reference's loss arithmetic (losses.py) to the nearest-upsampled logits.
 """
 from __future__ import annotations
 
@@ -155,12 +158,12 @@ class TrainEngine:
     def loss(self, image, seg_indices, seg_classes, coors, corpus, mask):
         net = self.net
         dev = corpus.device
-        if dev.type != "cuda":
+        if dev.type != "cuda" and not getattr(self, "_test_standins", False):      # the flag exists for tests/mock_autograd.py only
             raise RuntimeError("ViBERTgridNet (B200) trains on CUDA tensors only; there is no CPU fallback")
-        if net.classifier_mode != "simp" or net.loss_cfg["aux_sample_list"] is not None or tuple(net.loss_cfg["aux"]) != (-1, -1) \
-                or net.loss_weights is not None:
-            raise NotImplementedError("training-mode forward: the `simp` classifier with the default auxiliary loss is built; "
-                                      "`full` / `crf` heads and sampled / weighted auxiliary losses are not (DESIGN.md section 8)")
+        if net.classifier_mode not in ("simp", "full", "crf"):
+            raise ValueError(f"unknown classifier_mode {net.classifier_mode!r}")
+        default_aux = (net.classifier_mode == "simp" and net.loss_cfg["aux_sample_list"] is None
+                       and tuple(net.loss_cfg["aux"]) == (-1, -1) and net.loss_weights is None)
         sizes = list(net.image_min_size)
         # transform.py:124-131,192-194: one draw per image from the training min-size list
         min_sizes = [float(sizes[int(torch.empty(1).uniform_(0.0, float(len(sizes))).item())]) for _ in image]
@@ -202,8 +205,18 @@ class TrainEngine:
         seg_b = torch.cat([enc.conv_3_1.bias, enc.conv_3_2.bias], 0)
         Bs, Hs, Ws, Cs = s.shape
         lg = A.linear(s.reshape(Bs * Hs * Ws, Cs), seg_w, seg_b).view(Bs, Hs, Ws, -1)
-        aux = A.SegCEF.apply(lg, boxes, seg_off, cls_cat, B, plan.H, plan.W, net.p_fuse_downsampling_ratio, 3)
-        loss_aux = aux[0] + aux[1]
+        from . import losses
+        if default_aux:
+            aux = A.SegCEF.apply(lg, boxes, seg_off, cls_cat, B, plan.H, plan.W, net.p_fuse_downsampling_ratio, 3)
+            loss_aux = aux[0] + aux[1]
+        else:
+            # semantic_segmentation_head.py:73-78 (nearest upsample to the padded image size), :199-214 (label painting),
+            # :216-233 / :343-352 (sampled / OHEM losses, the binary second stage of the two-stage head)
+            full = torch.nn.functional.interpolate(lg.permute(0, 3, 1, 2), scale_factor=int(net.p_fuse_downsampling_ratio),
+                                                   mode="nearest")
+            pos_neg_labels, class_labels = ops.label_paint(boxes, seg_off, cls_cat, B, plan.H, plan.W)
+            loss_aux = losses.aux_loss(net, {"pred_mask": full[:, :3], "pred_ss": full[:, 3:],
+                                             "pos_neg_labels": pos_neg_labels, "class_labels": class_labels})
 
         # a7 / a8 ROI align, late fusion
         roi = A.RoiAlignF.apply(p_fuse, boxes, seg_off, 1.0 / float(net.p_fuse_downsampling_ratio), net.roi_shape)
@@ -221,13 +234,28 @@ class TrainEngine:
         head = net.field_type_classification_head
 
         def mlp(m, x):
+            if not hasattr(m, "linear_1"):                # layer_mode "single"
+                return A.linear(x, m.linear.weight, m.linear.bias)
             h = torch.relu(A.linear(x, m.linear_1.weight, m.linear_1.bias))
             return A.linear(h, m.linear_2.weight, m.linear_2.bias)
 
-        out = {"logits": mlp(head.category_classification_net, late), "gt_label": cls_cat, "plan": plan}
-        if hasattr(head, "pos_neg_classification_net"):
-            out["pos_neg_logits"] = mlp(head.pos_neg_classification_net, late)
-        from . import losses
-        loss_c = losses.main_loss(net, out)
+        out = {"gt_label": cls_cat, "plan": plan}
+        if net.classifier_mode == "simp":
+            out["logits"] = mlp(head.category_classification_net, late)
+            if hasattr(head, "pos_neg_classification_net"):
+                out["pos_neg_logits"] = mlp(head.pos_neg_classification_net, late)
+            loss_c = losses.main_loss(net, out)
+        elif net.classifier_mode == "crf":
+            # field_type_classification_head.py:683-699: emissions, then the mean over samples of the per-sample NLL
+            feats = mlp(head.category_classification_net, late)
+            nll = A.CrfNllF.apply(feats, head.crf_layer.transitions, cls_cat, seg_off, B)
+            loss_c = (nll.sum() / B).reshape(1)
+        else:
+            # field_type_classification_head.py:355-400: the binary heads run on every row here; main_loss gates the rows
+            # with the detached pos/neg decision, which leaves the same loss and gradients as running them on the gated rows
+            out["pos_neg_logits"] = mlp(head.pos_neg_classification_net.layer, late)
+            out["logits"] = torch.cat([mlp(getattr(head, f"category_classification_net_{i}").layer, late)
+                                       for i in range(net.num_tokens - 1)], 1)
+            loss_c = losses.main_loss(net, out)
         self.last = dict(status=status, loss_aux=loss_aux.detach(), loss_c=loss_c.detach())
         return loss_c + net.loss_control_lambda * loss_aux
