@@ -333,15 +333,17 @@ VBG_API int vbg_crf_viterbi(const float* feats /*[K,T]*/, const float* trans /*[
                     size_t ws_bytes, vbg_stream_t stream);
 /* CRF negative log-likelihood per sample, nll[b] = (logZ_b - gold_b) / S_b: the training branch of the `crf` head
  * (model/crf.py:47-93 `_forward_alg` / `_score_sentence`, :148-152 `forward`; looped over samples by
- * model/field_type_classification_head.py:686-699).  START = T-2, STOP = T-1.  alpha [K,T] and logz [B] are kept by the
- * caller for the backward.  tags = gold labels int32 [K] in [0, T-2).                                              */
+ * model/field_type_classification_head.py:686-699).  START = T-2, STOP = T-1.  alpha [K,T] receives the forward variables
+ * of every step with their maximum subtracted (all recursions run normalised, the normalisers are summed in double into
+ * logz, so the result is fp32-exact at any sequence length); the caller keeps it for the backward.
+ * tags = gold labels int32 [K] in [0, T-2).                                                                        */
 VBG_API int vbg_crf_nll_fwd(const float* feats /*[K,T]*/, const float* trans /*[T,T] to<-from*/, const int32_t* tags /*[K]*/,
                     const int32_t* seg_off, int B, int K, int T, float* alpha /*[K,T]*/, float* logz /*[B]*/,
                     float* nll /*[B]*/, vbg_stream_t stream);
 /* gradient of sum_b dnll[b] * nll[b]: posterior marginals minus gold counts (what autograd derives in the reference).
  * dtrans_part [B,T,T] holds each sample's share; the caller sums over B (fixed order => deterministic).           */
 VBG_API int vbg_crf_nll_bwd(const float* feats, const float* trans, const int32_t* tags, const int32_t* seg_off, int B, int K,
-                    int T, const float* alpha, const float* logz, const float* dnll /*[B]*/, float* dfeats /*[K,T]*/,
+                    int T, const float* alpha, const float* dnll /*[B]*/, float* dfeats /*[K,T]*/,
                     float* dtrans_part /*[B,T,T]*/, vbg_stream_t stream);
 
 #ifdef __cplusplus

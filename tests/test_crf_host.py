@@ -36,7 +36,7 @@ def host_crf(lib, feats, trans, tags, seg_off, dnll):
     lib.crf_host_nll_fwd(_p(feats), _p(trans), _p(tags), _p(seg_off), B, T, _p(alpha), _p(logz), _p(nll))
     dfeats = np.zeros((K, T), np.float32)
     dtr = np.zeros((B, T, T), np.float32)
-    lib.crf_host_nll_bwd(_p(feats), _p(trans), _p(tags), _p(seg_off), B, T, _p(alpha), _p(logz), _p(dnll), _p(dfeats), _p(dtr))
+    lib.crf_host_nll_bwd(_p(feats), _p(trans), _p(tags), _p(seg_off), B, T, _p(alpha), _p(dnll), _p(dfeats), _p(dtr))
     return nll, dfeats, dtr.sum(0)
 
 
@@ -54,7 +54,7 @@ def make_case(seed, lens, C):
     return feats, trans, tags, seg_off
 
 
-CASES = [(0, [7, 5], 4), (1, [64, 64], 4), (2, [1, 2, 130], 12), (3, [200], 30), (4, [65, 63, 128], 6)]
+CASES = [(0, [7, 5], 4), (1, [64, 64], 4), (2, [1, 2, 130], 12), (3, [200], 30), (4, [65, 63, 128], 6), (5, [1024, 700], 12)]
 
 
 @pytest.mark.parametrize("seed,lens,C", CASES)

@@ -249,3 +249,33 @@ def test_attention_bwd(lens, heads):
     dqkv = ops.attention_bwd(qkv, o.detach().float().contiguous(), d_o, cu, len(lens), max(lens), heads)
     assert rel(dqkv, ref) < 2e-5
     assert torch.equal(dqkv, ops.attention_bwd(qkv, o.detach().float().contiguous(), d_o, cu, len(lens), max(lens), heads))
+
+
+@pytest.mark.parametrize("seed,lens,C", [(0, [7, 5], 4), (1, [64, 64], 4), (2, [1, 2, 130], 12), (3, [200], 30),
+                                         (4, [65, 63, 128, 64, 1, 300, 17, 90], 6), (5, [1024] * 4, 12)])
+def test_crf_nll_forward_backward(seed, lens, C):
+    """vbg_crf_nll_{fwd,bwd} through the autograd Function against the oracle's float64 restatement of model/crf.py
+    (cfg5: 2 documents x 64 segments, T = 6; the last case is a cfg4-sized character-level batch)."""
+    from oracle import oracle_ops
+    from vibertgrid_pytorch_b200 import autograd as A
+    g = torch.Generator().manual_seed(seed)
+    T, K, B = C + 2, sum(lens), len(lens)
+    feats = torch.randn(K, T, generator=g) * 1.5
+    trans = torch.randn(T, T, generator=g)
+    trans[T - 2, :] = -10000.0
+    trans[:, T - 1] = -10000.0
+    tags = torch.randint(0, C, (K,), generator=g).to(torch.int32)
+    off = [0]
+    for n in lens:
+        off.append(off[-1] + n)
+    w = (torch.arange(B, dtype=torch.float32) + 1.0) / B
+    fd, td = feats.clone().cuda().requires_grad_(), trans.clone().cuda().requires_grad_()
+    nll = A.CrfNllF.apply(fd, td, tags.cuda(), torch.tensor(off, dtype=torch.int32).cuda(), B)
+    (nll * w.cuda()).sum().backward()
+    f64, t64 = feats.double().requires_grad_(), trans.double().requires_grad_()
+    want = torch.stack([oracle_ops.crf_nll_torch(f64[off[b]:off[b + 1]], tags[off[b]:off[b + 1]], t64, T - 2, T - 1)
+                        for b in range(B)])
+    (want * w.double()).sum().backward()
+    assert (nll.cpu().double() - want.detach()).abs().max() <= 2e-5 * max(1.0, float(want.abs().max()))
+    assert (fd.grad.cpu().double() - f64.grad).abs().max() <= 2e-5
+    assert (td.grad.cpu().double() - t64.grad).abs().max() <= 2e-5 * max(1.0, float(t64.grad.abs().max()))

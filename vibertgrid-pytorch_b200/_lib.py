@@ -105,7 +105,7 @@ SIGNATURES = {
     "vbg_nhwc_to_nchw": [_p, _i, _i, _i, _i, _p, _p],
     "vbg_crf_viterbi": [_p, _p, _p, _i, _i, _i, _p, _p, _p, _sz, _p],
     "vbg_crf_nll_fwd": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p],
-    "vbg_crf_nll_bwd": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "vbg_crf_nll_bwd": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p],
 }
 
 _lib = None

@@ -429,12 +429,12 @@ class CrfNllF(torch.autograd.Function):
     def forward(ctx, feats, trans, tags, seg_off, B):
         feats, trans = _c(feats.detach()), _c(trans.detach())
         nll, alpha, logz = ops.crf_nll_fwd(feats, trans, tags, seg_off, B)
-        ctx.save_for_backward(feats, trans, tags, seg_off, alpha, logz)
+        ctx.save_for_backward(feats, trans, tags, seg_off, alpha)
         ctx.B = B
         return nll
 
     @staticmethod
     def backward(ctx, g):
-        feats, trans, tags, seg_off, alpha, logz = ctx.saved_tensors
-        dfeats, dtrans = ops.crf_nll_bwd(feats, trans, tags, seg_off, ctx.B, alpha, logz, _c(g.float()))
+        feats, trans, tags, seg_off, alpha = ctx.saved_tensors
+        dfeats, dtrans = ops.crf_nll_bwd(feats, trans, tags, seg_off, ctx.B, alpha, _c(g.float()))
         return dfeats, dtrans, None, None, None

@@ -470,14 +470,14 @@ def crf_nll_fwd(feats, trans, tags, seg_off, B):
     return nll, alpha, logz
 
 
-def crf_nll_bwd(feats, trans, tags, seg_off, B, alpha, logz, dnll):
+def crf_nll_bwd(feats, trans, tags, seg_off, B, alpha, dnll):
     """Gradient of sum_b dnll[b] * nll[b] -> (dfeats [K,T], dtrans [T,T])."""
     K, T = feats.shape
     dev = feats.device
     dfeats = torch.empty((K, T), dtype=torch.float32, device=dev)
     part = torch.empty((B, T, T), dtype=torch.float32, device=dev)
-    L.check(L.load().vbg_crf_nll_bwd(_f32(feats), _f32(trans), _i32(tags), _i32(seg_off), B, K, T, _f32(alpha), _f32(logz),
-                                     _f32(dnll), _f32(dfeats), _f32(part), _stream()), "vbg_crf_nll_bwd")
+    L.check(L.load().vbg_crf_nll_bwd(_f32(feats), _f32(trans), _i32(tags), _i32(seg_off), B, K, T, _f32(alpha), _f32(dnll),
+                                     _f32(dfeats), _f32(part), _stream()), "vbg_crf_nll_bwd")
     return dfeats, part.sum(0)
 
 
