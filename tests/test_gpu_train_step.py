@@ -1,6 +1,7 @@
 """One training step (loss, every parameter gradient, BatchNorm running statistics) of the drop-in module on the B200 against
 the UNMODIFIED reference's ``model.train(); loss = model(...); loss.backward()`` on the same seeded weights and documents
 (fixtures: oracle/make_train_golden.py, dropout zeroed on both sides)."""
+import os
 import random
 
 import numpy as np
@@ -91,7 +92,7 @@ def check_step(fx, net, loss, tol_q90, tol_max, tol_norm, tol_loss):
     got_loss = float(loss.reshape(-1)[0])
     assert abs(got_loss - want) <= tol_loss * max(1.0, abs(want)), (got_loss, want)
     params = dict(net.named_parameters())
-    bad = []
+    bad, worst = [], [0.0, 0.0, 0.0]
     for k in fx["grad_names"]:
         k = str(k)
         ref = fx["g:" + k]
@@ -105,8 +106,11 @@ def check_step(fx, net, loss, tol_q90, tol_max, tol_norm, tol_loss):
             wref = fx["g:" + k.replace("key.bias", "key.weight")][1]
             assert got[1] <= 1e-3 * wref, (k, got[1], wref)
             continue
+        worst = [max(worst[0], float(q90)), max(worst[1], float(err)), max(worst[2], float(nerr))]
         if (tol_q90 is not None and q90 > tol_q90) or (tol_max is not None and err > tol_max) or nerr > tol_norm:
             bad.append((k, float(err), float(nerr)))
+    if os.environ.get("VBG_TEST_VERBOSE"):
+        print(f"MARGIN {fx['meta']['name']} loss {got_loss:.6f} vs {want:.6f}; worst q90 {worst[0]:.2e} max {worst[1]:.2e} norm {worst[2]:.2e}")
     assert not bad, f"{len(bad)} gradients off: {bad[:12]}"
     for k in fx["no_grad_names"]:
         g = params[str(k)].grad
