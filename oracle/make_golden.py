@@ -38,6 +38,7 @@ GOLDEN = {
     "tiny_pre": ("tiny_pre", "simp", 4, 4),
     "tiny_win": ("tiny_win", "simp", 5, 5),
     "cfg1": ("cfg1", "simp", 0, 0),
+    "tiny_rob": ("tiny_rob", "simp", 6, 6),      # bert_model="roberta-base": RobertaModel position ids, LayerNorm eps 1e-5
 }
 
 
@@ -124,7 +125,7 @@ def run_one(name, cfg_name, mode, wseed, iseed, outdir):
 
     # ---------------- oracle vs reference, on the spot
     ocfg = oracle_net.OracleConfig(backbone=cfg.backbone, classifier_mode=mode, num_classes=cfg.num_classes,
-                                   min_size=kw["test_image_min_size"], max_size=kw["image_max_size"])
+                                   min_size=kw["test_image_min_size"], max_size=kw["image_max_size"], **({"ln_eps": 1e-5, "roberta_pad": 1} if "roberta-" in cfg.bert_name else {}))
     o = oracle_net.forward(sd, ocfg, *batch)
     image_list, coors_t = cap["transform"]
     seg_emb_ref, grid_ref = cap["bertgrid"]

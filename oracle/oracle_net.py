@@ -43,6 +43,8 @@ class OracleConfig:
     num_heads: int = 12
     layer_mode: str = "single"
     with_seg_head: bool = True
+    ln_eps: float = LN_EPS                # BertConfig.layer_norm_eps (roberta-base: 1e-5)
+    roberta_pad: Optional[int] = None     # RobertaModel: padding_idx of its position-id rule; None = BertModel positions
 
 
 def _bn(x, sd, p):
@@ -84,15 +86,20 @@ def transform(images, coors, cfg: OracleConfig):
 
 # ----------------------------------------------------------------------------- a2
 def bert_encoder(sd: Dict[str, torch.Tensor], prefix: str, ids: torch.Tensor, attn_mask: torch.Tensor,
-                 num_heads: int) -> torch.Tensor:
+                 num_heads: int, ln_eps: float = LN_EPS, roberta_pad: Optional[int] = None) -> torch.Tensor:
     """Post-LN BERT encoder in eval mode (dropout off) -- the computation
     HuggingFace ``BertModel(input_ids, attention_mask).last_hidden_state`` performs,
     as called at model/BERTgrid_generator.py:134-135."""
     e = prefix + "embeddings."
     B, T = ids.shape
-    x = sd[e + "word_embeddings.weight"][ids] + sd[e + "token_type_embeddings.weight"][0] \
-        + sd[e + "position_embeddings.weight"][:T][None]
-    x = F.layer_norm(x, x.shape[-1:], sd[e + "LayerNorm.weight"], sd[e + "LayerNorm.bias"], LN_EPS)
+    if roberta_pad is None:
+        pos_emb = sd[e + "position_embeddings.weight"][:T][None]
+    else:
+        # transformers RobertaEmbeddings.create_position_ids_from_input_ids: cumsum over non-pad ids, offset by padding_idx
+        nz = (ids != roberta_pad).long()
+        pos_emb = sd[e + "position_embeddings.weight"][torch.cumsum(nz, 1) * nz + roberta_pad]
+    x = sd[e + "word_embeddings.weight"][ids] + sd[e + "token_type_embeddings.weight"][0] + pos_emb
+    x = F.layer_norm(x, x.shape[-1:], sd[e + "LayerNorm.weight"], sd[e + "LayerNorm.bias"], ln_eps)
     add_mask = (1.0 - attn_mask[:, None, None, :].float()) * torch.finfo(torch.float32).min
     n_layers = 1 + max(int(k.split("encoder.layer.")[1].split(".")[0]) for k in sd if k.startswith(prefix + "encoder.layer."))
     hd = x.shape[-1] // num_heads
@@ -105,10 +112,10 @@ def bert_encoder(sd: Dict[str, torch.Tensor], prefix: str, ids: torch.Tensor, at
         ctx = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, T, -1)
         a = _lin(ctx, sd, p + "attention.output.dense") + x
         x = F.layer_norm(a, a.shape[-1:], sd[p + "attention.output.LayerNorm.weight"],
-                         sd[p + "attention.output.LayerNorm.bias"], LN_EPS)
+                         sd[p + "attention.output.LayerNorm.bias"], ln_eps)
         h = F.gelu(_lin(x, sd, p + "intermediate.dense"))
         o = _lin(h, sd, p + "output.dense") + x
-        x = F.layer_norm(o, o.shape[-1:], sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"], LN_EPS)
+        x = F.layer_norm(o, o.shape[-1:], sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"], ln_eps)
     return x
 
 
@@ -116,7 +123,8 @@ def bert_token_embeddings(sd, corpus, mask, cfg: OracleConfig):
     """model/BERTgrid_generator.py:81-146 -- windowed BERT, strip [CLS], concat."""
     outs = []
     for ids, am, n in ops.bert_windows(corpus.numpy(), mask.numpy()):
-        h = bert_encoder(sd, "bert_model.", torch.from_numpy(ids), torch.from_numpy(am), cfg.num_heads)
+        h = bert_encoder(sd, "bert_model.", torch.from_numpy(ids), torch.from_numpy(am), cfg.num_heads, cfg.ln_eps,
+                         cfg.roberta_pad)
         outs.append(h[:, 1:1 + n])
     return torch.cat(outs, 1)            # [B, L, 768]
 

@@ -8,7 +8,7 @@ from conftest import build_case, load_golden, relerr
 
 from oracle import oracle_net, oracle_ops
 
-TINY = ["tiny_simp", "tiny_full", "tiny_crf", "tiny_d", "tiny_pre", "tiny_win"]
+TINY = ["tiny_simp", "tiny_full", "tiny_crf", "tiny_d", "tiny_pre", "tiny_win", "tiny_rob"]
 
 
 def _sub(t, *strides):
@@ -59,7 +59,7 @@ def test_oracle_matches_reference_fixture(name, bert_dir, tmp_path, monkeypatch)
     cfg, kw, net, batch = build_case(fx["meta"])
     ocfg = oracle_net.OracleConfig(backbone=cfg.backbone, classifier_mode=cfg.classifier_mode,
                                    num_classes=cfg.num_classes, min_size=kw["test_image_min_size"],
-                                   max_size=kw["image_max_size"])
+                                   max_size=kw["image_max_size"], **({"ln_eps": 1e-5, "roberta_pad": 1} if "roberta-" in cfg.bert_name else {}))
     o = oracle_net.forward(net.state_dict(), ocfg, *batch)
     check_against_golden(o, fx, {"default": 2e-5}, big=name.startswith("cfg"))
 

@@ -28,7 +28,7 @@ from . import ops
 from . import params as P
 from .ops import (ACT_GELU, ACT_NONE, ACT_RELU, PREC_BF16X3, PREC_FP32, PREC_TF32, RES_NONE, RES_SAME, RES_UP2,
                   Split, make_epilogue)
-from .plan import plan_batch
+from .plan import plan_batch, roberta_position_ids
 
 
 class _Prepared:
@@ -267,6 +267,8 @@ class ForwardEngine:
         heads = bm.cfg["num_attention_heads"]
         seq_tab, cu = dev_tab["seq_tab"], dev_tab["cu"]
         ids, pos = ops.bert_assemble(corpus, seq_tab, cu, plan.nseq, plan.R)
+        if bm.cfg.get("roberta"):
+            pos = roberta_position_ids(ids, pos, int(bm.cfg["pad_token_id"]))
         prec = self._prec()
         ps = self._ps()
         x = ops.embed_ln(ids, pos, e.word_embeddings.weight.detach(), e.position_embeddings.weight.detach(),

@@ -33,13 +33,17 @@ _BERT_NAMES = {
 }
 _BERT_DEFAULT_CFG = dict(vocab_size=30522, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
                          intermediate_size=3072, max_position_embeddings=512, type_vocab_size=2,
-                         hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1)
+                         hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, layer_norm_eps=1e-12, pad_token_id=0)
+# roberta-base's published hyper-parameters where they differ from bert-base
+_ROBERTA_DEFAULT_CFG = dict(vocab_size=50265, max_position_embeddings=514, type_vocab_size=1, layer_norm_eps=1e-5, pad_token_id=1)
 
 
 def _bert_config(name: str) -> dict:
     """Hyper-parameters of ``name``: a local directory's config.json first (works
     offline), then HuggingFace ``AutoConfig``, then bert-base defaults."""
     cfg = dict(_BERT_DEFAULT_CFG)
+    if "roberta-" in name:
+        cfg.update(_ROBERTA_DEFAULT_CFG)
     path = os.path.join(name, "config.json")
     src = None
     if os.path.isfile(path):
@@ -53,8 +57,10 @@ def _bert_config(name: str) -> dict:
             warnings.warn(f"[vibertgrid_b200] no config for {name!r} ({type(e).__name__}); using bert-base defaults")
     if src:
         for k in cfg:
-            if k in src:
+            if k in src and src[k] is not None:
                 cfg[k] = src[k]
+    # RobertaModel numbers positions from padding_idx + 1 and skips <pad> ids (HF create_position_ids_from_input_ids)
+    cfg["roberta"] = "roberta-" in name
     return cfg
 
 
@@ -117,8 +123,6 @@ class ViBERTgridNet(nn.Module):
             f"the given bert model {bert_model} does not exists, see attribute bert_model_list for all bert_models"
         self.bert_model_list = dict(_BERT_NAMES)
         self.bert_hidden_size = _BERT_NAMES[bert_model]
-        if "roberta-" in bert_model:
-            raise NotImplementedError("roberta position-id rule is not built yet (DESIGN.md, out of scope this round)")
         self.tokenizer = _load_tokenizer(bert_model, tokenizer)
         self.bert_cfg = _bert_config(bert_model)
         self.bert_model = P.BertParams(**self.bert_cfg)
@@ -201,8 +205,8 @@ class ViBERTgridNet(nn.Module):
     # ------------------------------------------------------------------ construction helpers
     def _load_pretrained_bert(self, name):
         try:
-            from transformers import BertModel
-            hf = BertModel.from_pretrained(name)
+            from transformers import BertModel, RobertaModel
+            hf = (RobertaModel if "roberta-" in name else BertModel).from_pretrained(name)
             missing = self.bert_model.load_state_dict(hf.state_dict(), strict=False)
             if missing.missing_keys:
                 warnings.warn(f"[vibertgrid_b200] pretrained BERT lacks keys: {missing.missing_keys[:4]}...")

@@ -43,12 +43,13 @@ class _NoForward(nn.Module):
 
 # --------------------------------------------------------------------------- BERT
 class BertEmbeddingsParams(_NoForward):
-    def __init__(self, vocab, hidden, max_pos, type_vocab):
+    def __init__(self, vocab, hidden, max_pos, type_vocab, eps=LN_EPS, pad_id=0, pad_positions=False):
         super().__init__()
-        self.word_embeddings = nn.Embedding(vocab, hidden, padding_idx=0)
-        self.position_embeddings = nn.Embedding(max_pos, hidden)
+        self.word_embeddings = nn.Embedding(vocab, hidden, padding_idx=pad_id)
+        # RobertaEmbeddings gives the position table a padding row as well
+        self.position_embeddings = nn.Embedding(max_pos, hidden, padding_idx=pad_id if pad_positions else None)
         self.token_type_embeddings = nn.Embedding(type_vocab, hidden)
-        self.LayerNorm = nn.LayerNorm(hidden, eps=LN_EPS)
+        self.LayerNorm = nn.LayerNorm(hidden, eps=eps)
 
 
 class _SelfParams(_NoForward):
@@ -60,10 +61,10 @@ class _SelfParams(_NoForward):
 
 
 class _DenseLN(_NoForward):
-    def __init__(self, cin, cout):
+    def __init__(self, cin, cout, eps=LN_EPS):
         super().__init__()
         self.dense = nn.Linear(cin, cout)
-        self.LayerNorm = nn.LayerNorm(cout, eps=LN_EPS)
+        self.LayerNorm = nn.LayerNorm(cout, eps=eps)
 
 
 class _Dense(_NoForward):
@@ -73,24 +74,24 @@ class _Dense(_NoForward):
 
 
 class _AttnParams(_NoForward):
-    def __init__(self, hidden):
+    def __init__(self, hidden, eps=LN_EPS):
         super().__init__()
         self.self = _SelfParams(hidden)
-        self.output = _DenseLN(hidden, hidden)
+        self.output = _DenseLN(hidden, hidden, eps)
 
 
 class BertLayerParams(_NoForward):
-    def __init__(self, hidden, inter):
+    def __init__(self, hidden, inter, eps=LN_EPS):
         super().__init__()
-        self.attention = _AttnParams(hidden)
+        self.attention = _AttnParams(hidden, eps)
         self.intermediate = _Dense(hidden, inter)
-        self.output = _DenseLN(inter, hidden)
+        self.output = _DenseLN(inter, hidden, eps)
 
 
 class _Encoder(_NoForward):
-    def __init__(self, n_layers, hidden, inter):
+    def __init__(self, n_layers, hidden, inter, eps=LN_EPS):
         super().__init__()
-        self.layer = nn.ModuleList([BertLayerParams(hidden, inter) for _ in range(n_layers)])
+        self.layer = nn.ModuleList([BertLayerParams(hidden, inter, eps) for _ in range(n_layers)])
 
 
 class BertParams(_NoForward):
@@ -102,17 +103,19 @@ class BertParams(_NoForward):
 
     def __init__(self, vocab_size=30522, hidden_size=768, num_hidden_layers=12,
                  num_attention_heads=12, intermediate_size=3072,
-                 max_position_embeddings=512, type_vocab_size=2, **_unused):
+                 max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=LN_EPS, pad_token_id=0, roberta=False,
+                 **_unused):
         super().__init__()
         self.cfg = dict(vocab_size=vocab_size, hidden_size=hidden_size,
                         num_hidden_layers=num_hidden_layers,
                         num_attention_heads=num_attention_heads,
                         intermediate_size=intermediate_size,
                         max_position_embeddings=max_position_embeddings,
-                        type_vocab_size=type_vocab_size)
-        self.embeddings = BertEmbeddingsParams(vocab_size, hidden_size,
-                                               max_position_embeddings, type_vocab_size)
-        self.encoder = _Encoder(num_hidden_layers, hidden_size, intermediate_size)
+                        type_vocab_size=type_vocab_size, layer_norm_eps=layer_norm_eps, pad_token_id=pad_token_id,
+                        roberta=bool(roberta))
+        self.embeddings = BertEmbeddingsParams(vocab_size, hidden_size, max_position_embeddings, type_vocab_size,
+                                               layer_norm_eps, pad_token_id, pad_positions=bool(roberta))
+        self.encoder = _Encoder(num_hidden_layers, hidden_size, intermediate_size, layer_norm_eps)
         self.pooler = _Dense(hidden_size, hidden_size)
         self.apply(self._init)
 

@@ -113,3 +113,16 @@ def plan_batch(image_shapes: Sequence[Tuple[int, int]], n_toks: Sequence[int], n
         pos += arr.size + pad
     table = np.concatenate(chunks) if chunks else np.zeros(0, np.int32)
     return BatchPlan(B, H, W, sizes, K, n_tok, L, nseq, R, max_len, [int(s) for s in n_segs], table, offsets)
+
+
+def roberta_position_ids(ids, pos, padding_idx):
+    """HF ``create_position_ids_from_input_ids`` (RobertaEmbeddings) over the packed rows: inside each sequence a non-pad id
+    gets ``padding_idx + (number of non-pad ids up to and including it)``, a pad id gets ``padding_idx``.  ``pos`` is the
+    row's 0-based index inside its sequence (what BertModel uses directly), so ``row - pos`` is the sequence's first row.
+    Integer torch ops on the [R] id vector (capturable in a CUDA graph); the result feeds the same embedding kernel."""
+    import torch
+    nz = (ids != padding_idx).to(torch.int32)
+    c = torch.cumsum(nz, 0, dtype=torch.int32)
+    first = (torch.arange(ids.numel(), device=ids.device, dtype=torch.int64) - pos.long())
+    before = c[first] - nz[first]
+    return ((c - before) * nz + padding_idx).to(pos.dtype).contiguous()

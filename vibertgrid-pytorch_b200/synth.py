@@ -40,6 +40,7 @@ class DocConfig:
     bert_layers: int = 12
     ragged: bool = False        # vary S / n_tok / image size per sample
     tag_to_idx: Optional[dict] = None
+    bert_name: str = "bert-base-uncased"   # one of the reference's seven names (model/ViBERTgrid_net.py:218-226)
 
 
 CONFIGS = {
@@ -56,6 +57,8 @@ CONFIGS = {
     "tiny_d": DocConfig("tiny_d", 2, 64, 96, 24, 6, 4, "resnet_18_D_fpn", vocab_size=2000, bert_layers=1, ragged=True),
     "tiny_pre": DocConfig("tiny_pre", 1, 64, 64, 16, 5, 5, "resnet_18_fpn_pretrained", vocab_size=2000, bert_layers=1),
     "tiny_win": DocConfig("tiny_win", 2, 64, 64, 515, 12, 5, "resnet_18_fpn", vocab_size=2000, bert_layers=1, ragged=True),
+    "tiny_rob": DocConfig("tiny_rob", 2, 64, 96, 24, 6, 5, "resnet_18_fpn", vocab_size=2000, bert_layers=2, ragged=True,
+                          bert_name="roberta-base"),
 }
 
 
@@ -117,6 +120,8 @@ def make_batch(cfg: DocConfig, seed: int = 0, device="cpu"):
     for b, n in enumerate(n_toks):
         assert n <= L
         corpus[b, :n] = torch.randint(1000, cfg.vocab_size, (n,), generator=g)
+    if "roberta-" in cfg.bert_name and n_toks[0] > 3:
+        corpus[0, 2] = 1        # RoBERTa's <pad> id inside the text: exercises the position-id rule's padding branch
     mask = (corpus != 0).to(torch.int32)
     mv = lambda seq: tuple(t.to(device) for t in seq)
     return mv(images), mv(segs), mv(classes), mv(coors), corpus.to(device), mask.to(device)
@@ -166,6 +171,11 @@ def fill_state_dict_(module: torch.nn.Module, seed: int = 0) -> None:
 
 def bert_config_dict(cfg: DocConfig) -> dict:
     """The HuggingFace ``config.json`` of the stand-in BERT directory."""
+    if "roberta-" in cfg.bert_name:
+        return dict(model_type="roberta", architectures=["RobertaModel"], hidden_size=768,
+                    num_hidden_layers=cfg.bert_layers, num_attention_heads=12, intermediate_size=3072, hidden_act="gelu",
+                    layer_norm_eps=1e-5, max_position_embeddings=514, type_vocab_size=1, vocab_size=cfg.vocab_size,
+                    hidden_dropout_prob=0.1, attention_probs_dropout_prob=0.1, pad_token_id=1, bos_token_id=0, eos_token_id=2)
     return dict(model_type="bert", architectures=["BertModel"], hidden_size=768,
                 num_hidden_layers=cfg.bert_layers, num_attention_heads=12,
                 intermediate_size=3072, hidden_act="gelu", layer_norm_eps=1e-12,
@@ -176,10 +186,20 @@ def bert_config_dict(cfg: DocConfig) -> dict:
 def write_bert_dir(cfg, root):
     """Stand-in HuggingFace directory literally named ``bert-base-uncased``:
     config.json with the workload's BERT hyper-parameters + a synthetic vocab."""
-    d = os.path.join(root, "bert-base-uncased")
+    d = os.path.join(root, cfg.bert_name)
     os.makedirs(d, exist_ok=True)
     with open(os.path.join(d, "config.json"), "w") as f:
         json.dump(bert_config_dict(cfg), f)
+    if "roberta-" in cfg.bert_name:      # byte-level BPE stand-in: specials + single-character tokens, no merges
+        vocab = {"<s>": 0, "<pad>": 1, "</s>": 2, "<unk>": 3}
+        for i in range(4, cfg.vocab_size - 1):
+            vocab[f"tok{i}"] = i
+        vocab["<mask>"] = cfg.vocab_size - 1
+        with open(os.path.join(d, "vocab.json"), "w") as f:
+            json.dump(vocab, f)
+        with open(os.path.join(d, "merges.txt"), "w") as f:
+            f.write("#version: 0.2\n")
+        return d
     special = {0: "[PAD]", 100: "[UNK]", 101: "[CLS]", 102: "[SEP]", 103: "[MASK]"}
     with open(os.path.join(d, "vocab.txt"), "w") as f:
         for i in range(cfg.vocab_size):
@@ -195,7 +215,7 @@ def model_kwargs(cfg: DocConfig, work_mode: str = "eval") -> dict:
               image_mean=[0.9248, 0.9224, 0.9215], image_std=[0.1532, 0.1545, 0.1536],
               image_min_size=[min(cfg.height, cfg.width)], image_max_size=max(cfg.height, cfg.width),
               test_image_min_size=min(cfg.height, cfg.width),
-              bert_model="bert-base-uncased", backbone=cfg.backbone,
+              bert_model=cfg.bert_name, backbone=cfg.backbone,
               classifier_mode=cfg.classifier_mode, layer_mode="single",
               loss_control_lambda=1, ohem_random=True, work_mode=work_mode)
     if cfg.tag_to_idx is not None:

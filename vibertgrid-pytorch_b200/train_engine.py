@@ -25,7 +25,7 @@ import torch.nn as nn
 
 from . import autograd as A
 from . import ops
-from .plan import plan_batch
+from .plan import plan_batch, roberta_position_ids
 
 
 def _rand_seed():
@@ -87,6 +87,8 @@ class TrainEngine:
         p_drop = float(getattr(self.net, "bert_hidden_dropout", 0.1))
         cu = dt["cu"]
         ids, pos = ops.bert_assemble(corpus, dt["seq_tab"], cu, plan.nseq, plan.R)
+        if cfg.get("roberta"):
+            pos = roberta_position_ids(ids, pos, int(cfg["pad_token_id"]))
         x = A.EmbedSumF.apply(e.word_embeddings.weight, e.position_embeddings.weight, e.token_type_embeddings.weight, ids, pos)
         x = A.LayerNormPS.apply(x, e.LayerNorm.weight, e.LayerNorm.bias, e.LayerNorm.eps)
 
