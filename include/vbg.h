@@ -263,6 +263,14 @@ VBG_API int vbg_bn_apply(const float* x, long long rows, int C, const float* mea
 VBG_API int vbg_bn_bwd(const float* x, const float* dy, const float* y_relu, long long rows, int C, const float* mean, const float* rstd,
                const float* gamma, float* dx, float* dres, float* dgamma, float* dbeta, float* workspace, size_t ws_bytes,
                vbg_stream_t stream);
+/* vbg_bn_bwd in two halves, for nn.SyncBatchNorm (the reference converts the model when syncBN is set: train_SROIE.py:203-205):
+ * _reduce leaves this rank's sum_dy_xhat = sum dy' * xhat (= dgamma) and sum_dy = sum dy' (= dbeta); the caller all-reduces both
+ * over the ranks; _dx then forms dx with inv_count = 1 / (total rows over all ranks) and the global mean / rstd               */
+VBG_API int vbg_bn_bwd_reduce(const float* x, const float* dy, const float* y_relu, long long rows, int C, const float* mean,
+                      const float* rstd, float* sum_dy_xhat, float* sum_dy, float* workspace, size_t ws_bytes, vbg_stream_t stream);
+VBG_API int vbg_bn_bwd_dx(const float* x, const float* dy, const float* y_relu, long long rows, int C, float inv_count, const float* mean,
+                  const float* rstd, const float* gamma, const float* sum_dy_xhat, const float* sum_dy, float* dx, float* dres,
+                  vbg_stream_t stream);
 /* dX of max_pool2d(3, 2, 1) (first-maximum rule), x [B,H,W,C], dy [B,Ho,Wo,C] */
 VBG_API int vbg_maxpool3x3s2_bwd(const float* x, const float* dy, int B, int H, int W, int C, float* dx, vbg_stream_t stream);
 /* y [B,H/2,W/2,C] = scale * 2x2 block sums: backward of the nearest-x2 upsample (scale 1) */

@@ -39,7 +39,7 @@ def _stem(x4, w):
     return _nhwc(F.conv2d(_nchw(x4[..., :3]), w, None, stride=2, padding=0))
 
 
-def _bn(x, gamma, beta, residual, relu, eps, stats):
+def _bn(x, gamma, beta, residual, relu, eps, stats, sync=None):
     Cc = x.shape[-1]
     x2 = x.reshape(-1, Cc)
     mean = x2.mean(0)

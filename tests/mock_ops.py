@@ -252,3 +252,39 @@ def crf_viterbi(feats, trans, seg_off, B):
         tags += path
         scores.append(s)
     return torch.tensor(tags, dtype=torch.float32), torch.tensor(scores, dtype=torch.float32)
+
+
+# ---- training-mode BatchNorm pieces (used by tests/test_syncbn_gloo.py to run the real autograd Function on CPU)
+def bn_stats(x2d, eps):
+    mean = x2d.mean(0)
+    var = x2d.var(0, unbiased=False)
+    return mean, var, torch.rsqrt(var + eps)
+
+
+def bn_apply(x2d, mean, rstd, gamma, beta, residual=None, relu=False):
+    y = (x2d - mean) * rstd * gamma + beta
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu else y
+
+
+def _masked(dy2d, y_relu):
+    return dy2d if y_relu is None else dy2d * (y_relu > 0).to(dy2d.dtype)
+
+
+def bn_bwd_reduce(x2d, dy2d, y_relu, mean, rstd):
+    g = _masked(dy2d, y_relu)
+    return (g * (x2d - mean) * rstd).sum(0), g.sum(0)
+
+
+def bn_bwd_dx(x2d, dy2d, y_relu, mean, rstd, gamma, s_xhat, s_dy, count, want_dres=False):
+    g = _masked(dy2d, y_relu)
+    inv = 1.0 / float(count)
+    dx = gamma * rstd * (g - s_dy * inv - (x2d - mean) * rstd * s_xhat * inv)
+    return dx, (g.clone() if want_dres else None)
+
+
+def bn_bwd(x2d, dy2d, y_relu, mean, rstd, gamma, want_dres=False):
+    s_xhat, s_dy = bn_bwd_reduce(x2d, dy2d, y_relu, mean, rstd)
+    dx, dres = bn_bwd_dx(x2d, dy2d, y_relu, mean, rstd, gamma, s_xhat, s_dy, x2d.shape[0], want_dres)
+    return dx, dres, s_xhat, s_dy

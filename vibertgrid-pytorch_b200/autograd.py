@@ -230,28 +230,64 @@ class StemF(torch.autograd.Function):
         return None, dw[..., :3].permute(0, 3, 1, 2).contiguous()
 
 
+def sync_batch_stats(mean, var, rows, eps, group):
+    """SyncBatchNorm statistics: this rank's (mean, biased var) over ``rows`` rows -> the statistics of all ranks' rows together
+    (count-weighted, combined in float64 on the device: no host synchronisation).  Returns (mean, var, rstd, total rows as a
+    0-d float64 device tensor).  What torch's ``batch_norm_gather_stats_with_counts`` does for the reference when
+    train_SROIE.py:203-205 converts the model."""
+    import torch.distributed as dist
+    Cc = mean.numel()
+    local = torch.cat([mean, var, torch.full((1,), float(rows), dtype=torch.float32, device=mean.device)])
+    gathered = [torch.empty_like(local) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(gathered, local, group=group)
+    g = torch.stack(gathered).double()
+    cnt = g[:, -1:]
+    total = cnt.sum()
+    m = (g[:, :Cc] * cnt).sum(0) / total
+    v = ((g[:, Cc:2 * Cc] + g[:, :Cc] ** 2) * cnt).sum(0) / total - m * m
+    v = v.clamp_min(0.0)
+    return m.float().contiguous(), v.float().contiguous(), torch.rsqrt(v + eps).float().contiguous(), total
+
+
 class BatchNormTrainF(torch.autograd.Function):
     """nn.BatchNorm2d in train mode over NHWC, with the residual add and ReLU that follow it in the ResNet blocks fused.
-    ``stats`` (a list) receives (mean, biased var, rows) so the caller can update the running statistics."""
+    ``stats`` (a list) receives (mean, biased var, rows) so the caller can update the running statistics.
+    ``sync`` = None (per-rank statistics) or a 1-tuple ``(process_group,)`` (None inside = the default group): the
+    nn.SyncBatchNorm form -- statistics over all ranks' rows in the forward, the two per-channel sums of the backward
+    all-reduced before dx is formed; the parameter gradients stay per-rank (the gradient average adds them up)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, relu, eps, stats):
+    def forward(ctx, x, gamma, beta, residual, relu, eps, stats, sync=None):
         Cc = x.shape[-1]
         x2 = _c(x.detach()).view(-1, Cc)
         mean, var, rstd = ops.bn_stats(x2, eps)
+        rows = x2.shape[0]
+        if sync is not None:
+            mean, var, rstd, rows = sync_batch_stats(mean, var, rows, eps, sync[0])
         g = _c(gamma.detach())
         y = ops.bn_apply(x2, mean, rstd, g, _c(beta.detach()), None if residual is None else _c(residual.detach()).view(-1, Cc), relu)
-        stats.append((mean, var, x2.shape[0]))
-        ctx.save_for_backward(x2, y if relu else None, mean, rstd, g)
+        stats.append((mean, var, rows))
+        ctx.save_for_backward(x2, y if relu else None, mean, rstd, g, rows if sync is not None else None)
         ctx.has_res = residual is not None
+        ctx.sync = sync
         return y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, y, mean, rstd, g = ctx.saved_tensors
+        x2, y, mean, rstd, g, total = ctx.saved_tensors
         Cc = x2.shape[1]
-        dx, dres, dg, db = ops.bn_bwd(x2, _c(dy).view(-1, Cc), y, mean, rstd, g, want_dres=ctx.has_res)
-        return dx.view(dy.shape), dg, db, (dres.view(dy.shape) if dres is not None else None), None, None, None
+        dy2 = _c(dy).view(-1, Cc)
+        if ctx.sync is None:
+            dx, dres, dg, db = ops.bn_bwd(x2, dy2, y, mean, rstd, g, want_dres=ctx.has_res)
+        else:
+            import torch.distributed as dist
+            dg, db = ops.bn_bwd_reduce(x2, dy2, y, mean, rstd)
+            sums = torch.stack([dg, db])
+            dist.all_reduce(sums, group=ctx.sync[0])
+            sums = (sums.double() / total).float()            # pre-divided by the global row count: inv_count = 1 below
+            dx, dres = ops.bn_bwd_dx(x2, dy2, y, mean, rstd, g, sums[0].contiguous(), sums[1].contiguous(), 1,
+                                     want_dres=ctx.has_res)
+        return dx.view(dy.shape), dg, db, (dres.view(dy.shape) if dres is not None else None), None, None, None, None
 
 
 class MaxPoolF(torch.autograd.Function):

@@ -580,6 +580,39 @@ extern "C" int vbg_bn_bwd(const float* x, const float* dy, const float* y_relu, 
   return check_launch("vbg_bn_bwd");
 }
 
+// The two halves of vbg_bn_bwd as separate entry points, for SyncBatchNorm: the per-channel sums are all-reduced between them.
+extern "C" int vbg_bn_bwd_reduce(const float* x, const float* dy, const float* y_relu, long long rows, int C, const float* mean,
+                                 const float* rstd, float* sum_dy_xhat, float* sum_dy, float* workspace, size_t ws_bytes,
+                                 vbg_stream_t stream) {
+  VBG_REQUIRE(x && dy && mean && rstd && sum_dy_xhat && sum_dy && workspace && rows > 0 && C >= 4 && C % 4 == 0 && 256 % (C / 4) == 0 &&
+                  aligned16(x) && aligned16(dy) && (!y_relu || aligned16(y_relu)) && aligned16(mean) && aligned16(rstd),
+              "vbg_bn_bwd_reduce: C must be 4 * a divisor of 256, 16B-aligned pointers");
+  long long rpc; const int nblk = colreduce_geometry(rows, C, rpc);
+  if ((size_t)nblk * 2 * C * 4 > ws_bytes) { set_error("vbg_bn_bwd_reduce: workspace of %zu bytes needed", (size_t)nblk * 2 * C * 4); return VBG_EWORKSPACE; }
+  cudaStream_t s = as_stream(stream);
+  BnBwdF f{reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y_relu),
+           reinterpret_cast<const float4*>(mean), reinterpret_cast<const float4*>(rstd)};
+  colreduce2_kernel<<<nblk, 256, 0, s>>>(f, rows, C / 4, rpc, workspace);
+  colreduce2_finish_kernel<<<cdiv(C, 8), 256, 0, s>>>(workspace, nblk, C, 0.0, 0.f, 1, sum_dy, sum_dy_xhat, nullptr);
+  return check_launch("vbg_bn_bwd_reduce");
+}
+
+extern "C" int vbg_bn_bwd_dx(const float* x, const float* dy, const float* y_relu, long long rows, int C, float inv_count, const float* mean,
+                             const float* rstd, const float* gamma, const float* sum_dy_xhat, const float* sum_dy, float* dx, float* dres,
+                             vbg_stream_t stream) {
+  VBG_REQUIRE(x && dy && mean && rstd && gamma && sum_dy_xhat && sum_dy && dx && rows > 0 && C >= 4 && C % 4 == 0 && aligned16(x) &&
+                  aligned16(dy) && aligned16(dx) && (!y_relu || aligned16(y_relu)) && (!dres || aligned16(dres)) && aligned16(gamma) &&
+                  aligned16(mean) && aligned16(rstd) && aligned16(sum_dy_xhat) && aligned16(sum_dy) && inv_count > 0.f,
+              "vbg_bn_bwd_dx: C %% 4 == 0, 16B-aligned pointers, inv_count = 1 / (rows summed into the two sums)");
+  const long long n4 = rows * (C / 4);
+  bn_bwd_dx_kernel<<<grid_for(n4, 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y_relu), n4, C / 4, inv_count,
+      reinterpret_cast<const float4*>(mean), reinterpret_cast<const float4*>(rstd), reinterpret_cast<const float4*>(gamma),
+      reinterpret_cast<const float4*>(sum_dy_xhat), reinterpret_cast<const float4*>(sum_dy), reinterpret_cast<float4*>(dx),
+      reinterpret_cast<float4*>(dres));
+  return check_launch("vbg_bn_bwd_dx");
+}
+
 extern "C" int vbg_maxpool3x3s2_bwd(const float* x, const float* dy, int B, int H, int W, int C, float* dx, vbg_stream_t stream) {
   VBG_REQUIRE(x && dy && dx && B > 0 && H > 0 && W > 0 && C % 4 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx),
               "vbg_maxpool3x3s2_bwd: C %% 4 == 0 and 16B-aligned pointers");

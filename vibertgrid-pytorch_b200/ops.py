@@ -592,6 +592,28 @@ def bn_bwd(x2d, dy2d, y_relu, mean, rstd, gamma, want_dres=False):
     return dx, dres, dg, db
 
 
+def bn_bwd_reduce(x2d, dy2d, y_relu, mean, rstd):
+    """This rank's (sum dy' * xhat, sum dy') of vbg_bn_bwd, before a SyncBatchNorm all-reduce."""
+    rows, Cc = x2d.shape
+    s_xhat, s_dy = (torch.empty(Cc, dtype=torch.float32, device=x2d.device) for _ in range(2))
+    ws = _ws_f32(L.load().vbg_bn_workspace(rows, Cc), x2d.device)
+    L.check(L.load().vbg_bn_bwd_reduce(_f32(x2d), _f32(dy2d), None if y_relu is None else _f32(y_relu), rows, Cc, _f32(mean),
+                                       _f32(rstd), _f32(s_xhat), _f32(s_dy), _f32(ws), ws.numel() * 4, _stream()),
+            "vbg_bn_bwd_reduce")
+    return s_xhat, s_dy
+
+
+def bn_bwd_dx(x2d, dy2d, y_relu, mean, rstd, gamma, s_xhat, s_dy, count, want_dres=False):
+    """dx (and the residual's gradient) from per-channel sums taken over ``count`` rows (all ranks)."""
+    rows, Cc = x2d.shape
+    dx = torch.empty_like(x2d)
+    dres = torch.empty_like(x2d) if want_dres else None
+    L.check(L.load().vbg_bn_bwd_dx(_f32(x2d), _f32(dy2d), None if y_relu is None else _f32(y_relu), rows, Cc, 1.0 / float(count),
+                                   _f32(mean), _f32(rstd), _f32(gamma), _f32(s_xhat), _f32(s_dy), _f32(dx),
+                                   None if dres is None else _f32(dres), _stream()), "vbg_bn_bwd_dx")
+    return dx, dres
+
+
 def maxpool3x3s2_bwd(x, dy):
     B, H, W, Cc = x.shape
     dx = torch.empty_like(x)

@@ -28,6 +28,9 @@ from . import ops
 from .plan import plan_batch, roberta_position_ids
 
 
+FORCE_SYNC_BN_SINGLE_RANK = False      # tests only: run the SyncBatchNorm code path in a one-rank process group
+
+
 def _rand_seed():
     return int(torch.empty((), dtype=torch.int64).random_(0, 2 ** 62).item())       # CPU generator: no device sync
 
@@ -37,16 +40,34 @@ class TrainEngine:
         self.net = net
 
     # ------------------------------------------------------------------ building blocks
+    @staticmethod
+    def _sync_group(bn):
+        """``(process_group,)`` when ``bn`` is an nn.SyncBatchNorm (the reference's ``convert_sync_batchnorm`` under
+        ``syncBN: True``, train_SROIE.py:203-205) in a job of more than one rank, else None -- torch's own rule
+        (SyncBatchNorm falls back to per-rank statistics in a single-process job)."""
+        if not isinstance(bn, nn.SyncBatchNorm):
+            return None
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return None
+        group = getattr(bn, "process_group", None)
+        if dist.get_world_size(group) == 1 and not FORCE_SYNC_BN_SINGLE_RANK:
+            return None
+        return (group,)
+
     def _bn(self, x, bn: nn.modules.batchnorm._BatchNorm, relu=False, residual=None):
         stats = []
-        y = A.BatchNormTrainF.apply(x, bn.weight, bn.bias, residual, relu, bn.eps, stats)
+        y = A.BatchNormTrainF.apply(x, bn.weight, bn.bias, residual, relu, bn.eps, stats, self._sync_group(bn))
         if bn.track_running_stats and bn.running_mean is not None:
             mean, var, n = stats[0]
             with torch.no_grad():
                 bn.num_batches_tracked += 1
                 m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
                 bn.running_mean.mul_(1.0 - m).add_(mean, alpha=m)
-                bn.running_var.mul_(1.0 - m).add_(var, alpha=m * n / max(n - 1, 1))
+                if isinstance(n, torch.Tensor):               # SyncBatchNorm: the global row count lives on the device
+                    bn.running_var.mul_(1.0 - m).add_(var * (n / (n - 1.0).clamp_min(1.0)).float(), alpha=m)
+                else:
+                    bn.running_var.mul_(1.0 - m).add_(var, alpha=m * n / max(n - 1, 1))
         return y
 
     @staticmethod
