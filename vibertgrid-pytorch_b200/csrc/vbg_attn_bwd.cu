@@ -172,9 +172,9 @@ __global__ void __launch_bounds__(256)
 attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o, const int32_t* __restrict__ cu, int heads, float scale,
                     const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dqkv) {
   extern __shared__ float sm[];
-  float *Kt = sm, *Vt = sm + kTile, *Qt = sm + 2 * kTile, *dOt = sm + 3 * kTile, *Qn = sm + 4 * kTile, *dOn = sm + 5 * kTile, *Pn = sm + 6 * kTile,
-        *dSn = sm + 7 * kTile;
-  float* lse_s = sm + 8 * kTile;
+  // six tiles (105 KB: two CTAs per SM): P and dS overwrite the transposed Q / dO tiles once S and dP have been formed
+  float *Kt = sm, *Vt = sm + kTile, *Qt = sm + 2 * kTile, *dOt = sm + 3 * kTile, *Qn = sm + 4 * kTile, *dOn = sm + 5 * kTile, *Pn = Qt, *dSn = dOt;
+  float* lse_s = sm + 6 * kTile;
   float* delta_s = lse_s + kT;
   const int seq = blockIdx.z, h = blockIdx.y;
   const long long rb = cu[seq];
@@ -203,6 +203,7 @@ attn_bwd_dkv_kernel(const float* __restrict__ qkv, const float* __restrict__ d_o
     float s[4][4], dp[4][4]; zero16(s); zero16(dp);
     mm64(Qt, Kt, ty, tx, s);           // rows q = 4 ty + i, columns k = 4 tx + j
     mm64(dOt, Vt, ty, tx, dp);
+    __syncthreads();                   // every thread is done reading Qt / dOt: their storage becomes P / dS
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float pr[4], ds[4];
@@ -245,7 +246,7 @@ extern "C" int vbg_attention_bwd(const float* qkv, const float* out, const float
   float* lse = workspace;
   float* delta = workspace + (size_t)rows * heads;
   const float scale = 1.0f / sqrtf((float)head_dim);
-  const size_t smem_a = (size_t)(6 * kTile + 2 * kT) * sizeof(float), smem_b = (size_t)(8 * kTile + 2 * kT) * sizeof(float);
+  const size_t smem_a = (size_t)(6 * kTile + 2 * kT) * sizeof(float), smem_b = (size_t)(6 * kTile + 2 * kT) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
