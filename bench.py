@@ -413,7 +413,10 @@ def main():
 
     train = None
     if not args.no_train and cfg.classifier_mode == "simp":
-        train = train_step_arm(net, cfg, resident, n_rot, world, min(args.steps, 10))
+        try:
+            train = train_step_arm(net, cfg, resident, n_rot, world, min(args.steps, 10))
+        except Exception as e:          # the headline (forward) line must survive a failure of the secondary measurement
+            train = {"error": f"{type(e).__name__}: {e}"[:300]}
         net.eval()
 
     imgs = cfg.batch * args.steps * world
