@@ -30,7 +30,17 @@ def _p(t: Optional[torch.Tensor], dtype=None, name="tensor"):
     return t.data_ptr()
 
 
+# torch.cuda.current_stream() walks several Python layers (device-index resolution, availability checks, a Stream object):
+# ~7 us per call, once per kernel launch -- a fifth of the host time of the launch-bound training step
+# (profiles/r1_train_host_profile.log).  The raw accessors return the same cudaStream_t (they honour torch.cuda.stream(...)
+# contexts and graph capture) in one C call each.
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def _stream():
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -192,7 +192,10 @@ class TrainEngine:
         min_sizes = [float(sizes[int(torch.empty(1).uniform_(0.0, float(len(sizes))).item())]) for _ in image]
         plan = plan_batch([tuple(im.shape[-2:]) for im in image], [int(s.shape[0]) for s in seg_indices],
                           [int(c.shape[0]) for c in coors], int(corpus.shape[1]), min_sizes, float(net.image_max_size))
-        tab = torch.from_numpy(plan.table).to(dev)
+        # pinned staging + asynchronous copy: a pageable H2D copy would hold the host until the stream has drained, i.e. until
+        # the previous step's kernels are done -- in a launch-bound step that bubble is paid in full
+        tab = torch.from_numpy(plan.table)
+        tab = (tab.pin_memory() if dev.type == "cuda" else tab).to(dev, non_blocking=True)
         dt = {k: tab[s:s + n] for k, (s, n) in plan.offsets.items()}
         dt["ratios"] = dt["ratios"].view(torch.float32)
         seg_off = dt["seg_off"]
