@@ -412,7 +412,7 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     train = None
-    if not args.no_train and cfg.classifier_mode == "simp":
+    if not args.no_train:
         try:
             train = train_step_arm(net, cfg, resident, n_rot, world, min(args.steps, 10))
         except Exception as e:          # the headline (forward) line must survive a failure of the secondary measurement
