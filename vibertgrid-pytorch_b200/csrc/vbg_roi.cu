@@ -401,6 +401,201 @@ roi_align_win_kernel(const void* __restrict__ feat, long long feat_plane, int B,
 #undef ROI_STAMP
 }
 
+
+// ------------------------------------------------------------------ row-per-warp windowed kernel (P = 7, C % 128 == 0)
+// The same separable arithmetic as roi_align_win_kernel (bit-identical results), re-mapped so that nothing is recomputed per
+// thread and no index is divided: a CTA owns (ROI, 128-channel chunk); warp w owns output row ph = w % 7 (two warps per row,
+// splitting the 7 columns 4 + 3) and lane l owns channel quad l, so every tap is one conflict-free 512-byte LDS.128 per warp
+// and the y-table of the row is warp-uniform.  Warp 0 alone does the ROI geometry and (while the window is in flight) the
+// weight tables; the window is fetched pixel-per-warp with 16-byte cp.async pieces (32 lanes = the pixel's 512 bytes: fp32,
+// or 256 B of the hi plane + 256 B of the lo plane, merged to fp32 in place by the warp that fetched it).
+// Instruction budget per 128 channels: ~8 k warp-instructions against ~20 k for two CTAs of the 64-channel kernel, which was
+// issue-bound (profiles/r1_timeline_roi.log).
+constexpr int kR2Ch = 128, kR2Cq = kR2Ch / 4, kR2P = 7, kR2Span = 32, kR2Warps = 14, kR2Threads = kR2Warps * 32;
+
+__global__ void __launch_bounds__(kR2Threads, 2)
+roi_align_row_kernel(const void* __restrict__ feat, long long feat_plane, int B, int Hf, int Wf, int C,
+                     const int32_t* __restrict__ boxes, const int32_t* __restrict__ seg_off, float scale,
+                     void* __restrict__ out, long long out_plane, int32_t* __restrict__ sample_grid, int win_bytes) {
+  constexpr int P = kR2P;
+  extern __shared__ __align__(16) unsigned char win_raw[];
+  __shared__ float wtab[2][kR2P][kR2Span];
+  __shared__ int t_start[2][kR2P], t_cnt[2][kR2P];
+  __shared__ int g_i[8];        // y_lo, x_lo, rows, cols, staged, b, gh, gw
+  __shared__ float g_f[4];      // sh, sw, bh, bw
+  __shared__ int t_ok;
+  const int nchunk = C / kR2Ch, k = blockIdx.x / nchunk, chunk = blockIdx.x - k * nchunk;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- warp 0: geometry (operation for operation as in the other kernels: the sample grid stays bit-exact)
+  float sh = 0.f, sw = 0.f, bh = 0.f, bw = 0.f;
+  int gh = 0, gw = 0, y_lo = 0, y_hi = 0, x_lo = 0, x_hi = 0;
+  if (warp == 0) {
+    int b;
+    if (B <= 31) {
+      const int so = (lane >= 1 && lane < B) ? __ldg(seg_off + lane) : 0x7fffffff;
+      b = __popc(__ballot_sync(0xffffffffu, so <= k));
+    } else {
+      b = sample_of(seg_off, B, k);
+    }
+    const int4 bx = __ldg(reinterpret_cast<const int4*>(boxes) + k);
+    sw = __fmul_rn((float)bx.x, scale); sh = __fmul_rn((float)bx.y, scale);
+    const float ew = __fmul_rn((float)bx.z, scale), eh = __fmul_rn((float)bx.w, scale);
+    const float rw = fmaxf(__fsub_rn(ew, sw), 1.0f), rh = fmaxf(__fsub_rn(eh, sh), 1.0f);
+    bw = __fdiv_rn(rw, (float)P); bh = __fdiv_rn(rh, (float)P);
+    gh = (int)ceilf(__fdiv_rn(rh, (float)P));
+    gw = (int)ceilf(__fdiv_rn(rw, (float)P));
+    const float y_first = __fadd_rn(sh, __fdiv_rn(__fmul_rn(0.5f, bh), (float)gh));
+    const float y_last = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)(P - 1), bh)), __fdiv_rn(__fmul_rn((float)gh - 0.5f, bh), (float)gh));
+    const float x_first = __fadd_rn(sw, __fdiv_rn(__fmul_rn(0.5f, bw), (float)gw));
+    const float x_last = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)(P - 1), bw)), __fdiv_rn(__fmul_rn((float)gw - 0.5f, bw), (float)gw));
+    y_lo = min(max((int)fmaxf(y_first, 0.f), 0), Hf - 1); y_hi = min(max((int)fmaxf(y_last, 0.f) + 1, y_lo), Hf - 1);
+    x_lo = min(max((int)fmaxf(x_first, 0.f), 0), Wf - 1); x_hi = min(max((int)fmaxf(x_last, 0.f) + 1, x_lo), Wf - 1);
+    const int rows = y_hi - y_lo + 1, cols = x_hi - x_lo + 1;
+    if (lane == 0) {
+      g_i[0] = y_lo; g_i[1] = x_lo; g_i[2] = rows; g_i[3] = cols;
+      g_i[4] = ((long long)rows * cols * (kR2Ch * 4) <= (long long)win_bytes) ? 1 : 0;
+      g_i[5] = b; g_i[6] = gh; g_i[7] = gw;
+      g_f[0] = sh; g_f[1] = sw; g_f[2] = bh; g_f[3] = bw;
+      if (sample_grid && chunk == 0) { sample_grid[2 * k] = gh; sample_grid[2 * k + 1] = gw; }
+    }
+  }
+  __syncthreads();
+  const int rows = g_i[2], cols = g_i[3], b = g_i[5];
+  const bool staged = g_i[4] != 0;
+  y_lo = g_i[0]; x_lo = g_i[1];
+  const int C4 = C >> 2, npix = rows * cols;
+  const size_t f0 = (size_t)b * Hf * Wf * C4 + (size_t)chunk * kR2Cq;       // in units of 4 elements
+
+  // ---- window fetch: warp w takes pixels w, w + 14, ...; lane l the l-th 16-byte piece of the pixel's 512 bytes
+  if (staged) {
+    const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(win_raw);
+    int y = warp / cols, x = warp - y * cols;
+    for (int pix = warp; pix < npix; pix += kR2Warps) {
+      const size_t g4 = f0 + ((size_t)(y_lo + y) * Wf + (x_lo + x)) * C4;
+      const uint32_t dst = win_s + (uint32_t)pix * 512u + (uint32_t)lane * 16u;
+      if (feat_plane == 0) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const float4*>(feat) + g4 + lane) : "memory");
+      } else {
+        // 4 elements = 8 bytes per plane: the chunk's 128 channels are 256 B = 16 pieces in each plane
+        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(feat) + (lane < 16 ? 0 : feat_plane) + g4 * 4 + (size_t)(lane & 15) * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      }
+      x += kR2Warps;
+      while (x >= cols) { x -= cols; ++y; }
+    }
+  }
+
+  // ---- warp 0: per-bin separable weight tables (same code path as roi_align_win_kernel), while the window is in flight
+  if (warp == 0) {
+    for (int i = lane; i < 2 * kR2P * kR2Span; i += 32) (&wtab[0][0][0])[i] = 0.f;
+    __syncwarp();
+    int ok = 1;
+    if (lane < 2 * P) {
+      const int axis = lane / P, pb = lane - axis * P;            // axis 0: x (columns), 1: y (rows)
+      const int g = axis ? gh : gw, dim = axis ? Hf : Wf, lo_w = axis ? y_lo : x_lo, hi_w = axis ? y_hi : x_hi;
+      const float start = axis ? sh : sw, bin = axis ? bh : bw;
+      float* w = wtab[axis][pb];
+      int base = 0, cnt = 0;
+      for (int i = 0; i < g; ++i) {
+        float c = __fadd_rn(__fadd_rn(start, __fmul_rn((float)pb, bin)), __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)g));
+        if (c < -1.0f || c > (float)dim) continue;
+        c = fmaxf(c, 0.f);
+        int lo = (int)c, hi;
+        if (lo >= dim - 1) { hi = lo = dim - 1; c = (float)lo; } else { hi = lo + 1; }
+        const float l = c - (float)lo, h = 1.f - l;
+        if (cnt == 0) base = lo;
+        if (hi - base >= kR2Span || lo < base || lo < lo_w || hi > hi_w) { ok = 0; break; }
+        w[lo - base] += h;
+        w[hi - base] += l;
+        cnt = hi - base + 1;
+      }
+      t_start[axis][pb] = base - lo_w;
+      t_cnt[axis][pb] = cnt;
+    }
+    const unsigned okm = __ballot_sync(0xffffffffu, ok != 0);
+    if (lane == 0) t_ok = (okm == 0xffffffffu) ? 1 : 0;
+  }
+
+  // ---- land + merge: each warp waits for ITS pixels only
+  if (staged) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    if (feat_plane != 0) {
+      for (int pix = warp; pix < npix; pix += kR2Warps) {
+        unsigned char* base = win_raw + (size_t)pix * 512;
+        const uint2 h = *reinterpret_cast<const uint2*>(base + lane * 8);
+        const uint2 l = *reinterpret_cast<const uint2*>(base + 256 + lane * 8);
+        __syncwarp();                       // all 32 lanes hold their pieces before the fp32 values overwrite them
+        *reinterpret_cast<float4*>(base + lane * 16) = merge4(h, l);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- bins: warp -> (row ph, column range), lane -> channel quad
+  const int ph = warp % P, pw0 = (warp < P) ? 0 : 4, pw1 = (warp < P) ? 4 : P;
+  const float count = (float)max(g_i[6] * g_i[7], 1);
+  const size_t o_base = ((size_t)k * P * P + (size_t)ph * P) * C4 + (size_t)chunk * kR2Cq + lane;
+  if (staged && t_ok) {
+    const int y0 = t_start[1][ph], ny = t_cnt[1][ph];
+    const float* wy = wtab[1][ph];
+    const float4* win4 = reinterpret_cast<const float4*>(win_raw) + lane;
+    for (int pw = pw0; pw < pw1; ++pw) {
+      const int x0 = t_start[0][pw], nx = t_cnt[0][pw];
+      const float* wx = wtab[0][pw];
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < ny; ++j) {
+        const float4* rowp = win4 + (size_t)((y0 + j) * cols + x0) * kR2Cq;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int i = 0; i < nx; ++i) {
+          const float w = wx[i];
+          const float4 v = rowp[i * kR2Cq];
+          t.x = fmaf(w, v.x, t.x); t.y = fmaf(w, v.y, t.y); t.z = fmaf(w, v.z, t.z); t.w = fmaf(w, v.w, t.w);
+        }
+        const float wj = wy[j];
+        acc.x = fmaf(wj, t.x, acc.x); acc.y = fmaf(wj, t.y, acc.y); acc.z = fmaf(wj, t.z, acc.z); acc.w = fmaf(wj, t.w, acc.w);
+      }
+      acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);
+      acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
+      st4_fmt(out, out_plane, o_base + (size_t)pw * C4, acc);
+    }
+  } else {
+    // window too large for shared memory, or a table assumption failed: per-sample taps straight from global memory
+    const float s_h = g_f[0], s_w = g_f[1], b_h = g_f[2], b_w = g_f[3];
+    const int g_h = g_i[6], g_w = g_i[7];
+    const size_t fq = f0 + lane;
+    for (int pw = pw0; pw < pw1; ++pw) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int iy = 0; iy < g_h; ++iy) {
+        float y = __fadd_rn(__fadd_rn(s_h, __fmul_rn((float)ph, b_h)), __fdiv_rn(__fmul_rn((float)iy + 0.5f, b_h), (float)g_h));
+        for (int ix = 0; ix < g_w; ++ix) {
+          float x = __fadd_rn(__fadd_rn(s_w, __fmul_rn((float)pw, b_w)), __fdiv_rn(__fmul_rn((float)ix + 0.5f, b_w), (float)g_w));
+          if (y < -1.0f || y > (float)Hf || x < -1.0f || x > (float)Wf) continue;
+          float yy = fmaxf(y, 0.f), xx = fmaxf(x, 0.f);
+          int yl = (int)yy, xl = (int)xx, yh, xh;
+          if (yl >= Hf - 1) { yh = yl = Hf - 1; yy = (float)yl; } else { yh = yl + 1; }
+          if (xl >= Wf - 1) { xh = xl = Wf - 1; xx = (float)xl; } else { xh = xl + 1; }
+          const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+          const float4 a = ld4_fmt(feat, feat_plane, fq + ((size_t)yl * Wf + xl) * C4);
+          const float4 bb = ld4_fmt(feat, feat_plane, fq + ((size_t)yl * Wf + xh) * C4);
+          const float4 cc = ld4_fmt(feat, feat_plane, fq + ((size_t)yh * Wf + xl) * C4);
+          const float4 d = ld4_fmt(feat, feat_plane, fq + ((size_t)yh * Wf + xh) * C4);
+          acc.x += w1 * a.x + w2 * bb.x + w3 * cc.x + w4 * d.x;
+          acc.y += w1 * a.y + w2 * bb.y + w3 * cc.y + w4 * d.y;
+          acc.z += w1 * a.z + w2 * bb.z + w3 * cc.z + w4 * d.z;
+          acc.w += w1 * a.w + w2 * bb.w + w3 * cc.w + w4 * d.w;
+        }
+      }
+      acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);
+      acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
+      st4_fmt(out, out_plane, o_base + (size_t)pw * C4, acc);
+    }
+  }
+}
+
 }  // namespace vbg
 
 using namespace vbg;
@@ -433,6 +628,21 @@ extern "C" int vbg_roi_align_x(const void* feat, long long feat_plane, int B, in
   }
   cudaStream_t s = as_stream(stream);
   static const bool direct = [] { const char* e = getenv("VBG_ROI_DIRECT"); return e && e[0] == '1'; }();
+  const char* row_env = getenv("VBG_ROI_ROW");                 // read per call: tests switch kernels inside one process
+  const bool rowk = row_env && row_env[0] == '1';              // opt-in until measured
+  if (!direct && rowk && P == kR2P && C % kR2Ch == 0) {
+    // 100 KB window (two resident CTAs of 14 warps per SM): a line-sized ROI at stride 4 needs 60-92 KB per 128-channel chunk
+    constexpr int win_bytes = 100 * 1024;
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(roi_align_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, win_bytes);
+      if (e != cudaSuccess) { set_error("vbg_roi_align_fwd: smem opt-in failed: %s", cudaGetErrorString(e)); return VBG_ECUDA; }
+      attr2 = true;
+    }
+    roi_align_row_kernel<<<(unsigned)((long long)K * (C / kR2Ch)), kR2Threads, win_bytes, s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off,
+                                                                                           spatial_scale, out, out_plane, sample_grid, win_bytes);
+    return check_launch("vbg_roi_align_fwd");
+  }
   if (!direct && C % kRoiCh == 0) {
     // 60 KB window (three resident CTAs per SM): a line-sized ROI at stride 4 needs 30-46 KB per 64-channel chunk
     constexpr int win_floats = 60 * 1024 / 4;
