@@ -21,8 +21,11 @@ flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 by = B * 256 * Hf * Wf * 4 + K * 256 * 49 * 4 + K * 20
 
 
+NAMES = {0: "windowed-64    ", 1: "row-per-warp 128", 2: "row-per-warp 64 "}
+
+
 def run(row, split):
-    os.environ["VBG_ROI_ROW"] = "1" if row else "0"
+    os.environ["VBG_ROI_ROW"] = str(int(row))
     f = feat_s if split else feat32
     return ops.roi_align(f, boxes, seg_off, 0.25, 7, want_grid=True, split_out=split)
 
@@ -41,12 +44,15 @@ def timed(row, split, reps=10):
 
 
 for split in (True, False):
-    (a, ga), (b, gb) = run(False, split), run(True, split)
-    ta, tb = (a.t if split else a), (b.t if split else b)
-    same = torch.equal(ta, tb) and torch.equal(ga, gb)
-    md = float((ta.float() - tb.float()).abs().max())
-    print(f"[{cfg.name} planes={split}] outputs identical: {same} (max |diff| {md:.3e}), finite: {bool(torch.isfinite(tb.float()).all())}")
-    for row in (False, True):
+    a, ga = run(0, split)
+    ta = a.t if split else a
+    for v in (1, 2):
+        b, gb = run(v, split)
+        tb = b.t if split else b
+        same = torch.equal(ta, tb) and torch.equal(ga, gb)
+        md = float((ta.float() - tb.float()).abs().max())
+        print(f"[{cfg.name} planes={split}] {NAMES[v]} == windowed-64: {same} (max |diff| {md:.3e}), finite: {bool(torch.isfinite(tb.float()).all())}")
+    for row in (0, 1, 2):
         ms, best = timed(row, split)
-        print(f"[{cfg.name} planes={split}] {'row-per-warp' if row else 'windowed-64 '} {ms * 1e3:7.1f} us avg, {best * 1e3:7.1f} us best"
+        print(f"[{cfg.name} planes={split}] {NAMES[row]} {ms * 1e3:7.1f} us avg, {best * 1e3:7.1f} us best"
               f" -> {by / ms / 1e6:7.0f} GB/s = {by / ms / 1e6 / 6548.8:.3f} of measured HBM peak")

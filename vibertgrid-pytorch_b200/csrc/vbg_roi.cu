@@ -411,21 +411,30 @@ roi_align_win_kernel(const void* __restrict__ feat, long long feat_plane, int B,
 // or 256 B of the hi plane + 256 B of the lo plane, merged to fp32 in place by the warp that fetched it).
 // Instruction budget per 128 channels: ~8 k warp-instructions against ~20 k for two CTAs of the 64-channel kernel, which was
 // issue-bound (profiles/r1_timeline_roi.log).
-constexpr int kR2Ch = 128, kR2Cq = kR2Ch / 4, kR2P = 7, kR2Span = 32, kR2Warps = 14, kR2Threads = kR2Warps * 32;
+constexpr int kR2P = 7, kR2Span = 32;
 
-__global__ void __launch_bounds__(kR2Threads, 2)
+// CH = 128: 14 warps, lane = channel quad, warps w and w + 7 share output row w (columns 0-3 / 4-6); 100 KB window, 2 CTAs per SM.
+// CH = 64:   7 warps, half-warps share the row (lanes 0-15: columns 0-3, lanes 16-31: columns 4-6), lane % 16 = channel quad;
+//            48 KB window, 4 CTAs per SM -- twice the CTAs in flight to hide the box -> geometry -> window -> bins chain.
+template <int CH>
+__global__ void __launch_bounds__(CH == 128 ? 448 : 224, CH == 128 ? 2 : 4)
 roi_align_row_kernel(const void* __restrict__ feat, long long feat_plane, int B, int Hf, int Wf, int C,
                      const int32_t* __restrict__ boxes, const int32_t* __restrict__ seg_off, float scale,
                      void* __restrict__ out, long long out_plane, int32_t* __restrict__ sample_grid, int win_bytes) {
   constexpr int P = kR2P;
+  constexpr int kCq = CH / 4;                 // channel quads per chunk = 16-byte pieces per window pixel
+  constexpr int kPix = 32 / kCq;              // window pixels one warp moves per iteration (1 or 2)
+  constexpr int kWarps = 7 * (2 / kPix);      // 14 or 7
+  constexpr int kPixBytes = CH * 4;
   extern __shared__ __align__(16) unsigned char win_raw[];
   __shared__ float wtab[2][kR2P][kR2Span];
   __shared__ int t_start[2][kR2P], t_cnt[2][kR2P];
   __shared__ int g_i[8];        // y_lo, x_lo, rows, cols, staged, b, gh, gw
   __shared__ float g_f[4];      // sh, sw, bh, bw
   __shared__ int t_ok;
-  const int nchunk = C / kR2Ch, k = blockIdx.x / nchunk, chunk = blockIdx.x - k * nchunk;
+  const int nchunk = C / CH, k = blockIdx.x / nchunk, chunk = blockIdx.x - k * nchunk;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int piece = lane % kCq, sub = lane / kCq;
 
   // ---- warp 0: geometry (operation for operation as in the other kernels: the sample grid stays bit-exact)
   float sh = 0.f, sw = 0.f, bh = 0.f, bw = 0.f;
@@ -454,7 +463,7 @@ roi_align_row_kernel(const void* __restrict__ feat, long long feat_plane, int B,
     const int rows = y_hi - y_lo + 1, cols = x_hi - x_lo + 1;
     if (lane == 0) {
       g_i[0] = y_lo; g_i[1] = x_lo; g_i[2] = rows; g_i[3] = cols;
-      g_i[4] = ((long long)rows * cols * (kR2Ch * 4) <= (long long)win_bytes) ? 1 : 0;
+      g_i[4] = ((long long)rows * cols * kPixBytes <= (long long)win_bytes) ? 1 : 0;
       g_i[5] = b; g_i[6] = gh; g_i[7] = gw;
       g_f[0] = sh; g_f[1] = sw; g_f[2] = bh; g_f[3] = bw;
       if (sample_grid && chunk == 0) { sample_grid[2 * k] = gh; sample_grid[2 * k + 1] = gw; }
@@ -465,23 +474,25 @@ roi_align_row_kernel(const void* __restrict__ feat, long long feat_plane, int B,
   const bool staged = g_i[4] != 0;
   y_lo = g_i[0]; x_lo = g_i[1];
   const int C4 = C >> 2, npix = rows * cols;
-  const size_t f0 = (size_t)b * Hf * Wf * C4 + (size_t)chunk * kR2Cq;       // in units of 4 elements
+  const size_t f0 = (size_t)b * Hf * Wf * C4 + (size_t)chunk * kCq;       // in units of 4 elements
 
-  // ---- window fetch: warp w takes pixels w, w + 14, ...; lane l the l-th 16-byte piece of the pixel's 512 bytes
+  // ---- window fetch: a warp moves kPix pixels per iteration; lane -> (pixel sub, 16-byte piece of its CH*4 bytes)
   if (staged) {
     const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(win_raw);
-    int y = warp / cols, x = warp - y * cols;
-    for (int pix = warp; pix < npix; pix += kR2Warps) {
+    const int first = warp * kPix + sub;
+    int y = first / cols, x = first - y * cols;
+    for (int pix = first; pix < npix; pix += kWarps * kPix) {
       const size_t g4 = f0 + ((size_t)(y_lo + y) * Wf + (x_lo + x)) * C4;
-      const uint32_t dst = win_s + (uint32_t)pix * 512u + (uint32_t)lane * 16u;
+      const uint32_t dst = win_s + (uint32_t)pix * (uint32_t)kPixBytes + (uint32_t)piece * 16u;
       if (feat_plane == 0) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const float4*>(feat) + g4 + lane) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const float4*>(feat) + g4 + piece) : "memory");
       } else {
-        // 4 elements = 8 bytes per plane: the chunk's 128 channels are 256 B = 16 pieces in each plane
-        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(feat) + (lane < 16 ? 0 : feat_plane) + g4 * 4 + (size_t)(lane & 15) * 8;
+        // the chunk's CH channels are CH*2 bytes = kCq/2 pieces in each plane: hi pieces first, then lo pieces
+        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(feat) + (piece < kCq / 2 ? 0 : feat_plane) + g4 * 4 +
+                                   (size_t)(piece % (kCq / 2)) * 8;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
       }
-      x += kR2Warps;
+      x += kWarps * kPix;
       while (x >= cols) { x -= cols; ++y; }
     }
   }
@@ -522,36 +533,41 @@ roi_align_row_kernel(const void* __restrict__ feat, long long feat_plane, int B,
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     if (feat_plane != 0) {
-      for (int pix = warp; pix < npix; pix += kR2Warps) {
-        unsigned char* base = win_raw + (size_t)pix * 512;
-        const uint2 h = *reinterpret_cast<const uint2*>(base + lane * 8);
-        const uint2 l = *reinterpret_cast<const uint2*>(base + 256 + lane * 8);
-        __syncwarp();                       // all 32 lanes hold their pieces before the fp32 values overwrite them
-        *reinterpret_cast<float4*>(base + lane * 16) = merge4(h, l);
+      for (int p0 = warp * kPix; p0 < npix; p0 += kWarps * kPix) {      // warp-uniform trip count
+        const int pix = p0 + sub;
+        unsigned char* base = win_raw + (size_t)pix * kPixBytes;
+        uint2 h = make_uint2(0u, 0u), l = h;
+        if (pix < npix) {
+          h = *reinterpret_cast<const uint2*>(base + piece * 8);
+          l = *reinterpret_cast<const uint2*>(base + CH * 2 + piece * 8);
+        }
+        __syncwarp();                       // every lane holds its pieces before the fp32 values overwrite them
+        if (pix < npix) *reinterpret_cast<float4*>(base + piece * 16) = merge4(h, l);
       }
     }
   }
   __syncthreads();
 
-  // ---- bins: warp -> (row ph, column range), lane -> channel quad
-  const int ph = warp % P, pw0 = (warp < P) ? 0 : 4, pw1 = (warp < P) ? 4 : P;
+  // ---- bins: (warp, half-warp) -> (row ph, column range), lane -> channel quad
+  const int ph = warp % P, part = (kPix == 2) ? sub : warp / P;
+  const int pw0 = part ? 4 : 0, pw1 = part ? P : 4;
   const float count = (float)max(g_i[6] * g_i[7], 1);
-  const size_t o_base = ((size_t)k * P * P + (size_t)ph * P) * C4 + (size_t)chunk * kR2Cq + lane;
+  const size_t o_base = ((size_t)k * P * P + (size_t)ph * P) * C4 + (size_t)chunk * kCq + piece;
   if (staged && t_ok) {
     const int y0 = t_start[1][ph], ny = t_cnt[1][ph];
     const float* wy = wtab[1][ph];
-    const float4* win4 = reinterpret_cast<const float4*>(win_raw) + lane;
+    const float4* win4 = reinterpret_cast<const float4*>(win_raw) + piece;
     for (int pw = pw0; pw < pw1; ++pw) {
       const int x0 = t_start[0][pw], nx = t_cnt[0][pw];
       const float* wx = wtab[0][pw];
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int j = 0; j < ny; ++j) {
-        const float4* rowp = win4 + (size_t)((y0 + j) * cols + x0) * kR2Cq;
+        const float4* rowp = win4 + (size_t)((y0 + j) * cols + x0) * kCq;
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
         for (int i = 0; i < nx; ++i) {
           const float w = wx[i];
-          const float4 v = rowp[i * kR2Cq];
+          const float4 v = rowp[i * kCq];
           t.x = fmaf(w, v.x, t.x); t.y = fmaf(w, v.y, t.y); t.z = fmaf(w, v.z, t.z); t.w = fmaf(w, v.w, t.w);
         }
         const float wj = wy[j];
@@ -565,7 +581,7 @@ roi_align_row_kernel(const void* __restrict__ feat, long long feat_plane, int B,
     // window too large for shared memory, or a table assumption failed: per-sample taps straight from global memory
     const float s_h = g_f[0], s_w = g_f[1], b_h = g_f[2], b_w = g_f[3];
     const int g_h = g_i[6], g_w = g_i[7];
-    const size_t fq = f0 + lane;
+    const size_t fq = f0 + piece;
     for (int pw = pw0; pw < pw1; ++pw) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int iy = 0; iy < g_h; ++iy) {
@@ -628,19 +644,33 @@ extern "C" int vbg_roi_align_x(const void* feat, long long feat_plane, int B, in
   }
   cudaStream_t s = as_stream(stream);
   static const bool direct = [] { const char* e = getenv("VBG_ROI_DIRECT"); return e && e[0] == '1'; }();
-  const char* row_env = getenv("VBG_ROI_ROW");                 // read per call: tests switch kernels inside one process
-  const bool rowk = row_env && row_env[0] == '1';              // opt-in until measured
-  if (!direct && rowk && P == kR2P && C % kR2Ch == 0) {
+  // VBG_ROI_ROW: 1 (default) = row-per-warp kernel, 128-channel chunks; 2 = its 64-channel form; 0 = the 64-channel windowed
+  // kernel below.  Read per call: tests and scripts/roi_compare.py switch kernels inside one process.
+  const char* row_env = getenv("VBG_ROI_ROW");
+  const int rowk = row_env ? (row_env[0] - '0') : 1;
+  if (!direct && rowk == 1 && P == kR2P && C % 128 == 0) {
     // 100 KB window (two resident CTAs of 14 warps per SM): a line-sized ROI at stride 4 needs 60-92 KB per 128-channel chunk
     constexpr int win_bytes = 100 * 1024;
     static bool attr2 = false;
     if (!attr2) {
-      cudaError_t e = cudaFuncSetAttribute(roi_align_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, win_bytes);
+      cudaError_t e = cudaFuncSetAttribute(roi_align_row_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, win_bytes);
       if (e != cudaSuccess) { set_error("vbg_roi_align_fwd: smem opt-in failed: %s", cudaGetErrorString(e)); return VBG_ECUDA; }
       attr2 = true;
     }
-    roi_align_row_kernel<<<(unsigned)((long long)K * (C / kR2Ch)), kR2Threads, win_bytes, s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off,
-                                                                                           spatial_scale, out, out_plane, sample_grid, win_bytes);
+    roi_align_row_kernel<128><<<(unsigned)((long long)K * (C / 128)), 448, win_bytes, s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off,
+                                                                                        spatial_scale, out, out_plane, sample_grid, win_bytes);
+    return check_launch("vbg_roi_align_fwd");
+  }
+  if (!direct && rowk == 2 && P == kR2P && C % 64 == 0) {
+    constexpr int win_bytes = 48 * 1024;      // four resident CTAs of 7 warps per SM
+    static bool attr3 = false;
+    if (!attr3) {
+      cudaError_t e = cudaFuncSetAttribute(roi_align_row_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, win_bytes);
+      if (e != cudaSuccess) { set_error("vbg_roi_align_fwd: smem opt-in failed: %s", cudaGetErrorString(e)); return VBG_ECUDA; }
+      attr3 = true;
+    }
+    roi_align_row_kernel<64><<<(unsigned)((long long)K * (C / 64)), 224, win_bytes, s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off,
+                                                                                      spatial_scale, out, out_plane, sample_grid, win_bytes);
     return check_launch("vbg_roi_align_fwd");
   }
   if (!direct && C % kRoiCh == 0) {
