@@ -80,3 +80,26 @@ def test_engine_orchestration_with_standins(name, tmp_path, monkeypatch):
         assert "aux_ce" in out2 and "pos_neg_labels" not in out2
     total2 = losses.main_loss(net, out2) + net.loss_control_lambda * losses.aux_loss(net, out2)
     assert abs(float(total2.reshape(-1)[0]) - float(fx["loss"][0])) <= 1e-4 * max(1.0, abs(float(fx["loss"][0])))
+
+
+def test_roberta_position_ids_match_transformers():
+    """plan.roberta_position_ids over PACKED rows (sequences back to back, ``pos`` = index inside the sequence) against
+    transformers' own RobertaEmbeddings.create_position_ids_from_input_ids applied per sequence -- including <pad> ids (1)
+    inside and at the start of a sequence."""
+    import torch
+    from vibertgrid_pytorch_b200.plan import roberta_position_ids
+    try:
+        from transformers.models.roberta.modeling_roberta import RobertaEmbeddings
+        hf = RobertaEmbeddings.create_position_ids_from_input_ids
+    except Exception:                       # pragma: no cover - other transformers layouts
+        pytest.skip("transformers without RobertaEmbeddings.create_position_ids_from_input_ids")
+    g = torch.Generator().manual_seed(3)
+    lens = [7, 1, 512, 4, 33]
+    seqs = [torch.randint(0, 50, (n,), generator=g) for n in lens]       # small vocabulary: id 1 occurs often
+    seqs[0][0] = 1
+    seqs[2][5:9] = 1
+    ids = torch.cat(seqs).to(torch.int32)
+    pos = torch.cat([torch.arange(n) for n in lens]).to(torch.int32)
+    got = roberta_position_ids(ids, pos, 1)
+    want = torch.cat([hf(s[None].long(), 1)[0] for s in seqs])
+    assert got.dtype == pos.dtype and torch.equal(got.long(), want)
