@@ -1,5 +1,5 @@
 """ROI-align kernels side by side at a BASELINE shape: the 64-channel windowed kernel (default) against the row-per-warp kernel
-(VBG_ROI_ROW=1): bit-equality of the outputs in both storage formats, then CUDA-event timings with an L2 flush between launches
+(VBG_ROI_ROW=1 / 2) and its persistent double-buffered forms (3 / 4): bit-equality of the outputs in both storage formats, then CUDA-event timings with an L2 flush between launches
 (the same recipe as bench.py's roofline_hbm_kernels)."""
 import os, sys
 import torch
@@ -21,7 +21,7 @@ flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 by = B * 256 * Hf * Wf * 4 + K * 256 * 49 * 4 + K * 20
 
 
-NAMES = {0: "windowed-64    ", 1: "row-per-warp 128", 2: "row-per-warp 64 "}
+NAMES = {0: "windowed-64     ", 1: "row-per-warp 128", 2: "row-per-warp 64 ", 3: "persistent 64   ", 4: "persistent 128  "}
 
 
 def run(row, split):
@@ -46,13 +46,13 @@ def timed(row, split, reps=10):
 for split in (True, False):
     a, ga = run(0, split)
     ta = a.t if split else a
-    for v in (1, 2):
+    for v in (1, 2, 3, 4):
         b, gb = run(v, split)
         tb = b.t if split else b
         same = torch.equal(ta, tb) and torch.equal(ga, gb)
         md = float((ta.float() - tb.float()).abs().max())
         print(f"[{cfg.name} planes={split}] {NAMES[v]} == windowed-64: {same} (max |diff| {md:.3e}), finite: {bool(torch.isfinite(tb.float()).all())}")
-    for row in (0, 1, 2):
+    for row in (0, 1, 2, 3, 4):
         ms, best = timed(row, split)
         print(f"[{cfg.name} planes={split}] {NAMES[row]} {ms * 1e3:7.1f} us avg, {best * 1e3:7.1f} us best"
               f" -> {by / ms / 1e6:7.0f} GB/s = {by / ms / 1e6 / 6548.8:.3f} of measured HBM peak")

@@ -612,6 +612,239 @@ roi_align_row_kernel(const void* __restrict__ feat, long long feat_plane, int B,
   }
 }
 
+
+// ------------------------------------------------------------------ persistent, double-buffered form of the row-per-warp kernel
+// NOT YET RUN ON A GPU (written after this round's GPU budget was spent; opt-in: VBG_ROI_ROW=3 / 4; bit-equality with the
+// kernels above and the timing are one `python scripts/roi_compare.py` away).  Why: roi_align_row_kernel keeps its window loads
+// in flight for only ~2.5 of a CTA's ~9 us, and bytes in flight per SM x SMs / DRAM latency is exactly the 2.9 TB/s it reaches
+// (DESIGN.md section 8).  Here a CTA is persistent over (ROI, chunk) items and owns TWO window buffers: the geometry and the
+// cp.async fetch of item i + 1 are issued before the merge + bins of item i (cp.async commit groups, wait_group 1), so a window
+// is in flight all the time.  The arithmetic is the row kernel's, statement for statement.
+// Slots: per-item geometry / tables live in 3 rotating slots (item i + 1 is written while items i - 1 and i may still be read),
+// windows in 2 buffers (buffer of item i + 1 is rewritten only after barrier A, i.e. after every warp left bins(i - 1)).
+struct RoiItemGeo {
+  int y_lo, x_lo, rows, cols, staged, b, gh, gw, ok;
+  float sh, sw, bh, bw;
+};
+
+template <int CH>
+__global__ void __launch_bounds__(CH == 128 ? 448 : 224, CH == 128 ? 1 : 2)
+roi_align_pipe_kernel(const void* __restrict__ feat, long long feat_plane, int B, int Hf, int Wf, int C,
+                      const int32_t* __restrict__ boxes, const int32_t* __restrict__ seg_off, int K, float scale,
+                      void* __restrict__ out, long long out_plane, int32_t* __restrict__ sample_grid, int win_bytes) {
+  constexpr int P = kR2P;
+  constexpr int kCq = CH / 4, kPix = 32 / kCq, kWarps = 7 * (2 / kPix), kPixBytes = CH * 4;
+  extern __shared__ __align__(16) unsigned char win_all[];          // two windows of win_bytes each
+  __shared__ float wtab[3][2][kR2P][kR2Span];
+  __shared__ int t_start[3][2][kR2P], t_cnt[3][2][kR2P];
+  __shared__ RoiItemGeo geo[3];
+  const int nchunk = C / CH, total = K * nchunk;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int piece = lane % kCq, sub = lane / kCq;
+  const int C4 = C >> 2;
+
+  // warp 0: geometry of `item` into slot `sl` (same operations as every other ROI kernel here: bit-exact sample grid)
+  auto geometry = [&](int item, int sl) {
+    const int k = item / nchunk, chunk = item - k * nchunk;
+    int b;
+    if (B <= 31) {
+      const int so = (lane >= 1 && lane < B) ? __ldg(seg_off + lane) : 0x7fffffff;
+      b = __popc(__ballot_sync(0xffffffffu, so <= k));
+    } else {
+      b = sample_of(seg_off, B, k);
+    }
+    const int4 bx = __ldg(reinterpret_cast<const int4*>(boxes) + k);
+    const float sw = __fmul_rn((float)bx.x, scale), sh = __fmul_rn((float)bx.y, scale);
+    const float ew = __fmul_rn((float)bx.z, scale), eh = __fmul_rn((float)bx.w, scale);
+    const float rw = fmaxf(__fsub_rn(ew, sw), 1.0f), rh = fmaxf(__fsub_rn(eh, sh), 1.0f);
+    const float bw = __fdiv_rn(rw, (float)P), bh = __fdiv_rn(rh, (float)P);
+    const int gh = (int)ceilf(__fdiv_rn(rh, (float)P));
+    const int gw = (int)ceilf(__fdiv_rn(rw, (float)P));
+    const float y_first = __fadd_rn(sh, __fdiv_rn(__fmul_rn(0.5f, bh), (float)gh));
+    const float y_last = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)(P - 1), bh)), __fdiv_rn(__fmul_rn((float)gh - 0.5f, bh), (float)gh));
+    const float x_first = __fadd_rn(sw, __fdiv_rn(__fmul_rn(0.5f, bw), (float)gw));
+    const float x_last = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)(P - 1), bw)), __fdiv_rn(__fmul_rn((float)gw - 0.5f, bw), (float)gw));
+    const int y_lo = min(max((int)fmaxf(y_first, 0.f), 0), Hf - 1), y_hi = min(max((int)fmaxf(y_last, 0.f) + 1, y_lo), Hf - 1);
+    const int x_lo = min(max((int)fmaxf(x_first, 0.f), 0), Wf - 1), x_hi = min(max((int)fmaxf(x_last, 0.f) + 1, x_lo), Wf - 1);
+    const int rows = y_hi - y_lo + 1, cols = x_hi - x_lo + 1;
+    if (lane == 0) {
+      RoiItemGeo g;
+      g.y_lo = y_lo; g.x_lo = x_lo; g.rows = rows; g.cols = cols;
+      g.staged = ((long long)rows * cols * kPixBytes <= (long long)win_bytes) ? 1 : 0;
+      g.b = b; g.gh = gh; g.gw = gw; g.ok = 0;
+      g.sh = sh; g.sw = sw; g.bh = bh; g.bw = bw;
+      geo[sl] = g;
+      if (sample_grid && chunk == 0) { sample_grid[2 * k] = gh; sample_grid[2 * k + 1] = gw; }
+    }
+    __syncwarp();
+  };
+
+  // warp 0: separable per-bin weight tables of the item in slot `sl` (geometry already published there)
+  auto tables = [&](int sl) {
+    const RoiItemGeo g = geo[sl];
+    const int y_hi = g.y_lo + g.rows - 1, x_hi = g.x_lo + g.cols - 1;
+    for (int i = lane; i < 2 * kR2P * kR2Span; i += 32) (&wtab[sl][0][0][0])[i] = 0.f;
+    __syncwarp();
+    int ok = 1;
+    if (lane < 2 * P) {
+      const int axis = lane / P, pb = lane - axis * P;            // axis 0: x (columns), 1: y (rows)
+      const int gn = axis ? g.gh : g.gw, dim = axis ? Hf : Wf, lo_w = axis ? g.y_lo : g.x_lo, hi_w = axis ? y_hi : x_hi;
+      const float start = axis ? g.sh : g.sw, bin = axis ? g.bh : g.bw;
+      float* w = wtab[sl][axis][pb];
+      int base = 0, cnt = 0;
+      for (int i = 0; i < gn; ++i) {
+        float c = __fadd_rn(__fadd_rn(start, __fmul_rn((float)pb, bin)), __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)gn));
+        if (c < -1.0f || c > (float)dim) continue;
+        c = fmaxf(c, 0.f);
+        int lo = (int)c, hi;
+        if (lo >= dim - 1) { hi = lo = dim - 1; c = (float)lo; } else { hi = lo + 1; }
+        const float l = c - (float)lo, h = 1.f - l;
+        if (cnt == 0) base = lo;
+        if (hi - base >= kR2Span || lo < base || lo < lo_w || hi > hi_w) { ok = 0; break; }
+        w[lo - base] += h;
+        w[hi - base] += l;
+        cnt = hi - base + 1;
+      }
+      t_start[sl][axis][pb] = base - lo_w;
+      t_cnt[sl][axis][pb] = cnt;
+    }
+    const unsigned okm = __ballot_sync(0xffffffffu, ok != 0);
+    if (lane == 0) geo[sl].ok = (okm == 0xffffffffu) ? 1 : 0;
+    __syncwarp();
+  };
+
+  // all warps: cp.async fetch of the item's window into `win`; always commits one group per thread
+  auto fetch = [&](int item, int sl, unsigned char* win) {
+    const RoiItemGeo g = geo[sl];
+    if (g.staged) {
+      const int chunk = item % nchunk, npix = g.rows * g.cols, cols = g.cols;
+      const size_t f0 = (size_t)g.b * Hf * Wf * C4 + (size_t)chunk * kCq;
+      const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(win);
+      const int first = warp * kPix + sub;
+      int y = first / cols, x = first - y * cols;
+      for (int pix = first; pix < npix; pix += kWarps * kPix) {
+        const size_t g4 = f0 + ((size_t)(g.y_lo + y) * Wf + (g.x_lo + x)) * C4;
+        const uint32_t dst = win_s + (uint32_t)pix * (uint32_t)kPixBytes + (uint32_t)piece * 16u;
+        if (feat_plane == 0) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(reinterpret_cast<const float4*>(feat) + g4 + piece) : "memory");
+        } else {
+          const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(feat) + (piece < kCq / 2 ? 0 : feat_plane) + g4 * 4 +
+                                     (size_t)(piece % (kCq / 2)) * 8;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+        x += kWarps * kPix;
+        while (x >= cols) { x -= cols; ++y; }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // ---- prologue: first item of this CTA
+  int item = blockIdx.x;
+  if (item >= total) return;
+  int sl = 0, buf = 0;
+  if (warp == 0) geometry(item, sl);
+  __syncthreads();
+  fetch(item, sl, win_all);
+  if (warp == 0) tables(sl);
+
+  for (; item < total; item += gridDim.x) {
+    const int next = item + gridDim.x;
+    const bool has_next = next < total;                               // CTA-uniform
+    const int sl_n = (sl + 1) % 3;
+    if (has_next) {
+      if (warp == 0) geometry(next, sl_n);
+      __syncthreads();                                                // (A) geometry(next) visible; every warp has left bins(item - stride)
+      fetch(next, sl_n, win_all + (size_t)(buf ^ 1) * win_bytes);
+      if (warp == 0) tables(sl_n);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");            // this item's group has landed (the newest one may be in flight)
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+
+    const RoiItemGeo g = geo[sl];
+    unsigned char* win = win_all + (size_t)buf * win_bytes;
+    const int npix = g.rows * g.cols, cols = g.cols;
+    if (g.staged && feat_plane != 0) {                                // merge the warp's own pixels: hi + lo -> fp32 in place
+      for (int p0 = warp * kPix; p0 < npix; p0 += kWarps * kPix) {
+        const int pix = p0 + sub;
+        unsigned char* base = win + (size_t)pix * kPixBytes;
+        uint2 h = make_uint2(0u, 0u), l = h;
+        if (pix < npix) {
+          h = *reinterpret_cast<const uint2*>(base + piece * 8);
+          l = *reinterpret_cast<const uint2*>(base + CH * 2 + piece * 8);
+        }
+        __syncwarp();
+        if (pix < npix) *reinterpret_cast<float4*>(base + piece * 16) = merge4(h, l);
+      }
+    }
+    __syncthreads();                                                  // (B) window complete, tables of this item visible
+
+    const int k = item / nchunk, chunk = item - k * nchunk;
+    const int ph = warp % P, part = (kPix == 2) ? sub : warp / P;
+    const int pw0 = part ? 4 : 0, pw1 = part ? P : 4;
+    const float count = (float)max(g.gh * g.gw, 1);
+    const size_t o_base = ((size_t)k * P * P + (size_t)ph * P) * C4 + (size_t)chunk * kCq + piece;
+    if (g.staged && geo[sl].ok) {
+      const int y0 = t_start[sl][1][ph], ny = t_cnt[sl][1][ph];
+      const float* wy = wtab[sl][1][ph];
+      const float4* win4 = reinterpret_cast<const float4*>(win) + piece;
+      for (int pw = pw0; pw < pw1; ++pw) {
+        const int x0 = t_start[sl][0][pw], nx = t_cnt[sl][0][pw];
+        const float* wx = wtab[sl][0][pw];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < ny; ++j) {
+          const float4* rowp = win4 + (size_t)((y0 + j) * cols + x0) * kCq;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+          for (int i = 0; i < nx; ++i) {
+            const float w = wx[i];
+            const float4 v = rowp[i * kCq];
+            t.x = fmaf(w, v.x, t.x); t.y = fmaf(w, v.y, t.y); t.z = fmaf(w, v.z, t.z); t.w = fmaf(w, v.w, t.w);
+          }
+          const float wj = wy[j];
+          acc.x = fmaf(wj, t.x, acc.x); acc.y = fmaf(wj, t.y, acc.y); acc.z = fmaf(wj, t.z, acc.z); acc.w = fmaf(wj, t.w, acc.w);
+        }
+        acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);
+        acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
+        st4_fmt(out, out_plane, o_base + (size_t)pw * C4, acc);
+      }
+    } else {
+      const size_t fq = (size_t)g.b * Hf * Wf * C4 + (size_t)chunk * kCq + piece;
+      for (int pw = pw0; pw < pw1; ++pw) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int iy = 0; iy < g.gh; ++iy) {
+          float y = __fadd_rn(__fadd_rn(g.sh, __fmul_rn((float)ph, g.bh)), __fdiv_rn(__fmul_rn((float)iy + 0.5f, g.bh), (float)g.gh));
+          for (int ix = 0; ix < g.gw; ++ix) {
+            float x = __fadd_rn(__fadd_rn(g.sw, __fmul_rn((float)pw, g.bw)), __fdiv_rn(__fmul_rn((float)ix + 0.5f, g.bw), (float)g.gw));
+            if (y < -1.0f || y > (float)Hf || x < -1.0f || x > (float)Wf) continue;
+            float yy = fmaxf(y, 0.f), xx = fmaxf(x, 0.f);
+            int yl = (int)yy, xl = (int)xx, yh, xh;
+            if (yl >= Hf - 1) { yh = yl = Hf - 1; yy = (float)yl; } else { yh = yl + 1; }
+            if (xl >= Wf - 1) { xh = xl = Wf - 1; xx = (float)xl; } else { xh = xl + 1; }
+            const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
+            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+            const float4 a = ld4_fmt(feat, feat_plane, fq + ((size_t)yl * Wf + xl) * C4);
+            const float4 bb = ld4_fmt(feat, feat_plane, fq + ((size_t)yl * Wf + xh) * C4);
+            const float4 cc = ld4_fmt(feat, feat_plane, fq + ((size_t)yh * Wf + xl) * C4);
+            const float4 d = ld4_fmt(feat, feat_plane, fq + ((size_t)yh * Wf + xh) * C4);
+            acc.x += w1 * a.x + w2 * bb.x + w3 * cc.x + w4 * d.x;
+            acc.y += w1 * a.y + w2 * bb.y + w3 * cc.y + w4 * d.y;
+            acc.z += w1 * a.z + w2 * bb.z + w3 * cc.z + w4 * d.z;
+            acc.w += w1 * a.w + w2 * bb.w + w3 * cc.w + w4 * d.w;
+          }
+        }
+        acc.x = __fdiv_rn(acc.x, count); acc.y = __fdiv_rn(acc.y, count);
+        acc.z = __fdiv_rn(acc.z, count); acc.w = __fdiv_rn(acc.w, count);
+        st4_fmt(out, out_plane, o_base + (size_t)pw * C4, acc);
+      }
+    }
+    sl = sl_n;
+    buf ^= 1;
+  }
+}
+
 }  // namespace vbg
 
 using namespace vbg;
@@ -671,6 +904,28 @@ extern "C" int vbg_roi_align_x(const void* feat, long long feat_plane, int B, in
     }
     roi_align_row_kernel<64><<<(unsigned)((long long)K * (C / 64)), 224, win_bytes, s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off,
                                                                                       spatial_scale, out, out_plane, sample_grid, win_bytes);
+    return check_launch("vbg_roi_align_fwd");
+  }
+  if (!direct && (rowk == 3 || rowk == 4) && P == kR2P && C % (rowk == 3 ? 64 : 128) == 0) {
+    // persistent double-buffered form (opt-in, not yet run on a GPU): 3 = 64-channel chunks, two CTAs per SM with 2 x 48 KB
+    // windows each; 4 = 128-channel chunks, one CTA per SM with 2 x 100 KB windows
+    const int win_bytes = rowk == 3 ? 48 * 1024 : 100 * 1024;
+    const int ctas = rowk == 3 ? 2 * kNumSMs : kNumSMs;
+    const long long items = (long long)K * (C / (rowk == 3 ? 64 : 128));
+    const unsigned grid = (unsigned)(items < ctas ? items : ctas);
+    static bool attr4 = false;
+    if (!attr4) {
+      cudaError_t e1 = cudaFuncSetAttribute(roi_align_pipe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 48 * 1024);
+      cudaError_t e2 = cudaFuncSetAttribute(roi_align_pipe_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 100 * 1024);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("vbg_roi_align_fwd: smem opt-in failed"); return VBG_ECUDA; }
+      attr4 = true;
+    }
+    if (rowk == 3)
+      roi_align_pipe_kernel<64><<<grid, 224, 2 * win_bytes, s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off, K, spatial_scale, out, out_plane,
+                                                               sample_grid, win_bytes);
+    else
+      roi_align_pipe_kernel<128><<<grid, 448, 2 * win_bytes, s>>>(feat, feat_plane, B, Hf, Wf, C, boxes, seg_off, K, spatial_scale, out, out_plane,
+                                                                sample_grid, win_bytes);
     return check_launch("vbg_roi_align_fwd");
   }
   if (!direct && C % kRoiCh == 0) {
