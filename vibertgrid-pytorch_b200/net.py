@@ -66,6 +66,14 @@ def _bert_config(name: str) -> dict:
 
 def _load_tokenizer(name, tokenizer):
     if tokenizer is not None:
+        # the reference accepts only an instance of the model family's tokenizer class (model/ViBERTgrid_net.py:235-252)
+        try:
+            from transformers import BertTokenizer, RobertaTokenizer
+            cls = RobertaTokenizer if "roberta-" in name else BertTokenizer
+        except Exception:       # pragma: no cover - transformers missing: nothing to check against
+            return tokenizer
+        if not isinstance(tokenizer, cls):
+            raise ValueError(f"invalid value of parameter tokenizer, must be None or callable {cls.__name__}")
         return tokenizer
     try:
         from transformers import BertTokenizer, RobertaTokenizer
