@@ -54,3 +54,45 @@ def test_state_dict_round_trips_with_the_live_reference(mode, tmp_path, monkeypa
     ref.load_state_dict(sd_ours, strict=True)
     ours.load_state_dict(ref.state_dict(), strict=True)
     assert [n for n, _ in ours.named_parameters()] == [n for n, _ in ref.named_parameters()]
+
+
+BAD_KWARGS = [
+    ("work_mode", {"work_mode": "deploy"}),
+    ("image_mean length", {"image_mean": [0.5, 0.5]}),
+    ("image_std type", {"image_std": "0.1"}),
+    ("image_min_size type", {"image_min_size": 512.0}),
+    ("image_max_size type", {"image_max_size": 800.0}),
+    ("bert name", {"bert_model": "bert-large-uncased"}),
+    ("backbone", {"backbone": "resnet_50_fpn"}),
+    ("grid_mode", {"grid_mode": "max"}),
+    ("classifier_mode", {"classifier_mode": "softmax"}),
+    ("crf without tags", {"classifier_mode": "crf", "tag_to_idx": None}),
+    ("crf tag format", {"classifier_mode": "crf", "tag_to_idx": {"a": 0, "b": 5}}),
+    ("loss_weights type", {"loss_weights": 3}),
+    ("tokenizer class", {"tokenizer": object()}),
+]
+
+
+@pytest.mark.parametrize("what,bad", BAD_KWARGS, ids=[w for w, _ in BAD_KWARGS])
+def test_constructor_rejects_what_the_reference_rejects(what, bad, tmp_path, monkeypatch):
+    """Error behaviour of the constructor: the same invalid arguments raise the same exception class in the
+    reference and in the drop-in."""
+    from vibertgrid_pytorch_b200 import synth
+    from vibertgrid_pytorch_b200.net import ViBERTgridNet as Ours
+    monkeypatch.chdir(tmp_path)
+    cfg = synth.CONFIGS["tiny"]
+    synth.write_bert_dir(cfg, str(tmp_path))
+    monkeypatch.syspath_prepend(REF)
+    for m in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+        monkeypatch.delitem(sys.modules, m)
+    from model.ViBERTgrid_net import ViBERTgridNet as Ref
+    errs = []
+    for cls in (Ref, Ours):
+        kw = {**synth.model_kwargs(cfg, "eval"), **{k: (dict(v) if isinstance(v, dict) else v) for k, v in bad.items()}}
+        try:
+            cls(**kw)
+            errs.append(None)
+        except Exception as e:          # noqa: BLE001 - the exception class is what is compared
+            errs.append(type(e))
+    assert errs[0] is not None, f"the reference accepts {what}: not a rejection case"
+    assert errs[1] is errs[0], f"{what}: reference raises {errs[0].__name__}, drop-in {getattr(errs[1], '__name__', None)}"
