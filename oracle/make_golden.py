@@ -38,6 +38,9 @@ GOLDEN = {
     "tiny_pre": ("tiny_pre", "simp", 4, 4),
     "tiny_win": ("tiny_win", "simp", 5, 5),
     "cfg1": ("cfg1", "simp", 0, 0),
+    "cfg2_b1": ("cfg2_b1", "simp", 1, 11),       # one document of BASELINE configs[1] (r34 + bert-base, 512^2, L=512, S=128)
+    "cfg4_b1": ("cfg4_b1", "simp", 1, 11),       # configs[3]: 768^2, L=1024 (3 windows), 1024 char boxes, pretrained-layout r34
+    "cfg5_b1": ("cfg5_b1", "crf", 1, 11),        # configs[4]: 1024^2, CRF head
     "tiny_rob": ("tiny_rob", "simp", 6, 6),      # bert_model="roberta-base": RobertaModel position ids, LayerNorm eps 1e-5
 }
 
@@ -174,7 +177,8 @@ def run_one(name, cfg_name, mode, wseed, iseed, outdir):
         seg_emb=np.concatenate([e.numpy() for e in seg_emb_ref], 0)[:, ::(8 if big else 2)],
         index_map=ref_idx,
         p_fuse_sub=sub(cap["p_fuse"], *s2)[:, ::4],
-        roi_sub=cap["roi"][:, ::8].contiguous().numpy() if big else cap["roi"][:, ::4].contiguous().numpy(),
+        roi_stride=np.asarray(32 if cap["roi"].shape[0] >= 512 else (8 if big else 4)),
+        roi_sub=cap["roi"][:, ::(32 if cap["roi"].shape[0] >= 512 else (8 if big else 4))].contiguous().numpy(),
         late_sub=cap["late"][:, ::4].contiguous().numpy(),
         pred_label=pred_label.numpy(),
         pred_mask_sub=sub(pred_mask, *((8, 8) if big else (2, 2))),

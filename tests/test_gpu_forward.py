@@ -40,7 +40,7 @@ def _collect(net, out):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
-@pytest.mark.parametrize("name", TINY + ["cfg1"])
+@pytest.mark.parametrize("name", TINY + ["cfg1", "cfg2_b1", "cfg4_b1", "cfg5_b1"])
 def test_forward_matches_reference_fixture(name, precision, tmp_path, monkeypatch):
     from vibertgrid_pytorch_b200 import ops
     if precision != "fp32":

@@ -103,3 +103,40 @@ def test_roberta_position_ids_match_transformers():
     got = roberta_position_ids(ids, pos, 1)
     want = torch.cat([hf(s[None].long(), 1)[0] for s in seqs])
     assert got.dtype == pos.dtype and torch.equal(got.long(), want)
+
+
+@pytest.mark.parametrize("n_toks,L", [([15, 24], 24), ([3, 40, 17], 40), ([515, 30], 515), ([9], 30)])
+def test_roberta_position_ids_ragged_packed_layout(n_toks, L):
+    """The packed layout of a ragged batch (sample 0 shorter than the batch maximum; RoBERTa's <pad> id inside a
+    later sample): ids / pos / cu exactly as ``bert_assemble_kernel`` writes them from ``plan_batch``'s window table -- the
+    [SEP] row carries its slot in the PADDED window -- against transformers' rule applied to the padded windows the reference
+    builds (model/BERTgrid_generator.py:106-129), read back at the rows the packed layout keeps."""
+    import numpy as np
+    import torch
+    from vibertgrid_pytorch_b200.plan import plan_batch, roberta_position_ids
+    try:
+        from transformers.models.roberta.modeling_roberta import RobertaEmbeddings
+        hf = RobertaEmbeddings.create_position_ids_from_input_ids
+    except Exception:                       # pragma: no cover
+        pytest.skip("transformers without RobertaEmbeddings.create_position_ids_from_input_ids")
+    from oracle import oracle_ops
+    B = len(n_toks)
+    g = torch.Generator().manual_seed(7)
+    corpus = torch.zeros(B, L, dtype=torch.int64)
+    for b, n in enumerate(n_toks):
+        corpus[b, :n] = torch.randint(1000, 2000, (n,), generator=g)
+    corpus[B - 1, min(2, n_toks[-1] - 1)] = 1                     # <pad> id inside the LAST sample's text
+    plan = plan_batch([(64, 64)] * B, n_toks, [1] * B, L, 64, 64)
+    seq_tab, cu = plan.view("seq_tab").reshape(-1, 4), plan.view("cu")
+    ids, pos, want = [], [], []
+    windows = oracle_ops.bert_windows(corpus.numpy(), (corpus != 0).int().numpy())
+    for (b, col0, n, sep) in seq_tab:
+        ids += [101] + corpus[b, col0:col0 + n].tolist() + [102]
+        pos += list(range(n + 1)) + [int(sep)]
+        wid = windows[col0 // 510][0]                               # [B, 512] padded window ids
+        full = hf(torch.from_numpy(wid[b:b + 1]).long(), 1)[0]
+        want += full[:n + 1].tolist() + [int(full[sep])]
+    got = roberta_position_ids(torch.tensor(ids, dtype=torch.int32), torch.tensor(pos, dtype=torch.int32), 1,
+                               torch.from_numpy(np.ascontiguousarray(cu)))
+    assert got.tolist() == want
+    assert min(got.tolist()) >= 1

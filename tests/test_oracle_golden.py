@@ -28,7 +28,8 @@ def check_against_golden(o, fx, tol, big):
     errs["seg_emb"] = relerr(np.concatenate([np.asarray(e) for e in o["seg_emb"]], 0)[:, ::(8 if big else 2)], fx["seg_emb"])
     p = (4, 4) if big else (2, 2)
     errs["p_fuse"] = relerr(_sub(o["p_fuse"], *p)[:, ::4], fx["p_fuse_sub"])
-    errs["roi"] = relerr(torch.as_tensor(o["roi"])[:, ::(8 if big else 4)].numpy(), fx["roi_sub"])
+    rs = int(fx["roi_stride"]) if "roi_stride" in fx else (8 if big else 4)
+    errs["roi"] = relerr(torch.as_tensor(o["roi"])[:, ::rs].numpy(), fx["roi_sub"])
     errs["late"] = relerr(torch.as_tensor(o["late"])[:, ::4].numpy(), fx["late_sub"])
     if "logits" in fx:
         errs["logits"] = relerr(o["logits"], fx["logits"])
@@ -52,7 +53,7 @@ def check_against_golden(o, fx, tol, big):
     return errs
 
 
-@pytest.mark.parametrize("name", TINY + ["cfg1"])
+@pytest.mark.parametrize("name", TINY + ["cfg1", "cfg2_b1", "cfg4_b1", "cfg5_b1"])
 def test_oracle_matches_reference_fixture(name, bert_dir, tmp_path, monkeypatch):
     fx = load_golden(name)
     monkeypatch.chdir(tmp_path)

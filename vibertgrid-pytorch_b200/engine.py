@@ -272,7 +272,7 @@ class ForwardEngine:
         seq_tab, cu = dev_tab["seq_tab"], dev_tab["cu"]
         ids, pos = ops.bert_assemble(corpus, seq_tab, cu, plan.nseq, plan.R)
         if bm.cfg.get("roberta"):
-            pos = roberta_position_ids(ids, pos, int(bm.cfg["pad_token_id"]))
+            pos = roberta_position_ids(ids, pos, int(bm.cfg["pad_token_id"]), cu)
         prec = self._prec()
         ps = self._ps()
         x = ops.embed_ln(ids, pos, e.word_embeddings.weight.detach(), e.position_embeddings.weight.detach(),

@@ -115,14 +115,26 @@ def plan_batch(image_shapes: Sequence[Tuple[int, int]], n_toks: Sequence[int], n
     return BatchPlan(B, H, W, sizes, K, n_tok, L, nseq, R, max_len, [int(s) for s in n_segs], table, offsets)
 
 
-def roberta_position_ids(ids, pos, padding_idx):
+def roberta_position_ids(ids, pos, padding_idx, cu=None):
     """HF ``create_position_ids_from_input_ids`` (RobertaEmbeddings) over the packed rows: inside each sequence a non-pad id
-    gets ``padding_idx + (number of non-pad ids up to and including it)``, a pad id gets ``padding_idx``.  ``pos`` is the
-    row's 0-based index inside its sequence (what BertModel uses directly), so ``row - pos`` is the sequence's first row.
+    gets ``padding_idx + (number of non-pad ids up to and including it)``, a pad id gets ``padding_idx``.
+
+    ``cu`` [nseq + 1] is the packed-row offset table (``cu_seqlens``): a row's sequence start is looked up there, never
+    derived from ``pos`` -- ``pos`` of the [SEP] row is its slot in the PADDED window (``len_w + 1``, after the dataset's
+    0-padding, model/BERTgrid_generator.py:106-129), not its packed index.  The dataset's 0 pads between the last real token
+    and [SEP] are not ``padding_idx`` (RoBERTa's <pad> is 1), so HF counts them: the [SEP] row adds ``pos - packed_index``.
+    Without ``cu`` (unit tests over plain back-to-back sequences) ``pos`` must be the packed index itself.
     Integer torch ops on the [R] id vector (capturable in a CUDA graph); the result feeds the same embedding kernel."""
     import torch
+    R = ids.numel()
+    rows = torch.arange(R, device=ids.device, dtype=torch.int64)
     nz = (ids != padding_idx).to(torch.int32)
     c = torch.cumsum(nz, 0, dtype=torch.int32)
-    first = (torch.arange(ids.numel(), device=ids.device, dtype=torch.int64) - pos.long())
+    if cu is None:
+        first = rows - pos.long()
+    else:
+        seq = torch.searchsorted(cu.long().contiguous(), rows, right=True) - 1
+        first = cu.long()[seq]
     before = c[first] - nz[first]
-    return ((c - before) * nz + padding_idx).to(pos.dtype).contiguous()
+    skipped = (pos.long() - (rows - first)).to(torch.int32)        # dataset pads the packed layout dropped before this row
+    return ((c - before + skipped) * nz + padding_idx).to(pos.dtype).contiguous()

@@ -51,6 +51,11 @@ CONFIGS = {
     "cfg4": DocConfig("cfg4", 4, 768, 768, 1024, 1024, 12, "resnet_34_fpn_pretrained", vocab_size=21128),
     "cfg5": DocConfig("cfg5", 2, 1024, 1024, 512, 64, 4, "resnet_34_fpn", classifier_mode="crf",
                       tag_to_idx={"O": 0, "B-q": 1, "B-a": 2, "B-h": 3}),
+    # one document of the headline shapes: live-reference fixtures at the sizes the numbers are quoted on
+    "cfg2_b1": DocConfig("cfg2_b1", 1, 512, 512, 512, 128, 5, "resnet_34_fpn"),
+    "cfg4_b1": DocConfig("cfg4_b1", 1, 768, 768, 1024, 1024, 12, "resnet_34_fpn_pretrained", vocab_size=21128),
+    "cfg5_b1": DocConfig("cfg5_b1", 1, 1024, 1024, 512, 64, 4, "resnet_34_fpn", classifier_mode="crf",
+                         tag_to_idx={"O": 0, "B-q": 1, "B-a": 2, "B-h": 3}),
     # small shapes for the CPU suite / golden fixtures
     "tiny": DocConfig("tiny", 2, 96, 128, 40, 9, 5, "resnet_18_fpn", vocab_size=2000, bert_layers=2, ragged=True),
     "mid": DocConfig("mid", 4, 160, 192, 64, 12, 5, "resnet_18_fpn", vocab_size=2000, bert_layers=2, ragged=True),

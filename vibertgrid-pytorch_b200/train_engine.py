@@ -109,7 +109,7 @@ class TrainEngine:
         cu = dt["cu"]
         ids, pos = ops.bert_assemble(corpus, dt["seq_tab"], cu, plan.nseq, plan.R)
         if cfg.get("roberta"):
-            pos = roberta_position_ids(ids, pos, int(cfg["pad_token_id"]))
+            pos = roberta_position_ids(ids, pos, int(cfg["pad_token_id"]), cu)
         x = A.EmbedSumF.apply(e.word_embeddings.weight, e.position_embeddings.weight, e.token_type_embeddings.weight, ids, pos)
         x = A.LayerNormPS.apply(x, e.LayerNorm.weight, e.LayerNorm.bias, e.LayerNorm.eps)
 
