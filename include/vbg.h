@@ -125,6 +125,12 @@ VBG_API int vbg_attention_fwd(const float* qkv, const int32_t* cu, int nseq, int
 VBG_API int vbg_attention_split_fwd(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len,
                             int heads, int head_dim, void* out, long long out_plane, vbg_stream_t stream);
 
+/* Input-contract check of forward()'s `mask` argument.  The reference selects the real token rows with it
+ * (model/BERTgrid_generator.py:152-158) and asserts their count against seg_indices (:233); the packed layout assumes the
+ * prefix mask its collate produces (data/SROIE_dataset.py:141-148).  mask i32[B,L]; tok_off i32[B+1] (token offsets from the
+ * SHAPES of seg_indices).  ORs bit 2 into *status when mask[b] is not exactly tok_off[b+1]-tok_off[b] leading ones. */
+VBG_API int vbg_mask_check(const int32_t* mask, int B, int L, const int32_t* tok_off, int32_t* status, vbg_stream_t stream);
+
 /* ---- a3: token -> segment aggregation (model/BERTgrid_generator.py:148-189) ----------------- */
 /* Run starts of consecutive-equal ids inside each sample.  status[0] |= 1 if #runs != K.        */
 VBG_API int vbg_segment_starts(const int32_t* seg_ids, const int32_t* tok_off, int B, int n_tok, int K,

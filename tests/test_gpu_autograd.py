@@ -139,3 +139,25 @@ def test_conv2d_s1_ps_weight_grad():
     dxr, dwr = torch.autograd.grad(yr, (xr, wr), dy.double().permute(0, 3, 1, 2))
     assert (dx.double() - dxr.permute(0, 2, 3, 1)).abs().max().item() / dxr.abs().max().item() < 2e-5
     assert (dw.double() - dwr.permute(0, 2, 3, 1)).abs().max().item() / dwr.abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(3000, 26, 256), (257, 23, 1024), (129, 25, 1024), (500, 5, 512), (64, 100, 64)])
+def test_linear_small_any_width(M, N, K):
+    """Output widths the tensor-core kernels do not take and that exceed the 16-column tile of ``vbg_small_wgrad``:
+    the reference's 23-tag EPHOIE BIO set gives a packed segmentation head of 3 + 23 = 26 columns, a 23-way simp head and 25
+    CRF emissions (model/field_type_classification_head.py:635-637).  Forward, dX, dW, db against float64 autograd."""
+    from vibertgrid_pytorch_b200.autograd import LinearSmall, linear
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g); w = torch.randn(N, K, generator=g) / K ** 0.5; b = torch.randn(N, generator=g)
+    dy = torch.randn(M, N, generator=g)
+    xd, wd, bd = (t.double().requires_grad_(True) for t in (x, w, b))
+    torch.nn.functional.linear(xd, wd, bd).backward(dy.double())
+    xc, wc, bc = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    y = linear(xc, wc, bc)
+    assert y.grad_fn is not None and "LinearSmall" in type(y.grad_fn).__name__
+    y.backward(dy.cuda())
+    torch.cuda.synchronize()
+    assert relerr(y.detach().cpu().numpy(), torch.nn.functional.linear(x.double(), w.double(), b.double()).numpy()) < 2e-5
+    assert relerr(xc.grad.cpu().numpy(), xd.grad.numpy()) < 2e-5
+    assert relerr(wc.grad.cpu().numpy(), wd.grad.numpy()) < 2e-5
+    assert relerr(bc.grad.cpu().numpy(), bd.grad.numpy()) < 2e-5

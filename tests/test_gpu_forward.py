@@ -83,6 +83,49 @@ def test_inference_entry_point_and_mode_quirk(tmp_path, monkeypatch):
     assert isinstance(loss, torch.Tensor) and loss.dim() == 0 and loss.requires_grad
 
 
+def test_mask_argument_is_checked_on_device(tmp_path, monkeypatch):
+    """forward()'s ``mask`` (reference: selects the real rows, model/BERTgrid_generator.py:152-158, asserted against
+    seg_indices :233) must be the prefix mask of the collate; a hole or a wrong count raises status bit 2 without a host
+    sync -- eagerly and through the CUDA-graph replay path -- and a valid mask leaves the status clean."""
+    fx = load_golden("tiny_simp")
+    monkeypatch.chdir(tmp_path)
+    cfg, kw, net, batch = build_case(fx["meta"])
+    net = net.cuda().eval()
+    img, seg, cls, coors, corpus, mask = _to_dev(batch)
+    hole = mask.clone(); hole[0, 1] = 0
+    extra = mask.clone(); extra[1, -1] = 1
+    for call in range(3):                            # eager, capture, replay
+        net(img, seg, cls, coors, corpus, mask)
+        assert int(net.last_intermediates["status"].item()) == 0
+        net(img, seg, cls, coors, corpus, hole)
+        assert int(net.last_intermediates["status"].item()) & 2
+        net(img, seg, cls, coors, corpus, extra)
+        assert int(net.last_intermediates["status"].item()) & 2
+    assert net._get_engine().graph_replays >= 3
+
+
+def test_crf_inference_decodes_the_batch_as_one_sequence(tmp_path, monkeypatch):
+    """``CRFFieldTypeClassification.inference`` (model/field_type_classification_head.py:655-668) runs Viterbi over
+    all K rows of the batch as ONE sequence, unlike forward() (per document, :703-713).  ``net.inference`` replicates that:
+    its tags equal the oracle's Viterbi over the concatenated emissions."""
+    from oracle import oracle_ops
+    fx = load_golden("tiny_crf")
+    monkeypatch.chdir(tmp_path)
+    cfg, kw, net, batch = build_case(fx["meta"])
+    net = net.cuda().eval()
+    img, seg, cls, coors, corpus, mask = _to_dev(batch)
+    net(img, seg, cls, coors, corpus, mask)
+    logits = net.last_intermediates["logits"].cpu().numpy()
+    per_doc = net.last_intermediates["pred_label"].cpu().numpy()
+    assert np.array_equal(per_doc, fx["pred_label"])
+    trans = net.field_type_classification_head.crf_layer.transitions.detach().cpu().numpy()
+    T = trans.shape[0]
+    _, path = oracle_ops.crf_viterbi(logits, trans, T - 2, T - 1)
+    for _ in range(3):                               # eager, capture, replay
+        got = net.inference(img, seg, coors, corpus, mask).cpu().numpy()
+        assert got.shape == (logits.shape[0], 1) and np.array_equal(got[:, 0], np.asarray(path, np.float32))
+
+
 def test_full_size_properties_cfg2(tmp_path, monkeypatch):
     """BASELINE configs[1] shape (r34, B=8, 512x512, L=512, S=128) -- no oracle run at this size;
     instead: (1) documents are independent => a sample's outputs do not depend on its batch mates

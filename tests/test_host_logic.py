@@ -140,3 +140,27 @@ def test_roberta_position_ids_ragged_packed_layout(n_toks, L):
                                torch.from_numpy(np.ascontiguousarray(cu)))
     assert got.tolist() == want
     assert min(got.tolist()) >= 1
+
+
+def test_missing_pretrained_weights_raise_outside_eval_mode(tmp_path, monkeypatch):
+    """in work_mode 'train' / 'inference' the reference's from_pretrained / resnetXX(pretrained=True) raise when the
+    weights are absent (model/ViBERTgrid_net.py:232-253, model/ResNetFPN_ViBERTgrid.py:521); the drop-in must not silently
+    train from scratch.  A directory with a config but no weights stands in for an offline node."""
+    import dataclasses
+    from vibertgrid_pytorch_b200 import synth
+    from vibertgrid_pytorch_b200.net import ViBERTgridNet
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("HF_HUB_OFFLINE", "1")
+    monkeypatch.setenv("TORCH_HOME", str(tmp_path / "no_hub"))
+    monkeypatch.delenv("VBG_ALLOW_RANDOM_INIT", raising=False)
+    cfg = synth.CONFIGS["tiny"]
+    synth.write_bert_dir(cfg, str(tmp_path))
+    with pytest.raises(Exception):
+        ViBERTgridNet(**synth.model_kwargs(cfg, "train"))
+    pre = dataclasses.replace(synth.CONFIGS["tiny_pre"])
+    synth.write_bert_dir(pre, str(tmp_path))
+    ViBERTgridNet(**synth.model_kwargs(pre, "eval"))                 # eval mode: a checkpoint is loaded right after
+    monkeypatch.setenv("VBG_ALLOW_RANDOM_INIT", "1")
+    with pytest.warns(UserWarning):
+        net = ViBERTgridNet(**synth.model_kwargs(cfg, "train"))
+    assert net.work_mode == "train"

@@ -45,6 +45,7 @@ SIGNATURES = {
     "vbg_layernorm_x": [_p, _p, _p, _f, _i, _i, _p, _ll, _p],
     "vbg_attention_split_fwd": [_p, _ll, _p, _i, _i, _i, _i, _i, _p, _ll, _p],
     "vbg_segment_starts": [_p, _p, _i, _i, _i, _p, _p, _p],
+    "vbg_mask_check": [_p, _i, _i, _p, _p, _p],
     "vbg_segment_reduce": [_p, _p, _p, _i, _i, _i, _p, _p],
     "vbg_box_index_map": [_p, _p, _i, _i, _i, _i, _p, _p],
     "vbg_grid_scatter": [_p, _p, _p, _i, _i, _i, _p, _p],

@@ -121,13 +121,13 @@ def _c(t):
 
 
 class LinearSmall(torch.autograd.Function):
-    """Linear layers the tensor-core kernels do not take (N <= 16 outputs: the 2 / C-way heads, the packed 1x1 segmentation
-    heads): CUDA-core GEMM forward and data gradient, ``vbg_small_wgrad`` weight gradient."""
+    """Linear layers the tensor-core kernels do not take (output width not a multiple of 64: the 2 / C-way heads, the packed
+    1x1 segmentation heads -- 3 + C columns, 26 for the reference's 23-tag EPHOIE BIO set, the 25 CRF emissions): CUDA-core
+    GEMM forward and data gradient; the weight gradient runs ``vbg_small_wgrad`` over column slices of 16 outputs (the
+    kernel's register tile), each slice a strided view of dY."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        if weight.shape[0] > 16:
-            raise ValueError("LinearSmall: at most 16 outputs (wider layers go through LinearPS)")
         x = _c(x.detach())
         y = ops.gemm(x, _c(weight.detach()), ep=ops.make_epilogue(None, None if bias is None else bias.detach()),
                      precision=ops.PREC_FP32)
@@ -143,7 +143,8 @@ class LinearSmall(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = ops.gemm(dy, _c(weight.detach().t()), precision=ops.PREC_FP32)
         if ctx.needs_input_grad[1]:
-            dw = ops.small_wgrad(dy, x)
+            N = dy.shape[1]
+            dw = ops.small_wgrad(dy, x) if N <= 16 else torch.cat([ops.small_wgrad(dy[:, i:i + 16], x) for i in range(0, N, 16)], 0)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = ops.colsum(dy)
         return dx, dw, db

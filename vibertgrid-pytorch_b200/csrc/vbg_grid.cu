@@ -283,6 +283,24 @@ extern "C" int vbg_segment_starts(const int32_t* seg_ids, const int32_t* tok_off
   return check_launch("vbg_segment_starts");
 }
 
+// The attention mask the reference gathers real rows with (model/BERTgrid_generator.py:152-158: emb[b][mask[b] == 1], then
+// the assert that the rows match seg_indices[b]).  The packed layout assumes the mask is the PREFIX of n_tok[b] ones the
+// reference's collate produces (data/SROIE_dataset.py:141-148); anything else raises status bit 2 instead of a syncing assert.
+__global__ void mask_check_kernel(const int32_t* __restrict__ mask, int B, int L, const int32_t* __restrict__ tok_off,
+                                  int32_t* __restrict__ status) {
+  const int b = blockIdx.x;
+  const int n = tok_off[b + 1] - tok_off[b];
+  int bad = 0;
+  for (int i = threadIdx.x; i < L; i += blockDim.x) bad |= ((mask[(size_t)b * L + i] == 1) != (i < n));
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(status, 2);
+}
+
+extern "C" int vbg_mask_check(const int32_t* mask, int B, int L, const int32_t* tok_off, int32_t* status, vbg_stream_t stream) {
+  VBG_REQUIRE(mask && tok_off && status && B > 0 && L > 0, "vbg_mask_check: bad arguments");
+  mask_check_kernel<<<B, 256, 0, as_stream(stream)>>>(mask, B, L, tok_off, status);
+  return check_launch("vbg_mask_check");
+}
+
 extern "C" int vbg_segment_reduce(const float* hidden, const int32_t* tok_row, const int32_t* seg_start, int K, int C,
                                   int mode, float* out, vbg_stream_t stream) {
   VBG_REQUIRE(hidden && tok_row && seg_start && out, "vbg_segment_reduce: null pointer");

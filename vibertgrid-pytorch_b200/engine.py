@@ -380,7 +380,7 @@ class ForwardEngine:
 
     # ------------------------------------------------------------------ whole forward
     @torch.no_grad()
-    def run(self, image, seg_indices, seg_classes, coors, corpus, mask, want_seg=True):
+    def run(self, image, seg_indices, seg_classes, coors, corpus, mask, want_seg=True, crf_one_sequence=False):
         """One joint forward.  A batch signature (all tensor shapes) seen for the second time is captured into a CUDA
         graph; from then on the step is: copy the inputs into the graph's static buffers, one graph launch.
         Tensors in the returned dict are owned by the engine and are overwritten by the next call with the same
@@ -395,7 +395,7 @@ class ForwardEngine:
         shapes = (tuple(tuple(im.shape[-2:]) for im in image), tuple(int(s.shape[0]) for s in seg_indices),
                   tuple(int(c.shape[0]) for c in coors), int(corpus.shape[1]))
         want_seg = bool(want_seg and net.semantic_segmentation_head is not None)
-        key = (shapes, want_seg, self._prec(), self._prep_gen, dev.index, self.fuse_aux_loss)
+        key = (shapes, want_seg, self._prec(), self._prep_gen, dev.index, self.fuse_aux_loss, bool(crf_one_sequence))
         ent = self._graphs.get(key) if self.use_graphs and not standins else None
         if ent is not None and ent.get("graph") is not None:
             st = ent["static"]
@@ -406,6 +406,8 @@ class ForwardEngine:
             if want_seg:
                 _cat_into(st["cls"], [c.reshape(-1) for c in seg_classes])
             st["corpus"].copy_(corpus, non_blocking=True)
+            if st["mask"] is not None:
+                st["mask"].copy_(mask, non_blocking=True)
             ent["graph"].replay()
             self.graph_replays += 1
             self.kernel_launches += ent["launches"]
@@ -420,7 +422,8 @@ class ForwardEngine:
             coors=torch.cat([c.reshape(-1, 4) for c in coors], 0).to(torch.int64).contiguous(),
             seg_ids=torch.cat([s.reshape(-1) for s in seg_indices], 0).to(torch.int32).contiguous(),
             cls=torch.cat([c.reshape(-1) for c in seg_classes], 0).to(torch.int32).contiguous() if want_seg else None,
-            corpus=corpus.contiguous(), tab=tab)
+            corpus=corpus.contiguous(), tab=tab,
+            mask=None if mask is None else mask.to(torch.int32).contiguous())
         if self.use_graphs and not standins:
             if ent is None:                                   # first sighting: run eagerly (also warms up lazy kernel attributes)
                 self._graphs[key] = {"graph": None}
@@ -435,7 +438,7 @@ class ForwardEngine:
                 g = torch.cuda.CUDAGraph()
                 c0 = ops.L.launch_count
                 with torch.cuda.graph(g):
-                    out = self._forward(plan, static, want_seg)
+                    out = self._forward(plan, static, want_seg, crf_one_sequence)
                 out["static"] = True
                 ent.update(graph=g, static=static, out=out, launches=ops.L.launch_count - c0)
                 g.replay()
@@ -443,12 +446,12 @@ class ForwardEngine:
                 self.kernel_launches += ent["launches"]
                 return out
         c0 = ops.L.launch_count if not standins else 0
-        out = self._forward(plan, static, want_seg)
+        out = self._forward(plan, static, want_seg, crf_one_sequence)
         if not standins:
             self.kernel_launches += ops.L.launch_count - c0
         return out
 
-    def _forward(self, plan, st, want_seg):
+    def _forward(self, plan, st, want_seg, crf_one_sequence=False):
         """The kernel sequence of one forward over staged inputs (capturable: no host sync, no host-dependent control flow)."""
         net, pr = self.net, self._prep
         B = plan.B
@@ -478,6 +481,8 @@ class ForwardEngine:
         def bert_branch():
             # a2 / a3 BERT + segment aggregation, a4 BERTgrid
             hidden = self._bert(plan, dt, corpus)
+            if st.get("mask") is not None:                          # input contract of `mask` (prefix of n_tok ones): status bit 2
+                ops.mask_check(st["mask"], dt["tok_off"], status)
             seg_start = ops.segment_starts(seg_ids, dt["tok_off"], B, plan.K, status)
             seg_emb = ops.segment_reduce(hidden, dt["tok_row"], seg_start, plan.K,
                                          ops.AGG_MEAN if net.grid_mode == "mean" else ops.AGG_FIRST)
@@ -553,7 +558,11 @@ class ForwardEngine:
         elif net.classifier_mode == "crf":
             logits = self._mlp_or_lin(late, head.category_classification_net, late_s)
             out["logits"] = logits
-            tags, scores = ops.crf_viterbi(logits, head.crf_layer.transitions.detach().contiguous(), seg_off, B)
+            # forward() decodes per document (field_type_classification_head.py:703-713); the label-free inference() entry
+            # decodes all K rows of the batch as ONE sequence (:655-668) -- replicated, tags at document boundaries differ
+            one = bool(crf_one_sequence)
+            tags, scores = ops.crf_viterbi(logits, head.crf_layer.transitions.detach().contiguous(),
+                                           dt["all_off"] if one else seg_off, 1 if one else B)
             out["pred_label"], out["crf_scores"] = tags[:, None], scores
         else:
             pn = self._mlp_or_lin(late, head.pos_neg_classification_net.layer, late_s)

@@ -147,6 +147,12 @@ class ViBERTgridNet(nn.Module):
         self.backbone_name = backbone
         self.backbone = P.BACKBONES[backbone](self.bert_hidden_size)
         if backbone.endswith("_pretrained") and not self.backbone.try_load_hub_weights():
+            # the reference calls torchvision's resnetXX(pretrained=True) (model/ResNetFPN_ViBERTgrid.py:521,524) and fails when
+            # the weights cannot be fetched; training from a silent random init is never what a drop-in user wants
+            if work_mode in ("train", "inference") and os.environ.get("VBG_ALLOW_RANDOM_INIT") != "1":
+                raise RuntimeError(f"[vibertgrid_b200] torchvision hub weights for {backbone!r} are not cached "
+                                   "($TORCH_HOME/hub/checkpoints) and cannot be downloaded; set VBG_ALLOW_RANDOM_INIT=1 to "
+                                   "train from a random initialisation")
             warnings.warn("[vibertgrid_b200] torchvision hub weights not cached; backbone keeps random init")
         self.p_fuse_channel = 256
 
@@ -219,8 +225,12 @@ class ViBERTgridNet(nn.Module):
             if missing.missing_keys:
                 warnings.warn(f"[vibertgrid_b200] pretrained BERT lacks keys: {missing.missing_keys[:4]}...")
         except Exception as e:
+            # the reference's BertModel.from_pretrained(...) raises here (model/ViBERTgrid_net.py:232-253); so do we, unless the
+            # caller opted into a random initialisation explicitly
+            if os.environ.get("VBG_ALLOW_RANDOM_INIT") != "1":
+                raise
             warnings.warn(f"[vibertgrid_b200] could not load pretrained {name!r} ({type(e).__name__}: {e}); "
-                          "keeping BERT-style random init")
+                          "keeping BERT-style random init (VBG_ALLOW_RANDOM_INIT=1)")
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         # checkpoints from transformers<4.31 carry a persistent position_ids buffer
@@ -247,7 +257,7 @@ class ViBERTgridNet(nn.Module):
         return self._engine
 
     def inference(self, image, seg_indices, coors, corpus, mask):
-        out = self._get_engine().run(image, seg_indices, None, coors, corpus, mask, want_seg=False)
+        out = self._get_engine().run(image, seg_indices, None, coors, corpus, mask, want_seg=False, crf_one_sequence=True)
         return out["pred_label"].clone() if out.get("static") else out["pred_label"]
 
     def forward(self, image, seg_indices, segment_classes, coors, corpus, mask):

@@ -219,6 +219,12 @@ def attention_split(qkv_split, cu, nseq, max_len, heads, split_out=False):
 
 
 # ------------------------------------------------------------------ a3
+def mask_check(mask, tok_off, status):
+    """Raises bit 2 of ``status`` when ``mask`` [B, L] is not the prefix mask the packed layout assumes (no host sync)."""
+    B, Lm = mask.shape
+    L.check(L.load().vbg_mask_check(_i32(mask), B, Lm, _i32(tok_off), _i32(status), _stream()), "vbg_mask_check")
+
+
 def segment_starts(seg_ids, tok_off, B, K, status):
     n_tok = seg_ids.shape[0]
     out = torch.empty(K + 1, dtype=torch.int32, device=seg_ids.device)

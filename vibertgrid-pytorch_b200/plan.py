@@ -101,6 +101,7 @@ def plan_batch(image_shapes: Sequence[Tuple[int, int]], n_toks: Sequence[int], n
     parts = {
         "seg_off": seg_off, "tok_off": tok_off, "ratios": ratios.reshape(-1).view(np.int32),
         "seq_tab": np.asarray(seq_tab, np.int32).reshape(-1), "cu": np.asarray(cu, np.int32), "tok_row": tok_row,
+        "all_off": np.asarray([0, K], np.int32),    # the batch as ONE sequence (CRF head's inference(), see engine.py)
     }
     offsets, chunks, pos = {}, [], 0
     for name, arr in parts.items():

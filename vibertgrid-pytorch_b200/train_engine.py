@@ -213,6 +213,8 @@ class TrainEngine:
 
         # a2 - a4 BERT, segment aggregation, BERTgrid
         hidden = self._bert(plan, dt, corpus.contiguous())
+        if mask is not None and dev.type == "cuda":                 # input contract of `mask` (prefix of n_tok ones): status bit 2
+            ops.mask_check(mask.to(torch.int32).contiguous(), dt["tok_off"], status)
         seg_start = ops.segment_starts(seg_ids, dt["tok_off"], B, plan.K, status)
         seg_emb = A.SegmentReduceF.apply(hidden, dt["tok_row"], seg_start, plan.K,
                                          ops.AGG_MEAN if net.grid_mode == "mean" else ops.AGG_FIRST)
