@@ -110,31 +110,68 @@ def nbytes(batch):
     return sum(sum(t.numel() * t.element_size() for t in x) if isinstance(x, tuple) else x.numel() * x.element_size() for x in batch)
 
 
-def cpu_reference_arm(cfg, steps, warmup, sample_images=1):
-    """The reference's CPU path = the oracle restatement (pinned to the live reference by tests/golden),
-    all host threads, on a bounded sample: `sample_images` documents of the workload per step."""
+def _staged_reference():
+    """The UNMODIFIED reference staged under oracle/_ref/reference (oracle/stage_reference.py), or None."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "reference")
+    return ref if os.path.isfile(os.path.join(ref, "model", "ViBERTgrid_net.py")) else None
+
+
+def cpu_reference_arm(cfg, steps, warmup, sample_images=None):
+    """The reference's own CPU implementation of the path on all host threads: the unmodified ``ViBERTgridNet`` from the
+    staged tree (kind "reference"; eval mode, no_grad, the seeded state dict of the GPU arm loaded with strict=True), or --
+    only when the staged tree is absent -- the oracle restatement (kind "port").  One step = ``sample_images`` documents of
+    the workload (default: the workload's own batch)."""
+    import contextlib
     import dataclasses
     from vibertgrid_pytorch_b200 import synth
-    from oracle import oracle_net
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    c1 = dataclasses.replace(cfg, batch=sample_images)
+    n_img = sample_images or cfg.batch
+    c1 = dataclasses.replace(cfg, batch=n_img)
     net, kw = build_net(c1)
     sd = {k: v for k, v in net.state_dict().items()}
-    ocfg = oracle_net.OracleConfig(backbone=c1.backbone, classifier_mode=c1.classifier_mode, num_classes=c1.num_classes,
-                                   min_size=kw["test_image_min_size"], max_size=kw["image_max_size"])
+    ref_dir = _staged_reference()
+    if ref_dir is not None:
+        kind = "reference"
+        sys.path.insert(0, ref_dir)
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as tmp:
+            os.chdir(tmp)
+            try:
+                synth.write_bert_dir(c1, tmp)
+                with contextlib.redirect_stdout(sys.stderr):
+                    from model.ViBERTgrid_net import ViBERTgridNet as RefNet
+                    assert os.path.abspath(sys.modules[RefNet.__module__].__file__).startswith(ref_dir)
+                    ref = RefNet(**synth.model_kwargs(c1, "eval"))
+            finally:
+                os.chdir(cwd)
+        ref.load_state_dict(sd, strict=True)
+        ref.eval()
+
+        def fwd(batch):
+            with torch.no_grad():
+                return ref(*batch)
+    else:
+        kind = "port"
+        from oracle import oracle_net
+        ocfg = oracle_net.OracleConfig(backbone=c1.backbone, classifier_mode=c1.classifier_mode, num_classes=c1.num_classes,
+                                       min_size=kw["test_image_min_size"], max_size=kw["image_max_size"])
+
+        def fwd(batch):
+            return oracle_net.forward(sd, ocfg, *batch)
     times = []
     for i in range(warmup + steps):
         batch = synth.make_batch(c1, i)
         t0 = time.perf_counter()
-        oracle_net.forward(sd, ocfg, *batch)
+        fwd(batch)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     total = sum(times)
-    return {"value": sample_images * len(times) / total, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{sample_images} image(s)/step of {cfg.name} ({cfg.backbone}, {cfg.height}x{cfg.width}, L={cfg.seq_len}, "
-                      f"S={cfg.segments}), {len(times)} timed forwards, fp32, eval, torch {torch.__version__} CPU",
+    what = "the unmodified reference ViBERTgridNet (oracle/_ref/reference)" if kind == "reference" else "oracle restatement (oracle/oracle_net.py)"
+    return {"value": n_img * len(times) / total, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{n_img} of the {cfg.batch} documents of a {cfg.name} step, {len(times)} timed forwards of {what}, "
+                      f"fp32, eval, no_grad, torch {torch.__version__} CPU, {cores} threads",
             "ms_per_step": 1e3 * total / len(times)}
 
 
@@ -327,6 +364,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement (the `train_step` object)")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="train: the line's value / ms_per_step are the TRAINING step (forward + backward + all-reduce + optimizers)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly ONE JSON line: libraries that write to fd 1 (NCCL prints its version banner there) go to stderr
@@ -341,17 +380,19 @@ def main():
     cfg = synth.CONFIGS[args.config]
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    workload = (f"{cfg.name}: eval-mode joint forward, {cfg.backbone} + bert-base({cfg.bert_layers}L), batch {cfg.batch}/GPU, "
-                f"{cfg.height}x{cfg.width} images, L={cfg.seq_len} tokens, S={cfg.segments} boxes, {cfg.classifier_mode} head")
+    workload = (f"{cfg.name} eval fwd: {cfg.backbone}+bert-base, {cfg.batch} docs/GPU/step, {cfg.height}x{cfg.width}, L={cfg.seq_len}, "
+                f"S={cfg.segments}, {cfg.classifier_mode}")           # < 150 characters: the driver's record truncates longer strings
+    # the SAME config object in both arms (the reference arm times the reference's CPU path on this workload)
+    config = {"workload": workload, "global_batch": cfg.batch * world, "parallelism": f"dp{world}"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = cpu_reference_arm(cfg, max(args.steps, 1), args.warmup)
+        r = cpu_reference_arm(cfg, max(args.steps, 1), args.warmup)          # one step = the workload's own batch
         line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "impl": "reference",
-                "config": {"workload": workload, "arm": "CPU restatement of the reference forward (oracle/), pinned to the live reference by tests/golden"},
+                "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config,
+                "arm": "rank 0 only: the reference's CPU forward on the host cores, one workload batch per step",
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         emit(line)
@@ -414,7 +455,7 @@ def main():
     train = None
     if not args.no_train:
         try:
-            train = train_step_arm(net, cfg, resident, n_rot, world, min(args.steps, 10))
+            train = train_step_arm(net, cfg, resident, n_rot, world, args.steps if args.mode == "train" else min(args.steps, 10))
         except Exception as e:          # the headline (forward) line must survive a failure of the secondary measurement
             train = {"error": f"{type(e).__name__}: {e}"[:300]}
         net.eval()
@@ -426,15 +467,26 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {ops.PREC_TF32: "tf32", ops.PREC_BF16X3: "bf16x3 (hi/lo split, f32 accumulate)", ops.PREC_FP32: "f32"}[prec],
             "data": "synthetic",
-            "config": {"workload": workload, "global_batch": cfg.batch * world, "parallelism": f"dp{world} (documents sharded, no data-path collective)",
-                       "l2": "working set (605 MB weights + activations) >> 126 MB L2; 4 input batches rotated",
-                       "scope_note": "value / e2e: eval-mode joint forward (the reference arm's workload); the training step "
-                                     "(forward + backward + optimizers, configs[1] 'forward+backward') is the train_step object"},
+            "config": dict(config),
+            "notes": {"sharding": "documents sharded over ranks, no data-path collective",
+                      "l2": "working set (605 MB weights + activations) >> 126 MB L2; 4 input batches rotated",
+                      "scope": "value / e2e: eval-mode joint forward (the reference arm's workload); the training step (forward + "
+                               "backward + gradient all-reduce + optimizers, configs[1] 'forward+backward') is the train_step object"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": nbytes(host[0]),
-                    "d2h_bytes_per_step": int(sink["pred"].numel() * 4 + sink["loss"].numel() * sink["loss"].element_size())},
+                    "d2h_bytes_per_step": int(sink["pred"].numel() * 4 + sink["loss"].numel() * sink["loss"].element_size()),
+                    "d2h_contents": "pred_label [K, C] fp32 + loss: what eval_SROIE.py / validate() read; pred_mask / pred_ss stay on the device"},
             "gpu_launches": launches, "cuda_graph_replays": eng.graph_replays, "clocks": clocks}
+    if args.mode == "train":
+        assert train is not None and "ms_per_step" in train, f"--mode train: the training-step arm failed: {train}"
+        line["forward"] = {"value": value, "ms_per_step": ms / args.steps, "e2e": e2e}
+        line.update(metric="train_" + METRIC, value=train["value"], ms_per_step=train["ms_per_step"], gpu_launches=train["gpu_launches"])
+        line["config"]["workload"] = workload.replace("eval fwd", "TRAIN step (fwd+bwd+allreduce+SGD/AdamW)")
     if train is not None:
         line["train_step"] = train
+        if "ms_per_step" in train:      # numeric copies where the driver's record keeps them
+            line["config"]["train_step_ms"] = round(train["ms_per_step"], 3)
+            line["config"]["train_images_per_s"] = round(train["value"], 1)
+            line["e2e"]["train_step_images_per_s"] = round(train["value"], 1)
     if rank == 0:
         fl = fwd_flops_as_executed(cfg)
         line["fwd_tflops_as_executed"] = fl * cfg.batch * args.steps / (ms / 1e3) / 1e12
@@ -445,7 +497,8 @@ def main():
             line["roofline_hbm_kernels"] = {k: kr[k] for k in ("grid_scatter", "roi_align")}
             line["peaks"] = peaks
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = {k: v for k, v in cpu_reference_arm(cfg, 3, 1).items() if k != "ms_per_step"}
+            line["cpu_baseline"] = {k: v for k, v in cpu_reference_arm(cfg, 5, 1, sample_images=min(2, cfg.batch)).items()
+                                    if k != "ms_per_step"}
         emit(line)
     if world > 1:
         dist.barrier()

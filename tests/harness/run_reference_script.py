@@ -12,7 +12,8 @@ Harness-side patches, none of which touches the script files or the hot path:
      ``len(None)`` (eval_SROIE.py:60-76,199): with untrained weights that is every document.  None is mapped to "".
   3. ``seqeval`` / ``matplotlib`` stand-ins on PYTHONPATH (tests/harness/stubs), imported by the reference at module level.
 Instrumentation: the module's training losses, optimizer step counts and a parameter checksum (all-gathered over ranks) are
-printed as one ``VBG_HARNESS {json}`` line per rank.
+printed as one ``VBG_HARNESS {json}`` line per rank; with ``VBG_HARNESS_DUMP=<file.npz>`` every eval-mode forward's loss and
+``pred_label`` are saved there (the numbers behind the strings the script itself writes).
 """
 import argparse
 import gc
@@ -35,7 +36,7 @@ def main():
     script, rest = sys.argv[1], sys.argv[2:]
     re.compile = _compile
     import torch
-    rec = {"losses": [], "sgd_steps": 0, "adamw_steps": 0}
+    rec = {"losses": [], "sgd_steps": 0, "adamw_steps": 0, "preds": []}
 
     import model.ViBERTgrid_net as M
     net_cls = M.ViBERTgridNet
@@ -45,6 +46,8 @@ def main():
         out = orig_forward(self, *a, **k)
         if self.training and isinstance(out, torch.Tensor):
             rec["losses"].append(out.detach().float().reshape(-1)[:1].clone())
+        elif not self.training and isinstance(out, tuple) and os.environ.get("VBG_HARNESS_DUMP"):
+            rec["preds"].append((out[0].detach().float().reshape(-1)[:1].cpu(), out[4].detach().float().cpu()))
         return out
     net_cls.forward = forward
     for opt, key in ((torch.optim.SGD, "sgd_steps"), (torch.optim.AdamW, "adamw_steps")):
@@ -91,6 +94,11 @@ def main():
             torch.distributed.all_gather_object(allc, (chk, info["losses"]))
             info["checksums_all_ranks"] = [c for c, _ in allc]
             info["losses_all_ranks"] = [l for _, l in allc]
+    if os.environ.get("VBG_HARNESS_DUMP") and rec["preds"]:
+        import numpy as np
+        np.savez_compressed(os.environ["VBG_HARNESS_DUMP"], n=len(rec["preds"]),
+                            **{f"loss_{i}": l.numpy() for i, (l, _) in enumerate(rec["preds"])},
+                            **{f"pred_{i}": p.numpy() for i, (_, p) in enumerate(rec["preds"])})
     sys.__stdout__.write("VBG_HARNESS " + json.dumps(info) + "\n")
     sys.__stdout__.flush()
     if torch.distributed.is_available() and torch.distributed.is_initialized():
