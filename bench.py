@@ -201,9 +201,10 @@ def kernel_rooflines(net, cfg, dev, peaks):
     # 512 MiB write between launches: flushes the 126 MB L2 and keeps the GPU busy (~80 us) while the host enqueues the
     # event + launch behind it, so the event pair brackets the kernel alone, not the Python launch latency
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed `ncu --set full` capture of these same launches
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures, KEYED BY KERNEL
+    # NAME: a figure is attached only to the kernel that is actually launched below (profiles/r2_traffic.json)
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.isfile(tp):
         with open(tp) as f:
             traffic = {k: v.get("dram_bytes") for k, v in json.load(f).items() if isinstance(v, dict)}
@@ -230,18 +231,40 @@ def kernel_rooflines(net, cfg, dev, peaks):
     idx = ops.box_index_map(boxes, seg_off, B, 8, Hg, Wg)
     ps = net._get_engine()._ps()        # pre-split mode: the kernels run in the storage formats the engine uses (same bytes)
     emb_src = ops.to_split(emb) if ps else emb
-    ms = timed(lambda: ops.grid_scatter(emb_src, idx, seg_off))
+    grid_out = ops.grid_scatter(emb_src, idx, seg_off)       # result buffers are allocated once: the event pair times the kernel
+    ms = timed(lambda: ops.grid_scatter(emb_src, idx, seg_off, out=grid_out))
     by = B * C * Hg * Wg * 4 + K * C * 4 + K * 16 + B * Hg * Wg * 4
+    sc_name = "grid_scatter_planes_kernel" if ps else "grid_scatter_kernel"
     out["grid_scatter"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                           "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": traffic.get("grid_scatter"), "ms": ms, "bytes": by}
+                           "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": traffic.get(sc_name), "ms": ms, "bytes": by, "kernel": sc_name}
+    # the same kernel back to back over a working set larger than the 126 MB L2 (4 output grids of 100 MB, no flush in
+    # between): the single-launch figure above ends with most of its output still in L2; this one is sustained HBM write-back
+    try:
+        grids = [ops.grid_scatter(emb_src, idx, seg_off) for _ in range(4)]
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            for gbuf in grids:
+                ops.grid_scatter(emb_src, idx, seg_off, out=gbuf)
+        e1.record(); torch.cuda.synchronize()
+        ms_b2b = e0.elapsed_time(e1) / (reps * len(grids))
+        out["grid_scatter"]["back_to_back"] = {"ms": ms_b2b, "achieved": by / ms_b2b / 1e6, "frac": by / ms_b2b / 1e6 / peaks["hbm_gbs"],
+                                               "how": f"{reps * len(grids)} launches rotating 4 output grids ({4 * by / 1e6:.0f} MB > L2), no flush"}
+        del grids
+    except Exception as exc:      # diagnostics only
+        print(f"[bench] back-to-back scatter timing skipped: {exc}", file=sys.stderr)
     Hf, Wf = cfg.height // 4, cfg.width // 4
     feat = torch.randn(B, Hf, Wf, 256, device=dev)
     if ps:
         feat = ops.to_split(feat)
-    ms = timed(lambda: ops.roi_align(feat, boxes, seg_off, 0.25, 7, split_out=ps))
+    roi_out = ops.roi_align(feat, boxes, seg_off, 0.25, 7, split_out=ps)
+    ms = timed(lambda: ops.roi_align(feat, boxes, seg_off, 0.25, 7, split_out=ps, out=roi_out))
     by = B * 256 * Hf * Wf * 4 + K * 256 * 49 * 4 + K * 20
+    roi_name = ops.ROI_KERNEL_NAMES[ops.roi_variant(7, 256)]
     out["roi_align"] = {"bound": "hbm", "achieved": by / ms / 1e6, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": traffic.get("roi_align"), "ms": ms, "bytes": by}
+                        "frac": by / ms / 1e6 / peaks["hbm_gbs"], "traffic": traffic.get(roi_name), "ms": ms, "bytes": by, "kernel": roi_name}
     # dominant tensor-bound kernel: the BERT FFN-up GEMM of the packed batch (M = real rows, N=3072, K=768)
     eng = net._get_engine()
     prec = eng._prec()
@@ -278,7 +301,7 @@ def kernel_rooflines(net, cfg, dev, peaks):
                                                                   + "; peak = measured bf16 peak / 3; frac == tensor-pipe share of bf16 peak"),
                   ops.PREC_FP32: (peaks["fp32_simt_tflops"], "CUDA-core fp32 FFMA")}[prec]
     out["gemm_ffn_up"] = {"bound": "tensor", "achieved": fl / ms / 1e9, "peak": peak, "unit": "TFLOP/s",
-                          "frac": fl / ms / 1e9 / peak, "traffic": traffic.get("gemm_ffn_up"), "ms": ms, "flops": fl, "path": path,
+                          "frac": fl / ms / 1e9 / peak, "traffic": traffic.get("gemm_ps2_kernel<256, 64, 3>") if ps else None, "ms": ms, "flops": fl, "path": path,
                           "executed_tensor_tflops": (3.0 if prec == ops.PREC_BF16X3 else 1.0) * fl / ms / 1e9,
                           "shape": [M, 3072, 768], "timing": "cold L2 (512 MiB flush before every launch)",
                           "warm_l2": None if not ms_warm else {"ms": ms_warm, "achieved": fl / ms_warm / 1e9, "frac": fl / ms_warm / 1e9 / peak,
@@ -495,6 +518,10 @@ def main():
             kr = kernel_rooflines(net, cfg, dev, peaks)
             line["roofline"] = kr["gemm_ffn_up"]
             line["roofline_hbm_kernels"] = {k: kr[k] for k in ("grid_scatter", "roi_align")}
+            # numeric copies inside the object the driver's record keeps
+            line["roofline"]["hbm_scatter_frac"] = round(kr["grid_scatter"]["frac"], 4)
+            line["roofline"]["hbm_scatter_b2b_frac"] = round(kr["grid_scatter"].get("back_to_back", {}).get("frac", 0.0), 4)
+            line["roofline"]["hbm_roi_align_frac"] = round(kr["roi_align"]["frac"], 4)
             line["peaks"] = peaks
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_arm(cfg, 5, 1, sample_images=min(2, cfg.batch)).items()

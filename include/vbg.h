@@ -331,6 +331,14 @@ VBG_API int vbg_roi_align_x(const void* feat, long long feat_plane, int B, int H
                     const int32_t* seg_off, int K, float spatial_scale, int P, void* out, long long out_plane,
                     int32_t* sample_grid, vbg_stream_t stream);
 
+/* The same operation with the kernel chosen by the CALLER (an argument, not process state): AUTO picks by shape -- the
+ * persistent TMA row-streaming kernel for P == 7, C in {128, 256}; tests and scripts pass ROW / DIRECT to compare the kernels
+ * on identical inputs.  All variants produce the same bit-exact sample grid; values agree to fp32 re-association. */
+enum { VBG_ROI_AUTO = 0, VBG_ROI_STREAM = 1, VBG_ROI_ROW = 2, VBG_ROI_DIRECT = 3 };
+VBG_API int vbg_roi_align_sel(const void* feat, long long feat_plane, int B, int Hf, int Wf, int C, const int32_t* boxes,
+                      const int32_t* seg_off, int K, float spatial_scale, int P, void* out, long long out_plane,
+                      int32_t* sample_grid, int variant, vbg_stream_t stream);
+
 /* ---- heads / outputs ---------------------------------------------------------------------- */
 VBG_API int vbg_softmax_rows(const float* x, int R, int C, float* y, vbg_stream_t stream);
 /* sigmoid cascade of the "full" head (field_type_classification_head.py:312-332) */

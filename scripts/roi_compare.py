@@ -1,6 +1,7 @@
-"""ROI-align kernels side by side at a BASELINE shape: the 64-channel windowed kernel (default) against the row-per-warp kernel
-(VBG_ROI_ROW=1 / 2) and its persistent double-buffered forms (3 / 4): bit-equality of the outputs in both storage formats, then CUDA-event timings with an L2 flush between launches
-(the same recipe as bench.py's roofline_hbm_kernels)."""
+"""ROI-align kernels side by side at a BASELINE shape: the persistent TMA row-streaming kernel (the product path) against the
+row-per-warp kernel (round-1 default) and the direct per-sample kernel -- sample grids bit-equal, values within fp32
+re-association -- then CUDA-event timings with an L2 flush between launches (the same recipe as bench.py's
+roofline_hbm_kernels).  `python scripts/roi_compare.py cfg2 [ncu]` (with `ncu`: one launch per variant, for a profiler)."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,6 +9,7 @@ sys.path.insert(0, ROOT)
 from vibertgrid_pytorch_b200 import ops, synth
 
 cfg = synth.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "cfg2"]
+ncu = len(sys.argv) > 2 and sys.argv[2] == "ncu"
 dev = torch.device("cuda")
 B, S = cfg.batch, cfg.segments
 K = B * S
@@ -19,40 +21,39 @@ feat32 = torch.randn(B, Hf, Wf, 256, device=dev)
 feat_s = ops.to_split(feat32)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 by = B * 256 * Hf * Wf * 4 + K * 256 * 49 * 4 + K * 20
+NAMES = {ops.ROI_STREAM: "stream (TMA rows)", ops.ROI_ROW: "row-per-warp 128 ", ops.ROI_DIRECT: "direct per-sample"}
 
 
-NAMES = {0: "windowed-64     ", 1: "row-per-warp 128", 2: "row-per-warp 64 ", 3: "persistent 64   ", 4: "persistent 128  "}
+def run(variant, split):
+    return ops.roi_align(feat_s if split else feat32, boxes, seg_off, 0.25, 7, want_grid=True, split_out=split, variant=variant)
 
 
-def run(row, split):
-    os.environ["VBG_ROI_ROW"] = str(int(row))
-    f = feat_s if split else feat32
-    return ops.roi_align(f, boxes, seg_off, 0.25, 7, want_grid=True, split_out=split)
-
-
-def timed(row, split, reps=10):
-    run(row, split)
+def timed(variant, split, reps=10):
+    run(variant, split)
     torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); run(row, split); e1.record()
+        e0.record(); run(variant, split); e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     return sum(ts) / len(ts), min(ts)
 
 
 for split in (True, False):
-    a, ga = run(0, split)
-    ta = a.t if split else a
-    for v in (1, 2, 3, 4):
+    a, ga = run(ops.ROI_ROW, split)
+    ta = (a.float() if split else a)
+    for v in (ops.ROI_STREAM, ops.ROI_DIRECT):
         b, gb = run(v, split)
-        tb = b.t if split else b
-        same = torch.equal(ta, tb) and torch.equal(ga, gb)
-        md = float((ta.float() - tb.float()).abs().max())
-        print(f"[{cfg.name} planes={split}] {NAMES[v]} == windowed-64: {same} (max |diff| {md:.3e}), finite: {bool(torch.isfinite(tb.float()).all())}")
-    for row in (0, 1, 2, 3, 4):
-        ms, best = timed(row, split)
-        print(f"[{cfg.name} planes={split}] {NAMES[row]} {ms * 1e3:7.1f} us avg, {best * 1e3:7.1f} us best"
-              f" -> {by / ms / 1e6:7.0f} GB/s = {by / ms / 1e6 / 6548.8:.3f} of measured HBM peak")
+        tb = (b.float() if split else b)
+        torch.cuda.synchronize()
+        md = float((ta - tb).abs().max() / ta.abs().max())
+        print(f"[{cfg.name} planes={split}] {NAMES[v]} vs row kernel: grid equal {torch.equal(ga, gb)}, max-rel diff {md:.2e}, "
+              f"finite {bool(torch.isfinite(tb).all())}", flush=True)
+    if ncu:
+        continue
+    for v in (ops.ROI_STREAM, ops.ROI_ROW, ops.ROI_DIRECT):
+        ms, best = timed(v, split)
+        print(f"[{cfg.name} planes={split}] {NAMES[v]} {ms * 1e3:7.1f} us avg, {best * 1e3:7.1f} us best"
+              f" -> {by / ms / 1e6:7.0f} GB/s = {by / ms / 1e6 / 6548.8:.3f} of measured HBM peak", flush=True)

@@ -71,6 +71,7 @@ SIGNATURES = {
     "vbg_repack_oihw_to_ohwi": [_p, _i, _i, _i, _i, _p, _p],
     "vbg_roi_align_fwd": [_p, _i, _i, _i, _i, _p, _p, _i, _f, _i, _p, _p, _p],
     "vbg_roi_align_x": [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _f, _i, _p, _ll, _p, _p],
+    "vbg_roi_align_sel": [_p, _ll, _i, _i, _i, _i, _p, _p, _i, _f, _i, _p, _ll, _p, _i, _p],
     "vbg_transpose_split": [_p, _ll, _i, _i, _p, _ll, _i, _p],
     "vbg_colsum_workspace": [_ll, _i],
     "vbg_colsum": [_p, _ll, _ll, _i, _p, _p, _sz, _p],

@@ -249,11 +249,11 @@ def box_index_map(boxes, seg_off, B, stride, Hg, Wg):
     return idx
 
 
-def grid_scatter(seg_emb, idx, seg_off, split=False):
+def grid_scatter(seg_emb, idx, seg_off, split=False, out=None):
     B, Hg, Wg = idx.shape
     Cc = seg_emb.shape[1]
     split = split or isinstance(seg_emb, Split)         # a Split source is copied plane-wise into a Split grid
-    grid = _new_act((B, Hg, Wg, Cc), seg_emb.device, split)
+    grid = out if out is not None else _new_act((B, Hg, Wg, Cc), seg_emb.device, split)
     (sp, splane), (gp, gplane) = _act(seg_emb), _act(grid)
     L.check(L.load().vbg_grid_scatter_x(sp, splane, _i32(idx), _i32(seg_off), B, Hg * Wg, Cc, gp, gplane, _stream()),
             "vbg_grid_scatter")
@@ -422,15 +422,28 @@ def repack_oihw_to_ohwi(w):
 
 
 # ------------------------------------------------------------------ a7
-def roi_align(feat, boxes, seg_off, spatial_scale, P, want_grid=False, split_out=False):
-    """``feat`` fp32 NHWC tensor or Split; ``split_out`` writes the [K,P,P,C] result as a Split."""
+ROI_AUTO, ROI_STREAM, ROI_ROW, ROI_DIRECT = 0, 1, 2, 3
+ROI_KERNEL_NAMES = {ROI_STREAM: "roi_align_stream_kernel", ROI_ROW: "roi_align_row_kernel<128>", ROI_DIRECT: "roi_align_kernel"}
+
+
+def roi_variant(P, C, variant=ROI_AUTO):
+    """The kernel ``vbg_roi_align_sel`` launches for this shape (mirrors its AUTO rule; bench.py keys ncu traffic by it)."""
+    if variant != ROI_AUTO:
+        return variant
+    return ROI_STREAM if (P == 7 and C in (128, 256)) else (ROI_ROW if (P == 7 and C % 128 == 0) else ROI_DIRECT)
+
+
+def roi_align(feat, boxes, seg_off, spatial_scale, P, want_grid=False, split_out=False, variant=ROI_AUTO, out=None):
+    """``feat`` fp32 NHWC tensor or Split; ``split_out`` writes the [K,P,P,C] result as a Split.  ``variant`` selects the
+    kernel explicitly (tests / scripts); the default picks by shape.  ``out``: a caller-owned result buffer to reuse."""
     B, Hf, Wf, Cc = feat.shape
     K = boxes.shape[0]
-    out = _new_act((K, P, P, Cc), feat.device, split_out)
+    if out is None:
+        out = _new_act((K, P, P, Cc), feat.device, split_out)
     sg = torch.empty((K, 2), dtype=torch.int32, device=feat.device) if want_grid else None
     (fp, fpl), (op, opl) = _act(feat), _act(out)
-    L.check(L.load().vbg_roi_align_x(fp, fpl, B, Hf, Wf, Cc, _i32(boxes), _i32(seg_off), K, spatial_scale, P,
-                                     op, opl, _i32(sg), _stream()), "vbg_roi_align_fwd")
+    L.check(L.load().vbg_roi_align_sel(fp, fpl, B, Hf, Wf, Cc, _i32(boxes), _i32(seg_off), K, spatial_scale, P,
+                                       op, opl, _i32(sg), int(variant), _stream()), "vbg_roi_align_fwd")
     return (out, sg) if want_grid else out
 
 
