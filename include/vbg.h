@@ -321,6 +321,24 @@ VBG_API int vbg_stem_wgrad(const float* x4, const float* dy, int B, int Hp, int 
 VBG_API int vbg_attention_bwd(const float* qkv, const float* out, const float* d_out, const int32_t* cu, int nseq, int max_len, int heads,
                       int head_dim, long long rows, float* dqkv, float* workspace, size_t ws_bytes, vbg_stream_t stream);
 
+/* ---- training-mode attention on the tensor cores (HF BertSelfAttention under model.train(), model/BERTgrid_generator.py:134)
+ * forward: vbg_attention_split_fwd that ALSO (1) applies dropout to the attention probabilities (attention_probs_dropout_prob)
+ *   with a counter-based mask -- a pure function of (seed, packed query row, key index, head) -- and (2) stores the base-2 row
+ *   log-sum-exp lse2 [R, heads] the backward rebuilds the probabilities from.
+ * backward: dQKV fp32 [R, 3*hidden] from the bf16 hi/lo planes of QKV and of dO (plus fp32 O, dO for delta = rowsum(dO o O)),
+ *   tcgen05 bf16x3 products, the same dropout mask regenerated; workspace >= R * heads floats (delta).  Deterministic.
+ * vbg_attention_dropout_mask: the keep mask [len, len] of one (sequence starting at packed row row0, head) and the scale
+ *   1 / (1 - p_effective) written to the HOST float *inv_keep -- test infrastructure for an exact reference. */
+VBG_API int vbg_attention_split_train_fwd(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len,
+                                  int heads, int head_dim, void* out, long long out_plane, float* lse2, float p_drop,
+                                  unsigned long long seed, vbg_stream_t stream);
+VBG_API int vbg_attention_bwd_tc(const void* qkv_hi, long long qkv_plane, const void* do_hi, long long do_plane, const float* out,
+                         const float* d_out, const float* lse2, const int32_t* cu, int nseq, int R, int max_len, int heads,
+                         int head_dim, float p_drop, unsigned long long seed, float* dqkv, float* workspace, size_t ws_bytes,
+                         vbg_stream_t stream);
+VBG_API int vbg_attention_dropout_mask(unsigned long long seed, float p_drop, int row0, int len, int head, float* mask,
+                               float* inv_keep, vbg_stream_t stream);
+
 /* ---- a7: GridROIAlign (model/grid_roi_align.py:37-41,81 -> torchvision roi_align, aligned=False,
  *          sampling_ratio=-1) over NHWC features; boxes are the int32 transformed coords.         */
 VBG_API int vbg_roi_align_fwd(const float* feat, int B, int Hf, int Wf, int C, const int32_t* boxes, const int32_t* seg_off,

@@ -12,7 +12,7 @@ for name in sys.argv[1:] or ["train_tiny"]:
     fx = load_golden(name)
     os.chdir(tempfile.mkdtemp())
     cfg, kw, net, batch = build_case(fx["meta"])
-    net = net.cuda(); net.train(); net.bert_hidden_dropout = 0.0
+    net = net.cuda(); net.train(); net.bert_hidden_dropout = net.bert_attn_dropout = 0.0
     try:
         loss = net(*_to_dev(batch))
         print(name, "loss", float(loss), "want", float(fx["loss"][0]), {k: float(v) for k, v in net._train_engine.last.items()})

@@ -34,7 +34,7 @@ def run_step(name, tmp_path, monkeypatch, precision="bf16x3"):
     cfg, kw, net, batch = build_case(fx["meta"])
     net = net.cuda()
     net.train()
-    net.bert_hidden_dropout = 0.0
+    net.bert_hidden_dropout = net.bert_attn_dropout = 0.0
     random.seed(fx["meta"].get("py_random_seed", 0))          # the sampled losses draw from Python's `random` like the reference
     loss = net(*_to_dev(batch))
     loss.backward()

@@ -80,7 +80,7 @@ def test_training_step_with_converted_syncbn(one_rank_group, tmp_path, monkeypat
             assert any(isinstance(m, torch.nn.SyncBatchNorm) for m in net.modules())
         net = net.cuda()
         net.train()
-        net.bert_hidden_dropout = 0.0
+        net.bert_hidden_dropout = net.bert_attn_dropout = 0.0
         monkeypatch.setattr(te, "FORCE_SYNC_BN_SINGLE_RANK", convert)
         random.seed(0)
         img, seg, cls, coors, corpus, mask = batch

@@ -35,7 +35,7 @@ def test_training_step_wiring_with_standins(name, tmp_path, monkeypatch):
     monkeypatch.setattr(te, "A", mock_autograd)
     monkeypatch.setattr(te, "ops", mock_ops)
     net.train()
-    net.bert_hidden_dropout = 0.0
+    net.bert_hidden_dropout = net.bert_attn_dropout = 0.0
     eng = te.TrainEngine(net)
     eng._test_standins = True
     torch.manual_seed(0)

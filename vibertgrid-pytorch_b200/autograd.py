@@ -350,27 +350,43 @@ class DropoutF(torch.autograd.Function):
 
 
 class AttentionF(torch.autograd.Function):
-    """Self-attention over the packed varlen batch: forward on the tcgen05 kernel (vbg_attention_split_fwd), backward
-    vbg_attention_bwd (probabilities recomputed from the row log-sum-exp)."""
+    """Self-attention over the packed varlen batch, both directions on the tcgen05 kernels: forward
+    ``vbg_attention_split_train_fwd`` (dropout on the attention probabilities inside the kernel, row log-sum-exp kept),
+    backward ``vbg_attention_bwd_tc`` (probabilities rebuilt from the log-sum-exp, the same counter-based mask regenerated).
+    ``VBG_PRECISION=fp32`` selects the CUDA-core pair (``vbg_attention_fwd`` / ``vbg_attention_bwd``), which has no
+    attention dropout: that mode exists to prove the wiring against the reference's gradients with dropout off."""
 
     @staticmethod
-    def forward(ctx, qkv, cu, nseq, max_len, heads):
+    def forward(ctx, qkv, cu, nseq, max_len, heads, p_drop=0.0, seed=0):
         qkv = _c(qkv.detach())
         hid = qkv.shape[1] // 3
         if hid // heads != 64:
             raise NotImplementedError("training attention: head dimension 64 only")
-        if max_len <= 512 and ops.tc_available() and not _fp32():
-            out = ops.attention_split(ops.to_split(qkv), cu, nseq, max_len, heads, split_out=False)
-        else:
-            out = ops.attention(qkv, cu, nseq, max_len, heads, ops.PREC_FP32)
-        ctx.save_for_backward(qkv, out, cu)
+        ctx.tc = max_len <= 512 and ops.tc_available() and not _fp32()
         ctx.cfg = (nseq, max_len, heads)
+        if ctx.tc:
+            qs = ops.to_split(qkv)
+            out, lse2 = ops.attention_split_train(qs, cu, nseq, max_len, heads, p_drop, seed)
+            ctx.save_for_backward(qs.t, out, lse2, cu)
+            ctx.drop = (float(p_drop), int(seed))
+        else:
+            if p_drop > 0.0 and not getattr(AttentionF, "_warned", False):
+                AttentionF._warned = True
+                import warnings
+                warnings.warn("[vibertgrid_b200] the fp32 CUDA-core attention path applies no attention-probability dropout")
+            out = ops.attention(qkv, cu, nseq, max_len, heads, ops.PREC_FP32)
+            ctx.save_for_backward(qkv, out, cu)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
-        qkv, out, cu = ctx.saved_tensors
-        return ops.attention_bwd(qkv, out, _c(d_out), cu, *ctx.cfg), None, None, None, None
+        if ctx.tc:
+            qs, out, lse2, cu = ctx.saved_tensors
+            dqkv = ops.attention_bwd_tc(ops.Split(qs), out, _c(d_out), lse2, cu, *ctx.cfg, *ctx.drop)
+        else:
+            qkv, out, cu = ctx.saved_tensors
+            dqkv = ops.attention_bwd(qkv, out, _c(d_out), cu, *ctx.cfg)
+        return dqkv, None, None, None, None, None, None
 
 
 class EmbedSumF(torch.autograd.Function):

@@ -251,11 +251,18 @@ attention_tc_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ c
 constexpr int kAt2Threads = 320;
 constexpr uint32_t kVTile = 64 * 128;        // 64 keys x 64 dims (bf16)
 
+// Training mode (HF BertSelfAttention under model.train(): dropout on the attention probabilities,
+// attention_probs_dropout_prob, reached through model/BERTgrid_generator.py:134): the kernel optionally
+//   * drops probabilities with a counter-based mask -- a pure function of (seed, packed query row, key index, head), so the
+//     backward kernels (vbg_attn_bwd_tc.cu) regenerate it; kept entries are scaled by 1 / (1 - p).  The row sum (softmax
+//     normalisation) is taken over the UN-dropped probabilities, as softmax -> dropout does;
+//   * stores the base-2 row log-sum-exp  lse2[row, head] = max * scale * log2(e) + log2(sum)  the backward rebuilds P from.
 __global__ void __launch_bounds__(kAt2Threads, 1)
 attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_constant__ CUtensorMap tmQKl,
                        const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
                        const int32_t* __restrict__ cu, int heads, float scale_log2e, void* __restrict__ out,
-                       long long out_plane, long long* __restrict__ dbg) {
+                       long long out_plane, long long* __restrict__ dbg, float* __restrict__ lse2, uint32_t drop_thr,
+                       float drop_inv_keep, uint32_t seed) {
 #define AT_STAMP(slot) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) dbg[slot] = clock64(); } while (0)
   const int seq = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * 128;
   const int row0 = cu[seq], len = cu[seq + 1] - row0;
@@ -412,9 +419,10 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
         if (c0 + 32 <= len) {                     // CTA-uniform fast path: arguments are <= 0, ex2.approx underflows to 0
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float pa = ex2_approx(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled));
-            const float pb = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled));
+            float pa = ex2_approx(fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled));
+            float pb = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled));
             sum += pa + pb;
+            if (drop_thr) attn_drop_pair(seed, (uint32_t)(row0 + q0 + r), (uint32_t)(c0 + 2 * j) >> 1, (uint32_t)head, drop_thr, drop_inv_keep, pa, pb);
             split2(pa, pb, hi[j], lo[j]);
           }
         } else {                                  // chunk holding the sequence end: masked keys get exponent -inf -> p = 0
@@ -422,8 +430,9 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
           for (int j = 0; j < 16; ++j) {
             const float xa = (c0 + 2 * j < len) ? fmaf(__uint_as_float(v[2 * j]), scale_log2e, -m_scaled) : -INFINITY;
             const float xb = (c0 + 2 * j + 1 < len) ? fmaf(__uint_as_float(v[2 * j + 1]), scale_log2e, -m_scaled) : -INFINITY;
-            const float pa = ex2_approx(xa), pb = ex2_approx(xb);
+            float pa = ex2_approx(xa), pb = ex2_approx(xb);
             sum += pa + pb;
+            if (drop_thr) attn_drop_pair(seed, (uint32_t)(row0 + q0 + r), (uint32_t)(c0 + 2 * j) >> 1, (uint32_t)head, drop_thr, drop_inv_keep, pa, pb);
             split2(pa, pb, hi[j], lo[j]);
           }
         }
@@ -444,6 +453,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
     xch[grp * 128 + r] = sum;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     sum = xch[r] + xch[128 + r];
+    if (lse2 && grp == 0 && q0 + r < len) lse2[(size_t)(row0 + q0 + r) * heads + head] = m_scaled + log2f(sum);
     if (threadIdx.x == 64) AT_STAMP(7);
     mbar_wait(o_full, 0);
     tc_fence_after();
@@ -489,7 +499,8 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
 }
 
 int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len, int heads,
-                    int head_dim, void* out, long long out_plane, cudaStream_t s) {
+                    int head_dim, void* out, long long out_plane, float* lse2, float p_drop, unsigned long long seed,
+                    cudaStream_t s) {
   if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
   if (head_dim != 64 || max_len > 512 || !aligned16(qkv_hi) || ((plane * 2) & 15)) return VBG_EUNSUPPORTED;
   const long long ld = 3LL * heads * 64;
@@ -510,7 +521,10 @@ int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int 
     attr = true;
   }
   dim3 grid(cdiv(max_len, 128), heads, nseq);
-  attention_split_kernel<<<grid, kAt2Threads, smem, s>>>(mq[0], mq[1], mv[0], mv[1], cu, heads, 0.125f * 1.4426950408889634f, out, out_plane, tc_debug_timeline());
+  uint32_t thr; float inv_keep;
+  attn_drop_params(p_drop, thr, inv_keep);
+  attention_split_kernel<<<grid, kAt2Threads, smem, s>>>(mq[0], mq[1], mv[0], mv[1], cu, heads, 0.125f * 1.4426950408889634f, out, out_plane,
+                                                         tc_debug_timeline(), lse2, thr, inv_keep, attn_seed32(seed));
   return check_launch("vbg_attention_split_fwd(tcgen05)");
 }
 

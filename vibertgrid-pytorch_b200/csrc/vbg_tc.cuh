@@ -124,6 +124,29 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t ab_fmt, int m, int n,
 }
 constexpr uint32_t kFmtTF32 = 2, kFmtBF16 = 1;
 
+// ------------------------------------------------------------------ attention-probability dropout (training)
+// keep(query row, key, head) is a pure function of a 32-bit seed: one lowbias32 hash per PAIR of keys (2j, 2j + 1), the low /
+// high 16 bits decide the even / odd key; an entry is kept when its 16 bits are >= thr = round(p * 65536), so the effective
+// drop probability is thr / 65536 (p = 0.1 -> 0.100006) and kept entries are scaled by 65536 / (65536 - thr).  Shared by the
+// forward kernel (vbg_attn_tc.cu) and the two backward kernels (vbg_attn_bwd_tc.cu), which must agree bit for bit.
+__host__ __device__ __forceinline__ uint32_t attn_drop_bits(uint32_t seed, uint32_t qrow, uint32_t kpair, uint32_t head) {
+  uint32_t x = seed ^ (qrow * 0x9E3779B1u) ^ (kpair * 0x85EBCA77u) ^ (head * 0xC2B2AE3Du);
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ void attn_drop_pair(uint32_t seed, uint32_t qrow, uint32_t kpair, uint32_t head, uint32_t thr, float inv_keep,
+                                               float& pa, float& pb) {
+  const uint32_t bits = attn_drop_bits(seed, qrow, kpair, head);
+  pa = (bits & 0xffffu) >= thr ? pa * inv_keep : 0.f;
+  pb = (bits >> 16) >= thr ? pb * inv_keep : 0.f;
+}
+inline void attn_drop_params(float p, uint32_t& thr, float& inv_keep) {
+  thr = p > 0.f ? (uint32_t)(p * 65536.0f + 0.5f) : 0u;
+  if (thr > 65535u) thr = 65535u;
+  inv_keep = 65536.0f / (65536.0f - (float)thr);
+}
+inline uint32_t attn_seed32(unsigned long long seed) { return (uint32_t)(seed ^ (seed >> 32)) * 0x9E3779B1u + 0x7F4A7C15u; }
+
 // ------------------------------------------------------------------ tile geometry shared by the tcgen05 GEMM kernels
 constexpr int BM = 128, BKE = 32;          // 32 fp32 = one 128-byte swizzle row
 constexpr int kTcThreads = 192;            // warp 0 TMA, warp 1 MMA, warps 2-5 convert / epilogue

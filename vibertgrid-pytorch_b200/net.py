@@ -135,6 +135,7 @@ class ViBERTgridNet(nn.Module):
         self.bert_cfg = _bert_config(bert_model)
         self.bert_model = P.BertParams(**self.bert_cfg)
         self.bert_hidden_dropout = float(self.bert_cfg["hidden_dropout_prob"])      # training-mode forward only
+        self.bert_attn_dropout = float(self.bert_cfg.get("attention_probs_dropout_prob", 0.0))
         if work_mode in ("train", "inference"):
             print("loading pretrained")
             self._load_pretrained_bert(bert_model)

@@ -218,6 +218,47 @@ def attention_split(qkv_split, cu, nseq, max_len, heads, split_out=False):
     return out
 
 
+def attention_split_train(qkv_split, cu, nseq, max_len, heads, p_drop=0.0, seed=0):
+    """Training-mode attention: like ``attention_split`` (fp32 result) plus dropout on the attention probabilities (mask =
+    pure function of ``seed``) and the base-2 row log-sum-exp [R, heads] the backward rebuilds the probabilities from."""
+    if not isinstance(qkv_split, Split):
+        qkv_split = Split(qkv_split)
+    R, three_h = qkv_split.shape
+    hidden = three_h // 3
+    out = torch.empty((R, hidden), dtype=torch.float32, device=qkv_split.device)
+    lse2 = torch.empty((R, heads), dtype=torch.float32, device=qkv_split.device)
+    L.check(L.load().vbg_attention_split_train_fwd(_p(qkv_split.t), R * three_h, _i32(cu), nseq, R, max_len, heads, hidden // heads,
+                                                   _f32(out), 0, _f32(lse2), float(p_drop), int(seed), _stream()),
+            "vbg_attention_split_train_fwd")
+    return out, lse2
+
+
+def attention_bwd_tc(qkv_split, out, d_out, lse2, cu, nseq, max_len, heads, p_drop=0.0, seed=0):
+    """dQKV fp32 [R, 3*hidden] on the tensor cores from the QKV planes, fp32 O / dO and the forward's ``lse2`` (same seed)."""
+    if not isinstance(qkv_split, Split):
+        qkv_split = Split(qkv_split)
+    R, three_h = qkv_split.shape
+    hidden = three_h // 3
+    dos = to_split(d_out)
+    # rows past a sequence's end are never written by the kernels (every packed row belongs to a sequence: all rows are)
+    dqkv = torch.empty((R, three_h), dtype=torch.float32, device=out.device)
+    ws = torch.empty(R * heads, dtype=torch.float32, device=out.device)
+    L.check(L.load().vbg_attention_bwd_tc(_p(qkv_split.t), R * three_h, _p(dos.t), R * hidden, _f32(out), _f32(d_out), _f32(lse2),
+                                          _i32(cu), nseq, R, max_len, heads, hidden // heads, float(p_drop), int(seed), _f32(dqkv),
+                                          _f32(ws), ws.numel() * 4, _stream()), "vbg_attention_bwd_tc")
+    return dqkv
+
+
+def attention_dropout_mask(seed, p_drop, row0, length, head, device):
+    """(keep mask [len, len] fp32, 1 / (1 - p_effective)) of the attention dropout for one (sequence, head) -- tests."""
+    import ctypes
+    mask = torch.empty((length, length), dtype=torch.float32, device=device)
+    ik = ctypes.c_float(0.0)
+    L.check(L.load().vbg_attention_dropout_mask(int(seed), float(p_drop), int(row0), int(length), int(head), _f32(mask),
+                                                ctypes.byref(ik), _stream()), "vbg_attention_dropout_mask")
+    return mask, float(ik.value)
+
+
 # ------------------------------------------------------------------ a3
 def mask_check(mask, tok_off, status):
     """Raises bit 2 of ``status`` when ``mask`` [B, L] is not the prefix mask the packed layout assumes (no host sync)."""

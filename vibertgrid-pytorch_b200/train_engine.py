@@ -106,6 +106,8 @@ class TrainEngine:
         cfg = bm.cfg
         heads = cfg["num_attention_heads"]
         p_drop = float(getattr(self.net, "bert_hidden_dropout", 0.1))
+        # dropout on the attention probabilities (HF attention_probs_dropout_prob), applied inside the attention kernels
+        p_attn = float(getattr(self.net, "bert_attn_dropout", cfg.get("attention_probs_dropout_prob", 0.1)))
         cu = dt["cu"]
         ids, pos = ops.bert_assemble(corpus, dt["seq_tab"], cu, plan.nseq, plan.R)
         if cfg.get("roberta"):
@@ -122,7 +124,7 @@ class TrainEngine:
             wqkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0)
             bqkv = torch.cat([sa.query.bias, sa.key.bias, sa.value.bias], 0)
             qkv = A.linear(x, wqkv, bqkv)
-            ctx = A.AttentionF.apply(qkv, cu, plan.nseq, plan.max_len, heads)
+            ctx = A.AttentionF.apply(qkv, cu, plan.nseq, plan.max_len, heads, p_attn, _rand_seed() if p_attn > 0.0 else 0)
             ao = lyr.attention.output
             a = drop(A.linear(ctx, ao.dense.weight, ao.dense.bias)) + x
             x = A.LayerNormPS.apply(a, ao.LayerNorm.weight, ao.LayerNorm.bias, ao.LayerNorm.eps)
