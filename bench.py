@@ -353,27 +353,52 @@ def train_step_arm(net, cfg, resident, n_rot, world, steps, warmup=3):
     opt_bert = torch.optim.AdamW(bert, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
     losses = []
 
+    ar = {"ms": 0.0, "bytes": 0, "n": 0, "on": False}
+
     def step(i):
         loss = net(*resident[i % n_rot])
         opt_cnn.zero_grad()
         opt_bert.zero_grad()
+        if world > 1 and ar["on"]:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        # graphed step: every gradient already sits in one flat arena -> in-place NCCL AVG over 4 slices, then backward()
+        # hands the averaged views to the parameters; eager step (first sighting of a batch signature): bucketed all-reduce
+        # of .grad after backward()
+        nbytes_ar = shard.allreduce_step_arena(net)
         loss.backward()
-        shard.allreduce_gradients(params)
+        if nbytes_ar == 0:
+            shard.allreduce_gradients(params)
+        if world > 1 and ar["on"] and nbytes_ar:
+            e1.record()
+            ar.setdefault("events", []).append((e0, e1))
+            ar["bytes"] = nbytes_ar
         opt_cnn.step()
         opt_bert.step()
         losses.append(loss.detach())
 
+    warmup = max(warmup, 2 * n_rot)        # every rotating batch signature is seen twice: eager, then captured
     for i in range(warmup):
         step(i)
-    c0 = _lib.launch_count
+    eng = net._train_engine
+    c0, r0 = _lib.launch_count, eng.graph_replays
+    ar["on"] = True
     ms = time_region(step, steps, True, world)
+    ar["on"] = False
     launches = _lib.launch_count - c0
     vals = [float(l) for l in losses]
-    return {"value": cfg.batch * steps * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
-            "includes": "train-mode forward (batch-stat BN, dropout) + backward + SGD/AdamW steps"
-                        + (" + NCCL gradient all-reduce" if world > 1 else ""),
-            "gpu_launches": launches, "loss_first": vals[0], "loss_last": vals[-1],
-            "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+    out = {"value": cfg.batch * steps * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "includes": "train-mode forward (batch-stat BN, hidden + attention dropout) + backward + SGD/AdamW steps"
+                       + (" + NCCL gradient all-reduce" if world > 1 else ""),
+           "whole_step_cuda_graph_replays": eng.graph_replays - r0,
+           "gpu_launches": launches, "loss_first": vals[0], "loss_last": vals[-1],
+           "peak_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}
+    if ar.get("events"):
+        t = [a.elapsed_time(b) for a, b in ar["events"]]
+        msa = sum(t) / len(t)
+        out["allreduce"] = {"exposed_ms_per_step": msa, "bytes": ar["bytes"], "how": "in-place NCCL AVG over 4 slices of the step's flat gradient arena",
+                            "bus_gbs": 2.0 * (world - 1) / world * ar["bytes"] / msa / 1e6}
+    return out
 
 
 def main():

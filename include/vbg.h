@@ -289,6 +289,10 @@ VBG_API int vbg_expand2x(const float* x, int B, int Hi, int Wi, int C, int H, in
 VBG_API int vbg_gelu(const float* x, const float* dy, long long n, float* out, vbg_stream_t stream);
 /* inverted dropout with a counter-based mask: y[i] = x[i] * keep(seed, i) / (1 - p); the same call is its own backward */
 VBG_API int vbg_dropout(const float* x, long long n, float p, unsigned long long seed, float* y, vbg_stream_t stream);
+/* the same with an optional DEVICE word `step_seed` folded into the seed at run time: a captured CUDA graph bakes the by-value
+ * seed of each call site; the host refreshes the one device word before every replay, so each step draws new masks */
+VBG_API int vbg_dropout_ds(const float* x, long long n, float p, unsigned long long seed, const unsigned long long* step_seed,
+                   float* y, vbg_stream_t stream);
 /* backward of vbg_grid_scatter: demb[k] = sum of dgrid over the cells segment k won (row stride ld floats between cells) */
 VBG_API int vbg_grid_scatter_bwd(const float* dgrid, long long ld, const int32_t* idx, const int32_t* boxes, const int32_t* seg_off, int B,
                          int K, int stride, int Hg, int Wg, int C, float* demb, vbg_stream_t stream);
@@ -331,13 +335,14 @@ VBG_API int vbg_attention_bwd(const float* qkv, const float* out, const float* d
  *   1 / (1 - p_effective) written to the HOST float *inv_keep -- test infrastructure for an exact reference. */
 VBG_API int vbg_attention_split_train_fwd(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len,
                                   int heads, int head_dim, void* out, long long out_plane, float* lse2, float p_drop,
-                                  unsigned long long seed, vbg_stream_t stream);
+                                  unsigned long long seed, const unsigned long long* step_seed /* device, or NULL */,
+                                  vbg_stream_t stream);
 VBG_API int vbg_attention_bwd_tc(const void* qkv_hi, long long qkv_plane, const void* do_hi, long long do_plane, const float* out,
                          const float* d_out, const float* lse2, const int32_t* cu, int nseq, int R, int max_len, int heads,
-                         int head_dim, float p_drop, unsigned long long seed, float* dqkv, float* workspace, size_t ws_bytes,
-                         vbg_stream_t stream);
-VBG_API int vbg_attention_dropout_mask(unsigned long long seed, float p_drop, int row0, int len, int head, float* mask,
-                               float* inv_keep, vbg_stream_t stream);
+                         int head_dim, float p_drop, unsigned long long seed, const unsigned long long* step_seed /* device, or NULL */,
+                         float* dqkv, float* workspace, size_t ws_bytes, vbg_stream_t stream);
+VBG_API int vbg_attention_dropout_mask(unsigned long long seed, unsigned long long step_seed /* host value */, int has_step_seed,
+                               float p_drop, int row0, int len, int head, float* mask, float* inv_keep, vbg_stream_t stream);
 
 /* ---- a7: GridROIAlign (model/grid_roi_align.py:37-41,81 -> torchvision roi_align, aligned=False,
  *          sampling_ratio=-1) over NHWC features; boxes are the int32 transformed coords.         */

@@ -92,6 +92,7 @@ SIGNATURES = {
     "vbg_expand2x": [_p, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p],
     "vbg_gelu": [_p, _p, _ll, _p, _p],
     "vbg_dropout": [_p, _ll, _f, C.c_ulonglong, _p, _p],
+    "vbg_dropout_ds": [_p, _ll, _f, C.c_ulonglong, _p, _p, _p],
     "vbg_grid_scatter_bwd": [_p, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "vbg_segment_reduce_bwd": [_p, _p, _p, _i, _i, _i, _p, _p],
     "vbg_embed_bwd": [_p, _p, _p, _i, _i, _p, _p, _p],
@@ -103,9 +104,9 @@ SIGNATURES = {
     "vbg_stem_wgrad_workspace": [],
     "vbg_stem_wgrad": [_p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p],
     "vbg_attention_bwd": [_p, _p, _p, _p, _i, _i, _i, _i, _ll, _p, _p, _sz, _p],
-    "vbg_attention_split_train_fwd": [_p, _ll, _p, _i, _i, _i, _i, _i, _p, _ll, _p, _f, C.c_ulonglong, _p],
-    "vbg_attention_bwd_tc": [_p, _ll, _p, _ll, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, C.c_ulonglong, _p, _p, _sz, _p],
-    "vbg_attention_dropout_mask": [C.c_ulonglong, _f, _i, _i, _i, _p, C.POINTER(_f), _p],
+    "vbg_attention_split_train_fwd": [_p, _ll, _p, _i, _i, _i, _i, _i, _p, _ll, _p, _f, C.c_ulonglong, _p, _p],
+    "vbg_attention_bwd_tc": [_p, _ll, _p, _ll, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, C.c_ulonglong, _p, _p, _p, _sz, _p],
+    "vbg_attention_dropout_mask": [C.c_ulonglong, C.c_ulonglong, _i, _f, _i, _i, _i, _p, C.POINTER(_f), _p],
     "vbg_softmax_rows": [_p, _i, _i, _p, _p],
     "vbg_full_head_scores": [_p, _p, _i, _i, _p, _p],
     "vbg_upsample_split_nchw": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p],

@@ -339,14 +339,17 @@ class GeluF(torch.autograd.Function):
 
 
 class DropoutF(torch.autograd.Function):
+    """``step_seed``: optional int64[1] DEVICE tensor folded into the seed at run time (see vbg_dropout_ds): under CUDA-graph
+    replay the by-value seed is baked, the device word changes every step."""
+
     @staticmethod
-    def forward(ctx, x, p, seed):
-        ctx.ps = (p, seed)
-        return ops.dropout(_c(x.detach()), p, seed)
+    def forward(ctx, x, p, seed, step_seed=None):
+        ctx.ps = (p, seed, step_seed)
+        return ops.dropout(_c(x.detach()), p, seed, step_seed)
 
     @staticmethod
     def backward(ctx, dy):
-        return ops.dropout(_c(dy), *ctx.ps), None, None
+        return ops.dropout(_c(dy), *ctx.ps), None, None, None
 
 
 class AttentionF(torch.autograd.Function):
@@ -357,7 +360,7 @@ class AttentionF(torch.autograd.Function):
     attention dropout: that mode exists to prove the wiring against the reference's gradients with dropout off."""
 
     @staticmethod
-    def forward(ctx, qkv, cu, nseq, max_len, heads, p_drop=0.0, seed=0):
+    def forward(ctx, qkv, cu, nseq, max_len, heads, p_drop=0.0, seed=0, step_seed=None):
         qkv = _c(qkv.detach())
         hid = qkv.shape[1] // 3
         if hid // heads != 64:
@@ -366,9 +369,9 @@ class AttentionF(torch.autograd.Function):
         ctx.cfg = (nseq, max_len, heads)
         if ctx.tc:
             qs = ops.to_split(qkv)
-            out, lse2 = ops.attention_split_train(qs, cu, nseq, max_len, heads, p_drop, seed)
+            out, lse2 = ops.attention_split_train(qs, cu, nseq, max_len, heads, p_drop, seed, step_seed)
             ctx.save_for_backward(qs.t, out, lse2, cu)
-            ctx.drop = (float(p_drop), int(seed))
+            ctx.drop = (float(p_drop), int(seed), step_seed)
         else:
             if p_drop > 0.0 and not getattr(AttentionF, "_warned", False):
                 AttentionF._warned = True
@@ -386,7 +389,7 @@ class AttentionF(torch.autograd.Function):
         else:
             qkv, out, cu = ctx.saved_tensors
             dqkv = ops.attention_bwd(qkv, out, _c(d_out), cu, *ctx.cfg)
-        return dqkv, None, None, None, None, None, None
+        return dqkv, None, None, None, None, None, None, None
 
 
 class EmbedSumF(torch.autograd.Function):

@@ -61,7 +61,9 @@ __global__ void __launch_bounds__(kAbThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUtensorMap tmQl,
                    const __grid_constant__ CUtensorMap tmDh, const __grid_constant__ CUtensorMap tmDl,
                    const int32_t* __restrict__ cu, int heads, float scale, float scale_log2e, const float* __restrict__ lse2,
-                   const float* __restrict__ delta, float* __restrict__ dqkv, uint32_t drop_thr, float drop_inv_keep, uint32_t seed) {
+                   const float* __restrict__ delta, float* __restrict__ dqkv, uint32_t drop_thr, float drop_inv_keep, uint32_t seed,
+                   const unsigned long long* __restrict__ step_seed) {
+  if (drop_thr && step_seed) seed = attn_fold_step(seed, __ldg(step_seed));
   const int seq = blockIdx.z, head = blockIdx.y, r0 = blockIdx.x * 128;
   const int row0 = cu[seq], len = cu[seq + 1] - row0;
   if (r0 >= len) return;                                        // whole CTA, before any barrier / allocation
@@ -309,7 +311,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_consta
 
 int attention_bwd_tc(const void* qkv_hi, long long qkv_plane, const void* do_hi, long long do_plane, const float* o, const float* d_o,
                      const float* lse2, const int32_t* cu, int nseq, int R, int max_len, int heads, float p_drop,
-                     unsigned long long seed, float* dqkv, float* delta, cudaStream_t s) {
+                     unsigned long long seed, const unsigned long long* step_seed, float* dqkv, float* delta, cudaStream_t s) {
   if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
   if (max_len > 512 || !aligned16(qkv_hi) || !aligned16(do_hi) || ((qkv_plane * 2) & 15) || ((do_plane * 2) & 15)) return VBG_EUNSUPPORTED;
   const long long ld3 = 3LL * heads * 64, ld1 = 1LL * heads * 64;
@@ -338,11 +340,11 @@ int attention_bwd_tc(const void* qkv_hi, long long qkv_plane, const void* do_hi,
   const float scale = 0.125f;
   dim3 grid(cdiv(max_len, 128), heads, nseq);
   attn_bwd_tc_kernel<true><<<grid, kAbThreads, smem, s>>>(mq[0], mq[1], md[0], md[1], cu, heads, scale, scale * 1.4426950408889634f, lse2, delta,
-                                                          dqkv, thr, inv_keep, seed32);
+                                                          dqkv, thr, inv_keep, seed32, step_seed);
   rc = check_launch("vbg_attention_bwd_tc(dK, dV)");
   if (rc) return rc;
   attn_bwd_tc_kernel<false><<<grid, kAbThreads, smem, s>>>(mq[0], mq[1], md[0], md[1], cu, heads, scale, scale * 1.4426950408889634f, lse2, delta,
-                                                           dqkv, thr, inv_keep, seed32);
+                                                           dqkv, thr, inv_keep, seed32, step_seed);
   return check_launch("vbg_attention_bwd_tc(dQ)");
 }
 
@@ -361,8 +363,8 @@ using namespace vbg;
 
 extern "C" int vbg_attention_bwd_tc(const void* qkv_hi, long long qkv_plane, const void* do_hi, long long do_plane, const float* out,
                                     const float* d_out, const float* lse2, const int32_t* cu, int nseq, int R, int max_len, int heads,
-                                    int head_dim, float p_drop, unsigned long long seed, float* dqkv, float* workspace, size_t ws_bytes,
-                                    vbg_stream_t stream) {
+                                    int head_dim, float p_drop, unsigned long long seed, const unsigned long long* step_seed, float* dqkv,
+                                    float* workspace, size_t ws_bytes, vbg_stream_t stream) {
   VBG_REQUIRE(qkv_hi && do_hi && out && d_out && lse2 && cu && dqkv && workspace && nseq > 0 && R > 0 && max_len > 0 && heads > 0 &&
                   qkv_plane > 0 && do_plane > 0 && aligned16(out) && aligned16(d_out) && aligned16(dqkv),
               "vbg_attention_bwd_tc: bad arguments");
@@ -372,18 +374,20 @@ extern "C" int vbg_attention_bwd_tc(const void* qkv_hi, long long qkv_plane, con
     set_error("vbg_attention_bwd_tc: workspace of %zu bytes needed", (size_t)R * heads * sizeof(float));
     return VBG_EWORKSPACE;
   }
-  int rc = attention_bwd_tc(qkv_hi, qkv_plane, do_hi, do_plane, out, d_out, lse2, cu, nseq, R, max_len, heads, p_drop, seed, dqkv,
+  int rc = attention_bwd_tc(qkv_hi, qkv_plane, do_hi, do_plane, out, d_out, lse2, cu, nseq, R, max_len, heads, p_drop, seed, step_seed, dqkv,
                             workspace, as_stream(stream));
   if (rc == VBG_EUNSUPPORTED) set_error("vbg_attention_bwd_tc: needs sm_100a, max_len <= 512, 16-byte aligned planes (max_len %d)", max_len);
   return rc;
 }
 
-extern "C" int vbg_attention_dropout_mask(unsigned long long seed, float p_drop, int row0, int len, int head, float* mask,
-                                          float* inv_keep, vbg_stream_t stream) {
+extern "C" int vbg_attention_dropout_mask(unsigned long long seed, unsigned long long step_seed, int has_step_seed, float p_drop, int row0,
+                                          int len, int head, float* mask, float* inv_keep, vbg_stream_t stream) {
   VBG_REQUIRE(mask && inv_keep && len > 0 && p_drop >= 0.f && p_drop < 1.f, "vbg_attention_dropout_mask: bad arguments");
   uint32_t thr; float ik;
   attn_drop_params(p_drop, thr, ik);
   *inv_keep = ik;
-  attn_drop_mask_kernel<<<cdiv((long long)len * len, 256), 256, 0, as_stream(stream)>>>(attn_seed32(seed), row0, len, head, thr, mask);
+  uint32_t s32 = attn_seed32(seed);
+  if (has_step_seed) s32 = attn_fold_step(s32, step_seed);
+  attn_drop_mask_kernel<<<cdiv((long long)len * len, 256), 256, 0, as_stream(stream)>>>(s32, row0, len, head, thr, mask);
   return check_launch("vbg_attention_dropout_mask");
 }

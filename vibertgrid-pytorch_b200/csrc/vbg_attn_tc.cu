@@ -262,7 +262,8 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
                        const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
                        const int32_t* __restrict__ cu, int heads, float scale_log2e, void* __restrict__ out,
                        long long out_plane, long long* __restrict__ dbg, float* __restrict__ lse2, uint32_t drop_thr,
-                       float drop_inv_keep, uint32_t seed) {
+                       float drop_inv_keep, uint32_t seed, const unsigned long long* __restrict__ step_seed) {
+  if (drop_thr && step_seed) seed = attn_fold_step(seed, __ldg(step_seed));
 #define AT_STAMP(slot) do { if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) dbg[slot] = clock64(); } while (0)
   const int seq = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * 128;
   const int row0 = cu[seq], len = cu[seq + 1] - row0;
@@ -500,7 +501,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
 
 int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len, int heads,
                     int head_dim, void* out, long long out_plane, float* lse2, float p_drop, unsigned long long seed,
-                    cudaStream_t s) {
+                    const unsigned long long* step_seed, cudaStream_t s) {
   if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
   if (head_dim != 64 || max_len > 512 || !aligned16(qkv_hi) || ((plane * 2) & 15)) return VBG_EUNSUPPORTED;
   const long long ld = 3LL * heads * 64;
@@ -524,7 +525,7 @@ int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int 
   uint32_t thr; float inv_keep;
   attn_drop_params(p_drop, thr, inv_keep);
   attention_split_kernel<<<grid, kAt2Threads, smem, s>>>(mq[0], mq[1], mv[0], mv[1], cu, heads, 0.125f * 1.4426950408889634f, out, out_plane,
-                                                         tc_debug_timeline(), lse2, thr, inv_keep, attn_seed32(seed));
+                                                         tc_debug_timeline(), lse2, thr, inv_keep, attn_seed32(seed), step_seed);
   return check_launch("vbg_attention_split_fwd(tcgen05)");
 }
 

@@ -234,7 +234,7 @@ int attention_tc(const float* qkv, const int32_t* cu, int nseq, int max_len, int
                  cudaStream_t s);
 int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len, int heads,
                     int head_dim, void* out, long long out_plane, float* lse2, float p_drop, unsigned long long seed,
-                    cudaStream_t s);
+                    const unsigned long long* step_seed, cudaStream_t s);
 
 }  // namespace vbg
 
@@ -309,7 +309,7 @@ extern "C" int vbg_attention_split_fwd(const void* qkv_hi, long long plane, cons
   VBG_REQUIRE(qkv_hi && cu && out && nseq >= 0 && R >= 0 && heads > 0 && plane > 0, "vbg_attention_split_fwd: bad arguments");
   VBG_REQUIRE(fmt_ok(out, out_plane), "vbg_attention_split_fwd: output must be 16B aligned, plane %% 8 == 0");
   if (nseq == 0 || max_len == 0) return VBG_OK;
-  int rc = attention_split(qkv_hi, plane, cu, nseq, R, max_len, heads, head_dim, out, out_plane, nullptr, 0.f, 0ull, as_stream(stream));
+  int rc = attention_split(qkv_hi, plane, cu, nseq, R, max_len, heads, head_dim, out, out_plane, nullptr, 0.f, 0ull, nullptr, as_stream(stream));
   if (rc == VBG_EUNSUPPORTED)
     set_error("vbg_attention_split_fwd: needs sm_100a, head_dim 64, max_len <= 512 (got head_dim %d, max_len %d)", head_dim, max_len);
   return rc;
@@ -317,12 +317,12 @@ extern "C" int vbg_attention_split_fwd(const void* qkv_hi, long long plane, cons
 
 extern "C" int vbg_attention_split_train_fwd(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len,
                                              int heads, int head_dim, void* out, long long out_plane, float* lse2, float p_drop,
-                                             unsigned long long seed, vbg_stream_t stream) {
+                                             unsigned long long seed, const unsigned long long* step_seed, vbg_stream_t stream) {
   VBG_REQUIRE(qkv_hi && cu && out && lse2 && nseq >= 0 && R >= 0 && heads > 0 && plane > 0, "vbg_attention_split_train_fwd: bad arguments");
   VBG_REQUIRE(fmt_ok(out, out_plane), "vbg_attention_split_train_fwd: output must be 16B aligned, plane %% 8 == 0");
   VBG_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "vbg_attention_split_train_fwd: 0 <= p_drop < 1");
   if (nseq == 0 || max_len == 0) return VBG_OK;
-  int rc = attention_split(qkv_hi, plane, cu, nseq, R, max_len, heads, head_dim, out, out_plane, lse2, p_drop, seed, as_stream(stream));
+  int rc = attention_split(qkv_hi, plane, cu, nseq, R, max_len, heads, head_dim, out, out_plane, lse2, p_drop, seed, step_seed, as_stream(stream));
   if (rc == VBG_EUNSUPPORTED)
     set_error("vbg_attention_split_train_fwd: needs sm_100a, head_dim 64, max_len <= 512 (got head_dim %d, max_len %d)", head_dim, max_len);
   return rc;

@@ -145,6 +145,10 @@ inline void attn_drop_params(float p, uint32_t& thr, float& inv_keep) {
   if (thr > 65535u) thr = 65535u;
   inv_keep = 65536.0f / (65536.0f - (float)thr);
 }
+// fold the optional DEVICE step seed (refreshed by the host before each CUDA-graph replay) into the launch's 32-bit seed
+__host__ __device__ __forceinline__ uint32_t attn_fold_step(uint32_t seed, unsigned long long step) {
+  return seed ^ ((uint32_t)step * 0x9E3779B1u) ^ ((uint32_t)(step >> 32) * 0x85EBCA77u);
+}
 inline uint32_t attn_seed32(unsigned long long seed) { return (uint32_t)(seed ^ (seed >> 32)) * 0x9E3779B1u + 0x7F4A7C15u; }
 
 // ------------------------------------------------------------------ tile geometry shared by the tcgen05 GEMM kernels

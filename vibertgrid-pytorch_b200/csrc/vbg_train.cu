@@ -227,7 +227,11 @@ __device__ __forceinline__ float keep_of(unsigned long long seed, unsigned long 
   return ((float)(z >> 40) * (1.0f / 16777216.0f)) >= p ? 1.0f : 0.0f;
 }
 // y = x * keep(seed, index) / (1 - p): the same call regenerates the mask for the backward
-__global__ void dropout_kernel(const float* __restrict__ x, long long n, float p, unsigned long long seed, float* __restrict__ y) {
+// `step_seed` (optional, DEVICE memory) is folded into the by-value seed: a captured CUDA graph bakes the by-value seed of
+// each call site, the host refreshes the one device word before every replay, so every step draws a new mask
+__global__ void dropout_kernel(const float* __restrict__ x, long long n, float p, unsigned long long seed,
+                               const unsigned long long* __restrict__ step_seed, float* __restrict__ y) {
+  if (step_seed) seed ^= __ldg(step_seed) * 0xD6E8FEB86659FD93ull;
   const float s = 1.0f / (1.0f - p);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __ldg(x + i) * keep_of(seed, (unsigned long long)i, p) * s;
@@ -647,8 +651,13 @@ extern "C" int vbg_gelu(const float* x, const float* dy, long long n, float* out
 }
 
 extern "C" int vbg_dropout(const float* x, long long n, float p, unsigned long long seed, float* y, vbg_stream_t stream) {
+  return vbg_dropout_ds(x, n, p, seed, nullptr, y, stream);
+}
+
+extern "C" int vbg_dropout_ds(const float* x, long long n, float p, unsigned long long seed, const unsigned long long* step_seed,
+                              float* y, vbg_stream_t stream) {
   VBG_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "vbg_dropout: 0 <= p < 1");
-  dropout_kernel<<<grid_for(n, 1024), 256, 0, as_stream(stream)>>>(x, n, p, seed, y);
+  dropout_kernel<<<grid_for(n, 1024), 256, 0, as_stream(stream)>>>(x, n, p, seed, step_seed, y);
   return check_launch("vbg_dropout");
 }
 

@@ -218,7 +218,12 @@ def attention_split(qkv_split, cu, nseq, max_len, heads, split_out=False):
     return out
 
 
-def attention_split_train(qkv_split, cu, nseq, max_len, heads, p_drop=0.0, seed=0):
+def _u64ptr(t):
+    """Device pointer of an optional int64[1] step-seed tensor (None -> NULL)."""
+    return None if t is None else _p(t, torch.int64)
+
+
+def attention_split_train(qkv_split, cu, nseq, max_len, heads, p_drop=0.0, seed=0, step_seed=None):
     """Training-mode attention: like ``attention_split`` (fp32 result) plus dropout on the attention probabilities (mask =
     pure function of ``seed``) and the base-2 row log-sum-exp [R, heads] the backward rebuilds the probabilities from."""
     if not isinstance(qkv_split, Split):
@@ -228,12 +233,12 @@ def attention_split_train(qkv_split, cu, nseq, max_len, heads, p_drop=0.0, seed=
     out = torch.empty((R, hidden), dtype=torch.float32, device=qkv_split.device)
     lse2 = torch.empty((R, heads), dtype=torch.float32, device=qkv_split.device)
     L.check(L.load().vbg_attention_split_train_fwd(_p(qkv_split.t), R * three_h, _i32(cu), nseq, R, max_len, heads, hidden // heads,
-                                                   _f32(out), 0, _f32(lse2), float(p_drop), int(seed), _stream()),
+                                                   _f32(out), 0, _f32(lse2), float(p_drop), int(seed), _u64ptr(step_seed), _stream()),
             "vbg_attention_split_train_fwd")
     return out, lse2
 
 
-def attention_bwd_tc(qkv_split, out, d_out, lse2, cu, nseq, max_len, heads, p_drop=0.0, seed=0):
+def attention_bwd_tc(qkv_split, out, d_out, lse2, cu, nseq, max_len, heads, p_drop=0.0, seed=0, step_seed=None):
     """dQKV fp32 [R, 3*hidden] on the tensor cores from the QKV planes, fp32 O / dO and the forward's ``lse2`` (same seed)."""
     if not isinstance(qkv_split, Split):
         qkv_split = Split(qkv_split)
@@ -244,18 +249,19 @@ def attention_bwd_tc(qkv_split, out, d_out, lse2, cu, nseq, max_len, heads, p_dr
     dqkv = torch.empty((R, three_h), dtype=torch.float32, device=out.device)
     ws = torch.empty(R * heads, dtype=torch.float32, device=out.device)
     L.check(L.load().vbg_attention_bwd_tc(_p(qkv_split.t), R * three_h, _p(dos.t), R * hidden, _f32(out), _f32(d_out), _f32(lse2),
-                                          _i32(cu), nseq, R, max_len, heads, hidden // heads, float(p_drop), int(seed), _f32(dqkv),
-                                          _f32(ws), ws.numel() * 4, _stream()), "vbg_attention_bwd_tc")
+                                          _i32(cu), nseq, R, max_len, heads, hidden // heads, float(p_drop), int(seed), _u64ptr(step_seed),
+                                          _f32(dqkv), _f32(ws), ws.numel() * 4, _stream()), "vbg_attention_bwd_tc")
     return dqkv
 
 
-def attention_dropout_mask(seed, p_drop, row0, length, head, device):
+def attention_dropout_mask(seed, p_drop, row0, length, head, device, step_seed=None):
     """(keep mask [len, len] fp32, 1 / (1 - p_effective)) of the attention dropout for one (sequence, head) -- tests."""
     import ctypes
     mask = torch.empty((length, length), dtype=torch.float32, device=device)
     ik = ctypes.c_float(0.0)
-    L.check(L.load().vbg_attention_dropout_mask(int(seed), float(p_drop), int(row0), int(length), int(head), _f32(mask),
-                                                ctypes.byref(ik), _stream()), "vbg_attention_dropout_mask")
+    L.check(L.load().vbg_attention_dropout_mask(int(seed), int(step_seed or 0), int(step_seed is not None), float(p_drop), int(row0),
+                                                int(length), int(head), _f32(mask), ctypes.byref(ik), _stream()),
+            "vbg_attention_dropout_mask")
     return mask, float(ik.value)
 
 
@@ -711,9 +717,9 @@ def gelu(x, dy=None):
     return out
 
 
-def dropout(x, p, seed):
+def dropout(x, p, seed, step_seed=None):
     y = torch.empty_like(x)
-    L.check(L.load().vbg_dropout(_f32(x), x.numel(), p, seed, _f32(y), _stream()), "vbg_dropout")
+    L.check(L.load().vbg_dropout_ds(_f32(x), x.numel(), p, seed, _u64ptr(step_seed), _f32(y), _stream()), "vbg_dropout")
     return y
 
 

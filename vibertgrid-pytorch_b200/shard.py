@@ -64,3 +64,25 @@ def allreduce_gradients(params, bucket_bytes: int = 128 << 20) -> int:
         for g, f in zip(b, torch._utils._unflatten_dense_tensors(flat, b)):
             g.copy_(f)
     return len(buckets)
+
+
+def allreduce_step_arena(net, chunks: int = 4) -> int:
+    """Gradient average of a GRAPHED training step (train_engine.TrainEngine._graphed_loss): the replayed CUDA graph left every
+    parameter gradient in ONE flat fp32 arena (gradients are views of it), so the exchange is ``chunks`` in-place NCCL
+    all-reduces (op = AVG: the division happens inside the collective) over slices of that arena -- no flatten, no unflatten,
+    no separate division pass.  Call it between ``loss = net(batch)`` and ``loss.backward()``: the backward of the step's one
+    autograd node hands the (now averaged) arena views to the parameters.  Returns the bytes reduced (0: nothing to do --
+    not a graphed step, or a single rank; use ``allreduce_gradients`` after ``backward()`` then)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    eng = getattr(net, "_train_engine", None)
+    arena = getattr(eng, "grad_arena", None) if eng is not None else None
+    if arena is None or not getattr(eng, "arena_fresh", False):
+        return 0
+    eng.arena_fresh = False
+    n = arena.numel()
+    step = -(-n // max(1, chunks))
+    step = -(-step // 1024) * 1024
+    for off in range(0, n, step):
+        dist.all_reduce(arena[off:min(n, off + step)], op=dist.ReduceOp.AVG)
+    return n * arena.element_size()

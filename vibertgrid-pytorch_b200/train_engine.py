@@ -7,10 +7,15 @@ What differs from the eval engine (engine.py):
     ``loss.backward()`` fills ``.grad`` of the registered parameters -- DDP hooks, ``clip_grad_norm`` and the optimizers of the
     reference's training loop see ordinary gradients;
   * BatchNorm uses batch statistics and updates ``running_mean / running_var / num_batches_tracked`` (momentum form);
-  * the BERT hidden-state dropouts are applied (counter-based mask kernel).  NOT applied: the dropout on the attention
-    probabilities (it lives inside the attention kernel; listed in DESIGN.md as a deviation of the training path);
+  * the BERT hidden-state dropouts are applied (counter-based mask kernel) and so is the dropout on the attention
+    probabilities (inside the attention kernels, forward and backward);
   * the image min-size is drawn per image like ``transform.py:124-131,192-194`` (same torch CPU RNG consumption);
-  * no CUDA graphs, no stream forking: the tape is rebuilt every step.
+  * WHOLE-STEP CUDA GRAPH: a batch signature seen for the second time is captured -- train-mode forward AND the backward to
+    every parameter gradient -- into one CUDA graph (``_graphed_loss``).  From then on ``model(batch)`` copies the inputs into
+    the graph's static buffers, refreshes one device word (the dropout step seed) and replays the graph; the returned loss is
+    the output of a one-node autograd Function whose backward hands the already-computed gradients (times the incoming
+    ``grad_output``, e.g. GradScaler's scale) to the parameters, so ``loss.backward()``, DDP's hooks, ``clip_grad_norm`` and the
+    optimizers of the reference's loop work unchanged while ~2 000 Python-issued launches per step collapse into one.
 
 Heads: ``simp`` (BASELINE configs[1]-[3]), ``full`` (binary gate + C-1 binary heads) and ``crf`` (emissions + the CRF
 negative log-likelihood kernel, BASELINE configs[4]).  The ``simp`` head with the default auxiliary loss uses the fused
@@ -35,9 +40,58 @@ def _rand_seed():
     return int(torch.empty((), dtype=torch.int64).random_(0, 2 ** 62).item())       # CPU generator: no device sync
 
 
+class _parameters_as:
+    """Context: every module attribute that resolves to a registered Parameter ``p`` with ``id(p)`` in ``aliases`` resolves to
+    the alias tensor instead (an instance-dict entry shadows ``nn.Module.__getattr__``); the registration itself is untouched,
+    so ``named_parameters()``, the optimizers and DDP never see a difference.  (torch's ``_reparametrize_module`` cannot be
+    used: the BERT module is registered under two parents -- ``bert_model`` and ``BERTgrid_generator.model``, the reference's
+    state-dict layout -- and its tie handling leaves such a module holding the aliases on exit.)"""
+
+    def __init__(self, net, aliases):
+        self.net, self.aliases, self.done = net, aliases, []
+
+    def __enter__(self):
+        for mod in self.net.modules():
+            for name, p in mod._parameters.items():
+                if p is not None and id(p) in self.aliases and name not in mod.__dict__:
+                    mod.__dict__[name] = self.aliases[id(p)]
+                    self.done.append((mod, name))
+        return self
+
+    def __exit__(self, *exc):
+        for mod, name in self.done:
+            del mod.__dict__[name]
+        return False
+
+
+class _StepGradsF(torch.autograd.Function):
+    """The one autograd node of a graphed training step: ``forward`` returns the loss the replayed CUDA graph produced;
+    ``backward`` hands each parameter its gradient -- already computed by the same replay -- times the incoming grad_output."""
+
+    @staticmethod
+    def forward(ctx, loss, n_grads, *rest):
+        ctx.grads = rest[:n_grads]                     # static tensors of the graph (rewritten by the next replay)
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, go):
+        scaled = torch._foreach_mul(list(ctx.grads), go.reshape(()))       # fresh tensors: .grad never aliases graph memory
+        return (None, None) + (None,) * len(ctx.grads) + tuple(scaled)
+
+
 class TrainEngine:
     def __init__(self, net):
+        import os
         self.net = net
+        self.use_graphs = os.environ.get("VBG_TRAIN_GRAPHS", "1") != "0"
+        self.max_graphs = 4
+        self._graphs = {}
+        self.graph_replays = 0
+        self._step_seed = None
+        self.grad_arena, self.arena_fresh = None, False
+
+    def invalidate(self):
+        self._graphs.clear()
 
     # ------------------------------------------------------------------ building blocks
     @staticmethod
@@ -115,8 +169,10 @@ class TrainEngine:
         x = A.EmbedSumF.apply(e.word_embeddings.weight, e.position_embeddings.weight, e.token_type_embeddings.weight, ids, pos)
         x = A.LayerNormPS.apply(x, e.LayerNorm.weight, e.LayerNorm.bias, e.LayerNorm.eps)
 
+        step_seed = getattr(self, "_step_seed", None)      # device word, refreshed per step (None outside the graphed path)
+
         def drop(t):
-            return A.DropoutF.apply(t, p_drop, _rand_seed()) if p_drop > 0.0 else t
+            return A.DropoutF.apply(t, p_drop, _rand_seed(), step_seed) if p_drop > 0.0 else t
 
         x = drop(x)
         for lyr in bm.encoder.layer:
@@ -124,7 +180,7 @@ class TrainEngine:
             wqkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0)
             bqkv = torch.cat([sa.query.bias, sa.key.bias, sa.value.bias], 0)
             qkv = A.linear(x, wqkv, bqkv)
-            ctx = A.AttentionF.apply(qkv, cu, plan.nseq, plan.max_len, heads, p_attn, _rand_seed() if p_attn > 0.0 else 0)
+            ctx = A.AttentionF.apply(qkv, cu, plan.nseq, plan.max_len, heads, p_attn, _rand_seed() if p_attn > 0.0 else 0, step_seed)
             ao = lyr.attention.output
             a = drop(A.linear(ctx, ao.dense.weight, ao.dense.bias)) + x
             x = A.LayerNormPS.apply(a, ao.LayerNorm.weight, ao.LayerNorm.bias, ao.LayerNorm.eps)
@@ -180,6 +236,25 @@ class TrainEngine:
         return t
 
     # ------------------------------------------------------------------ the step's forward
+    def _graphable(self, dev):
+        """Whole-step capture needs a step without host-side randomness inside the losses (index-sampled / OHEM losses draw
+        with Python's ``random`` and upload indices, losses.py) and without collectives inside the tape (SyncBatchNorm)."""
+        net = self.net
+        cfg = net.loss_cfg
+        if not self.use_graphs or dev.type != "cuda" or getattr(self, "_test_standins", False):
+            return False
+        if net.classifier_mode != "simp" or net.loss_weights is not None:
+            return False                     # full / crf: the two-stage auxiliary head and the gated heads index by device masks
+        if cfg["aux_sample_list"] is not None or tuple(cfg["aux"]) != (-1, -1):
+            return False
+        if any(int(v) >= 0 and int(v) < (1 << 20) for v in tuple(cfg["main_1"]) + tuple(cfg["main_2"])):
+            return False
+        if any(self._sync_group(m) is not None for m in net.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)):
+            return False
+        if any(m.momentum is None for m in net.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)):
+            return False                     # cumulative moving average: the factor is read back from the step counter
+        return True
+
     def loss(self, image, seg_indices, seg_classes, coors, corpus, mask):
         net = self.net
         dev = corpus.device
@@ -187,8 +262,6 @@ class TrainEngine:
             raise RuntimeError("ViBERTgridNet (B200) trains on CUDA tensors only; there is no CPU fallback")
         if net.classifier_mode not in ("simp", "full", "crf"):
             raise ValueError(f"unknown classifier_mode {net.classifier_mode!r}")
-        default_aux = (net.classifier_mode == "simp" and net.loss_cfg["aux_sample_list"] is None
-                       and tuple(net.loss_cfg["aux"]) == (-1, -1) and net.loss_weights is None)
         sizes = list(net.image_min_size)
         # transform.py:124-131,192-194: one draw per image from the training min-size list
         min_sizes = [float(sizes[int(torch.empty(1).uniform_(0.0, float(len(sizes))).item())]) for _ in image]
@@ -198,25 +271,102 @@ class TrainEngine:
         # the previous step's kernels are done -- in a launch-bound step that bubble is paid in full
         tab = torch.from_numpy(plan.table)
         tab = (tab.pin_memory() if dev.type == "cuda" else tab).to(dev, non_blocking=True)
+        st = dict(image=[im.contiguous() for im in image],
+                  coors=torch.cat([c.reshape(-1, 4) for c in coors], 0).to(torch.int64).contiguous(),
+                  seg_ids=torch.cat([s.reshape(-1) for s in seg_indices], 0).to(torch.int32).contiguous(),
+                  cls=torch.cat([c.reshape(-1) for c in seg_classes], 0).to(torch.int32).contiguous(),
+                  corpus=corpus.contiguous(), mask=None if mask is None else mask.to(torch.int32).contiguous(), tab=tab)
+        if self._graphable(dev):
+            return self._graphed_loss(plan, st, tuple(min_sizes))
+        self._step_seed = None
+        self.arena_fresh = False
+        return self._forward(plan, st)
+
+    # ------------------------------------------------------------------ whole-step CUDA graph
+    def _graphed_loss(self, plan, st, min_sizes):
+        net = self.net
+        dev = st["corpus"].device
+        named = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
+        params = [p for _, p in named]
+        key = (tuple(tuple(im.shape) for im in st["image"]), tuple(st["coors"].shape), tuple(st["seg_ids"].shape), tuple(st["corpus"].shape),
+               st["mask"] is None, min_sizes, dev.index, tuple(p.data_ptr() for p in params),
+               tuple(b.data_ptr() for b in net.buffers()), float(net.bert_hidden_dropout), float(net.bert_attn_dropout),
+               tuple(plan.seg_counts), tuple(int(v) for v in plan.view("tok_off")))
+        ent = self._graphs.get(key)
+        if ent is None:                        # first sighting: an ordinary eager step (also warms lazy kernel attributes up)
+            self._graphs[key] = {"graph": None}
+            if len(self._graphs) > self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+            self._step_seed = None
+            self.arena_fresh = False
+            return self._forward(plan, st)
+        if self._step_seed is None or self._step_seed.device != dev:
+            self._step_seed = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        if ent["graph"] is None:               # second sighting: capture forward + backward
+            static = {k: ([t.clone() for t in v] if isinstance(v, list) else (None if v is None else v.clone())) for k, v in st.items()}
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                # The tape is built over ALIASES of the parameters (detached views of the same storage, made leaves inside the
+                # capture): the real Parameters' AccumulateGrad nodes were created by earlier eager steps / by DDP on the default
+                # stream and stay alive, and routing a captured backward through them makes the engine synchronise the capturing
+                # stream with the legacy stream, which invalidates the capture (scripts/train_graph_debug3.py).  The aliases read
+                # the parameter storage, so replays follow every in-place optimizer update.
+                aliases = {id(p_): p_.detach().requires_grad_() for _, p_ in named}
+                with _parameters_as(net, aliases):
+                    with torch.enable_grad():
+                        loss = self._forward(plan, static)
+                        grads = torch.autograd.grad(loss, [aliases[id(p_)] for p_ in params], allow_unused=True)
+                used = [(p_, g_) for p_, g_ in zip(params, grads) if g_ is not None]
+                # one flat arena, gradients as views (the N > 1 bench averages it with a single bucketed all-reduce)
+                arena = torch.empty(sum(g_.numel() for _, g_ in used), dtype=torch.float32, device=dev)
+                views, off = [], 0
+                for _, g_ in used:
+                    views.append(arena[off:off + g_.numel()].view(g_.shape))
+                    off += g_.numel()
+                torch._foreach_copy_(views, [g_ for _, g_ in used])
+                loss_out = loss.detach().clone()
+            ent.update(graph=g, static=static, loss=loss_out, views=views, arena=arena, params=[p_ for p_, _ in used], last=self.last)
+        else:
+            sd = ent["static"]
+            for dst, src in zip(sd["image"], st["image"]):
+                dst.copy_(src, non_blocking=True)
+            for k in ("coors", "seg_ids", "cls", "corpus", "mask"):
+                if sd[k] is not None:
+                    sd[k].copy_(st[k], non_blocking=True)
+        self._seed_host.random_(0, 2 ** 62)
+        self._step_seed.copy_(self._seed_host, non_blocking=True)
+        ent["graph"].replay()
+        self.graph_replays += 1
+        self.last = ent["last"]
+        self.grad_arena, self.arena_fresh = ent["arena"], True
+        return _StepGradsF.apply(ent["loss"], len(ent["views"]), *ent["views"], *ent["params"])
+
+    def _forward(self, plan, st):
+        """The kernel sequence of one training forward over staged inputs (capturable: no host sync)."""
+        net = self.net
+        image, coors_cat, seg_ids, cls_cat, corpus, mask, tab = (st["image"], st["coors"], st["seg_ids"], st["cls"], st["corpus"],
+                                                                 st["mask"], st["tab"])
+        dev = corpus.device
+        default_aux = (net.classifier_mode == "simp" and net.loss_cfg["aux_sample_list"] is None
+                       and tuple(net.loss_cfg["aux"]) == (-1, -1) and net.loss_weights is None)
         dt = {k: tab[s:s + n] for k, (s, n) in plan.offsets.items()}
         dt["ratios"] = dt["ratios"].view(torch.float32)
         seg_off = dt["seg_off"]
         B = plan.B
         status = torch.zeros(1, dtype=torch.int32, device=dev)
-        coors_cat = torch.cat([c.reshape(-1, 4) for c in coors], 0).to(torch.int64).contiguous()
-        seg_ids = torch.cat([s.reshape(-1) for s in seg_indices], 0).to(torch.int32).contiguous()
-        cls_cat = torch.cat([c.reshape(-1) for c in seg_classes], 0).to(torch.int32).contiguous()
 
         # a1 transform
         boxes = ops.resize_coords(coors_cat, seg_off, dt["ratios"], B)
         img4 = torch.zeros((B, plan.H + 6, plan.W + 6, 4), dtype=torch.float32, device=dev)
         for b, im in enumerate(image):
-            ops.normalize_resize_pad(im.contiguous(), img4, b, plan.sizes[b][0], plan.sizes[b][1], net.image_mean, net.image_std)
+            ops.normalize_resize_pad(im, img4, b, plan.sizes[b][0], plan.sizes[b][1], net.image_mean, net.image_std)
 
         # a2 - a4 BERT, segment aggregation, BERTgrid
-        hidden = self._bert(plan, dt, corpus.contiguous())
+        hidden = self._bert(plan, dt, corpus)
         if mask is not None and dev.type == "cuda":                 # input contract of `mask` (prefix of n_tok ones): status bit 2
-            ops.mask_check(mask.to(torch.int32).contiguous(), dt["tok_off"], status)
+            ops.mask_check(mask, dt["tok_off"], status)
         seg_start = ops.segment_starts(seg_ids, dt["tok_off"], B, plan.K, status)
         seg_emb = A.SegmentReduceF.apply(hidden, dt["tok_row"], seg_start, plan.K,
                                          ops.AGG_MEAN if net.grid_mode == "mean" else ops.AGG_FIRST)
