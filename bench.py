@@ -381,11 +381,13 @@ def train_step_arm(net, cfg, resident, n_rot, world, steps, warmup=3):
     for i in range(warmup):
         step(i)
     eng = net._train_engine
-    c0, r0 = _lib.launch_count, eng.graph_replays
+    c0, r0, k0 = _lib.launch_count, eng.graph_replays, eng.kernel_launches
     ar["on"] = True
     ms = time_region(step, steps, True, world)
     ar["on"] = False
-    launches = _lib.launch_count - c0
+    # kernels of this library executed in the timed region: host-issued C-ABI launches + those replayed from the step graphs
+    # (the capture itself happens in the warm-up; its host-side calls are not counted twice)
+    launches = (_lib.launch_count - c0) + (eng.kernel_launches - k0)
     vals = [float(l) for l in losses]
     out = {"value": cfg.batch * steps * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
            "includes": "train-mode forward (batch-stat BN, hidden + attention dropout) + backward + SGD/AdamW steps"

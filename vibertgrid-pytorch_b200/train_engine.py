@@ -87,6 +87,7 @@ class TrainEngine:
         self.max_graphs = 4
         self._graphs = {}
         self.graph_replays = 0
+        self.kernel_launches = 0          # C-ABI kernel launches executed on the device by graph replays (bench.py: gpu_launches)
         self._step_seed = None
         self.grad_arena, self.arena_fresh = None, False
 
@@ -307,6 +308,7 @@ class TrainEngine:
             static = {k: ([t.clone() for t in v] if isinstance(v, list) else (None if v is None else v.clone())) for k, v in st.items()}
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            c0 = ops.L.launch_count
             with torch.cuda.graph(g):
                 # The tape is built over ALIASES of the parameters (detached views of the same storage, made leaves inside the
                 # capture): the real Parameters' AccumulateGrad nodes were created by earlier eager steps / by DDP on the default
@@ -327,7 +329,8 @@ class TrainEngine:
                     off += g_.numel()
                 torch._foreach_copy_(views, [g_ for _, g_ in used])
                 loss_out = loss.detach().clone()
-            ent.update(graph=g, static=static, loss=loss_out, views=views, arena=arena, params=[p_ for p_, _ in used], last=self.last)
+            ent.update(graph=g, static=static, loss=loss_out, views=views, arena=arena, params=[p_ for p_, _ in used], last=self.last,
+                       launches=ops.L.launch_count - c0)       # C-ABI kernel launches recorded into the graph = executed per replay
         else:
             sd = ent["static"]
             for dst, src in zip(sd["image"], st["image"]):
@@ -339,6 +342,7 @@ class TrainEngine:
         self._step_seed.copy_(self._seed_host, non_blocking=True)
         ent["graph"].replay()
         self.graph_replays += 1
+        self.kernel_launches += ent["launches"]
         self.last = ent["last"]
         self.grad_arena, self.arena_fresh = ent["arena"], True
         return _StepGradsF.apply(ent["loss"], len(ent["views"]), *ent["views"], *ent["params"])
