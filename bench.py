@@ -309,6 +309,96 @@ def kernel_rooflines(net, cfg, dev, peaks):
     return out
 
 
+def library_bar(cfg, dev, steps=3, warmup=2):
+    """The library-kernel bar: what stock library kernels reach on this B200 for the same work --
+      * the UNMODIFIED reference ViBERTgridNet in eager mode on the GPU (HF BertModel on cuBLAS, cuDNN convolutions,
+        torchvision's CUDA roi_align, its own Python glue with its device->host syncs), fp32 and with TF32 allowed;
+      * cuBLAS on the dominant GEMM's shape (fp32 / TF32 / bf16) and torchvision.ops.roi_align on the ROI kernel's shape.
+    Library calls appear ONLY here, as the bar the hand-written path is held against; never on the hot path."""
+    import contextlib
+    import dataclasses
+    from vibertgrid_pytorch_b200 import synth
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def t_ms(fn, reps=10):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = ev(), ev()
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    M = cfg.batch * (cfg.seq_len + 2 * (cfg.seq_len // 510 + 1))
+    a, w = torch.randn(M, 768, device=dev), torch.randn(3072, 768, device=dev)
+    fl = 2.0 * M * 3072 * 768
+    gemm = {}
+    for name, tf32 in (("fp32", False), ("tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        ms = t_ms(lambda: torch.nn.functional.linear(a, w))
+        gemm[name] = {"ms": ms, "tflops": fl / ms / 1e9}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ab, wb = a.bfloat16(), w.bfloat16()
+    ms = t_ms(lambda: torch.nn.functional.linear(ab, wb))
+    gemm["bf16"] = {"ms": ms, "tflops": fl / ms / 1e9}
+    out["cublas_ffn_up"] = {"shape": [M, 3072, 768], **gemm, "note": "warm L2, no bias / GELU epilogue"}
+    try:
+        import torchvision
+        B, S = cfg.batch, cfg.segments
+        g = torch.Generator().manual_seed(1)
+        boxes = torch.cat([synth.make_boxes(S, cfg.height, cfg.width, g) for _ in range(B)], 0).float().to(dev)
+        bidx = torch.arange(B, device=dev).repeat_interleave(S).float()[:, None]
+        feat = torch.randn(B, 256, cfg.height // 4, cfg.width // 4, device=dev)
+        rois = torch.cat([bidx, boxes], 1)
+        ms = t_ms(lambda: torchvision.ops.roi_align(feat, rois, output_size=7, spatial_scale=0.25, sampling_ratio=-1, aligned=False))
+        out["torchvision_roi_align"] = {"ms": ms, "layout": "NCHW fp32 (the reference's call, model/grid_roi_align.py:81)"}
+    except Exception as exc:
+        out["torchvision_roi_align"] = {"error": str(exc)[:120]}
+    ref_dir = _staged_reference()
+    if ref_dir is not None:
+        try:
+            sys.path.insert(0, ref_dir)
+            net, kw = build_net(cfg)
+            sd = {k: v for k, v in net.state_dict().items()}
+            cwd = os.getcwd()
+            with tempfile.TemporaryDirectory() as tmp:
+                os.chdir(tmp)
+                try:
+                    synth.write_bert_dir(cfg, tmp)
+                    with contextlib.redirect_stdout(sys.stderr):
+                        from model.ViBERTgrid_net import ViBERTgridNet as RefNet
+                        ref = RefNet(**synth.model_kwargs(cfg, "eval"))
+                finally:
+                    os.chdir(cwd)
+            ref.load_state_dict(sd, strict=True)
+            ref = ref.to(dev).eval()
+            batches = [to_device(synth.make_batch(cfg, i), dev, False) for i in range(2)]
+            res = {}
+            for name, tf32 in (("fp32", False), ("tf32", True)):
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.allow_tf32 = tf32
+                with torch.no_grad():
+                    for i in range(warmup):
+                        ref(*batches[i % 2])
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    for i in range(steps):
+                        ref(*batches[i % 2])
+                    torch.cuda.synchronize()
+                    dt = time.perf_counter() - t0
+                res[name] = {"images_per_s": cfg.batch * steps / dt, "ms_per_step": 1e3 * dt / steps}
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+            out["reference_eager_cuda"] = {**res, "what": f"unmodified reference ViBERTgridNet on this GPU, eager, batch {cfg.batch}, {steps} timed steps "
+                                                          "(wall clock: its Python glue synchronises the device thousands of times per step)"}
+            del ref
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            out["reference_eager_cuda"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    return out
+
+
 def measured_peaks(dev):
     """MEASURED_PEAKS.json (driver-written) + a live cuBLAS TF32 / fp32 GEMM measured the same way
     (library call used ONLY as the roofline denominator, never on the hot path)."""
@@ -414,6 +504,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement (the `train_step` object)")
+    ap.add_argument("--no-library-bar", action="store_true", help="skip the library-kernel bar (reference eager on the GPU, cuBLAS, torchvision)")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="train: the line's value / ms_per_step are the TRAINING step (forward + backward + all-reduce + optimizers)")
     args = ap.parse_args()
@@ -550,6 +641,15 @@ def main():
             line["roofline"]["hbm_scatter_b2b_frac"] = round(kr["grid_scatter"].get("back_to_back", {}).get("frac", 0.0), 4)
             line["roofline"]["hbm_roi_align_frac"] = round(kr["roi_align"]["frac"], 4)
             line["peaks"] = peaks
+        if not args.no_library_bar and world == 1:
+            try:
+                line["library_bar"] = library_bar(cfg, dev)
+                rb = line["library_bar"].get("reference_eager_cuda", {})
+                if "fp32" in rb:       # numeric copies where the driver's record keeps them
+                    line["e2e"]["reference_eager_cuda_fp32_images_per_s"] = round(rb["fp32"]["images_per_s"], 2)
+                    line["e2e"]["reference_eager_cuda_tf32_images_per_s"] = round(rb["tf32"]["images_per_s"], 2)
+            except Exception as exc:
+                line["library_bar"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = {k: v for k, v in cpu_reference_arm(cfg, 5, 1, sample_images=min(2, cfg.batch)).items()
                                     if k != "ms_per_step"}
