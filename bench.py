@@ -399,6 +399,32 @@ def library_bar(cfg, dev, steps=3, warmup=2):
     return out
 
 
+def serving_latency(dev, n=200):
+    """the deployment path -- ``model.inference(image, seg_indices, coors, corpus, mask)`` (reference
+    deployment/module_load.py -> model/ViBERTgrid_net.py:470-499) for ONE document of BASELINE configs[0] (cfg1: r18 +
+    bert-base, 512x512, 512 tokens, 128 boxes), CUDA-graph replay, host buffers in pinned memory: per-request latency from
+    the first H2D byte to the predictions read back on the host."""
+    import dataclasses
+    from vibertgrid_pytorch_b200 import synth
+    cfg = synth.CONFIGS["cfg1"]
+    net, _ = build_net(cfg, dev)
+    host = [pin(synth.make_batch(cfg, 100 + i)) for i in range(4)]
+    out_host = torch.empty((cfg.segments, cfg.num_classes), dtype=torch.float32).pin_memory()
+    lat = []
+    for i in range(n + 10):
+        t0 = time.perf_counter()
+        img, seg, cls, coors, corpus, mask = to_device(host[i % 4], dev, True)
+        pred = net.inference(img, seg, coors, corpus, mask)
+        out_host.copy_(pred, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        if i >= 10:
+            lat.append((time.perf_counter() - t0) * 1e3)
+    lat.sort()
+    return {"workload": "cfg1, one document per request, inference() entry point, host -> host", "requests": n,
+            "p50_ms": lat[len(lat) // 2], "p99_ms": lat[int(len(lat) * 0.99) - 1], "mean_ms": sum(lat) / len(lat),
+            "documents_per_s_one_stream": 1e3 / (sum(lat) / len(lat)), "graph_replays": net._get_engine().graph_replays}
+
+
 def measured_peaks(dev):
     """MEASURED_PEAKS.json (driver-written) + a live cuBLAS TF32 / fp32 GEMM measured the same way
     (library call used ONLY as the roofline denominator, never on the hot path)."""
@@ -641,6 +667,13 @@ def main():
             line["roofline"]["hbm_scatter_b2b_frac"] = round(kr["grid_scatter"].get("back_to_back", {}).get("frac", 0.0), 4)
             line["roofline"]["hbm_roi_align_frac"] = round(kr["roi_align"]["frac"], 4)
             line["peaks"] = peaks
+        if world == 1 and args.mode == "forward":
+            try:
+                line["serving"] = serving_latency(dev)
+                line["e2e"]["serve_cfg1_p50_ms"] = round(line["serving"]["p50_ms"], 3)
+                line["e2e"]["serve_cfg1_p99_ms"] = round(line["serving"]["p99_ms"], 3)
+            except Exception as exc:
+                line["serving"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         if not args.no_library_bar and world == 1:
             try:
                 line["library_bar"] = library_bar(cfg, dev)
