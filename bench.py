@@ -465,8 +465,10 @@ def train_step_arm(net, cfg, resident, n_rot, world, steps, warmup=3):
     bert = [p for n, p in net.named_parameters() if "bert_model" in n]
     cnn = [p for n, p in net.named_parameters() if "bert_model" not in n]
     params = list(net.parameters())
-    opt_cnn = torch.optim.SGD(cnn, lr=1e-4, momentum=0.9, weight_decay=5e-4)
-    opt_bert = torch.optim.AdamW(bert, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
+    # the reference's two optimizers (train_SROIE.py:217-235) as one multi-tensor kernel launch each (optim.py)
+    from vibertgrid_pytorch_b200.optim import FusedAdamW, FusedSGD
+    opt_cnn = FusedSGD(cnn, lr=1e-4, momentum=0.9, weight_decay=5e-4)
+    opt_bert = FusedAdamW(bert, lr=1e-6, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2)
     losses = []
 
     ar = {"ms": 0.0, "bytes": 0, "n": 0, "on": False}
@@ -506,7 +508,7 @@ def train_step_arm(net, cfg, resident, n_rot, world, steps, warmup=3):
     launches = (_lib.launch_count - c0) + (eng.kernel_launches - k0)
     vals = [float(l) for l in losses]
     out = {"value": cfg.batch * steps * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
-           "includes": "train-mode forward (batch-stat BN, hidden + attention dropout) + backward + SGD/AdamW steps"
+           "includes": "train-mode forward (batch-stat BN, hidden + attention dropout) + backward + fused multi-tensor SGD/AdamW steps"
                        + (" + NCCL gradient all-reduce" if world > 1 else ""),
            "whole_step_cuda_graph_replays": eng.graph_replays - r0,
            "gpu_launches": launches, "loss_first": vals[0], "loss_last": vals[-1],

@@ -344,6 +344,19 @@ VBG_API int vbg_attention_bwd_tc(const void* qkv_hi, long long qkv_plane, const 
 VBG_API int vbg_attention_dropout_mask(unsigned long long seed, unsigned long long step_seed /* host value */, int has_step_seed,
                                float p_drop, int row0, int len, int head, float* mask, float* inv_keep, vbg_stream_t stream);
 
+/* ---- multi-tensor optimizer steps (the reference's torch.optim.SGD / torch.optim.AdamW, train_SROIE.py:217-235, stepped at
+ * pipeline/train_val_utils.py:272-284): one launch updates every tensor of a param group with torch's single-tensor update
+ * rules.  `table`: DEVICE array of 6 int64 per tensor {param ptr, grad ptr, state1 ptr, state2 ptr, numel, first_chunk};
+ * a CTA owns one chunk of vbg_optim_chunk() elements; first_chunk = running sum of ceil(numel / chunk).  SGD: state1 =
+ * momentum_buffer (unused when momentum == 0), first_step != 0 initialises it to the gradient; AdamW: state1 / state2 =
+ * exp_avg / exp_avg_sq, bias_correction1 = 1 - beta1^t, sqrt_bias_correction2 = sqrt(1 - beta2^t).  grad_scale multiplies
+ * the gradients on the fly (1 / world size of an un-averaged all-reduce, or 1). */
+VBG_API int vbg_optim_chunk(void);
+VBG_API int vbg_sgd_step_mt(const void* table, int n_tensors, long long total_chunks, float lr, float momentum, float weight_decay,
+                    int first_step, float grad_scale, vbg_stream_t stream);
+VBG_API int vbg_adamw_step_mt(const void* table, int n_tensors, long long total_chunks, float lr, float beta1, float beta2, float eps,
+                      float weight_decay, float bias_correction1, float sqrt_bias_correction2, float grad_scale, vbg_stream_t stream);
+
 /* ---- a7: GridROIAlign (model/grid_roi_align.py:37-41,81 -> torchvision roi_align, aligned=False,
  *          sampling_ratio=-1) over NHWC features; boxes are the int32 transformed coords.         */
 VBG_API int vbg_roi_align_fwd(const float* feat, int B, int Hf, int Wf, int C, const int32_t* boxes, const int32_t* seg_off,

@@ -107,6 +107,9 @@ SIGNATURES = {
     "vbg_attention_split_train_fwd": [_p, _ll, _p, _i, _i, _i, _i, _i, _p, _ll, _p, _f, C.c_ulonglong, _p, _p],
     "vbg_attention_bwd_tc": [_p, _ll, _p, _ll, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, C.c_ulonglong, _p, _p, _p, _sz, _p],
     "vbg_attention_dropout_mask": [C.c_ulonglong, C.c_ulonglong, _i, _f, _i, _i, _i, _p, C.POINTER(_f), _p],
+    "vbg_optim_chunk": [],
+    "vbg_sgd_step_mt": [_p, _i, _ll, _f, _f, _f, _i, _f, _p],
+    "vbg_adamw_step_mt": [_p, _i, _ll, _f, _f, _f, _f, _f, _f, _f, _f, _p],
     "vbg_softmax_rows": [_p, _i, _i, _p, _p],
     "vbg_full_head_scores": [_p, _p, _i, _i, _p, _p],
     "vbg_upsample_split_nchw": [_p, _i, _i, _i, _i, _i, _i, _p, _p, _p],

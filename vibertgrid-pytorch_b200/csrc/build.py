@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libvbg_sm100a.so")
-SOURCES = ["vbg_api.cu", "vbg_grid.cu", "vbg_roi.cu", "vbg_roi_stream.cu", "vbg_image.cu", "vbg_bert.cu", "vbg_gemm_simt.cu", "vbg_gemm_tc.cu", "vbg_gemm_tc3.cu", "vbg_gemm_ps.cu", "vbg_wgrad.cu", "vbg_attn_tc.cu", "vbg_train.cu", "vbg_attn_bwd.cu", "vbg_attn_bwd_tc.cu", "vbg_crf.cu"]
+SOURCES = ["vbg_api.cu", "vbg_grid.cu", "vbg_roi.cu", "vbg_roi_stream.cu", "vbg_image.cu", "vbg_bert.cu", "vbg_gemm_simt.cu", "vbg_gemm_tc.cu", "vbg_gemm_tc3.cu", "vbg_gemm_ps.cu", "vbg_wgrad.cu", "vbg_attn_tc.cu", "vbg_train.cu", "vbg_attn_bwd.cu", "vbg_attn_bwd_tc.cu", "vbg_crf.cu", "vbg_optim.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
