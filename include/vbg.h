@@ -255,7 +255,7 @@ VBG_API int vbg_layernorm_bwd(const float* x, const float* dy, const float* gamm
 
 /* ---- training step: the backward of loss.backward() (pipeline/train_val_utils.py:277) through the modules of the path, and the
  *      training-mode forward pieces (batch-statistics BatchNorm, dropout).  fp32 channels-last; reductions have a fixed order;
- *      the only atomics are the scatter-adds of vbg_roi_align_bwd and vbg_embed_bwd.                                          */
+ *      every reduction has a fixed order: no atomics anywhere in the training step (bitwise reproducible gradients).          */
 /* nn.BatchNorm2d in train mode (model/ResNetFPN_ViBERTgrid.py:106-186, semantic_segmentation_head.py:66, field_type_..._head.py:64)
  * over [rows, C]: batch mean / biased variance / 1/sqrt(var+eps); C = 4 * a divisor of 256; workspace from vbg_bn_workspace     */
 VBG_API long long vbg_bn_workspace(long long rows, int C);
@@ -299,12 +299,15 @@ VBG_API int vbg_grid_scatter_bwd(const float* dgrid, long long ld, const int32_t
 /* backward of vbg_segment_reduce into the rows of dhidden that belong to a segment (caller zero-fills dhidden) */
 VBG_API int vbg_segment_reduce_bwd(const float* dseg, const int32_t* tok_row, const int32_t* seg_start, int K, int C, int mode,
                            float* dhidden, vbg_stream_t stream);
-/* embedding tables: dword[ids[r]] += dx[r], dpos[pos[r]] += dx[r] (caller zero-fills the tables) */
+/* embedding tables: dword[ids[r]] += dx[r], dpos[pos[r]] += dx[r] (caller zero-fills the tables); deterministic: the first packed
+ * row of each table row sums its matches in ascending row order */
 VBG_API int vbg_embed_bwd(const float* dx, const int32_t* ids, const int32_t* pos, int R, int hidden, float* dword, float* dpos,
                   vbg_stream_t stream);
-/* backward of vbg_roi_align_fwd into dfeat [B,Hf,Wf,C] (caller zero-fills) */
+/* backward of vbg_roi_align_fwd into dfeat [B,Hf,Wf,C]: deterministic gather form (every pixel written exactly once: no atomics,
+ * no zero-fill); workspace >= vbg_roi_align_bwd_workspace(K) bytes (per-ROI geometry) */
+VBG_API long long vbg_roi_align_bwd_workspace(int K);
 VBG_API int vbg_roi_align_bwd(const float* dout, int B, int Hf, int Wf, int C, const int32_t* boxes, const int32_t* seg_off, int K,
-                      float spatial_scale, int P, float* dfeat, vbg_stream_t stream);
+                      float spatial_scale, int P, float* dfeat, void* workspace, size_t ws_bytes, vbg_stream_t stream);
 /* gradient of gscale[0] * mean CE(mask head) + gscale[1] * mean CE(class head) (semantic_segmentation_head.py:343-347) w.r.t. the
  * LOW-resolution logits [B,H/up,W/up,Ct], labels = the int64 maps of vbg_label_paint                                       */
 VBG_API int vbg_seg_ce_bwd(const float* logits, const long long* pos_neg, const long long* cls, int B, int H, int W, int up, int Ct,

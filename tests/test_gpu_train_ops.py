@@ -156,6 +156,18 @@ def test_embed_bwd_scatter_add():
     rw = torch.zeros(V, Hd, dtype=torch.float64, device="cuda").index_add_(0, ids.long(), dx.double())
     rp = torch.zeros(Pm, Hd, dtype=torch.float64, device="cuda").index_add_(0, pos.long(), dx.double())
     assert rel(dw, rw) < 1e-5 and rel(dp, rp) < 1e-5
+    dw2, dp2 = ops.embed_bwd(dx, ids, pos, V, Pm)
+    assert torch.equal(dw, dw2) and torch.equal(dp, dp2)                 # ascending-row sums, no atomics: bitwise reproducible
+    # BERT-sized: 4128 packed rows, vocabulary 30522, a token repeated a thousand times
+    R, Hd, V, Pm = 4128, 768, 30522, 512
+    dx = torch.randn(R, Hd, device="cuda", generator=g)
+    ids = torch.randint(1000, V, (R,), device="cuda", generator=g).int()
+    ids[::4] = 1012
+    pos = (torch.arange(R, device="cuda") % 514).clamp_max(511).int()
+    dw, dp = ops.embed_bwd(dx, ids, pos, V, Pm)
+    rw = torch.zeros(V, Hd, dtype=torch.float64, device="cuda").index_add_(0, ids.long(), dx.double())
+    rp = torch.zeros(Pm, Hd, dtype=torch.float64, device="cuda").index_add_(0, pos.long(), dx.double())
+    assert rel(dw, rw) < 1e-5 and rel(dp, rp) < 1e-5
 
 
 def test_roi_align_bwd_matches_torchvision():
@@ -176,6 +188,34 @@ def test_roi_align_bwd_matches_torchvision():
     assert rel(out, ref.detach().permute(0, 2, 3, 1)) < 1e-5
     (gref,) = torch.autograd.grad(ref, fr, dout.double().permute(0, 3, 1, 2).contiguous())
     assert rel(dfeat, gref.permute(0, 2, 3, 1)) < 1e-5
+    assert torch.equal(dfeat, ops.roi_align_bwd(dout, boxes, seg_off, B, Hf, Wf, 0.25))      # gather form: no atomics, bitwise reproducible
+
+
+def test_roi_align_bwd_many_rois_per_tile_and_wide_channels():
+    """More ROIs over one 8 x 8 tile than a round of the gather kernel lists (32), page-sized ROIs (bins of > 32 pixels), a
+    document without ROIs, C = 512 (two channel slabs), map sizes that are not multiples of the tile."""
+    torchvision = pytest.importorskip("torchvision")
+    from vibertgrid_pytorch_b200 import ops
+    g = gen(9)
+    B, Hf, Wf, C, P = 3, 75, 83, 512, 7
+    counts = [70, 0, 9]
+    per = []
+    for n in counts:
+        l = torch.randint(0, 60, (n,), generator=torch.Generator().manual_seed(n)); t = torch.randint(0, 60, (n,), generator=torch.Generator().manual_seed(n + 1))
+        per.append(torch.stack([l, t, l + torch.randint(1, 270, (n,), generator=torch.Generator().manual_seed(n + 2)),
+                                t + torch.randint(1, 240, (n,), generator=torch.Generator().manual_seed(n + 3))], 1))
+    per[0][0] = torch.tensor([0, 0, Wf * 4 - 1, Hf * 4 - 1]); per[0][1] = torch.tensor([0, 0, 2000, 2000]); per[0][2] = torch.tensor([10, 10, 10, 10])
+    boxes = torch.cat(per).int().cuda()
+    seg_off = torch.tensor([0, 70, 70, 79], dtype=torch.int32, device="cuda")
+    dout = torch.randn(79, P, P, C, device="cuda", generator=g)
+    dfeat = ops.roi_align_bwd(dout, boxes, seg_off, B, Hf, Wf, 0.25)
+    fr = torch.zeros(B, C, Hf, Wf, dtype=torch.float64, device="cuda", requires_grad=True)
+    lists = [boxes[int(seg_off[b]):int(seg_off[b + 1])].double() for b in range(B)]
+    ref = torchvision.ops.roi_align(fr, lists, output_size=P, spatial_scale=0.25, sampling_ratio=-1, aligned=False)
+    (gref,) = torch.autograd.grad(ref, fr, dout.double().permute(0, 3, 1, 2).contiguous())
+    assert rel(dfeat, gref.permute(0, 2, 3, 1)) < 1e-5
+    assert float(dfeat[1].abs().max()) == 0.0
+    assert torch.equal(dfeat, ops.roi_align_bwd(dout, boxes, seg_off, B, Hf, Wf, 0.25))
 
 
 def test_seg_ce_and_upsample_backward():

@@ -96,7 +96,8 @@ SIGNATURES = {
     "vbg_grid_scatter_bwd": [_p, _ll, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "vbg_segment_reduce_bwd": [_p, _p, _p, _i, _i, _i, _p, _p],
     "vbg_embed_bwd": [_p, _p, _p, _i, _i, _p, _p, _p],
-    "vbg_roi_align_bwd": [_p, _i, _i, _i, _i, _p, _p, _i, _f, _i, _p, _p],
+    "vbg_roi_align_bwd_workspace": [_i],
+    "vbg_roi_align_bwd": [_p, _i, _i, _i, _i, _p, _p, _i, _f, _i, _p, _p, _sz, _p],
     "vbg_seg_ce_bwd": [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p],
     "vbg_upsample_split_bwd": [_p, _p, _i, _i, _i, _i, _i, _i, _p, _p],
     "vbg_small_wgrad_workspace": [_ll, _i, _i],

@@ -277,65 +277,201 @@ __global__ void segment_reduce_bwd_kernel(const float* __restrict__ dseg, const 
   }
 }
 
-// d(word table)[ids[r]] += dx[r], d(position table)[pos[r]] += dx[r]   (fp32 atomics; tables zeroed by the caller)
-__global__ void embed_bwd_kernel(const float* __restrict__ dx, const int32_t* __restrict__ ids, const int32_t* __restrict__ pos, int R, int H,
-                                 float* __restrict__ dword, float* __restrict__ dpos) {
-  const long long total = (long long)R * H;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / H), c = (int)(i - (long long)r * H);
-    const float g = __ldg(dx + i);
-    atomicAdd(dword + (size_t)__ldg(ids + r) * H + c, g);
-    atomicAdd(dpos + (size_t)__ldg(pos + r) * H + c, g);
+// d(word table)[ids[r]] += dx[r], d(position table)[pos[r]] += dx[r]   (tables zeroed by the caller).  DETERMINISTIC, no atomics:
+// the CTA of row r owns table row key = idx[r] iff r is the FIRST packed row with that key (a scan of idx[0, r)); the owner then
+// sums dx[j] over every j >= r with idx[j] == key in ascending j (matches compacted in order by warp ballots), and stores the row.
+// blockIdx.y = 0: word table through ids, 1: position table through pos.  O(R^2) integer compares per table -- R is a few
+// thousand packed rows -- against R * H floats of real traffic.
+__global__ void __launch_bounds__(256)
+embed_bwd_kernel(const float* __restrict__ dx, const int32_t* __restrict__ ids, const int32_t* __restrict__ pos, int R, int H,
+                 float* __restrict__ dword, float* __restrict__ dpos) {
+  const int32_t* __restrict__ idx = blockIdx.y ? pos : ids;
+  float* __restrict__ out = blockIdx.y ? dpos : dword;
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int key = __ldg(idx + r);
+  int seen = 0;
+  for (int j = tid; j < r; j += blockDim.x) seen |= (__ldg(idx + j) == key);
+  if (__syncthreads_or(seen)) return;                      // an earlier row owns this table row
+  __shared__ int list[256];
+  __shared__ int wcnt[8];
+  const int H4 = H >> 2;
+  float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};       // H <= 2048: two float4 per thread
+  for (int base = r; base < R; base += blockDim.x) {
+    const int j = base + tid;
+    const bool hit = j < R && __ldg(idx + j) == key;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int w = 0; w < nwarp; ++w) { const int c = wcnt[w]; if (w < warp) before += c; total += c; }
+    if (hit) list[before + __popc(bal & ((1u << lane) - 1u))] = j;
+    __syncthreads();
+    for (int e = 0; e < total; ++e) {
+      const float4* src = reinterpret_cast<const float4*>(dx + (size_t)list[e] * H);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = tid + u * blockDim.x;
+        if (c < H4) { const float4 v = __ldg(src + c); acc[u].x += v.x; acc[u].y += v.y; acc[u].z += v.z; acc[u].w += v.w; }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int c = tid + u * blockDim.x;
+    if (c < H4) reinterpret_cast<float4*>(out + (size_t)key * H)[c] = acc[u];
   }
 }
 
-// ------------------------------------------------------------------ ROI-align backward
-// One warp per (roi, bin), lanes over channel float4s: every sample scatters w_tap * dOut / count into its four taps.
-__global__ void __launch_bounds__(256)
-roi_align_bwd_kernel(const float* __restrict__ dout, int B, int Hf, int Wf, int C, const int32_t* __restrict__ boxes, const int32_t* __restrict__ seg_off,
-                     int K, float scale, int P, float* __restrict__ dfeat) {
-  const int lane = threadIdx.x & 31;
-  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long total = (long long)K * P * P;
-  if (warp >= total) return;
-  const int k = (int)(warp / (P * P));
-  const int bin = (int)(warp - (long long)k * P * P);
-  const int ph = bin / P, pw = bin - ph * P;
-  const int b = sample_of(seg_off, B, k);
+// ------------------------------------------------------------------ ROI-align backward (deterministic gather form)
+// dfeat[b, y, x, :] = sum over the ROIs k of document b (ascending k), bins (ph, pw):  Wy_k[ph](y) * Wx_k[pw](x) / count_k * dout[k, ph, pw, :]
+// where Wy_k[ph](y) = the summed bilinear row weights of bin ph's samples on feature row y (torchvision's sampling rule, the
+// forward's arithmetic operation for operation).  A CTA owns an 8 x 8 tile of feature pixels of one document: it lists the ROIs
+// whose sample window meets the tile (ascending k), builds for each the 7 x 8 row weights and 7 x 8 column weights of ITS rows /
+// columns straight from the sample coordinates (only the few samples near a row can touch it, so no per-ROI table of bounded
+// span is needed: any ROI size takes this path), and accumulates -- every pixel is written exactly once: no atomics, no
+// zero-fill, bitwise reproducible.  (torchvision's CUDA backward, like round 1's kernel, scatters with atomics.)
+struct RoiGeo { float sh, sw, bh, bw, inv_count; int gh, gw, y_lo, y_hi, x_lo, x_hi, pad; };
+
+__global__ void roi_geo_kernel(const int32_t* __restrict__ boxes, int K, float scale, int P, int Hf, int Wf, RoiGeo* __restrict__ geo) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
   const int4 bx = __ldg(reinterpret_cast<const int4*>(boxes) + k);
-  const float sw = __fmul_rn((float)bx.x, scale), sh = __fmul_rn((float)bx.y, scale);
+  RoiGeo g;
+  g.sw = __fmul_rn((float)bx.x, scale); g.sh = __fmul_rn((float)bx.y, scale);
   const float ew = __fmul_rn((float)bx.z, scale), eh = __fmul_rn((float)bx.w, scale);
-  const float rw = fmaxf(__fsub_rn(ew, sw), 1.0f), rh = fmaxf(__fsub_rn(eh, sh), 1.0f);
-  const float bw = __fdiv_rn(rw, (float)P), bh = __fdiv_rn(rh, (float)P);
-  const int gh = (int)ceilf(__fdiv_rn(rh, (float)P));
-  const int gw = (int)ceilf(__fdiv_rn(rw, (float)P));
-  const float inv_count = 1.0f / (float)max(gh * gw, 1);
+  const float rw = fmaxf(__fsub_rn(ew, g.sw), 1.0f), rh = fmaxf(__fsub_rn(eh, g.sh), 1.0f);
+  g.bw = __fdiv_rn(rw, (float)P); g.bh = __fdiv_rn(rh, (float)P);
+  g.gh = (int)ceilf(__fdiv_rn(rh, (float)P));
+  g.gw = (int)ceilf(__fdiv_rn(rw, (float)P));
+  g.inv_count = 1.0f / (float)max(g.gh * g.gw, 1);
+  // rows / columns any sample can touch (first and last sample coordinate of each axis; the +1 row of the bilinear pair)
+  const float y_first = __fadd_rn(g.sh, __fdiv_rn(__fmul_rn(0.5f, g.bh), (float)g.gh));
+  const float y_last = __fadd_rn(__fadd_rn(g.sh, __fmul_rn((float)(P - 1), g.bh)), __fdiv_rn(__fmul_rn((float)g.gh - 0.5f, g.bh), (float)g.gh));
+  const float x_first = __fadd_rn(g.sw, __fdiv_rn(__fmul_rn(0.5f, g.bw), (float)g.gw));
+  const float x_last = __fadd_rn(__fadd_rn(g.sw, __fmul_rn((float)(P - 1), g.bw)), __fdiv_rn(__fmul_rn((float)g.gw - 0.5f, g.bw), (float)g.gw));
+  g.y_lo = min(max((int)fmaxf(y_first, 0.f), 0), Hf - 1); g.y_hi = min(max((int)fmaxf(y_last, 0.f) + 1, g.y_lo), Hf - 1);
+  g.x_lo = min(max((int)fmaxf(x_first, 0.f), 0), Wf - 1); g.x_hi = min(max((int)fmaxf(x_last, 0.f) + 1, g.x_lo), Wf - 1);
+  g.pad = 0;
+  geo[k] = g;
+}
+
+// summed weight of bin `pb`'s samples on row / column `t` of an axis of size `dim` (start, bin size, samples per bin as in the forward)
+__device__ __forceinline__ float roi_axis_weight(float start, float bin, int g, int pb, int t, int dim) {
+  const float s0 = __fadd_rn(start, __fmul_rn((float)pb, bin));
+  // candidate samples: coordinates within (t - 1, t + 1), widened for the clamped edges and by a safety margin of two samples
+  const float inv_step = (float)g / bin;
+  const float lo_c = (t == 0 ? -1.5f : (float)t - 1.0f), hi_c = (t == dim - 1 ? (float)dim + 0.5f : (float)t + 1.0f);
+  int i0 = (int)floorf((lo_c - s0) * inv_step - 0.5f) - 2, i1 = (int)ceilf((hi_c - s0) * inv_step - 0.5f) + 2;
+  i0 = max(i0, 0); i1 = min(i1, g - 1);
+  float w = 0.f;
+  for (int i = i0; i <= i1; ++i) {
+    float c = __fadd_rn(s0, __fdiv_rn(__fmul_rn((float)i + 0.5f, bin), (float)g));
+    if (c < -1.0f || c > (float)dim) continue;
+    c = fmaxf(c, 0.f);
+    int lo = (int)c, hi;
+    if (lo >= dim - 1) { hi = lo = dim - 1; c = (float)lo; } else { hi = lo + 1; }
+    const float l = c - (float)lo, h = 1.f - l;
+    if (lo == t) w += h;
+    if (hi == t) w += l;
+  }
+  return w;
+}
+
+constexpr int kRbT = 8;          // tile edge (feature pixels)
+constexpr int kRbMax = 32;       // ROIs processed per round of a tile
+__global__ void __launch_bounds__(256)
+roi_align_bwd_kernel(const float* __restrict__ dout, int B, int Hf, int Wf, int C, const int32_t* __restrict__ seg_off, const RoiGeo* __restrict__ geo,
+                     int P, float* __restrict__ dfeat) {
+  __shared__ int list[kRbMax];
+  __shared__ int n_list, next_k;
+  __shared__ float wy[kRbMax][8][kRbT], wx[kRbMax][8][kRbT];       // [roi][bin][tile row / column]; bin index 7 unused
+  const int b = blockIdx.z, ty0 = blockIdx.y * kRbT, tx0 = blockIdx.x * kRbT, tid = threadIdx.x;
+  const int k_begin = __ldg(seg_off + b), k_end = __ldg(seg_off + b + 1);
   const int C4 = C >> 2;
-  const size_t f0 = (size_t)b * Hf * Wf * C;
-  const float4* g4 = reinterpret_cast<const float4*>(dout) + (size_t)warp * C4;
-  for (int iy = 0; iy < gh; ++iy) {
-    const float y = __fadd_rn(__fadd_rn(sh, __fmul_rn((float)ph, bh)), __fdiv_rn(__fmul_rn((float)iy + 0.5f, bh), (float)gh));
-    for (int ix = 0; ix < gw; ++ix) {
-      const float x = __fadd_rn(__fadd_rn(sw, __fmul_rn((float)pw, bw)), __fdiv_rn(__fmul_rn((float)ix + 0.5f, bw), (float)gw));
-      if (y < -1.0f || y > (float)Hf || x < -1.0f || x > (float)Wf) continue;
-      float yy = fmaxf(y, 0.f), xx = fmaxf(x, 0.f);
-      int yl = (int)yy, xl = (int)xx, yh, xh;
-      if (yl >= Hf - 1) { yh = yl = Hf - 1; yy = (float)yl; } else { yh = yl + 1; }
-      if (xl >= Wf - 1) { xh = xl = Wf - 1; xx = (float)xl; } else { xh = xl + 1; }
-      const float ly = yy - (float)yl, lx = xx - (float)xl, hy = 1.f - ly, hx = 1.f - lx;
-      const float w1 = hy * hx * inv_count, w2 = hy * lx * inv_count, w3 = ly * hx * inv_count, w4 = ly * lx * inv_count;
-      float* p1 = dfeat + f0 + ((size_t)yl * Wf + xl) * C;
-      float* p2 = dfeat + f0 + ((size_t)yl * Wf + xh) * C;
-      float* p3 = dfeat + f0 + ((size_t)yh * Wf + xl) * C;
-      float* p4 = dfeat + f0 + ((size_t)yh * Wf + xh) * C;
-      for (int c = lane; c < C4; c += 32) {
-        const float4 g = __ldg(g4 + c);
-        atomicAdd(reinterpret_cast<float4*>(p1) + c, make_float4(w1 * g.x, w1 * g.y, w1 * g.z, w1 * g.w));
-        atomicAdd(reinterpret_cast<float4*>(p2) + c, make_float4(w2 * g.x, w2 * g.y, w2 * g.z, w2 * g.w));
-        atomicAdd(reinterpret_cast<float4*>(p3) + c, make_float4(w3 * g.x, w3 * g.y, w3 * g.z, w3 * g.w));
-        atomicAdd(reinterpret_cast<float4*>(p4) + c, make_float4(w4 * g.x, w4 * g.y, w4 * g.z, w4 * g.w));
+  const int quads_per_round = 256 / 4;                    // 64 channel quads x 4 pixel groups
+  const int pg = tid >> 6, q0 = tid & 63;
+  // each thread owns pixels pg, pg + 4, ... of the tile (16 pixels) for channel quads q0, q0 + 64, ... : accumulators in registers
+  // for C <= 256 (one quad per thread); larger C loops the whole tile again per 256-channel slab
+  for (int cbase = 0; cbase < C4; cbase += quads_per_round) {
+    const int cq = cbase + q0;
+    float4 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid == 0) next_k = k_begin;
+    __syncthreads();
+    while (true) {
+      // ---- list up to kRbMax ROIs (ascending k) whose window meets the tile: one warp scans with ballots
+      if (tid < 32) {
+        int cnt = 0, k = next_k;
+        while (k < k_end && cnt < kRbMax) {
+          const int kk = k + tid;
+          bool hit = false;
+          if (kk < k_end) {
+            const RoiGeo g = geo[kk];
+            hit = g.y_lo < ty0 + kRbT && g.y_hi >= ty0 && g.x_lo < tx0 + kRbT && g.x_hi >= tx0;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          const int room = kRbMax - cnt;
+          const int npop = __popc(bal);
+          if (npop <= room) {
+            if (hit) list[cnt + __popc(bal & ((1u << tid) - 1u))] = kk;
+            cnt += npop; k += 32;
+          } else {                                   // take the first `room` hits only; resume after the last one taken
+            const int rank = __popc(bal & ((1u << tid) - 1u));
+            if (hit && rank < room) list[cnt + rank] = kk;
+            int last = 0;
+            for (int l = 0, seen = 0; l < 32; ++l) if ((bal >> l) & 1u) { if (++seen == room) { last = l; break; } }
+            cnt += room; k += last + 1;
+          }
+        }
+        if (tid == 0) { n_list = cnt; next_k = k; }
+      }
+      __syncthreads();
+      const int n = n_list;
+      if (n == 0) break;
+      // ---- row / column weights of the listed ROIs for this tile's rows and columns
+      for (int item = tid; item < n * 2 * 7 * kRbT; item += 256) {
+        const int t = item % kRbT, pb = (item / kRbT) % 7, axis = (item / (kRbT * 7)) & 1, li = item / (kRbT * 7 * 2);
+        const RoiGeo g = geo[list[li]];
+        if (axis) wy[li][pb][t] = ty0 + t < Hf ? roi_axis_weight(g.sh, g.bh, g.gh, pb, ty0 + t, Hf) * g.inv_count : 0.f;
+        else wx[li][pb][t] = tx0 + t < Wf ? roi_axis_weight(g.sw, g.bw, g.gw, pb, tx0 + t, Wf) : 0.f;
+      }
+      __syncthreads();
+      // ---- accumulate
+      if (cq < C4) {
+        for (int li = 0; li < n; ++li) {
+          const float4* g4 = reinterpret_cast<const float4*>(dout) + (size_t)list[li] * P * P * C4 + cq;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int pix = pg + 4 * i, ty = pix >> 3, tx = pix & 7;
+#pragma unroll 1
+            for (int ph = 0; ph < 7; ++ph) {
+              const float a = wy[li][ph][ty];
+              if (a == 0.f) continue;
+#pragma unroll 1
+              for (int pw = 0; pw < 7; ++pw) {
+                const float w = a * wx[li][pw][tx];
+                if (w == 0.f) continue;
+                const float4 v = __ldg(g4 + (size_t)(ph * 7 + pw) * C4);
+                acc[i].x = fmaf(w, v.x, acc[i].x); acc[i].y = fmaf(w, v.y, acc[i].y);
+                acc[i].z = fmaf(w, v.z, acc[i].z); acc[i].w = fmaf(w, v.w, acc[i].w);
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();
+      if (n < kRbMax) break;
+    }
+    if (cq < C4) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int pix = pg + 4 * i, y = ty0 + (pix >> 3), x = tx0 + (pix & 7);
+        if (y < Hf && x < Wf) reinterpret_cast<float4*>(dfeat)[(((size_t)b * Hf + y) * Wf + x) * C4 + cq] = acc[i];
       }
     }
+    __syncthreads();
   }
 }
 
@@ -682,19 +818,26 @@ extern "C" int vbg_segment_reduce_bwd(const float* dseg, const int32_t* tok_row,
 
 extern "C" int vbg_embed_bwd(const float* dx, const int32_t* ids, const int32_t* pos, int R, int hidden, float* dword, float* dpos,
                              vbg_stream_t stream) {
-  VBG_REQUIRE(dx && ids && pos && dword && dpos && R > 0 && hidden > 0, "vbg_embed_bwd: bad arguments");
-  embed_bwd_kernel<<<grid_for((long long)R * hidden, 256), 256, 0, as_stream(stream)>>>(dx, ids, pos, R, hidden, dword, dpos);
+  VBG_REQUIRE(dx && ids && pos && dword && dpos && R > 0 && hidden > 0 && hidden % 4 == 0 && hidden <= 2048 && aligned16(dx) &&
+                  aligned16(dword) && aligned16(dpos),
+              "vbg_embed_bwd: hidden %% 4 == 0, hidden <= 2048, 16B-aligned pointers");
+  embed_bwd_kernel<<<dim3((unsigned)R, 2), 256, 0, as_stream(stream)>>>(dx, ids, pos, R, hidden, dword, dpos);
   return check_launch("vbg_embed_bwd");
 }
 
+extern "C" long long vbg_roi_align_bwd_workspace(int K) { return (long long)(K > 0 ? K : 1) * (long long)sizeof(RoiGeo); }
+
 extern "C" int vbg_roi_align_bwd(const float* dout, int B, int Hf, int Wf, int C, const int32_t* boxes, const int32_t* seg_off, int K, float scale,
-                                 int P, float* dfeat, vbg_stream_t stream) {
-  VBG_REQUIRE(dout && boxes && seg_off && dfeat && B > 0 && Hf > 0 && Wf > 0 && C % 4 == 0 && K >= 0 && P > 0 && aligned16(dout) &&
-                  aligned16(dfeat) && aligned16(boxes),
+                                 int P, float* dfeat, void* workspace, size_t ws_bytes, vbg_stream_t stream) {
+  VBG_REQUIRE(dout && boxes && seg_off && dfeat && workspace && B > 0 && Hf > 0 && Wf > 0 && C % 4 == 0 && K >= 0 && aligned16(dout) &&
+                  aligned16(dfeat) && aligned16(boxes) && aligned16(workspace),
               "vbg_roi_align_bwd: C %% 4 == 0, 16B-aligned pointers");
-  if (K == 0) return VBG_OK;
-  const long long warps = (long long)K * P * P;
-  roi_align_bwd_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, as_stream(stream)>>>(dout, B, Hf, Wf, C, boxes, seg_off, K, scale, P, dfeat);
+  VBG_REQUIRE(P == 7, "vbg_roi_align_bwd: 7 x 7 bins only (got %d)", P);
+  if ((size_t)vbg_roi_align_bwd_workspace(K) > ws_bytes) { set_error("vbg_roi_align_bwd: workspace of %lld bytes needed", vbg_roi_align_bwd_workspace(K)); return VBG_EWORKSPACE; }
+  cudaStream_t s = as_stream(stream);
+  RoiGeo* geo = reinterpret_cast<RoiGeo*>(workspace);
+  if (K > 0) roi_geo_kernel<<<cdiv(K, 128), 128, 0, s>>>(boxes, K, scale, P, Hf, Wf, geo);
+  roi_align_bwd_kernel<<<dim3(cdiv(Wf, kRbT), cdiv(Hf, kRbT), B), 256, 0, s>>>(dout, B, Hf, Wf, C, seg_off, geo, P, dfeat);
   return check_launch("vbg_roi_align_bwd");
 }
 

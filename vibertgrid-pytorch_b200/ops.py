@@ -750,9 +750,11 @@ def embed_bwd(dx, ids, pos, vocab, max_pos):
 
 def roi_align_bwd(dout, boxes, seg_off, B, Hf, Wf, spatial_scale):
     K, Pp, _, Cc = dout.shape
-    dfeat = torch.zeros((B, Hf, Wf, Cc), dtype=torch.float32, device=dout.device)
+    dfeat = torch.empty((B, Hf, Wf, Cc), dtype=torch.float32, device=dout.device)        # every pixel is written by the kernel
+    nb = int(L.load().vbg_roi_align_bwd_workspace(K))
+    ws = torch.empty(nb, dtype=torch.uint8, device=dout.device)
     L.check(L.load().vbg_roi_align_bwd(_f32(dout), B, Hf, Wf, Cc, _i32(boxes), _i32(seg_off), K, spatial_scale, Pp, _f32(dfeat),
-                                       _stream()), "vbg_roi_align_bwd")
+                                       _p(ws), nb, _stream()), "vbg_roi_align_bwd")
     return dfeat
 
 
