@@ -289,6 +289,10 @@ VBG_API int vbg_expand2x(const float* x, int B, int Hi, int Wi, int C, int H, in
 VBG_API int vbg_gelu(const float* x, const float* dy, long long n, float* out, vbg_stream_t stream);
 /* inverted dropout with a counter-based mask: y[i] = x[i] * keep(seed, i) / (1 - p); the same call is its own backward */
 VBG_API int vbg_dropout(const float* x, long long n, float p, unsigned long long seed, float* y, vbg_stream_t stream);
+/* 31-bit sampling keys key[i] = hash(seed, step_seed, i) for the device-side sampled / OHEM losses (pipeline/custom_loss.py:9-382
+ * restated without host randomness: an element is kept iff its key is among the k smallest of its group) */
+VBG_API int vbg_uniform_keys(long long n, unsigned long long seed, const unsigned long long* step_seed /* device, or NULL */,
+                     int32_t* out, vbg_stream_t stream);
 /* the same with an optional DEVICE word `step_seed` folded into the seed at run time: a captured CUDA graph bakes the by-value
  * seed of each call site; the host refreshes the one device word before every replay, so each step draws new masks */
 VBG_API int vbg_dropout_ds(const float* x, long long n, float p, unsigned long long seed, const unsigned long long* step_seed,

@@ -54,7 +54,8 @@ def _bn(x, gamma, beta, residual, relu, eps, stats, sync=None):
     return y
 
 
-def _attention(qkv, cu, nseq, max_len, heads):
+def _attention(qkv, cu, nseq, max_len, heads, p_drop=0.0, seed=0, step_seed=None):
+    assert p_drop == 0.0, "the stand-in has no attention dropout (tests zero it)"
     hid = qkv.shape[1] // 3
     d = hid // heads
     outs = []
@@ -118,7 +119,7 @@ MaxPoolF = _Apply(lambda x: _nhwc(F.max_pool2d(_nchw(x), 3, 2, 1)))
 AvgPoolF = _Apply(lambda x: _nhwc(F.avg_pool2d(_nchw(x), 2, 2)))
 Up2F = _Apply(lambda x: x.repeat_interleave(2, 1).repeat_interleave(2, 2))
 GeluF = _Apply(F.gelu)
-DropoutF = _Apply(lambda t, p, seed: t if p == 0.0 else F.dropout(t, p, True))
+DropoutF = _Apply(lambda t, p, seed, step_seed=None: t if p == 0.0 else F.dropout(t, p, True))
 LayerNormPS = _Apply(lambda x, g, b, eps: F.layer_norm(x, (x.shape[-1],), g, b, eps))
 AttentionF = _Apply(_attention)
 EmbedSumF = _Apply(lambda word, position, type_emb, ids, pos: word[ids.long()] + position[pos.long()] + type_emb[0])

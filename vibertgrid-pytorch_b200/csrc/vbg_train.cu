@@ -918,3 +918,26 @@ extern "C" int vbg_stem_wgrad(const float* x4, const float* dy, int B, int Hp, i
   sum_slabs_kernel<<<grid_for(64 * kStemCols, 256), 256, 0, s>>>(workspace, nblk, 64 * kStemCols, dw774);
   return check_launch("vbg_stem_wgrad");
 }
+
+// ------------------------------------------------------------------ sampling keys of the device-side sampled / OHEM losses
+// key[i] = 31-bit hash of (seed, i): "element i is kept iff its key is among the k smallest of its group" (losses_device.py) --
+// uniform k-subsets without host randomness, so the loss tail needs no device->host sync and can live in a CUDA graph
+// (step_seed: the device word refreshed per replay, see vbg_dropout_ds).
+namespace vbg {
+__global__ void uniform_keys_kernel(long long n, unsigned long long seed, const unsigned long long* __restrict__ step_seed, int32_t* __restrict__ out) {
+  if (step_seed) seed ^= __ldg(step_seed) * 0xD6E8FEB86659FD93ull;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    unsigned long long z = seed + (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    out[i] = (int32_t)(z >> 33);
+  }
+}
+}  // namespace vbg
+
+extern "C" int vbg_uniform_keys(long long n, unsigned long long seed, const unsigned long long* step_seed, int32_t* out, vbg_stream_t stream) {
+  VBG_REQUIRE(out && n > 0, "vbg_uniform_keys: bad arguments");
+  vbg::uniform_keys_kernel<<<vbg::grid_for(n, 1024), 256, 0, vbg::as_stream(stream)>>>(n, seed, step_seed, out);
+  return vbg::check_launch("vbg_uniform_keys");
+}

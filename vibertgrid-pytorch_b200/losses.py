@@ -100,13 +100,20 @@ def _w(net, like):
     return None if net.loss_weights is None else net.loss_weights.to(like.device)
 
 
-def aux_loss(net, out):
+def aux_loss(net, out, ctx=None):
+    """``ctx``: a losses_device.SamplingCtx selects the sync-free device-side sampling (simp head); None = the reference's own
+    host-side draws (Python ``random``), bit-compatible with its RNG consumption."""
     cfg = net.loss_cfg
     if "aux_ce" in out:                 # fused kernel (vbg_seg_ce_loss): [mean CE mask head, mean CE class head]
         return out["aux_ce"][0] + out["aux_ce"][1]
     pm, ps = out["pred_mask"], out["pred_ss"]
-    l1 = ce_random_sample(pm, out["pos_neg_labels"], cfg["aux_sample_list"])
     n_pos, n_neg = cfg["aux"]
+    if ctx is not None and net.classifier_mode == "simp":
+        from . import losses_device as D
+        l1 = D.ce_random_sample(pm.permute(0, 2, 3, 1).reshape(-1, pm.shape[1]), out["pos_neg_labels"].reshape(-1), cfg["aux_sample_list"], ctx=ctx)
+        l2 = D.ce_ohem(ps.permute(0, 2, 3, 1).reshape(-1, ps.shape[1]), out["class_labels"].reshape(-1), n_pos, n_neg, weight=_w(net, ps), ctx=ctx)
+        return l1 + l2
+    l1 = ce_random_sample(pm, out["pos_neg_labels"], cfg["aux_sample_list"])
     if net.classifier_mode == "simp":
         l2 = ce_ohem(ps, out["class_labels"], n_pos, n_neg, weight=_w(net, ps))
         return l1 + l2
@@ -122,12 +129,17 @@ def aux_loss(net, out):
     return l1 + l2
 
 
-def main_loss(net, out):
+def main_loss(net, out, ctx=None):
     cfg = net.loss_cfg
     label = out["gt_label"].long()
     if net.classifier_mode == "simp":
         p1, n1 = cfg["main_1"]
         p2, n2 = cfg["main_2"]
+        if ctx is not None:
+            from . import losses_device as D
+            l_pn = D.ce_ohem(out["pos_neg_logits"], (label > 0).long(), p1, n1, rnd=cfg["random"], ctx=ctx) if net.add_pos_neg else None
+            l_c = D.ce_ohem(out["logits"], label, p2, n2, weight=_w(net, out["logits"]), rnd=cfg["random"], ctx=ctx)
+            return l_pn + l_c if net.add_pos_neg else l_c
         l_pn = ce_ohem(out["pos_neg_logits"], (label > 0).long(), p1, n1, rnd=cfg["random"])
         l_c = ce_ohem(out["logits"], label, p2, n2, weight=_w(net, out["logits"]), rnd=cfg["random"])
         return l_pn + l_c if net.add_pos_neg else l_c

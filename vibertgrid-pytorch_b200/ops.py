@@ -717,6 +717,13 @@ def gelu(x, dy=None):
     return out
 
 
+def uniform_keys(n, seed, step_seed, device):
+    """int32 [n] of 31-bit hash keys (sampling keys of losses_device.py)."""
+    out = torch.empty(int(n), dtype=torch.int32, device=device)
+    L.check(L.load().vbg_uniform_keys(int(n), int(seed), _u64ptr(step_seed), _i32(out), _stream()), "vbg_uniform_keys")
+    return out
+
+
 def dropout(x, p, seed, step_seed=None):
     y = torch.empty_like(x)
     L.check(L.load().vbg_dropout_ds(_f32(x), x.numel(), p, seed, _u64ptr(step_seed), _f32(y), _stream()), "vbg_dropout")

@@ -246,15 +246,26 @@ class TrainEngine:
             return False
         if net.classifier_mode != "simp" or net.loss_weights is not None:
             return False                     # full / crf: the two-stage auxiliary head and the gated heads index by device masks
-        if cfg["aux_sample_list"] is not None or tuple(cfg["aux"]) != (-1, -1):
-            return False
-        if any(int(v) >= 0 and int(v) < (1 << 20) for v in tuple(cfg["main_1"]) + tuple(cfg["main_2"])):
-            return False
+        if self._sampled_losses() and not self._device_sampling(dev):
+            return False                     # host-side draws (Python `random`) and data-dependent shapes cannot be captured
         if any(self._sync_group(m) is not None for m in net.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)):
             return False
         if any(m.momentum is None for m in net.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)):
             return False                     # cumulative moving average: the factor is read back from the step counter
         return True
+
+    def _sampled_losses(self):
+        cfg = self.net.loss_cfg
+        return not (cfg["aux_sample_list"] is None and tuple(cfg["aux"]) == (-1, -1)
+                    and all(int(v) == -1 or int(v) >= (1 << 20) for v in tuple(cfg["main_1"]) + tuple(cfg["main_2"])))
+
+    def _device_sampling(self, dev):
+        """Sampled / OHEM losses drawn on the device (losses_device.py: no host randomness, no syncs, capturable) -- the default
+        for the `simp` head on a GPU; ``net.loss_sampling = "host"`` keeps the reference's own Python-``random`` draws."""
+        from . import losses_device
+        net = self.net
+        return (dev.type == "cuda" and not getattr(self, "_test_standins", False) and net.classifier_mode == "simp"
+                and getattr(net, "loss_sampling", "device") == "device" and losses_device.supported(net.loss_cfg))
 
     def loss(self, image, seg_indices, seg_classes, coors, corpus, mask):
         net = self.net
@@ -390,6 +401,10 @@ class TrainEngine:
         Bs, Hs, Ws, Cs = s.shape
         lg = A.linear(s.reshape(Bs * Hs * Ws, Cs), seg_w, seg_b).view(Bs, Hs, Ws, -1)
         from . import losses
+        ctx = None
+        if self._sampled_losses() and self._device_sampling(dev):
+            from .losses_device import SamplingCtx
+            ctx = SamplingCtx(getattr(self, "_step_seed", None), base_seed=_rand_seed() & 0xFFFFFFFF)
         if default_aux:
             aux = A.SegCEF.apply(lg, boxes, seg_off, cls_cat, B, plan.H, plan.W, net.p_fuse_downsampling_ratio, 3)
             loss_aux = aux[0] + aux[1]
@@ -400,7 +415,7 @@ class TrainEngine:
                                                    mode="nearest")
             pos_neg_labels, class_labels = ops.label_paint(boxes, seg_off, cls_cat, B, plan.H, plan.W)
             loss_aux = losses.aux_loss(net, {"pred_mask": full[:, :3], "pred_ss": full[:, 3:],
-                                             "pos_neg_labels": pos_neg_labels, "class_labels": class_labels})
+                                             "pos_neg_labels": pos_neg_labels, "class_labels": class_labels}, ctx)
 
         # a7 / a8 ROI align, late fusion
         roi = A.RoiAlignF.apply(p_fuse, boxes, seg_off, 1.0 / float(net.p_fuse_downsampling_ratio), net.roi_shape)
@@ -428,7 +443,7 @@ class TrainEngine:
             out["logits"] = mlp(head.category_classification_net, late)
             if hasattr(head, "pos_neg_classification_net"):
                 out["pos_neg_logits"] = mlp(head.pos_neg_classification_net, late)
-            loss_c = losses.main_loss(net, out)
+            loss_c = losses.main_loss(net, out, ctx)
         elif net.classifier_mode == "crf":
             # field_type_classification_head.py:683-699: emissions, then the mean over samples of the per-sample NLL
             feats = mlp(head.category_classification_net, late)
