@@ -108,6 +108,16 @@ def attention(qkv, cu, nseq, max_len, heads, precision=0):
     return out
 
 
+def mask_check(mask, tok_off, status):
+    to = tok_off.numpy()
+    for b in range(mask.shape[0]):
+        n = int(to[b + 1] - to[b])
+        want = torch.zeros(mask.shape[1], dtype=mask.dtype)
+        want[:n] = 1
+        if not torch.equal(mask[b].ne(0), want.ne(0)):
+            status |= 4
+
+
 def segment_starts(seg_ids, tok_off, B, K, status):
     starts = []
     to = tok_off.numpy()
