@@ -75,7 +75,17 @@ typedef struct vbg_epilogue {
   long long out_plane;   /* VBG_OUT_SPLIT_BF16: elements between the hi and the lo plane */
   long long res_plane;   /* > 0: `residual` points at the bf16 hi plane of a split activation (same indexing), the lo
                             plane res_plane elements later (tensor-core paths only); 0: residual is float */
+  int tune;              /* VBG_TUNE_* bits, 0 = the library's own tile / pipeline heuristics (what ships) */
 } vbg_epilogue_t;
+
+/* Per-call overrides of the pre-split tensor-core kernels' variant choice (vbg_gemm_ps / vbg_conv2d_ps and their
+ * *_workspace queries).  The library reads no environment variable and keeps no mutable tuning state: a sweep or a
+ * parity test that wants a specific variant says so in the call. */
+enum { VBG_TUNE_KB32 = 1,      /* 32-element K ring stages (SWIZZLE_64B) instead of 64 (SWIZZLE_128B)        */
+       VBG_TUNE_PAIRS_OFF = 2, /* never use CTA-pair (cta_group::2) tiles                                    */
+       VBG_TUNE_PAIRS_ON = 4,  /* CTA-pair tiles whenever the problem has two row tiles                      */
+       VBG_TUNE_SPLITK = 8,    /* allow split-K work units for under-filled grids (needs the workspace)      */
+       VBG_TUNE_NO_PDL = 16    /* launch without programmatic stream serialization                           */ };
 
 VBG_API int vbg_version(void);
 /* copies the calling thread's last error text into buf (NUL terminated); returns its length */
@@ -186,9 +196,9 @@ VBG_API int vbg_conv2d_ps(const void* x_hi, long long x_plane, int B, int H, int
  * (tile, K-range) work units whose fp32 partial tiles go to `workspace` and are summed in a fixed order by a finishing
  * kernel that applies the epilogue (deterministic).  These return the workspace bytes such a call can use (0 = the shape
  * never splits); passing NULL / fewer bytes just disables the split.  Host-only arithmetic, no device work.  Opt-in via
- * VBG_PS_SPLITK=1 (measured slower than the CTA-pair tiles at the BASELINE shapes, so off by default: these return 0). */
-VBG_API long long vbg_gemm_ps_workspace(int M, int N, int K);
-VBG_API long long vbg_conv2d_ps_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad);
+ * VBG_TUNE_SPLITK in `tune` (measured slower than the CTA-pair tiles at the BASELINE shapes: without it these return 0). */
+VBG_API long long vbg_gemm_ps_workspace(int M, int N, int K, int tune);
+VBG_API long long vbg_conv2d_ps_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int tune);
 /* Tuning aid: when dev_buf (>= 16 int64, device memory) is non-NULL, CTA 0 of every following CTA-pair GEMM launch writes
  * clock64 stamps of its pipeline milestones into it (entry, setup done, first TMA issued, first operands landed, last MMA
  * committed, epilogue start / end, exit).  NULL (the default) disables it.  Not thread safe; never used on the hot path. */

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Tuning experiment: pre-split bf16x3 GEMM / conv (TMA-fed planes) vs the fp32-A converter kernel, per ring-stage
-variant (VBG_PS_KB = 64: SWIZZLE_128B, 32: SWIZZLE_64B) and per forced N tile (VBG_TC3_BN)."""
+variant (ops.TUNE: 64-element K stages / SWIZZLE_128B, single-CTA or CTA-pair tiles; TUNE_KB32: 32 / SWIZZLE_64B)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -24,7 +24,7 @@ for (M, N, K) in GEMMS:
     ms = timed(lambda: ops.gemm(A, W, ep=ep, precision=ops.PREC_BF16X3, W_split=Ws))
     line = f"[gemm {M}x{N}x{K}] fp32-A {ms*1e3:7.1f} us {2.0*M*N*K/ms/1e9:6.1f} TF/s |"
     for kb, cg in (("64", "0"), ("64", "1"), ("32", "0")):
-        os.environ["VBG_PS_KB"] = kb; os.environ["VBG_PS_CG2"] = cg
+        ops.TUNE = (ops.TUNE_KB32 if kb == "32" else 0) | (ops.TUNE_PAIRS_ON if cg == "1" else ops.TUNE_PAIRS_OFF)
         ms = timed(lambda: ops.gemm(As, W, ep=ep, precision=ops.PREC_BF16X3, W_split=Ws, split_out=True))
         line += f" ps{kb}{'x2' if cg == '1' else ''} {ms*1e3:7.1f} us {2.0*M*N*K/ms/1e9:6.1f} TF/s |"
     print(line, flush=True)
@@ -40,7 +40,7 @@ for (B, H, Wd, Cin, Cout, k, s) in CONVS:
     ms = timed(lambda: ops.conv2d(x, w, s, 1, ep=ep, precision=ops.PREC_BF16X3, W_split=ws))
     line = f"[conv B{B} {H}x{Wd} {Cin}->{Cout} k{k} s{s}] fp32-A {ms*1e3:7.1f} us {fl/ms/1e9:6.1f} TF/s |"
     for kb, cg in (("64", "0"), ("64", "1"), ("32", "0")):
-        os.environ["VBG_PS_KB"] = kb; os.environ["VBG_PS_CG2"] = cg
+        ops.TUNE = (ops.TUNE_KB32 if kb == "32" else 0) | (ops.TUNE_PAIRS_ON if cg == "1" else ops.TUNE_PAIRS_OFF)
         ms = timed(lambda: ops.conv2d(xs, w, s, 1, ep=ep, precision=ops.PREC_BF16X3, W_split=ws, split_out=True))
         line += f" ps{kb}{'x2' if cg == '1' else ''} {ms*1e3:7.1f} us {fl/ms/1e9:6.1f} TF/s |"
     print(line, flush=True)

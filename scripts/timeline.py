@@ -5,7 +5,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vibertgrid_pytorch_b200 import ops, _lib
-os.environ["VBG_PS_CG2"] = "1"
+ops.TUNE = ops.TUNE_PAIRS_ON
 dev = "cuda"
 buf = torch.zeros(16, dtype=torch.int64, device=dev)
 names = ["entry", "setup_done", "after_pdl_wait", "first_tma_issued", "first_operands_landed", "last_mma_committed(tile0)",

@@ -381,14 +381,17 @@ def _merged(x):
 @pytest.fixture(params=["64", "32"])
 def ps_kb(request, monkeypatch):
     """Both ring-stage variants of the pre-split kernel: K=64 (SWIZZLE_128B) and K=32 (SWIZZLE_64B)."""
-    monkeypatch.setenv("VBG_PS_KB", request.param)
+    from vibertgrid_pytorch_b200 import ops as _ops
+    monkeypatch.setattr(_ops, "TUNE", (_ops.TUNE & ~_ops.TUNE_KB32) | (_ops.TUNE_KB32 if request.param == "32" else 0))
     return int(request.param)
 
 
 @pytest.fixture(params=["0", "1"])
 def ps_cg2(request, monkeypatch):
     """Single-CTA tiles (128 x BN) and CTA-pair tiles (tcgen05 cta_group::2, 256 x BN over a cluster of two)."""
-    monkeypatch.setenv("VBG_PS_CG2", request.param)
+    from vibertgrid_pytorch_b200 import ops as _ops
+    keep = _ops.TUNE & ~(_ops.TUNE_PAIRS_OFF | _ops.TUNE_PAIRS_ON)
+    monkeypatch.setattr(_ops, "TUNE", keep | (_ops.TUNE_PAIRS_ON if request.param == "1" else _ops.TUNE_PAIRS_OFF))
     return int(request.param)
 
 
@@ -491,15 +494,15 @@ def test_gemm_presplit_split_k(ops, monkeypatch, M, N, K):
     """Under-filled shapes run as (tile, K-range) work units + a deterministic finishing kernel: same result as the unsplit
     kernel up to fp32 re-association of the K sum, residual / activation / plane output applied once at the end."""
     from vibertgrid_pytorch_b200 import _lib
-    monkeypatch.setenv("VBG_PS_SPLITK", "1")
-    assert _lib.load().vbg_gemm_ps_workspace(M, N, K) > 0, "shape expected to split"
+    assert _lib.load().vbg_gemm_ps_workspace(M, N, K, ops.TUNE_SPLITK) > 0, "shape expected to split"
+    assert _lib.load().vbg_gemm_ps_workspace(M, N, K, 0) == 0, "split-K is opt-in"
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g); Wt = torch.randn(N, K, generator=g) / K ** 0.5
     bias = torch.randn(N, generator=g); res = torch.randn(M, N, generator=g)
     Wd = Wt.cuda(); Ws = ops.split_bf16(Wd); As = ops.to_split(A.cuda()); rs = ops.to_split(res.cuda())
     outs = {}
     for flag in ("0", "1"):
-        monkeypatch.setenv("VBG_PS_SPLITK", flag)
+        monkeypatch.setattr(ops, "TUNE", ops.TUNE_SPLITK if flag == "1" else 0)
         mk = lambda: ops.make_epilogue(None, bias.cuda(), rs, ops.RES_SAME, ldr=N, act=ops.ACT_RELU)   # gemm(split_out) edits its ep
         outs[flag] = (ops.gemm(As, Wd, ep=mk(), precision=ops.PREC_BF16X3, W_split=Ws, split_out=True).float().cpu(),
                       ops.gemm(As, Wd, ep=mk(), precision=ops.PREC_BF16X3, W_split=Ws).cpu())
@@ -515,8 +518,7 @@ def test_gemm_presplit_split_k(ops, monkeypatch, M, N, K):
 def test_conv2d_presplit_split_k(ops, monkeypatch):
     B, H, W, Cin, Cout = 8, 16, 16, 512, 512
     from vibertgrid_pytorch_b200 import _lib
-    monkeypatch.setenv("VBG_PS_SPLITK", "1")
-    assert _lib.load().vbg_conv2d_ps_workspace(B, H, W, Cin, Cout, 3, 3, 1, 1) > 0
+    assert _lib.load().vbg_conv2d_ps_workspace(B, H, W, Cin, Cout, 3, 3, 1, 1, ops.TUNE_SPLITK) > 0
     g = torch.Generator().manual_seed(99)
     x = torch.randn(B, Cin, H, W, generator=g); w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
     scale = torch.rand(Cout, generator=g) + 0.5; shift = torch.randn(Cout, generator=g); res = torch.randn(B, Cout, H, W, generator=g)
@@ -526,7 +528,7 @@ def test_conv2d_presplit_split_k(ops, monkeypatch):
     xs = ops.to_split(x.permute(0, 2, 3, 1).contiguous().cuda()); rs = ops.to_split(res.permute(0, 2, 3, 1).contiguous().cuda())
     got = {}
     for flag in ("0", "1"):
-        monkeypatch.setenv("VBG_PS_SPLITK", flag)
+        monkeypatch.setattr(ops, "TUNE", ops.TUNE_SPLITK if flag == "1" else 0)
         ep = ops.make_epilogue(scale.cuda(), shift.cuda(), rs, ops.RES_SAME, ldr=Cout, act=ops.ACT_RELU)
         got[flag] = ops.conv2d(xs, w_ohwi, 1, 1, ep=ep, precision=ops.PREC_BF16X3, W_split=ws, split_out=True).float().permute(0, 3, 1, 2).cpu()
         assert relerr(got[flag].numpy(), want.numpy()) < 3e-5

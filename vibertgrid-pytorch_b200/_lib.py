@@ -19,7 +19,8 @@ OUT_F32, OUT_SPLIT_BF16 = 0, 1
 class Epilogue(C.Structure):
     _fields_ = [("scale", C.c_void_p), ("shift", C.c_void_p), ("residual", C.c_void_p),
                 ("res_mode", C.c_int), ("ldr", C.c_int), ("out_h", C.c_int), ("out_w", C.c_int),
-                ("act", C.c_int), ("out_mode", C.c_int), ("out_plane", C.c_longlong), ("res_plane", C.c_longlong)]
+                ("act", C.c_int), ("out_mode", C.c_int), ("out_plane", C.c_longlong), ("res_plane", C.c_longlong),
+                ("tune", C.c_int)]
 
 
 class VbgError(RuntimeError):
@@ -55,8 +56,8 @@ SIGNATURES = {
     "vbg_gemm": [_p, _i, _p, _i, _i, _p, _i, _p, _ll, _p, _i, _i, _i, _i, _EP, _i, _p],
     "vbg_gemm_ps": [_p, _ll, _i, _p, _ll, _i, _i, _p, _ll, _i, _p, _i, _i, _i, _i, _EP, _p, _sz, _p],
     "vbg_conv2d_ps": [_p, _ll, _i, _i, _i, _i, _p, _ll, _i, _i, _i, _i, _i, _p, _EP, _p, _sz, _p],
-    "vbg_gemm_ps_workspace": [_i, _i, _i],
-    "vbg_conv2d_ps_workspace": [_i, _i, _i, _i, _i, _i, _i, _i, _i],
+    "vbg_gemm_ps_workspace": [_i, _i, _i, _i],
+    "vbg_conv2d_ps_workspace": [_i, _i, _i, _i, _i, _i, _i, _i, _i, _i],
     "vbg_debug_set_timeline": [_p],
     "vbg_merge_bf16": [_p, _p, _ll, _p, _p],
     "vbg_conv2d": [_p, _i, _i, _i, _i, _p, _p, _ll, _i, _i, _i, _i, _i, _p, _EP, _i, _p],

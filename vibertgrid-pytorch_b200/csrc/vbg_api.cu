@@ -35,14 +35,14 @@ int gemm_ps(const void* A, long long a_plane, int lda, const void* A2, long long
             size_t ws_bytes, cudaStream_t s);
 int conv_ps(const void* x, long long x_plane, int B, int H, int W, int Cin, const void* w_hi, long long w_plane, int Cout, int kh,
             int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, void* workspace, size_t ws_bytes, cudaStream_t s);
-size_t ps_workspace_bytes(int m_tiles, long long M, int N, int K);
+size_t ps_workspace_bytes(int m_tiles, long long M, int N, int K, int tune);
 size_t linear_wgrad_workspace(int M, int N, int K);
 size_t conv_wgrad_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad);
 int conv_wgrad(const void* dY, long long y_plane, const void* X, long long x_plane, int B, int H, int W, int Cin, int Cout, int kh, int kw,
                int stride, int pad, float* dW, void* workspace, size_t ws_bytes, cudaStream_t s);
 int linear_wgrad(const void* dY, long long y_plane, const void* X, long long x_plane, int M, int N, int K, float* dW, void* workspace,
                  size_t ws_bytes, cudaStream_t s);
-size_t conv_ps_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad);
+size_t conv_ps_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int tune);
 bool tc_available();
 
 // ------------------------------------------------------------------ CRF Viterbi (model/crf.py:96-146)
@@ -226,13 +226,13 @@ extern "C" int vbg_debug_set_timeline(long long* dev_buf) {
   return VBG_OK;
 }
 
-extern "C" long long vbg_gemm_ps_workspace(int M, int N, int K) {
-  return (M > 0 && N > 0 && K > 0) ? (long long)ps_workspace_bytes(cdiv(M, 128), M, N, K) : 0;
+extern "C" long long vbg_gemm_ps_workspace(int M, int N, int K, int tune) {
+  return (M > 0 && N > 0 && K > 0) ? (long long)ps_workspace_bytes(cdiv(M, 128), M, N, K, tune) : 0;
 }
 
-extern "C" long long vbg_conv2d_ps_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad) {
+extern "C" long long vbg_conv2d_ps_workspace(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int tune) {
   if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || kh <= 0 || kw <= 0 || stride <= 0 || pad < 0) return 0;
-  return (long long)conv_ps_workspace_bytes(B, H, W, Cin, Cout, kh, kw, stride, pad);
+  return (long long)conv_ps_workspace_bytes(B, H, W, Cin, Cout, kh, kw, stride, pad, tune);
 }
 
 extern "C" long long vbg_linear_wgrad_workspace(int M, int N, int K) { return (long long)linear_wgrad_workspace(M, N, K); }

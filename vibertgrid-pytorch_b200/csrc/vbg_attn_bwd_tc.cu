@@ -312,7 +312,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_consta
 int attention_bwd_tc(const void* qkv_hi, long long qkv_plane, const void* do_hi, long long do_plane, const float* o, const float* d_o,
                      const float* lse2, const int32_t* cu, int nseq, int R, int max_len, int heads, float p_drop,
                      unsigned long long seed, const unsigned long long* step_seed, float* dqkv, float* delta, cudaStream_t s) {
-  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!tc_available()) return VBG_EUNSUPPORTED;
   if (max_len > 512 || !aligned16(qkv_hi) || !aligned16(do_hi) || ((qkv_plane * 2) & 15) || ((do_plane * 2) & 15)) return VBG_EUNSUPPORTED;
   const long long ld3 = 3LL * heads * 64, ld1 = 1LL * heads * 64;
   CUtensorMap mq[2], md[2];

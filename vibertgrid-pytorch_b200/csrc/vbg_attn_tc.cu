@@ -502,7 +502,7 @@ attention_split_kernel(const __grid_constant__ CUtensorMap tmQKh, const __grid_c
 int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int nseq, int R, int max_len, int heads,
                     int head_dim, void* out, long long out_plane, float* lse2, float p_drop, unsigned long long seed,
                     const unsigned long long* step_seed, cudaStream_t s) {
-  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!tc_available()) return VBG_EUNSUPPORTED;
   if (head_dim != 64 || max_len > 512 || !aligned16(qkv_hi) || ((plane * 2) & 15)) return VBG_EUNSUPPORTED;
   const long long ld = 3LL * heads * 64;
   const __nv_bfloat16* hi = reinterpret_cast<const __nv_bfloat16*>(qkv_hi);
@@ -531,7 +531,7 @@ int attention_split(const void* qkv_hi, long long plane, const int32_t* cu, int 
 
 int attention_tc(const float* qkv, const int32_t* cu, int nseq, int max_len, int heads, int head_dim, float* out,
                  cudaStream_t s) {
-  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!tc_available()) return VBG_EUNSUPPORTED;
   if (head_dim != 64 || max_len > 512) return VBG_EUNSUPPORTED;
   constexpr size_t smem = 2 * kTileQ + 4 * kTileQ + 4 * kVtTile + 1024 + 256;
   static bool attr = false;

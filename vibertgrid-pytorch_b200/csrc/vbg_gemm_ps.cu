@@ -436,12 +436,8 @@ __global__ void merge_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __
 }
 
 // ------------------------------------------------------------------ host side
-// K elements per ring stage.  Read per call (not cached) so the parity tests can exercise both variants in one process.
-static int ps_kb() {
-  const char* e = getenv("VBG_PS_KB");
-  const int k = e ? atoi(e) : 0;
-  return (k == 32 || k == 64) ? k : kPsDefaultKB;
-}
+// K elements per ring stage: a per-call choice (vbg_epilogue_t::tune) so the parity tests can exercise both variants.
+static int ps_kb(int tune) { return (tune & VBG_TUNE_KB32) ? 32 : kPsDefaultKB; }
 
 // rank-3 (k, row, plane) map over bf16 planes [rows, ld] + [rows, ld] `plane` elements later
 static bool map_ps_2d(CUtensorMap* tm, const void* hi, long long plane, long long rows, long long cols, long long ld, int box_rows,
@@ -464,7 +460,7 @@ static int launch_ps(const CUtensorMap& a, const CUtensorMap& a2, const CUtensor
     attr = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
-  static const bool pdl = [] { const char* e = getenv("VBG_PDL"); return !(e && e[0] == '0'); }();
+  const bool pdl = !(p.ep.tune & VBG_TUNE_NO_PDL);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(tiles < kNumSMs ? tiles : kNumSMs); cfg.blockDim = dim3(kPsThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
   cudaLaunchAttribute at[1];
@@ -495,7 +491,7 @@ static int launch_ps2(const CUtensorMap& a, const CUtensorMap& a2, const CUtenso
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = 1;
-  static const bool pdl = [] { const char* e = getenv("VBG_PDL"); return !(e && e[0] == '0'); }();
+  const bool pdl = !(p.ep.tune & VBG_TUNE_NO_PDL);
   cfg.attrs = at; cfg.numAttrs = pdl ? 2 : 1;
   if (max_clusters == 0) {
     cudaError_t e = cudaFuncSetAttribute(gemm_ps2_kernel<BN, KB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -517,28 +513,24 @@ static int launch_ps2(const CUtensorMap& a, const CUtensorMap& a2, const CUtenso
 // halves for the weight tile): a grid that fills most of the chip, a K long enough that the mainloop -- not the epilogue --
 // sets the tile time, and a weight tile wide enough to matter next to the A tile.  Measured on B200 (profiles/
 // r1_gemm_presplit_pairs_k.log): +10..25 % on the BERT GEMMs and the 256-channel convs, -4..8 % on N <= 128 / short-K shapes.
-// VBG_PS_CG2 = 0 / 1 forces the choice (tests run both).
-static bool use_pairs(int m_tiles, int n_tiles_1cta, int N, int num_kb) {
-  const char* e = getenv("VBG_PS_CG2");
-  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1' && m_tiles >= 2;
+// VBG_TUNE_PAIRS_OFF / VBG_TUNE_PAIRS_ON in the call's `tune` force the choice (tests run both).
+static bool use_pairs(int m_tiles, int n_tiles_1cta, int N, int num_kb, int tune) {
+  if (tune & (VBG_TUNE_PAIRS_OFF | VBG_TUNE_PAIRS_ON)) return (tune & VBG_TUNE_PAIRS_ON) && m_tiles >= 2;
   return m_tiles >= 2 && N >= 192 && num_kb >= 8 && (long long)m_tiles * n_tiles_1cta >= 96;
 }
 
 // Single-CTA tiles: N tile width and split-K factor chosen together.  An under-filled grid (layer-3/4 convs at 32x32 / 16x16,
 // the ROI FC: 8 - 64 row tiles) used to shrink BN to get more CTAs, which quadruples the A traffic per FLOP; splitting K
 // instead keeps wide tiles and fills the SMs with (tile, split) work units.  Needs a workspace of splits * M * N floats.
-static void pick_bn_splits(int m_tiles, int N, int num_kb, bool allow_split, int* bn_out, int* splits_out) {
-  static const int forced_bn = [] { const char* e = getenv("VBG_TC3_BN"); return e ? atoi(e) : 0; }();
-  // Opt-in (VBG_PS_SPLITK=1): measured on B200 at cfg2 the split form (single-CTA units + finishing kernel) is SLOWER than
+static void pick_bn_splits(int m_tiles, int N, int num_kb, bool allow_split, int tune, int* bn_out, int* splits_out) {
+  // Opt-in (VBG_TUNE_SPLITK): measured on B200 at cfg2 the split form (single-CTA units + finishing kernel) is SLOWER than
   // the narrow CTA-pair tiles it replaces (6.67 vs 6.37 ms/step) -- kept, with its parity tests, as a tuning experiment.
-  const char* es = getenv("VBG_PS_SPLITK");
-  if (!(es && es[0] == '1')) allow_split = false;
+  if (!(tune & VBG_TUNE_SPLITK)) allow_split = false;
   const int cand[4] = {256, 192, 128, 64};
   const int scand[6] = {1, 2, 3, 4, 6, 8};
   int best_bn = 64, best_s = 1; double best = -1.0;
   for (int i = 0; i < 4; ++i) {
     const int bn = cand[i];
-    if (forced_bn && bn != forced_bn) continue;
     if (bn > 64 && N < bn - 32) continue;
     for (int j = 0; j < 6; ++j) {
       const int sp = scand[j];
@@ -565,12 +557,12 @@ static int dispatch_ps(const CUtensorMap& a, const CUtensorMap& a2, const void* 
   p.m_tiles = m_tiles;
   int bn = 64, splits = 1;
   const bool ws_ok = workspace && aligned16(workspace);
-  pick_bn_splits(m_tiles, p.N, p.num_kb, ws_ok, &bn, &splits);
+  pick_bn_splits(m_tiles, p.N, p.num_kb, ws_ok, p.ep.tune, &bn, &splits);
   // a grid that stays under one wave even with the widest tile is a split-K case, not a pair case
   const bool underfilled = (long long)m_tiles * cdiv(p.N, 256) * 2 <= kNumSMs;
   if (!(underfilled && splits > 1)) {
   const int bn_pairs_probe = pick_bn3(m_tiles, p.N);
-  if (kb == 64 && use_pairs(m_tiles, cdiv(p.N, bn_pairs_probe), p.N, p.num_kb)) {
+  if (kb == 64 && use_pairs(m_tiles, cdiv(p.N, bn_pairs_probe), p.N, p.num_kb, p.ep.tune)) {
     // pair tiles: same (wave efficiency x column fill x tile efficiency) score as pick_bn3, over clusters of two SMs
     const int pm_tiles = (m_tiles + 1) / 2, n_cl = kNumSMs / 2;
     const int cand[4] = {256, 192, 128, 64};
@@ -598,7 +590,7 @@ static int dispatch_ps(const CUtensorMap& a, const CUtensorMap& a2, const void* 
     if (splits < 2 || (size_t)splits * (size_t)p.M * (size_t)p.N * 4 > ws_bytes) splits = 1;
     else p.kb_per_split = per;
   }
-  if (splits == 1) pick_bn_splits(m_tiles, p.N, p.num_kb, false, &bn, &splits);
+  if (splits == 1) pick_bn_splits(m_tiles, p.N, p.num_kb, false, p.ep.tune, &bn, &splits);
   if (!map_ps_2d(&w, w_hi, w_plane, p.N, K, ldw, bn, kb)) return VBG_EUNSUPPORTED;
   p.n_tiles = cdiv(p.N, bn);
   TcParams q = p;                                                   // what the GEMM kernel sees
@@ -606,6 +598,7 @@ static int dispatch_ps(const CUtensorMap& a, const CUtensorMap& a2, const void* 
     q.splits = splits;
     q.C = reinterpret_cast<float*>(workspace); q.ldc = p.N;
     q.ep = vbg_epilogue_t{};                                        // raw fp32 partial accumulators
+    q.ep.tune = p.ep.tune;
   }
   int rc;
   if (kb == 64) {
@@ -628,13 +621,13 @@ static int dispatch_ps(const CUtensorMap& a, const CUtensorMap& a2, const void* 
 }
 
 // Workspace a caller should provide so that under-filled shapes may split K (0: the shape never splits).
-size_t ps_workspace_bytes(int m_tiles, long long M, int N, int K) {
+size_t ps_workspace_bytes(int m_tiles, long long M, int N, int K, int tune) {
   if (K % 64 || N < 64 || (N & 3)) return 0;
   const int num_kb = K / 64;
   int bn, splits;
-  pick_bn_splits(m_tiles, N, num_kb, true, &bn, &splits);
+  pick_bn_splits(m_tiles, N, num_kb, true, tune, &bn, &splits);
   const bool underfilled = (long long)m_tiles * cdiv(N, 256) * 2 <= kNumSMs;
-  if (!(underfilled && splits > 1) && use_pairs(m_tiles, cdiv(N, pick_bn3(m_tiles, N)), N, num_kb)) return 0;
+  if (!(underfilled && splits > 1) && use_pairs(m_tiles, cdiv(N, pick_bn3(m_tiles, N)), N, num_kb, tune)) return 0;
   return splits > 1 ? (size_t)splits * (size_t)M * (size_t)N * 4 : 0;
 }
 
@@ -643,12 +636,12 @@ static bool planes_ok(const void* p, long long plane) { return p && aligned16(p)
 int gemm_ps(const void* A, long long a_plane, int lda, const void* A2, long long a2_plane, int lda2, int K1, const void* w_hi,
             long long w_plane, int ldw, void* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep, void* workspace,
             size_t ws_bytes, cudaStream_t s) {
-  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!tc_available()) return VBG_EUNSUPPORTED;
   // N < 64: one 64-wide tile with N live columns (weight rows beyond N are TMA zero fill) -- worth it only for tall problems
   if ((N < 64 && ((N & 3) || M < 8192)) || K % 64 || K1 % 64 || (lda & 7) || (ldw & 7) || !planes_ok(A, a_plane) || !planes_ok(w_hi, w_plane))
     return VBG_EUNSUPPORTED;
   if (K1 < K && ((lda2 & 7) || !planes_ok(A2, a2_plane))) return VBG_EUNSUPPORTED;
-  const int kb = ps_kb();
+  const int kb = ps_kb(ep ? ep->tune : 0);
   CUtensorMap ta, ta2;
   if (!map_ps_2d(&ta, A, a_plane, M, K1, lda, BM, kb)) return VBG_EUNSUPPORTED;
   if (K1 < K) { if (!map_ps_2d(&ta2, A2, a2_plane, M, K - K1, lda2, BM, kb)) return VBG_EUNSUPPORTED; } else ta2 = ta;
@@ -661,18 +654,18 @@ int gemm_ps(const void* A, long long a_plane, int lda, const void* A2, long long
 bool tc_conv_geometry(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, TcParams& p,
                       cuuint64_t dims[4], cuuint64_t strides_b[3], cuuint32_t box[4], cuuint32_t estr[4]);
 
-size_t conv_ps_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad) {
+size_t conv_ps_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride, int pad, int tune) {
   TcParams p{};
   cuuint64_t d4[4], s4[3]; cuuint32_t b4[4], e4[4];
   if (Cin % 64 || !tc_conv_geometry(B, H, W, Cin, Cout, kh, kw, stride, pad, p, d4, s4, b4, e4)) return 0;
-  return ps_workspace_bytes(p.tiles_w * p.tiles_h * cdiv(B, p.tb), p.M, Cout, kh * kw * Cin);
+  return ps_workspace_bytes(p.tiles_w * p.tiles_h * cdiv(B, p.tb), p.M, Cout, kh * kw * Cin, tune);
 }
 
 int conv_ps(const void* x, long long x_plane, int B, int H, int W, int Cin, const void* w_hi, long long w_plane, int Cout, int kh,
             int kw, int stride, int pad, void* y, const vbg_epilogue_t* ep, void* workspace, size_t ws_bytes, cudaStream_t s) {
-  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!tc_available()) return VBG_EUNSUPPORTED;
   if (Cin % 64 || Cout < 64 || !planes_ok(x, x_plane) || !planes_ok(w_hi, w_plane)) return VBG_EUNSUPPORTED;
-  const int kb = ps_kb();
+  const int kb = ps_kb(ep ? ep->tune : 0);
   TcParams p{};
   cuuint64_t d4[4], s4[3]; cuuint32_t b4[4], e4[4];
   if (!tc_conv_geometry(B, H, W, Cin, Cout, kh, kw, stride, pad, p, d4, s4, b4, e4)) return VBG_EUNSUPPORTED;

@@ -211,15 +211,9 @@ static int dispatch(const CUtensorMap& a, const CUtensorMap& a2, CUtensorMap& w,
   return launch<64, 4>(a, a2, w, p, grid, s);
 }
 
-bool tc_disabled_by_env() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("VBG_DISABLE_TC"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v == 1;
-}
-
 int gemm_tc(const float* A, int lda, const float* A2, int lda2, int K1, const float* W, int ldw, float* C, int ldc,
             int M, int N, int K, const vbg_epilogue_t* ep, cudaStream_t s) {
-  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!tc_available()) return VBG_EUNSUPPORTED;
   if (N < 64 || K % BKE || K1 % BKE || (lda & 3) || (ldw & 3) || !aligned16(A) || !aligned16(W)) return VBG_EUNSUPPORTED;
   if (K1 < K && ((lda2 & 3) || !aligned16(A2))) return VBG_EUNSUPPORTED;
   CUtensorMap ta, ta2, tw;
@@ -255,7 +249,7 @@ bool tc_conv_geometry(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
 
 int conv_tc(const float* x, int B, int H, int W, int Cin, const float* w, int Cout, int kh, int kw, int stride, int pad,
             float* y, const vbg_epilogue_t* ep, cudaStream_t s) {
-  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!tc_available()) return VBG_EUNSUPPORTED;
   if (Cin % BKE || Cout < 64 || !aligned16(x) || !aligned16(w)) return VBG_EUNSUPPORTED;
   TcParams p{};
   cuuint64_t dims[4], strides[3]; cuuint32_t box[4], estr[4];

@@ -260,8 +260,6 @@ static int launch3(const CUtensorMap& a, const CUtensorMap& a2, const CUtensorMa
 // N-tile width: the candidate with the best (wave efficiency x tile efficiency).  Wider tiles re-read A less often;
 // the persistent grid makes the cost of a partial last wave explicit.
 int pick_bn3(int m_tiles, int N) {
-  static const int forced = [] { const char* e = getenv("VBG_TC3_BN"); return e ? atoi(e) : 0; }();   // tuning experiments only
-  if ((forced == 64 || forced == 128 || forced == 192 || forced == 256) && N >= forced - 32) return forced;
   const int cand[4] = {256, 192, 128, 64};
   int best = 64; double best_score = -1.0;
   for (int i = 0; i < 4; ++i) {
@@ -296,7 +294,7 @@ bool tc_conv_geometry(int B, int H, int W, int Cin, int Cout, int kh, int kw, in
 
 int gemm_tc3(const float* A, int lda, const float* A2, int lda2, int K1, const void* w_split, long long plane, int ldw,
              float* C, int ldc, int M, int N, int K, const vbg_epilogue_t* ep, cudaStream_t s) {
-  if (!w_split || tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!w_split || !tc_available()) return VBG_EUNSUPPORTED;
   if (N < 64 || K % 64 || K1 % 64 || (lda & 3) || (ldw & 7) || !aligned16(A) || !aligned16(w_split) || ((plane * 2) & 15))
     return VBG_EUNSUPPORTED;
   if (K1 < K && ((lda2 & 3) || !aligned16(A2))) return VBG_EUNSUPPORTED;
@@ -311,7 +309,7 @@ int gemm_tc3(const float* A, int lda, const float* A2, int lda2, int K1, const v
 
 int conv_tc3(const float* x, int B, int H, int W, int Cin, const void* w_split, long long plane, int Cout, int kh, int kw,
              int stride, int pad, float* y, const vbg_epilogue_t* ep, cudaStream_t s) {
-  if (!w_split || tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!w_split || !tc_available()) return VBG_EUNSUPPORTED;
   if (Cin % 64 || Cout < 64 || !aligned16(x) || !aligned16(w_split) || ((plane * 2) & 15)) return VBG_EUNSUPPORTED;
   TcParams p{};
   cuuint64_t dims[4], strides[3]; cuuint32_t box[4], estr[4];
@@ -336,7 +334,7 @@ int conv_tc3(const float* x, int B, int H, int W, int Cin, const void* w_split, 
 // zeros at r = 7, px = 7, ch = 3 (vbg_stem_pack_weights).
 int stem_tc3(const float* x4, int B, int H, int W, const void* w_split, long long plane, int Cout, float* y,
              const vbg_epilogue_t* ep, cudaStream_t s) {
-  if (!w_split || tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!w_split || !tc_available()) return VBG_EUNSUPPORTED;
   if ((H & 1) || (W & 1) || Cout < 64 || !aligned16(x4) || !aligned16(w_split) || ((plane * 2) & 15)) return VBG_EUNSUPPORTED;
   const int Ho = H / 2, Wo = W / 2, Hp = H + 6, Wp = W + 6;
   TcParams p{};

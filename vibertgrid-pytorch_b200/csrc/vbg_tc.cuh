@@ -422,7 +422,6 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const TcTile& t, 
 
 // ---- host helpers (vbg_gemm_tc.cu)
 bool tc_available();
-bool tc_disabled_by_env();
 // rank-N tiled map with SWIZZLE_128B; dtype_bf16 selects 2-byte elements
 bool tc_encode(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, const cuuint32_t* elem_strides, bool dtype_bf16, bool swizzle64 = false);

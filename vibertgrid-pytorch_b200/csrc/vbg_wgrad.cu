@@ -191,7 +191,7 @@ size_t linear_wgrad_workspace(int M, int N, int K) {
 
 int linear_wgrad(const void* dY, long long y_plane, const void* X, long long x_plane, int M, int N, int K, float* dW, void* workspace,
                  size_t ws_bytes, cudaStream_t s) {
-  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!tc_available()) return VBG_EUNSUPPORTED;
   if (N % 64 || K % 64 || !aligned16(dY) || !aligned16(X) || !aligned16(dW) || (y_plane & 7) || (x_plane & 7) || y_plane <= 0 || x_plane <= 0)
     return VBG_EUNSUPPORTED;
   const int bn = K % 128 == 0 ? 128 : 64;
@@ -236,7 +236,7 @@ size_t conv_wgrad_workspace(int B, int H, int W, int Cin, int Cout, int kh, int 
 
 int conv_wgrad(const void* dY, long long y_plane, const void* X, long long x_plane, int B, int H, int W, int Cin, int Cout, int kh, int kw,
                int stride, int pad, float* dW, void* workspace, size_t ws_bytes, cudaStream_t s) {
-  if (tc_disabled_by_env() || !tc_available()) return VBG_EUNSUPPORTED;
+  if (!tc_available()) return VBG_EUNSUPPORTED;
   if (Cout % 64 || Cin % 64 || stride < 1 || stride > 2 || !aligned16(dY) || !aligned16(X) || !aligned16(dW) || (y_plane & 7) ||
       (x_plane & 7) || y_plane <= 0 || x_plane <= 0)
     return VBG_EUNSUPPORTED;

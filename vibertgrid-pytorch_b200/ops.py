@@ -132,6 +132,22 @@ def make_epilogue(scale=None, shift=None, residual=None, res_mode=RES_NONE, ldr=
     return ep
 
 
+# Variant overrides of the pre-split tensor-core kernels (include/vbg.h VBG_TUNE_*), passed with every call in the epilogue
+# descriptor: 0 (what ships) = the library's own heuristics.  Sweeps and parity tests set ops.TUNE; the library itself
+# reads no environment variable.
+TUNE_KB32, TUNE_PAIRS_OFF, TUNE_PAIRS_ON, TUNE_SPLITK, TUNE_NO_PDL = 1, 2, 4, 8, 16
+TUNE = 0
+
+
+def _tuned(ep):
+    if TUNE == 0 and (ep is None or ep.tune == 0):
+        return ep
+    if ep is None:
+        ep = make_epilogue()
+    ep.tune = TUNE
+    return ep
+
+
 # ------------------------------------------------------------------ a1
 def normalize_resize_pad(img_chw, batch_nhwc4, b, oh, ow, mean, std):
     """``batch_nhwc4`` is the zero-initialised [B, H+6, W+6, 4] stem input (3-pixel border, 4th channel 0)."""
@@ -370,7 +386,8 @@ def gemm(A, W, *, A2=None, ep: Optional[Epilogue] = None, precision=PREC_FP32, N
             raise TypeError("gemm: A and A2 must use the same storage format")
         ap, aplane = _act(A)
         a2p, a2plane = _act(A2) if A2 is not None else (None, 0)
-        ws = _workspace(L.load().vbg_gemm_ps_workspace(M, Nn, Kt), A.device)
+        ep = _tuned(ep)
+        ws = _workspace(L.load().vbg_gemm_ps_workspace(M, Nn, Kt, TUNE), A.device)
         L.check(L.load().vbg_gemm_ps(ap, aplane, K1, a2p, a2plane, K2, K1, sp, plane, ldw_, optr, ldc, M, Nn, Kt,
                                      C.byref(ep) if ep is not None else None, _p(ws), 0 if ws is None else ws.numel(), _stream()),
                 "vbg_gemm_ps")
@@ -403,7 +420,8 @@ def conv2d(x, w_ohwi, stride, pad, *, ep: Optional[Epilogue] = None, precision=P
         if sp is None:
             raise TypeError("conv2d over a Split activation needs W_split")
         xp, xplane = _act(x)
-        ws = _workspace(L.load().vbg_conv2d_ps_workspace(B, H, W, Cin, Cout, kh, kw, stride, pad), x.device)
+        ep = _tuned(ep)
+        ws = _workspace(L.load().vbg_conv2d_ps_workspace(B, H, W, Cin, Cout, kh, kw, stride, pad, TUNE), x.device)
         L.check(L.load().vbg_conv2d_ps(xp, xplane, B, H, W, Cin, sp, plane, Cout, kh, kw, stride, pad, yp,
                                        C.byref(ep) if ep is not None else None, _p(ws), 0 if ws is None else ws.numel(), _stream()),
                 "vbg_conv2d_ps")
