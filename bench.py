@@ -425,6 +425,69 @@ def serving_latency(dev, n=200):
             "documents_per_s_one_stream": 1e3 / (sum(lat) / len(lat)), "graph_replays": net._get_engine().graph_replays}
 
 
+def input_pipeline_arm(net, cfg, dev, rank, world, steps):
+    """the same e2e step fed by the package's input pipeline instead of ready-made host batches -- documents come
+    out of a shard (pre-tokenised, decoded uint8 pixels; shards.py / csrc/vbg_shard.cpp), the native collate gathers each
+    step's batch into ONE pinned staging buffer on a background thread, ONE host->device copy per step on a side stream, the
+    decode kernel applies ToTensor's / 255 on the device.  Also the host-only rate of the reader + collate (no GPU in it)."""
+    from vibertgrid_pytorch_b200 import shards, synth
+    from vibertgrid_pytorch_b200.prefetch import HostResultQueue
+    n_batches_distinct = 4
+    docs = []
+    for i in range(n_batches_distinct):
+        img, seg, cls, coors, corpus, mask = synth.make_batch(cfg, 7000 + 1000 * rank + i)
+        for b in range(len(img)):
+            n = int(seg[b].shape[0])
+            docs.append(dict(image=(img[b].permute(1, 2, 0) * 255.0).round().clamp(0, 255).to(torch.uint8).numpy(),
+                             corpus=corpus[b, :n].numpy(), seg_ids=seg[b].numpy(), classes=cls[b].numpy(), coors=coors[b].numpy()))
+    tmp = tempfile.mkdtemp(prefix="vbg_shard_")
+    path = os.path.join(tmp, f"bench_rank{rank}.vbgshard")
+    shards.write_shard(path, docs)
+    sh = shards.Shard(path)
+    B = cfg.batch
+    plan = lambda n: [[(i % n_batches_distinct) * B + b for b in range(B)] for i in range(n)]
+    results, sink = HostResultQueue(), {}
+
+    def run(n, timed):
+        ld = shards.ShardLoader(sh, batches=plan(n), device=dev, depth=3, threads=4)
+        it = iter(ld)
+
+        def step(i):
+            loss, pm, ps, gt, pred = net(*next(it))
+            results.push(pred, loss)
+            while len(results) > (0 if i == n - 1 else 1):
+                sink["pred"], sink["loss"] = results.pop()
+        if not timed:
+            for i in range(n):
+                step(i)
+            return None, ld
+        return time_region(step, n, True, world), ld
+
+    run(3, False)                                    # eager, capture, replay of the uint8 batch signature
+    ms, ld = run(steps, True)
+    out = {"value": B * steps * world / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps,
+           "h2d_bytes_per_step": ld.h2d_bytes // steps, "h2d_copies_per_step": 1,
+           "what": "ShardLoader(device) -> net() -> HostResultQueue: shard -> native collate (background thread, pinned staging) -> one "
+                   "H2D per step -> uint8 decode kernel -> joint forward -> D2H of pred_label + loss"}
+    if rank == 0:                                    # host-only: reader + collate into pinned staging
+        lay = sh.layout(plan(1)[0])
+        staging = torch.empty(lay[0], dtype=torch.uint8).pin_memory()
+        for threads in (1, 4):
+            sh.collate_into(plan(1)[0], staging, threads)
+            t0, n = time.perf_counter(), 0
+            while time.perf_counter() - t0 < 0.5:
+                sh.collate_into(plan(n + 1)[n], staging, threads)
+                n += 1
+            dt = time.perf_counter() - t0
+            out[f"host_collate_{threads}t"] = {"documents_per_s": B * n / dt, "gb_per_s": lay[0] * n / dt / 1e9, "batch_bytes": int(lay[0])}
+    sh.close()
+    try:
+        os.remove(path); os.rmdir(tmp)
+    except OSError:
+        pass
+    return out
+
+
 def measured_peaks(dev):
     """MEASURED_PEAKS.json (driver-written) + a live cuBLAS TF32 / fp32 GEMM measured the same way
     (library call used ONLY as the roofline denominator, never on the hot path)."""
@@ -532,6 +595,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement (the `train_step` object)")
+    ap.add_argument("--no-input-pipeline", action="store_true", help="skip the shard-fed e2e measurement (the `input_pipeline` object)")
     ap.add_argument("--no-library-bar", action="store_true", help="skip the library-kernel bar (reference eager on the GPU, cuBLAS, torchvision)")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="train: the line's value / ms_per_step are the TRAINING step (forward + backward + all-reduce + optimizers)")
@@ -619,6 +683,12 @@ def main():
         step_e2e(i)
     new_feed(args.steps)
     ms_e2e = time_region(step_e2e, args.steps, True, world)
+    pipeline = None
+    if not args.no_input_pipeline:
+        try:
+            pipeline = input_pipeline_arm(net, cfg, dev, rank, world, args.steps)
+        except Exception as e:          # secondary measurement: never loses the headline line
+            pipeline = {"error": f"{type(e).__name__}: {e}"[:300]}
     clocks = sampler.stop() if sampler else None
 
     train = None
@@ -650,6 +720,11 @@ def main():
         line["forward"] = {"value": value, "ms_per_step": ms / args.steps, "e2e": e2e}
         line.update(metric="train_" + METRIC, value=train["value"], ms_per_step=train["ms_per_step"], gpu_launches=train["gpu_launches"])
         line["config"]["workload"] = workload.replace("eval fwd", "TRAIN step (fwd+bwd+allreduce+SGD/AdamW)")
+    if pipeline is not None:
+        line["input_pipeline"] = pipeline
+        if "value" in pipeline:         # numeric copy where the driver's record keeps it
+            line["e2e"]["from_shards_images_per_s"] = round(pipeline["value"], 1)
+            line["e2e"]["from_shards_h2d_bytes_per_step"] = int(pipeline["h2d_bytes_per_step"])
     if train is not None:
         line["train_step"] = train
         if "ms_per_step" in train:      # numeric copies where the driver's record keeps them

@@ -103,6 +103,15 @@ VBG_API int vbg_normalize_resize_pad(const float* img_chw, int h, int w, float* 
 /* the same for n same-shape images [n,3,h,w] (contiguous) resized to the same (oh,ow): samples b0 .. b0+n-1, one launch */
 VBG_API int vbg_normalize_resize_pad_batch(const float* imgs, int n, int h, int w, float* batch_nhwc, int b0, int H, int W,
                                    int oh, int ow, const float* h_mean3, const float* h_std3, vbg_stream_t stream);
+/* The same transform reading DECODED uint8 pixels [n, h, w, 3] (HWC, RGB) instead of ToTensor's fp32 planes: the kernel applies
+ * ToTensor's `byte / 255` (data/SROIE_dataset.py:84-86, one IEEE division) itself, so results are bit-identical to
+ * vbg_normalize_resize_pad_batch over ToTensor(img) while the host never touches a pixel and the upload is a quarter of the bytes. */
+VBG_API int vbg_normalize_resize_pad_u8(const uint8_t* imgs_hwc, int n, int h, int w, float* batch_nhwc, int b0, int H, int W,
+                                int oh, int ow, const float* h_mean3, const float* h_std3, vbg_stream_t stream);
+/* A whole batch of differently-sized uint8 documents in ONE launch: tab int32 [B, 6] = {byte offset of the document's pixels
+ * relative to `arena` (low word, high word of a signed 64-bit offset), h, w, oh, ow}; max_oh / max_ow size the grid. */
+VBG_API int vbg_decode_batch_u8(const uint8_t* arena, const int32_t* tab, int B, int max_oh, int max_ow, float* batch_nhwc, int H,
+                        int W, const float* h_mean3, const float* h_std3, vbg_stream_t stream);
 /* coords int64 [K,4] (l,t,r,b) -> int32 [K,4]: cols 0,2 *= ratio[b][0] (height ratio), cols 1,3 *= ratio[b][1]
  * (width ratio) in fp32, then truncation (pipeline/transform.py:163-169, axis swap included).    */
 VBG_API int vbg_resize_coords(const int64_t* coors, const int32_t* seg_off, const float* ratios /*[B,2]*/, int B, int K,
@@ -420,6 +429,25 @@ VBG_API int vbg_crf_nll_fwd(const float* feats /*[K,T]*/, const float* trans /*[
 VBG_API int vbg_crf_nll_bwd(const float* feats, const float* trans, const int32_t* tags, const int32_t* seg_off, int B, int K,
                     int T, const float* alpha, const float* dnll /*[B]*/, float* dfeats /*[K,T]*/,
                     float* dtrans_part /*[B,T,T]*/, vbg_stream_t stream);
+
+/* ---- f3: input pipeline -- shards of pre-tokenised, pre-decoded documents (HOST functions, no device work) ------------
+ * Replaces the per-item work of data/SROIE_dataset.py:94-162 (__getitem__: PIL decode, pandas CSV rows, Python tokenisation)
+ * and :165-208 (_ViBERTgrid_coll_func: pad_sequence + mask) on the way INTO the hot path.  A shard (csrc/vbg_shard.cpp documents
+ * the file layout; shards.py writes it once, offline) is memory-mapped; a batch is collated into ONE caller-owned (pinned)
+ * staging buffer that crosses to the device as one copy.  Handles are not thread safe against close; collate may be called
+ * concurrently on one handle (read-only mapping). */
+VBG_API int vbg_shard_open(const char* path, void** handle);
+VBG_API int vbg_shard_close(void* handle);
+VBG_API int vbg_shard_num_docs(void* handle);                                     /* < 0: bad handle */
+VBG_API int vbg_shard_doc_shape(void* handle, int doc, int32_t* out4 /* h, w, n_tok, n_seg */);
+/* per-document side data the eval loop reads (ocr text list + key dict, data/SROIE_dataset.py:150-162) as a JSON blob */
+VBG_API int vbg_shard_doc_meta(void* handle, int doc, const char** ptr, int64_t* bytes);
+/* layout13: [0] total staging bytes, [1] L = padded corpus width, [2] sum n_tok, [3] sum n_seg, then byte offsets of
+ * [4] corpus int64 [B,L], [5] mask int32 [B,L], [6] seg_ids int32 [sum n_tok], [7] classes int32 [sum n_seg],
+ * [8] coors int64 [sum n_seg,4], [9] shapes int32 [B,4] = (h,w,n_tok,n_seg), [10] image offsets int64 [B] (relative to the
+ * arena), [11] the uint8 image arena, and [12] the arena's bytes. */
+VBG_API int vbg_shard_batch_layout(void* handle, const int32_t* docs, int B, int64_t* layout13);
+VBG_API int vbg_shard_collate(void* handle, const int32_t* docs, int B, void* staging, size_t staging_bytes, int n_threads);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,8 @@ SIGNATURES = {
     "vbg_tc_available": [],
     "vbg_normalize_resize_pad": [_p, _i, _i, _p, _i, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _p],
     "vbg_normalize_resize_pad_batch": [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _p],
+    "vbg_normalize_resize_pad_u8": [_p, _i, _i, _i, _p, _i, _i, _i, _i, _i, C.POINTER(_f), C.POINTER(_f), _p],
+    "vbg_decode_batch_u8": [_p, _p, _i, _i, _i, _p, _i, _i, C.POINTER(_f), C.POINTER(_f), _p],
     "vbg_resize_coords": [_p, _p, _p, _i, _i, _p, _p],
     "vbg_bert_assemble": [_p, _i, _p, _p, _i, _i, _p, _p, _p],
     "vbg_embed_ln": [_p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _p, _p],
@@ -120,6 +122,13 @@ SIGNATURES = {
     "vbg_crf_viterbi": [_p, _p, _p, _i, _i, _i, _p, _p, _p, _sz, _p],
     "vbg_crf_nll_fwd": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p],
     "vbg_crf_nll_bwd": [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p],
+    "vbg_shard_open": [C.c_char_p, C.POINTER(_p)],
+    "vbg_shard_close": [_p],
+    "vbg_shard_num_docs": [_p],
+    "vbg_shard_doc_shape": [_p, _i, _p],
+    "vbg_shard_doc_meta": [_p, _i, C.POINTER(_p), C.POINTER(_ll)],
+    "vbg_shard_batch_layout": [_p, _p, _i, _p],
+    "vbg_shard_collate": [_p, _p, _i, _p, _sz, _i],
 }
 
 _lib = None
@@ -152,8 +161,10 @@ def last_error() -> str:
 launch_count = 0     # kernels enqueued through the C-ABI (bench.py reports it as gpu_launches)
 
 
-def check(rc: int, what: str = ""):
+def check(rc: int, what: str = "", launch: bool = True):
+    """``launch=False`` for host-only entry points (the shard reader): they enqueue no kernel."""
     global launch_count
-    launch_count += 1
+    if launch:
+        launch_count += 1
     if rc != VBG_OK:
         raise VbgError(f"{what or 'libvbg'} failed (code {rc}): {last_error()}")

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libvbg_sm100a.so")
-SOURCES = ["vbg_api.cu", "vbg_grid.cu", "vbg_roi.cu", "vbg_roi_stream.cu", "vbg_image.cu", "vbg_bert.cu", "vbg_gemm_simt.cu", "vbg_gemm_tc.cu", "vbg_gemm_tc3.cu", "vbg_gemm_ps.cu", "vbg_wgrad.cu", "vbg_attn_tc.cu", "vbg_train.cu", "vbg_attn_bwd.cu", "vbg_attn_bwd_tc.cu", "vbg_crf.cu", "vbg_optim.cu"]
+SOURCES = ["vbg_api.cu", "vbg_grid.cu", "vbg_roi.cu", "vbg_roi_stream.cu", "vbg_image.cu", "vbg_bert.cu", "vbg_gemm_simt.cu", "vbg_gemm_tc.cu", "vbg_gemm_tc3.cu", "vbg_gemm_ps.cu", "vbg_wgrad.cu", "vbg_attn_tc.cu", "vbg_train.cu", "vbg_attn_bwd.cu", "vbg_attn_bwd_tc.cu", "vbg_crf.cu", "vbg_optim.cu", "vbg_shard.cpp"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     objs, procs = [], []
     for src in SOURCES:
         s = os.path.join(HERE, src)
-        o = os.path.join(objdir, src.replace(".cu", ".o"))
+        o = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
             cmd = [nvcc, *FLAGS, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else [])
@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if procs or force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"]
+        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl", "-lpthread"]
         subprocess.run(cmd, check=True)
     return LIB
 

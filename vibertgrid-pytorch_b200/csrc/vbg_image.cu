@@ -10,14 +10,23 @@ namespace vbg {
 // border = the stem conv's padding, 4th channel = 0) that the tensor-core stem reads through one TMA map
 // (vbg_gemm_tc3.cu::stem_tc3).  Replaces the per-image
 // normalize/interpolate/copy_ kernels of reference pipeline/transform.py:122,149-155,261-269.
-__global__ void normalize_resize_kernel(const float* __restrict__ img, int h, int w, float* __restrict__ out, int H,
-                                        int W, int oh, int ow, float3 mean, float3 stdv) {
-  // blockIdx.z = image of a same-shape batch ([n,3,h,w] contiguous in, consecutive samples of the padded batch out)
-  img += (size_t)blockIdx.z * 3 * h * w;
-  out += (size_t)blockIdx.z * (H + 6) * (W + 6) * 4;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  const int y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (x >= ow || y >= oh) return;
+// Pixel sources: fp32 CHW planes in [0, 1] (what torchvision's ToTensor hands the reference model, data/SROIE_dataset.py:84-86)
+// or the decoded uint8 HWC bytes themselves (the shard format of the input pipeline, shards.py): ToTensor is
+// `byte.to(float32).div(255)`, one IEEE division, so doing it here is bit-identical and the host never touches pixels.
+struct PixF32 {
+  const float* img; int h, w;
+  __device__ __forceinline__ float at(int c, int y, int x) const { return __ldg(img + ((size_t)c * h + y) * w + x); }
+};
+struct PixU8 {
+  const unsigned char* img; int h, w;
+  __device__ __forceinline__ float at(int c, int y, int x) const {
+    return __fdiv_rn((float)__ldg(img + ((size_t)y * w + x) * 3 + c), 255.f);
+  }
+};
+
+template <class Pix>
+__device__ __forceinline__ void normalize_resize_pixel(const Pix& px, int h, int w, float* __restrict__ out, int W, int oh, int ow,
+                                                       int x, int y, const float3& mean, const float3& stdv) {
   const float sy = (float)h / (float)oh, sx = (float)w / (float)ow;
   float fy = sy * ((float)y + 0.5f) - 0.5f; if (fy < 0.f) fy = 0.f;
   float fx = sx * ((float)x + 0.5f) - 0.5f; if (fx < 0.f) fx = 0.f;
@@ -28,14 +37,44 @@ __global__ void normalize_resize_kernel(const float* __restrict__ img, int h, in
   float r[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float* p = img + (size_t)c * h * w;
-    float p00 = __fdiv_rn(__ldg(p + (size_t)y0 * w + x0) - m[c], s[c]);
-    float p01 = __fdiv_rn(__ldg(p + (size_t)y0 * w + x1) - m[c], s[c]);
-    float p10 = __fdiv_rn(__ldg(p + (size_t)y1 * w + x0) - m[c], s[c]);
-    float p11 = __fdiv_rn(__ldg(p + (size_t)y1 * w + x1) - m[c], s[c]);
+    float p00 = __fdiv_rn(px.at(c, y0, x0) - m[c], s[c]);
+    float p01 = __fdiv_rn(px.at(c, y0, x1) - m[c], s[c]);
+    float p10 = __fdiv_rn(px.at(c, y1, x0) - m[c], s[c]);
+    float p11 = __fdiv_rn(px.at(c, y1, x1) - m[c], s[c]);
     r[c] = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
   }
   *reinterpret_cast<float4*>(out + ((size_t)(y + 3) * (W + 6) + (x + 3)) * 4) = make_float4(r[0], r[1], r[2], 0.f);
+}
+
+template <bool kU8>
+__global__ void normalize_resize_kernel(const void* __restrict__ img, int h, int w, float* __restrict__ out, int H,
+                                        int W, int oh, int ow, float3 mean, float3 stdv) {
+  // blockIdx.z = image of a same-shape batch ([n,3,h,w] fp32 or [n,h,w,3] uint8 contiguous in, consecutive samples of the padded batch out)
+  out += (size_t)blockIdx.z * (H + 6) * (W + 6) * 4;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= ow || y >= oh) return;
+  if (kU8) {
+    PixU8 px{reinterpret_cast<const unsigned char*>(img) + (size_t)blockIdx.z * 3 * h * w, h, w};
+    normalize_resize_pixel(px, h, w, out, W, oh, ow, x, y, mean, stdv);
+  } else {
+    PixF32 px{reinterpret_cast<const float*>(img) + (size_t)blockIdx.z * 3 * h * w, h, w};
+    normalize_resize_pixel(px, h, w, out, W, oh, ow, x, y, mean, stdv);
+  }
+}
+
+// The whole batch of a collated shard batch in ONE launch, documents of different sizes: `tab` holds per document
+// {byte offset into `arena` (lo, hi 32 bits), h, w, oh, ow}; blockIdx.z = document, the x / y grid covers the largest output.
+__global__ void decode_batch_u8_kernel(const unsigned char* __restrict__ arena, const int* __restrict__ tab, float* __restrict__ out,
+                                       int H, int W, float3 mean, float3 stdv) {
+  const int* t = tab + 6 * blockIdx.z;
+  const long long off = (long long)(unsigned)t[0] | ((long long)t[1] << 32);
+  const int h = t[2], w = t[3], oh = t[4], ow = t[5];
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (x >= ow || y >= oh) return;
+  PixU8 px{arena + off, h, w};
+  normalize_resize_pixel(px, h, w, out + (size_t)blockIdx.z * (H + 6) * (W + 6) * 4, W, oh, ow, x, y, mean, stdv);
 }
 
 // PyTorch stem weight [O,3,7,7] -> (a) [O,7,7,4] (4th channel 0) for the CUDA-core path, (b) [O,8,8,4] with zero
@@ -320,7 +359,7 @@ extern "C" int vbg_normalize_resize_pad(const float* img_chw, int h, int w, floa
   VBG_REQUIRE(h > 0 && w > 0 && oh > 0 && ow > 0 && oh <= H && ow <= W && b >= 0,
               "vbg_normalize_resize_pad: bad geometry h=%d w=%d oh=%d ow=%d H=%d W=%d", h, w, oh, ow, H, W);
   dim3 blk(32, 8), grd(cdiv(ow, 32), cdiv(oh, 8));
-  normalize_resize_kernel<<<grd, blk, 0, as_stream(stream)>>>(
+  normalize_resize_kernel<false><<<grd, blk, 0, as_stream(stream)>>>(
       img_chw, h, w, batch_nhwc + (size_t)b * (H + 6) * (W + 6) * 4, H, W, oh, ow,
       make_float3(h_mean3[0], h_mean3[1], h_mean3[2]), make_float3(h_std3[0], h_std3[1], h_std3[2]));
   return check_launch("vbg_normalize_resize_pad");
@@ -332,10 +371,33 @@ extern "C" int vbg_normalize_resize_pad_batch(const float* imgs, int n, int h, i
   VBG_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0 && oh > 0 && ow > 0 && oh <= H && ow <= W && b0 >= 0,
               "vbg_normalize_resize_pad_batch: bad geometry n=%d h=%d w=%d oh=%d ow=%d H=%d W=%d", n, h, w, oh, ow, H, W);
   dim3 blk(32, 8), grd(cdiv(ow, 32), cdiv(oh, 8), n);
-  normalize_resize_kernel<<<grd, blk, 0, as_stream(stream)>>>(
+  normalize_resize_kernel<false><<<grd, blk, 0, as_stream(stream)>>>(
       imgs, h, w, batch_nhwc + (size_t)b0 * (H + 6) * (W + 6) * 4, H, W, oh, ow,
       make_float3(h_mean3[0], h_mean3[1], h_mean3[2]), make_float3(h_std3[0], h_std3[1], h_std3[2]));
   return check_launch("vbg_normalize_resize_pad_batch");
+}
+
+extern "C" int vbg_normalize_resize_pad_u8(const uint8_t* imgs_hwc, int n, int h, int w, float* batch_nhwc, int b0, int H, int W,
+                                           int oh, int ow, const float* h_mean3, const float* h_std3, vbg_stream_t stream) {
+  VBG_REQUIRE(imgs_hwc && batch_nhwc && h_mean3 && h_std3 && aligned16(batch_nhwc), "vbg_normalize_resize_pad_u8: null / unaligned pointer");
+  VBG_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0 && oh > 0 && ow > 0 && oh <= H && ow <= W && b0 >= 0,
+              "vbg_normalize_resize_pad_u8: bad geometry n=%d h=%d w=%d oh=%d ow=%d H=%d W=%d", n, h, w, oh, ow, H, W);
+  dim3 blk(32, 8), grd(cdiv(ow, 32), cdiv(oh, 8), n);
+  normalize_resize_kernel<true><<<grd, blk, 0, as_stream(stream)>>>(
+      imgs_hwc, h, w, batch_nhwc + (size_t)b0 * (H + 6) * (W + 6) * 4, H, W, oh, ow,
+      make_float3(h_mean3[0], h_mean3[1], h_mean3[2]), make_float3(h_std3[0], h_std3[1], h_std3[2]));
+  return check_launch("vbg_normalize_resize_pad_u8");
+}
+
+extern "C" int vbg_decode_batch_u8(const uint8_t* arena, const int32_t* tab, int B, int max_oh, int max_ow, float* batch_nhwc, int H,
+                                   int W, const float* h_mean3, const float* h_std3, vbg_stream_t stream) {
+  VBG_REQUIRE(arena && tab && batch_nhwc && h_mean3 && h_std3 && aligned16(batch_nhwc), "vbg_decode_batch_u8: null / unaligned pointer");
+  VBG_REQUIRE(B > 0 && B <= 65535 && max_oh > 0 && max_ow > 0 && max_oh <= H && max_ow <= W,
+              "vbg_decode_batch_u8: bad geometry B=%d max_oh=%d max_ow=%d H=%d W=%d", B, max_oh, max_ow, H, W);
+  dim3 blk(32, 8), grd(cdiv(max_ow, 32), cdiv(max_oh, 8), B);
+  decode_batch_u8_kernel<<<grd, blk, 0, as_stream(stream)>>>(
+      arena, tab, batch_nhwc, H, W, make_float3(h_mean3[0], h_mean3[1], h_mean3[2]), make_float3(h_std3[0], h_std3[1], h_std3[2]));
+  return check_launch("vbg_decode_batch_u8");
 }
 
 extern "C" int vbg_stem_pack_weights(const float* w_oihw, int O, float* w_ohwi4, float* w_k256, vbg_stream_t stream) {

@@ -392,10 +392,13 @@ class ForwardEngine:
             raise RuntimeError("ViBERTgridNet (B200) runs on CUDA tensors only; there is no CPU fallback")
         self._prepare()
         min_size = float(net.test_image_min_size)            # eval/inference branch of transform.py:192-196
-        shapes = (tuple(tuple(im.shape[-2:]) for im in image), tuple(int(s.shape[0]) for s in seg_indices),
+        shapes = (tuple(ops.image_hw(im) if not standins else tuple(im.shape[-2:]) for im in image), tuple(int(s.shape[0]) for s in seg_indices),
                   tuple(int(c.shape[0]) for c in coors), int(corpus.shape[1]))
         want_seg = bool(want_seg and net.semantic_segmentation_head is not None)
-        key = (shapes, want_seg, self._prec(), self._prep_gen, dev.index, self.fuse_aux_loss, bool(crf_one_sequence))
+        u8 = image[0].dtype == torch.uint8                    # decoded pixels [h, w, 3] (shards.py) instead of ToTensor's fp32 planes
+        if any((im.dtype == torch.uint8) != u8 for im in image):
+            raise TypeError("all images of a batch must share one format: float32 [3, h, w] or uint8 [h, w, 3]")
+        key = (shapes, want_seg, self._prec(), self._prep_gen, dev.index, self.fuse_aux_loss, bool(crf_one_sequence), u8)
         ent = self._graphs.get(key) if self.use_graphs and not standins else None
         if ent is not None and ent.get("graph") is not None:
             st = ent["static"]
@@ -424,6 +427,8 @@ class ForwardEngine:
             cls=torch.cat([c.reshape(-1) for c in seg_classes], 0).to(torch.int32).contiguous() if want_seg else None,
             corpus=corpus.contiguous(), tab=tab,
             mask=None if mask is None else mask.to(torch.int32).contiguous())
+        ragged_u8 = u8 and not uniform
+        static["img_tab"] = ops.image_table(static["image"], plan.sizes) if ragged_u8 else None
         if self.use_graphs and not standins:
             if ent is None:                                   # first sighting: run eagerly (also warms up lazy kernel attributes)
                 self._graphs[key] = {"graph": None}
@@ -434,6 +439,8 @@ class ForwardEngine:
                           for k, v in static.items()}
                 if static["image_stack"] is not None:             # the per-image static inputs are views of the stacked buffer
                     static["image"] = [static["image_stack"][b] for b in range(len(image))]
+                if ragged_u8:                                     # the table holds the addresses of the (cloned) static images
+                    static["img_tab"] = ops.image_table(static["image"], plan.sizes)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 c0 = ops.L.launch_count
@@ -501,6 +508,8 @@ class ForwardEngine:
         batch = torch.zeros((B, plan.H + 6, plan.W + 6, 4), dtype=torch.float32, device=dev)   # zero-bordered NHWC4 stem input
         if st.get("image_stack") is not None:
             ops.normalize_resize_pad_batch(st["image_stack"], batch, 0, plan.sizes[0][0], plan.sizes[0][1], net.image_mean, net.image_std)
+        elif st.get("img_tab") is not None:                        # differently-sized uint8 documents: one table-driven launch
+            ops.decode_batch_u8(st["image"], st["img_tab"], batch, plan.sizes, net.image_mean, net.image_std)
         else:
             for b, im in enumerate(st["image"]):
                 ops.normalize_resize_pad(im, batch, b, plan.sizes[b][0], plan.sizes[b][1], net.image_mean, net.image_std)

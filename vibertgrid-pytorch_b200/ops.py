@@ -149,26 +149,82 @@ def _tuned(ep):
 
 
 # ------------------------------------------------------------------ a1
+def image_hw(img):
+    """(h, w) of one input image: ToTensor's float32 [3, h, w] (the reference's dataset output) or the decoded uint8 [h, w, 3]
+    pixels of the shard loader (shards.py)."""
+    if img.dtype == torch.uint8:
+        if img.dim() != 3 or img.shape[2] != 3:
+            raise TypeError(f"uint8 images are decoded pixels [h, w, 3]; got {tuple(img.shape)}")
+        return int(img.shape[0]), int(img.shape[1])
+    if img.dim() != 3 or img.shape[0] != 3:
+        raise TypeError(f"float images are [3, h, w]; got {tuple(img.shape)}")
+    return int(img.shape[1]), int(img.shape[2])
+
+
+def _u8(t, what="image"):
+    if t.dtype != torch.uint8 or not t.is_contiguous() or t.device.type != "cuda":
+        raise TypeError(f"{what}: contiguous uint8 CUDA tensor required (no CPU fallback)")
+    return t.data_ptr()
+
+
 def normalize_resize_pad(img_chw, batch_nhwc4, b, oh, ow, mean, std):
-    """``batch_nhwc4`` is the zero-initialised [B, H+6, W+6, 4] stem input (3-pixel border, 4th channel 0)."""
-    _, h, w = img_chw.shape
+    """``batch_nhwc4`` is the zero-initialised [B, H+6, W+6, 4] stem input (3-pixel border, 4th channel 0).  ``img_chw`` may
+    also be a decoded uint8 [h, w, 3] image (the kernel then applies ToTensor's ``/ 255`` itself)."""
     B, Hp, Wp, c4 = batch_nhwc4.shape
     assert c4 == 4
     H, W = Hp - 6, Wp - 6
-    batch_nhwc = batch_nhwc4
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
+    if img_chw.dtype == torch.uint8:
+        h, w = image_hw(img_chw)
+        L.check(L.load().vbg_normalize_resize_pad_u8(_u8(img_chw), 1, h, w, _f32(batch_nhwc4), b, H, W, oh, ow, m, s, _stream()),
+                "vbg_normalize_resize_pad_u8")
+        return
+    _, h, w = img_chw.shape
+    batch_nhwc = batch_nhwc4
     L.check(L.load().vbg_normalize_resize_pad(_f32(img_chw, "image"), h, w, _f32(batch_nhwc), b, H, W, oh, ow, m, s,
                                               _stream()), "vbg_normalize_resize_pad")
 
 
-def normalize_resize_pad_batch(imgs_nchw, batch_nhwc4, b0, oh, ow, mean, std):
-    """n same-shape images [n,3,h,w] -> samples b0..b0+n-1 of the padded batch, one launch."""
-    n, _, h, w = imgs_nchw.shape
+def image_table(images, sizes):
+    """Device table [B, 6] int32 for ``decode_batch_u8``: per image the signed 64-bit byte offset of its pixels from the FIRST
+    image's (low word, high word -- any two device addresses work, the images need not share an allocation), h, w and the
+    resize target (oh, ow).  Staged through pinned memory with an asynchronous copy; build it OUTSIDE a graph capture."""
+    import numpy as np
+    base = _u8(images[0])
+    rows = []
+    for im, (oh, ow) in zip(images, sizes):
+        h, w = image_hw(im)
+        off = (_u8(im) - base) & 0xFFFFFFFFFFFFFFFF
+        rows.append([off & 0xFFFFFFFF, off >> 32, h, w, int(oh), int(ow)])
+    host = torch.from_numpy(np.asarray(rows, dtype=np.int64).astype(np.uint32).view(np.int32)).pin_memory()
+    return host.to(images[0].device, non_blocking=True)
+
+
+def decode_batch_u8(images, tab, batch_nhwc4, sizes, mean, std):
+    """All uint8 [h, w, 3] images of a batch (any sizes) -> samples 0..B-1 of the padded batch in ONE launch (``tab`` from
+    ``image_table`` over the same tensors)."""
     B, Hp, Wp, c4 = batch_nhwc4.shape
-    assert c4 == 4 and b0 + n <= B
+    assert c4 == 4 and len(images) == B == len(sizes) == tab.shape[0]
     m = (C.c_float * 3)(*mean)
     s = (C.c_float * 3)(*std)
+    L.check(L.load().vbg_decode_batch_u8(_u8(images[0]), _i32(tab), B, max(int(o[0]) for o in sizes), max(int(o[1]) for o in sizes),
+                                         _f32(batch_nhwc4), Hp - 6, Wp - 6, m, s, _stream()), "vbg_decode_batch_u8")
+
+
+def normalize_resize_pad_batch(imgs_nchw, batch_nhwc4, b0, oh, ow, mean, std):
+    """n same-shape images [n,3,h,w] (or uint8 [n,h,w,3]) -> samples b0..b0+n-1 of the padded batch, one launch."""
+    B, Hp, Wp, c4 = batch_nhwc4.shape
+    m = (C.c_float * 3)(*mean)
+    s = (C.c_float * 3)(*std)
+    if imgs_nchw.dtype == torch.uint8:
+        n, h, w, _ = imgs_nchw.shape
+        assert c4 == 4 and b0 + n <= B
+        L.check(L.load().vbg_normalize_resize_pad_u8(_u8(imgs_nchw, "images"), n, h, w, _f32(batch_nhwc4), b0, Hp - 6, Wp - 6, oh, ow,
+                                                     m, s, _stream()), "vbg_normalize_resize_pad_u8")
+        return
+    n, _, h, w = imgs_nchw.shape
+    assert c4 == 4 and b0 + n <= B
     L.check(L.load().vbg_normalize_resize_pad_batch(_f32(imgs_nchw, "images"), n, h, w, _f32(batch_nhwc4), b0, Hp - 6, Wp - 6, oh, ow,
                                                     m, s, _stream()), "vbg_normalize_resize_pad_batch")
 

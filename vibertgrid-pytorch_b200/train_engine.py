@@ -277,7 +277,8 @@ class TrainEngine:
         sizes = list(net.image_min_size)
         # transform.py:124-131,192-194: one draw per image from the training min-size list
         min_sizes = [float(sizes[int(torch.empty(1).uniform_(0.0, float(len(sizes))).item())]) for _ in image]
-        plan = plan_batch([tuple(im.shape[-2:]) for im in image], [int(s.shape[0]) for s in seg_indices],
+        standins = getattr(self, "_test_standins", False)
+        plan = plan_batch([ops.image_hw(im) if not standins else tuple(im.shape[-2:]) for im in image], [int(s.shape[0]) for s in seg_indices],
                           [int(c.shape[0]) for c in coors], int(corpus.shape[1]), min_sizes, float(net.image_max_size))
         # pinned staging + asynchronous copy: a pageable H2D copy would hold the host until the stream has drained, i.e. until
         # the previous step's kernels are done -- in a launch-bound step that bubble is paid in full
@@ -300,7 +301,7 @@ class TrainEngine:
         dev = st["corpus"].device
         named = [(n, p) for n, p in net.named_parameters() if p.requires_grad]
         params = [p for _, p in named]
-        key = (tuple(tuple(im.shape) for im in st["image"]), tuple(st["coors"].shape), tuple(st["seg_ids"].shape), tuple(st["corpus"].shape),
+        key = (tuple((tuple(im.shape), im.dtype) for im in st["image"]), tuple(st["coors"].shape), tuple(st["seg_ids"].shape), tuple(st["corpus"].shape),
                st["mask"] is None, min_sizes, dev.index, tuple(p.data_ptr() for p in params),
                tuple(b.data_ptr() for b in net.buffers()), float(net.bert_hidden_dropout), float(net.bert_attn_dropout),
                tuple(plan.seg_counts), tuple(int(v) for v in plan.view("tok_off")))
