@@ -123,9 +123,11 @@ def test_training_step_from_shard_loader(tmp_path, monkeypatch):
         synth.fill_state_dict_(net, 0)
         net = net.cuda().train()
         net.bert_hidden_dropout = net.bert_attn_dropout = 0.0
-        batch = next(iter(shards.ShardLoader(path, batches=[[0, 3]], device="cuda")))
-        if fmt == "float":
-            batch = _float_batch(batch)
+        if fmt == "u8":
+            batch = next(iter(shards.ShardLoader(path, batches=[[0, 3]], device="cuda")))
+        else:       # ToTensor on the HOST like the reference's dataset (torch's CUDA div-by-scalar multiplies by the reciprocal)
+            batch = _float_batch(next(iter(shards.ShardLoader(path, batches=[[0, 3]]))))
+            batch = [tuple(t.cuda() for t in x) if isinstance(x, tuple) else x.cuda() for x in batch]
         loss = net(*batch)
         loss.backward()
         losses[fmt] = (float(loss), float(net.backbone.conv_1[0].weight.grad.abs().sum()) if hasattr(net.backbone, "conv_1") else 0.0)

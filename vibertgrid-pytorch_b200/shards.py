@@ -242,6 +242,8 @@ class ShardLoader:
         self.device = None if device is None else torch.device(device)
         if self.device is not None and self.device.type != "cuda":
             raise RuntimeError("ShardLoader uploads to a CUDA device (device=None yields pinned host batches)")
+        if self.device is not None and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.depth, self.threads = max(2, int(depth)), int(threads)
         self.epoch = 0
         self.h2d_bytes = 0                                  # staged bytes copied to the device so far (bench.py reads it)
