@@ -596,6 +596,7 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step measurement (the `train_step` object)")
     ap.add_argument("--no-input-pipeline", action="store_true", help="skip the shard-fed e2e measurement (the `input_pipeline` object)")
+    ap.add_argument("--no-serving", action="store_true", help="skip the serving-latency measurement (the `serving` object)")
     ap.add_argument("--no-library-bar", action="store_true", help="skip the library-kernel bar (reference eager on the GPU, cuBLAS, torchvision)")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="train: the line's value / ms_per_step are the TRAINING step (forward + backward + all-reduce + optimizers)")
@@ -744,7 +745,7 @@ def main():
             line["roofline"]["hbm_scatter_b2b_frac"] = round(kr["grid_scatter"].get("back_to_back", {}).get("frac", 0.0), 4)
             line["roofline"]["hbm_roi_align_frac"] = round(kr["roi_align"]["frac"], 4)
             line["peaks"] = peaks
-        if world == 1 and args.mode == "forward":
+        if world == 1 and args.mode == "forward" and not args.no_serving:
             try:
                 line["serving"] = serving_latency(dev)
                 line["e2e"]["serve_cfg1_p50_ms"] = round(line["serving"]["p50_ms"], 3)

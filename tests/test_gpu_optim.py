@@ -82,7 +82,7 @@ def test_fused_optimizers_step_the_model(tmp_path, monkeypatch):
     dev = [tuple(t.cuda() for t in x) if isinstance(x, tuple) else x.cuda() for x in batch]
     sd0 = {k: v.clone() for k, v in net.state_dict().items()}
     res = []
-    for fused in (False, False, True):          # torch twice: the run-to-run noise of the atomic scatter-adds is the yardstick
+    for fused in (False, False, True):          # torch twice: the training step is deterministic, so the two must agree bit for bit
         net.load_state_dict(sd0)
         bert = [p for n, p in net.named_parameters() if "bert_model" in n]
         cnn = [p for n, p in net.named_parameters() if "bert_model" not in n]
@@ -92,16 +92,23 @@ def test_fused_optimizers_step_the_model(tmp_path, monkeypatch):
         from vibertgrid_pytorch_b200.train_engine import TrainEngine
         net._train_engine = TrainEngine(net)
         net._train_engine.use_graphs = False
+        snaps = []
         for _ in range(2):
             o_c.zero_grad(); o_b.zero_grad()
             net(*dev).backward()
             o_c.step(); o_b.step()
-        res.append({k: v.clone() for k, v in net.state_dict().items() if v.dtype == torch.float32})
-    # The runs repeat the same steps; their gradients agree only to the summation order of the atomic scatter-adds (ROI-align /
-    # embedding backward), which this fixture's tiny-batch BatchNorms amplify.  Yardstick: torch's optimizers run twice.
+            snaps.append({k: v.clone() for k, v in net.state_dict().items() if v.dtype == torch.float32})
+        res.append(snaps)
+
     def dev(a, b, keys):
         return max(float((a[k] - b[k]).abs().max()) / max(1e-3, float(a[k].abs().max())) for k in keys)
-    keys = [k for k in res[0] if not k.endswith("attention.self.key.bias")]
-    noise, fused_dev = dev(res[0], res[1], keys), dev(res[0], res[2], keys)
-    print(f"parameters after 2 model steps: torch vs torch (atomics noise) {noise:.2e}, torch vs fused {fused_dev:.2e}")
-    assert fused_dev <= 3.0 * noise + 1e-5
+    keys = [k for k in res[0][0] if not k.endswith("attention.self.key.bias")]
+    repeat = dev(res[0][1], res[1][1], keys)
+    one, two = dev(res[0][0], res[2][0], keys), dev(res[0][1], res[2][1], keys)
+    print(f"parameters, torch vs torch after 2 steps {repeat:.2e}; torch vs fused after 1 step {one:.2e}, after 2 steps {two:.2e}")
+    assert repeat == 0.0, "the training step is deterministic: two identical runs must agree exactly"
+    # step 1 starts from identical gradients: only the optimizers' own rounding differs (AdamW's first update is lr * g / (|g| + eps),
+    # ill-conditioned where |g| ~ eps, hence the 1e-3 floor in the denominator of `dev`)
+    assert one <= 2e-5
+    # step 2 sees gradients of parameters that differ by ~1e-7, amplified by this fixture's tiny-batch BatchNorms
+    assert two <= 5e-3

@@ -111,6 +111,18 @@ def test_collate_matches_reference_collate(tmp_path, tokenizer, train):
             assert [list(t) for t in got[6]] == [list(t) for t in want[6]] and list(got[7]) == list(want[7])
 
 
+@pytest.mark.parametrize("train", [True, False])
+def test_convert_dataset_equals_direct_conversion(tmp_path, tokenizer, train):
+    """The generic converter (consumes the reference dataset's own items: works for its SROIE / EPHOIE / FUNSD datasets alike)
+    writes byte for byte the shard the restated SROIE rules write."""
+    split = make_tree(str(tmp_path), train)
+    ds = reference_dataset(split, tokenizer, train)
+    a, b = str(tmp_path / "a.vbgshard"), str(tmp_path / "b.vbgshard")
+    assert shards.convert_sroie_split(split, tokenizer, a, train=train, files=ds.filename_list) == len(ds)
+    assert shards.convert_dataset(ds, b, train=train) == len(ds)
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
 @pytest.mark.parametrize("n,world,bs,shuffle", [(10, 1, 3, False), (10, 4, 2, True), (7, 2, 2, True), (3, 4, 1, False), (16, 8, 2, True)])
 def test_default_batches_are_torch_samplers(n, world, bs, shuffle):
     from torch.utils.data import BatchSampler, DistributedSampler

@@ -227,6 +227,24 @@ __global__ void split_bf16_kernel(const float* __restrict__ w, long long n, __nv
   }
 }
 
+// The same split, four elements per thread: one 16-byte load, two 8-byte stores (the training step re-splits every fp32
+// activation and gradient that feeds a tensor-core kernel: ~340 launches per step, so this is a bandwidth kernel).
+__global__ void __launch_bounds__(256) split_bf16_vec_kernel(const float4* __restrict__ w, long long n4, uint2* __restrict__ hi,
+                                                             uint2* __restrict__ lo) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (; i + step < n4; i += 2 * step) {                    // two independent loads in flight per thread
+    const float4 a = __ldg(w + i), b = __ldg(w + i + step);
+    uint2 h, l;
+    split4(a, h, l); hi[i] = h; lo[i] = l;
+    split4(b, h, l); hi[i + step] = h; lo[i + step] = l;
+  }
+  if (i < n4) {
+    uint2 h, l;
+    split4(__ldg(w + i), h, l); hi[i] = h; lo[i] = l;
+  }
+}
+
 // ------------------------------------------------------------------ host side
 static bool map_w_bf16(CUtensorMap* tm, const void* base, long long rows, long long cols, long long ld, int box_rows) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -361,6 +379,14 @@ int split_bf16(const float* w, long long n, void* hi, void* lo, cudaStream_t s) 
   if (n == 0) return VBG_OK;
   int blocks = (int)((n + 255) / 256);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if ((n & 3) == 0 && aligned16(w) && (reinterpret_cast<uintptr_t>(hi) & 7) == 0 && (reinterpret_cast<uintptr_t>(lo) & 7) == 0) {
+    const long long n4 = n / 4;
+    int b4 = (int)((n4 + 511) / 512);                        // two float4 per thread
+    if (b4 > kNumSMs * 8) b4 = kNumSMs * 8;
+    if (b4 < 1) b4 = 1;
+    split_bf16_vec_kernel<<<b4, 256, 0, s>>>(reinterpret_cast<const float4*>(w), n4, reinterpret_cast<uint2*>(hi), reinterpret_cast<uint2*>(lo));
+    return check_launch("vbg_split_bf16");
+  }
   split_bf16_kernel<<<blocks, 256, 0, s>>>(w, n, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
   return check_launch("vbg_split_bf16");
 }

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(256) colreduce2_kernel(F f, long long rows, in
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   long long r1 = r0 + rows_per_cta; if (r1 > rows) r1 = rows;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+#pragma unroll 4
   for (long long r = r0 + rl; r < r1; r += RL) f((size_t)r * C4 + c, c, a, b);
   sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b;
   __syncthreads();
@@ -233,6 +234,18 @@ __global__ void dropout_kernel(const float* __restrict__ x, long long n, float p
                                const unsigned long long* __restrict__ step_seed, float* __restrict__ y) {
   if (step_seed) seed ^= __ldg(step_seed) * 0xD6E8FEB86659FD93ull;
   const float s = 1.0f / (1.0f - p);
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {     // same mask, 16-byte accesses
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* y4 = reinterpret_cast<float4*>(y);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += (long long)gridDim.x * blockDim.x) {
+      float4 v = __ldg(x4 + i);
+      const unsigned long long e = 4ull * (unsigned long long)i;
+      v.x = v.x * keep_of(seed, e, p) * s; v.y = v.y * keep_of(seed, e + 1, p) * s;
+      v.z = v.z * keep_of(seed, e + 2, p) * s; v.w = v.w * keep_of(seed, e + 3, p) * s;
+      y4[i] = v;
+    }
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = __ldg(x + i) * keep_of(seed, (unsigned long long)i, p) * s;
 }
@@ -590,6 +603,41 @@ colsum_kernel(const void* __restrict__ x, long long x_plane, long long rows, int
   }
 }
 
+// fp32 input with cols % 4 == 0: a warp reads 512 contiguous bytes of a row (lane = float4 of 4 columns), 8 row lanes per CTA,
+// four rows in flight per thread; per column the rows are still added in ascending order within a lane, lanes in fixed order.
+__global__ void __launch_bounds__(256)
+colsum4_kernel(const float4* __restrict__ x, long long rows, int cols4, long long rows_per_cta, float4* __restrict__ partial) {
+  __shared__ float4 part[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  long long r1 = r0 + rows_per_cta; if (r1 > rows) r1 = rows;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < cols4) {
+    const float4* p = x + c;
+    long long r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      const float4 v0 = __ldg(p + (size_t)r * cols4), v1 = __ldg(p + (size_t)(r + 8) * cols4);
+      const float4 v2 = __ldg(p + (size_t)(r + 16) * cols4), v3 = __ldg(p + (size_t)(r + 24) * cols4);
+      acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+      acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+      acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+      acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+    }
+    for (; r < r1; r += 8) {
+      const float4 v = __ldg(p + (size_t)r * cols4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c < cols4) {
+    float4 t = part[0][tx];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { const float4 u = part[i][tx]; t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w; }
+    partial[(size_t)blockIdx.y * cols4 + c] = t;
+  }
+}
+
 __global__ void sum_slabs_kernel(const float* __restrict__ partial, int slabs, long long n, float* __restrict__ out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float a = 0.f;
@@ -857,8 +905,9 @@ extern "C" int vbg_upsample_split_bwd(const float* d1, const float* d2, int B, i
   return check_launch("vbg_upsample_split_bwd");
 }
 
-static int colsum_geometry(long long rows, int cols, long long& rows_per_cta) {
-  const int col_tiles = cdiv(cols, 32);
+static bool colsum_vec(const void* x, long long x_plane, int cols) { return x_plane == 0 && (cols & 3) == 0 && aligned16(x); }
+static int colsum_geometry(long long rows, int cols, long long& rows_per_cta, bool vec = false) {
+  const int col_tiles = vec ? cdiv(cols, 128) : cdiv(cols, 32);
   long long g = (kNumSMs * 8 + col_tiles - 1) / col_tiles;
   const long long max_g = (rows + 63) / 64;
   if (g > max_g) g = max_g;
@@ -868,17 +917,23 @@ static int colsum_geometry(long long rows, int cols, long long& rows_per_cta) {
 }
 
 extern "C" long long vbg_colsum_workspace(long long rows, int cols) {
-  long long rpc; const int g = colsum_geometry(rows, cols, rpc);
+  long long rpc; int g = colsum_geometry(rows, cols, rpc);
+  if ((cols & 3) == 0) { const int gv = colsum_geometry(rows, cols, rpc, true); if (gv > g) g = gv; }    // the float4 form splits rows finer
   return g > 1 ? (long long)g * cols * 4 : 0;
 }
 
 extern "C" int vbg_colsum(const void* x, long long x_plane, long long rows, int cols, float* out, float* workspace, size_t ws_bytes,
                           vbg_stream_t stream) {
   VBG_REQUIRE(x && out && rows > 0 && cols > 0 && x_plane >= 0, "vbg_colsum: bad arguments");
-  long long rpc; int g = colsum_geometry(rows, cols, rpc);
+  const bool vec = colsum_vec(x, x_plane, cols) && aligned16(out) && (!workspace || aligned16(workspace));
+  long long rpc; int g = colsum_geometry(rows, cols, rpc, vec);
   if (g > 1 && (!workspace || (size_t)g * cols * 4 > ws_bytes)) { g = 1; rpc = rows; }       // no workspace: one CTA row per column tile
   cudaStream_t s = as_stream(stream);
-  colsum_kernel<<<dim3(cdiv(cols, 32), g), 256, 0, s>>>(x, x_plane, rows, cols, rpc, g > 1 ? workspace : out);
+  if (vec)
+    colsum4_kernel<<<dim3(cdiv(cols, 128), g), 256, 0, s>>>(reinterpret_cast<const float4*>(x), rows, cols / 4, rpc,
+                                                            reinterpret_cast<float4*>(g > 1 ? workspace : out));
+  else
+    colsum_kernel<<<dim3(cdiv(cols, 32), g), 256, 0, s>>>(x, x_plane, rows, cols, rpc, g > 1 ? workspace : out);
   if (g > 1) sum_slabs_kernel<<<grid_for(cols, 256), 256, 0, s>>>(workspace, g, cols, out);
   return check_launch("vbg_colsum");
 }

@@ -128,6 +128,26 @@ def convert_sroie_split(split_dir: str, tokenizer, out_path: str, train: bool = 
     return write_shard(out_path, (sroie_document(split_dir, f, tokenizer, train) for f in names))
 
 
+def convert_dataset(dataset, out_path: str, train: bool = True, indices: Optional[Sequence[int]] = None) -> int:
+    """Any map-style dataset in the reference's item layout -- ``(ToTensor image f32 [3,h,w], seg_indices, seg_classes, coors,
+    corpus[, ocr_text, key_dict])``, i.e. the reference's own ``SROIEDataset`` / ``EPHOIEDataset`` / ``FUNSDDataset``
+    (data/*_dataset.py) -- -> one shard, offline: each item is produced once by the dataset's own code and stored; the pixels
+    go back to the bytes ``ToTensor`` divided by 255 (exact: ``round(x * 255)`` inverts ``byte / 255`` for every byte, checked)."""
+    def docs():
+        for i in (range(len(dataset)) if indices is None else indices):
+            item = dataset[i]
+            img = item[0]
+            u8 = (img * 255.0).round().clamp_(0, 255).to(torch.uint8)
+            if not torch.equal(u8.to(torch.float32).div(255), img):
+                raise ValueError(f"document {i}: the image is not ToTensor of 8-bit pixels; shards hold uint8 pixels")
+            d = dict(image=u8.permute(1, 2, 0).contiguous().numpy(), seg_ids=item[1].numpy(), classes=item[2].numpy().reshape(-1),
+                     coors=item[3].numpy().reshape(-1, 4), corpus=item[4].numpy())
+            if not train:
+                d["meta"] = {"text": list(item[5]), "key": item[6]}
+            yield d
+    return write_shard(out_path, docs())
+
+
 # ------------------------------------------------------------------ native reader
 _LAYOUT_N = 13
 
