@@ -1,7 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-bash scripts/jobs/tests.sh
-cp gpurun_out/pytest_gpu.log gpurun_out/r2_pytest_gpu_full_c.log
-bash scripts/jobs/train_profile.sh > gpurun_out/r2_train_profile_c.txt 2>&1; head -45 gpurun_out/r2_train_profile_c.txt | cut -c1-160
-bash scripts/jobs/ncu_launches.sh > gpurun_out/r2_launches_summary.txt 2>&1
-head -30 gpurun_out/r2_launches_summary.txt
+timeout 900 python -m pytest tests/test_gpu_train_graph.py tests/test_gpu_train_step.py tests/test_gpu_autograd.py tests/test_gpu_optim.py tests/test_gpu_shards.py -m gpu -q -x --timeout 600 2>&1 | grep -E "passed|failed|FAILED|Error|error|assert |^E " | tail -15
+for prep in 1 0; do
+VBG_TRAIN_SIDE_PREP=$prep timeout 600 python bench.py --mode train --steps 15 --no-roofline --no-cpu-baseline --no-library-bar --no-input-pipeline > gpurun_out/r2_bench_train_prep$prep.json 2> gpurun_out/r2_bench_train_prep$prep.err; echo "bench prep=$prep exit $?"
+python - <<PY
+import json
+j = json.loads(open('gpurun_out/r2_bench_train_prep$prep.json').read().strip().splitlines()[-1])
+print('prep=$prep', {k: j['train_step'].get(k) for k in ('value','ms_per_step','gpu_launches','loss_first','loss_last','peak_mem_gib')})
+PY
+tail -2 gpurun_out/r2_bench_train_prep$prep.err
+done

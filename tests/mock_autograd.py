@@ -25,6 +25,14 @@ def linear(x, weight, bias=None):
     return F.linear(x, weight, bias)
 
 
+def pack_rows(*parts):
+    return torch.cat(parts, 0)
+
+
+def leaf_view(p, *shape):
+    return p.view(*shape)
+
+
 class _Apply:
     def __init__(self, fn):
         self.apply = fn

@@ -32,22 +32,163 @@ def _fp32():
     return os.environ.get("VBG_PRECISION", "").lower() == "fp32"
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# Weight-gradient work on a SIDE STREAM of the captured training step.
+#
+# The backward's critical path is the data-gradient chain (dY -> dgrad GEMM -> elementwise backward -> next dgrad ...); the
+# weight gradients, bias column sums and the stem / embedding-table gradients feed nothing but the gradient arena.  Inside the
+# whole-step capture (train_engine.TrainEngine._graphed_loss) they are therefore launched on a second stream right after the
+# layer's data gradient, and the main stream joins that stream ONCE, after ``torch.autograd.grad`` has returned: in the CUDA
+# graph they become branches that run beside the following layers' bandwidth-bound elementwise kernels (a persistent tcgen05
+# CTA leaves the SM's LSU / most of its threads idle).  Safety rules:
+#   * only when the gradient's consumer launches no kernel before the join: the parameter is a LEAF of the tape, or a tensor
+#     marked by ``pack_rows`` / ``leaf_view`` below (their backward is pure view arithmetic);
+#   * every main-stream tensor the side kernels read (dY planes, saved activation planes, dY) is kept referenced until the
+#     join, so the caching allocator cannot hand its memory to a later main-stream kernel;
+#   * outside a capture (eager steps, DDP, tests of single Functions) ``SIDE`` is None and everything runs in line.
+class _SideWork:
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device)
+        self.keep = []
+        self.launched = 0
+
+
+SIDE = None
+
+
+def side_begin(device):
+    global SIDE
+    SIDE = _SideWork(device)
+    return SIDE
+
+
+def side_join():
+    """Main stream waits for everything deferred so far; releases the kept tensors.  Idempotent."""
+    global SIDE
+    s, SIDE = SIDE, None
+    if s is not None and s.launched:
+        torch.cuda.current_stream().wait_stream(s.stream)
+    if s is not None:
+        s.keep.clear()
+
+
+def _can_defer(*tensors):
+    """Evaluated in a Function's forward (the side stream itself exists only while the captured backward runs)."""
+    return all(t is None or t.is_leaf or getattr(t, "_vbg_defer_ok", False) for t in tensors)
+
+
+def _deferred(fn, ok, *keep):
+    """``fn()`` on the side stream (after everything enqueued on the current stream so far) when ``ok``, else in line."""
+    s = SIDE
+    if s is None or not ok:
+        return fn()
+    s.stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s.stream):
+        out = fn()
+    s.launched += 1
+    s.keep.append((keep, out))
+    return out
+
+
+# Parameter-only preparation (bf16 planes of a weight, its transposed planes for the data gradient, conv weight repacks) on a
+# PREP STREAM of the captured training step: these kernels read nothing but parameters, so in the CUDA graph they form a chain
+# that depends on no activation and runs ahead of the forward, beside its tensor-core kernels; every consumer waits for its own
+# layer's event.  The backward's weight forms are produced in the forward call too, which takes them off the backward's
+# critical path.  Results are kept referenced until ``prep_end`` (their memory must not be recycled on the prep stream while a
+# main-stream kernel still reads them).  Eligible: leaves of the tape and tensors marked by ``pack_rows`` / ``leaf_view``.
+class _PrepWork:
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device)
+        self.keep = []
+
+
+PREP = None
+
+
+def prep_begin(device):
+    global PREP
+    PREP = _PrepWork(device)
+    PREP.stream.wait_stream(torch.cuda.current_stream())          # the prep stream joins the capture here, once
+    return PREP
+
+
+def prep_end():
+    global PREP
+    p, PREP = PREP, None
+    if p is not None:
+        torch.cuda.current_stream().wait_stream(p.stream)
+        p.keep.clear()
+
+
+def _prepped(fn, ok=True):
+    """``fn()`` (kernels over parameters only) on the prep stream; the current stream waits for exactly that work."""
+    p = PREP
+    if p is None or not ok:
+        return fn()
+    with torch.cuda.stream(p.stream):
+        out = fn()
+        ev = torch.cuda.Event()
+        ev.record(p.stream)
+    torch.cuda.current_stream().wait_event(ev)
+    p.keep.append(out)
+    return out
+
+
+class _PackRowsF(torch.autograd.Function):
+    """``torch.cat(parts, 0)`` whose backward hands every part a VIEW of the incoming gradient (no kernel): the packed QKV
+    weight / bias of a BERT layer stays eligible for the deferred weight gradient."""
+
+    @staticmethod
+    def forward(ctx, *parts):
+        ctx.rows = [int(p.shape[0]) for p in parts]
+        return _prepped(lambda: torch.cat([p.detach() for p in parts], 0), all(p.is_leaf for p in parts))
+
+    @staticmethod
+    def backward(ctx, g):
+        out, r0 = [], 0
+        for r in ctx.rows:
+            out.append(g[r0:r0 + r])
+            r0 += r
+        return tuple(out)
+
+
+def pack_rows(*parts):
+    t = _PackRowsF.apply(*parts)
+    t._vbg_defer_ok = all(p.is_leaf for p in parts)
+    return t
+
+
+def leaf_view(p, *shape):
+    """``p.view(shape)`` of a leaf parameter, marked: the view's backward is metadata only."""
+    t = p.view(*shape)
+    t._vbg_defer_ok = bool(p.is_leaf)
+    return t
+
+
 class LinearPS(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         if x.dim() != 2 or weight.shape[1] != x.shape[1] or weight.shape[0] % 64 or weight.shape[1] % 64:
             raise ValueError("LinearPS: x [M, K], weight [N, K] with N and K multiples of 64")
-        w = weight.detach().contiguous()
         ep = ops.make_epilogue(None, None if bias is None else bias.detach())
+        ctx.wt = None
         if _fp32():
+            w = weight.detach().contiguous()
             y = ops.gemm(x.detach().contiguous(), w, ep=ep, precision=ops.PREC_FP32)
             ctx.save_for_backward(x, weight)
         else:
+            param_only = _can_defer(weight) or (weight._base is not None and _can_defer(weight._base))
+
+            def weight_forms():          # forward planes and, when the input needs a gradient, the [K, N] planes of the data gradient
+                w_ = weight.detach().contiguous()
+                return w_, ops.split_bf16(w_), (ops.transpose_split(w_) if PREP is not None and x.requires_grad else None)
+            w, ws, ctx.wt = _prepped(weight_forms, param_only)
             xs = ops.to_split(x.detach().contiguous())
-            y = ops.gemm(xs, w, ep=ep, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w))
+            y = ops.gemm(xs, w, ep=ep, precision=ops.PREC_BF16X3, W_split=ws)
             ctx.save_for_backward(xs.t, weight)          # the planes are what the weight-gradient kernel reads (same bytes as x)
         ctx.planes = not _fp32()
         ctx.has_bias = bias is not None
+        ctx.defer = _can_defer(weight, bias)
         return y
 
     @staticmethod
@@ -62,13 +203,14 @@ class LinearPS(torch.autograd.Function):
         if ctx.needs_input_grad[0] and _fp32():
             dx = ops.gemm(dy, weight.detach().t().contiguous(), precision=ops.PREC_FP32)
         elif ctx.needs_input_grad[0]:
-            wt = ops.transpose_split(weight.detach().contiguous())                 # [K, N] planes
+            wt = ctx.wt if ctx.wt is not None else ops.transpose_split(weight.detach().contiguous())     # [K, N] planes
             dx = ops.gemm(dys, weight.detach().t(), precision=ops.PREC_BF16X3, W_split=wt.t, N=K, K=N, ldw=N)
-        if ctx.needs_input_grad[1]:
+        want_w, want_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+
+        def param_grads():
             # MN-major tcgen05 operands straight from the row-major planes (no transposes)
-            dw = ops.linear_wgrad(dys, xs)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = ops.colsum(dy)
+            return (ops.linear_wgrad(dys, xs) if want_w else None), (ops.colsum(dy) if want_b else None)
+        dw, db = _deferred(param_grads, ctx.defer, dys, xs, dy)
         return dx, dw, db
 
 
@@ -167,15 +309,22 @@ class ConvPS(torch.autograd.Function):
     def forward(ctx, x, w_oihw, bias, stride, pad):
         w = w_oihw.detach()
         Cout, Cin, kh, kw = w.shape
-        w_ohwi = ops.repack_oihw_to_ohwi(_c(w)) if kh * kw > 1 else _c(w.reshape(Cout, 1, 1, Cin))
+
+        def weight_forms():              # OHWI repack, its planes and, when the input needs a gradient, the data-gradient planes
+            w_ohwi_ = ops.repack_oihw_to_ohwi(_c(w)) if kh * kw > 1 else _c(w.reshape(Cout, 1, 1, Cin))
+            fp = _fp32()
+            return (w_ohwi_, None if fp else ops.split_bf16(w_ohwi_),
+                    ops.conv_dgrad_weight(w_ohwi_) if (PREP is not None and not fp and x.requires_grad) else None)
+        w_ohwi, ws, ctx.wd = _prepped(weight_forms, _can_defer(w_oihw))
         xs = ops.to_split(_c(x.detach()))
         ep = ops.make_epilogue(None, bias.detach()) if bias is not None else None
         if _fp32():
             y = ops.conv2d(_c(x.detach()), w_ohwi, stride, pad, ep=ep, precision=ops.PREC_FP32)
         else:
-            y = ops.conv2d(xs, w_ohwi, stride, pad, ep=ep, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w_ohwi))
+            y = ops.conv2d(xs, w_ohwi, stride, pad, ep=ep, precision=ops.PREC_BF16X3, W_split=ws)
         ctx.save_for_backward(xs.t, w_ohwi)
         ctx.cfg = (stride, pad, bias is not None)
+        ctx.defer = _can_defer(w_oihw, bias)
         return y
 
     @staticmethod
@@ -194,7 +343,7 @@ class ConvPS(torch.autograd.Function):
             src = dy if stride == 1 else ops.expand2x(dy, H - kh + 1 + 2 * pad, W - kw + 1 + 2 * pad, 1.0, zero_insert=True)
             dx = ops.conv2d(src, wf, 1, kh - 1 - pad, precision=ops.PREC_FP32)
         elif ctx.needs_input_grad[0]:
-            wd = ops.conv_dgrad_weight(w_ohwi)                              # planes [2, Cin, kh, kw, Cout]
+            wd = ctx.wd if ctx.wd is not None else ops.conv_dgrad_weight(w_ohwi)      # planes [2, Cin, kh, kw, Cout]
             if stride == 1:
                 dx = ops.conv2d(dys, wd[0], 1, kh - 1 - pad, precision=ops.PREC_BF16X3, W_split=wd)
             elif kh == 1 and kw == 1 and pad == 0:                          # 1x1 / 2: a GEMM on the coarse lattice, then spread
@@ -204,10 +353,12 @@ class ConvPS(torch.autograd.Function):
             else:                                                           # dY onto the stride-1 lattice, then a stride-1 conv
                 dyz = ops.expand2x(dy, H - kh + 1 + 2 * pad, W - kw + 1 + 2 * pad, 1.0, zero_insert=True)
                 dx = ops.conv2d(ops.to_split(dyz), wd[0], 1, kh - 1 - pad, precision=ops.PREC_BF16X3, W_split=wd)
-        if ctx.needs_input_grad[1]:
-            dw = ops.conv2d_wgrad(dys, xs, kh, kw, stride, pad).permute(0, 3, 1, 2).contiguous()
-        if has_bias and ctx.needs_input_grad[2]:
-            db = ops.colsum(dy.view(-1, Cout))
+        want_w, want_b = ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
+
+        def param_grads():
+            return ((ops.conv2d_wgrad(dys, xs, kh, kw, stride, pad).permute(0, 3, 1, 2).contiguous() if want_w else None),
+                    (ops.colsum(dy.view(-1, Cout)) if want_b else None))
+        dw, db = _deferred(param_grads, ctx.defer, dys, xs, dy)
         return dx, dw, db, None, None
 
 
@@ -222,13 +373,15 @@ class StemF(torch.autograd.Function):
         else:
             y = ops.stem_conv(x4, w774, precision=ops.PREC_BF16X3, W_split=ops.split_bf16(w256))
         ctx.save_for_backward(x4)
+        ctx.defer = _can_defer(w_oihw)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         (x4,) = ctx.saved_tensors
-        dw = ops.stem_wgrad(x4, _c(dy))                                     # [64, 7, 7, 4]
-        return None, dw[..., :3].permute(0, 3, 1, 2).contiguous()
+        dy = _c(dy)
+        dw = _deferred(lambda: ops.stem_wgrad(x4, dy)[..., :3].permute(0, 3, 1, 2).contiguous(), ctx.defer, x4, dy)   # via [64, 7, 7, 4]
+        return None, dw
 
 
 def sync_batch_stats(mean, var, rows, eps, group):
@@ -400,6 +553,7 @@ class EmbedSumF(torch.autograd.Function):
     def forward(ctx, word, position, type_emb, ids, pos):
         ctx.save_for_backward(ids, pos)
         ctx.shapes = (word.shape[0], position.shape[0], type_emb.shape)
+        ctx.defer = _can_defer(word, position, type_emb)
         idl, pol = ids.long(), pos.long()
         return word.detach().index_select(0, idl) + position.detach().index_select(0, pol) + type_emb.detach()[0]
 
@@ -408,9 +562,13 @@ class EmbedSumF(torch.autograd.Function):
         ids, pos = ctx.saved_tensors
         V, Pm, tshape = ctx.shapes
         dx = _c(dx)
-        dword, dpos = ops.embed_bwd(dx, ids, pos, V, Pm)
-        dtype = torch.zeros(tshape, dtype=torch.float32, device=dx.device)
-        dtype[0] = ops.colsum(dx)
+
+        def tables():
+            dword, dpos = ops.embed_bwd(dx, ids, pos, V, Pm)
+            dtype = torch.zeros(tshape, dtype=torch.float32, device=dx.device)
+            dtype[0] = ops.colsum(dx)
+            return dword, dpos, dtype
+        dword, dpos, dtype = _deferred(tables, ctx.defer, dx, ids, pos)
         return dword, dpos, dtype, None, None
 
 

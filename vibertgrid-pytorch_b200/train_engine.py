@@ -84,6 +84,8 @@ class TrainEngine:
         import os
         self.net = net
         self.use_graphs = os.environ.get("VBG_TRAIN_GRAPHS", "1") != "0"
+        self.side_wgrad = os.environ.get("VBG_TRAIN_SIDE_WGRAD", "1") != "0"
+        self.side_prep = os.environ.get("VBG_TRAIN_SIDE_PREP", "1") != "0"
         self.max_graphs = 4
         self._graphs = {}
         self.graph_replays = 0
@@ -130,7 +132,7 @@ class TrainEngine:
         k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
         if k == 1 and s == 1 and p == 0:
             B, H, W, Cin = x.shape
-            y = A.linear(x.reshape(B * H * W, Cin), conv.weight.view(conv.out_channels, Cin), conv.bias)
+            y = A.linear(x.reshape(B * H * W, Cin), A.leaf_view(conv.weight, conv.out_channels, Cin), conv.bias)
             return y.view(B, H, W, conv.out_channels)
         return A.ConvPS.apply(x, conv.weight, conv.bias, s, p)
 
@@ -178,8 +180,8 @@ class TrainEngine:
         x = drop(x)
         for lyr in bm.encoder.layer:
             sa = lyr.attention.self
-            wqkv = torch.cat([sa.query.weight, sa.key.weight, sa.value.weight], 0)
-            bqkv = torch.cat([sa.query.bias, sa.key.bias, sa.value.bias], 0)
+            wqkv = A.pack_rows(sa.query.weight, sa.key.weight, sa.value.weight)       # cat whose backward is three views
+            bqkv = A.pack_rows(sa.query.bias, sa.key.bias, sa.value.bias)
             qkv = A.linear(x, wqkv, bqkv)
             ctx = A.AttentionF.apply(qkv, cu, plan.nseq, plan.max_len, heads, p_attn, _rand_seed() if p_attn > 0.0 else 0, step_seed)
             ao = lyr.attention.output
@@ -330,8 +332,22 @@ class TrainEngine:
                 aliases = {id(p_): p_.detach().requires_grad_() for _, p_ in named}
                 with _parameters_as(net, aliases):
                     with torch.enable_grad():
-                        loss = self._forward(plan, static)
-                        grads = torch.autograd.grad(loss, [aliases[id(p_)] for p_ in params], allow_unused=True)
+                        # parameter-only preparation (weight planes, transposes, repacks) runs ahead on a prep stream
+                        # (autograd.py "_PrepWork"); joined after the backward, when its last consumer has been enqueued
+                        if self.side_prep:
+                            A.prep_begin(dev)
+                        try:
+                            loss = self._forward(plan, static)
+                            # weight gradients / bias sums / table gradients run on a side stream beside the data-gradient
+                            # chain and are joined once, below (autograd.py "_SideWork")
+                            if self.side_wgrad:
+                                A.side_begin(dev)
+                            try:
+                                grads = torch.autograd.grad(loss, [aliases[id(p_)] for p_ in params], allow_unused=True)
+                            finally:
+                                A.side_join()
+                        finally:
+                            A.prep_end()
                 used = [(p_, g_) for p_, g_ in zip(params, grads) if g_ is not None]
                 # one flat arena, gradients as views (the N > 1 bench averages it with a single bucketed all-reduce)
                 arena = torch.empty(sum(g_.numel() for _, g_ in used), dtype=torch.float32, device=dev)
