@@ -33,6 +33,10 @@ def leaf_view(p, *shape):
     return p.view(*shape)
 
 
+def _deferred(fn, ok, *keep):
+    return fn()
+
+
 class _Apply:
     def __init__(self, fn):
         self.apply = fn

@@ -117,14 +117,17 @@ class TrainEngine:
         y = A.BatchNormTrainF.apply(x, bn.weight, bn.bias, residual, relu, bn.eps, stats, self._sync_group(bn))
         if bn.track_running_stats and bn.running_mean is not None:
             mean, var, n = stats[0]
-            with torch.no_grad():
-                bn.num_batches_tracked += 1
-                m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-                bn.running_mean.mul_(1.0 - m).add_(mean, alpha=m)
-                if isinstance(n, torch.Tensor):               # SyncBatchNorm: the global row count lives on the device
-                    bn.running_var.mul_(1.0 - m).add_(var * (n / (n - 1.0).clamp_min(1.0)).float(), alpha=m)
-                else:
-                    bn.running_var.mul_(1.0 - m).add_(var, alpha=m * n / max(n - 1, 1))
+
+            def update():         # five tiny kernels per BatchNorm that nothing in the step reads: off the main stream when captured
+                with torch.no_grad():
+                    bn.num_batches_tracked += 1
+                    m = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                    bn.running_mean.mul_(1.0 - m).add_(mean, alpha=m)
+                    if isinstance(n, torch.Tensor):               # SyncBatchNorm: the global row count lives on the device
+                        bn.running_var.mul_(1.0 - m).add_(var * (n / (n - 1.0).clamp_min(1.0)).float(), alpha=m)
+                    else:
+                        bn.running_var.mul_(1.0 - m).add_(var, alpha=m * n / max(n - 1, 1))
+            A._deferred(update, True, mean, var, n)
         return y
 
     @staticmethod
@@ -337,12 +340,13 @@ class TrainEngine:
                         if self.side_prep:
                             A.prep_begin(dev)
                         try:
-                            loss = self._forward(plan, static)
-                            # weight gradients / bias sums / table gradients run on a side stream beside the data-gradient
-                            # chain and are joined once, below (autograd.py "_SideWork")
+                            # weight gradients / bias sums / table gradients (backward) and the BatchNorm running-statistics
+                            # updates (forward) run on a side stream beside the main chain and are joined once, below
+                            # (autograd.py "_SideWork")
                             if self.side_wgrad:
                                 A.side_begin(dev)
                             try:
+                                loss = self._forward(plan, static)
                                 grads = torch.autograd.grad(loss, [aliases[id(p_)] for p_ in params], allow_unused=True)
                             finally:
                                 A.side_join()
