@@ -1,13 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_train_graph.py tests/test_gpu_train_step.py tests/test_gpu_zz_syncbn.py tests/test_gpu_reference_scripts.py -m gpu -q -x --timeout 600 2>&1 | grep -E "passed|failed|FAILED|Error|error|assert |^E " | tail -15
-timeout 600 python bench.py --mode train --steps 15 --no-roofline --no-cpu-baseline --no-library-bar --no-input-pipeline > gpurun_out/r2_bench_train_n1_b.json 2> gpurun_out/r2_bench_train_n1_b.err; echo "bench exit $?"
-python - <<PY
-import json
-j = json.loads(open('gpurun_out/r2_bench_train_n1_b.json').read().strip().splitlines()[-1])
-print({k: j['train_step'].get(k) for k in ('value','ms_per_step','gpu_launches','loss_first','loss_last','peak_mem_gib')})
-PY
-bash scripts/jobs/ncu_launches.sh > gpurun_out/r2_launches_summary.txt 2>&1
-head -32 gpurun_out/r2_launches_summary.txt
-VBG_TRAIN_GRAPHS=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'attn_bwd_tc_kernel|split_bf16_vec|colsum4|decode_batch|normalize_resize' -c 12 -o gpurun_out/r2_ncu_train_kernels -f python scripts/train_bench.py cfg2 2 > gpurun_out/r2_ncu_train_kernels.log 2>&1; echo "ncu exit $?"
-tail -3 gpurun_out/r2_ncu_train_kernels.log
+bash scripts/jobs/bench_n.sh 2 2>&1 | grep -v "^\[W\|^W1\|Warning" | cut -c1-1800
+timeout 900 python -m pytest tests/test_gpu_reference_scripts.py -m gpu -q -x -s --timeout 900 -k "train" 2>&1 | grep -E "^\[|passed|failed|Error" | tail -8
