@@ -163,12 +163,14 @@ def test_full_size_properties_cfg2(tmp_path, monkeypatch):
     assert int(full["status"].item()) == 0
 
 
-def test_cuda_graph_replay_equals_eager(tmp_path, monkeypatch):
+@pytest.mark.parametrize("name", ["tiny_simp", "tiny_rob"])
+def test_cuda_graph_replay_equals_eager(name, tmp_path, monkeypatch):
     """A batch signature seen twice is captured into a CUDA graph; replays with NEW data of the same shapes must equal the
-    eager launches bit for bit, and returned tensors must not alias the graph's static buffers."""
+    eager launches bit for bit, and returned tensors must not alias the graph's static buffers.  ``tiny_rob``: the RoBERTa
+    position ids (integer torch ops between the kernels, plan.roberta_position_ids) are part of the captured graph."""
     import dataclasses
     from vibertgrid_pytorch_b200 import synth
-    fx = load_golden("tiny_simp")
+    fx = load_golden(name)
     monkeypatch.chdir(tmp_path)
     cfg, kw, net, batch0 = build_case(fx["meta"])
     net = net.cuda().eval()

@@ -73,10 +73,6 @@ class ForwardEngine:
         self.precision = {"fp32": PREC_FP32, "tf32": PREC_TF32, "bf16x3": PREC_BF16X3}.get(env)
         self.launches = 0
         self.use_graphs = os.environ.get("VBG_CUDA_GRAPHS", "1") != "0"
-        if net.bert_model.cfg.get("roberta"):
-            # the RoBERTa position ids are integer torch ops between the kernels; their capture into a CUDA graph has not been
-            # run on a GPU yet (the eager path has: tests/test_gpu_forward.py[tiny_rob]), so this configuration stays eager
-            self.use_graphs = False
         self.fuse_aux_loss = os.environ.get("VBG_FUSED_AUX_LOSS", "1") != "0"
         # bf16x3 only: keep activations as bf16 hi/lo planes between the tensor-core kernels (no in-kernel conversion)
         self.presplit = os.environ.get("VBG_PRESPLIT", "1") != "0"

@@ -258,6 +258,11 @@ class ViBERTgridNet(nn.Module):
         return self._engine
 
     def inference(self, image, seg_indices, coors, corpus, mask):
+        # the reference's deployment path hands ``seg_indices`` over as HOST tensors (deployment/inference_preporcessing.py:184:
+        # only image / coors / corpus / mask are moved to the device; its model reads them with .item() in Python loops)
+        dev = corpus.device
+        if dev.type == "cuda" and any(s.device != dev for s in seg_indices):
+            seg_indices = tuple(s.to(dev, non_blocking=True) for s in seg_indices)
         out = self._get_engine().run(image, seg_indices, None, coors, corpus, mask, want_seg=False, crf_one_sequence=True)
         return out["pred_label"].clone() if out.get("static") else out["pred_label"]
 
