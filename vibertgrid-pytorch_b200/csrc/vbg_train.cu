@@ -438,6 +438,7 @@ roi_align_bwd_kernel(const float* __restrict__ dout, int B, int Hf, int Wf, int 
             cnt += room; k += last + 1;
           }
         }
+        __syncwarp();                                  // every lane has read next_k (a zero-trip scan has no ballot to converge on)
         if (tid == 0) { n_list = cnt; next_k = k; }
       }
       __syncthreads();

@@ -24,9 +24,20 @@ class _FusedBase(torch.optim.Optimizer):
         buffer: gradient tensors are fresh every step, so the table is rebuilt per step (a few hundred pointers)."""
         chunk = L.load().vbg_optim_chunk()
         n = len(rows)
-        host = getattr(self, "_host_tab", None)
-        if host is None or host.shape[0] < n:
-            host = self._host_tab = torch.empty((max(n, 64), 6), dtype=torch.int64).pin_memory()
+        # Pinned staging: a RING of host tables, each guarded by an event recorded after its asynchronous upload.  The host runs
+        # ahead of the device (a whole training step can be queued in front of the copy), so a single buffer would be rewritten
+        # with the NEXT call's pointers before the previous upload has executed (found by running the suite under
+        # compute-sanitizer, which slows the device down enough to expose it).
+        ring = getattr(self, "_host_ring", None)
+        if ring is None:
+            ring = self._host_ring = {"slots": [None] * 4, "i": 0}
+        ring["i"] = (ring["i"] + 1) % len(ring["slots"])
+        slot_h = ring["slots"][ring["i"]]
+        if slot_h is None or slot_h["buf"].shape[0] < n:
+            slot_h = ring["slots"][ring["i"]] = {"buf": torch.empty((max(n, 64), 6), dtype=torch.int64).pin_memory(), "ev": None}
+        if slot_h["ev"] is not None:
+            slot_h["ev"].synchronize()               # the upload that last read this buffer has completed
+        host = slot_h["buf"]
         dev = getattr(self, "_dev_tabs", None)
         if dev is None:
             dev = self._dev_tabs = {}
@@ -41,6 +52,8 @@ class _FusedBase(torch.optim.Optimizer):
         slot[2] ^= 1
         tab = slot[slot[2]]
         tab.copy_(host[:n], non_blocking=True)
+        slot_h["ev"] = torch.cuda.Event()
+        slot_h["ev"].record()
         return tab, first
 
     @staticmethod

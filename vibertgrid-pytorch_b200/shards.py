@@ -293,7 +293,7 @@ class ShardLoader:
                 if s["dev"] is not None:                    # growing a slot (rare): nothing may still read the old buffer
                     torch.cuda.synchronize(self.device)
                 s["dev"] = torch.empty(cap, dtype=torch.uint8, device=self.device)
-                s["free"] = None
+                s["free"] = s["copied"] = None
         return s
 
     def _finish(self, docs, views):
@@ -333,6 +333,8 @@ class ShardLoader:
                         return
                     lay = self.shard.layout(docs)
                     slot = self._slot(i, lay[0])
+                    if slot.get("copied") is not None:
+                        slot["copied"].synchronize()         # HOST wait: the upload that last read this pinned buffer has executed
                     self.shard.collate_into(docs, slot["host"], self.threads)
                     if slot["free"] is not None:
                         stream.wait_event(slot["free"])      # the consumer's kernels on this slot's previous batch
@@ -340,6 +342,7 @@ class ShardLoader:
                         slot["dev"][:lay[0]].copy_(slot["host"][:lay[0]], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(stream)
+                    slot["copied"] = ev
                     ready.put((i, docs, lay, ev))
                 ready.put(None)
             except BaseException as e:                       # surface producer failures in the consumer

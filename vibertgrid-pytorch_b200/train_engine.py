@@ -320,7 +320,10 @@ class TrainEngine:
             return self._forward(plan, st)
         if self._step_seed is None or self._step_seed.device != dev:
             self._step_seed = torch.zeros(1, dtype=torch.int64, device=dev)
-            self._seed_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+            # pinned staging ring: the host runs a step or more ahead of the device, so the word of step t must not be
+            # rewritten before its (asynchronous) upload has executed -- each slot is guarded by an event
+            self._seed_ring = [[torch.zeros(1, dtype=torch.int64).pin_memory(), None] for _ in range(8)]
+            self._seed_i = 0
         if ent["graph"] is None:               # second sighting: capture forward + backward
             static = {k: ([t.clone() for t in v] if isinstance(v, list) else (None if v is None else v.clone())) for k, v in st.items()}
             torch.cuda.synchronize()
@@ -370,8 +373,14 @@ class TrainEngine:
             for k in ("coors", "seg_ids", "cls", "corpus", "mask"):
                 if sd[k] is not None:
                     sd[k].copy_(st[k], non_blocking=True)
-        self._seed_host.random_(0, 2 ** 62)
-        self._step_seed.copy_(self._seed_host, non_blocking=True)
+        self._seed_i = (self._seed_i + 1) % len(self._seed_ring)
+        slot = self._seed_ring[self._seed_i]
+        if slot[1] is not None:
+            slot[1].synchronize()
+        slot[0].random_(0, 2 ** 62)
+        self._step_seed.copy_(slot[0], non_blocking=True)
+        slot[1] = torch.cuda.Event()
+        slot[1].record()
         ent["graph"].replay()
         self.graph_replays += 1
         self.kernel_launches += ent["launches"]
