@@ -306,6 +306,9 @@ VBG_API int vbg_expand2x(const float* x, int B, int Hi, int Wi, int C, int H, in
                  vbg_stream_t stream);
 /* erf-GELU: out = gelu(x) when dy == NULL, else out = dy * gelu'(x) */
 VBG_API int vbg_gelu(const float* x, const float* dy, long long n, float* out, vbg_stream_t stream);
+/* the same with x, dy and out each in either storage format (plane == 0: fp32; > 0: bf16 hi/lo planes `plane` elements apart) */
+VBG_API int vbg_gelu_x(const void* x, long long x_plane, const void* dy, long long dy_plane, long long n, void* out, long long out_plane,
+               vbg_stream_t stream);
 /* inverted dropout with a counter-based mask: y[i] = x[i] * keep(seed, i) / (1 - p); the same call is its own backward */
 VBG_API int vbg_dropout(const float* x, long long n, float p, unsigned long long seed, float* y, vbg_stream_t stream);
 /* 31-bit sampling keys key[i] = hash(seed, step_seed, i) for the device-side sampled / OHEM losses (pipeline/custom_loss.py:9-382

@@ -1,4 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out
-bash scripts/jobs/bench_n.sh 2 2>&1 | grep -v "^\[W\|^W1\|Warning" | cut -c1-1800
-timeout 900 python -m pytest tests/test_gpu_reference_scripts.py -m gpu -q -x -s --timeout 900 -k "train" 2>&1 | grep -E "^\[|passed|failed|Error" | tail -8
+timeout 900 python -m pytest tests/test_gpu_train_graph.py tests/test_gpu_train_step.py tests/test_gpu_autograd.py tests/test_gpu_attention_train.py tests/test_gpu_train_ops.py -m gpu -q -x --timeout 600 2>&1 | grep -E "passed|failed|FAILED|Error|error|assert |^E " | tail -15
+for pl in 1 0; do
+VBG_TRAIN_PLANES=$pl timeout 600 python bench.py --mode train --steps 15 --no-roofline --no-cpu-baseline --no-library-bar --no-input-pipeline > gpurun_out/r2_bench_train_planes$pl.json 2> gpurun_out/r2_bench_train_planes$pl.err; echo "bench planes=$pl exit $?"
+python - <<PY
+import json
+j = json.loads(open('gpurun_out/r2_bench_train_planes$pl.json').read().strip().splitlines()[-1])
+print('planes=$pl', {k: j['train_step'].get(k) for k in ('value','ms_per_step','gpu_launches','loss_first','loss_last','peak_mem_gib')})
+PY
+tail -2 gpurun_out/r2_bench_train_planes$pl.err
+done

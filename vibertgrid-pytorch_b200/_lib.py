@@ -94,6 +94,7 @@ SIGNATURES = {
     "vbg_sumpool2x2": [_p, _i, _i, _i, _i, _f, _p, _p],
     "vbg_expand2x": [_p, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p],
     "vbg_gelu": [_p, _p, _ll, _p, _p],
+    "vbg_gelu_x": [_p, _ll, _p, _ll, _ll, _p, _ll, _p],
     "vbg_dropout": [_p, _ll, _f, C.c_ulonglong, _p, _p],
     "vbg_uniform_keys": [_ll, C.c_ulonglong, _p, _p, _p],
     "vbg_dropout_ds": [_p, _ll, _f, C.c_ulonglong, _p, _p, _p],

@@ -165,10 +165,26 @@ def leaf_view(p, *shape):
     return t
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# The PLANES PROTOCOL: between two tensor-core stages an activation (and its gradient) may travel through the tape as the bf16
+# ``[2, *shape]`` tensor of a ``Split`` -- hi / lo planes, the operand format of the bf16x3 kernels -- instead of fp32.  A stage
+# that accepts it skips its ``to_split`` pass; a stage that emits it writes the planes from its epilogue / elementwise kernel
+# and never writes the fp32 tensor.  The gradient of a planes tensor is a planes tensor (same shape and dtype, as autograd
+# requires), so the backward chain keeps the format too.  Used for the QKV -> attention and FFN-up -> GELU -> FFN-down chains
+# of a BERT layer (the [rows, 2304] / [rows, 3072] tensors, the largest elementwise traffic of the layer).
+def _is_planes(t):
+    return t is not None and t.dtype == torch.bfloat16 and t.dim() >= 2 and t.shape[0] == 2
+
+
 class LinearPS(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        if x.dim() != 2 or weight.shape[1] != x.shape[1] or weight.shape[0] % 64 or weight.shape[1] % 64:
+    def forward(ctx, x, weight, bias, out_planes=False):
+        ctx.x_planes = _is_planes(x)
+        ctx.out_planes = bool(out_planes)
+        if (ctx.x_planes or ctx.out_planes) and _fp32():
+            raise ValueError("LinearPS: the planes protocol belongs to the tensor-core mode")
+        xshape = tuple(x.shape[1:]) if ctx.x_planes else tuple(x.shape)
+        if len(xshape) != 2 or weight.shape[1] != xshape[1] or weight.shape[0] % 64 or weight.shape[1] % 64:
             raise ValueError("LinearPS: x [M, K], weight [N, K] with N and K multiples of 64")
         ep = ops.make_epilogue(None, None if bias is None else bias.detach())
         ctx.wt = None
@@ -183,8 +199,10 @@ class LinearPS(torch.autograd.Function):
                 w_ = weight.detach().contiguous()
                 return w_, ops.split_bf16(w_), (ops.transpose_split(w_) if PREP is not None and x.requires_grad else None)
             w, ws, ctx.wt = _prepped(weight_forms, param_only)
-            xs = ops.to_split(x.detach().contiguous())
-            y = ops.gemm(xs, w, ep=ep, precision=ops.PREC_BF16X3, W_split=ws)
+            xs = ops.Split(x.detach()) if ctx.x_planes else ops.to_split(x.detach().contiguous())
+            y = ops.gemm(xs, w, ep=ep, precision=ops.PREC_BF16X3, W_split=ws, split_out=ctx.out_planes)
+            if ctx.out_planes:
+                y = y.t
             ctx.save_for_backward(xs.t, weight)          # the planes are what the weight-gradient kernel reads (same bytes as x)
         ctx.planes = not _fp32()
         ctx.has_bias = bias is not None
@@ -198,20 +216,23 @@ class LinearPS(torch.autograd.Function):
         M, K = xs.shape
         N = weight.shape[0]
         dy = dy.contiguous()
-        dys = ops.to_split(dy)
+        dys = ops.Split(dy) if ctx.out_planes else ops.to_split(dy)
+        dy_sum = dys if ctx.out_planes else dy                                       # the column sums read either format
         dx = dw = db = None
         if ctx.needs_input_grad[0] and _fp32():
             dx = ops.gemm(dy, weight.detach().t().contiguous(), precision=ops.PREC_FP32)
         elif ctx.needs_input_grad[0]:
             wt = ctx.wt if ctx.wt is not None else ops.transpose_split(weight.detach().contiguous())     # [K, N] planes
-            dx = ops.gemm(dys, weight.detach().t(), precision=ops.PREC_BF16X3, W_split=wt.t, N=K, K=N, ldw=N)
+            dx = ops.gemm(dys, weight.detach().t(), precision=ops.PREC_BF16X3, W_split=wt.t, N=K, K=N, ldw=N, split_out=ctx.x_planes)
+            if ctx.x_planes:
+                dx = dx.t
         want_w, want_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
 
         def param_grads():
             # MN-major tcgen05 operands straight from the row-major planes (no transposes)
-            return (ops.linear_wgrad(dys, xs) if want_w else None), (ops.colsum(dy) if want_b else None)
+            return (ops.linear_wgrad(dys, xs) if want_w else None), (ops.colsum(dy_sum) if want_b else None)
         dw, db = _deferred(param_grads, ctx.defer, dys, xs, dy)
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 class LayerNormPS(torch.autograd.Function):
@@ -292,10 +313,13 @@ class LinearSmall(torch.autograd.Function):
         return dx, dw, db
 
 
-def linear(x, weight, bias=None):
-    """[M, K] x [N, K]^T (+ bias) on whichever kernel takes the shape."""
+def linear(x, weight, bias=None, out_planes=False):
+    """[M, K] x [N, K]^T (+ bias) on whichever kernel takes the shape.  ``out_planes``: emit the result in the plane format
+    (tensor-core kernel only; see "planes protocol")."""
     if weight.shape[0] % 64 == 0 and weight.shape[1] % 64 == 0:
-        return LinearPS.apply(x, weight, bias)
+        return LinearPS.apply(x, weight, bias, out_planes)
+    if out_planes or _is_planes(x):
+        raise ValueError("linear: the plane format needs output / input widths that are multiples of 64")
     return LinearSmall.apply(x, weight, bias)
 
 
@@ -480,15 +504,22 @@ class Up2F(torch.autograd.Function):
 
 
 class GeluF(torch.autograd.Function):
+    """erf-GELU; an input in the plane format stays in it (output, saved activation and both gradients): nothing fp32 of size
+    [rows, 3072] is written in either direction."""
+
     @staticmethod
     def forward(ctx, x):
         x = _c(x.detach())
         ctx.save_for_backward(x)
-        return ops.gelu(x)
+        ctx.planes = _is_planes(x)
+        return ops.gelu(ops.Split(x), split_out=True).t if ctx.planes else ops.gelu(x)
 
     @staticmethod
     def backward(ctx, dy):
-        return ops.gelu(ctx.saved_tensors[0], _c(dy))
+        (x,) = ctx.saved_tensors
+        if ctx.planes:
+            return ops.gelu(ops.Split(x), ops.Split(_c(dy)), split_out=True).t
+        return ops.gelu(x, _c(dy))
 
 
 class DropoutF(torch.autograd.Function):
@@ -515,13 +546,16 @@ class AttentionF(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, cu, nseq, max_len, heads, p_drop=0.0, seed=0, step_seed=None):
         qkv = _c(qkv.detach())
-        hid = qkv.shape[1] // 3
+        hid = qkv.shape[-1] // 3
         if hid // heads != 64:
             raise NotImplementedError("training attention: head dimension 64 only")
         ctx.tc = max_len <= 512 and ops.tc_available() and not _fp32()
         ctx.cfg = (nseq, max_len, heads)
+        ctx.planes = _is_planes(qkv)                  # packed QKV straight from the GEMM's epilogue in the plane format
+        if ctx.planes and not ctx.tc:
+            raise ValueError("AttentionF: a QKV tensor in the plane format needs the tensor-core attention kernels")
         if ctx.tc:
-            qs = ops.to_split(qkv)
+            qs = ops.Split(qkv) if ctx.planes else ops.to_split(qkv)
             out, lse2 = ops.attention_split_train(qs, cu, nseq, max_len, heads, p_drop, seed, step_seed)
             ctx.save_for_backward(qs.t, out, lse2, cu)
             ctx.drop = (float(p_drop), int(seed), step_seed)
@@ -539,6 +573,8 @@ class AttentionF(torch.autograd.Function):
         if ctx.tc:
             qs, out, lse2, cu = ctx.saved_tensors
             dqkv = ops.attention_bwd_tc(ops.Split(qs), out, _c(d_out), lse2, cu, *ctx.cfg, *ctx.drop)
+            if ctx.planes:                               # the gradient of a planes tensor is a planes tensor
+                dqkv = ops.to_split(dqkv).t
         else:
             qkv, out, cu = ctx.saved_tensors
             dqkv = ops.attention_bwd(qkv, out, _c(d_out), cu, *ctx.cfg)

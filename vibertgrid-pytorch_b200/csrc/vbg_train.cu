@@ -205,18 +205,21 @@ __global__ void expand2x_kernel(const float4* __restrict__ x, int B, int H, int 
 }
 
 // ------------------------------------------------------------------ elementwise
-__global__ void gelu_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, long long n4, float4* __restrict__ out) {
+// x, dy and out in either storage format (plane == 0: fp32; > 0: bf16 hi/lo planes `plane` elements apart): the FFN of the
+// training step keeps its [rows, 3072] activations and gradients in the plane format end to end (autograd.py "planes protocol")
+__global__ void gelu_kernel(const void* __restrict__ x, long long x_plane, const void* __restrict__ dy, long long dy_plane, long long n4,
+                            void* __restrict__ out, long long out_plane) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 v = __ldg(x + i);
+    const float4 v = ld4_fmt(x, x_plane, (size_t)i);
     float4 o;
     if (!dy) {
       o = make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
     } else {
-      const float4 g = __ldg(dy + i);
+      const float4 g = ld4_fmt(dy, dy_plane, (size_t)i);
       auto d = [](float u) { return 0.5f * (1.0f + erff(u * 0.70710678118654752440f)) + u * 0.3989422804014327f * expf(-0.5f * u * u); };
       o = make_float4(g.x * d(v.x), g.y * d(v.y), g.z * d(v.z), g.w * d(v.w));
     }
-    out[i] = o;
+    st4_fmt(out, out_plane, (size_t)i, o);
   }
 }
 
@@ -829,9 +832,14 @@ extern "C" int vbg_expand2x(const float* x, int B, int Hi, int Wi, int C, int H,
 }
 
 extern "C" int vbg_gelu(const float* x, const float* dy, long long n, float* out, vbg_stream_t stream) {
-  VBG_REQUIRE(x && out && n > 0 && n % 4 == 0 && aligned16(x) && aligned16(out) && (!dy || aligned16(dy)), "vbg_gelu: n %% 4 == 0, 16B alignment");
-  gelu_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy), n / 4,
-                                                                   reinterpret_cast<float4*>(out));
+  return vbg_gelu_x(x, 0, dy, 0, n, out, 0, stream);
+}
+
+extern "C" int vbg_gelu_x(const void* x, long long x_plane, const void* dy, long long dy_plane, long long n, void* out, long long out_plane,
+                          vbg_stream_t stream) {
+  VBG_REQUIRE(n > 0 && n % 4 == 0 && fmt_ok(x, x_plane) && fmt_ok(out, out_plane) && (!dy || fmt_ok(dy, dy_plane)),
+              "vbg_gelu: n %% 4 == 0, 16B-aligned tensors, planes a multiple of 8 elements apart");
+  gelu_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(x, x_plane, dy, dy_plane, n / 4, out, out_plane);
   return check_launch("vbg_gelu");
 }
 

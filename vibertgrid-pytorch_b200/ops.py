@@ -785,9 +785,22 @@ def expand2x(x, H, W, scale=1.0, zero_insert=False):
     return y
 
 
-def gelu(x, dy=None):
-    out = torch.empty_like(x)
-    L.check(L.load().vbg_gelu(_f32(x), None if dy is None else _f32(dy), x.numel(), _f32(out), _stream()), "vbg_gelu")
+def gelu(x, dy=None, split_out=False):
+    """erf-GELU (``dy`` None) or its backward ``dy * gelu'(x)``; ``x`` / ``dy`` fp32 tensors or Splits, the result a Split when
+    ``split_out``."""
+    if not split_out and not isinstance(x, Split) and not isinstance(dy, Split):
+        out = torch.empty_like(x)
+        L.check(L.load().vbg_gelu(_f32(x), None if dy is None else _f32(dy), x.numel(), _f32(out), _stream()), "vbg_gelu")
+        return out
+    shape = tuple(x.shape)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    out = _new_act(shape, (x.t if isinstance(x, Split) else x).device, split_out)
+    xp, xpl = _act(x)
+    dp, dpl = _act(dy) if dy is not None else (None, 0)
+    op, opl = _act(out)
+    L.check(L.load().vbg_gelu_x(xp, xpl, dp, dpl, n, op, opl, _stream()), "vbg_gelu_x")
     return out
 
 

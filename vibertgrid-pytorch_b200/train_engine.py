@@ -86,6 +86,7 @@ class TrainEngine:
         self.use_graphs = os.environ.get("VBG_TRAIN_GRAPHS", "1") != "0"
         self.side_wgrad = os.environ.get("VBG_TRAIN_SIDE_WGRAD", "1") != "0"
         self.side_prep = os.environ.get("VBG_TRAIN_SIDE_PREP", "1") != "0"
+        self.bert_planes = os.environ.get("VBG_TRAIN_PLANES", "1") != "0"
         self.max_graphs = 4
         self._graphs = {}
         self.graph_replays = 0
@@ -181,16 +182,19 @@ class TrainEngine:
             return A.DropoutF.apply(t, p_drop, _rand_seed(), step_seed) if p_drop > 0.0 else t
 
         x = drop(x)
+        # QKV -> attention and FFN-up -> GELU -> FFN-down keep their wide tensors in the plane format (autograd.py "planes protocol")
+        planes = bool(self.bert_planes and not getattr(self, "_test_standins", False) and not A._fp32()
+                      and plan.max_len <= 512 and ops.tc_available() and cfg["hidden_size"] // heads == 64)
         for lyr in bm.encoder.layer:
             sa = lyr.attention.self
             wqkv = A.pack_rows(sa.query.weight, sa.key.weight, sa.value.weight)       # cat whose backward is three views
             bqkv = A.pack_rows(sa.query.bias, sa.key.bias, sa.value.bias)
-            qkv = A.linear(x, wqkv, bqkv)
+            qkv = A.linear(x, wqkv, bqkv, out_planes=planes)
             ctx = A.AttentionF.apply(qkv, cu, plan.nseq, plan.max_len, heads, p_attn, _rand_seed() if p_attn > 0.0 else 0, step_seed)
             ao = lyr.attention.output
             a = drop(A.linear(ctx, ao.dense.weight, ao.dense.bias)) + x
             x = A.LayerNormPS.apply(a, ao.LayerNorm.weight, ao.LayerNorm.bias, ao.LayerNorm.eps)
-            h = A.GeluF.apply(A.linear(x, lyr.intermediate.dense.weight, lyr.intermediate.dense.bias))
+            h = A.GeluF.apply(A.linear(x, lyr.intermediate.dense.weight, lyr.intermediate.dense.bias, out_planes=planes))
             o = drop(A.linear(h, lyr.output.dense.weight, lyr.output.dense.bias)) + x
             x = A.LayerNormPS.apply(o, lyr.output.LayerNorm.weight, lyr.output.LayerNorm.bias, lyr.output.LayerNorm.eps)
         return x
