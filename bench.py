@@ -543,7 +543,7 @@ def train_step_arm(net, cfg, resident, n_rot, world, steps, warmup=3):
         if world > 1 and ar["on"]:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        # graphed step: every gradient already sits in one flat arena -> in-place NCCL AVG over 4 slices, then backward()
+        # graphed step: every gradient already sits in one flat arena -> in-place NCCL AVG over slices of it, then backward()
         # hands the averaged views to the parameters; eager step (first sighting of a batch signature): bucketed all-reduce
         # of .grad after backward()
         nbytes_ar = shard.allreduce_step_arena(net)
@@ -579,7 +579,7 @@ def train_step_arm(net, cfg, resident, n_rot, world, steps, warmup=3):
     if ar.get("events"):
         t = [a.elapsed_time(b) for a, b in ar["events"]]
         msa = sum(t) / len(t)
-        out["allreduce"] = {"exposed_ms_per_step": msa, "bytes": ar["bytes"], "how": "in-place NCCL AVG over 4 slices of the step's flat gradient arena",
+        out["allreduce"] = {"exposed_ms_per_step": msa, "bytes": ar["bytes"], "how": "in-place NCCL AVG over slices of the step's flat gradient arena (shard.allreduce_step_arena)",
                             "bus_gbs": 2.0 * (world - 1) / world * ar["bytes"] / msa / 1e6}
     return out
 

@@ -1,12 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_train_graph.py tests/test_gpu_train_step.py tests/test_gpu_autograd.py tests/test_gpu_attention_train.py tests/test_gpu_train_ops.py -m gpu -q -x --timeout 600 2>&1 | grep -E "passed|failed|FAILED|Error|error|assert |^E " | tail -15
-for pl in 1 0; do
-VBG_TRAIN_PLANES=$pl timeout 600 python bench.py --mode train --steps 15 --no-roofline --no-cpu-baseline --no-library-bar --no-input-pipeline > gpurun_out/r2_bench_train_planes$pl.json 2> gpurun_out/r2_bench_train_planes$pl.err; echo "bench planes=$pl exit $?"
+for ch in 1 2; do
+VBG_ARENA_CHUNKS=$ch timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2971$ch bench.py --gpus 8 --steps 10 --warmup 3 --mode train --no-roofline --no-cpu-baseline --no-input-pipeline > gpurun_out/r2_bench_train_n8_ch$ch.json 2> gpurun_out/r2_bench_train_n8_ch$ch.err; echo "exit $?"
 python - <<PY
 import json
-j = json.loads(open('gpurun_out/r2_bench_train_planes$pl.json').read().strip().splitlines()[-1])
-print('planes=$pl', {k: j['train_step'].get(k) for k in ('value','ms_per_step','gpu_launches','loss_first','loss_last','peak_mem_gib')})
+j = json.loads(open('gpurun_out/r2_bench_train_n8_ch$ch.json').read().strip().splitlines()[-1])
+print('chunks=$ch', {k: j.get('train_step', {}).get(k) for k in ('value', 'ms_per_step', 'allreduce')})
 PY
-tail -2 gpurun_out/r2_bench_train_planes$pl.err
 done
