@@ -21,8 +21,9 @@ from vibertgrid_pytorch_b200 import _lib, shards, synth  # noqa: E402
 REF = os.path.join(ROOT, "oracle", "_ref", "reference")
 
 
-def make_tree(tmp, train):
-    """Documents of three different sizes plus the rows the reference's filter drops (blank text, text that tokenises to nothing)."""
+def make_tree(tmp, train, edge_rows=True):
+    """Documents of three different sizes plus the rows the reference's filter drops (blank text, text that tokenises to nothing).
+    ``edge_rows=False``: without the blank / numeric rows (the reference's EPHOIE / FUNSD datasets raise on a NaN text cell)."""
     split = os.path.join(tmp, "data", "train" if train else "test")
     base = synth.CONFIGS["tiny"]
     for seed, (h, w, segs) in enumerate([(96, 128, 9), (64, 96, 5), (80, 72, 12)]):
@@ -31,9 +32,10 @@ def make_tree(tmp, train):
     name = sorted(os.listdir(os.path.join(split, "label")))[0]
     path = os.path.join(split, "label", name)
     rows = list(csv.reader(open(path)))
-    rows.insert(2, ["", 1, 2, 30, 40, 1])
-    rows.insert(4, ["   ", 3, 4, 50, 60, 2])
-    rows.append(["12.50", 5, 6, 70, 80, 4])
+    if edge_rows:
+        rows.insert(2, ["", 1, 2, 30, 40, 1])
+        rows.insert(4, ["   ", 3, 4, 50, 60, 2])
+        rows.append(["12.50", 5, 6, 70, 80, 4])
     rows.append(["Zebra tok1500", 7, 8, 90, 95, 3])
     with open(path, "w", newline="") as f:
         csv.writer(f).writerows(rows)
@@ -121,6 +123,64 @@ def test_convert_dataset_equals_direct_conversion(tmp_path, tokenizer, train):
     assert shards.convert_sroie_split(split, tokenizer, a, train=train, files=ds.filename_list) == len(ds)
     assert shards.convert_dataset(ds, b, train=train) == len(ds)
     assert open(a, "rb").read() == open(b, "rb").read()
+
+
+def _other_tree(tmp, kind):
+    """The SROIE-shaped synthetic split rearranged into the EPHOIE / FUNSD on-disk layouts (data/EPHOIE_dataset.py:96-115,
+    data/FUNSD_dataset.py:87-106)."""
+    import shutil
+    from PIL import Image
+    src = make_tree(os.path.join(tmp, "src"), False, edge_rows=False)
+    root = os.path.join(tmp, kind)
+    names = sorted(f[:-4] for f in os.listdir(os.path.join(src, "image")))
+    if kind == "ephoie":
+        for sub in ("image", "_label_csv", "kvpair"):
+            os.makedirs(os.path.join(root, sub))
+        for n in names:
+            shutil.copy(os.path.join(src, "image", n + ".jpg"), os.path.join(root, "image", n + ".jpg"))
+            shutil.copy(os.path.join(src, "label", n + ".csv"), os.path.join(root, "_label_csv", n + ".csv"))
+            shutil.copy(os.path.join(src, "key", n + ".json"), os.path.join(root, "kvpair", n + ".txt"))
+        for split in ("train.txt", "test.txt"):
+            open(os.path.join(root, split), "w").write("\n".join(names) + "\n")
+    else:
+        for sub in ("images", "_label_csv"):
+            os.makedirs(os.path.join(root, "training_data", sub))
+        for n in names:
+            Image.open(os.path.join(src, "image", n + ".jpg")).save(os.path.join(root, "training_data", "images", n + ".png"))
+            shutil.copy(os.path.join(src, "label", n + ".csv"), os.path.join(root, "training_data", "_label_csv", n + ".csv"))
+    return root
+
+
+@pytest.mark.parametrize("kind,train", [("ephoie", True), ("ephoie", False), ("funsd", True), ("funsd", False)])
+def test_generic_converter_on_the_other_reference_datasets(tmp_path, tokenizer, kind, train):
+    """convert_dataset + ShardLoader against the reference's EPHOIE / FUNSD datasets and their collate functions."""
+    if not os.path.isdir(REF):
+        pytest.skip("oracle/_ref/reference is not staged")
+    if REF not in sys.path:
+        sys.path.append(REF)
+    root = _other_tree(str(tmp_path), kind)
+    if kind == "ephoie":
+        from data.EPHOIE_dataset import EPHOIEDataset as DS
+    else:
+        from data.FUNSD_dataset import FUNSDDataset as DS
+    ds = DS(root, train=train, tokenizer=tokenizer)
+    out = str(tmp_path / f"{kind}.vbgshard")
+    assert shards.convert_dataset(ds, out, train=train) == len(ds) == 6
+    for docs in ([0, 4, 5], [3, 1]):
+        want = ds._ViBERTgrid_coll_func([ds[i] for i in docs])
+        got = next(iter(shards.ShardLoader(out, batches=[docs], train=train)))
+        assert len(got) == len(want)
+        for a, b in zip(got[0], want[0]):
+            assert torch.equal(a.permute(2, 0, 1).float().div(255), b)
+        for k in (1, 2, 3):
+            for a, b in zip(got[k], want[k]):
+                assert a.dtype == b.dtype and torch.equal(a, b)
+        assert torch.equal(got[4], want[4]) and torch.equal(got[5], want[5]) and got[5].dtype == want[5].dtype
+        for k in range(6, len(want)):
+            if want[k] is None:
+                assert got[k] is None
+            else:
+                assert [x for x in got[k]] == [x for x in want[k]]
 
 
 @pytest.mark.parametrize("n,world,bs,shuffle", [(10, 1, 3, False), (10, 4, 2, True), (7, 2, 2, True), (3, 4, 1, False), (16, 8, 2, True)])

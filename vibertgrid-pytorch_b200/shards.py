@@ -142,8 +142,10 @@ def convert_dataset(dataset, out_path: str, train: bool = True, indices: Optiona
                 raise ValueError(f"document {i}: the image is not ToTensor of 8-bit pixels; shards hold uint8 pixels")
             d = dict(image=u8.permute(1, 2, 0).contiguous().numpy(), seg_ids=item[1].numpy(), classes=item[2].numpy().reshape(-1),
                      coors=item[3].numpy().reshape(-1, 4), corpus=item[4].numpy())
-            if not train:
-                d["meta"] = {"text": list(item[5]), "key": item[6]}
+            if not train:                                   # SROIE / EPHOIE: (..., ocr_text, key_dict); FUNSD: (..., ocr_text)
+                d["meta"] = {"text": list(item[5])}
+                if len(item) > 6:
+                    d["meta"]["key"] = item[6]
             yield d
     return write_shard(out_path, docs())
 
@@ -300,7 +302,9 @@ class ShardLoader:
         if self.train:
             return views
         metas = [self.shard.meta(d) or {} for d in docs]
-        return views + (tuple(m.get("text", []) for m in metas), tuple(m.get("key", {}) for m in metas))
+        # SROIE / EPHOIE: (..., ocr_text, key_dicts); FUNSD has no key dictionaries and its collate returns None in that slot
+        keys = tuple(m.get("key", {}) for m in metas) if any("key" in m for m in metas) else None
+        return views + (tuple(m.get("text", []) for m in metas), keys)
 
     def __iter__(self) -> Iterator[tuple]:
         todo = self._epoch_batches()
