@@ -248,7 +248,8 @@ def default_batches(n_docs: int, batch_size: int, rank: int = 0, world: int = 1,
 class ShardLoader:
     """Iterates batches of a shard in the reference's collate layout (see the module docstring).
 
-    ``batches``: any iterable of index lists (e.g. ``torch.utils.data.BatchSampler(DistributedSampler(shard), bs, True)``);
+    ``batches``: any RE-ITERABLE of index lists (e.g. ``torch.utils.data.BatchSampler(DistributedSampler(shard), bs, True)``;
+    it is walked once per epoch and once by ``len()``, so a one-shot generator will not do);
     default: ``default_batches`` for (rank, world).  ``device``: a CUDA device -> batches arrive on the device, each by ONE
     asynchronous copy of the pinned staging buffer on a side stream, prepared ``depth - 1`` batches ahead by a background
     thread; ``None`` -> pinned host tensors.  A yielded batch stays valid until ``depth - 1`` further batches were requested.
