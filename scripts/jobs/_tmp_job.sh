@@ -1,10 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for ch in 1 2; do
-VBG_ARENA_CHUNKS=$ch timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 2971$ch bench.py --gpus 8 --steps 10 --warmup 3 --mode train --no-roofline --no-cpu-baseline --no-input-pipeline > gpurun_out/r2_bench_train_n8_ch$ch.json 2> gpurun_out/r2_bench_train_n8_ch$ch.err; echo "exit $?"
+timeout 900 python -m pytest tests/test_gpu_train_graph.py tests/test_gpu_train_step.py -m gpu -q -x --timeout 600 2>&1 | grep -E "passed|failed|FAILED|Error|error|assert |^E " | tail -15
+timeout 600 python bench.py --config cfg5 --steps 10 --no-roofline --no-cpu-baseline --no-library-bar --no-serving --no-input-pipeline > gpurun_out/r2_bench_cfg5.json 2> gpurun_out/r2_bench_cfg5.err; echo "bench cfg5 exit $?"
 python - <<PY
 import json
-j = json.loads(open('gpurun_out/r2_bench_train_n8_ch$ch.json').read().strip().splitlines()[-1])
-print('chunks=$ch', {k: j.get('train_step', {}).get(k) for k in ('value', 'ms_per_step', 'allreduce')})
+j = json.loads(open('gpurun_out/r2_bench_cfg5.json').read().strip().splitlines()[-1])
+print('cfg5', {k: j[k] for k in ('value','ms_per_step')}, 'train', {k: j.get('train_step',{}).get(k) for k in ('value','ms_per_step','whole_step_cuda_graph_replays','error')})
 PY
-done
+tail -3 gpurun_out/r2_bench_cfg5.err

@@ -130,3 +130,40 @@ def test_example_config_losses_are_drawn_on_the_device_and_captured(tmp_path, mo
         net.zero_grad(set_to_none=True)
         net(*batch).backward()
     assert net._train_engine.graph_replays == 0
+
+
+def test_crf_step_is_captured_and_equals_eager(tmp_path, monkeypatch):
+    """BASELINE configs[4]'s head: the `crf` classifier mode (two-stage auxiliary head with the plain-mean loss, CRF negative
+    log-likelihood kernel) has no host sync left in its step (losses_device.two_stage_aux_default) and is captured like the
+    `simp` step; replays give the eager tape's loss and gradients bit for bit."""
+    from vibertgrid_pytorch_b200 import synth
+    fx = load_golden("train_tiny_crf")
+    monkeypatch.chdir(tmp_path)
+    cfg, kw, net, batch = build_case(fx["meta"])
+    cfg = dataclasses.replace(cfg, ragged=False)
+    net = net.cuda().train()
+    net.bert_hidden_dropout = net.bert_attn_dropout = 0.0
+    batches = [_to_dev(synth.make_batch(cfg, s)) for s in (3, 4)]
+    sd0 = {k: v.clone() for k, v in net.state_dict().items()}
+
+    def run(use_graphs):
+        net.load_state_dict(sd0)
+        net._train_engine = None
+        out = []
+        for b in (batches[0], batches[0], batches[1], batches[0]):
+            net.zero_grad(set_to_none=True)
+            loss = net(*b)
+            net._train_engine.use_graphs = use_graphs
+            loss.backward()
+            out.append((loss.detach().clone(), _grads(net)))
+        return out, net._train_engine.graph_replays
+
+    eager, r0 = run(False)
+    graphed, r1 = run(True)
+    assert r0 == 0 and r1 >= 3, (r0, r1)
+    for step, ((le, ge), (lg, gg)) in enumerate(zip(eager, graphed)):
+        assert torch.equal(le, lg), f"loss differs at step {step}: {float(le):.7f} vs {float(lg):.7f}"
+        assert ge.keys() == gg.keys()
+        for k in ge:
+            assert torch.equal(ge[k], gg[k]), f"gradient of {k} differs at step {step}"
+    assert "field_type_classification_head.crf_layer.transitions" in eager[0][1]

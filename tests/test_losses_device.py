@@ -107,3 +107,45 @@ def test_supported_settings():
     assert D.supported({**base, "main_1": (-1, -1), "aux_sample_list": None})
     assert not D.supported({**base, "aux": (-1, 256)})
     assert not D.supported({**base, "aux_sample_list": [0, 5, 5]})
+
+
+class _TwoStageNet:
+    """What losses.aux_loss / losses_device.two_stage_aux_default read of the module in the `full` / `crf` classifier modes."""
+
+    def __init__(self, c, seed):
+        import types
+        torch.manual_seed(seed)
+        self.classifier_mode, self.num_tokens, self.loss_weights = "crf", c, None
+        self.loss_cfg = {"aux": (-1, -1), "aux_sample_list": None}
+        self.semantic_segmentation_head = types.SimpleNamespace()
+        for i in range(c - 1):
+            setattr(self.semantic_segmentation_head, f"ss_binary_classifier_{i}", types.SimpleNamespace(conv1=torch.nn.Conv2d(c, 1, 1)))
+
+
+@pytest.mark.parametrize("seed,none_selected", [(1, False), (2, False), (3, True)])
+def test_two_stage_aux_default_equals_host_form(seed, none_selected):
+    """The fixed-shape two-stage auxiliary loss (no host sync, no boolean gathers: what the captured `crf` step runs) against
+    the host restatement of model/semantic_segmentation_head.py:216-233: same value and same gradients, also when no pixel is
+    selected for the second stage (the reference skips it)."""
+    c, B, Hh, Ww = 5, 2, 12, 16
+    net = _TwoStageNet(c, seed)
+    g = torch.Generator().manual_seed(100 + seed)
+    pm = torch.randn(B, 3, Hh, Ww, generator=g)
+    if none_selected:
+        pm[:, 1] = -10.0                                            # the predicted mask class is never 1
+    pm.requires_grad_()
+    ps = torch.randn(B, c, Hh, Ww, generator=g, requires_grad=True)
+    pos_neg = torch.randint(0, 3, (B, Hh, Ww), generator=g)
+    cls = torch.randint(0, c, (B, Hh, Ww), generator=g)
+    params = [p for i in range(c - 1) for p in getattr(net.semantic_segmentation_head, f"ss_binary_classifier_{i}").conv1.parameters()]
+    a = H.aux_loss(net, {"pred_mask": pm, "pred_ss": ps, "pos_neg_labels": pos_neg, "class_labels": cls})
+    b = D.two_stage_aux_default(net, pm, ps, pos_neg, cls)
+    assert a.shape == b.shape == (1,)
+    assert abs(float(a) - float(b)) <= 2e-6 * max(1.0, abs(float(a)))
+    ga = torch.autograd.grad(a.sum(), [pm, ps] + params, allow_unused=True)
+    gb = torch.autograd.grad(b.sum(), [pm, ps] + params, allow_unused=True)
+    for x, y in zip(ga, gb):
+        if x is None or y is None:
+            assert (x is None or float(x.abs().max()) == 0.0) and (y is None or float(y.abs().max()) == 0.0)
+        else:
+            assert float((x - y).abs().max()) <= 2e-6 * max(1.0, float(x.abs().max()))

@@ -155,3 +155,27 @@ def supported(cfg) -> bool:
         return p == (-1, -1) or (p[0] > 0 and p[1] > 0)
     sl = cfg["aux_sample_list"]
     return pair_ok(cfg["main_1"]) and pair_ok(cfg["main_2"]) and pair_ok(cfg["aux"]) and (sl is None or all(int(v) > 0 for v in sl))
+
+
+def two_stage_aux_default(net, pm, ps, pos_neg_labels, class_labels):
+    """The auxiliary loss of the two-stage segmentation head (``full`` / ``crf`` classifier modes,
+    model/semantic_segmentation_head.py:216-233) for the plain-mean loss configuration, WITHOUT its device->host sync and its
+    boolean-mask gathers: stage 1 = mean cross entropy of the 3-way mask head; stage 2 = for every class c the binary cross
+    entropy of ``ss_binary_classifier_c`` over the pixels whose PREDICTED mask class is 1 -- here as sum(bce * m) / sum(m) over
+    all pixels (m the 0/1 selection), which is the same mean up to the order of the sum, and 0 when nothing is selected (the
+    reference skips the stage then).  Fixed shapes, no host reads: capturable in the training step's CUDA graph.  The 1x1
+    classifier convolutions are per-pixel dot products over <= C channels, written as a broadcast multiply-add (no library conv)."""
+    head = net.semantic_segmentation_head
+    l1 = F.cross_entropy(pm.float(), pos_neg_labels)
+    m = (pm.softmax(1).argmax(1) == 1).float()                                   # [B, H, W]
+    cnt = m.sum()
+    l2 = torch.zeros((1,), device=pm.device)
+    for c in range(net.num_tokens - 1):
+        conv = getattr(head, f"ss_binary_classifier_{c}").conv1
+        w = conv.weight.reshape(1, -1, 1, 1)
+        pred = (ps * w).sum(1) + conv.bias.reshape(1, 1, 1)                      # [B, H, W]
+        lab = (class_labels == (c + 1)).float()
+        bce = F.binary_cross_entropy_with_logits(pred.float(), lab, reduction="none")
+        l2 = l2 + (bce * m).sum() / cnt.clamp_min(1.0)
+    return l1 + l2
+

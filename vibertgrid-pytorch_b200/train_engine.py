@@ -253,8 +253,12 @@ class TrainEngine:
         cfg = net.loss_cfg
         if not self.use_graphs or dev.type != "cuda" or getattr(self, "_test_standins", False):
             return False
-        if net.classifier_mode != "simp" or net.loss_weights is not None:
-            return False                     # full / crf: the two-stage auxiliary head and the gated heads index by device masks
+        if net.loss_weights is not None:
+            return False
+        if net.classifier_mode == "full":
+            return False                     # the gated binary heads of `full` index rows by a device mask (losses.main_loss)
+        if net.classifier_mode == "crf" and not self._two_stage_default(dev):
+            return False                     # two-stage auxiliary head with sampled / OHEM settings: boolean-mask gathers
         if self._sampled_losses() and not self._device_sampling(dev):
             return False                     # host-side draws (Python `random`) and data-dependent shapes cannot be captured
         if any(self._sync_group(m) is not None for m in net.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)):
@@ -262,6 +266,14 @@ class TrainEngine:
         if any(m.momentum is None for m in net.modules() if isinstance(m, nn.modules.batchnorm._BatchNorm)):
             return False                     # cumulative moving average: the factor is read back from the step counter
         return True
+
+    def _two_stage_default(self, dev):
+        """The two-stage auxiliary head (``full`` / ``crf``) with the plain-mean loss configuration on a GPU: computed by the
+        fixed-shape form losses_device.two_stage_aux_default (no host sync); ``net.loss_sampling = "host"`` keeps losses.py."""
+        net, cfg = self.net, self.net.loss_cfg
+        return (dev.type == "cuda" and not getattr(self, "_test_standins", False) and net.classifier_mode in ("full", "crf")
+                and cfg["aux_sample_list"] is None and tuple(int(v) for v in cfg["aux"]) == (-1, -1) and net.loss_weights is None
+                and getattr(net, "loss_sampling", "device") == "device")
 
     def _sampled_losses(self):
         cfg = self.net.loss_cfg
@@ -448,8 +460,13 @@ class TrainEngine:
             full = torch.nn.functional.interpolate(lg.permute(0, 3, 1, 2), scale_factor=int(net.p_fuse_downsampling_ratio),
                                                    mode="nearest")
             pos_neg_labels, class_labels = ops.label_paint(boxes, seg_off, cls_cat, B, plan.H, plan.W)
-            loss_aux = losses.aux_loss(net, {"pred_mask": full[:, :3], "pred_ss": full[:, 3:],
-                                             "pos_neg_labels": pos_neg_labels, "class_labels": class_labels}, ctx)
+            if self._two_stage_default(dev):
+                # full / crf heads with the plain-mean loss configuration: the fixed-shape, sync-free form (capturable)
+                from .losses_device import two_stage_aux_default
+                loss_aux = two_stage_aux_default(net, full[:, :3], full[:, 3:], pos_neg_labels, class_labels)
+            else:
+                loss_aux = losses.aux_loss(net, {"pred_mask": full[:, :3], "pred_ss": full[:, 3:],
+                                                 "pos_neg_labels": pos_neg_labels, "class_labels": class_labels}, ctx)
 
         # a7 / a8 ROI align, late fusion
         roi = A.RoiAlignF.apply(p_fuse, boxes, seg_off, 1.0 / float(net.p_fuse_downsampling_ratio), net.roi_shape)
