@@ -78,7 +78,7 @@ def test_eval_sroie_main_through_the_dropin(precision, tmp_path):
     assert got == want                          # the file the script itself writes: per-document key strings + metrics
 
 
-def _train_case(tmp, batch_size, n_train=12):
+def _train_case(tmp, batch_size, n_train=12, sync_bn=True):
     import dataclasses
     import sroie_synth
     from vibertgrid_pytorch_b200 import synth
@@ -88,13 +88,13 @@ def _train_case(tmp, batch_size, n_train=12):
     sroie_synth.write_split(os.path.join(tmp, "data", "test"), 2, cfg, seed=3, tokens_per_seg=3)
     sroie_synth.write_bert(cfg, tmp, with_weights=True, seed=0, dropout=0.0)     # dropout off: runs must be comparable
     cpath = os.path.join(tmp, "train.yaml")
-    sroie_synth.write_config(cpath, cfg, os.path.join(tmp, "data"), batch_size=batch_size, end_epoch=1, sync_bn=True, amp=True)
+    sroie_synth.write_config(cpath, cfg, os.path.join(tmp, "data"), batch_size=batch_size, end_epoch=1, sync_bn=sync_bn, amp=True)
     return cpath
 
 
-def _run_train(tmp, nproc, batch_size, port):
+def _run_train(tmp, nproc, batch_size, port, sync_bn=True):
     import sroie_synth
-    cpath = _train_case(tmp, batch_size)
+    cpath = _train_case(tmp, batch_size, sync_bn=sync_bn)
     env = sroie_synth.script_env(ROOT, with_dropin=True)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), LAUNCHER, "train_SROIE", "-c", cpath]
@@ -114,6 +114,9 @@ def test_train_sroie_one_rank_ddp_syncbn_amp(tmp_path):
     assert info["sgd_steps"] == 3 and info["adamw_steps"] == 3, info    # GradScaler found finite gradients and stepped both
     assert info["params_with_grad"] > 100
     assert "train_loss" in stdout and "validate_loss" in stdout          # train_one_epoch and validate() both printed
+    # one rank: SyncBatchNorm falls back to per-rank statistics (torch's own rule), so the step has no collective inside the tape
+    # and is captured -- under DDP, autocast and GradScaler: step 0 eager, step 1 capture + replay, step 2 replay
+    assert info["train_graph_replays"] >= 2, info
     print(f"[train_SROIE.py, 1 rank, syncBN + amp] losses {info['losses']}")
 
 
@@ -129,3 +132,18 @@ def test_train_sroie_two_ranks_match_one_rank(tmp_path):
     print(f"[train_SROIE.py] one rank x batch 4: {l1.tolist()}  two ranks x batch 2 (mean over ranks): {l2.tolist()}")
     assert np.allclose(l1, l2, rtol=2e-3), (l1, l2)
     assert abs(one[0]["param_checksum"] - a["param_checksum"]) <= 1e-5 * abs(a["param_checksum"])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_train_sroie_two_ranks_graphed_step_under_ddp(tmp_path):
+    """``syncBN: False``: no collective inside the tape, so each rank replays its whole-step CUDA graph and DDP's bucket hooks fire
+    from the step's one autograd node -- replicas stay bit-identical and the losses equal the one-rank run of the same global
+    batch up to the per-rank BatchNorm statistics (two documents per rank instead of four)."""
+    two, _ = _run_train(str(tmp_path / "w2"), 2, 2, 29615, sync_bn=False)
+    a, b = two
+    assert a["bn_classes"] == ["BatchNorm2d"], a
+    assert a["train_graph_replays"] >= 2 and b["train_graph_replays"] >= 2, (a["train_graph_replays"], b["train_graph_replays"])
+    assert a["checksums_all_ranks"][0] == a["checksums_all_ranks"][1], a     # DDP kept the replicas bit-identical
+    assert a["sgd_steps"] == b["sgd_steps"] == 3 and a["adamw_steps"] == 3
+    assert all(np.isfinite(a["losses"])) and all(np.isfinite(b["losses"]))
+    print(f"[train_SROIE.py, 2 ranks, graphed step under DDP] losses rank0 {a['losses']} rank1 {b['losses']}")
