@@ -298,6 +298,9 @@ VBG_API int vbg_bn_bwd_dx(const float* x, const float* dy, const float* y_relu, 
                   vbg_stream_t stream);
 /* dX of max_pool2d(3, 2, 1) (first-maximum rule), x [B,H,W,C], dy [B,Ho,Wo,C] */
 VBG_API int vbg_maxpool3x3s2_bwd(const float* x, const float* dy, int B, int H, int W, int C, float* dx, vbg_stream_t stream);
+/* the same with the pooled output y [B, Ho, Wo, C] at hand (a position can take a window's gradient only where x == y): ~3x fewer loads */
+VBG_API int vbg_maxpool3x3s2_bwd_y(const float* x, const float* y, const float* dy, int B, int H, int W, int C, float* dx,
+                           vbg_stream_t stream);
 /* y [B,H/2,W/2,C] = scale * 2x2 block sums: backward of the nearest-x2 upsample (scale 1) */
 VBG_API int vbg_sumpool2x2(const float* x, int B, int H, int W, int C, float scale, float* y, vbg_stream_t stream);
 /* y [B,H,W,C] from x [B,Hi,Wi,C]: nearest x2 times scale (backward of avg_pool2d(2): scale 0.25), or zero insertion (zero_insert != 0:

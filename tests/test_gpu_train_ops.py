@@ -62,6 +62,7 @@ def test_maxpool_bwd_first_max_rule(B, H, W, C):
     assert torch.equal(yr.permute(0, 2, 3, 1), y)
     (ref,) = torch.autograd.grad(yr, xr, dy.permute(0, 3, 1, 2).contiguous())
     assert rel(dx, ref.permute(0, 2, 3, 1)) < 1e-6
+    assert torch.equal(ops.maxpool3x3s2_bwd(x, dy, y), dx)            # the y-assisted gather: same rule, same bits
 
 
 def test_sumpool_expand_gelu_dropout():

@@ -91,6 +91,7 @@ SIGNATURES = {
     "vbg_bn_bwd_reduce": [_p, _p, _p, _ll, _i, _p, _p, _p, _p, _p, _sz, _p],
     "vbg_bn_bwd_dx": [_p, _p, _p, _ll, _i, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     "vbg_maxpool3x3s2_bwd": [_p, _p, _i, _i, _i, _i, _p, _p],
+    "vbg_maxpool3x3s2_bwd_y": [_p, _p, _p, _i, _i, _i, _i, _p, _p],
     "vbg_sumpool2x2": [_p, _i, _i, _i, _i, _f, _p, _p],
     "vbg_expand2x": [_p, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p],
     "vbg_gelu": [_p, _p, _ll, _p, _p],

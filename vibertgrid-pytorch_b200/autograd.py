@@ -472,12 +472,14 @@ class MaxPoolF(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         x = _c(x.detach())
-        ctx.save_for_backward(x)
-        return ops.maxpool3x3s2(x)
+        y = ops.maxpool3x3s2(x)
+        ctx.save_for_backward(x, y)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        return ops.maxpool3x3s2_bwd(ctx.saved_tensors[0], _c(dy))
+        x, y = ctx.saved_tensors
+        return ops.maxpool3x3s2_bwd(x, _c(dy), y)
 
 
 class AvgPoolF(torch.autograd.Function):

@@ -170,6 +170,46 @@ __global__ void maxpool3x3s2_bwd_kernel(const float4* __restrict__ x, const floa
   }
 }
 
+// The same gather with the pooled OUTPUT at hand: (h, w) can hold a window's maximum only where x == y, so the window is
+// scanned (earlier positions only: is there an earlier element that also equals the maximum?) just for those channels --
+// ~14 loads per input pixel instead of ~40.  Same first-maximum rule, same results.
+__global__ void maxpool3x3s2_bwd_y_kernel(const float4* __restrict__ x, const float4* __restrict__ y, const float4* __restrict__ dy, int B,
+                                          int H, int W, int C4, int Ho, int Wo, float4* __restrict__ dx) {
+  const long long total = (long long)B * H * W * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4); long long t = i / C4;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H); const int b = (int)(t / H);
+    const float4 self = __ldg(x + i);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ho0 = h >> 1, ho1 = (h + 1) >> 1, wo0 = w >> 1, wo1 = (w + 1) >> 1;
+    for (int ho = ho0; ho <= ho1; ++ho) {
+      if (ho >= Ho) continue;
+      for (int wo = wo0; wo <= wo1; ++wo) {
+        if (wo >= Wo) continue;
+        const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * C4 + c;
+        const float4 m = __ldg(y + o);
+        bool kx = self.x == m.x, ky = self.y == m.y, kz = self.z == m.z, kw = self.w == m.w;
+        if (!(kx | ky | kz | kw)) continue;
+        // an EARLIER element of the window (scan order r, s) equal to the maximum takes the gradient instead
+        for (int r = 0; r < 3; ++r) {
+          const int hh = 2 * ho - 1 + r;
+          if (hh < 0 || hh > h) continue;
+          for (int s2 = 0; s2 < 3; ++s2) {
+            const int ww = 2 * wo - 1 + s2;
+            if (ww < 0 || ww >= W || !(hh < h || ww < w)) continue;
+            const float4 v = __ldg(x + (((size_t)b * H + hh) * W + ww) * C4 + c);
+            kx &= !(v.x == m.x); ky &= !(v.y == m.y); kz &= !(v.z == m.z); kw &= !(v.w == m.w);
+          }
+        }
+        const float4 g = __ldg(dy + o);
+        if (kx) acc.x += g.x; if (ky) acc.y += g.y; if (kz) acc.z += g.z; if (kw) acc.w += g.w;
+      }
+    }
+    dx[i] = acc;
+  }
+}
+
 // y[b, h, w] = scale * sum of the 2x2 block of x (H, W even)
 __global__ void sumpool2x2_kernel(const float4* __restrict__ x, int B, int H, int W, int C4, float scale, float4* __restrict__ y) {
   const int Ho = H >> 1, Wo = W >> 1;
@@ -812,6 +852,17 @@ extern "C" int vbg_maxpool3x3s2_bwd(const float* x, const float* dy, int B, int 
   maxpool3x3s2_bwd_kernel<<<grid_for((long long)B * H * W * (C / 4), 256, kNumSMs * 16), 256, 0, as_stream(stream)>>>(
       reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy), B, H, W, C / 4, Ho, Wo, reinterpret_cast<float4*>(dx));
   return check_launch("vbg_maxpool3x3s2_bwd");
+}
+
+extern "C" int vbg_maxpool3x3s2_bwd_y(const float* x, const float* y, const float* dy, int B, int H, int W, int C, float* dx,
+                                      vbg_stream_t stream) {
+  VBG_REQUIRE(x && y && dy && dx && B > 0 && H > 0 && W > 0 && C % 4 == 0 && aligned16(x) && aligned16(y) && aligned16(dy) && aligned16(dx),
+              "vbg_maxpool3x3s2_bwd_y: C %% 4 == 0 and 16B-aligned pointers");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  maxpool3x3s2_bwd_y_kernel<<<grid_for((long long)B * H * W * (C / 4), 256, kNumSMs * 16), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(dy), B, H, W, C / 4, Ho, Wo,
+      reinterpret_cast<float4*>(dx));
+  return check_launch("vbg_maxpool3x3s2_bwd_y");
 }
 
 extern "C" int vbg_sumpool2x2(const float* x, int B, int H, int W, int C, float scale, float* y, vbg_stream_t stream) {

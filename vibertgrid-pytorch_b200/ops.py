@@ -764,10 +764,14 @@ def bn_bwd_dx(x2d, dy2d, y_relu, mean, rstd, gamma, s_xhat, s_dy, count, want_dr
     return dx, dres
 
 
-def maxpool3x3s2_bwd(x, dy):
+def maxpool3x3s2_bwd(x, dy, y=None):
+    """``y``: the forward's output, when the caller kept it (the gather then scans a window only where x equals its maximum)."""
     B, H, W, Cc = x.shape
     dx = torch.empty_like(x)
-    L.check(L.load().vbg_maxpool3x3s2_bwd(_f32(x), _f32(dy), B, H, W, Cc, _f32(dx), _stream()), "vbg_maxpool3x3s2_bwd")
+    if y is not None:
+        L.check(L.load().vbg_maxpool3x3s2_bwd_y(_f32(x), _f32(y), _f32(dy), B, H, W, Cc, _f32(dx), _stream()), "vbg_maxpool3x3s2_bwd_y")
+    else:
+        L.check(L.load().vbg_maxpool3x3s2_bwd(_f32(x), _f32(dy), B, H, W, Cc, _f32(dx), _stream()), "vbg_maxpool3x3s2_bwd")
     return dx
 
 
