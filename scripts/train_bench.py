@@ -64,3 +64,22 @@ if os.environ.get("VBG_TRAIN_PROFILE"):
     print(f"profiled one step: {tot:.2f} ms of device time over {sum(r[2] for r in rows)} kernels")
     for k, t, n in rows[:45]:
         print(f"{t:8.3f} ms {100 * t / tot:5.1f}% x{n:<5d} {k[:110]}")
+    # where the step's wall time goes: kernels as intervals on the device timeline (a graph replay: no host in the way)
+    ks = [e for e in prof.events() if e.device_type.name == "CUDA" and e.time_range.end > e.time_range.start]
+    if ks:
+        iv = sorted((e.time_range.start, e.time_range.end) for e in ks)
+        span = iv[-1][1] - iv[0][0] if iv else 0.0
+        span = max(b for _, b in iv) - iv[0][0]
+        busy, cur_a, cur_b = 0.0, iv[0][0], iv[0][1]
+        for a, b in iv[1:]:
+            if a > cur_b:
+                busy += cur_b - cur_a
+                cur_a, cur_b = a, b
+            else:
+                cur_b = max(cur_b, b)
+        busy += cur_b - cur_a
+        total = sum(b - a for a, b in iv)
+        short = sum(1 for a, b in iv if b - a < 5.0)
+        print(f"device timeline of the profiled step: span {span / 1e3:.2f} ms, some kernel running {busy / 1e3:.2f} ms "
+              f"(idle gaps {(span - busy) / 1e3:.2f} ms), sum of kernel durations {total / 1e3:.2f} ms (overlap {(total - busy) / 1e3:.2f} ms), "
+              f"{len(iv)} kernels of which {short} shorter than 5 us")

@@ -86,7 +86,7 @@ def main():
         net = nets[0]
         info["bn_classes"] = sorted({type(m).__name__ for m in net.modules() if isinstance(m, torch.nn.modules.batchnorm._BatchNorm)})
         eng = getattr(net, "_train_engine", None)
-        info["train_graph_replays"] = int(getattr(eng, "graph_replays", 0)) if eng is not None else 0
+        info["train_graph_replays"] = int(getattr(eng, "graph_replays", 0) + getattr(eng, "capture_failures", 0)) if eng is not None else 0
         with torch.no_grad():
             chk = float(sum(p.detach().double().abs().sum() for p in net.parameters()))
             grads = sum(1 for p in net.parameters() if p.grad is not None)

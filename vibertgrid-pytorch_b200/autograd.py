@@ -47,8 +47,8 @@ def _fp32():
 #     join, so the caching allocator cannot hand its memory to a later main-stream kernel;
 #   * outside a capture (eager steps, DDP, tests of single Functions) ``SIDE`` is None and everything runs in line.
 class _SideWork:
-    def __init__(self, device):
-        self.stream = torch.cuda.Stream(device)
+    def __init__(self, device, stream=None):
+        self.stream = stream if stream is not None else torch.cuda.Stream(device)
         self.keep = []
         self.launched = 0
 
@@ -56,9 +56,9 @@ class _SideWork:
 SIDE = None
 
 
-def side_begin(device):
+def side_begin(device, stream=None):
     global SIDE
-    SIDE = _SideWork(device)
+    SIDE = _SideWork(device, stream)
     return SIDE
 
 
@@ -97,17 +97,17 @@ def _deferred(fn, ok, *keep):
 # critical path.  Results are kept referenced until ``prep_end`` (their memory must not be recycled on the prep stream while a
 # main-stream kernel still reads them).  Eligible: leaves of the tape and tensors marked by ``pack_rows`` / ``leaf_view``.
 class _PrepWork:
-    def __init__(self, device):
-        self.stream = torch.cuda.Stream(device)
+    def __init__(self, device, stream=None):
+        self.stream = stream if stream is not None else torch.cuda.Stream(device)
         self.keep = []
 
 
 PREP = None
 
 
-def prep_begin(device):
+def prep_begin(device, stream=None):
     global PREP
-    PREP = _PrepWork(device)
+    PREP = _PrepWork(device, stream)
     PREP.stream.wait_stream(torch.cuda.current_stream())          # the prep stream joins the capture here, once
     return PREP
 

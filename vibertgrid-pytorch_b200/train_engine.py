@@ -92,6 +92,9 @@ class TrainEngine:
         self.graph_replays = 0
         self.kernel_launches = 0          # C-ABI kernel launches executed on the device by graph replays (bench.py: gpu_launches)
         self._step_seed = None
+        self._graph_step = False
+        self.capture_failures = 0
+        self._side_streams = None
         self.grad_arena, self.arena_fresh = None, False
 
     def invalidate(self):
@@ -176,7 +179,7 @@ class TrainEngine:
         x = A.EmbedSumF.apply(e.word_embeddings.weight, e.position_embeddings.weight, e.token_type_embeddings.weight, ids, pos)
         x = A.LayerNormPS.apply(x, e.LayerNorm.weight, e.LayerNorm.bias, e.LayerNorm.eps)
 
-        step_seed = getattr(self, "_step_seed", None)      # device word, refreshed per step (None outside the graphed path)
+        step_seed = self._seed_word()                      # device word, refreshed per step (None outside the graphed path)
 
         def drop(t):
             return A.DropoutF.apply(t, p_drop, _rand_seed(), step_seed) if p_drop > 0.0 else t
@@ -312,7 +315,15 @@ class TrainEngine:
                   corpus=corpus.contiguous(), mask=None if mask is None else mask.to(torch.int32).contiguous(), tab=tab)
         if self._graphable(dev):
             return self._graphed_loss(plan, st, tuple(min_sizes))
-        self._step_seed = None
+        return self._eager(plan, st)
+
+    def _seed_word(self):
+        """The device seed word of graphed steps, or None on the eager path (by-value seeds).  The tensor itself lives as long
+        as the engine: every captured graph has its ADDRESS baked in, so it must never be dropped and re-created."""
+        return self._step_seed if self._graph_step else None
+
+    def _eager(self, plan, st):
+        self._graph_step = False
         self.arena_fresh = False
         return self._forward(plan, st)
 
@@ -331,9 +342,9 @@ class TrainEngine:
             self._graphs[key] = {"graph": None}
             if len(self._graphs) > self.max_graphs:
                 self._graphs.pop(next(iter(self._graphs)))
-            self._step_seed = None
-            self.arena_fresh = False
-            return self._forward(plan, st)
+            return self._eager(plan, st)
+        if ent.get("never"):
+            return self._eager(plan, st)
         if self._step_seed is None or self._step_seed.device != dev:
             self._step_seed = torch.zeros(1, dtype=torch.int64, device=dev)
             # pinned staging ring: the host runs a step or more ahead of the device, so the word of step t must not be
@@ -341,47 +352,27 @@ class TrainEngine:
             self._seed_ring = [[torch.zeros(1, dtype=torch.int64).pin_memory(), None] for _ in range(8)]
             self._seed_i = 0
         if ent["graph"] is None:               # second sighting: capture forward + backward
-            static = {k: ([t.clone() for t in v] if isinstance(v, list) else (None if v is None else v.clone())) for k, v in st.items()}
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            c0 = ops.L.launch_count
-            with torch.cuda.graph(g):
-                # The tape is built over ALIASES of the parameters (detached views of the same storage, made leaves inside the
-                # capture): the real Parameters' AccumulateGrad nodes were created by earlier eager steps / by DDP on the default
-                # stream and stay alive, and routing a captured backward through them makes the engine synchronise the capturing
-                # stream with the legacy stream, which invalidates the capture (scripts/train_graph_debug3.py).  The aliases read
-                # the parameter storage, so replays follow every in-place optimizer update.
-                aliases = {id(p_): p_.detach().requires_grad_() for _, p_ in named}
-                with _parameters_as(net, aliases):
-                    with torch.enable_grad():
-                        # parameter-only preparation (weight planes, transposes, repacks) runs ahead on a prep stream
-                        # (autograd.py "_PrepWork"); joined after the backward, when its last consumer has been enqueued
-                        if self.side_prep:
-                            A.prep_begin(dev)
-                        try:
-                            # weight gradients / bias sums / table gradients (backward) and the BatchNorm running-statistics
-                            # updates (forward) run on a side stream beside the main chain and are joined once, below
-                            # (autograd.py "_SideWork")
-                            if self.side_wgrad:
-                                A.side_begin(dev)
-                            try:
-                                loss = self._forward(plan, static)
-                                grads = torch.autograd.grad(loss, [aliases[id(p_)] for p_ in params], allow_unused=True)
-                            finally:
-                                A.side_join()
-                        finally:
-                            A.prep_end()
-                used = [(p_, g_) for p_, g_ in zip(params, grads) if g_ is not None]
-                # one flat arena, gradients as views (the N > 1 bench averages it with a single bucketed all-reduce)
-                arena = torch.empty(sum(g_.numel() for _, g_ in used), dtype=torch.float32, device=dev)
-                views, off = [], 0
-                for _, g_ in used:
-                    views.append(arena[off:off + g_.numel()].view(g_.shape))
-                    off += g_.numel()
-                torch._foreach_copy_(views, [g_ for _, g_ in used])
-                loss_out = loss.detach().clone()
-            ent.update(graph=g, static=static, loss=loss_out, views=views, arena=arena, params=[p_ for p_, _ in used], last=self.last,
-                       launches=ops.L.launch_count - c0)       # C-ABI kernel launches recorded into the graph = executed per replay
+            try:
+                self._capture(ent, plan, st, named, params, dev)
+            except RuntimeError as e:
+                # A capture can be invalidated from outside the step (any thread's synchronising CUDA call while the stream
+                # records): never fatal -- this step runs eagerly and the capture is tried again at the next sighting.
+                if "capture" not in str(e).lower():
+                    raise
+                for cleanup in (A.side_join, A.prep_end):
+                    try:
+                        cleanup()
+                    except RuntimeError:
+                        pass
+                torch.cuda.synchronize()
+                self.capture_failures += 1
+                ent["failed"] = ent.get("failed", 0) + 1
+                if ent["failed"] >= 3:
+                    ent["never"] = True
+                import warnings
+                warnings.warn(f"[vibertgrid_b200] whole-step capture failed ({type(e).__name__}: {str(e)[:120]}); eager step, "
+                              + ("capture disabled for this signature" if ent.get("never") else "will retry"))
+                return self._eager(plan, st)
         else:
             sd = ent["static"]
             for dst, src in zip(sd["image"], st["image"]):
@@ -397,12 +388,60 @@ class TrainEngine:
         self._step_seed.copy_(slot[0], non_blocking=True)
         slot[1] = torch.cuda.Event()
         slot[1].record()
+        self._graph_step = True
         ent["graph"].replay()
         self.graph_replays += 1
         self.kernel_launches += ent["launches"]
         self.last = ent["last"]
         self.grad_arena, self.arena_fresh = ent["arena"], True
         return _StepGradsF.apply(ent["loss"], len(ent["views"]), *ent["views"], *ent["params"])
+
+    def _capture(self, ent, plan, st, named, params, dev):
+        net = self.net
+        static = {k: ([t.clone() for t in v] if isinstance(v, list) else (None if v is None else v.clone())) for k, v in st.items()}
+        if self._side_streams is None:         # the two helper streams of the captured step, created once, outside any capture
+            self._side_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        c0 = ops.L.launch_count
+        self._graph_step = True
+        with torch.cuda.graph(g):
+            # The tape is built over ALIASES of the parameters (detached views of the same storage, made leaves inside the
+            # capture): the real Parameters' AccumulateGrad nodes were created by earlier eager steps / by DDP on the default
+            # stream and stay alive, and routing a captured backward through them makes the engine synchronise the capturing
+            # stream with the legacy stream, which invalidates the capture.  The aliases read the parameter storage, so replays
+            # follow every in-place optimizer update.
+            aliases = {id(p_): p_.detach().requires_grad_() for _, p_ in named}
+            with _parameters_as(net, aliases):
+                with torch.enable_grad():
+                    # parameter-only preparation (weight planes, transposes, repacks) runs ahead on a prep stream
+                    # (autograd.py "_PrepWork"); joined after the backward, when its last consumer has been enqueued
+                    if self.side_prep:
+                        A.prep_begin(dev, self._side_streams[0])
+                    try:
+                        # weight gradients / bias sums / table gradients (backward) and the BatchNorm running-statistics
+                        # updates (forward) run on a side stream beside the main chain and are joined once, below
+                        # (autograd.py "_SideWork")
+                        if self.side_wgrad:
+                            A.side_begin(dev, self._side_streams[1])
+                        try:
+                            loss = self._forward(plan, static)
+                            grads = torch.autograd.grad(loss, [aliases[id(p_)] for p_ in params], allow_unused=True)
+                        finally:
+                            A.side_join()
+                    finally:
+                        A.prep_end()
+            used = [(p_, g_) for p_, g_ in zip(params, grads) if g_ is not None]
+            # one flat arena, gradients as views (the N > 1 bench averages it with in-place all-reduces over its slices)
+            arena = torch.empty(sum(g_.numel() for _, g_ in used), dtype=torch.float32, device=dev)
+            views, off = [], 0
+            for _, g_ in used:
+                views.append(arena[off:off + g_.numel()].view(g_.shape))
+                off += g_.numel()
+            torch._foreach_copy_(views, [g_ for _, g_ in used])
+            loss_out = loss.detach().clone()
+        ent.update(graph=g, static=static, loss=loss_out, views=views, arena=arena, params=[p_ for p_, _ in used], last=self.last,
+                   launches=ops.L.launch_count - c0)       # C-ABI kernel launches recorded into the graph = executed per replay
 
     def _forward(self, plan, st):
         """The kernel sequence of one training forward over staged inputs (capturable: no host sync)."""
@@ -450,7 +489,7 @@ class TrainEngine:
         ctx = None
         if self._sampled_losses() and self._device_sampling(dev):
             from .losses_device import SamplingCtx
-            ctx = SamplingCtx(getattr(self, "_step_seed", None), base_seed=_rand_seed() & 0xFFFFFFFF)
+            ctx = SamplingCtx(self._seed_word(), base_seed=_rand_seed() & 0xFFFFFFFF)
         if default_aux:
             aux = A.SegCEF.apply(lg, boxes, seg_off, cls_cat, B, plan.H, plan.W, net.p_fuse_downsampling_ratio, 3)
             loss_aux = aux[0] + aux[1]
