@@ -1,5 +1,6 @@
 """Linear-layer forward + backward on the pre-split tcgen05 GEMM (vibertgrid_pytorch_b200.autograd.LinearPS) against
 torch's float64 autograd of the same layer: y, dX, dW, db within fp32-class tolerance (bf16x3 products, fp32 accumulate)."""
+import numpy as np
 import pytest
 import torch
 
@@ -42,6 +43,26 @@ def test_transpose_split_and_colsum():
     t2 = ops.transpose_split(ops.to_split(x.cuda()))                      # planes in, planes out
     assert relerr(t2.float().cpu().numpy(), x.t().numpy()) < 2 ** -15
     assert relerr(ops.colsum(x.cuda()).cpu().numpy(), x.double().sum(0).numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("rows,cols", [(4128, 3072), (301, 200), (77, 26), (5000, 768), (9, 8)])
+def test_colsum_both_formats(rows, cols):
+    """Column sums over fp32 tensors and over the bf16 hi/lo plane format (what the bias gradients of the planes protocol read);
+    widths that are / are not multiples of four take the float4 / the scalar kernel."""
+    from vibertgrid_pytorch_b200 import ops
+    g = torch.Generator().manual_seed(rows + cols)
+    x = torch.randn(rows, cols, generator=g)
+    want = x.double().sum(0).numpy()
+    scale = float(np.abs(x.numpy()).sum(0).max())
+    got = ops.colsum(x.cuda()).cpu().numpy()
+    assert np.abs(got - want).max() <= 2e-6 * scale
+    if cols % 8 == 0:
+        xs = ops.to_split(x.cuda())
+        got_s = ops.colsum(xs).cpu().numpy()
+        want_s = xs.float().cpu().double().sum(0).numpy()              # the planes hold x to 2^-17
+        assert np.abs(got_s - want_s).max() <= 2e-6 * scale
+    again = ops.colsum(x.cuda()).cpu().numpy()
+    assert np.array_equal(got, again), "fixed-order sums: bitwise reproducible"
 
 
 @pytest.mark.parametrize("R,H", [(4128, 768), (37, 128), (1000, 1024)])

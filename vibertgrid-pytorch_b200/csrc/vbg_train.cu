@@ -647,28 +647,28 @@ colsum_kernel(const void* __restrict__ x, long long x_plane, long long rows, int
   }
 }
 
-// fp32 input with cols % 4 == 0: a warp reads 512 contiguous bytes of a row (lane = float4 of 4 columns), 8 row lanes per CTA,
-// four rows in flight per thread; per column the rows are still added in ascending order within a lane, lanes in fixed order.
+// cols % 4 == 0, either storage format: a warp reads 512 contiguous bytes of a row (lane = 4 columns: one float4, or one
+// 8-byte load from each bf16 plane), 8 row lanes per CTA, four rows in flight per thread; per column the rows are still
+// added in ascending order within a lane, lanes in fixed order.
 __global__ void __launch_bounds__(256)
-colsum4_kernel(const float4* __restrict__ x, long long rows, int cols4, long long rows_per_cta, float4* __restrict__ partial) {
+colsum4_kernel(const void* __restrict__ x, long long x_plane, long long rows, int cols4, long long rows_per_cta, float4* __restrict__ partial) {
   __shared__ float4 part[8][32];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5, c = blockIdx.x * 32 + tx;
   const long long r0 = (long long)blockIdx.y * rows_per_cta;
   long long r1 = r0 + rows_per_cta; if (r1 > rows) r1 = rows;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (c < cols4) {
-    const float4* p = x + c;
     long long r = r0 + ty;
     for (; r + 24 < r1; r += 32) {
-      const float4 v0 = __ldg(p + (size_t)r * cols4), v1 = __ldg(p + (size_t)(r + 8) * cols4);
-      const float4 v2 = __ldg(p + (size_t)(r + 16) * cols4), v3 = __ldg(p + (size_t)(r + 24) * cols4);
+      const float4 v0 = ld4_fmt(x, x_plane, (size_t)r * cols4 + c), v1 = ld4_fmt(x, x_plane, (size_t)(r + 8) * cols4 + c);
+      const float4 v2 = ld4_fmt(x, x_plane, (size_t)(r + 16) * cols4 + c), v3 = ld4_fmt(x, x_plane, (size_t)(r + 24) * cols4 + c);
       acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
       acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
       acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
       acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
     }
     for (; r < r1; r += 8) {
-      const float4 v = __ldg(p + (size_t)r * cols4);
+      const float4 v = ld4_fmt(x, x_plane, (size_t)r * cols4 + c);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
@@ -965,7 +965,7 @@ extern "C" int vbg_upsample_split_bwd(const float* d1, const float* d2, int B, i
   return check_launch("vbg_upsample_split_bwd");
 }
 
-static bool colsum_vec(const void* x, long long x_plane, int cols) { return x_plane == 0 && (cols & 3) == 0 && aligned16(x); }
+static bool colsum_vec(const void* x, long long x_plane, int cols) { return (cols & 3) == 0 && fmt_ok(x, x_plane); }
 static int colsum_geometry(long long rows, int cols, long long& rows_per_cta, bool vec = false) {
   const int col_tiles = vec ? cdiv(cols, 128) : cdiv(cols, 32);
   long long g = (kNumSMs * 8 + col_tiles - 1) / col_tiles;
@@ -990,8 +990,7 @@ extern "C" int vbg_colsum(const void* x, long long x_plane, long long rows, int 
   if (g > 1 && (!workspace || (size_t)g * cols * 4 > ws_bytes)) { g = 1; rpc = rows; }       // no workspace: one CTA row per column tile
   cudaStream_t s = as_stream(stream);
   if (vec)
-    colsum4_kernel<<<dim3(cdiv(cols, 128), g), 256, 0, s>>>(reinterpret_cast<const float4*>(x), rows, cols / 4, rpc,
-                                                            reinterpret_cast<float4*>(g > 1 ? workspace : out));
+    colsum4_kernel<<<dim3(cdiv(cols, 128), g), 256, 0, s>>>(x, x_plane, rows, cols / 4, rpc, reinterpret_cast<float4*>(g > 1 ? workspace : out));
   else
     colsum_kernel<<<dim3(cdiv(cols, 32), g), 256, 0, s>>>(x, x_plane, rows, cols, rpc, g > 1 ? workspace : out);
   if (g > 1) sum_slabs_kernel<<<grid_for(cols, 256), 256, 0, s>>>(workspace, g, cols, out);
