@@ -5,9 +5,19 @@ N B200s, one process per GPU, documents sharded across ranks (no data-path colle
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...      # CPU arm: the oracle restatement of the reference on host cores
+    python bench.py --impl reference ...      # CPU arm: the UNMODIFIED reference (staged under oracle/_ref) on the host cores
+    python bench.py --mode train ...          # the line's value is the training step (forward + backward + all-reduce + optimizers)
 
-Prints ONE JSON line on rank 0 (contract in the task statement / DESIGN.md section 6).
+Prints ONE JSON line on rank 0 (contract in the task statement / DESIGN.md section 6).  Objects of the line:
+  value / ms_per_step   eval-mode joint forward, inputs resident in HBM, CUDA events, max over ranks
+  e2e                   the same through DevicePrefetcher -> net() -> HostResultQueue from pinned host batches (H2D + D2H timed)
+  input_pipeline        e2e fed by the shard reader (ShardLoader: native collate, one uint8 H2D per step) + host-only collate rate
+  train_step            whole-step CUDA graph + arena all-reduce (N > 1) + fused SGD / AdamW
+  roofline              FFN-up GEMM: operands beyond L2 (primary), flush per launch, L2-warm; scatter / ROI-align in
+                        roofline_hbm_kernels (flush per launch + back to back)          -- DESIGN.md section 4
+  library_bar           reference eager on this GPU, cuBLAS, torchvision roi_align      (N = 1)
+  serving               inference() latency for one cfg1 document, host to host         (N = 1)
+  cpu_baseline          the unmodified reference on the host cores, bounded sample      (N = 1)
 """
 from __future__ import annotations
 
